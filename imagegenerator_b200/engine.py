@@ -1,0 +1,454 @@
+"""Host-side orchestration of the StackGAN train step on top of the C-ABI kernels.
+
+This file contains no arithmetic: every tensor operation is a call into ``ops`` (the ctypes
+binding of libsgb200.so, ``imagegenerator_b200.ops.CudaOps``).  Autograd is not used -- the
+backward passes, including the second-order path of the WGAN-GP gradient penalty
+(reference utils.py:8-26 differentiated by stage_1_train_fn.py:147), are written out by hand
+(DESIGN.md "Hand-derived backward").
+
+Layout: activations are NHWC in the storage type T of the ops object (bf16 or fp32);
+parameters/gradients/statistics are fp32 (sums in fp64).  The critic processes up to three
+*groups* of B images in one batched pass -- (real, fake, interpolated) -- each group with its own
+BatchNorm statistics, exactly like the reference's separate critic calls
+(stage_1_train_fn.py:125-138); the "mismatched text" call (:130) shares the real group's
+feature maps and differs only in the affine head.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from .layers import FlatParams
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+N_CRITIC = 5       # stage_1_train_fn.py:14
+LAMBDA_GP = 10.0   # stage_1_train_fn.py:15
+Z_DIM = 100        # stage_1_train_fn.py:16
+
+_DEFAULT_OPS = None
+
+
+def default_ops():
+    """The CUDA ops object.  Fails loudly when the extension or a GPU is missing: there is no
+    CPU fallback in this package."""
+    global _DEFAULT_OPS
+    if _DEFAULT_OPS is None:
+        from .ops import CudaOps
+        _DEFAULT_OPS = CudaOps()
+    return _DEFAULT_OPS
+
+
+def _conv_out(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+class _LayerRT:
+    """One conv operator (Conv2d orientation: ``co`` x ``ci`` x k x k weight) + optional BN."""
+
+    def __init__(self, ops, conv, bn):
+        self.conv, self.bn = conv, bn
+        w = conv.weight
+        self.co, self.ci, self.k = w.shape[0], w.shape[1], w.shape[2]
+        self.s, self.p = conv.stride, conv.pad
+        self.pf = ops.empty((self.co, self.k, self.k, self.ci))
+        self.pd = ops.empty((self.ci, self.k, self.k, self.co))
+
+    def pack(self, ops):
+        ops.pack_weight(self.conv.weight.data, self.pf, self.pd)
+
+
+# ============================================================================================ CA
+class CART:
+    """Conditioning augmentation runtime (reference con_augment.py:13-22)."""
+
+    def __init__(self, ops, module):
+        self.ops, self.m = ops, module
+        self.fp = None
+        self.st = None
+
+    def ensure(self, B):
+        ops, m = self.ops, self.m
+        if self.fp is None:
+            self.fp = FlatParams(m, ops.device, dtype=ops.f32)
+        if self.st is None or self.st.B != B:
+            f = ops.f32
+            self.st = SimpleNamespace(
+                B=B, h=ops.empty((B, m.h_dim), f), mu=ops.empty((B, m.c_dim), f), sigma=ops.empty((B, m.c_dim), f),
+                c_hat=ops.empty((B, m.c_dim), f), dmu=ops.empty((B, m.c_dim), f), dsigma=ops.empty((B, m.c_dim), f),
+                dh=ops.empty((B, m.h_dim), f), tem=None, eps=None)
+        return self.st
+
+    def forward(self, tem, eps, z, cg=None):
+        """tem [B,512] fp32; eps [B,128] or None (encode only); z [B,nz] or None; cg: optional
+        [B,1,1,128+nz] T buffer receiving [c_hat, z] (stage_1_train_fn.py:120-122)."""
+        ops, m = self.ops, self.m
+        st = self.ensure(tem.shape[0])
+        st.tem, st.eps = tem, eps
+        ops.linear_fwd(tem, m.h.weight.data, m.h.bias.data, st.h, relu=True)
+        ops.linear_fwd(st.h, m.mu.weight.data, m.mu.bias.data, st.mu)
+        ops.linear_fwd(st.h, m.sigma.weight.data, m.sigma.bias.data, st.sigma)
+        if eps is not None:
+            ops.ca_reparam(st.mu, st.sigma, eps, z, st.c_hat, cg)
+        return st
+
+    def backward(self, dcg, kl_scale, dtem, dtem_acc):
+        """Accumulates parameter grads; dtem (+)= d/d tem.  dcg: grad of the [c_hat, z] buffer
+        (T) or None; kl_scale multiplies d/d(mu,sigma) of sum(1+log s^2-mu^2-s^2)
+        (stage_1_train_fn.py:156-159)."""
+        ops, m, st = self.ops, self.m, self.st
+        ops.ca_bwd_seed(dcg, st.eps, st.mu, st.sigma, kl_scale, st.dmu, st.dsigma)
+        ops.linear_bwd(st.h, m.mu.weight.data, st.dmu, m.mu.weight.grad, m.mu.bias.grad, st.dh, dx_acc=False)
+        ops.linear_bwd(st.h, m.sigma.weight.data, st.dsigma, m.sigma.weight.grad, m.sigma.bias.grad, st.dh, dx_acc=True)
+        ops.linear_bwd(st.tem, m.h.weight.data, st.dh, m.h.weight.grad, m.h.bias.grad, dtem, dx_acc=dtem_acc,
+                       relu_out=st.h)
+
+
+# ============================================================================================ generator (Stage-I)
+class GenRT:
+    """Stage-I generator runtime (reference generator_1.py:38-40).  Every layer is a
+    ConvTranspose2d = the data-gradient direction of a Conv2d operator."""
+
+    def __init__(self, ops, module, B, out=None):
+        self.ops, self.m, self.B = ops, module, B
+        self.fp = FlatParams(module, ops.device, dtype=ops.f32)
+        self.layers = [_LayerRT(ops, c, bn) for c, bn in module.conv_layers()]
+        self.cg = ops.empty((B, 1, 1, self.layers[0].co))
+        self.dcg = ops.empty((B, 1, 1, self.layers[0].co))
+        h = 1
+        self.y, self.a, self.dy, self.da, self.mr, self.stats, self.sums = [], [], [], [], [], [], []
+        for L in self.layers:
+            h = (h - 1) * L.s - 2 * L.p + L.k
+            shp = (B, h, h, L.ci)
+            if L.bn is not None:
+                self.y.append(ops.empty(shp)); self.a.append(ops.empty(shp))
+                self.dy.append(ops.empty(shp)); self.da.append(ops.empty(shp))
+                self.mr.append(ops.empty((1, L.ci, 2), ops.f32))
+                self.stats.append(ops.zeros((1, L.ci, 2), ops.f64))
+                self.sums.append(ops.zeros((1, L.ci, 2), ops.f64))
+            else:
+                self.out = out if out is not None else ops.empty(shp)
+                self.dpre = ops.empty(shp)
+        self.packed = False
+
+    def refresh_weights(self):
+        for L in self.layers:
+            L.pack(self.ops)
+        self.packed = True
+
+    def set_input(self, x):
+        """x [B, c_dim+z_dim] fp32 -> cg buffer (module-level API only; the engine writes cg directly)."""
+        self.ops.nchw_to_nhwc(x.reshape(self.B, -1, 1, 1).contiguous().float(), self.cg)
+
+    def forward(self, training=True):
+        ops = self.ops
+        x = self.cg
+        for i, L in enumerate(self.layers):
+            if L.bn is None:
+                ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
+                break
+            ops.conv_dgrad(x, L.pd, None, self.y[i], L.k, L.s, L.p)
+            bn = L.bn
+            if training:
+                ops.zero(self.stats[i])
+                ops.col_stats(self.y[i], self.stats[i], 1)
+                n = self.y[i].numel() // L.ci
+                ops.bn_finalize(self.stats[i], n, self.mr[i], bn.running_mean, bn.running_var,
+                                bn.num_batches_tracked, 1, True)
+            else:
+                ops.bn_eval_mr(bn.running_mean, bn.running_var, self.mr[i])
+            ops.bn_act(self.y[i], self.mr[i], bn.weight.data, bn.bias.data, self.a[i], 1, ACT_RELU)
+            x = self.a[i]
+        return self.out
+
+    def backward(self, dout):
+        """dout: d loss / d out (T, NHWC).  Accumulates parameter grads, leaves d/d cg in self.dcg."""
+        ops = self.ops
+        last = self.layers[-1]
+        ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
+        ops.colsum(self.dpre, last.conv.bias.grad)
+        ops.conv_wgrad(self.dpre, self.a[-1], last.conv.weight.grad, last.k, last.s, last.p)
+        ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
+        for i in range(len(self.layers) - 2, -1, -1):
+            L, bn = self.layers[i], self.layers[i].bn
+            ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU)
+            ops.bn_bwd_apply(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i],
+                             self.dy[i], 1, ACT_RELU)
+            ops.bn_param_grad(self.sums[i], bn.weight.grad, bn.bias.grad)
+            x_in = self.a[i - 1] if i > 0 else self.cg
+            ops.conv_wgrad(self.dy[i], x_in, L.conv.weight.grad, L.k, L.s, L.p)
+            ops.conv_fprop(self.dy[i], L.pf, None, self.da[i - 1] if i > 0 else self.dcg, L.k, L.s, L.p)
+        return self.dcg
+
+
+# ============================================================================================ critic
+class CriticRT:
+    """Critic runtime for both stages (reference discrminator_1.py:41-52 / discriminator_2.py:27-38)."""
+
+    NG = 3   # groups: 0 real, 1 fake, 2 interpolated
+
+    def __init__(self, ops, module, B):
+        self.ops, self.m, self.B = ops, module, B
+        self.fp = FlatParams(module, ops.device, dtype=ops.f32)
+        self.layers = [_LayerRT(ops, c, bn) for c, bn in module.conv_layers()]
+        G, f32, f64 = self.NG, ops.f32, ops.f64
+        h = module.in_hw
+        self.a = [ops.empty((G * B, h, h, 3))]
+        self.y, self.dy, self.da = [None], [], [None]
+        self.mr, self.stats, self.sums = [None], [None], [None]
+        # gradient-penalty chain buffers (one group)
+        self.gda, self.gdy, self.gsums, self.tsums, self.v, self.w, self.gy = [None], [], [None], [None], [], [None], [None]
+        for l, L in enumerate(self.layers):
+            h = _conv_out(h, L.k, L.s, L.p)
+            shp, shp1 = (G * B, h, h, L.co), (B, h, h, L.co)
+            self.a.append(ops.empty(shp))
+            self.da.append(ops.empty(shp))
+            self.dy.append(ops.empty(shp))
+            self.gda.append(ops.empty(shp1))
+            self.gdy.append(ops.empty(shp1))
+            self.v.append(ops.empty(shp1))
+            self.w.append(ops.empty(shp1))
+            if l > 0:
+                self.y.append(ops.empty(shp))
+                self.mr.append(ops.empty((G, L.co, 2), f32))
+                self.stats.append(ops.zeros((G, L.co, 2), f64))
+                self.sums.append(ops.zeros((G, L.co, 2), f64))
+                self.gsums.append(ops.zeros((1, L.co, 2), f64))
+                self.tsums.append(ops.zeros((L.co, 3), f64))
+                self.gy.append(ops.empty(shp1))
+        assert h == 4, h
+        self.nl = len(self.layers)
+        cl, Nd = self.layers[-1].co, module.Nd
+        self.A, self.dA = ops.empty((16, cl), f32), ops.zeros((16, cl), f32)
+        self.Bv, self.dBv = ops.empty((Nd,), f32), ops.zeros((Nd,), f32)
+        self.c0, self.dc0 = ops.empty((1,), f32), ops.zeros((1,), f32)
+        self.tem_all = ops.empty((2 * B, module.tem_size), f32)     # rows [0,B) tem, [B,2B) mismatched
+        self.ce = ops.empty((2 * B, Nd), f32)
+        self.dce = ops.empty((2 * B, Nd), f32)
+        self.score = ops.empty((4, B), f32)                          # real, mismatched, fake, interpolated
+        self.g = ops.empty((B, module.in_hw, module.in_hw, 3))       # d score_interp / d interp
+        self.v0 = ops.empty((B, module.in_hw, module.in_hw, 3))
+        self.dx = ops.empty((G * B, module.in_hw, module.in_hw, 3))  # d loss / d images (when requested)
+        self.sq = ops.empty((B,), f32)
+        self.dtem = ops.zeros((B, module.tem_size), f32)
+        # per-sample head coefficients (d loss / d score)
+        cc = torch.zeros(G * B, dtype=f32)
+        cc[:B] = -1.0 / (2 * B)      # real (-1/B) and mismatched (+1/2B) share features
+        cc[B:2 * B] = 1.0 / (2 * B)  # fake
+        self.coef_critic = cc.to(ops.device)
+        ct = torch.zeros(2 * B, dtype=f32)
+        ct[:B] = -1.0 / (2 * B)      # text rows: real(-1/B)+fake(+1/2B) use tem; mismatched rows +1/2B
+        ct[B:] = 1.0 / (2 * B)
+        self.coef_text = ct.to(ops.device)
+        self.coef_one = torch.ones(B, dtype=f32).to(ops.device)
+        self.coef_gen = torch.full((B,), -1.0 / B, dtype=f32).to(ops.device)
+
+    # ---------------------------------------------------------------- helpers
+    def group_view(self, t, g0, ng):
+        B = self.B
+        return t[g0 * B:(g0 + ng) * B]
+
+    def refresh_weights(self):
+        ops, m = self.ops, self.m
+        for L in self.layers:
+            L.pack(ops)
+        ops.head_prepare(m.channel_resize.weight.data, m.channel_resize.bias.data, m.critic_score.weight.data,
+                         m.critic_score.bias.data, self.A, self.Bv, self.c0)
+
+    def set_text(self, tem, tem_mis):
+        self.tem_all[:self.B].copy_(tem)
+        if tem_mis is not None:
+            self.tem_all[self.B:].copy_(tem_mis)
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False):
+        """Trunk + head on groups [g0, g0+ng).  BN running statistics are updated once per group,
+        group g0 ``dup_first`` times (the mismatched-text call sees the real images again)."""
+        ops, m, B = self.ops, self.m, self.B
+        gv = lambda t: self.group_view(t, g0, ng)
+        L0 = self.layers[0]
+        ops.conv_fprop(gv(self.a[0]), L0.pf, L0.conv.bias.data, gv(self.a[1]), L0.k, L0.s, L0.p, act=ACT_LRELU)
+        for l in range(1, self.nl):
+            L, bn = self.layers[l], self.layers[l].bn
+            y = gv(self.y[l])
+            ops.conv_fprop(gv(self.a[l]), L.pf, None, y, L.k, L.s, L.p)
+            mr = self.mr[l][g0:g0 + ng]
+            if training:
+                st = self.stats[l][g0:g0 + ng]
+                ops.zero(st)
+                ops.col_stats(y, st, ng)
+                ops.bn_finalize(st, y.numel() // (ng * L.co), mr, bn.running_mean, bn.running_var,
+                                bn.num_batches_tracked, dup_first, True)
+            else:
+                for g in range(ng):
+                    ops.bn_eval_mr(bn.running_mean, bn.running_var, mr[g:g + 1])
+            ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)
+        # head: compressed text, then the collapsed affine score
+        nt = 2 * B if with_mismatched else B
+        ops.linear_fwd(self.tem_all[:nt], m.compress.weight.data, m.compress.bias.data, self.ce[:nt])
+        a4 = self.a[self.nl]
+        for g in range(g0, g0 + ng):
+            row = {0: 0, 1: 2, 2: 3}[g]
+            ops.head_fwd(self.group_view(a4, g, 1), self.ce[:B], self.A, self.Bv, self.c0, self.score[row])
+        if with_mismatched:
+            ops.head_fwd(self.group_view(a4, 0, 1), self.ce[B:], self.A, self.Bv, self.c0, self.score[1])
+
+    # ---------------------------------------------------------------- first-order backward
+    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad):
+        """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
+        d loss / d y_l on the interpolated group from the gradient-penalty second-order pass)."""
+        ops, nl = self.ops, self.nl
+        gv = lambda t: self.group_view(t, g0, ng)
+        a4 = gv(self.a[nl])
+        ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
+        if param_grads:
+            ops.head_bwd_reduce(coef, a4, self.dA)
+        for l in range(nl - 1, 0, -1):
+            L, bn = self.layers[l], self.layers[l].bn
+            mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
+            da, a_out, y, dy = gv(self.da[l + 1]), gv(self.a[l + 1]), gv(self.y[l]), gv(self.dy[l])
+            ops.bn_bwd_reduce(da, a_out, y, mr, sums, ng, ACT_LRELU)
+            ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
+                             inject=self.gy[l] if inject else None, inject_group=2 - g0)
+            if param_grads:
+                ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
+                ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p)
+            ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
+        L0 = self.layers[0]
+        dy0 = gv(self.dy[0])
+        ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU)
+        if param_grads:
+            ops.conv_wgrad(gv(self.a[0]), dy0, L0.conv.weight.grad, L0.k, L0.s, L0.p)
+            ops.colsum(dy0, L0.conv.bias.grad)
+        if need_input_grad:
+            ops.conv_dgrad(dy0, L0.pd, None, gv(self.dx), L0.k, L0.s, L0.p)
+
+    def text_backward(self, coef_text, nt, dc0, param_grads, dtem):
+        """Head/text parameter grads for d loss/d score coefficients; dtem (=) d/d tem rows [0,B)."""
+        ops, m, B = self.ops, self.m, self.B
+        ops.head_bwd_data(coef_text[:nt], self.Bv, self.dce[:nt])            # dce = coef (x) Bv
+        if param_grads:
+            ops.head_bwd_reduce(coef_text[:nt], self.ce[:nt], self.dBv)
+            ops.fill(self.dc0, dc0)
+            ops.linear_bwd(self.tem_all[:nt], m.compress.weight.data, self.dce[:nt], m.compress.weight.grad,
+                           m.compress.bias.grad, None, dx_acc=False)
+            ops.head_param_grads(self.dA, self.dBv, self.dc0, m.channel_resize.weight.data,
+                                 m.channel_resize.bias.data, m.critic_score.weight.data,
+                                 m.channel_resize.weight.grad, m.channel_resize.bias.grad,
+                                 m.critic_score.weight.grad, m.critic_score.bias.grad)
+        if dtem is not None:
+            ops.linear_bwd(self.tem_all[:B], m.compress.weight.data, self.dce[:B], None, None, dtem, dx_acc=False)
+
+    # ---------------------------------------------------------------- gradient penalty
+    def gp_first_order(self):
+        """g = d sum_b score_interp[b] / d interp through train-mode BN (utils.py:15-21)."""
+        ops, nl = self.ops, self.nl
+        i2 = lambda t: self.group_view(t, 2, 1)
+        ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
+        for l in range(nl - 1, 0, -1):
+            L, bn = self.layers[l], self.layers[l].bn
+            mr = self.mr[l][2:3]
+            ops.bn_bwd_reduce(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.gsums[l], 1, ACT_LRELU)
+            ops.bn_bwd_apply(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
+                             self.gdy[l], 1, ACT_LRELU)
+            ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
+        L0 = self.layers[0]
+        ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
+        ops.conv_dgrad(self.gdy[0], L0.pd, None, self.g, L0.k, L0.s, L0.p)
+        ops.sample_sqnorm(self.g, self.sq)
+
+    def gp_second_order(self, coef):
+        """Backward of coef/2 * sum_b (||g_b||-1)^2 through the first-order graph: parameter grads
+        via wgrad / gamma / head, and gy[l] = d/d y_l for the plain backward to pick up."""
+        ops, nl = self.ops, self.nl
+        i2 = lambda t: self.group_view(t, 2, 1)
+        ops.gp_seed(self.g, self.sq, coef, self.v0)
+        L0 = self.layers[0]
+        ops.conv_fprop(self.v0, L0.pf, None, self.v[0], L0.k, L0.s, L0.p)
+        ops.conv_wgrad(self.v0, self.gdy[0], L0.conv.weight.grad, L0.k, L0.s, L0.p)
+        ops.act_bwd(self.v[0], i2(self.a[1]), self.w[1], ACT_LRELU)
+        for l in range(1, nl):
+            L, bn = self.layers[l], self.layers[l].bn
+            ops.conv_fprop(self.w[l], L.pf, None, self.v[l], L.k, L.s, L.p)
+            ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p)
+            mr = self.mr[l][2:3]
+            ops.gp_bn_reduce(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.tsums[l], ACT_LRELU)
+            ops.gp_bn_apply(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
+                            self.gsums[l], self.tsums[l], self.w[l + 1], self.gy[l], bn.weight.grad, ACT_LRELU)
+        ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA)
+
+
+# ============================================================================================ Stage-I engine
+class Stage1Engine:
+    """One reference outer step (stage_1_train_fn.py:116-172): five critic updates + one
+    generator/CA update, with all noise supplied by the caller."""
+
+    def __init__(self, ca, critic, gen, batch_size, ops=None, lr=1e-3, world_size=1, allreduce=None):
+        ops = ops or default_ops()
+        self.ops, self.B = ops, batch_size
+        self.ca_m, self.d_m, self.g_m = ca, critic, gen
+        self.d = CriticRT(ops, critic, batch_size)
+        self.ca = CART(ops, ca)
+        self.ca.ensure(batch_size)
+        # the generator writes its tanh output straight into the critic's "fake" group
+        self.g = GenRT(ops, gen, batch_size, out=self.d.group_view(self.d.a[0], 1, 1))
+        for fp in (self.d.fp, self.g.fp, self.ca.fp):
+            fp.set_lr(lr)
+        self.losses = ops.zeros((4,), ops.f32)       # [loss_critic, gp, lossG, kl]
+        self.allreduce = allreduce                   # callable(flat_grad) or None
+        self.world = world_size
+        self.real_nchw = None
+        self.refresh_all()
+
+    def refresh_all(self):
+        self.d.refresh_weights()
+        self.g.refresh_weights()
+
+    def optimizer_step(self, fp):
+        if self.allreduce is not None:
+            self.allreduce(fp.grad)                  # mean over replicas (xm.optimizer_step semantics)
+        self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
+
+    # -- inputs
+    def load_batch(self, real_nchw, tem, tem_mis):
+        d = self.d
+        self.ops.nchw_to_nhwc(real_nchw, d.group_view(d.a[0], 0, 1))
+        d.set_text(tem, tem_mis)
+
+    def critic_iteration(self, z, eps_ca, eps_gp):
+        ops, d, B = self.ops, self.d, self.B
+        tem = d.tem_all[:B]
+        self.ca.forward(tem, eps_ca, z, cg=self.g.cg)           # stage_1_train_fn.py:120-122
+        self.g.forward(training=True)                            # :123 -> critic group 1
+        X = d.a[0]
+        ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
+        d.forward(0, 3, dup_first=2, training=True, with_mismatched=True)    # :125-132 + utils.py:13
+        ops.zero(d.fp.grad)                                      # :146
+        ops.zero(d.dA); ops.zero(d.dBv)
+        d.gp_first_order()                                       # utils.py:15-24
+        ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])   # :140-144
+        d.gp_second_order(2.0 * LAMBDA_GP / B)
+        d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False)    # :147
+        d.text_backward(d.coef_text, 2 * B, 0.0, True, None)
+        self.optimizer_step(d.fp)                                # :149
+        d.refresh_weights()
+
+    def generator_step(self):
+        ops, d, B = self.ops, self.d, self.B
+        d.forward(1, 1, dup_first=1, training=True)              # :154 (updated critic, last fake)
+        st = self.ca.st
+        ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])          # :155-159
+        ops.zero(self.g.fp.grad); ops.zero(self.ca.fp.grad)      # :161-164
+        d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
+        d.text_backward(d.coef_gen, B, -1.0, False, d.dtem)      # d lossG/d tem through the critic head
+        self.g.backward(d.group_view(d.dx, 1, 1))
+        self.ca.backward(self.g.dcg, 1.0, d.dtem, True)
+        self.optimizer_step(self.g.fp)                           # :166
+        self.optimizer_step(self.ca.fp)                          # :172
+        self.g.refresh_weights()
+
+    def outer_step(self, z, eps_ca, eps_gp):
+        """z [5,B,100], eps_ca [5,B,128], eps_gp [5,B] (fp32, device)."""
+        for it in range(N_CRITIC):
+            self.critic_iteration(z[it], eps_ca[it], eps_gp[it])
+        self.generator_step()

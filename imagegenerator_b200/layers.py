@@ -1,0 +1,111 @@
+"""Parameter containers that reproduce the reference modules' ``state_dict`` layout and default
+initialisation without using torch.nn compute layers.
+
+The reference builds its networks from ``nn.Linear`` / ``nn.Conv2d`` / ``nn.ConvTranspose2d`` /
+``nn.BatchNorm2d`` (e.g. generator_1.py:9-36, discrminator_1.py:9-39) and never overrides their
+initialisation, so checkpoints interchange iff the key names, shapes and (for seeded construction)
+the order of RNG draws agree.  The holders below only own tensors; all
+arithmetic is done by the CUDA kernels behind ``imagegenerator_b200.ops``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+
+def _default_init_(weight, bias, fan_in):
+    # what torch's Linear/_ConvNd.reset_parameters do: kaiming_uniform(a=sqrt(5)) then U(+-1/sqrt(fan_in))
+    nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+    if bias is not None:
+        bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+        nn.init.uniform_(bias, -bound, bound)
+
+
+class DenseParams(nn.Module):
+    """weight [out, in] (+ bias [out])  -- state_dict twin of nn.Linear."""
+
+    def __init__(self, n_in, n_out):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n_out, n_in))
+        self.bias = nn.Parameter(torch.empty(n_out))
+        _default_init_(self.weight, self.bias, n_in)
+
+
+class ConvParams(nn.Module):
+    """Conv2d-layout weight [Cout, Cin, k, k]; ``transposed`` stores ConvTranspose2d's [Cin, Cout, k, k].
+
+    In both cases dim 0 is what this package calls the layer's *wide* side ``co`` and dim 1 its
+    *narrow* side ``ci`` of the underlying Conv2d operator (a ConvTranspose2d is that operator's
+    data-gradient), so one set of kernels serves both ("one operator, two directions")."""
+
+    def __init__(self, c_in, c_out, k, stride, pad, bias=False, transposed=False):
+        super().__init__()
+        self.c_in, self.c_out, self.k, self.stride, self.pad, self.transposed = c_in, c_out, k, stride, pad, transposed
+        shape = (c_in, c_out, k, k) if transposed else (c_out, c_in, k, k)
+        self.weight = nn.Parameter(torch.empty(shape))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(c_out))
+        else:
+            self.register_parameter("bias", None)
+        _default_init_(self.weight, self.bias, shape[1] * k * k)   # torch: fan_in = size(1) * receptive field
+
+
+class BNParams(nn.Module):
+    """state_dict twin of nn.BatchNorm2d (eps 1e-5, momentum 0.1)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class Slot(nn.Module):
+    """Parameter-less placeholder keeping nn.Sequential indices equal to the reference's
+    (activation modules occupy an index there)."""
+
+
+def block(conv, c_bn):
+    """(conv, bn, activation-slot) triple -> keys '<i>.0.weight', '<i>.1.*' like the reference's
+    upsampling_block / downsampling_block helpers."""
+    return nn.Sequential(conv, BNParams(c_bn), Slot())
+
+
+class FlatParams:
+    """All trainable parameters of a module re-pointed into ONE contiguous fp32 buffer, with a
+    matching flat gradient buffer and Adam moments: one fused Adam launch and one all-reduce per
+    optimizer, and ``module.state_dict()`` keeps working because the Parameters are views."""
+
+    def __init__(self, module, device, opt_hyper=None, dtype=torch.float32):
+        ps = [p for p in module.parameters()]
+        self.params = ps
+        n = sum(p.numel() for p in ps)
+        # pad to a multiple of 4 floats so the vectorised Adam kernel needs no tail
+        self.n = n
+        npad = (n + 3) // 4 * 4
+        self.flat = torch.zeros(npad, dtype=dtype, device=device)
+        self.grad = torch.zeros(npad, dtype=dtype, device=device)
+        self.m = torch.zeros(npad, dtype=dtype, device=device)
+        self.v = torch.zeros(npad, dtype=dtype, device=device)
+        off = 0
+        self.views = {}
+        for p in ps:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1).to(device=device, dtype=dtype))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+        lr, b1, b2, eps = opt_hyper or (1e-3, 0.9, 0.999, 1e-8)
+        # [lr, beta1, beta2, eps, step]: lives on the device so a captured CUDA graph sees updates
+        self.hyper = torch.tensor([lr, b1, b2, eps, 0.0], dtype=dtype, device=device)
+        for mod in module.modules():               # buffers follow to the device
+            for name, buf in list(mod._buffers.items()):
+                if buf is not None:
+                    mod._buffers[name] = buf.to(device=device, dtype=dtype if buf.is_floating_point() else buf.dtype)
+
+    def set_lr(self, lr):
+        self.hyper[0] = lr

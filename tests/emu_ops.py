@@ -1,0 +1,344 @@
+"""Torch-CPU statement of what every C-ABI kernel computes -- TEST DOUBLE, lives in tests/ only.
+
+Same method names/arguments as ``imagegenerator_b200.ops.CudaOps``.  Two uses:
+  * host-logic tests: run the engine (imagegenerator_b200/engine.py) on CPU in fp64 and
+    compare a whole train step with the oracle (no GPU needed);
+  * kernel tests (-m gpu): each CUDA kernel is compared against the method of the
+    same name here on random inputs.
+The product package never imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+SLOPE = 0.1
+
+
+def _act(x, act):
+    if act == ACT_RELU:
+        return F.relu(x)
+    if act == ACT_LRELU:
+        return F.leaky_relu(x, SLOPE)
+    if act == ACT_TANH:
+        return torch.tanh(x)
+    return x
+
+
+def _mask(a_out, act):
+    """d act / d pre-activation, from the stored activation OUTPUT."""
+    if act == ACT_RELU:
+        return (a_out > 0).to(a_out.dtype)
+    if act == ACT_LRELU:
+        return torch.where(a_out > 0, torch.ones_like(a_out), torch.full_like(a_out, SLOPE))
+    if act == ACT_TANH:
+        return 1 - a_out * a_out
+    return torch.ones_like(a_out)
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1)
+
+
+class EmuOps:
+    is_emulator = True
+
+    def __init__(self, dtype=torch.float64, device="cpu"):
+        self.act_dtype = dtype          # storage type of activations ("T")
+        self.device = torch.device(device)
+        self.launches = 0
+
+    # ---- allocation helpers the engine uses
+    def empty(self, shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        return torch.zeros(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    @property
+    def f32(self):
+        # "fp32" side tensors (params, grads, stats outputs) follow the emulation precision
+        return torch.float64 if self.act_dtype == torch.float64 else torch.float32
+
+    @property
+    def f64(self):
+        return torch.float64
+
+    # ---- layout
+    def nchw_to_nhwc(self, src, dst):
+        dst.copy_(nhwc(src).to(dst.dtype))
+
+    def nhwc_to_nchw(self, src, dst):
+        dst.copy_(nchw(src).to(dst.dtype))
+
+    def pack_weight(self, w, pf, pd):
+        """w [Co,Ci,kh,kw] fp32 -> pf [Co,kh,kw,Ci], pd [Ci,kh,kw,Co] in T."""
+        if pf is not None:
+            pf.copy_(w.permute(0, 2, 3, 1).to(pf.dtype))
+        if pd is not None:
+            pd.copy_(w.permute(1, 2, 3, 0).to(pd.dtype))
+
+    # ---- convolutions (Conv2d-layout semantics; ConvTranspose2d layers use them mirrored)
+    def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE):
+        w = pf.permute(0, 3, 1, 2).to(x.dtype)                      # [Co,Ci,kh,kw]
+        out = F.conv2d(nchw(x), w, None if bias is None else bias.to(x.dtype), s, p)
+        y.copy_(nhwc(_act(out, act)).to(y.dtype))
+
+    def conv_dgrad(self, dy, pd, bias, dx, k, s, p, act=ACT_NONE):
+        w = pd.permute(3, 0, 1, 2).to(dy.dtype)                     # [Co,Ci,kh,kw] (= convT weight [in,out,kh,kw])
+        out = F.conv_transpose2d(nchw(dy), w, None if bias is None else bias.to(dy.dtype), s, p)
+        assert out.shape[2] == dx.shape[1], (out.shape, dx.shape)
+        dx.copy_(nhwc(_act(out, act)).to(dx.dtype))
+
+    def conv_wgrad(self, x, dy, dw, k, s, p):
+        """dw[Co,Ci,kh,kw] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]."""
+        g = torch.nn.grad.conv2d_weight(nchw(x).to(dw.dtype), dw.shape, nchw(dy).to(dw.dtype), stride=s, padding=p)
+        dw.add_(g)
+
+    def colsum(self, x, out):
+        """out[C] (fp32) += sum over all leading dims of x[..., C]."""
+        out.add_(x.reshape(-1, x.shape[-1]).to(out.dtype).sum(0))
+
+    # ---- batch norm
+    def col_stats(self, y, stats, groups):
+        """stats[G,C,2] (f64) += (sum, sum of squares) per group; rows split evenly into groups."""
+        C = y.shape[-1]
+        v = y.reshape(groups, -1, C).to(torch.float64)
+        stats[:, :, 0] += v.sum(1)
+        stats[:, :, 1] += (v * v).sum(1)
+
+    def bn_finalize(self, stats, count, mr, running_mean, running_var, nbt, dup_first, update_running=True,
+                    momentum=0.1, eps=1e-5):
+        """mr[G,C,2] = (mean, rstd) from biased variance; running stats EMA-updated once per group
+        in group order, group 0 ``dup_first`` times (real + mismatched share statistics)."""
+        mean = stats[:, :, 0] / count
+        var = (stats[:, :, 1] / count - mean * mean).clamp_min(0)
+        mr[:, :, 0] = mean.to(mr.dtype)
+        mr[:, :, 1] = (1.0 / torch.sqrt(var + eps)).to(mr.dtype)
+        if update_running:
+            G = stats.shape[0]
+            order = [0] * dup_first + list(range(1, G))
+            for g in order:
+                running_mean.mul_(1 - momentum).add_(momentum * mean[g].to(running_mean.dtype))
+                running_var.mul_(1 - momentum).add_(momentum * (var[g] * count / max(count - 1, 1)).to(running_var.dtype))
+            nbt += len(order)
+
+    def bn_eval_mr(self, running_mean, running_var, mr, eps=1e-5):
+        mr[0, :, 0] = running_mean.to(mr.dtype)
+        mr[0, :, 1] = (1.0 / torch.sqrt(running_var.to(torch.float64) + eps)).to(mr.dtype)
+
+    def _xhat(self, y, mr, groups):
+        C = y.shape[-1]
+        v = y.reshape(groups, -1, C).to(mr.dtype)
+        return (v - mr[:, None, :, 0]) * mr[:, None, :, 1]
+
+    def bn_act(self, y, mr, gamma, beta, out, groups, act, residual=None):
+        xh = self._xhat(y, mr, groups)
+        z = xh * gamma.to(mr.dtype) + beta.to(mr.dtype)
+        z = z.reshape(y.shape)
+        if residual is not None:
+            z = z + residual.to(z.dtype)
+        out.copy_(_act(z, act).to(out.dtype))
+
+    def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act):
+        """sums[G,C,2] (f64) = (S1, S2) = (sum dz, sum dz*xhat), dz = da * act'(.) from a_out."""
+        C = y.shape[-1]
+        dz = (da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).reshape(groups, -1, C)
+        xh = self._xhat(y, mr, groups).to(torch.float64)
+        sums[:, :, 0] = dz.sum(1)
+        sums[:, :, 1] = (dz * xh).sum(1)
+
+    def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0):
+        """dy = gamma*rstd/N * (N dz - S1 - xhat S2)  [+ inject on rows of group inject_group]."""
+        C = y.shape[-1]
+        ft = mr.dtype
+        dz = (da.to(ft) * _mask(a_out, act).to(ft)).reshape(groups, -1, C)
+        n = dz.shape[1]
+        xh = self._xhat(y, mr, groups)
+        a = gamma.to(ft)[None, None, :] * mr[:, None, :, 1] / n
+        out = a * (n * dz - sums[:, None, :, 0].to(ft) - xh * sums[:, None, :, 1].to(ft))
+        if inject is not None:
+            out[inject_group] += inject.reshape(-1, C).to(ft)
+        dy.copy_(out.reshape(dy.shape).to(dy.dtype))
+
+    def bn_param_grad(self, sums, dgamma, dbeta):
+        dgamma.add_(sums[:, :, 1].sum(0).to(dgamma.dtype))
+        dbeta.add_(sums[:, :, 0].sum(0).to(dbeta.dtype))
+
+    def act_bwd(self, da, a_out, out, act):
+        out.copy_((da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).to(out.dtype))
+
+    # ---- gradient-penalty second order through a train-mode BN (one group)
+    def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act):
+        """tsums[C,3] (f64) = (sum v, sum v*xhat, sum v*dz)."""
+        C = y.shape[-1]
+        vv = v.reshape(-1, C).to(torch.float64)
+        dz = (da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).reshape(-1, C)
+        xh = self._xhat(y, mr, 1)[0].to(torch.float64)
+        tsums[:, 0] = vv.sum(0)
+        tsums[:, 1] = (vv * xh).sum(0)
+        tsums[:, 2] = (vv * dz).sum(0)
+
+    def gp_bn_apply(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act):
+        """Backward of dy = BNbwd(dz; y, gamma) given v = dL/d dy  (SURVEY section 7):
+             w_out  = mask * a (N v - T1 - xhat T2)                      (dL/d da: feeds the next conv_fprop)
+             gy_out = r (G - sum G/N - xhat sum(G xhat)/N) - P r xhat/N   (dL/d y: injected into the plain backward)
+             dgamma += P / gamma,  P = sum v*dy = a (N T3 - S1 T1 - S2 T2),  G = -a (v S2 + dz T2)."""
+        C = y.shape[-1]
+        ft = torch.float64
+        vv = v.reshape(-1, C).to(ft)
+        m = _mask(a_out, act).reshape(-1, C).to(ft)
+        dz = da.reshape(-1, C).to(ft) * m
+        n = vv.shape[0]
+        r = mr[0, :, 1].to(ft)
+        xh = self._xhat(y, mr, 1)[0].to(ft)
+        g = gamma.to(ft)
+        a = g * r / n
+        S1, S2 = sums[0, :, 0].to(ft), sums[0, :, 1].to(ft)
+        T1, T2, T3 = tsums[:, 0].to(ft), tsums[:, 1].to(ft), tsums[:, 2].to(ft)
+        u = a * (n * vv - T1 - xh * T2)
+        w_out.copy_((u * m).reshape(w_out.shape).to(w_out.dtype))
+        P = a * (n * T3 - S1 * T1 - S2 * T2)
+        G = -a * (vv * S2 + dz * T2)
+        sG = -a * (S2 * T1 + S1 * T2)
+        sGx = -2 * a * S2 * T2
+        gy = r * (G - sG / n - xh * sGx / n) - P * r * xh / n
+        gy_out.copy_(gy.reshape(gy_out.shape).to(gy_out.dtype))
+        dgamma.add_((r / n * (n * T3 - S1 * T1 - S2 * T2)).to(dgamma.dtype))
+
+    # ---- small dense layers (fp32)
+    def linear_fwd(self, x, w, b, out, relu=False):
+        o = F.linear(x, w, b)
+        out.copy_(F.relu(o) if relu else o)
+
+    def linear_bwd(self, x, w, dout, dw, db, dx, dx_acc=False, relu_out=None):
+        """dw += dout^T x ; db += sum dout ; dx (may be None) (+)= dout w.  If relu_out is given,
+        dout is first masked by relu_out > 0."""
+        if relu_out is not None:
+            dout = dout * (relu_out > 0).to(dout.dtype)
+        if dw is not None:
+            dw.add_(dout.t() @ x)
+        if db is not None:
+            db.add_(dout.sum(0))
+        if dx is not None:
+            if dx_acc:
+                dx.add_(dout @ w)
+            else:
+                dx.copy_(dout @ w)
+
+    # ---- critic head (text replicate + concat + 1x1 conv + linear collapse into A, Bv, c0)
+    def head_prepare(self, wcr, bcr, wcs, bcs, A, Bv, c0):
+        """score = <A, a4> + <Bv, ce> + c0 with A[hw,c] = sum_k wcs[k,hw] wcr[k,c] (c < 512),
+        Bv[j] = sum_k (sum_hw wcs[k,hw]) wcr[k,512+j], c0 = sum_k bcr[k] sum_hw wcs[k,hw] + bcs."""
+        K = wcr.shape[0]
+        ws = wcs.reshape(K, 16)
+        wr = wcr.reshape(K, -1)
+        nx = A.shape[1]
+        A.copy_(ws.t() @ wr[:, :nx])
+        sw = ws.sum(1)
+        Bv.copy_(sw @ wr[:, nx:])
+        c0.copy_((bcr * sw).sum().reshape(1) + bcs)
+
+    def head_fwd(self, a4, ce, A, Bv, c0, score):
+        n = a4.shape[0]
+        s = (a4.reshape(n, -1).to(A.dtype) * A.reshape(1, -1)).sum(1) + ce @ Bv + c0
+        score.copy_(s)
+
+    def head_bwd_data(self, coef, A, da4):
+        """da4[n] = coef[n] * A."""
+        da4.copy_((coef[:, None, None] * A[None]).reshape(da4.shape).to(da4.dtype))
+
+    def head_bwd_reduce(self, coef, a4, dA):
+        """dA[hw,c] += sum_n coef[n] a4[n,hw,c]."""
+        n = a4.shape[0]
+        dA.add_((coef[:, None].to(dA.dtype) * a4.reshape(n, -1).to(dA.dtype)).sum(0).reshape(dA.shape))
+
+    def head_param_grads(self, dA, dBv, dc0, wcr, bcr, wcs, dwcr, dbcr, dwcs, dbcs):
+        K = wcr.shape[0]
+        ws = wcs.reshape(K, 16)
+        wr = wcr.reshape(K, -1)
+        nx = dA.shape[1]
+        sw = ws.sum(1)
+        g = torch.zeros_like(wr)
+        g[:, :nx] = ws @ dA
+        g[:, nx:] = sw[:, None] * dBv[None, :]
+        dwcr.add_(g.reshape(dwcr.shape))
+        dbcr.add_(sw * dc0)
+        gs = wr[:, :nx] @ dA.t() + (wr[:, nx:] @ dBv)[:, None] + (bcr * dc0)[:, None]
+        dwcs.add_(gs.reshape(dwcs.shape))
+        dbcs.add_(dc0)
+
+    # ---- conditioning augmentation pieces
+    def ca_reparam(self, mu, sigma, eps, z, c_hat, cg):
+        """c_hat = mu + sigma*eps (fp32); cg[N,1,1,128+nz] (T) = [c_hat, z] when cg is given."""
+        c = mu + sigma * eps
+        c_hat.copy_(c)
+        if cg is not None:
+            n = c.shape[0]
+            cg.reshape(n, -1)[:, :c.shape[1]] = c.to(cg.dtype)
+            if z is not None:
+                cg.reshape(n, -1)[:, c.shape[1]:] = z.to(cg.dtype)
+
+    def ca_bwd_seed(self, dcg, eps, mu, sigma, kl_scale, dmu, dsigma):
+        """dmu = dc + kl_scale*(-2 mu); dsigma = dc*eps + kl_scale*(2/sigma - 2 sigma);
+        dc = first 128 columns of dcg (T) or 0 when dcg is None."""
+        nc = mu.shape[1]
+        dc = 0 if dcg is None else dcg.reshape(mu.shape[0], -1)[:, :nc].to(mu.dtype)
+        dmu.copy_(dc + kl_scale * (-2 * mu))
+        dsigma.copy_(dc * eps + kl_scale * (2 / sigma - 2 * sigma))
+
+    # ---- losses / gradient penalty
+    def interp(self, real, fake, eps, out):
+        e = eps.to(torch.float64)[:, None, None, None]
+        out.copy_((real.to(torch.float64) * e + fake.to(torch.float64) * (1 - e)).to(out.dtype))
+
+    def sample_sqnorm(self, g, out):
+        out.copy_((g.reshape(g.shape[0], -1).to(torch.float64) ** 2).sum(1).to(out.dtype))
+
+    def gp_seed(self, g, sq, coef, v):
+        """v = coef * (1 - 1/||g||) g  (= d[coef/2 * sum (||g||-1)^2] / dg)."""
+        nrm = torch.sqrt(sq.to(torch.float64))
+        f = coef * (1 - 1 / nrm)
+        v.copy_((g.to(torch.float64) * f[:, None, None, None]).to(v.dtype))
+
+    def critic_loss(self, s_real, s_mis, s_fake, sq, lam, out):
+        """out[0] = mean(cat(mis,fake)) - mean(real) + lam*gp ; out[1] = gp."""
+        gp = ((torch.sqrt(sq) - 1) ** 2).mean()
+        out[0] = torch.cat((s_mis, s_fake)).mean() - s_real.mean() + lam * gp
+        out[1] = gp
+
+    def gen_loss(self, s_fake, mu, sigma, out):
+        """out[0] = -mean(s) + sum(1 + log sigma^2 - mu^2 - sigma^2) ; out[1] = kl term."""
+        kl = (1 + torch.log(sigma * sigma) - mu * mu - sigma * sigma).sum()
+        out[0] = -s_fake.mean() + kl
+        out[1] = kl
+
+    # ---- optimiser
+    def adam_step(self, p, g, m, v, hyper):
+        """hyper (fp32, device) = [lr, beta1, beta2, eps, step]; step is incremented first (torch Adam)."""
+        hyper[4] += 1
+        lr, b1, b2, eps, t = (float(x) for x in hyper)
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1 = 1 - b1 ** t
+        bc2 = 1 - b2 ** t
+        denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / bc1)
+
+    def fill(self, t, value):
+        t.fill_(value)
+
+    def zero(self, t):
+        t.zero_()
+
+    def scale_rows_add(self, x, scale, out, accumulate):
+        """out (+)= scale[n] * x[n, ...]   (per-sample scale)."""
+        s = scale.to(torch.float64).reshape(-1, *([1] * (x.dim() - 1)))
+        r = x.to(torch.float64) * s
+        if accumulate:
+            out.copy_((out.to(torch.float64) + r).to(out.dtype))
+        else:
+            out.copy_(r.to(out.dtype))
