@@ -1,0 +1,799 @@
+// elementwise.cu -- HBM/L2-bound kernels of the StackGAN step: layout, BatchNorm (statistics,
+// apply, backward, the gradient-penalty double backward), activations' backward, losses, Adam.
+// All are streaming kernels: 4-wide vector accesses, channel-fastest (NHWC) indexing, per-channel
+// reductions finished with one fp64 atomic per channel per CTA.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace sg {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic 4-wide elementwise driver: F::apply(i4, lanes...) handles elements [4*i4, 4*i4+4)
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) ew4_kernel(F f, int64_t n4) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) f(i);
+}
+
+template <typename F>
+static int launch_ew4(F f, int64_t n, cudaStream_t st, const char* what) {
+    if (n % 4 != 0) {
+        set_error("%s: element count %lld not a multiple of 4", what, (long long)n);
+        return SG_ERR_BAD_ARG;
+    }
+    int64_t n4 = n / 4;
+    if (n4 == 0) return 0;
+    ew4_kernel<F><<<grid_for(n4, 256, 16), 256, 0, st>>>(f, n4);
+    g_launches.fetch_add(1);
+    return check_launch(what);
+}
+
+// ---- BN apply + activation (+ residual)
+template <typename T>
+struct BnActF {
+    const T* y; const float* mr; const float* gamma; const float* beta; const T* res; T* out;
+    int64_t rows_per_group; int C; int act;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        F4 v = ld4(y + e), r;
+        F4 rs;
+        if (res) rs = ld4(res + e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t row = (e + j) / C;
+            int c = (int)((e + j) - row * C);
+            int g = (int)(row / rows_per_group);
+            const float* m = mr + ((int64_t)g * C + c) * 2;
+            float z = (v.v[j] - m[0]) * m[1] * gamma[c] + beta[c];
+            if (res) z += rs.v[j];
+            r.v[j] = act_fwd(z, act);
+        }
+        st4(out + e, r);
+    }
+};
+
+// ---- BN backward apply
+template <typename T>
+struct BnBwdApplyF {
+    const T* da; const T* a_out; const T* y; const float* mr; const float* gamma; const double* sums;
+    const T* inject; int inject_group; T* dy; int64_t rows_per_group; int C; int act;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        F4 d = ld4(da + e), a = ld4(a_out + e), yy = ld4(y + e), r, inj;
+        int64_t row0 = e / C;
+        int g0 = (int)(row0 / rows_per_group);
+        bool has_inj = inject != nullptr && g0 == inject_group;   // 4 elements never straddle groups (group size % 4 == 0)
+        if (has_inj) inj = ld4(inject + (e - (int64_t)inject_group * rows_per_group * C));
+        float n = (float)rows_per_group;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t row = (e + j) / C;
+            int c = (int)((e + j) - row * C);
+            int g = (int)(row / rows_per_group);
+            const float* m = mr + ((int64_t)g * C + c) * 2;
+            const double* s = sums + ((int64_t)g * C + c) * 2;
+            float xh = (yy.v[j] - m[0]) * m[1];
+            float dz = d.v[j] * act_mask(a.v[j], act);
+            float coef = gamma[c] * m[1] / n;
+            float o = coef * (n * dz - (float)s[0] - xh * (float)s[1]);
+            if (has_inj) o += inj.v[j];
+            r.v[j] = o;
+        }
+        st4(dy + e, r);
+    }
+};
+
+template <typename T>
+struct ActBwdF {
+    const T* da; const T* a_out; T* out; int act;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        F4 d = ld4(da + e), a = ld4(a_out + e), r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = d.v[j] * act_mask(a.v[j], act);
+        st4(out + e, r);
+    }
+};
+
+// ---- gradient-penalty BN double backward, apply part
+template <typename T>
+struct GpBnApplyF {
+    const T* v; const T* da; const T* a_out; const T* y; const float* mr; const float* gamma;
+    const double* sums; const double* tsums; T* w_out; T* gy_out; int64_t rows; int C; int act;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        F4 vv = ld4(v + e), d = ld4(da + e), a = ld4(a_out + e), yy = ld4(y + e), w, gy;
+        float n = (float)rows;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = (int)((e + j) % C);
+            float mean = mr[c * 2], r = mr[c * 2 + 1];
+            float S1 = (float)sums[c * 2], S2 = (float)sums[c * 2 + 1];
+            float T1 = (float)tsums[c * 3], T2 = (float)tsums[c * 3 + 1], T3 = (float)tsums[c * 3 + 2];
+            float al = gamma[c] * r / n;
+            float xh = (yy.v[j] - mean) * r;
+            float mk = act_mask(a.v[j], act);
+            float dz = d.v[j] * mk;
+            float u = al * (n * vv.v[j] - T1 - xh * T2);
+            w.v[j] = u * mk;
+            float P = al * (n * T3 - S1 * T1 - S2 * T2);
+            float G = -al * (vv.v[j] * S2 + dz * T2);
+            float sG = -al * (S2 * T1 + S1 * T2);
+            float sGx = -2.f * al * S2 * T2;
+            gy.v[j] = r * (G - sG / n - xh * sGx / n) - P * r * xh / n;
+        }
+        st4(w_out + e, w);
+        st4(gy_out + e, gy);
+    }
+};
+
+__global__ void gp_bn_dgamma_kernel(const float* mr, const double* sums, const double* tsums, float* dgamma,
+                                    double n, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double r = mr[c * 2 + 1];
+    double S1 = sums[c * 2], S2 = sums[c * 2 + 1];
+    double T1 = tsums[c * 3], T2 = tsums[c * 3 + 1], T3 = tsums[c * 3 + 2];
+    dgamma[c] += (float)(r / n * (n * T3 - S1 * T1 - S2 * T2));
+}
+
+// ---- per-sample scale kernels
+template <typename T>
+struct InterpF {
+    const T* real; const T* fake; const float* eps; T* out; int64_t per_sample;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        float ep = eps[e / per_sample];
+        F4 a = ld4(real + e), b = ld4(fake + e), r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = a.v[j] * ep + b.v[j] * (1.f - ep);
+        st4(out + e, r);
+    }
+};
+
+template <typename T>
+struct GpSeedF {
+    const T* g; const float* sq; float coef; T* v; int64_t per_sample;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        float f = coef * (1.f - rsqrtf(sq[e / per_sample]));
+        F4 a = ld4(g + e), r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = a.v[j] * f;
+        st4(v + e, r);
+    }
+};
+
+template <typename T>
+struct ScaleRowsAddF {
+    const T* x; const float* scale; T* out; int accumulate; int64_t per_sample;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        float s = scale[e / per_sample];
+        F4 a = ld4(x + e), r;
+        if (accumulate) r = ld4(out + e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = (accumulate ? r.v[j] : 0.f) + a.v[j] * s;
+        st4(out + e, r);
+    }
+};
+
+template <typename T>
+struct OuterF {
+    const float* coef; const float* vec; T* out; int M;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        int64_t n = e / M;
+        int m = (int)(e - n * M);
+        float c = coef[n];
+        F4 r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = c * vec[m + j];
+        st4(out + e, r);
+    }
+};
+
+struct AdamF {
+    float* p; const float* g; float* m; float* v; const float* hyper;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], t = hyper[4];
+        float bc1 = 1.f - powf(b1, t), bc2s = sqrtf(1.f - powf(b2, t));
+        F4 pp = ld4(p + e), gg = ld4(g + e), mm = ld4(m + e), vv = ld4(v + e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mm.v[j] = b1 * mm.v[j] + (1.f - b1) * gg.v[j];
+            vv.v[j] = b2 * vv.v[j] + (1.f - b2) * gg.v[j] * gg.v[j];
+            float denom = sqrtf(vv.v[j]) / bc2s + eps;
+            pp.v[j] -= (lr / bc1) * (mm.v[j] / denom);
+        }
+        st4(p + e, pp); st4(m + e, mm); st4(v + e, vv);
+    }
+};
+
+__global__ void adam_tick_kernel(float* hyper) { hyper[4] += 1.f; }
+
+struct FillF {
+    float* p; float val;
+    __device__ void operator()(int64_t i4) const {
+        F4 r;
+        r.v[0] = r.v[1] = r.v[2] = r.v[3] = val;
+        st4(p + i4 * 4, r);
+    }
+};
+__global__ void fill_tail_kernel(float* p, float v, int64_t from, int64_t n) {
+    int64_t i = from + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions over rows of a [rows][C] tensor
+//   block = (TX channel lanes) x (256/TX row lanes); grid = (row chunks, groups, channel chunks)
+// ------------------------------------------------------------------------------------------------
+template <int NV, typename F, typename OutT>
+__global__ void __launch_bounds__(256) rowreduce_kernel(F f, OutT* out, int64_t rows_per_group, int C,
+                                                         int64_t rows_per_block, int out_group_stride) {
+    __shared__ double sh[NV][256];
+    int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    int c = blockIdx.z * TX + tx;
+    int g = blockIdx.y;
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > rows_per_group) r1 = rows_per_group;
+    float acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+    if (c < C) {
+        for (int64_t r = r0 + ty; r < r1; r += TY) {
+            float vals[NV];
+            f((int64_t)g * rows_per_group + r, c, g, vals);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] += vals[k];
+        }
+    }
+    int tid = ty * TX + tx;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sh[k][tid] = (double)acc[k];
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int j = 0; j < TY; ++j) s += sh[k][j * TX + tx];
+            atomicAdd(out + (int64_t)g * out_group_stride + (int64_t)c * NV + k, (OutT)s);
+        }
+    }
+}
+
+template <int NV, typename F, typename OutT>
+static int launch_rowreduce(F f, OutT* out, int64_t rows_per_group, int C, int groups, cudaStream_t st,
+                            const char* what) {
+    int TX = 4;
+    while (TX < C && TX < 64) TX *= 2;
+    int TY = 256 / TX;
+    int cchunks = (C + TX - 1) / TX;
+    int64_t target_blocks = (4 * SG_NUM_SMS + groups * cchunks - 1) / (groups * cchunks);
+    if (target_blocks < 1) target_blocks = 1;
+    int64_t rpb = (rows_per_group + target_blocks - 1) / target_blocks;
+    int64_t min_rpb = (int64_t)TY * 4;
+    if (rpb < min_rpb) rpb = min_rpb;
+    if (rpb > (int64_t)TY * 256) rpb = (int64_t)TY * 256;   // bound the fp32 partial length per thread
+    int64_t rblocks = (rows_per_group + rpb - 1) / rpb;
+    dim3 grid((unsigned)rblocks, groups, cchunks), block(TX, TY);
+    rowreduce_kernel<NV, F, OutT><<<grid, block, 0, st>>>(f, out, rows_per_group, C, rpb, C * NV);
+    g_launches.fetch_add(1);
+    return check_launch(what);
+}
+
+template <typename T>
+struct ColStatsF {
+    const T* y; int C;
+    __device__ void operator()(int64_t row, int c, int g, float* o) const {
+        float v = ldf(y + row * C + c);
+        o[0] = v; o[1] = v * v;
+    }
+};
+template <typename T>
+struct ColSumF {
+    const T* x; int C;
+    __device__ void operator()(int64_t row, int c, int g, float* o) const { o[0] = ldf(x + row * C + c); }
+};
+template <typename T>
+struct BnBwdReduceF {
+    const T* da; const T* a_out; const T* y; const float* mr; int C; int act;
+    __device__ void operator()(int64_t row, int c, int g, float* o) const {
+        int64_t i = row * C + c;
+        const float* m = mr + ((int64_t)g * C + c) * 2;
+        float dz = ldf(da + i) * act_mask(ldf(a_out + i), act);
+        o[0] = dz;
+        o[1] = dz * (ldf(y + i) - m[0]) * m[1];
+    }
+};
+template <typename T>
+struct GpBnReduceF {
+    const T* v; const T* da; const T* a_out; const T* y; const float* mr; int C; int act;
+    __device__ void operator()(int64_t row, int c, int g, float* o) const {
+        int64_t i = row * C + c;
+        float vv = ldf(v + i);
+        float dz = ldf(da + i) * act_mask(ldf(a_out + i), act);
+        o[0] = vv;
+        o[1] = vv * (ldf(y + i) - mr[c * 2]) * mr[c * 2 + 1];
+        o[2] = vv * dz;
+    }
+};
+
+__global__ void bn_finalize_kernel(const double* stats, double count, float* mr, float* rm, float* rv,
+                                   long long* nbt, int dup_first, int update_running, float momentum, float eps,
+                                   int G, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && update_running && nbt) *nbt += dup_first + G - 1;
+    if (c >= C) return;
+    float m_run = 0.f, v_run = 0.f;
+    if (update_running) { m_run = rm[c]; v_run = rv[c]; }
+    for (int g = 0; g < G; ++g) {
+        double s = stats[((int64_t)g * C + c) * 2], q = stats[((int64_t)g * C + c) * 2 + 1];
+        double mean = s / count;
+        double var = q / count - mean * mean;
+        if (var < 0) var = 0;
+        mr[((int64_t)g * C + c) * 2] = (float)mean;
+        mr[((int64_t)g * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        if (update_running) {
+            float unb = (float)(var * count / (count > 1 ? count - 1 : 1));
+            int reps = g == 0 ? dup_first : 1;
+            for (int r = 0; r < reps; ++r) {
+                m_run = (1.f - momentum) * m_run + momentum * (float)mean;
+                v_run = (1.f - momentum) * v_run + momentum * unb;
+            }
+        }
+    }
+    if (update_running) { rm[c] = m_run; rv[c] = v_run; }
+}
+
+__global__ void bn_eval_mr_kernel(const float* rm, const float* rv, float* mr, float eps, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        mr[c * 2] = rm[c];
+        mr[c * 2 + 1] = (float)(1.0 / sqrt((double)rv[c] + (double)eps));
+    }
+}
+
+__global__ void bn_param_grad_kernel(const double* sums, float* dgamma, float* dbeta, int G, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int g = 0; g < G; ++g) {
+        s1 += sums[((int64_t)g * C + c) * 2];
+        s2 += sums[((int64_t)g * C + c) * 2 + 1];
+    }
+    dgamma[c] += (float)s2;
+    dbeta[c] += (float)s1;
+}
+
+// ---- layout
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* src, T* dst, int N, int C, int64_t HW) {
+    int64_t total = (int64_t)N * HW;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t n = i / HW, hw = i - n * HW;
+        const float* s = src + n * C * HW + hw;
+        T* d = dst + i * C;
+        for (int c = 0; c < C; ++c) stf(d + c, s[(int64_t)c * HW]);
+    }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* src, float* dst, int N, int C, int64_t HW) {
+    int64_t total = (int64_t)N * HW;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t n = i / HW, hw = i - n * HW;
+        const T* s = src + i * C;
+        float* d = dst + n * C * HW + hw;
+        for (int c = 0; c < C; ++c) d[(int64_t)c * HW] = ldf(s + c);
+    }
+}
+template <typename T>
+__global__ void pack_weight_kernel(const float* w, T* pf, T* pd, int Co, int Ci, int kk) {
+    int64_t total = (int64_t)Co * Ci * kk;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int t = (int)(i % kk);
+        int64_t r = i / kk;
+        int ci = (int)(r % Ci);
+        int co = (int)(r / Ci);
+        float v = w[i];
+        if (pf) stf(pf + ((int64_t)co * kk + t) * Ci + ci, v);
+        if (pd) stf(pd + ((int64_t)ci * kk + t) * Co + co, v);
+    }
+}
+
+// ---- losses
+template <typename T>
+__global__ void __launch_bounds__(256) sample_sqnorm_kernel(const T* g, float* out, int64_t per_sample,
+                                                            int64_t per_block) {
+    int n = blockIdx.y;
+    int64_t b0 = (int64_t)blockIdx.x * per_block, b1 = b0 + per_block;
+    if (b1 > per_sample) b1 = per_sample;
+    const T* p = g + (int64_t)n * per_sample;
+    float acc = 0.f;
+    for (int64_t i = b0 + threadIdx.x * 4; i < b1; i += 256 * 4) {
+        F4 v = ld4(p + i);
+        acc += v.v[0] * v.v[0] + v.v[1] * v.v[1] + v.v[2] * v.v[2] + v.v[3] * v.v[3];
+    }
+    __shared__ float sh[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += sh[i];
+        atomicAdd(out + n, s);
+    }
+}
+
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) critic_loss_kernel(const float* s_real, const float* s_mis, const float* s_fake,
+                                                          const float* sq, float lam, float* out, int N) {
+    __shared__ double sh[8];
+    double a = 0, b = 0, c = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        a += (double)s_mis[i] + (double)s_fake[i];
+        b += s_real[i];
+        double d = sqrt((double)sq[i]) - 1.0;
+        c += d * d;
+    }
+    a = block_sum_d(a, sh); b = block_sum_d(b, sh); c = block_sum_d(c, sh);
+    if (threadIdx.x == 0) {
+        double gp = c / N;
+        out[0] = (float)(a / (2.0 * N) - b / N + lam * gp);
+        out[1] = (float)gp;
+    }
+}
+
+__global__ void __launch_bounds__(256) gen_loss_kernel(const float* s, const float* mu, const float* sigma, float* out,
+                                                       int N, int C) {
+    __shared__ double sh[8];
+    double a = 0, k = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) a += s[i];
+    for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+        double m = mu[i], sg_ = sigma[i];
+        k += 1.0 + log(sg_ * sg_) - m * m - sg_ * sg_;
+    }
+    a = block_sum_d(a, sh); k = block_sum_d(k, sh);
+    if (threadIdx.x == 0) {
+        out[0] = (float)(-a / N + k);
+        out[1] = (float)k;
+    }
+}
+
+// ---- conditioning augmentation elementwise parts
+template <typename T>
+__global__ void ca_reparam_kernel(const float* mu, const float* sigma, const float* eps, const float* z, float* c_hat,
+                                  T* cg, int N, int C, int nz) {
+    int W = C + nz;
+    int64_t total = (int64_t)N * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int n = (int)(i / W), j = (int)(i - (int64_t)n * W);
+        if (j < C) {
+            int64_t k = (int64_t)n * C + j;
+            float c = mu[k] + sigma[k] * eps[k];
+            c_hat[k] = c;
+            if (cg) stf(cg + i, c);
+        } else if (cg && z) {
+            stf(cg + i, z[(int64_t)n * nz + (j - C)]);
+        }
+    }
+}
+template <typename T>
+__global__ void ca_bwd_seed_kernel(const T* dcg, const float* eps, const float* mu, const float* sigma, float kl,
+                                   float* dmu, float* dsigma, int N, int C, int ld) {
+    int64_t total = (int64_t)N * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int n = (int)(i / C), j = (int)(i - (int64_t)n * C);
+        float dc = dcg ? ldf(dcg + (int64_t)n * ld + j) : 0.f;
+        float s = sigma[i];
+        dmu[i] = dc + kl * (-2.f * mu[i]);
+        dsigma[i] = dc * eps[i] + kl * (2.f / s - 2.f * s);
+    }
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int sg_version(void) { return 1; }
+const char* sg_last_error(void) { return sg::g_err; }
+int64_t sg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sg_check_device(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return SG_ERR_NO_DEVICE; }
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return SG_ERR_NO_DEVICE; }
+    if (p.major != 10) {
+        set_error("libsgb200 is built for sm_100a (B200) only; device is sm_%d%d", p.major, p.minor);
+        return SG_ERR_NO_DEVICE;
+    }
+    return 0;
+}
+
+int sg_zero(void* ptr, int64_t bytes, void* stream) {
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, SG_STREAM(stream));
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+int sg_fill_f32(float* ptr, float value, int64_t n, void* stream) {
+    int64_t n4 = n / 4 * 4;
+    if (n4) {
+        FillF f{ptr, value};
+        int e = launch_ew4(f, n4, SG_STREAM(stream), "fill");
+        if (e) return e;
+    }
+    if (n4 < n) {
+        fill_tail_kernel<<<1, 4, 0, SG_STREAM(stream)>>>(ptr, value, n4, n);
+        SG_LAUNCHED("fill_tail");
+    }
+    return 0;
+}
+
+int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dtype, void* stream) {
+    int64_t HW = (int64_t)H * W;
+    SG_DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for((int64_t)N * HW, 256), 256, 0, SG_STREAM(stream)>>>(
+                             src, (T*)dst, N, C, HW)));
+    SG_LAUNCHED("nchw_to_nhwc");
+    return 0;
+}
+int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int dtype, void* stream) {
+    int64_t HW = (int64_t)H * W;
+    SG_DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<grid_for((int64_t)N * HW, 256), 256, 0, SG_STREAM(stream)>>>(
+                             (const T*)src, dst, N, C, HW)));
+    SG_LAUNCHED("nhwc_to_nchw");
+    return 0;
+}
+int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream) {
+    int64_t n = (int64_t)Co * Ci * kk;
+    SG_DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(w, (T*)pf, (T*)pd, Co,
+                                                                                                   Ci, kk)));
+    SG_LAUNCHED("pack_weight");
+    return 0;
+}
+
+int sg_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream) {
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        ColSumF<T> f{(const T*)x, C};
+        e = launch_rowreduce<1>(f, out, rows, C, 1, SG_STREAM(stream), "colsum");
+    });
+    return e;
+}
+
+int sg_col_stats(const void* y, double* stats, int64_t rows_per_group, int C, int groups, int dtype, void* stream) {
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        ColStatsF<T> f{(const T*)y, C};
+        e = launch_rowreduce<2>(f, stats, rows_per_group, C, groups, SG_STREAM(stream), "col_stats");
+    });
+    return e;
+}
+
+int sg_bn_finalize(const double* stats, int64_t count, float* mr, float* running_mean, float* running_var,
+                   int64_t* nbt, int dup_first, int update_running, float momentum, float eps, int groups, int C,
+                   void* stream) {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(stats, (double)count, mr, running_mean,
+                                                                       running_var, (long long*)nbt, dup_first,
+                                                                       update_running, momentum, eps, groups, C);
+    SG_LAUNCHED("bn_finalize");
+    return 0;
+}
+int sg_bn_eval_mr(const float* running_mean, const float* running_var, float* mr, float eps, int C, void* stream) {
+    bn_eval_mr_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(running_mean, running_var, mr, eps, C);
+    SG_LAUNCHED("bn_eval_mr");
+    return 0;
+}
+
+int sg_bn_act(const void* y, const float* mr, const float* gamma, const float* beta, const void* residual, void* out,
+              int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream) {
+    int64_t n = rows_per_group * C * groups;
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        BnActF<T> f{(const T*)y, mr, gamma, beta, (const T*)residual, (T*)out, rows_per_group, C, act};
+        e = launch_ew4(f, n, SG_STREAM(stream), "bn_act");
+    });
+    return e;
+}
+
+int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const float* mr, double* sums,
+                     int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream) {
+    cudaStream_t st = SG_STREAM(stream);
+    cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        BnBwdReduceF<T> f{(const T*)da, (const T*)a_out, (const T*)y, mr, C, act};
+        e = launch_rowreduce<2>(f, sums, rows_per_group, C, groups, st, "bn_bwd_reduce");
+    });
+    return e;
+}
+
+int sg_bn_bwd_apply(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
+                    const double* sums, const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C,
+                    int groups, int act, int dtype, void* stream) {
+    int64_t n = rows_per_group * C * groups;
+    SG_REQUIRE((rows_per_group * C) % 4 == 0, "bn_bwd_apply: group size must be a multiple of 4 elements");
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        BnBwdApplyF<T> f{(const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, (const T*)inject, inject_group,
+                         (T*)dy, rows_per_group, C, act};
+        e = launch_ew4(f, n, SG_STREAM(stream), "bn_bwd_apply");
+    });
+    return e;
+}
+
+int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream) {
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(sums, dgamma, dbeta, groups, C);
+    SG_LAUNCHED("bn_param_grad");
+    return 0;
+}
+
+int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act, int dtype, void* stream) {
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        ActBwdF<T> f{(const T*)da, (const T*)a_out, (T*)out, act};
+        e = launch_ew4(f, n, SG_STREAM(stream), "act_bwd");
+    });
+    return e;
+}
+
+int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums,
+                    int64_t rows, int C, int act, int dtype, void* stream) {
+    cudaStream_t st = SG_STREAM(stream);
+    cudaMemsetAsync(tsums, 0, (size_t)C * 3 * sizeof(double), st);
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        GpBnReduceF<T> f{(const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, C, act};
+        e = launch_rowreduce<3>(f, tsums, rows, C, 1, st, "gp_bn_reduce");
+    });
+    return e;
+}
+
+int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
+                   const float* gamma, const double* sums, const double* tsums, void* w_out, void* gy_out,
+                   float* dgamma, int64_t rows, int C, int act, int dtype, void* stream) {
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        GpBnApplyF<T> f{(const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, tsums,
+                        (T*)w_out, (T*)gy_out, rows, C, act};
+        e = launch_ew4(f, rows * C, SG_STREAM(stream), "gp_bn_apply");
+    });
+    if (e) return e;
+    gp_bn_dgamma_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(mr, sums, tsums, dgamma, (double)rows, C);
+    SG_LAUNCHED("gp_bn_dgamma");
+    return 0;
+}
+
+int sg_outer(const float* coef, const float* vec, void* out, int N, int M, int out_dtype, void* stream) {
+    SG_REQUIRE(M % 4 == 0, "outer: M %% 4 != 0");
+    int e = 0;
+    SG_DISPATCH_T(out_dtype, {
+        OuterF<T> f{coef, vec, (T*)out, M};
+        e = launch_ew4(f, (int64_t)N * M, SG_STREAM(stream), "outer");
+    });
+    return e;
+}
+
+int sg_ca_reparam(const float* mu, const float* sigma, const float* eps, const float* z, float* c_hat, void* cg, int N,
+                  int C, int nz, int dtype, void* stream) {
+    int64_t n = (int64_t)N * (C + nz);
+    SG_DISPATCH_T(dtype, (ca_reparam_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(mu, sigma, eps, z, c_hat,
+                                                                                               (T*)cg, N, C, nz)));
+    SG_LAUNCHED("ca_reparam");
+    return 0;
+}
+int sg_ca_bwd_seed(const void* dcg, const float* eps, const float* mu, const float* sigma, float kl_scale, float* dmu,
+                   float* dsigma, int N, int C, int ld, int dtype, void* stream) {
+    int64_t n = (int64_t)N * C;
+    SG_DISPATCH_T(dtype, (ca_bwd_seed_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(
+                             (const T*)dcg, eps, mu, sigma, kl_scale, dmu, dsigma, N, C, ld)));
+    SG_LAUNCHED("ca_bwd_seed");
+    return 0;
+}
+
+int sg_interp(const void* real, const void* fake, const float* eps, void* out, int N, int64_t per_sample, int dtype,
+              void* stream) {
+    SG_REQUIRE(per_sample % 4 == 0, "interp: per_sample %% 4 != 0");
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        InterpF<T> f{(const T*)real, (const T*)fake, eps, (T*)out, per_sample};
+        e = launch_ew4(f, (int64_t)N * per_sample, SG_STREAM(stream), "interp");
+    });
+    return e;
+}
+
+int sg_sample_sqnorm(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream) {
+    SG_REQUIRE(per_sample % 4 == 0, "sample_sqnorm: per_sample %% 4 != 0");
+    cudaStream_t st = SG_STREAM(stream);
+    cudaMemsetAsync(out, 0, N * sizeof(float), st);
+    int64_t per_block = 256 * 4 * 4;
+    int bx = (int)((per_sample + per_block - 1) / per_block);
+    dim3 grid(bx, N);
+    SG_DISPATCH_T(dtype, (sample_sqnorm_kernel<T><<<grid, 256, 0, st>>>((const T*)g, out, per_sample, per_block)));
+    SG_LAUNCHED("sample_sqnorm");
+    return 0;
+}
+
+int sg_gp_seed(const void* g, const float* sq, float coef, void* v, int N, int64_t per_sample, int dtype, void* stream) {
+    SG_REQUIRE(per_sample % 4 == 0, "gp_seed: per_sample %% 4 != 0");
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        GpSeedF<T> f{(const T*)g, sq, coef, (T*)v, per_sample};
+        e = launch_ew4(f, (int64_t)N * per_sample, SG_STREAM(stream), "gp_seed");
+    });
+    return e;
+}
+
+int sg_scale_rows_add(const void* x, const float* scale, void* out, int accumulate, int N, int64_t per_sample, int dtype,
+                      void* stream) {
+    SG_REQUIRE(per_sample % 4 == 0, "scale_rows_add: per_sample %% 4 != 0");
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        ScaleRowsAddF<T> f{(const T*)x, scale, (T*)out, accumulate, per_sample};
+        e = launch_ew4(f, (int64_t)N * per_sample, SG_STREAM(stream), "scale_rows_add");
+    });
+    return e;
+}
+
+int sg_critic_loss(const float* s_real, const float* s_mis, const float* s_fake, const float* sq, float lam, float* out2,
+                   int N, void* stream) {
+    critic_loss_kernel<<<1, 256, 0, SG_STREAM(stream)>>>(s_real, s_mis, s_fake, sq, lam, out2, N);
+    SG_LAUNCHED("critic_loss");
+    return 0;
+}
+int sg_gen_loss(const float* s_fake, const float* mu, const float* sigma, float* out2, int N, int C, void* stream) {
+    gen_loss_kernel<<<1, 256, 0, SG_STREAM(stream)>>>(s_fake, mu, sigma, out2, N, C);
+    SG_LAUNCHED("gen_loss");
+    return 0;
+}
+
+int sg_adam_step(float* p, const float* g, float* m, float* v, float* hyper, int64_t n, void* stream) {
+    SG_REQUIRE(n % 4 == 0, "adam: n %% 4 != 0 (pad the flat buffer)");
+    adam_tick_kernel<<<1, 1, 0, SG_STREAM(stream)>>>(hyper);
+    SG_LAUNCHED("adam_tick");
+    AdamF f{p, g, m, v, hyper};
+    return launch_ew4(f, n, SG_STREAM(stream), "adam");
+}
+
+}  // extern "C"

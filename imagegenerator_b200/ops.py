@@ -1,0 +1,359 @@
+"""ctypes binding of libsgb200.so (include/sgb200.h) -- the only compute backend of this package.
+
+``CudaOps`` exposes one method per C-ABI entry point, taking torch CUDA tensors (used purely as
+device-memory handles) and launching on torch's current stream.  There is NO CPU fallback:
+constructing ``CudaOps`` without the built library or without an sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsgb200.so")
+
+SG_F32, SG_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+
+_c = ctypes
+_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+# name -> argtypes (stream is always the trailing void*)
+_SIGS = {
+    "sg_zero": [_P, _L, _P],
+    "sg_fill_f32": [_P, _F, _L, _P],
+    "sg_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "sg_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "sg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "sg_conv_fprop": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_dgrad": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_wgrad": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_conv_fprop_ffma": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_dgrad_ffma": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_wgrad_ffma": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_colsum": [_P, _P, _L, _I, _I, _P],
+    "sg_col_stats": [_P, _P, _L, _I, _I, _I, _P],
+    "sg_bn_finalize": [_P, _L, _P, _P, _P, _P, _I, _I, _F, _F, _I, _I, _P],
+    "sg_bn_eval_mr": [_P, _P, _P, _F, _I, _P],
+    "sg_bn_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "sg_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "sg_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
+    "sg_bn_param_grad": [_P, _P, _P, _I, _I, _P],
+    "sg_act_bwd": [_P, _P, _P, _L, _I, _I, _P],
+    "sg_gp_bn_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "sg_gp_bn_apply": [_P] * 11 + [_L, _I, _I, _I, _P],
+    "sg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "sg_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "sg_head_prepare": [_P] * 7 + [_I, _I, _I, _P],
+    "sg_head_fwd": [_P] * 6 + [_I, _I, _I, _I, _P],
+    "sg_outer": [_P, _P, _P, _I, _I, _I, _P],
+    "sg_wsum_rows": [_P, _P, _P, _I, _I, _I, _P],
+    "sg_head_param_grads": [_P] * 10 + [_I, _I, _I, _P],
+    "sg_ca_reparam": [_P] * 6 + [_I, _I, _I, _I, _P],
+    "sg_ca_bwd_seed": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
+    "sg_interp": [_P, _P, _P, _P, _I, _L, _I, _P],
+    "sg_sample_sqnorm": [_P, _P, _I, _L, _I, _P],
+    "sg_gp_seed": [_P, _P, _F, _P, _I, _L, _I, _P],
+    "sg_critic_loss": [_P, _P, _P, _P, _F, _P, _I, _P],
+    "sg_gen_loss": [_P, _P, _P, _P, _I, _I, _P],
+    "sg_scale_rows_add": [_P, _P, _P, _I, _I, _L, _I, _P],
+    "sg_adam_step": [_P, _P, _P, _P, _P, _L, _P],
+}
+
+EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count"])
+
+
+def load_library(path=LIB_PATH):
+    """dlopen libsgb200.so and attach argtypes.  Raises if it has not been built."""
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -m imagegenerator_b200.build` "
+            "(there is no CPU or PyTorch fallback for the StackGAN kernels)")
+    lib = ctypes.CDLL(path)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _I
+    lib.sg_version.restype = _I
+    lib.sg_last_error.restype = _c.c_char_p
+    lib.sg_check_device.restype = _I
+    lib.sg_launch_count.restype = _L
+    return lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaOps:
+    """The CUDA backend.  ``dtype``: 'bf16' (tensor-core mode) or 'fp32' (validation mode)."""
+
+    is_emulator = False
+
+    def __init__(self, dtype="bf16", device=None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("imagegenerator_b200 needs a CUDA device (sm_100a); none is visible")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        with torch.cuda.device(self.device):
+            if self.lib.sg_check_device() != 0:
+                raise RuntimeError(self.lib.sg_last_error().decode())
+        if dtype in ("bf16", torch.bfloat16):
+            self.act_dtype, self.dt = torch.bfloat16, SG_BF16
+        elif dtype in ("fp32", torch.float32):
+            self.act_dtype, self.dt = torch.float32, SG_F32
+        else:
+            raise ValueError(dtype)
+        self.f32, self.f64 = torch.float32, torch.float64
+
+    # ---- plumbing
+    def _st(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"libsgb200 error {rc}: {self.lib.sg_last_error().decode()}")
+
+    def launch_count(self):
+        return int(self.lib.sg_launch_count())
+
+    def empty(self, shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        return torch.zeros(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def _dt_of(self, t):
+        if t.dtype == torch.float32:
+            return SG_F32
+        if t.dtype == torch.bfloat16:
+            return SG_BF16
+        raise TypeError(f"unsupported tensor dtype {t.dtype}")
+
+    @staticmethod
+    def _c(*ts):
+        for t in ts:
+            if t is not None:
+                assert t.is_cuda and t.is_contiguous(), "libsgb200 needs contiguous CUDA tensors"
+
+    # ---- memory
+    def zero(self, t):
+        self._c(t)
+        self._ck(self.lib.sg_zero(_ptr(t), t.numel() * t.element_size(), self._st()))
+
+    def fill(self, t, value):
+        self._c(t)
+        assert t.dtype == torch.float32
+        self._ck(self.lib.sg_fill_f32(_ptr(t), float(value), t.numel(), self._st()))
+
+    # ---- layout
+    def nchw_to_nhwc(self, src, dst):
+        self._c(src, dst)
+        assert src.dtype == torch.float32
+        N, C, H, W = src.shape
+        assert dst.numel() == src.numel()
+        self._ck(self.lib.sg_nchw_to_nhwc(_ptr(src), _ptr(dst), N, C, H, W, self._dt_of(dst), self._st()))
+
+    def nhwc_to_nchw(self, src, dst):
+        self._c(src, dst)
+        N, C, H, W = dst.shape
+        assert dst.dtype == torch.float32 and dst.numel() == src.numel()
+        self._ck(self.lib.sg_nhwc_to_nchw(_ptr(src), _ptr(dst), N, C, H, W, self._dt_of(src), self._st()))
+
+    def pack_weight(self, w, pf, pd):
+        self._c(w, pf, pd)
+        Co, Ci, k, _ = w.shape
+        ref = pf if pf is not None else pd
+        self._ck(self.lib.sg_pack_weight(_ptr(w), _ptr(pf), _ptr(pd), Co, Ci, k * k, self._dt_of(ref), self._st()))
+
+    # ---- convolution operator
+    def _conv_dims(self, x, y):
+        N, H, W, Ci = x.shape
+        N2, Ho, Wo, Co = y.shape
+        assert N == N2
+        return N, H, W, Ci, Ho, Wo, Co
+
+    def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE, impl=""):
+        self._c(x, pf, bias, y)
+        d = self._conv_dims(x, y)
+        fn = getattr(self.lib, "sg_conv_fprop" + impl)
+        self._ck(fn(_ptr(x), _ptr(pf), _ptr(bias), _ptr(y), *d, k, s, p, act, self._dt_of(x), self._st()))
+
+    def conv_dgrad(self, dy, pd, bias, dx, k, s, p, act=ACT_NONE, impl=""):
+        self._c(dy, pd, bias, dx)
+        d = self._conv_dims(dx, dy)
+        fn = getattr(self.lib, "sg_conv_dgrad" + impl)
+        self._ck(fn(_ptr(dy), _ptr(pd), _ptr(bias), _ptr(dx), *d, k, s, p, act, self._dt_of(dy), self._st()))
+
+    def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
+        self._c(x, dy, dw)
+        d = self._conv_dims(x, dy)
+        assert dw.dtype == torch.float32 and tuple(dw.shape) == (d[6], d[3], k, k), (dw.shape, d)
+        fn = getattr(self.lib, "sg_conv_wgrad" + impl)
+        self._ck(fn(_ptr(x), _ptr(dy), _ptr(dw), *d, k, s, p, self._dt_of(x), self._st()))
+
+    def colsum(self, x, out):
+        self._c(x, out)
+        C = x.shape[-1]
+        self._ck(self.lib.sg_colsum(_ptr(x), _ptr(out), x.numel() // C, C, self._dt_of(x), self._st()))
+
+    # ---- batch norm
+    def col_stats(self, y, stats, groups):
+        self._c(y, stats)
+        C = y.shape[-1]
+        assert stats.dtype == torch.float64
+        self._ck(self.lib.sg_col_stats(_ptr(y), _ptr(stats), y.numel() // (C * groups), C, groups, self._dt_of(y), self._st()))
+
+    def bn_finalize(self, stats, count, mr, running_mean, running_var, nbt, dup_first, update_running=True,
+                    momentum=0.1, eps=1e-5):
+        self._c(stats, mr, running_mean, running_var, nbt)
+        G, C, _ = stats.shape
+        self._ck(self.lib.sg_bn_finalize(_ptr(stats), int(count), _ptr(mr), _ptr(running_mean), _ptr(running_var),
+                                         _ptr(nbt), dup_first, int(update_running), momentum, eps, G, C, self._st()))
+
+    def bn_eval_mr(self, running_mean, running_var, mr, eps=1e-5):
+        self._c(running_mean, running_var, mr)
+        self._ck(self.lib.sg_bn_eval_mr(_ptr(running_mean), _ptr(running_var), _ptr(mr), eps, running_mean.numel(), self._st()))
+
+    def bn_act(self, y, mr, gamma, beta, out, groups, act, residual=None):
+        self._c(y, mr, gamma, beta, out, residual)
+        C = y.shape[-1]
+        self._ck(self.lib.sg_bn_act(_ptr(y), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(out),
+                                    y.numel() // (C * groups), C, groups, act, self._dt_of(y), self._st()))
+
+    def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act):
+        self._c(da, a_out, y, mr, sums)
+        C = y.shape[-1]
+        self._ck(self.lib.sg_bn_bwd_reduce(_ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(sums),
+                                           y.numel() // (C * groups), C, groups, act, self._dt_of(y), self._st()))
+
+    def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0):
+        self._c(da, a_out, y, mr, gamma, sums, dy, inject)
+        C = y.shape[-1]
+        self._ck(self.lib.sg_bn_bwd_apply(_ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(sums),
+                                          _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C, groups,
+                                          act, self._dt_of(y), self._st()))
+
+    def bn_param_grad(self, sums, dgamma, dbeta):
+        self._c(sums, dgamma, dbeta)
+        G, C, _ = sums.shape
+        self._ck(self.lib.sg_bn_param_grad(_ptr(sums), _ptr(dgamma), _ptr(dbeta), G, C, self._st()))
+
+    def act_bwd(self, da, a_out, out, act):
+        self._c(da, a_out, out)
+        self._ck(self.lib.sg_act_bwd(_ptr(da), _ptr(a_out), _ptr(out), da.numel(), act, self._dt_of(da), self._st()))
+
+    def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act):
+        self._c(v, da, a_out, y, mr, tsums)
+        C = y.shape[-1]
+        self._ck(self.lib.sg_gp_bn_reduce(_ptr(v), _ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(tsums),
+                                          y.numel() // C, C, act, self._dt_of(y), self._st()))
+
+    def gp_bn_apply(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act):
+        self._c(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma)
+        C = y.shape[-1]
+        self._ck(self.lib.sg_gp_bn_apply(_ptr(v), _ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(sums),
+                                         _ptr(tsums), _ptr(w_out), _ptr(gy_out), _ptr(dgamma), y.numel() // C, C, act,
+                                         self._dt_of(y), self._st()))
+
+    # ---- dense
+    def linear_fwd(self, x, w, b, out, relu=False):
+        self._c(x, w, b, out)
+        N, K = x.shape
+        M = w.shape[0]
+        self._ck(self.lib.sg_linear_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), N, K, M, int(relu), self._st()))
+
+    def linear_bwd(self, x, w, dout, dw, db, dx, dx_acc=False, relu_out=None):
+        self._c(x, w, dout, dw, db, dx, relu_out)
+        N, K = x.shape
+        M = w.shape[0]
+        self._ck(self.lib.sg_linear_bwd(_ptr(x), _ptr(w), _ptr(dout), _ptr(relu_out), _ptr(dw), _ptr(db), _ptr(dx),
+                                        int(dx_acc), N, K, M, self._st()))
+
+    # ---- critic head
+    def head_prepare(self, wcr, bcr, wcs, bcs, A, Bv, c0):
+        self._c(wcr, bcr, wcs, bcs, A, Bv, c0)
+        K = wcr.shape[0]
+        Cx, Nd = A.shape[1], Bv.shape[0]
+        self._ck(self.lib.sg_head_prepare(_ptr(wcr), _ptr(bcr), _ptr(wcs), _ptr(bcs), _ptr(A), _ptr(Bv), _ptr(c0),
+                                          K, Cx, Nd, self._st()))
+
+    def head_fwd(self, a4, ce, A, Bv, c0, score):
+        self._c(a4, ce, A, Bv, c0, score)
+        N = a4.shape[0]
+        self._ck(self.lib.sg_head_fwd(_ptr(a4), _ptr(ce), _ptr(A), _ptr(Bv), _ptr(c0), _ptr(score), N,
+                                      a4.numel() // N, Bv.shape[0], self._dt_of(a4), self._st()))
+
+    def head_bwd_data(self, coef, A, da4):
+        self._c(coef, A, da4)
+        N = coef.shape[0]
+        self._ck(self.lib.sg_outer(_ptr(coef), _ptr(A), _ptr(da4), N, A.numel(), self._dt_of(da4), self._st()))
+
+    def head_bwd_reduce(self, coef, a4, dA):
+        self._c(coef, a4, dA)
+        N = coef.shape[0]
+        assert a4.numel() == N * dA.numel()
+        self._ck(self.lib.sg_wsum_rows(_ptr(coef), _ptr(a4), _ptr(dA), N, dA.numel(), self._dt_of(a4), self._st()))
+
+    def head_param_grads(self, dA, dBv, dc0, wcr, bcr, wcs, dwcr, dbcr, dwcs, dbcs):
+        self._c(dA, dBv, dc0, wcr, bcr, wcs, dwcr, dbcr, dwcs, dbcs)
+        K = wcr.shape[0]
+        self._ck(self.lib.sg_head_param_grads(_ptr(dA), _ptr(dBv), _ptr(dc0), _ptr(wcr), _ptr(bcr), _ptr(wcs),
+                                              _ptr(dwcr), _ptr(dbcr), _ptr(dwcs), _ptr(dbcs), K, dA.shape[1],
+                                              dBv.shape[0], self._st()))
+
+    # ---- conditioning augmentation
+    def ca_reparam(self, mu, sigma, eps, z, c_hat, cg):
+        self._c(mu, sigma, eps, z, c_hat, cg)
+        N, C = mu.shape
+        nz = (cg.numel() // N - C) if cg is not None else 0
+        self._ck(self.lib.sg_ca_reparam(_ptr(mu), _ptr(sigma), _ptr(eps), _ptr(z), _ptr(c_hat), _ptr(cg), N, C, nz,
+                                        self._dt_of(cg) if cg is not None else SG_F32, self._st()))
+
+    def ca_bwd_seed(self, dcg, eps, mu, sigma, kl_scale, dmu, dsigma):
+        self._c(dcg, eps, mu, sigma, dmu, dsigma)
+        N, C = mu.shape
+        ld = dcg.numel() // N if dcg is not None else 0
+        self._ck(self.lib.sg_ca_bwd_seed(_ptr(dcg), _ptr(eps), _ptr(mu), _ptr(sigma), float(kl_scale), _ptr(dmu),
+                                         _ptr(dsigma), N, C, ld, self._dt_of(dcg) if dcg is not None else SG_F32,
+                                         self._st()))
+
+    # ---- losses
+    def interp(self, real, fake, eps, out):
+        self._c(real, fake, eps, out)
+        N = real.shape[0]
+        self._ck(self.lib.sg_interp(_ptr(real), _ptr(fake), _ptr(eps), _ptr(out), N, real.numel() // N,
+                                    self._dt_of(real), self._st()))
+
+    def sample_sqnorm(self, g, out):
+        self._c(g, out)
+        N = g.shape[0]
+        self._ck(self.lib.sg_sample_sqnorm(_ptr(g), _ptr(out), N, g.numel() // N, self._dt_of(g), self._st()))
+
+    def gp_seed(self, g, sq, coef, v):
+        self._c(g, sq, v)
+        N = g.shape[0]
+        self._ck(self.lib.sg_gp_seed(_ptr(g), _ptr(sq), float(coef), _ptr(v), N, g.numel() // N, self._dt_of(g), self._st()))
+
+    def critic_loss(self, s_real, s_mis, s_fake, sq, lam, out):
+        self._c(s_real, s_mis, s_fake, sq, out)
+        self._ck(self.lib.sg_critic_loss(_ptr(s_real), _ptr(s_mis), _ptr(s_fake), _ptr(sq), float(lam), _ptr(out),
+                                         s_real.numel(), self._st()))
+
+    def gen_loss(self, s_fake, mu, sigma, out):
+        self._c(s_fake, mu, sigma, out)
+        N, C = mu.shape
+        self._ck(self.lib.sg_gen_loss(_ptr(s_fake), _ptr(mu), _ptr(sigma), _ptr(out), N, C, self._st()))
+
+    def scale_rows_add(self, x, scale, out, accumulate):
+        self._c(x, scale, out)
+        N = x.shape[0]
+        self._ck(self.lib.sg_scale_rows_add(_ptr(x), _ptr(scale), _ptr(out), int(accumulate), N, x.numel() // N,
+                                            self._dt_of(x), self._st()))
+
+    # ---- optimiser
+    def adam_step(self, p, g, m, v, hyper):
+        self._c(p, g, m, v, hyper)
+        self._ck(self.lib.sg_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(hyper), p.numel(), self._st()))

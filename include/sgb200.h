@@ -1,0 +1,161 @@
+/* sgb200.h -- C ABI of libsgb200.so: hand-written sm_100a CUDA kernels for the StackGAN
+ * training step of anishbasnet969/ImageGenerator.
+ *
+ * The reference has no FFI of its own (it is pure Python on torch.nn); every
+ * entry point below replaces the torch operator(s) the cited reference line executes.  A host
+ * program binds these with ctypes / cffi / dlopen (INTEGRATION.md shows the ctypes stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t (> 0) or SG_ERR_* (< 0) otherwise;
+ *     sg_last_error() returns a thread-local message for the last non-zero return.
+ *   - all buffers are caller-owned DEVICE pointers; nothing is allocated or freed across the ABI,
+ *     no host synchronisation happens inside, every call is asynchronous on `stream`
+ *     (a cudaStream_t passed as void*) and is CUDA-graph capturable.
+ *   - "T" tensors are activations/packed weights in the storage type selected by `dtype`
+ *     (SG_F32 or SG_BF16), laid out NHWC ([rows][C], channel fastest).  Parameters, gradients,
+ *     scores and statistics are fp32; statistic sums are fp64.
+ *   - a convolution *operator* is described in Conv2d orientation: weight [Co][Ci][k][k],
+ *     x [N][H][W][Ci] -> y [N][Ho][Wo][Co], stride s, padding p.  A ConvTranspose2d layer whose
+ *     weight is [Cin_t][Cout_t][k][k] is the SAME operator with Co=Cin_t, Ci=Cout_t run in its
+ *     data-gradient direction (sg_conv_dgrad), and vice versa.
+ *   - act codes: 0 none, 1 ReLU, 2 LeakyReLU(0.1), 3 Tanh.
+ */
+#ifndef SGB200_H
+#define SGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_F32 0
+#define SG_BF16 1
+
+#define SG_ACT_NONE 0
+#define SG_ACT_RELU 1
+#define SG_ACT_LRELU 2
+#define SG_ACT_TANH 3
+
+#define SG_ERR_BAD_ARG (-1)
+#define SG_ERR_UNSUPPORTED (-2)
+#define SG_ERR_NO_DEVICE (-3)
+
+/* ---- library / device probes ------------------------------------------------------------- */
+int sg_version(void);                       /* ABI version, currently 1 */
+const char* sg_last_error(void);
+/* 0 if the current device is sm_100 (B200); SG_ERR_NO_DEVICE otherwise.  Kernels are compiled
+ * for sm_100a only -- there is no other code path. */
+int sg_check_device(void);
+/* number of kernels launched through this library since load (all threads) */
+int64_t sg_launch_count(void);
+
+/* ---- memory helpers ------------------------------------------------------------------------ */
+int sg_zero(void* ptr, int64_t bytes, void* stream);
+int sg_fill_f32(float* ptr, float value, int64_t n, void* stream);
+
+/* ---- layout: the reference API is NCHW fp32 (e.g. generator_1.py:38-40 output) -------------- */
+int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dtype, void* stream);
+int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int dtype, void* stream);
+/* w [Co][Ci][k*k] fp32 -> pf [Co][k*k][Ci] and pd [Ci][k*k][Co] in T (either may be NULL) */
+int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream);
+
+/* ---- convolution operator (replaces nn.Conv2d / nn.ConvTranspose2d and their autograd:
+ *      generator_1.py:20,26  generator_2.py:30,46,55,71,87  discrminator_1.py:10,29
+ *      discriminator_2.py:9,44) ------------------------------------------------------------- */
+/* y = act(conv(x, W) + bias);  pf is the [Co][k][k][Ci] pack; bias may be NULL */
+int sg_conv_fprop(const void* x, const void* pf, const float* bias, void* y,
+                  int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p,
+                  int act, int dtype, void* stream);
+/* dx = act(conv_transpose(dy, W) + bias);  pd is the [Ci][k][k][Co] pack; bias ([Ci]) may be NULL */
+int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx,
+                  int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p,
+                  int act, int dtype, void* stream);
+/* dw[Co][Ci][k][k] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci] */
+int sg_conv_wgrad(const void* x, const void* dy, float* dw,
+                  int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p,
+                  int dtype, void* stream);
+/* out[C] (fp32) += column sums of x[rows][C]  (bias gradients) */
+int sg_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream);
+
+/* ---- BatchNorm2d, train and eval mode (replaces nn.BatchNorm2d: generator_1.py:34,
+ *      generator_2.py:38,79,95  discrminator_1.py:37  discriminator_2.py:52) ------------------ */
+/* stats[G][C][2] (fp64) += (sum, sum of squares) of y, rows split evenly into G groups */
+int sg_col_stats(const void* y, double* stats, int64_t rows_per_group, int C, int groups, int dtype, void* stream);
+/* mr[G][C][2] = (mean, 1/sqrt(var_biased+eps)); running stats EMA-updated once per group in group
+ * order, group 0 `dup_first` times; *nbt += dup_first + G - 1 */
+int sg_bn_finalize(const double* stats, int64_t count, float* mr, float* running_mean, float* running_var,
+                   int64_t* nbt, int dup_first, int update_running, float momentum, float eps,
+                   int groups, int C, void* stream);
+int sg_bn_eval_mr(const float* running_mean, const float* running_var, float* mr, float eps, int C, void* stream);
+/* out = act(gamma*(y-mean)*rstd + beta [+ residual]) */
+int sg_bn_act(const void* y, const float* mr, const float* gamma, const float* beta, const void* residual,
+              void* out, int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+/* sums[G][C][2] (fp64) = (sum dz, sum dz*xhat),  dz = da * act'(a_out) */
+int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const float* mr, double* sums,
+                     int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+/* dy = gamma*rstd/N*(N dz - S1 - xhat S2) [+ inject on the rows of group inject_group] */
+int sg_bn_bwd_apply(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
+                    const double* sums, const void* inject, int inject_group, void* dy,
+                    int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+/* dgamma += sum_g S2, dbeta += sum_g S1 */
+int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream);
+/* out = da * act'(a_out)   (LeakyReLU / ReLU / Tanh backward without BN) */
+int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act, int dtype, void* stream);
+
+/* ---- WGAN-GP second order through a train-mode BN (replaces autograd's double backward of
+ *      utils.py:15-21 under stage_1_train_fn.py:147) ------------------------------------------ */
+/* tsums[C][3] (fp64) = (sum v, sum v*xhat, sum v*dz) */
+int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
+                    double* tsums, int64_t rows, int C, int act, int dtype, void* stream);
+int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
+                   const float* gamma, const double* sums, const double* tsums, void* w_out, void* gy_out,
+                   float* dgamma, int64_t rows, int C, int act, int dtype, void* stream);
+
+/* ---- small dense layers, fp32 (replaces nn.Linear: con_augment.py:9-11, discrminator_1.py:16) - */
+/* out[N][M] = x[N][K] w[M][K]^T + b  (optional ReLU) */
+int sg_linear_fwd(const float* x, const float* w, const float* b, float* out, int N, int K, int M, int relu, void* stream);
+/* dout masked by relu_out>0 if given; dw += dout^T x; db += colsum(dout); dx (+)= dout w.  dw/db/dx may be NULL */
+int sg_linear_bwd(const float* x, const float* w, const float* dout, const float* relu_out,
+                  float* dw, float* db, float* dx, int dx_acc, int N, int K, int M, void* stream);
+
+/* ---- critic head: compress + replicate + concat + 1x1 conv + flatten + linear
+ *      (discrminator_1.py:43-52, discriminator_2.py:29-38) collapsed to score = <A,a4>+<Bv,ce>+c0 - */
+int sg_head_prepare(const float* wcr, const float* bcr, const float* wcs, const float* bcs,
+                    float* A, float* Bv, float* c0, int K, int Cx, int Nd, void* stream);
+int sg_head_fwd(const void* a4, const float* ce, const float* A, const float* Bv, const float* c0,
+                float* score, int N, int M, int Nd, int dtype, void* stream);
+/* out[n][m] = coef[n] * vec[m]   (out in T when out_dtype says so, else fp32) */
+int sg_outer(const float* coef, const float* vec, void* out, int N, int M, int out_dtype, void* stream);
+/* out[m] (fp32) += sum_n coef[n] * x[n][m] */
+int sg_wsum_rows(const float* coef, const void* x, float* out, int N, int M, int dtype, void* stream);
+int sg_head_param_grads(const float* dA, const float* dBv, const float* dc0, const float* wcr, const float* bcr,
+                        const float* wcs, float* dwcr, float* dbcr, float* dwcs, float* dbcs,
+                        int K, int Cx, int Nd, void* stream);
+
+/* ---- conditioning augmentation (con_augment.py:18-22; stage_1_train_fn.py:120-122,156-159) ---- */
+/* c_hat = mu + sigma*eps; cg[N][C+nz] (T) = [c_hat, z] when cg != NULL (z may be NULL) */
+int sg_ca_reparam(const float* mu, const float* sigma, const float* eps, const float* z, float* c_hat,
+                  void* cg, int N, int C, int nz, int dtype, void* stream);
+/* dmu = dc + kl*(-2mu); dsigma = dc*eps + kl*(2/sigma-2sigma); dc = first C of each dcg row (ld = row length) */
+int sg_ca_bwd_seed(const void* dcg, const float* eps, const float* mu, const float* sigma, float kl_scale,
+                   float* dmu, float* dsigma, int N, int C, int ld, int dtype, void* stream);
+
+/* ---- losses (utils.py:8-26; stage_1_train_fn.py:134-144,154-159) ------------------------------ */
+int sg_interp(const void* real, const void* fake, const float* eps, void* out, int N, int64_t per_sample, int dtype, void* stream);
+int sg_sample_sqnorm(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream);
+int sg_gp_seed(const void* g, const float* sq, float coef, void* v, int N, int64_t per_sample, int dtype, void* stream);
+int sg_critic_loss(const float* s_real, const float* s_mis, const float* s_fake, const float* sq, float lam,
+                   float* out2, int N, void* stream);
+int sg_gen_loss(const float* s_fake, const float* mu, const float* sigma, float* out2, int N, int C, void* stream);
+/* out[n,...] (+)= scale[n] * x[n,...] */
+int sg_scale_rows_add(const void* x, const float* scale, void* out, int accumulate, int N, int64_t per_sample, int dtype, void* stream);
+
+/* ---- Adam (train.py:92-102; torch.optim.Adam semantics, bias-corrected, eps outside sqrt/bc2) -- */
+/* hyper (device) = [lr, beta1, beta2, eps, step]; the kernel increments step first */
+int sg_adam_step(float* p, const float* g, float* m, float* v, float* hyper, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB200_H */

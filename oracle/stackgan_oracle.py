@@ -261,9 +261,10 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, world_grads=
     perm [B] (the randperm of :109), z [5,B,100] (:121), eps_ca [5,B,128]
     (con_augment.py:20), eps_gp [5,B] (utils.py:10).
     Returns losses and the gradients each optimizer saw at its step."""
-    out = {"loss_critic": [], "critic_grads": []}
+    out = {"loss_critic": [], "critic_grads": [], "critic_before": [], "scores": []}
     tem_mis = tem[perm]                                        # :108-111, :127-129
     for it in range(N_CRITIC):
+        out["critic_before"].append(_snap(d1))
         c_hat, mu, sigma = ca_forward(ca, tem, eps_ca[it])      # :120
         fake = g1_forward(g1, torch.cat((c_hat, z[it]), dim=1))  # :121-123 (not detached)
         s_real = d1_forward(d1, real, tem).view(-1)             # :125
@@ -275,14 +276,19 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, world_grads=
         loss_c.backward(retain_graph=True)                      # :147
         out["critic_grads"].append(tr["d1"].grads())
         out["loss_critic"].append(loss_c.detach().clone())
+        out["scores"].append(dict(s_real=s_real.detach().clone(), s_mis=s_mis.detach().clone(),
+                                  s_fake=s_fake.detach().clone(), gp=gp.detach().clone(),
+                                  fake=fake.detach().clone()))
         if it == 0:
             out["first"] = dict(fake=fake.detach().clone(), s_real=s_real.detach().clone(),
                                 s_mis=s_mis.detach().clone(), s_fake=s_fake.detach().clone(),
                                 gp=gp.detach().clone(), c_hat=c_hat.detach().clone(),
                                 mu=mu.detach().clone(), sigma=sigma.detach().clone())
         tr["d1"].opt.step()                                     # :149
+    out["critic_before"].append(_snap(d1))
     s = d1_forward(d1, fake, tem).view(-1)                      # :154
     lossG = -torch.mean(s) + kl_term(mu, sigma)                 # :155-159
+    out["s_gen"] = s.detach().clone()
     tr["g1"].opt.zero_grad()                                    # :161-164
     tr["ca"].opt.zero_grad()
     tem.grad = None

@@ -1,0 +1,256 @@
+"""Every C-ABI kernel against the torch statement of the same name in tests/emu_ops.py (fp64),
+in both storage modes.  Runs on the B200 box: ``pytest -m gpu``."""
+import pytest
+import torch
+
+from emu_ops import EmuOps, ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp32", "bf16"]
+TOL = {"fp32": dict(rtol=1e-4, atol=1e-5), "bf16": dict(rtol=2e-2, atol=1e-3)}
+
+
+class T:      # activation-typed tensor (storage type of the mode)
+    def __init__(self, t): self.t = t
+class F:      # fp32 tensor
+    def __init__(self, t): self.t = t
+class D:      # fp64 tensor
+    def __init__(self, t): self.t = t
+class I64:
+    def __init__(self, t): self.t = t
+
+
+def _ops(mode):
+    from imagegenerator_b200.ops import CudaOps
+    return CudaOps(mode)
+
+
+def run_pair(mode, name, args, outs, kwargs=None, scale_atol=True, tol=None):
+    """Call ops.<name>(*args) on the emulator (fp64, CPU) and on CUDA; compare tensors at positions ``outs``."""
+    kwargs = kwargs or {}
+    ops = _ops(mode)
+    emu = EmuOps(torch.float64)
+    sd = ops.act_dtype
+
+    def conv(a, side):
+        if isinstance(a, T):
+            q = a.t.to(sd)                       # both sides see the storage-rounded values
+            return q.double().clone() if side == "emu" else q.cuda().contiguous()
+        if isinstance(a, F):
+            return a.t.float().double().clone() if side == "emu" else a.t.float().cuda().contiguous()
+        if isinstance(a, D):
+            return a.t.double().clone() if side == "emu" else a.t.double().cuda().contiguous()
+        if isinstance(a, I64):
+            return a.t.clone() if side == "emu" else a.t.cuda()
+        return a
+
+    ea = [conv(a, "emu") for a in args]
+    ca = [conv(a, "cuda") for a in args]
+    ek = {k: conv(v, "emu") for k, v in kwargs.items()}
+    ck = {k: conv(v, "cuda") for k, v in kwargs.items()}
+    getattr(emu, name)(*ea, **ek)
+    getattr(ops, name)(*ca, **ck)
+    torch.cuda.synchronize()
+    t = dict(TOL[mode])
+    if tol:
+        t.update(tol)
+    for i in outs:
+        ref, got = ea[i].double(), ca[i].double().cpu()
+        atol = t["atol"] * (max(ref.abs().max().item(), 1e-30) if scale_atol else 1.0)
+        if not torch.allclose(got, ref, rtol=t["rtol"], atol=atol):
+            err = (got - ref).abs().max().item()
+            raise AssertionError(f"{name}[{mode}] arg {i}: max abs err {err:.3e}, ref max {ref.abs().max().item():.3e}")
+    return ea, ca
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g) * scale
+
+
+CONV_CASES = [
+    # N, H, Ci, Co, k, s, p
+    (2, 64, 3, 64, 4, 2, 1),        # critic ds0
+    (2, 32, 64, 128, 4, 2, 1),      # critic ds2
+    (3, 8, 256, 512, 4, 2, 1),      # critic ds4
+    (2, 16, 48, 96, 4, 2, 1),       # G1 up2 operator (Co=convT in, Ci=convT out)
+    (2, 64, 3, 24, 4, 2, 1),        # G1 up4 operator
+    (5, 4, 192, 228, 4, 1, 0),      # G1 up0 operator (1x1 <-> 4x4)
+    (2, 16, 40, 24, 3, 1, 1),       # residual-block style 3x3
+    (1, 256, 3, 16, 4, 2, 1),       # stage-II critic ds0
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True), (ACT_TANH, True)])
+def test_conv_fprop(mode, case, act, use_bias):
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    x, w = rnd(N, H, H, Ci), rnd(Co, Ci, k, k, scale=(Ci * k * k) ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    bias = F(rnd(Co)) if use_bias else None
+    run_pair(mode, "conv_fprop", [T(x), T(pf), bias, T(torch.zeros(N, Ho, Ho, Co)), k, s, p], [3], dict(act=act))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_TANH, True)])
+def test_conv_dgrad(mode, case, act, use_bias):
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    dy, w = rnd(N, Ho, Ho, Co), rnd(Co, Ci, k, k, scale=(Co * k * k / (s * s)) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    bias = F(rnd(Ci)) if use_bias else None
+    run_pair(mode, "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci)), k, s, p], [3], dict(act=act))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(mode, case):
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    x, dy = rnd(N, H, H, Ci), rnd(N, Ho, Ho, Co, scale=(N * Ho * Ho) ** -0.5)
+    dw0 = rnd(Co, Ci, k, k, scale=0.1)          # accumulate semantics
+    run_pair(mode, "conv_wgrad", [T(x), T(dy), F(dw0), k, s, p], [2], tol=dict(rtol=2e-3) if mode == "fp32" else None)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_layout_and_pack(mode):
+    x = rnd(3, 5, 8, 12)
+    run_pair(mode, "nchw_to_nhwc", [F(x), T(torch.zeros(3, 8, 12, 5))], [1])
+    run_pair(mode, "nhwc_to_nchw", [T(rnd(3, 8, 12, 5)), F(torch.zeros(3, 5, 8, 12))], [1])
+    w = rnd(24, 10, 4, 4)
+    run_pair(mode, "pack_weight", [F(w), T(torch.zeros(24, 4, 4, 10)), T(torch.zeros(10, 4, 4, 24))], [1, 2])
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("C,rows,G", [(3, 4096, 1), (24, 1024, 2), (128, 512, 3), (512, 64, 3), (640, 256, 1)])
+def test_bn_chain(mode, C, rows, G):
+    y = rnd(G * rows, C) * 2 + 0.5
+    stats = torch.zeros(G, C, 2, dtype=torch.float64)
+    ea, ca = run_pair(mode, "col_stats", [T(y.reshape(G, rows, 1, C)), D(stats), G], [1], tol=dict(rtol=1e-5, atol=1e-6))
+    stats = ea[1]
+    rm, rv, nbt = rnd(C) * 0.1, torch.rand(C) + 0.5, torch.tensor(3)
+    mr = torch.zeros(G, C, 2)
+    ea, ca = run_pair(mode, "bn_finalize", [D(stats), rows, F(mr), F(rm), F(rv), I64(nbt), 2, True], [2, 3, 4],
+                      tol=dict(rtol=1e-4, atol=1e-5))
+    assert int(ca[5]) == 3 + G + 1
+    mr = ea[2].float()
+    gamma, beta = rnd(C) * 0.5 + 1, rnd(C) * 0.2
+    y4 = y.reshape(G * rows, 1, 1, C)
+    res = rnd(G * rows, 1, 1, C)
+    for act, r in ((ACT_LRELU, None), (ACT_RELU, res), (ACT_NONE, None)):
+        out = torch.zeros_like(y4)
+        ea, _ = run_pair(mode, "bn_act", [T(y4), F(mr), F(gamma), F(beta), T(out), G, act], [4],
+                         dict(residual=T(r)) if r is not None else None)
+    a_out = ea[4] if False else None
+    # backward pieces use a consistent a_out
+    emu = EmuOps(torch.float64)
+    a_out = torch.zeros_like(y4).double()
+    sd = torch.bfloat16 if mode == "bf16" else torch.float32
+    emu.bn_act(y4.to(sd).double(), mr.double(), gamma.double(), beta.double(), a_out, G, ACT_LRELU)
+    a_out = a_out.float()
+    da = rnd(G * rows, 1, 1, C, seed=5)
+    sums = torch.zeros(G, C, 2, dtype=torch.float64)
+    ea, _ = run_pair(mode, "bn_bwd_reduce", [T(da), T(a_out), T(y4), F(mr), D(sums), G, ACT_LRELU], [4],
+                     tol=dict(rtol=1e-3, atol=1e-4))
+    sums = ea[4]
+    inj = rnd(rows, 1, 1, C, seed=9)
+    run_pair(mode, "bn_bwd_apply", [T(da), T(a_out), T(y4), F(mr), F(gamma), D(sums), T(torch.zeros_like(y4)), G, ACT_LRELU],
+             [6], dict(inject=T(inj), inject_group=G - 1))
+    run_pair(mode, "bn_param_grad", [D(sums), F(rnd(C)), F(rnd(C))], [1, 2], tol=dict(rtol=1e-4, atol=1e-5))
+    run_pair(mode, "act_bwd", [T(da), T(a_out), T(torch.zeros_like(y4)), ACT_LRELU], [2])
+    run_pair(mode, "act_bwd", [T(da), T(torch.tanh(y4)), T(torch.zeros_like(y4)), ACT_TANH], [2])
+    run_pair(mode, "colsum", [T(y4), F(rnd(C))], [1], tol=dict(rtol=1e-3, atol=1e-4))
+    if G == 1:
+        v = rnd(rows, 1, 1, C, seed=11)
+        ts = torch.zeros(C, 3, dtype=torch.float64)
+        ea, _ = run_pair(mode, "gp_bn_reduce", [T(v), T(da), T(a_out), T(y4), F(mr), D(ts), ACT_LRELU], [5],
+                         tol=dict(rtol=1e-3, atol=1e-4))
+        ts = ea[5]
+        run_pair(mode, "gp_bn_apply", [T(v), T(da), T(a_out), T(y4), F(mr), F(gamma), D(sums), D(ts),
+                                       T(torch.zeros_like(y4)), T(torch.zeros_like(y4)), F(rnd(C)), ACT_LRELU], [8, 9, 10],
+                 tol=dict(rtol=3e-2, atol=2e-3) if mode == "bf16" else dict(rtol=1e-3, atol=1e-4))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_bn_eval_mr(mode):
+    C = 96
+    run_pair(mode, "bn_eval_mr", [F(rnd(C)), F(torch.rand(C) + 0.1), F(torch.zeros(1, C, 2))], [2],
+             tol=dict(rtol=1e-5, atol=1e-6))
+
+
+@pytest.mark.parametrize("mode", ["fp32"])
+def test_linear(mode):
+    N, K, M = 9, 512, 256
+    x, w, b = rnd(N, K), rnd(M, K, scale=K ** -0.5), rnd(M)
+    ea, _ = run_pair(mode, "linear_fwd", [F(x), F(w), F(b), F(torch.zeros(N, M))], [3], dict(relu=True))
+    h = ea[3].float()
+    dout = rnd(N, M, seed=3)
+    run_pair(mode, "linear_bwd", [F(x), F(w), F(dout), F(rnd(M, K)), F(rnd(M)), F(rnd(N, K))], [3, 4, 5],
+             dict(dx_acc=True, relu_out=F(h)))
+    run_pair(mode, "linear_bwd", [F(x), F(w), F(dout), None, None, F(rnd(N, K))], [5], dict(dx_acc=False))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("K,Cx,Nd", [(128, 512, 128), (160, 512, 128)])
+def test_head(mode, K, Cx, Nd):
+    N = 6
+    wcr, bcr = rnd(K, Cx + Nd, 1, 1, scale=0.04), rnd(K, scale=0.04)
+    wcs, bcs = rnd(1, K * 16, scale=0.02), rnd(1, scale=0.02)
+    ea, _ = run_pair(mode, "head_prepare", [F(wcr), F(bcr), F(wcs), F(bcs), F(torch.zeros(16, Cx)), F(torch.zeros(Nd)),
+                                            F(torch.zeros(1))], [4, 5, 6], tol=dict(rtol=1e-4, atol=1e-5))
+    A, Bv, c0 = ea[4].float(), ea[5].float(), ea[6].float()
+    a4, ce = rnd(N, 4, 4, Cx), rnd(N, Nd)
+    run_pair(mode, "head_fwd", [T(a4), F(ce), F(A), F(Bv), F(c0), F(torch.zeros(N))], [5],
+             tol=dict(rtol=1e-3, atol=1e-4))
+    coef = rnd(N)
+    coef[2] = 0.0
+    run_pair(mode, "head_bwd_data", [F(coef), F(A), T(torch.zeros(N, 4, 4, Cx))], [2])
+    run_pair(mode, "head_bwd_data", [F(coef), F(Bv), F(torch.zeros(N, Nd))], [2])
+    run_pair(mode, "head_bwd_reduce", [F(coef), T(a4), F(rnd(16, Cx))], [2], tol=dict(rtol=1e-3, atol=1e-4))
+    run_pair(mode, "head_param_grads", [F(rnd(16, Cx)), F(rnd(Nd)), F(rnd(1)), F(wcr), F(bcr), F(wcs),
+                                        F(torch.zeros(K, Cx + Nd, 1, 1)), F(torch.zeros(K)), F(torch.zeros(1, K * 16)),
+                                        F(torch.zeros(1))], [6, 7, 8, 9], tol=dict(rtol=1e-3, atol=1e-4))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_ca_and_losses(mode):
+    N, C, nz = 7, 128, 100
+    mu, sigma, eps, z = rnd(N, C), rnd(N, C, seed=1), rnd(N, C, seed=2), rnd(N, nz)
+    run_pair(mode, "ca_reparam", [F(mu), F(sigma), F(eps), F(z), F(torch.zeros(N, C)), T(torch.zeros(N, 1, 1, C + nz))], [4, 5])
+    dcg = rnd(N, 1, 1, C + nz, seed=4)
+    run_pair(mode, "ca_bwd_seed", [T(dcg), F(eps), F(mu), F(sigma), 1.0, F(torch.zeros(N, C)), F(torch.zeros(N, C))], [5, 6],
+             tol=dict(rtol=1e-4, atol=1e-6))
+    real, fake = rnd(N, 8, 8, 3), rnd(N, 8, 8, 3, seed=3)
+    e = torch.rand(N)
+    run_pair(mode, "interp", [T(real), T(fake), F(e), T(torch.zeros(N, 8, 8, 3))], [3])
+    g = rnd(N, 64, 64, 3, scale=0.02)
+    ea, _ = run_pair(mode, "sample_sqnorm", [T(g), F(torch.zeros(N))], [1], tol=dict(rtol=1e-4, atol=1e-6))
+    sq = ea[1].float()
+    run_pair(mode, "gp_seed", [T(g), F(sq), 2.5, T(torch.zeros_like(g))], [3])
+    sr, sm, sf = rnd(N), rnd(N, seed=1), rnd(N, seed=2)
+    run_pair(mode, "critic_loss", [F(sr), F(sm), F(sf), F(sq), 10.0, F(torch.zeros(2))], [5], tol=dict(rtol=1e-5, atol=1e-6))
+    run_pair(mode, "gen_loss", [F(sf), F(mu), F(sigma), F(torch.zeros(2))], [3], tol=dict(rtol=1e-5, atol=1e-6))
+    run_pair(mode, "scale_rows_add", [T(real), F(e), T(fake), True], [2])
+
+
+def test_adam_matches_torch():
+    from imagegenerator_b200.ops import CudaOps
+    ops = CudaOps("fp32")
+    n = 4096 + 8
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0], device="cuda")
+    for step in range(5):
+        g = torch.randn(n, device="cuda") * (0.1 ** step)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, hyper)
+    torch.cuda.synchronize()
+    assert float(hyper[4]) == 5
+    assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
