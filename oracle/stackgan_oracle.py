@@ -253,7 +253,15 @@ def _snap(p):
 
 
 # --------------------------------------------------------------------------- Stage-I outer step
-def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, world_grads=None):
+def _force(p, snap):
+    """Overwrite a parameter dict in place with a snapshot (any dtype) -- used to re-synchronise
+    a lower-precision run with the fp64 trajectory ("teacher forcing") in the parity tests."""
+    with torch.no_grad():
+        for k, v in snap.items():
+            p[k].copy_(v.to(p[k].dtype))
+
+
+def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None):
     """One outer step of stage_1_train_fn.py:93-196 with synthetic text embeddings.
 
     ca/d1/g1: parameter dicts; tr = dict(ca=Trainer, d1=Trainer, g1=Trainer);
@@ -264,6 +272,8 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, world_grads=
     out = {"loss_critic": [], "critic_grads": [], "critic_before": [], "scores": []}
     tem_mis = tem[perm]                                        # :108-111, :127-129
     for it in range(N_CRITIC):
+        if force is not None:
+            _force(d1, force[it])
         out["critic_before"].append(_snap(d1))
         c_hat, mu, sigma = ca_forward(ca, tem, eps_ca[it])      # :120
         fake = g1_forward(g1, torch.cat((c_hat, z[it]), dim=1))  # :121-123 (not detached)
@@ -285,6 +295,8 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, world_grads=
                                 gp=gp.detach().clone(), c_hat=c_hat.detach().clone(),
                                 mu=mu.detach().clone(), sigma=sigma.detach().clone())
         tr["d1"].opt.step()                                     # :149
+    if force is not None:
+        _force(d1, force[N_CRITIC])
     out["critic_before"].append(_snap(d1))
     s = d1_forward(d1, fake, tem).view(-1)                      # :154
     lossG = -torch.mean(s) + kl_term(mu, sigma)                 # :155-159

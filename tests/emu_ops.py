@@ -83,20 +83,21 @@ class EmuOps:
 
     # ---- convolutions (Conv2d-layout semantics; ConvTranspose2d layers use them mirrored)
     def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE):
-        w = pf.permute(0, 3, 1, 2).to(x.dtype)                      # [Co,Ci,kh,kw]
-        out = F.conv2d(nchw(x), w, None if bias is None else bias.to(x.dtype), s, p)
+        # arithmetic is always fp64; only STORAGE follows the emulated mode (ideal-rounding model)
+        w = pf.permute(0, 3, 1, 2).double()                         # [Co,Ci,kh,kw]
+        out = F.conv2d(nchw(x).double(), w, None if bias is None else bias.double(), s, p)
         y.copy_(nhwc(_act(out, act)).to(y.dtype))
 
     def conv_dgrad(self, dy, pd, bias, dx, k, s, p, act=ACT_NONE):
-        w = pd.permute(3, 0, 1, 2).to(dy.dtype)                     # [Co,Ci,kh,kw] (= convT weight [in,out,kh,kw])
-        out = F.conv_transpose2d(nchw(dy), w, None if bias is None else bias.to(dy.dtype), s, p)
+        w = pd.permute(3, 0, 1, 2).double()                         # [Co,Ci,kh,kw] (= convT weight [in,out,kh,kw])
+        out = F.conv_transpose2d(nchw(dy).double(), w, None if bias is None else bias.double(), s, p)
         assert out.shape[2] == dx.shape[1], (out.shape, dx.shape)
         dx.copy_(nhwc(_act(out, act)).to(dx.dtype))
 
     def conv_wgrad(self, x, dy, dw, k, s, p):
         """dw[Co,Ci,kh,kw] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]."""
-        g = torch.nn.grad.conv2d_weight(nchw(x).to(dw.dtype), dw.shape, nchw(dy).to(dw.dtype), stride=s, padding=p)
-        dw.add_(g)
+        g = torch.nn.grad.conv2d_weight(nchw(x).double(), dw.shape, nchw(dy).double(), stride=s, padding=p)
+        dw.add_(g.to(dw.dtype))
 
     def colsum(self, x, out):
         """out[C] (fp32) += sum over all leading dims of x[..., C]."""
@@ -132,15 +133,16 @@ class EmuOps:
 
     def _xhat(self, y, mr, groups):
         C = y.shape[-1]
-        v = y.reshape(groups, -1, C).to(mr.dtype)
+        v = y.reshape(groups, -1, C).double()
+        mr = mr.double()
         return (v - mr[:, None, :, 0]) * mr[:, None, :, 1]
 
     def bn_act(self, y, mr, gamma, beta, out, groups, act, residual=None):
         xh = self._xhat(y, mr, groups)
-        z = xh * gamma.to(mr.dtype) + beta.to(mr.dtype)
+        z = xh * gamma.double() + beta.double()
         z = z.reshape(y.shape)
         if residual is not None:
-            z = z + residual.to(z.dtype)
+            z = z + residual.double()
         out.copy_(_act(z, act).to(out.dtype))
 
     def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act):
@@ -154,11 +156,11 @@ class EmuOps:
     def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0):
         """dy = gamma*rstd/N * (N dz - S1 - xhat S2)  [+ inject on rows of group inject_group]."""
         C = y.shape[-1]
-        ft = mr.dtype
+        ft = torch.float64
         dz = (da.to(ft) * _mask(a_out, act).to(ft)).reshape(groups, -1, C)
         n = dz.shape[1]
         xh = self._xhat(y, mr, groups)
-        a = gamma.to(ft)[None, None, :] * mr[:, None, :, 1] / n
+        a = gamma.to(ft)[None, None, :] * mr.to(ft)[:, None, :, 1] / n
         out = a * (n * dz - sums[:, None, :, 0].to(ft) - xh * sums[:, None, :, 1].to(ft))
         if inject is not None:
             out[inject_group] += inject.reshape(-1, C).to(ft)
@@ -211,71 +213,73 @@ class EmuOps:
 
     # ---- small dense layers (fp32)
     def linear_fwd(self, x, w, b, out, relu=False):
-        o = F.linear(x, w, b)
-        out.copy_(F.relu(o) if relu else o)
+        o = F.linear(x.double(), w.double(), None if b is None else b.double())
+        out.copy_((F.relu(o) if relu else o).to(out.dtype))
 
     def linear_bwd(self, x, w, dout, dw, db, dx, dx_acc=False, relu_out=None):
         """dw += dout^T x ; db += sum dout ; dx (may be None) (+)= dout w.  If relu_out is given,
         dout is first masked by relu_out > 0."""
+        dout, x, w = dout.double(), x.double(), w.double()
         if relu_out is not None:
             dout = dout * (relu_out > 0).to(dout.dtype)
         if dw is not None:
-            dw.add_(dout.t() @ x)
+            dw.add_((dout.t() @ x).to(dw.dtype))
         if db is not None:
-            db.add_(dout.sum(0))
+            db.add_(dout.sum(0).to(db.dtype))
         if dx is not None:
             if dx_acc:
-                dx.add_(dout @ w)
+                dx.add_((dout @ w).to(dx.dtype))
             else:
-                dx.copy_(dout @ w)
+                dx.copy_((dout @ w).to(dx.dtype))
 
     # ---- critic head (text replicate + concat + 1x1 conv + linear collapse into A, Bv, c0)
     def head_prepare(self, wcr, bcr, wcs, bcs, A, Bv, c0):
         """score = <A, a4> + <Bv, ce> + c0 with A[hw,c] = sum_k wcs[k,hw] wcr[k,c] (c < 512),
         Bv[j] = sum_k (sum_hw wcs[k,hw]) wcr[k,512+j], c0 = sum_k bcr[k] sum_hw wcs[k,hw] + bcs."""
         K = wcr.shape[0]
-        ws = wcs.reshape(K, 16)
-        wr = wcr.reshape(K, -1)
+        ws = wcs.reshape(K, 16).double()
+        wr = wcr.reshape(K, -1).double()
         nx = A.shape[1]
-        A.copy_(ws.t() @ wr[:, :nx])
+        A.copy_((ws.t() @ wr[:, :nx]).to(A.dtype))
         sw = ws.sum(1)
-        Bv.copy_(sw @ wr[:, nx:])
-        c0.copy_((bcr * sw).sum().reshape(1) + bcs)
+        Bv.copy_((sw @ wr[:, nx:]).to(Bv.dtype))
+        c0.copy_(((bcr.double() * sw).sum().reshape(1) + bcs.double()).to(c0.dtype))
 
     def head_fwd(self, a4, ce, A, Bv, c0, score):
         n = a4.shape[0]
-        s = (a4.reshape(n, -1).to(A.dtype) * A.reshape(1, -1)).sum(1) + ce @ Bv + c0
-        score.copy_(s)
+        s = (a4.reshape(n, -1).double() * A.double().reshape(1, -1)).sum(1) + ce.double() @ Bv.double() + c0.double()
+        score.copy_(s.to(score.dtype))
 
     def head_bwd_data(self, coef, A, da4):
         """da4[n] = coef[n] * A."""
-        da4.copy_((coef[:, None, None] * A[None]).reshape(da4.shape).to(da4.dtype))
+        da4.copy_((coef.double()[:, None, None] * A.double()[None]).reshape(da4.shape).to(da4.dtype))
 
     def head_bwd_reduce(self, coef, a4, dA):
         """dA[hw,c] += sum_n coef[n] a4[n,hw,c]."""
         n = a4.shape[0]
-        dA.add_((coef[:, None].to(dA.dtype) * a4.reshape(n, -1).to(dA.dtype)).sum(0).reshape(dA.shape))
+        dA.add_((coef[:, None].double() * a4.reshape(n, -1).double()).sum(0).reshape(dA.shape).to(dA.dtype))
 
     def head_param_grads(self, dA, dBv, dc0, wcr, bcr, wcs, dwcr, dbcr, dwcs, dbcs):
         K = wcr.shape[0]
-        ws = wcs.reshape(K, 16)
-        wr = wcr.reshape(K, -1)
+        ws = wcs.reshape(K, 16).double()
+        wr = wcr.reshape(K, -1).double()
+        dA, dBv, dc0, bcr = dA.double(), dBv.double(), dc0.double(), bcr.double()
         nx = dA.shape[1]
         sw = ws.sum(1)
         g = torch.zeros_like(wr)
         g[:, :nx] = ws @ dA
         g[:, nx:] = sw[:, None] * dBv[None, :]
-        dwcr.add_(g.reshape(dwcr.shape))
-        dbcr.add_(sw * dc0)
+        dwcr.add_(g.reshape(dwcr.shape).to(dwcr.dtype))
+        dbcr.add_((sw * dc0).to(dbcr.dtype))
         gs = wr[:, :nx] @ dA.t() + (wr[:, nx:] @ dBv)[:, None] + (bcr * dc0)[:, None]
-        dwcs.add_(gs.reshape(dwcs.shape))
-        dbcs.add_(dc0)
+        dwcs.add_(gs.reshape(dwcs.shape).to(dwcs.dtype))
+        dbcs.add_(dc0.to(dbcs.dtype))
 
     # ---- conditioning augmentation pieces
     def ca_reparam(self, mu, sigma, eps, z, c_hat, cg):
         """c_hat = mu + sigma*eps (fp32); cg[N,1,1,128+nz] (T) = [c_hat, z] when cg is given."""
-        c = mu + sigma * eps
-        c_hat.copy_(c)
+        c = mu.double() + sigma.double() * eps.double()
+        c_hat.copy_(c.to(c_hat.dtype))
         if cg is not None:
             n = c.shape[0]
             cg.reshape(n, -1)[:, :c.shape[1]] = c.to(cg.dtype)
@@ -286,9 +290,10 @@ class EmuOps:
         """dmu = dc + kl_scale*(-2 mu); dsigma = dc*eps + kl_scale*(2/sigma - 2 sigma);
         dc = first 128 columns of dcg (T) or 0 when dcg is None."""
         nc = mu.shape[1]
-        dc = 0 if dcg is None else dcg.reshape(mu.shape[0], -1)[:, :nc].to(mu.dtype)
-        dmu.copy_(dc + kl_scale * (-2 * mu))
-        dsigma.copy_(dc * eps + kl_scale * (2 / sigma - 2 * sigma))
+        mu, sigma, eps = mu.double(), sigma.double(), eps.double()
+        dc = 0 if dcg is None else dcg.reshape(mu.shape[0], -1)[:, :nc].double()
+        dmu.copy_((dc + kl_scale * (-2 * mu)).to(dmu.dtype))
+        dsigma.copy_((dc * eps + kl_scale * (2 / sigma - 2 * sigma)).to(dsigma.dtype))
 
     # ---- losses / gradient penalty
     def interp(self, real, fake, eps, out):
@@ -306,14 +311,15 @@ class EmuOps:
 
     def critic_loss(self, s_real, s_mis, s_fake, sq, lam, out):
         """out[0] = mean(cat(mis,fake)) - mean(real) + lam*gp ; out[1] = gp."""
-        gp = ((torch.sqrt(sq) - 1) ** 2).mean()
-        out[0] = torch.cat((s_mis, s_fake)).mean() - s_real.mean() + lam * gp
+        gp = ((torch.sqrt(sq.double()) - 1) ** 2).mean()
+        out[0] = torch.cat((s_mis, s_fake)).double().mean() - s_real.double().mean() + lam * gp
         out[1] = gp
 
     def gen_loss(self, s_fake, mu, sigma, out):
         """out[0] = -mean(s) + sum(1 + log sigma^2 - mu^2 - sigma^2) ; out[1] = kl term."""
+        mu, sigma = mu.double(), sigma.double()
         kl = (1 + torch.log(sigma * sigma) - mu * mu - sigma * sigma).sum()
-        out[0] = -s_fake.mean() + kl
+        out[0] = -s_fake.double().mean() + kl
         out[1] = kl
 
     # ---- optimiser
