@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- StackGAN Stage-I train step (BASELINE.json configs[1]: 64x64, batch 128/GPU, bf16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32]
+
+A "step" is one reference outer step (stage_1_train_fn.py:116-172): five critic updates (WGAN-GP with
+matching-aware negatives, double backward through the critic) + one generator/conditioning-
+augmentation update, Adam included, on synthetic text embeddings and images.  One JSON line on rank 0.
+
+  value   images/s, whole job, inputs resident in HBM, timed with CUDA events per step (L2 flushed
+          between steps, flush not timed), max over ranks
+  e2e     the same metric through the public ``train_1`` call with HOST (pinned) batches: H2D copies of
+          images / embeddings / noise and the D2H loss read are inside the timed region
+  roofline  dominant kernel timed live with CUDA events on its launch stream
+  cpu_baseline  the oracle (torch-CPU restatement of the reference; /root/reference does not exist on
+          the GPU box) on a bounded sample: B=16 fp32 outer steps
+
+``--impl reference`` times that CPU path alone with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_D1, F_G1 = 0.21037e9, 0.03207e9          # forward FLOPs / image
+# FLOPs this implementation must execute per image and outer step (DESIGN.md "Work per step"):
+# critic iteration = G fwd + 3 trunk fwd (real, fake, interp; the mismatched call reuses real's
+# features) + 3 trunk bwd (dgrad+wgrad = 2 F_D each) + GP first order (1 F_D) + GP second order
+# (fprop chain + wgrad = 2 F_D)  = F_G + 12 F_D ;  G step = F_D fwd + F_D dgrad + 2 F_G bwd
+FLOPS_PER_IMG = 5 * (F_G1 + 12 * F_D1) + (2 * F_D1 + 2 * F_G1)
+FLOPS_PER_IMG_REFERENCE_NECESSARY = 77 * F_D1 + 7 * F_G1
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_modules(seed=42):
+    from imagegenerator_b200.con_augment import ConditioningAugmentation
+    from imagegenerator_b200.discrminator_1 import StageIDiscriminator
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    torch.manual_seed(seed)                                   # train.py:66
+    return ConditioningAugmentation(512, 256, 128), StageIDiscriminator(512, 128), StageIGenerator(128, 100)
+
+
+def synthetic_host_batches(n, B, seed):
+    """Pinned host batches shaped like the reference loader's (dict, real_img_64) items."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        real = torch.randn(B, 3, 64, 64, generator=g).clamp_(-1, 1).pin_memory()
+        idx = torch.arange(B)
+        out.append(({"idx": idx}, real))
+    return out
+
+
+class TableEncoder(torch.nn.Module):
+    """Synthetic text side: ``encoder(idx=...)`` returns rows of a fixed embedding table as the CLS state."""
+
+    def __init__(self, table):
+        super().__init__()
+        self.register_buffer("table", table)
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, idx):
+        class _O:
+            pass
+        o = _O()
+        o.last_hidden_state = self.table[idx][:, None, :]
+        return o
+
+
+class IdentityHead(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        return x
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_steps(B, steps, warmup, threads):
+    """Oracle outer steps on the host cores (fp32, like the reference on CPU).  Returns img/s."""
+    from oracle import stackgan_oracle as O
+    torch.set_num_threads(threads)
+    ps = O.init_all(42, with_stage2=False)
+    ca, d1, g1 = ps["con_augment_1"], ps["critic_1"], ps["gen_1"]
+    tr = dict(ca=O.Trainer(ca), d1=O.Trainer(d1), g1=O.Trainer(g1))
+    times = []
+    for s in range(warmup + steps):
+        b = O.synthetic_batch(B, 1, s)
+        tem = b["tem"].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        O.stage1_step(ca, d1, g1, b["real"], tem, b["perm"], b["z"], b["eps_ca"], b["eps_gp"], tr)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return B / med, med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = 16
+    ips, med = cpu_reference_steps(B, max(1, min(args.steps, 5)), min(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": "stackgan_stage1_train_images_per_sec", "value": round(ips, 3),
+        "unit": "images/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1),
+        "ms_per_step": round(med * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "StackGAN Stage-I 64x64 G+D outer step (5 critic + 1 generator update), CPU sample",
+                   "batch_per_step": B},
+        "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle (torch-CPU restatement of stage_1_train_fn.py:93-196) B={B} fp32 outer steps, median"},
+        "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ kernel roofline
+def time_dominant_kernel(ops, B, reps=20):
+    """The critic's heaviest conv (ds3: 128->256, 16x16 -> 8x8, all three image groups batched) timed
+    alone with CUDA events on its launch stream; algorithmic FLOPs = 2*M*N*K."""
+    N, H, Ci, Co, k = 3 * B, 16, 128, 256, 4
+    x = torch.randn(N, H, H, Ci, device="cuda").to(ops.act_dtype)
+    pf = (torch.randn(Co, k, k, Ci, device="cuda") * 0.02).to(ops.act_dtype)
+    y = torch.empty(N, H // 2, H // 2, Co, device="cuda", dtype=ops.act_dtype)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ops.conv_fprop(x, pf, None, y, k, 2, 1)
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv_fprop(x, pf, None, y, k, 2, 1)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = sum(ts) / len(ts)
+    flops = 2.0 * (N * (H // 2) ** 2) * Co * (k * k * Ci)
+    return flops, ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", default="bf16")
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from imagegenerator_b200.engine import Stage1Engine
+    from imagegenerator_b200.ops import CudaOps
+    from imagegenerator_b200.stage_1_train_fn import train_1, make_allreduce
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    W = max(args.warmup, 3)
+    K, B = args.steps, args.batch
+    dev = torch.device(f"cuda:{local}")
+    ops = CudaOps(args.mode, device=dev)
+    ca, d1, g1 = build_modules()
+    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, allreduce=make_allreduce(world))
+    use_graph = not args.no_graph
+
+    # ---- resident-input timing
+    g = torch.Generator().manual_seed(1000 + rank)           # each replica its own images/embeddings
+    real = torch.randn(B, 3, 64, 64, generator=g).clamp_(-1, 1).to(dev)
+    tem = torch.randn(B, 512, generator=g).to(dev)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(7))
+    tem_mis = tem[perm.to(dev)].contiguous()
+    gz = torch.Generator().manual_seed(5)                     # shared noise (same z on every replica, like the reference)
+    z = torch.randn(5, B, 100, generator=gz).to(dev)
+    eca = torch.randn(5, B, 128, generator=gz).to(dev)
+    egp = torch.rand(5, B, generator=gz).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    try:
+        for _ in range(W):
+            eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
+    except Exception as e:                                    # graph capture of NCCL can fail: fall back to eager launches
+        if not use_graph:
+            raise
+        print(f"[bench] CUDA-graph path failed ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
+        use_graph = False
+        eng.graph = None
+        for _ in range(W):
+            eng.step(real, tem, tem_mis, z, eca, egp, use_graph=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()                                         # L2 flush between timed steps (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    launches = (eng.launches_per_step or 0) * K if use_graph else ops.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item())
+    value = B * world / (step_ms * 1e-3)
+
+    # ---- end to end through train_1 with host batches
+    table = torch.randn(B, 512, generator=torch.Generator().manual_seed(2000 + rank)).to(dev)
+    enc, head = TableEncoder(table).to(dev), IdentityHead().to(dev)
+    mk = lambda m, lr=1e-3: torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.999))
+    opts = [mk(enc, 0.0), mk(head, 0.0), mk(ca), mk(d1), mk(g1)]
+    scheds = [torch.optim.lr_scheduler.StepLR(o, step_size=100, gamma=0.5) for o in opts]
+    quiet = lambda *a, **k: None
+    ck_dir = f"/tmp/sgb200_bench_ckpt_{os.getpid()}"
+    train_1([enc, head, ca, d1, g1], opts, scheds, synthetic_host_batches(2, B, 1), 2, dev, B, start_epoch=1,
+            save_dir=ck_dir, log=quiet, use_graph=use_graph, engine=eng)      # warm-up pass
+    batches = synthetic_host_batches(K, B, 2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    train_1([enc, head, ca, d1, g1], opts, scheds, batches, 2, dev, B, start_epoch=1, save_dir=ck_dir, log=quiet,
+            use_graph=use_graph, engine=eng)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = B * 3 * 64 * 64 * 4 + B * 8 + 5 * B * 100 * 4 + 5 * B * 4       # images + idx + z + gp eps (fp32)
+    d2h = 4 * 4
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        kflops, kms = time_dominant_kernel(ops, B)
+        peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+        ach = kflops / (kms * 1e-3) / 1e12
+        line = {
+            "metric": "stackgan_stage1_train_images_per_sec", "value": round(value, 2), "unit": "images/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+            "config": {"workload": "StackGAN Stage-I 64x64 G+D outer step (5 critic updates w/ WGAN-GP double backward "
+                                   "+ 1 generator/CA update, Adam), batch 128/GPU",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "cuda_graph": use_graph, "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "flops_per_image_executed": FLOPS_PER_IMG,
+                       "flops_per_image_reference_necessary": FLOPS_PER_IMG_REFERENCE_NECESSARY},
+            "step_tflops": round(FLOPS_PER_IMG * B / (step_ms * 1e-3) / 1e12, 2),
+            "wall_s_timed_region": round(wall, 3),
+            "gpu_launches": int(launches),
+            "e2e": {"value": round(B * world / (e2e_ms * 1e-3), 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "imagegenerator_b200.stage_1_train_fn.train_1"},
+            "roofline": {"bound": "tensor", "kernel": "sg_conv_fprop critic ds3 (128->256, k4 s2, 3 groups batched)",
+                         "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PF",
+                         "kernel_ms": round(kms, 5)},
+            "clocks": clocks,
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            ips, med = cpu_reference_steps(16, 3, 1, threads)
+            line["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle (torch-CPU restatement of the reference step) B=16 fp32, 1 warm-up + 3 outer steps, median"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -409,6 +409,17 @@ class Stage1Engine:
             self.allreduce(fp.grad)                  # mean over replicas (xm.optimizer_step semantics)
         self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
 
+    def export_optimizer_state(self, opt, fp):
+        """Mirror the fused Adam state into a torch.optim.Adam so ``opt.state_dict()`` checkpoints
+        carry exp_avg / exp_avg_sq / step like the reference's (stage_1_train_fn.py:218-222)."""
+        step = float(fp.hyper[4].item())
+        off = 0
+        for p in fp.params:
+            k = p.numel()
+            opt.state[p] = {"step": torch.tensor(step), "exp_avg": fp.m[off:off + k].view(p.shape).clone(),
+                            "exp_avg_sq": fp.v[off:off + k].view(p.shape).clone()}
+            off += k
+
     # -- inputs
     def load_batch(self, real_nchw, tem, tem_mis):
         d = self.d
@@ -452,3 +463,47 @@ class Stage1Engine:
         for it in range(N_CRITIC):
             self.critic_iteration(z[it], eps_ca[it], eps_gp[it])
         self.generator_step()
+
+    # -- whole step behind static buffers, replayed as one CUDA graph
+    def _ensure_static(self):
+        if getattr(self, "s_real", None) is None:
+            ops, B, f = self.ops, self.B, self.ops.f32
+            hw = self.d_m.in_hw
+            self.s_real = ops.empty((B, 3, hw, hw), f)
+            self.s_z = ops.empty((N_CRITIC, B, Z_DIM), f)
+            self.s_eca = ops.empty((N_CRITIC, B, self.ca_m.c_dim), f)
+            self.s_egp = ops.empty((N_CRITIC, B), f)
+            self.graph = None
+            self.launches_per_step = None
+
+    def _body(self):
+        d = self.d
+        self.ops.nchw_to_nhwc(self.s_real, d.group_view(d.a[0], 0, 1))
+        self.outer_step(self.s_z, self.s_eca, self.s_egp)
+
+    def step(self, real_nchw, tem, tem_mis, z, eps_ca, eps_gp, use_graph=True):
+        """One outer step.  Inputs may live on the host (pinned) or the device; they are copied into
+        static device buffers, then the ~650 kernels of the step run as one CUDA-graph replay
+        (Stage-I kernels are microseconds long: launch-bound otherwise, SURVEY.md section 7 hard part 3)."""
+        self._ensure_static()
+        self.s_real.copy_(real_nchw, non_blocking=True)
+        self.d.tem_all[:self.B].copy_(tem, non_blocking=True)
+        self.d.tem_all[self.B:].copy_(tem_mis, non_blocking=True)
+        self.s_z.copy_(z, non_blocking=True)
+        self.s_eca.copy_(eps_ca, non_blocking=True)
+        self.s_egp.copy_(eps_gp, non_blocking=True)
+        if not use_graph or getattr(self.ops, "is_emulator", False):
+            n0 = self.ops.launch_count() if hasattr(self.ops, "launch_count") else 0
+            self._body()
+            if hasattr(self.ops, "launch_count"):
+                self.launches_per_step = self.ops.launch_count() - n0
+            return
+        if self.graph is None:
+            torch.cuda.synchronize()
+            n0 = self.ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.launches_per_step = self.ops.launch_count() - n0
+            self.graph = g
+        self.graph.replay()
