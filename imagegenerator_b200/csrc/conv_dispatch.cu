@@ -1,6 +1,7 @@
 // conv_dispatch.cu -- public convolution entry points: route each call to the tcgen05 kernels
 // (bf16, tensor-core-shaped layers) or to the CUDA-core implicit GEMM (fp32 mode, thin layers).
 #include "common.cuh"
+#include <stdlib.h>
 
 extern "C" {
 int sg_conv_fprop_ffma(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int,
@@ -9,12 +10,31 @@ int sg_conv_dgrad_ffma(const void*, const void*, const float*, void*, int, int, 
                        int, void*);
 int sg_conv_wgrad_ffma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, void*);
 
+int sg_conv_fprop_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int,
+                     void*);
+int sg_conv_dgrad_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int,
+                     void*);
+int sg_conv_tc_supported(int, int, int, int, int, int, int, int, int, int, int);
+
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SG_DISABLE_TC");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int sg_conv_fprop(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho, int Wo,
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
+    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+        return sg_conv_fprop_tc(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
     return sg_conv_fprop_ffma(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
 }
 int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int H, int W, int Ci, int Ho, int Wo,
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
+    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+        return sg_conv_dgrad_tc(dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
     return sg_conv_dgrad_ffma(dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
 }
 int sg_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,

@@ -82,19 +82,19 @@ class EmuOps:
             pd.copy_(w.permute(1, 2, 3, 0).to(pd.dtype))
 
     # ---- convolutions (Conv2d-layout semantics; ConvTranspose2d layers use them mirrored)
-    def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE):
+    def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE, impl=""):
         # arithmetic is always fp64; only STORAGE follows the emulated mode (ideal-rounding model)
         w = pf.permute(0, 3, 1, 2).double()                         # [Co,Ci,kh,kw]
         out = F.conv2d(nchw(x).double(), w, None if bias is None else bias.double(), s, p)
         y.copy_(nhwc(_act(out, act)).to(y.dtype))
 
-    def conv_dgrad(self, dy, pd, bias, dx, k, s, p, act=ACT_NONE):
+    def conv_dgrad(self, dy, pd, bias, dx, k, s, p, act=ACT_NONE, impl=""):
         w = pd.permute(3, 0, 1, 2).double()                         # [Co,Ci,kh,kw] (= convT weight [in,out,kh,kw])
         out = F.conv_transpose2d(nchw(dy).double(), w, None if bias is None else bias.double(), s, p)
         assert out.shape[2] == dx.shape[1], (out.shape, dx.shape)
         dx.copy_(nhwc(_act(out, act)).to(dx.dtype))
 
-    def conv_wgrad(self, x, dy, dw, k, s, p):
+    def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         """dw[Co,Ci,kh,kw] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]."""
         g = torch.nn.grad.conv2d_weight(nchw(x).double(), dw.shape, nchw(dy).double(), stride=s, padding=p)
         dw.add_(g.to(dw.dtype))

@@ -254,3 +254,46 @@ def test_adam_matches_torch():
     torch.cuda.synchronize()
     assert float(hyper[4]) == 5
     assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+TC_CASES = CONV_CASES + [
+    (128, 16, 128, 256, 4, 2, 1),    # critic ds3 at the bench batch
+    (16, 32, 64, 128, 4, 2, 1),
+    (24, 8, 256, 512, 4, 2, 1),      # critic ds4, batch not a multiple of the 8-image tile
+    (4, 16, 640, 320, 3, 1, 1),      # Stage-II residual block layer1 operator
+    (2, 128, 16, 32, 4, 2, 1),       # Stage-II critic ds2 operator (Wo = 64)
+    (2, 256, 8, 16, 4, 2, 1),        # wide rows: Wo = 128 -> one-row tiles
+]
+
+
+def _tc_ok(mode, case):
+    from imagegenerator_b200.ops import CudaOps
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    return bool(CudaOps("bf16").lib.sg_conv_tc_supported(mode, N, H, H, Ci, Ho, Ho, Co, k, s, p))
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True)])
+def test_conv_fprop_tcgen05(case, act, use_bias):
+    if not _tc_ok(0, case):
+        pytest.skip("shape routed to the CUDA-core kernel")
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    x, w = rnd(N, H, H, Ci), rnd(Co, Ci, k, k, scale=(Ci * k * k) ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    bias = F(rnd(Co)) if use_bias else None
+    run_pair("bf16", "conv_fprop", [T(x), T(pf), bias, T(torch.zeros(N, Ho, Ho, Co)), k, s, p], [3], dict(act=act, impl="_tc"))
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_TANH, True)])
+def test_conv_dgrad_tcgen05(case, act, use_bias):
+    if not _tc_ok(1, case):
+        pytest.skip("shape routed to the CUDA-core kernel")
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    dy, w = rnd(N, Ho, Ho, Co), rnd(Co, Ci, k, k, scale=(Co * k * k / (s * s)) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    bias = F(rnd(Ci)) if use_bias else None
+    run_pair("bf16", "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci)), k, s, p], [3], dict(act=act, impl="_tc"))
