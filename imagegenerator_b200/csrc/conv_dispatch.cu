@@ -15,6 +15,8 @@ int sg_conv_fprop_tc(const void*, const void*, const float*, void*, int, int, in
 int sg_conv_dgrad_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int,
                      void*);
 int sg_conv_tc_supported(int, int, int, int, int, int, int, int, int, int, int);
+int sg_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, void*);
+int sg_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int, int, int);
 
 static bool tc_enabled() {
     static int v = -1;
@@ -39,6 +41,8 @@ int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx, i
 }
 int sg_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
                   int s, int p, int dtype, void* stream) {
+    if (dtype == SG_BF16 && tc_enabled() && sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p))
+        return sg_conv_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
     return sg_conv_wgrad_ffma(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
 }
 }

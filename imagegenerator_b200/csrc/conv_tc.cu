@@ -251,6 +251,153 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad
+// dW[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]  as  D[co][(tap,ci)] = A^T B with the pixel
+// index as the reduction: both operands are "MN-major" (channels contiguous, pixels strided), which
+// UMMA reads directly through MN-major 128B-swizzled descriptors -- no transposes.  One CTA owns a
+// 128-channel slab of co, one 64-channel block of ci and up to 8 taps (8 x 64 fp32 columns = all 512
+// TMEM columns) and walks a slice of the pixels 64 at a time; slices are combined with vector
+// fp32 reductions (red.global.add.v4.f32) into the PyTorch-layout gradient.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // between 64-element blocks along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;                    // between 8-row groups along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TcWParams {
+    int Mpix, Ho, Wo;      // pixels of dy
+    int bw, bh, bn;        // pixel box of one 64-pixel k-block
+    int Co, Ci, kk, k, s, p;
+    int tpg;               // taps per group (<= 8)
+    int tap_groups;
+    int kb_per_split;      // 64-pixel blocks per split
+    float* dw;
+};
+
+constexpr int W_A_BYTES = 2 * 64 * 128;     // dy: two 64-channel blocks x 64 pixels
+constexpr int W_B_BYTES = 64 * 128;         // x at one tap: 64 channels x 64 pixels
+constexpr int W_STAGES = 2;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[W_STAGES], empty_bar[W_STAGES], accum_bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int stage_bytes = W_A_BYTES + P.tpg * W_B_BYTES;
+
+    const int co0 = blockIdx.x * 128;
+    const int cib = blockIdx.y / P.tap_groups, tg = blockIdx.y - cib * P.tap_groups;
+    const int ci0 = cib * 64, tap0 = tg * P.tpg;
+    const int ntap = min(P.tpg, P.kk - tap0);
+    const int total_kb = (P.Mpix + 63) / 64;
+    const int kb0 = blockIdx.z * P.kb_per_split;
+    const int nkb = min(P.kb_per_split, total_kb - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int i = 0; i < nkb; ++i) {
+                    const int st = i % W_STAGES, it = i / W_STAGES;
+                    mbar_wait(&empty_bar[st], (it & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[st], (uint32_t)(W_A_BYTES + ntap * W_B_BYTES));
+                    const int pix0 = (kb0 + i) * 64;
+                    const int ow0 = pix0 % P.Wo, oh0 = (pix0 / P.Wo) % P.Ho, n0 = pix0 / (P.Wo * P.Ho);
+                    uint8_t* sa = smem + (size_t)st * stage_bytes;
+                    tma_load_2d(&tmDy, &full_bar[st], sa, co0, pix0);
+                    tma_load_2d(&tmDy, &full_bar[st], sa + 64 * 128, co0 + 64, pix0);
+                    for (int t = 0; t < ntap; ++t) {
+                        const int tap = tap0 + t, kh = tap / P.k, kw = tap - kh * P.k;
+                        tma_load_4d(&tmX, &full_bar[st], sa + W_A_BYTES + t * W_B_BYTES, ci0, ow0 * P.s - P.p + kw,
+                                    oh0 * P.s - P.p + kh, n0);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                // D=f32, A=B=bf16, both MN-major, N=64, M=128
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) |
+                                       ((128u >> 4) << 24);
+                for (int i = 0; i < nkb; ++i) {
+                    const int st = i % W_STAGES, it = i / W_STAGES;
+                    mbar_wait(&full_bar[st], it & 1);
+                    tc_fence_after();
+                    const uint32_t sa = base + (uint32_t)st * stage_bytes;
+                    for (int t = 0; t < ntap; ++t) {
+                        const uint32_t sb = sa + W_A_BYTES + t * W_B_BYTES;
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16) {
+                            uint64_t ad = make_mnmajor_sw128_desc(sa + k16 * 2048, 64 * 128);
+                            uint64_t bd = make_mnmajor_sw128_desc(sb + k16 * 2048, 64 * 128);
+                            tc_mma_bf16(tmem_base + t * 64, ad, bd, idesc, (i | k16) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty_bar[st]);
+                }
+                tc_commit(&accum_bar);
+            }
+        } else {
+            const int q = warp & 3;
+            const int co = co0 + q * 32 + lane;
+            mbar_wait(&accum_bar, 0);
+            tc_fence_after();
+            const bool vec = (P.kk == 16) && (P.tpg == 8);
+            for (int c16 = 0; c16 < 64; c16 += 16) {
+                if (ci0 + c16 >= P.Ci) break;            // warp-uniform
+                for (int t = 0; t < ntap; t += 4) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (t + u < ntap) tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t + u) * 64 + c16), v[u]);
+                    if (co >= P.Co) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int ci = ci0 + c16 + j;
+                        if (ci >= P.Ci) break;
+                        float* dst = P.dw + ((int64_t)co * P.Ci + ci) * P.kk + tap0 + t;
+                        if (vec) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v[0][j])),
+                                         "f"(__uint_as_float(v[1][j])), "f"(__uint_as_float(v[2][j])),
+                                         "f"(__uint_as_float(v[3][j]))
+                                         : "memory");
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (t + u < ntap) atomicAdd(dst + u, __uint_as_float(v[u][j]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -381,6 +528,72 @@ static int launch_conv_tc(int mode, const void* act, const void* wpack, const fl
     return check_launch("conv_tc");
 }
 
+static bool choose_box64(int Ho, int Wo, int* bw, int* bh, int* bn) {
+    if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
+    if (Wo >= 64) { *bw = 64; *bh = 1; *bn = 1; return true; }
+    *bw = Wo;
+    int rows = 64 / Wo;
+    if (Ho >= rows) { *bh = rows; *bn = 1; return true; }
+    *bh = Ho;
+    *bn = rows / Ho;
+    return true;
+}
+
+// 2-D [rows][C] bf16 view, box {64, 64}
+static int get_rows_map(const void* ptr, int64_t rows, int C, CUtensorMap* out) {
+    MapKey key(ptr, (int)rows, C, 64, 64, 0, 0, 0, 0, 22);
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rows=%lld C=%d) failed: %d", (long long)rows, C, (int)r); return SG_ERR_UNSUPPORTED; }
+    g_maps[key] = m;
+    *out = m;
+    return 0;
+}
+
+static bool g_wattr_set = false;
+
+static int launch_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                           int k, int s, int p, cudaStream_t st) {
+    int e = ensure_encode();
+    if (e) return e;
+    TcWParams P;
+    P.Mpix = N * Ho * Wo; P.Ho = Ho; P.Wo = Wo; P.Co = Co; P.Ci = Ci; P.kk = k * k; P.k = k; P.s = s; P.p = p; P.dw = dw;
+    if (!choose_box64(Ho, Wo, &P.bw, &P.bh, &P.bn)) { set_error("wgrad_tc: grid not tileable"); return SG_ERR_UNSUPPORTED; }
+    P.tpg = P.kk < 8 ? P.kk : 8;
+    P.tap_groups = (P.kk + P.tpg - 1) / P.tpg;
+    CUtensorMap tmDy, tmX;
+    if ((e = get_rows_map(dy, P.Mpix, Co, &tmDy))) return e;
+    if ((e = get_act_map(x, N, H, W, Ci, P.bw, P.bh, P.bn, s, &tmX))) return e;
+    int co_tiles = (Co + 127) / 128, ci_blocks = (Ci + 63) / 64;
+    int tiles = co_tiles * ci_blocks * P.tap_groups;
+    int total_kb = (P.Mpix + 63) / 64;
+    int want = (SG_NUM_SMS + tiles - 1) / tiles;          // about one wave of CTAs
+    int max_splits = (total_kb + 3) / 4;                  // at least 4 k-blocks per CTA
+    int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+    if (splits < 1) splits = 1;
+    P.kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
+    size_t smem = (size_t)W_STAGES * (W_A_BYTES + P.tpg * W_B_BYTES) + 1024;
+    if (!g_wattr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(ce)); return (int)ce; }
+        g_wattr_set = true;
+    }
+    dim3 grid(co_tiles, ci_blocks * P.tap_groups, splits);
+    conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmDy, tmX, P);
+    g_launches.fetch_add(1);
+    return check_launch("conv_wgrad_tc");
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -413,6 +626,22 @@ int sg_conv_dgrad_tc(const void* dy, const void* pd, const float* bias, void* dx
     SG_REQUIRE(sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_dgrad_tc: unsupported shape");
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc: inconsistent sizes");
     return launch_conv_tc(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
+}
+
+int sg_conv_wgrad_tc_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p) {
+    int bw, bh, bn;
+    if (Ci % 8 != 0 || Co % 8 != 0) return 0;
+    if (s < 1 || s > 2 || k > 4) return 0;
+    if (!choose_box64(Ho, Wo, &bw, &bh, &bn)) return 0;
+    if (bw * s > 256 || bh * s > 256) return 0;
+    return 1;
+}
+
+int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
+                     int s, int p, int dtype, void* stream) {
+    SG_REQUIRE(dtype == SG_BF16, "conv_wgrad_tc: bf16 only");
+    SG_REQUIRE(sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_wgrad_tc: unsupported shape");
+    return launch_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
 }
 
 }  // extern "C"

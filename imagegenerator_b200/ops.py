@@ -35,6 +35,7 @@ _SIGS = {
     "sg_conv_wgrad_ffma": [_P, _P, _P] + [_I] * 11 + [_P],
     "sg_conv_fprop_tc": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_dgrad_tc": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_wgrad_tc": [_P, _P, _P] + [_I] * 11 + [_P],
     "sg_colsum": [_P, _P, _L, _I, _I, _P],
     "sg_col_stats": [_P, _P, _L, _I, _I, _I, _P],
     "sg_bn_finalize": [_P, _L, _P, _P, _P, _P, _I, _I, _F, _F, _I, _I, _P],
@@ -64,7 +65,7 @@ _SIGS = {
     "sg_adam_step": [_P, _P, _P, _P, _P, _L, _P],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported"])
+EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported"])
 
 
 def load_library(path=LIB_PATH):
@@ -80,6 +81,8 @@ def load_library(path=LIB_PATH):
         fn.restype = _I
     lib.sg_conv_tc_supported.argtypes = [_I] * 11
     lib.sg_conv_tc_supported.restype = _I
+    lib.sg_conv_wgrad_tc_supported.argtypes = [_I] * 10
+    lib.sg_conv_wgrad_tc_supported.restype = _I
     lib.sg_version.restype = _I
     lib.sg_last_error.restype = _c.c_char_p
     lib.sg_check_device.restype = _I

@@ -297,3 +297,21 @@ def test_conv_dgrad_tcgen05(case, act, use_bias):
     pd = w.permute(1, 2, 3, 0).contiguous()
     bias = F(rnd(Ci)) if use_bias else None
     run_pair("bf16", "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci)), k, s, p], [3], dict(act=act, impl="_tc"))
+
+
+def _wtc_ok(case):
+    from imagegenerator_b200.ops import CudaOps
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    return bool(CudaOps("bf16").lib.sg_conv_wgrad_tc_supported(N, H, H, Ci, Ho, Ho, Co, k, s, p))
+
+
+@pytest.mark.parametrize("case", TC_CASES + [(5, 8, 192, 96, 4, 2, 1), (7, 32, 24, 48, 4, 2, 1)])
+def test_conv_wgrad_tcgen05(case):
+    if not _wtc_ok(case):
+        pytest.skip("shape routed to the CUDA-core kernel")
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    x, dy = rnd(N, H, H, Ci), rnd(N, Ho, Ho, Co, scale=(N * Ho * Ho) ** -0.5)
+    dw0 = rnd(Co, Ci, k, k, scale=0.1)
+    run_pair("bf16", "conv_wgrad", [T(x), T(dy), F(dw0), k, s, p], [2], dict(impl="_tc"), tol=dict(rtol=2e-3, atol=2e-4))
