@@ -297,6 +297,9 @@ int sg_conv_dgrad_ffma(const void* dy, const void* pd, const float* bias, void* 
                        int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream) {
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k,
                "conv_dgrad: dx size must equal the transposed-conv output size");
+    // 1x1 input (Stage-I generator's first layer): the stride is immaterial; using s = k turns the k*k
+    // output pixels into k*k parity phases with exactly ONE live tap each instead of k*k mostly-empty taps
+    if (Ho == 1 && Wo == 1 && p == 0 && H == k && W == k) s = k;
     SG_REQUIRE(H % s == 0 && W % s == 0, "conv_dgrad: H, W must be multiples of the stride");
     int Hq = H / s, Wq = W / s;
     int64_t Mq = (int64_t)N * Hq * Wq;

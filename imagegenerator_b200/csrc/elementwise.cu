@@ -427,6 +427,28 @@ __global__ void pack_weight_kernel(const float* w, T* pf, T* pd, int Co, int Ci,
     }
 }
 
+// ---- patch matrix of a thin (<= 4 channel) image: P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci]
+// (the PyTorch weight order, so the layer becomes a 1x1 convolution over P for the tensor-core kernels)
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ x, T* __restrict__ P, int N, int H, int W,
+                                                       int C, int Ho, int Wo, int k, int s, int p) {
+    const int kk = k * k, K = C * kk;
+    int64_t total = (int64_t)N * Ho * Wo * kk;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int t = (int)(i % kk);
+        int64_t pix = i / kk;
+        int ow = (int)(pix % Wo);
+        int64_t r = pix / Wo;
+        int oh = (int)(r % Ho), n = (int)(r / Ho);
+        int kh = t / k, kw = t - kh * k;
+        int ih = oh * s - p + kh, iw = ow * s - p + kw;
+        bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        const T* src = x + (((int64_t)n * H + ih) * W + iw) * C;
+        T* dst = P + pix * K + t;
+        for (int c = 0; c < C; ++c) dst[c * kk] = ok ? src[c] : T(0.f);
+    }
+}
+
 // ---- losses
 template <typename T>
 __global__ void __launch_bounds__(256) sample_sqnorm_kernel(const T* g, float* out, int64_t per_sample,
@@ -585,6 +607,15 @@ int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
     SG_LAUNCHED("nhwc_to_nchw");
     return 0;
 }
+int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int dtype,
+                void* stream) {
+    int64_t n = (int64_t)N * Ho * Wo * k * k;
+    SG_DISPATCH_T(dtype, (patchify_kernel<T><<<grid_for(n, 256, 16), 256, 0, SG_STREAM(stream)>>>((const T*)x, (T*)P, N, H, W, C,
+                                                                                                Ho, Wo, k, s, p)));
+    SG_LAUNCHED("patchify");
+    return 0;
+}
+
 int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream) {
     int64_t n = (int64_t)Co * Ci * kk;
     SG_DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(w, (T*)pf, (T*)pd, Co,

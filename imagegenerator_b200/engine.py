@@ -218,6 +218,15 @@ class CriticRT:
                 self.gy.append(ops.empty(shp1))
         assert h == 4, h
         self.nl = len(self.layers)
+        # first layer (3-channel image): run as a 1x1 conv over the patch matrix P[pix][ci*16+tap] -- the
+        # PyTorch weight order, so the weight itself (viewed [Co,48,1,1]) is the packed operand and the
+        # weight gradient lands in place.  P is shared by fprop and wgrad.
+        L0 = self.layers[0]
+        h1 = _conv_out(module.in_hw, L0.k, L0.s, L0.p)
+        self.K0 = L0.ci * L0.k * L0.k
+        self.P = ops.empty((G * B, h1, h1, self.K0))
+        self.Pv = ops.empty((B, h1, h1, self.K0))
+        self.pf0 = ops.empty((L0.co, 1, 1, self.K0))
         cl, Nd = self.layers[-1].co, module.Nd
         self.A, self.dA = ops.empty((16, cl), f32), ops.zeros((16, cl), f32)
         self.Bv, self.dBv = ops.empty((Nd,), f32), ops.zeros((Nd,), f32)
@@ -252,6 +261,8 @@ class CriticRT:
         ops, m = self.ops, self.m
         for L in self.layers:
             L.pack(ops)
+        L0 = self.layers[0]
+        ops.pack_weight(L0.conv.weight.data.view(L0.co, self.K0, 1, 1), self.pf0, None)
         ops.head_prepare(m.channel_resize.weight.data, m.channel_resize.bias.data, m.critic_score.weight.data,
                          m.critic_score.bias.data, self.A, self.Bv, self.c0)
 
@@ -267,7 +278,8 @@ class CriticRT:
         ops, m, B = self.ops, self.m, self.B
         gv = lambda t: self.group_view(t, g0, ng)
         L0 = self.layers[0]
-        ops.conv_fprop(gv(self.a[0]), L0.pf, L0.conv.bias.data, gv(self.a[1]), L0.k, L0.s, L0.p, act=ACT_LRELU)
+        ops.patchify(gv(self.a[0]), gv(self.P), L0.k, L0.s, L0.p)
+        ops.conv_fprop(gv(self.P), self.pf0, L0.conv.bias.data, gv(self.a[1]), 1, 1, 0, act=ACT_LRELU)
         for l in range(1, self.nl):
             L, bn = self.layers[l], self.layers[l].bn
             y = gv(self.y[l])
@@ -318,7 +330,7 @@ class CriticRT:
         dy0 = gv(self.dy[0])
         ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU)
         if param_grads:
-            ops.conv_wgrad(gv(self.a[0]), dy0, L0.conv.weight.grad, L0.k, L0.s, L0.p)
+            ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
             ops.colsum(dy0, L0.conv.bias.grad)
         if need_input_grad:
             ops.conv_dgrad(dy0, L0.pd, None, gv(self.dx), L0.k, L0.s, L0.p)
@@ -364,8 +376,9 @@ class CriticRT:
         i2 = lambda t: self.group_view(t, 2, 1)
         ops.gp_seed(self.g, self.sq, coef, self.v0)
         L0 = self.layers[0]
-        ops.conv_fprop(self.v0, L0.pf, None, self.v[0], L0.k, L0.s, L0.p)
-        ops.conv_wgrad(self.v0, self.gdy[0], L0.conv.weight.grad, L0.k, L0.s, L0.p)
+        ops.patchify(self.v0, self.Pv, L0.k, L0.s, L0.p)
+        ops.conv_fprop(self.Pv, self.pf0, None, self.v[0], 1, 1, 0)
+        ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
         ops.act_bwd(self.v[0], i2(self.a[1]), self.w[1], ACT_LRELU)
         for l in range(1, nl):
             L, bn = self.layers[l], self.layers[l].bn

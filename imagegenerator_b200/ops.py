@@ -27,6 +27,7 @@ _SIGS = {
     "sg_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "sg_patchify": [_P, _P] + [_I] * 10 + [_P],
     "sg_conv_fprop": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_dgrad": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_wgrad": [_P, _P, _P] + [_I] * 11 + [_P],
@@ -174,6 +175,13 @@ class CudaOps:
         Co, Ci, k, _ = w.shape
         ref = pf if pf is not None else pd
         self._ck(self.lib.sg_pack_weight(_ptr(w), _ptr(pf), _ptr(pd), Co, Ci, k * k, self._dt_of(ref), self._st()))
+
+    def patchify(self, x, P, k, s, p):
+        self._c(x, P)
+        N, H, W, C = x.shape
+        _, Ho, Wo, K = P.shape
+        assert K == C * k * k
+        self._ck(self.lib.sg_patchify(_ptr(x), _ptr(P), N, H, W, C, Ho, Wo, k, s, p, self._dt_of(x), self._st()))
 
     # ---- convolution operator
     def _conv_dims(self, x, y):

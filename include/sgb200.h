@@ -60,6 +60,12 @@ int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
 /* w [Co][Ci][k*k] fp32 -> pf [Co][k*k][Ci] and pd [Ci][k*k][Co] in T (either may be NULL) */
 int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream);
 
+/* P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci] (0 outside): patch matrix of a thin
+ * (3-channel) image in the PyTorch weight order, so that discrminator_1.py:10 / discriminator_2.py:9 run as
+ * a 1x1 convolution on the tensor-core kernels */
+int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p,
+                int dtype, void* stream);
+
 /* ---- convolution operator (replaces nn.Conv2d / nn.ConvTranspose2d and their autograd:
  *      generator_1.py:20,26  generator_2.py:30,46,55,71,87  discrminator_1.py:10,29
  *      discriminator_2.py:9,44) ------------------------------------------------------------- */
@@ -75,6 +81,24 @@ int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx,
 int sg_conv_wgrad(const void* x, const void* dy, float* dw,
                   int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p,
                   int dtype, void* stream);
+/* the same three entry points pinned to one implementation: *_ffma = CUDA-core implicit GEMM (fp32 or bf16
+ * storage, fp32 accumulate), *_tc = tcgen05/TMEM/TMA (bf16 only; sg_conv_tc_supported / sg_conv_wgrad_tc_supported
+ * say whether a shape is eligible).  sg_conv_* above dispatch between them. */
+int sg_conv_fprop_ffma(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho,
+                       int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream);
+int sg_conv_dgrad_ffma(const void* dy, const void* pd, const float* bias, void* dx, int N, int H, int W, int Ci, int Ho,
+                       int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream);
+int sg_conv_wgrad_ffma(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                       int k, int s, int p, int dtype, void* stream);
+int sg_conv_fprop_tc(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho,
+                     int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream);
+int sg_conv_dgrad_tc(const void* dy, const void* pd, const float* bias, void* dx, int N, int H, int W, int Ci, int Ho,
+                     int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream);
+int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                     int k, int s, int p, int dtype, void* stream);
+int sg_conv_tc_supported(int mode /*0 fprop, 1 dgrad*/, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
+int sg_conv_wgrad_tc_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
+
 /* out[C] (fp32) += column sums of x[rows][C]  (bias gradients) */
 int sg_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream);
 

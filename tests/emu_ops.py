@@ -81,6 +81,12 @@ class EmuOps:
         if pd is not None:
             pd.copy_(w.permute(1, 2, 3, 0).to(pd.dtype))
 
+    def patchify(self, x, P, k, s, p):
+        """P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci]  (F.unfold order)."""
+        N, Ho, Wo, K = P.shape
+        u = F.unfold(nchw(x).double(), k, padding=p, stride=s)          # [N, C*k*k, Ho*Wo]
+        P.copy_(u.transpose(1, 2).reshape(N, Ho, Wo, K).to(P.dtype))
+
     # ---- convolutions (Conv2d-layout semantics; ConvTranspose2d layers use them mirrored)
     def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE, impl=""):
         # arithmetic is always fp64; only STORAGE follows the emulated mode (ideal-rounding model)

@@ -315,3 +315,9 @@ def test_conv_wgrad_tcgen05(case):
     x, dy = rnd(N, H, H, Ci), rnd(N, Ho, Ho, Co, scale=(N * Ho * Ho) ** -0.5)
     dw0 = rnd(Co, Ci, k, k, scale=0.1)
     run_pair("bf16", "conv_wgrad", [T(x), T(dy), F(dw0), k, s, p], [2], dict(impl="_tc"), tol=dict(rtol=2e-3, atol=2e-4))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_patchify(mode):
+    x = rnd(3, 16, 16, 3)
+    run_pair(mode, "patchify", [T(x), T(torch.zeros(3, 8, 8, 48)), 4, 2, 1], [1])
