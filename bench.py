@@ -203,7 +203,8 @@ def main():
     import torch.distributed as dist
     from imagegenerator_b200.engine import Stage1Engine
     from imagegenerator_b200.ops import CudaOps
-    from imagegenerator_b200.stage_1_train_fn import train_1, make_allreduce
+    from imagegenerator_b200.stage_1_train_fn import train_1
+    from imagegenerator_b200.comm import DistComm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,7 +217,8 @@ def main():
     dev = torch.device(f"cuda:{local}")
     ops = CudaOps(args.mode, device=dev)
     ca, d1, g1 = build_modules()
-    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, allreduce=make_allreduce(world))
+    comm = DistComm(device=dev) if world > 1 else None
+    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, comm=comm)
     use_graph = not args.no_graph
 
     # ---- resident-input timing
@@ -315,7 +317,8 @@ def main():
             "config": {"workload": "StackGAN Stage-I 64x64 G+D outer step (5 critic updates w/ WGAN-GP double backward "
                                    "+ 1 generator/CA update, Adam), batch 128/GPU",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "cuda_graph": use_graph, "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "cuda_graph": use_graph, "grad_allreduce": ("NCCL avg, 2 buckets/critic step on a side stream, "
+                                                                    f"{comm.bytes_reduced // (W + 2 * K + 2)} B/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "flops_per_image_executed": FLOPS_PER_IMG,
                        "flops_per_image_reference_necessary": FLOPS_PER_IMG_REFERENCE_NECESSARY},
             "step_tflops": round(FLOPS_PER_IMG * B / (step_ms * 1e-3) / 1e12, 2),

@@ -306,14 +306,15 @@ class CriticRT:
             ops.head_fwd(self.group_view(a4, 0, 1), self.ce[B:], self.A, self.Bv, self.c0, self.score[1])
 
     # ---------------------------------------------------------------- first-order backward
-    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad):
+    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, on_layer_done=None, head_reduce=True):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
-        d loss / d y_l on the interpolated group from the gradient-penalty second-order pass)."""
+        d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).
+        ``on_layer_done(l)`` is called once the parameter gradients of conv layer l are final."""
         ops, nl = self.ops, self.nl
         gv = lambda t: self.group_view(t, g0, ng)
         a4 = gv(self.a[nl])
         ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
-        if param_grads:
+        if param_grads and head_reduce:
             ops.head_bwd_reduce(coef, a4, self.dA)
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
@@ -325,6 +326,8 @@ class CriticRT:
             if param_grads:
                 ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
                 ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p)
+                if on_layer_done is not None:
+                    on_layer_done(l)
             ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
         L0 = self.layers[0]
         dy0 = gv(self.dy[0])
@@ -396,7 +399,7 @@ class Stage1Engine:
     """One reference outer step (stage_1_train_fn.py:116-172): five critic updates + one
     generator/CA update, with all noise supplied by the caller."""
 
-    def __init__(self, ca, critic, gen, batch_size, ops=None, lr=1e-3, world_size=1, allreduce=None):
+    def __init__(self, ca, critic, gen, batch_size, ops=None, lr=1e-3, world_size=1, allreduce=None, comm=None):
         ops = ops or default_ops()
         self.ops, self.B = ops, batch_size
         self.ca_m, self.d_m, self.g_m = ca, critic, gen
@@ -408,8 +411,20 @@ class Stage1Engine:
         for fp in (self.d.fp, self.g.fp, self.ca.fp):
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)       # [loss_critic, gp, lossG, kl]
-        self.allreduce = allreduce                   # callable(flat_grad) or None
+        self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
+        self.comm = comm                             # comm.DistComm or None
         self.world = world_size
+        if comm is not None:
+            for fp in (self.d.fp, self.g.fp, self.ca.fp):
+                comm.broadcast_params(fp.flat)       # train.py:78-85
+            # critic bucket boundary: everything from the LAST conv layer's weight to the end of the flat
+            # buffer (ds4/ds6 weight + its BN + compress + channel_resize + critic_score) is final first
+            first_tail, off = self.d.layers[-1].conv.weight, 0
+            for p in self.d.fp.params:
+                if p is first_tail:
+                    break
+                off += p.numel()
+            self.d_tail_off = off
         self.real_nchw = None
         self.refresh_all()
 
@@ -417,9 +432,17 @@ class Stage1Engine:
         self.d.refresh_weights()
         self.g.refresh_weights()
 
-    def optimizer_step(self, fp):
-        if self.allreduce is not None:
-            self.allreduce(fp.grad)                  # mean over replicas (xm.optimizer_step semantics)
+    def optimizer_step(self, fp, already_reduced=0):
+        """xm.optimizer_step: average gradients over replicas, then Adam.  ``already_reduced`` = offset
+        from which the flat buffer has been handed to the communicator by the backward pass."""
+        if self.comm is not None:
+            if already_reduced > 0:
+                self.comm.allreduce_async(fp.grad[:already_reduced])
+            elif already_reduced == 0:
+                self.comm.allreduce_async(fp.grad)
+            self.comm.wait_all()
+        elif self.allreduce is not None:
+            self.allreduce(fp.grad)
         self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
 
     def export_optimizer_state(self, opt, fp):
@@ -452,9 +475,19 @@ class Stage1Engine:
         d.gp_first_order()                                       # utils.py:15-24
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])   # :140-144
         d.gp_second_order(2.0 * LAMBDA_GP / B)
-        d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False)    # :147
+        # head/text gradients first (dA is complete once the plain backward has added its head term), so
+        # that the tail of the flat gradient buffer can go to NCCL while the trunk backward still runs
+        ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA)
         d.text_backward(d.coef_text, 2 * B, 0.0, True, None)
-        self.optimizer_step(d.fp)                                # :149
+        tail = [0]
+
+        def bucket(l):
+            if self.comm is not None and l == d.nl - 1:
+                self.comm.allreduce_async(d.fp.grad[self.d_tail_off:])
+                tail[0] = self.d_tail_off
+        d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
+                   on_layer_done=bucket, head_reduce=False)
+        self.optimizer_step(d.fp, already_reduced=tail[0])       # :149
         d.refresh_weights()
 
     def generator_step(self):

@@ -75,8 +75,11 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
 
     for m in models:
         m.train()                                              # :86-90
-    eng = engine or Stage1Engine(con_augment_1, critic_1, gen_1, batch_size, world_size=world,
-                                 allreduce=make_allreduce(world))
+    if engine is None:
+        from .comm import DistComm
+        comm = DistComm(device=torch.device(device) if not isinstance(device, torch.device) else device) if world > 1 else None
+        engine = Stage1Engine(con_augment_1, critic_1, gen_1, batch_size, world_size=world, comm=comm)
+    eng = engine
     for fp, opt in ((eng.ca.fp, opt_con_augment_1), (eng.d.fp, opt_critic_1), (eng.g.fp, opt_gen_1)):
         lr, b1, b2, eps = _adam_hyper(opt)
         fp.hyper[:4] = torch.tensor([lr, b1, b2, eps], dtype=torch.float32)

@@ -261,14 +261,17 @@ def _force(p, snap):
             p[k].copy_(v.to(p[k].dtype))
 
 
-def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None):
+def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None, sync=None):
     """One outer step of stage_1_train_fn.py:93-196 with synthetic text embeddings.
 
     ca/d1/g1: parameter dicts; tr = dict(ca=Trainer, d1=Trainer, g1=Trainer);
     tem [B,512] requires_grad (leaf) so d lossG / d tem is reported;
     perm [B] (the randperm of :109), z [5,B,100] (:121), eps_ca [5,B,128]
     (con_augment.py:20), eps_gp [5,B] (utils.py:10).
+    ``sync(trainer)``: optional hook run right before every optimizer step -- the data-parallel tests
+    use it to average gradients over replicas (xm.optimizer_step, :149,:166-172).
     Returns losses and the gradients each optimizer saw at its step."""
+    sync = sync or (lambda t: None)
     out = {"loss_critic": [], "critic_grads": [], "critic_before": [], "scores": []}
     tem_mis = tem[perm]                                        # :108-111, :127-129
     for it in range(N_CRITIC):
@@ -294,6 +297,7 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None):
                                 s_mis=s_mis.detach().clone(), s_fake=s_fake.detach().clone(),
                                 gp=gp.detach().clone(), c_hat=c_hat.detach().clone(),
                                 mu=mu.detach().clone(), sigma=sigma.detach().clone())
+        sync(tr["d1"])
         tr["d1"].opt.step()                                     # :149
     if force is not None:
         _force(d1, force[N_CRITIC])
@@ -309,7 +313,9 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None):
     out["g1_grads"] = tr["g1"].grads()
     out["ca_grads"] = tr["ca"].grads()
     out["dtem"] = tem.grad.detach().clone() if tem.grad is not None else None
+    sync(tr["g1"])
     tr["g1"].opt.step()                                         # :166
+    sync(tr["ca"])
     tr["ca"].opt.step()                                         # :172
     for k in ("d1", "g1", "ca"):                                # :187-192 (per batch)
         tr[k].sched.step()

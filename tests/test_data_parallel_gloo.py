@@ -1,0 +1,88 @@
+"""Data-parallel semantics on CPU: world_size 2, gloo.  Each rank runs the engine (kernel emulator, fp64)
+through ``comm.DistComm`` on ITS OWN images/embeddings with the SHARED noise, next to an oracle replica
+whose optimizer steps are preceded by a gradient average -- the reference's xm.optimizer_step
+(stage_1_train_fn.py:149,166-172) with per-replica BatchNorm statistics."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    try:
+        from oracle import stackgan_oracle as O
+        from emu_ops import EmuOps
+        from imagegenerator_b200.comm import DistComm
+        from imagegenerator_b200.con_augment import ConditioningAugmentation
+        from imagegenerator_b200.discrminator_1 import StageIDiscriminator
+        from imagegenerator_b200.generator_1 import StageIGenerator
+        from imagegenerator_b200.engine import Stage1Engine
+        dt, B = torch.float64, 2
+        # rank-dependent init on purpose: the broadcast from rank 0 must make replicas identical
+        torch.manual_seed(42 + rank)
+        ca, d1, g1 = ConditioningAugmentation(512, 256, 128), StageIDiscriminator(512, 128), StageIGenerator(128, 100)
+        ps = O.init_all(42, with_stage2=False)               # what rank 0 holds
+        pca, pd1, pg1 = (O.to_dtype(ps[k], dt) for k in ("con_augment_1", "critic_1", "gen_1"))
+        mine = O.synthetic_batch(B, 1, 100 + rank, dtype=dt)  # per-replica images / embeddings
+        shared = O.synthetic_batch(B, 1, 7, dtype=dt)         # same z / eps on every replica (stage_1_train_fn.py:98-121)
+        tr = dict(ca=O.Trainer(pca), d1=O.Trainer(pd1), g1=O.Trainer(pg1))
+
+        def sync(t):
+            for p in t.params.values():
+                dist.all_reduce(p.grad)
+                p.grad.div_(world)
+        tem = mine["tem"].clone().requires_grad_(True)
+        ref = O.stage1_step(pca, pd1, pg1, mine["real"], tem, shared["perm"], shared["z"], shared["eps_ca"],
+                            shared["eps_gp"], tr, sync=sync)
+        eng = Stage1Engine(ca, d1, g1, B, ops=EmuOps(dt), comm=DistComm())
+        eng.load_batch(mine["real"], mine["tem"], mine["tem"][shared["perm"]])
+        eng.outer_step(shared["z"], shared["eps_ca"], shared["eps_gp"])
+        worst = 0.0
+        for m, key in ((ca, "ca"), (d1, "d1"), (g1, "g1")):
+            sd = m.state_dict()
+            for k, v in ref["after"][key].items():
+                if v.is_floating_point():
+                    err = (sd[k].double() - v).abs().max().item() / max(v.abs().max().item(), 1e-12)
+                    worst = max(worst, err)
+                    assert err < 1e-6, (key, k, err)
+        # replicas hold identical parameters after the step, different BN running stats (no SyncBN)
+        w = d1.down_sampler[2][0].weight.data.clone()
+        w0 = w.clone()
+        dist.broadcast(w0, 0)
+        assert torch.equal(w, w0)
+        rm = d1.down_sampler[2][1].running_mean.clone()
+        rm0 = rm.clone()
+        dist.broadcast(rm0, 0)
+        if rank == 1:
+            assert not torch.equal(rm, rm0)
+        q.put((rank, "ok", worst))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.slow
+def test_stage1_data_parallel_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", f"rank {rank}: {info}"
