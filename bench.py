@@ -238,17 +238,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    try:
-        for _ in range(W):
-            eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
-    except Exception as e:                                    # graph capture of NCCL can fail: fall back to eager launches
-        if not use_graph:
-            raise
-        print(f"[bench] CUDA-graph path failed ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
-        use_graph = False
-        eng.graph = None
-        for _ in range(W):
-            eng.step(real, tem, tem_mis, z, eca, egp, use_graph=False)
+    def dbg(msg):
+        if os.environ.get("SG_BENCH_DEBUG"):
+            print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
+
+    ok = 1
+    if use_graph:
+        try:
+            eng.step(real, tem, tem_mis, z, eca, egp, use_graph=True)      # captures, then replays once
+            torch.cuda.synchronize()
+        except Exception as e:                                # e.g. NCCL refusing stream capture
+            print(f"[bench r{rank}] CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            ok = 0
+        dbg(f"capture ok={ok}")
+        if world > 1:                                         # all ranks must agree, or collectives mismatch
+            t_ok = torch.tensor([ok], device=dev)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            ok = int(t_ok.item())
+        if not ok:
+            use_graph = False
+            eng.graph = None
+    for _ in range(W):
+        eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
+    dbg("warm-up done")
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

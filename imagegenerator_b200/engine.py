@@ -394,6 +394,47 @@ class CriticRT:
         ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA)
 
 
+class _SegmentedGraph:
+    """A train step captured as a SEQUENCE of CUDA graphs with the NCCL calls issued eagerly between them.
+
+    Capturing NCCL collectives inside a CUDA graph hung on this stack (torch 2.11 / NCCL 2.28, see
+    DESIGN.md); cutting the graph at every hand-off to the communicator keeps the ~650 kernel launches
+    of a step off the host's critical path and still lets the side-stream all-reduce overlap the next
+    graph segment."""
+
+    def __init__(self, ops):
+        self.ops, self.items, self.g, self.n0 = ops, [], None, 0
+        self.capturing = False
+
+    def begin(self):
+        self.g = torch.cuda.CUDAGraph()
+        self.n0 = self.ops.launch_count()
+        self.g.capture_begin(capture_error_mode="thread_local")
+        self.capturing = True
+
+    def _close(self):
+        self.g.capture_end()
+        self.capturing = False
+        if self.ops.launch_count() > self.n0:
+            self.items.append(self.g)
+        self.g = None
+
+    def cut(self, action):
+        self._close()
+        self.items.append(action)
+        self.begin()
+
+    def end(self):
+        self._close()
+
+    def replay(self):
+        for it in self.items:
+            if isinstance(it, torch.cuda.CUDAGraph):
+                it.replay()
+            else:
+                it()
+
+
 # ============================================================================================ Stage-I engine
 class Stage1Engine:
     """One reference outer step (stage_1_train_fn.py:116-172): five critic updates + one
@@ -436,11 +477,8 @@ class Stage1Engine:
         """xm.optimizer_step: average gradients over replicas, then Adam.  ``already_reduced`` = offset
         from which the flat buffer has been handed to the communicator by the backward pass."""
         if self.comm is not None:
-            if already_reduced > 0:
-                self.comm.allreduce_async(fp.grad[:already_reduced])
-            elif already_reduced == 0:
-                self.comm.allreduce_async(fp.grad)
-            self.comm.wait_all()
+            self._comm_allreduce(fp.grad[:already_reduced] if already_reduced > 0 else fp.grad)
+            self._comm_wait()
         elif self.allreduce is not None:
             self.allreduce(fp.grad)
         self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
@@ -455,6 +493,20 @@ class Stage1Engine:
             opt.state[p] = {"step": torch.tensor(step), "exp_avg": fp.m[off:off + k].view(p.shape).clone(),
                             "exp_avg_sq": fp.v[off:off + k].view(p.shape).clone()}
             off += k
+
+    def _comm_allreduce(self, t):
+        seg = getattr(self, "_seg", None)
+        if seg is not None and seg.capturing:
+            seg.cut(lambda: self.comm.allreduce_async(t))       # eager NCCL between two graph segments
+        else:
+            self.comm.allreduce_async(t)
+
+    def _comm_wait(self):
+        seg = getattr(self, "_seg", None)
+        if seg is not None and seg.capturing:
+            seg.cut(self.comm.wait_all)
+        else:
+            self.comm.wait_all()
 
     # -- inputs
     def load_batch(self, real_nchw, tem, tem_mis):
@@ -483,7 +535,7 @@ class Stage1Engine:
 
         def bucket(l):
             if self.comm is not None and l == d.nl - 1:
-                self.comm.allreduce_async(d.fp.grad[self.d_tail_off:])
+                self._comm_allreduce(d.fp.grad[self.d_tail_off:])
                 tail[0] = self.d_tail_off
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
                    on_layer_done=bucket, head_reduce=False)
@@ -543,6 +595,27 @@ class Stage1Engine:
             self._body()
             if hasattr(self.ops, "launch_count"):
                 self.launches_per_step = self.ops.launch_count() - n0
+            return
+        if self.comm is not None and self.comm.world > 1:
+            # multi-GPU: graph segments on a private stream, NCCL eager in between
+            if getattr(self, "gstream", None) is None:
+                self.gstream = torch.cuda.Stream(device=self.ops.device)
+            cur = torch.cuda.current_stream(self.ops.device)
+            self.gstream.wait_stream(cur)
+            with torch.cuda.stream(self.gstream):
+                if self.graph is None:
+                    torch.cuda.synchronize()
+                    n0 = self.ops.launch_count()
+                    self._seg = _SegmentedGraph(self.ops)
+                    self._seg.begin()
+                    try:
+                        self._body()
+                    finally:
+                        self._seg.end()
+                    self.launches_per_step = self.ops.launch_count() - n0
+                    self.graph = self._seg
+                self.graph.replay()
+            cur.wait_stream(self.gstream)
             return
         if self.graph is None:
             torch.cuda.synchronize()
