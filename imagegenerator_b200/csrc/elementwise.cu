@@ -241,6 +241,10 @@ struct FillF {
         st4(p + i4 * 4, r);
     }
 };
+__global__ void affine_f32_kernel(const float* x, float a, float b, float* out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + b;
+}
 __global__ void fill_tail_kernel(float* p, float v, int64_t from, int64_t n) {
     int64_t i = from + threadIdx.x;
     if (i < n) p[i] = v;
@@ -449,6 +453,48 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ x, 
     }
 }
 
+// ---- text replicate + channel concat (generator_2.py:61-63) and its backward
+template <typename T>
+__global__ void __launch_bounds__(256) concat_rep_kernel(const T* __restrict__ x, const float* __restrict__ c,
+                                                         T* __restrict__ out, int64_t rows, int HW, int Cx, int Cc) {
+    const int C = Cx + Cc;
+    int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = i / C;
+        int ch = (int)(i - row * C);
+        if (ch < Cx) out[i] = x[row * Cx + ch];
+        else stf(out + i, c[(row / HW) * Cc + (ch - Cx)]);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) split_copy_kernel(const T* __restrict__ dout, T* __restrict__ dx, int64_t rows, int Cx,
+                                                         int C) {
+    int64_t total = rows * Cx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = i / Cx;
+        int ch = (int)(i - row * Cx);
+        dx[i] = dout[row * C + ch];
+    }
+}
+// dc[n][j] = sum_hw dout[n,hw,Cx+j]; one CTA per (n, 32-channel slab)
+template <typename T>
+__global__ void __launch_bounds__(256) rep_bwd_kernel(const T* __restrict__ dout, float* __restrict__ dc, int HW, int Cx,
+                                                      int Cc) {
+    __shared__ float sh[8][33];
+    const int n = blockIdx.y, j = blockIdx.x * 32 + (threadIdx.x & 31), lane_r = threadIdx.x >> 5;
+    const int C = Cx + Cc;
+    float acc = 0.f;
+    if (j < Cc)
+        for (int r = lane_r; r < HW; r += 8) acc += ldf(dout + ((int64_t)n * HW + r) * C + Cx + j);
+    sh[lane_r][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (lane_r == 0 && j < Cc) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x & 31];
+        dc[(int64_t)n * Cc + j] = s;
+    }
+}
+
 // ---- losses
 template <typename T>
 __global__ void __launch_bounds__(256) sample_sqnorm_kernel(const T* g, float* out, int64_t per_sample,
@@ -593,6 +639,12 @@ int sg_fill_f32(float* ptr, float value, int64_t n, void* stream) {
     return 0;
 }
 
+int sg_affine_f32(const float* x, float a, float b, float* out, int64_t n, void* stream) {
+    affine_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, SG_STREAM(stream)>>>(x, a, b, out, n);
+    SG_LAUNCHED("affine_f32");
+    return 0;
+}
+
 int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dtype, void* stream) {
     int64_t HW = (int64_t)H * W;
     SG_DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for((int64_t)N * HW, 256), 256, 0, SG_STREAM(stream)>>>(
@@ -607,6 +659,26 @@ int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
     SG_LAUNCHED("nhwc_to_nchw");
     return 0;
 }
+int sg_concat_rep(const void* x, const float* c, void* out, int N, int HW, int Cx, int Cc, int dtype, void* stream) {
+    int64_t rows = (int64_t)N * HW;
+    SG_DISPATCH_T(dtype, (concat_rep_kernel<T><<<grid_for(rows * (Cx + Cc), 256, 16), 256, 0, SG_STREAM(stream)>>>(
+                             (const T*)x, c, (T*)out, rows, HW, Cx, Cc)));
+    SG_LAUNCHED("concat_rep");
+    return 0;
+}
+
+int sg_split_rep_bwd(const void* dout, void* dx, float* dc, int N, int HW, int Cx, int Cc, int dtype, void* stream) {
+    int64_t rows = (int64_t)N * HW;
+    cudaStream_t st = SG_STREAM(stream);
+    SG_DISPATCH_T(dtype, (split_copy_kernel<T><<<grid_for(rows * Cx, 256, 16), 256, 0, st>>>((const T*)dout, (T*)dx, rows, Cx,
+                                                                                            Cx + Cc)));
+    SG_LAUNCHED("split_copy");
+    dim3 grid((Cc + 31) / 32, N);
+    SG_DISPATCH_T(dtype, (rep_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)dout, dc, HW, Cx, Cc)));
+    SG_LAUNCHED("rep_bwd");
+    return 0;
+}
+
 int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int dtype,
                 void* stream) {
     int64_t n = (int64_t)N * Ho * Wo * k * k;

@@ -103,6 +103,11 @@ class CART:
         ops.linear_bwd(st.tem, m.h.weight.data, st.dh, m.h.weight.grad, m.h.bias.grad, dtem, dx_acc=dtem_acc,
                        relu_out=st.h)
 
+    def backward_from_dc(self, dc, kl_scale):
+        """Same with d loss / d c_hat given directly as an fp32 [B,c_dim] tensor and no d/d tem wanted
+        (Stage-II: the text side is frozen, stage_2_train_fn.py:52-57)."""
+        self.backward(dc, kl_scale, None, False)
+
 
 # ============================================================================================ generator (Stage-I)
 class GenRT:

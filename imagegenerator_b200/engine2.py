@@ -1,0 +1,264 @@
+"""Stage-II of the StackGAN train step on the C-ABI kernels (reference stage_2_train_fn.py:120-168,
+generator_2.py:59-67, discriminator_2.py:27-38).
+
+Differences from Stage-I that matter for parity:
+  * ``gen_1`` / ``con_augment_1`` are frozen and in eval mode (:52-63): gen_1's BatchNorm uses running
+    statistics, con_augment_1 still samples;
+  * ``fake_256`` is not detached and ``opt_gen_2.zero_grad()`` runs only after the step (:131,:154,
+    :163-168), so the gradients G2 / CA2 are stepped with are  d lossG + sum_5 d loss_critic_i  --
+    every critic iteration back-propagates through the critic INTO the generator, including the
+    gradient-penalty's second-order term through the interpolated images;
+  * there is no zero_grad before ``lossG.backward()`` (:163).
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, LAMBDA_GP, N_CRITIC, Z_DIM, CART, CriticRT, GenRT,
+                     _LayerRT, _conv_out, default_ops)
+from .layers import FlatParams
+
+
+class _BN:
+    """Buffers of one BatchNorm'ed tensor: pre-BN conv output y, activation a, their gradients."""
+
+    def __init__(self, ops, shape, C, alloc_a=True):
+        self.y, self.dy = ops.empty(shape), ops.empty(shape)
+        self.a = ops.empty(shape) if alloc_a else None
+        self.da = ops.empty(shape) if alloc_a else None
+        self.mr = ops.empty((1, C, 2), ops.f32)
+        self.stats = ops.zeros((1, C, 2), ops.f64)
+        self.sums = ops.zeros((1, C, 2), ops.f64)
+
+
+def _bn_forward(ops, bn, buf, out, act, training, residual=None):
+    C = buf.y.shape[-1]
+    if training:
+        ops.zero(buf.stats)
+        ops.col_stats(buf.y, buf.stats, 1)
+        ops.bn_finalize(buf.stats, buf.y.numel() // C, buf.mr, bn.running_mean, bn.running_var, bn.num_batches_tracked, 1, True)
+    else:
+        ops.bn_eval_mr(bn.running_mean, bn.running_var, buf.mr)
+    ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
+
+
+def _bn_backward(ops, bn, buf, da, a_out, act):
+    """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads."""
+    ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act)
+    ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act)
+    ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad)
+    return buf.dy
+
+
+class Gen2RT:
+    """Stage-II generator runtime."""
+
+    def __init__(self, ops, module, B, x_in=None, out=None):
+        self.ops, self.m, self.B = ops, module, B
+        self.fp = FlatParams(module, ops.device, dtype=ops.f32)
+        m = module
+        f32 = ops.f32
+        self.ds0 = _LayerRT(ops, m.down_sampler[0], None)
+        self.ds2 = _LayerRT(ops, m.down_sampler[2][0], m.down_sampler[2][1])
+        self.res = [[_LayerRT(ops, c, bn) for c, bn in blk.conv_layers()] for blk in m.residual_blocks]
+        self.ups = [_LayerRT(ops, m.up_sampler[i][0], m.up_sampler[i][1]) for i in range(3)]
+        self.up3 = _LayerRT(ops, m.up_sampler[3], None)
+        # thin (3-channel) operators run as 1x1 convs over a patch matrix
+        self.K0 = 3 * 16
+        self.pf_ds0 = ops.empty((self.ds0.co, 1, 1, self.K0))
+        self.pf_up3 = ops.empty((self.up3.co, 1, 1, self.K0))
+        self.x_in = x_in if x_in is not None else ops.empty((B, 64, 64, 3))
+        self.P0 = ops.empty((B, 32, 32, self.K0))
+        self.a1, self.da1, self.dy0 = ops.empty((B, 32, 32, 128)), ops.empty((B, 32, 32, 128)), ops.empty((B, 32, 32, 128))
+        self.b2 = _BN(ops, (B, 16, 16, 512), 512)
+        self.c_hat = None
+        self.dc_hat = ops.empty((B, m.C_TEXT), f32)
+        self.X = [ops.empty((B, 16, 16, 640)) for _ in range(5)]       # residual-block boundaries
+        self.dX = [ops.empty((B, 16, 16, 640)) for _ in range(5)]
+        self.dz = ops.empty((B, 16, 16, 640))
+        self.rb = [[_BN(ops, (B, 16, 16, 320), 320), _BN(ops, (B, 16, 16, 320), 320), _BN(ops, (B, 16, 16, 640), 640, alloc_a=False)]
+                   for _ in range(4)]
+        self.ub = [_BN(ops, (B, 32, 32, 320), 320), _BN(ops, (B, 64, 64, 160), 160), _BN(ops, (B, 128, 128, 80), 80)]
+        self.out = out if out is not None else ops.empty((B, 256, 256, 3))
+        self.dpre = ops.empty((B, 256, 256, 3))
+        self.Pd = ops.empty((B, 128, 128, self.K0))
+        self.ones = torch.ones(B, dtype=f32).to(ops.device)
+
+    def all_layers(self):
+        out = [self.ds0, self.ds2]
+        for blk in self.res:
+            out += blk
+        return out + self.ups + [self.up3]
+
+    def refresh_weights(self):
+        ops = self.ops
+        for L in self.all_layers():
+            L.pack(ops)
+        ops.pack_weight(self.ds0.conv.weight.data.view(self.ds0.co, self.K0, 1, 1), self.pf_ds0, None)
+        ops.pack_weight(self.up3.conv.weight.data.view(self.up3.co, self.K0, 1, 1), self.pf_up3, None)
+
+    def forward(self, c_hat, training=True):
+        """x_in (NHWC T) and c_hat [B,128] fp32 -> self.out [B,256,256,3] (generator_2.py:59-67)."""
+        ops = self.ops
+        self.c_hat = c_hat
+        L = self.ds0
+        ops.patchify(self.x_in, self.P0, L.k, L.s, L.p)
+        ops.conv_fprop(self.P0, self.pf_ds0, L.conv.bias.data, self.a1, 1, 1, 0, act=ACT_LRELU)
+        L = self.ds2
+        ops.conv_fprop(self.a1, L.pf, None, self.b2.y, L.k, L.s, L.p)
+        _bn_forward(ops, L.bn, self.b2, self.b2.a, ACT_LRELU, training)
+        ops.concat_rep(self.b2.a, c_hat, self.X[0])
+        for r in range(4):
+            l1, l2, l3 = self.res[r]
+            b1, b2, b3 = self.rb[r]
+            ops.conv_fprop(self.X[r], l1.pf, None, b1.y, 3, 1, 1)
+            _bn_forward(ops, l1.bn, b1, b1.a, ACT_RELU, training)
+            ops.conv_fprop(b1.a, l2.pf, None, b2.y, 3, 1, 1)
+            _bn_forward(ops, l2.bn, b2, b2.a, ACT_RELU, training)
+            ops.conv_fprop(b2.a, l3.pf, None, b3.y, 3, 1, 1)
+            _bn_forward(ops, l3.bn, b3, self.X[r + 1], ACT_RELU, training, residual=self.X[r])     # x += identity; relu
+        x = self.X[4]
+        for i in range(3):
+            L, b = self.ups[i], self.ub[i]
+            ops.conv_dgrad(x, L.pd, None, b.y, L.k, L.s, L.p)
+            _bn_forward(ops, L.bn, b, b.a, ACT_RELU, training)
+            x = b.a
+        L = self.up3
+        ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
+        return self.out
+
+    def backward(self, dout):
+        """Accumulates parameter gradients; leaves d/d c_hat in self.dc_hat (fp32)."""
+        ops = self.ops
+        L = self.up3
+        ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
+        ops.colsum(self.dpre, L.conv.bias.grad)
+        ops.patchify(self.dpre, self.Pd, L.k, L.s, L.p)
+        ops.conv_wgrad(self.Pd, self.ub[2].a, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
+        ops.conv_fprop(self.Pd, self.pf_up3, None, self.ub[2].da, 1, 1, 0)
+        for i in range(2, -1, -1):
+            L, b = self.ups[i], self.ub[i]
+            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU)
+            x_in = self.ub[i - 1].a if i > 0 else self.X[4]
+            ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p)
+            ops.conv_fprop(dy, L.pf, None, self.ub[i - 1].da if i > 0 else self.dX[4], L.k, L.s, L.p)
+        for r in range(3, -1, -1):
+            l1, l2, l3 = self.res[r]
+            b1, b2, b3 = self.rb[r]
+            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU)
+            ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
+            ops.conv_wgrad(b2.a, dy3, l3.conv.weight.grad, 3, 1, 1)
+            ops.conv_dgrad(dy3, l3.pd, None, b2.da, 3, 1, 1)
+            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU)
+            ops.conv_wgrad(b1.a, dy2, l2.conv.weight.grad, 3, 1, 1)
+            ops.conv_dgrad(dy2, l2.pd, None, b1.da, 3, 1, 1)
+            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU)
+            ops.conv_wgrad(self.X[r], dy1, l1.conv.weight.grad, 3, 1, 1)
+            ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
+            ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)
+        ops.split_rep_bwd(self.dX[0], self.b2.da, self.dc_hat)
+        L = self.ds2
+        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU)
+        ops.conv_wgrad(self.a1, dy2, L.conv.weight.grad, L.k, L.s, L.p)
+        ops.conv_dgrad(dy2, L.pd, None, self.da1, L.k, L.s, L.p)
+        L = self.ds0
+        ops.act_bwd(self.da1, self.a1, self.dy0, ACT_LRELU)
+        ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
+        ops.colsum(self.dy0, L.conv.bias.grad)
+        return self.dc_hat
+
+
+class Stage2Engine:
+    """One reference Stage-II outer step with caller-supplied noise."""
+
+    def __init__(self, ca1, gen1, ca2, critic2, gen2, batch_size, ops=None, lr=1e-3, comm=None):
+        ops = ops or default_ops()
+        self.ops, self.B = ops, batch_size
+        B = batch_size
+        self.d = CriticRT(ops, critic2, B)
+        self.ca1, self.ca2 = CART(ops, ca1), CART(ops, ca2)
+        self.ca1.ensure(B)
+        self.ca2.ensure(B)
+        self.g1 = GenRT(ops, gen1, B)                                   # frozen, eval mode
+        self.g2 = Gen2RT(ops, gen2, B, x_in=self.g1.out, out=self.d.group_view(self.d.a[0], 1, 1))
+        for fp in (self.d.fp, self.g2.fp, self.ca2.fp):
+            fp.set_lr(lr)
+        self.losses = ops.zeros((4,), ops.f32)
+        self.comm = comm
+        self.one_minus_eps = ops.empty((B,), ops.f32)
+        self.dcg2 = ops.zeros((B, 1, 1, ca2.c_dim), ops.f32)
+        if comm is not None:
+            for fp in (self.d.fp, self.g2.fp, self.ca2.fp, self.g1.fp, self.ca1.fp):
+                comm.broadcast_params(fp.flat)
+        self.g1.refresh_weights()
+        self.refresh_all()
+        ops.zero(self.g2.fp.grad)
+        ops.zero(self.ca2.fp.grad)
+
+    def refresh_all(self):
+        self.d.refresh_weights()
+        self.g2.refresh_weights()
+
+    def optimizer_step(self, fp):
+        if self.comm is not None:
+            self.comm.allreduce_async(fp.grad)
+            self.comm.wait_all()
+        self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
+
+    def load_batch(self, real_nchw, tem, tem_mis):
+        d = self.d
+        self.ops.nchw_to_nhwc(real_nchw, d.group_view(d.a[0], 0, 1))
+        d.set_text(tem, tem_mis)
+
+    def _generate(self, z, eps_ca1, eps_ca2):
+        d, B = self.d, self.B
+        tem = d.tem_all[:B]
+        self.ca1.forward(tem, eps_ca1, z, cg=self.g1.cg)           # stage_2_train_fn.py:124-127 (frozen)
+        self.g1.forward(training=False)                             # :128, eval-mode BN
+        st2 = self.ca2.forward(tem, eps_ca2, None)                  # :130
+        self.g2.forward(st2.c_hat, training=True)                   # :131 -> critic group 1
+
+    def _generator_backward(self, dfake, kl_scale):
+        """Back-propagate d loss / d fake_256 into G2 and CA2 (accumulating)."""
+        ops = self.ops
+        dc = self.g2.backward(dfake)                                # fp32 [B,128]
+        self.ca2.backward_from_dc(dc, kl_scale)
+
+    def critic_iteration(self, z, eps_ca1, eps_ca2, eps_gp):
+        ops, d, B = self.ops, self.d, self.B
+        self._generate(z, eps_ca1, eps_ca2)
+        X = d.a[0]
+        ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
+        d.forward(0, 3, dup_first=2, training=True, with_mismatched=True)        # :133-140 + utils.py:13
+        ops.zero(d.fp.grad)                                         # :153
+        ops.zero(d.dA); ops.zero(d.dBv)
+        d.gp_first_order()
+        ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])     # :148-152
+        d.gp_second_order(2.0 * LAMBDA_GP / B)
+        d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=True)       # :154
+        d.text_backward(d.coef_text, 2 * B, 0.0, True, None)
+        # d loss_critic / d fake_256 = d/d(fake group) + (1 - eps) * d/d(interpolated group)  (utils.py:11, not detached)
+        ops.affine_f32(eps_gp, -1.0, 1.0, self.one_minus_eps)
+        dfake = d.group_view(d.dx, 1, 1)
+        ops.scale_rows_add(d.group_view(d.dx, 2, 1), self.one_minus_eps, dfake, True)
+        self._generator_backward(dfake, 0.0)                        # accumulates into G2 / CA2 (:154, no zero_grad)
+        self.optimizer_step(d.fp)                                   # :155
+        d.refresh_weights()
+
+    def generator_step(self):
+        ops, d, B = self.ops, self.d, self.B
+        d.forward(1, 1, dup_first=1, training=True)                 # :157
+        st = self.ca2.st
+        ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])  # :158-162
+        d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
+        self._generator_backward(d.group_view(d.dx, 1, 1), 1.0)     # :163 (no zero_grad before)
+        self.optimizer_step(self.g2.fp)                             # :164
+        self.optimizer_step(self.ca2.fp)                            # :167
+        ops.zero(self.g2.fp.grad)                                   # :165
+        ops.zero(self.ca2.fp.grad)                                  # :168
+        self.g2.refresh_weights()
+
+    def outer_step(self, z, eps_ca1, eps_ca2, eps_gp):
+        for it in range(N_CRITIC):
+            self.critic_iteration(z[it], eps_ca1[it], eps_ca2[it], eps_gp[it])
+        self.generator_step()

@@ -24,10 +24,13 @@ _P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 _SIGS = {
     "sg_zero": [_P, _L, _P],
     "sg_fill_f32": [_P, _F, _L, _P],
+    "sg_affine_f32": [_P, _F, _F, _P, _L, _P],
     "sg_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
     "sg_patchify": [_P, _P] + [_I] * 10 + [_P],
+    "sg_concat_rep": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "sg_split_rep_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "sg_conv_fprop": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_dgrad": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_wgrad": [_P, _P, _P] + [_I] * 11 + [_P],
@@ -156,6 +159,10 @@ class CudaOps:
         assert t.dtype == torch.float32
         self._ck(self.lib.sg_fill_f32(_ptr(t), float(value), t.numel(), self._st()))
 
+    def affine_f32(self, x, a, b, out):
+        self._c(x, out)
+        self._ck(self.lib.sg_affine_f32(_ptr(x), float(a), float(b), _ptr(out), x.numel(), self._st()))
+
     # ---- layout
     def nchw_to_nhwc(self, src, dst):
         self._c(src, dst)
@@ -175,6 +182,19 @@ class CudaOps:
         Co, Ci, k, _ = w.shape
         ref = pf if pf is not None else pd
         self._ck(self.lib.sg_pack_weight(_ptr(w), _ptr(pf), _ptr(pd), Co, Ci, k * k, self._dt_of(ref), self._st()))
+
+    def concat_rep(self, x, c, out):
+        self._c(x, c, out)
+        N, H, W, Cx = x.shape
+        Cc = c.shape[1]
+        assert out.shape[-1] == Cx + Cc and c.dtype == torch.float32
+        self._ck(self.lib.sg_concat_rep(_ptr(x), _ptr(c), _ptr(out), N, H * W, Cx, Cc, self._dt_of(x), self._st()))
+
+    def split_rep_bwd(self, dout, dx, dc):
+        self._c(dout, dx, dc)
+        N, H, W, Cx = dx.shape
+        Cc = dc.shape[1]
+        self._ck(self.lib.sg_split_rep_bwd(_ptr(dout), _ptr(dx), _ptr(dc), N, H * W, Cx, Cc, self._dt_of(dout), self._st()))
 
     def patchify(self, x, P, k, s, p):
         self._c(x, P)

@@ -53,6 +53,8 @@ int64_t sg_launch_count(void);
 /* ---- memory helpers ------------------------------------------------------------------------ */
 int sg_zero(void* ptr, int64_t bytes, void* stream);
 int sg_fill_f32(float* ptr, float value, int64_t n, void* stream);
+/* out = a*x + b on fp32 vectors (e.g. 1 - eps of utils.py:11) */
+int sg_affine_f32(const float* x, float a, float b, float* out, int64_t n, void* stream);
 
 /* ---- layout: the reference API is NCHW fp32 (e.g. generator_1.py:38-40 output) -------------- */
 int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dtype, void* stream);
@@ -65,6 +67,11 @@ int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, i
  * a 1x1 convolution on the tensor-core kernels */
 int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p,
                 int dtype, void* stream);
+
+/* out[n,hw,:Cx] = x, out[n,hw,Cx:] = c[n]  (generator_2.py:61-63 reshape/repeat/cat);  backward:
+ * dx = dout[..., :Cx], dc[n] (fp32) = sum_hw dout[n,hw,Cx:] */
+int sg_concat_rep(const void* x, const float* c, void* out, int N, int HW, int Cx, int Cc, int dtype, void* stream);
+int sg_split_rep_bwd(const void* dout, void* dx, float* dc, int N, int HW, int Cx, int Cc, int dtype, void* stream);
 
 /* ---- convolution operator (replaces nn.Conv2d / nn.ConvTranspose2d and their autograd:
  *      generator_1.py:20,26  generator_2.py:30,46,55,71,87  discrminator_1.py:10,29

@@ -349,6 +349,8 @@ def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_
         out["critic_grads"].append(tr["d2"].grads())
         out["loss_critic"].append(loss_c.detach().clone())
         if it == 0:
+            out["g2_grads_it0"] = tr["g2"].grads()             # what one critic backward leaves in G2
+            out["ca2_grads_it0"] = tr["ca2"].grads()
             out["first"] = dict(fake_64=fake_64.detach().clone(), fake=fake.detach().clone(),
                                 s_real=s_real.detach().clone(), s_mis=s_mis.detach().clone(),
                                 s_fake=s_fake.detach().clone(), gp=gp.detach().clone())

@@ -340,6 +340,22 @@ class EmuOps:
         denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
         p.addcdiv_(m, denom, value=-lr / bc1)
 
+    def concat_rep(self, x, c, out):
+        """out[n,h,w,:Cx] = x ; out[n,h,w,Cx:] = c[n]  (generator_2.py:61-63: reshape/repeat/cat)."""
+        Cx = x.shape[-1]
+        out[..., :Cx] = x.to(out.dtype)
+        out[..., Cx:] = c[:, None, None, :].to(out.dtype)
+
+    def split_rep_bwd(self, dout, dx, dc):
+        """dx = dout[..., :Cx] ; dc[n] (fp32, =) = sum_hw dout[n,h,w,Cx:]."""
+        Cx = dx.shape[-1]
+        dx.copy_(dout[..., :Cx])
+        dc.copy_(dout[..., Cx:].double().sum((1, 2)).to(dc.dtype))
+
+    def affine_f32(self, x, a, b, out):
+        """out = a*x + b  (fp32 vectors)."""
+        out.copy_(a * x + b)
+
     def fill(self, t, value):
         t.fill_(value)
 

@@ -321,3 +321,14 @@ def test_conv_wgrad_tcgen05(case):
 def test_patchify(mode):
     x = rnd(3, 16, 16, 3)
     run_pair(mode, "patchify", [T(x), T(torch.zeros(3, 8, 8, 48)), 4, 2, 1], [1])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_concat_split_affine(mode):
+    N, H, Cx, Cc = 3, 16, 512, 128
+    x, c = rnd(N, H, H, Cx), rnd(N, Cc)
+    run_pair(mode, "concat_rep", [T(x), F(c), T(torch.zeros(N, H, H, Cx + Cc))], [2])
+    dout = rnd(N, H, H, Cx + Cc, seed=2)
+    run_pair(mode, "split_rep_bwd", [T(dout), T(torch.zeros(N, H, H, Cx)), F(torch.zeros(N, Cc))], [1, 2],
+             tol=dict(rtol=1e-3, atol=1e-4))
+    run_pair("fp32", "affine_f32", [F(torch.rand(37)), -1.0, 1.0, F(torch.zeros(37))], [3])
