@@ -262,3 +262,37 @@ class Stage2Engine:
         for it in range(N_CRITIC):
             self.critic_iteration(z[it], eps_ca1[it], eps_ca2[it], eps_gp[it])
         self.generator_step()
+
+    # -- whole step behind static buffers, replayed as one CUDA graph (single GPU)
+    def step(self, real_nchw, tem, tem_mis, z, eps_ca1, eps_ca2, eps_gp, use_graph=True):
+        ops, B = self.ops, self.B
+        if getattr(self, "s_real", None) is None:
+            f = ops.f32
+            self.s_real = ops.empty((B, 3, 256, 256), f)
+            self.s_z = ops.empty((N_CRITIC, B, Z_DIM), f)
+            self.s_e1 = ops.empty((N_CRITIC, B, self.ca1.m.c_dim), f)
+            self.s_e2 = ops.empty((N_CRITIC, B, self.ca2.m.c_dim), f)
+            self.s_egp = ops.empty((N_CRITIC, B), f)
+            self.graph, self.launches_per_step = None, None
+        for dst, src in ((self.s_real, real_nchw), (self.d.tem_all[:B], tem), (self.d.tem_all[B:], tem_mis), (self.s_z, z),
+                         (self.s_e1, eps_ca1), (self.s_e2, eps_ca2), (self.s_egp, eps_gp)):
+            dst.copy_(src, non_blocking=True)
+
+        def body():
+            ops.nchw_to_nhwc(self.s_real, self.d.group_view(self.d.a[0], 0, 1))
+            self.outer_step(self.s_z, self.s_e1, self.s_e2, self.s_egp)
+        if not use_graph or getattr(ops, "is_emulator", False) or self.comm is not None:
+            n0 = ops.launch_count() if hasattr(ops, "launch_count") else 0
+            body()
+            if hasattr(ops, "launch_count"):
+                self.launches_per_step = ops.launch_count() - n0
+            return
+        if self.graph is None:
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self.launches_per_step = ops.launch_count() - n0
+            self.graph = g
+        self.graph.replay()
