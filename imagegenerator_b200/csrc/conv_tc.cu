@@ -251,6 +251,190 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 2-CTA variant
+// Same dataflow with a CTA PAIR (cluster 2x1x1, tcgen05 cta_group::2): the pair owns a 256-row x BN tile,
+// each CTA stages its own 128 rows of A and HALF of the weight slab (BN/2 rows); one tcgen05.mma
+// (M=256, N=BN, K=16) issued by the leader reads both CTAs' shared memory and writes each CTA's half of
+// the accumulator into its own TMEM.  Operand traffic per FLOP halves for B: 32 KB per 128x256x64 block
+// per CTA = 128 FLOP/B instead of 64.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0
+__device__ __forceinline__ void mbar_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & PEER_BIT_MASK), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[4], empty_bar[4], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int half_n = P.BN / 2;
+    const int b_stage_bytes = half_n * 128;
+    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+
+    const int phase = blockIdx.z;
+    const int ph = phase / P.s, pw = phase - ph * P.s;
+    int nth, ntw, rh = 0, rw = 0, base_h = 0, base_w = 0;
+    if (P.mode == 0) {
+        nth = ntw = P.k;
+    } else {
+        rh = (ph + P.p) % P.s; rw = (pw + P.p) % P.s;
+        nth = (P.k - rh + P.s - 1) / P.s; ntw = (P.k - rw + P.s - 1) / P.s;
+        base_h = (ph + P.p - rh) / P.s; base_w = (pw + P.p - rw) / P.s;
+    }
+    const int nkb = nth * ntw * P.cblocks;
+    const int m0 = blockIdx.x * 128;                 // this CTA's 128 rows (blockIdx.x = 2*pair + rank)
+    const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
+    const int nt0 = blockIdx.y * P.BN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % P.stages, it = kb / P.stages;
+                mbar_wait(&empty_bar[st], (it & 1) ^ 1);
+                mbar_expect_tx_leader(&full_bar[st], (uint32_t)stage_bytes);
+                const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
+                const int th = tap / ntw, tw = tap - th * ntw;
+                int ca_w, ca_h, bk;
+                if (P.mode == 0) {
+                    ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
+                    bk = (th * P.k + tw) * P.Ck + cb * 64;
+                } else {
+                    ca_w = w0 + base_w - tw; ca_h = h0 + base_h - th;
+                    bk = ((rh + P.s * th) * P.k + (rw + P.s * tw)) * P.Ck + cb * 64;
+                }
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                tma2_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
+                tma2_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk, nt0 + (int)rank * half_n);
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((256u >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % P.stages, it = kb / P.stages;
+                mbar_wait(&full_bar[st], it & 1);
+                tc_fence_after();
+                const uint32_t sa = base + (uint32_t)st * stage_bytes;
+                const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    uint64_t ad = make_kmajor_sw128_desc(sa + k4 * 32);
+                    uint64_t bd = make_kmajor_sw128_desc(sb + k4 * 32);
+                    tc2_mma_bf16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+                }
+                tc2_commit_mc(&empty_bar[st]);
+            }
+            tc2_commit_mc(&accum_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int dn = r / (P.bw * P.bh), rem = r - dn * (P.bw * P.bh);
+        const int dh = rem / P.bw, dw = rem - dh * P.bw;
+        const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
+        const bool row_ok = n_img < P.M / (P.Hq * P.Wq);
+        int oh = hh, ow = ww;
+        if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
+        bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total;
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const bool vec_ok = (P.n_total % 8) == 0;
+        for (int c0 = 0; c0 < P.BN; c0 += 16) {
+            uint32_t v[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int n_base = nt0 + c0;
+            if (!row_ok || n_base >= P.n_total) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(v[j]);
+                int n = n_base + j;
+                if (P.bias && n < P.n_total) x += P.bias[n];
+                f[j] = act_fwd(x, P.act);
+            }
+            if (vec_ok && n_base + 16 <= P.n_total) {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
+                o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
+                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                *reinterpret_cast<uint4*>(orow + n_base) = o0;
+                *reinterpret_cast<uint4*>(orow + n_base + 8) = o1;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n_base + j < P.n_total) orow[n_base + j] = __float2bfloat16_rn(f[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]  as  D[co][(tap,ci)] = A^T B with the pixel
 // index as the reduction: both operands are "MN-major" (channels contiguous, pixels strided), which
@@ -488,6 +672,8 @@ static int pick_bn(int n_total) {
 }
 
 static bool g_attr_set = false;
+static bool g_attr2_set = false;
+int g_use_tc2 = 1;     // 2-CTA (cta_group::2) tiles for wide layers; sg_set_option("tc2", 0) disables
 
 // mode 0: fprop (act = x [N][H][W][Ck], out = y [N][Ho][Wo][n_total]);
 // mode 1: dgrad (act = dy [N][Ho][Wo][Ck], out = dx [N][H][W][n_total])
@@ -526,6 +712,61 @@ static int launch_conv_tc(int mode, const void* act, const void* wpack, const fl
     conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P);
     g_launches.fetch_add(1);
     return check_launch("conv_tc");
+}
+
+// CTA-pair launch: 256-row x BN tiles (BN = 128 or 256)
+static int launch_conv_tc2(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
+                           int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, cudaStream_t st) {
+    int e = ensure_encode();
+    if (e) return e;
+    TcParams P;
+    int aH, aW;
+    if (mode == 0) {
+        P.Hq = Ho; P.Wq = Wo; P.Ck = Ci; P.n_total = Co; P.outH = Ho; P.outW = Wo; aH = H; aW = W;
+    } else {
+        P.Hq = H / s; P.Wq = W / s; P.Ck = Co; P.n_total = Ci; P.outH = H; P.outW = W; aH = Ho; aW = Wo;
+    }
+    if (!choose_box(P.Hq, P.Wq, &P.bw, &P.bh, &P.bn)) { set_error("conv_tc2: grid not tileable"); return SG_ERR_UNSUPPORTED; }
+    P.M = N * P.Hq * P.Wq;
+    {   // widest tile (<= 256, multiple of 32) that wastes the fewest padded columns
+        int best = 128, best_waste = 1 << 30;
+        for (int bn = 256; bn >= 128; bn -= 32) {
+            int waste = (P.n_total + bn - 1) / bn * bn - P.n_total;
+            if (waste < best_waste) { best_waste = waste; best = bn; }
+        }
+        P.BN = best;
+    }
+    P.cblocks = (P.Ck + 63) / 64;
+    P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
+    P.stages = 3;
+    P.tmem_cols = 32;
+    while (P.tmem_cols < P.BN) P.tmem_cols *= 2;
+    CUtensorMap tmA, tmB;
+    int es = mode == 0 ? s : 1;
+    if ((e = get_act_map(act, N, aH, aW, P.Ck, P.bw, P.bh, P.bn, es, &tmA))) return e;
+    if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, P.BN / 2, &tmB))) return e;
+    size_t smem = (size_t)P.stages * (A_STAGE_BYTES + (P.BN / 2) * 128) + 1024;
+    if (!g_attr2_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(tc2): %s", cudaGetErrorString(ce)); return (int)ce; }
+        g_attr2_set = true;
+    }
+    int phases = mode == 0 ? 1 : s * s;
+    int mt = (P.M + 127) / 128;
+    mt = (mt + 1) / 2 * 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(mt, (P.n_total + P.BN - 1) / P.BN, phases);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, tmA, tmB, P);
+    if (ce != cudaSuccess) { set_error("conv_tc2 launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+    g_launches.fetch_add(1);
+    return check_launch("conv_tc2");
 }
 
 static bool choose_box64(int Ho, int Wo, int* bw, int* bh, int* bn) {
@@ -613,10 +854,20 @@ int sg_conv_tc_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, 
     return 1;
 }
 
+int sg_set_option(const char* name, int value) {
+    if (name && name[0] == 't' && name[1] == 'c' && name[2] == '2') { g_use_tc2 = value; return 0; }
+    set_error("unknown option");
+    return SG_ERR_BAD_ARG;
+}
+
+static bool want_tc2(int n_total, int M) { return g_use_tc2 && n_total >= 128 && n_total % 32 == 0 && M >= 256; }
+
 int sg_conv_fprop_tc(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho, int Wo,
                      int Co, int k, int s, int p, int act, int dtype, void* stream) {
     SG_REQUIRE(dtype == SG_BF16, "conv_fprop_tc: bf16 only");
     SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc: unsupported shape");
+    if (want_tc2(Co, N * Ho * Wo))
+        return launch_conv_tc2(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
     return launch_conv_tc(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
 }
 
@@ -625,6 +876,8 @@ int sg_conv_dgrad_tc(const void* dy, const void* pd, const float* bias, void* dx
     SG_REQUIRE(dtype == SG_BF16, "conv_dgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_dgrad_tc: unsupported shape");
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc: inconsistent sizes");
+    if (want_tc2(Ci, N * (H / s) * (W / s)))
+        return launch_conv_tc2(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
     return launch_conv_tc(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
 }
 

@@ -69,7 +69,7 @@ _SIGS = {
     "sg_adam_step": [_P, _P, _P, _P, _P, _L, _P],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported"])
+EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option"])
 
 
 def load_library(path=LIB_PATH):
@@ -87,6 +87,8 @@ def load_library(path=LIB_PATH):
     lib.sg_conv_tc_supported.restype = _I
     lib.sg_conv_wgrad_tc_supported.argtypes = [_I] * 10
     lib.sg_conv_wgrad_tc_supported.restype = _I
+    lib.sg_set_option.argtypes = [_c.c_char_p, _I]
+    lib.sg_set_option.restype = _I
     lib.sg_version.restype = _I
     lib.sg_last_error.restype = _c.c_char_p
     lib.sg_check_device.restype = _I
@@ -126,6 +128,9 @@ class CudaOps:
     def _ck(self, rc):
         if rc != 0:
             raise RuntimeError(f"libsgb200 error {rc}: {self.lib.sg_last_error().decode()}")
+
+    def set_option(self, name, value):
+        self._ck(self.lib.sg_set_option(name.encode(), int(value)))
 
     def launch_count(self):
         return int(self.lib.sg_launch_count())

@@ -49,6 +49,8 @@ const char* sg_last_error(void);
 int sg_check_device(void);
 /* number of kernels launched through this library since load (all threads) */
 int64_t sg_launch_count(void);
+/* tuning switches: "tc2" = 1/0 use CTA-pair (cta_group::2) tiles for layers with >= 128 output channels */
+int sg_set_option(const char* name, int value);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
 int sg_zero(void* ptr, int64_t bytes, void* stream);
