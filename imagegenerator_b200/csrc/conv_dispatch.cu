@@ -18,6 +18,13 @@ int sg_conv_tc_supported(int, int, int, int, int, int, int, int, int, int, int);
 int sg_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, void*);
 int sg_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int, int, int);
 
+int sg_conv_tc_stats_supported(int, int, int, int, int, int, int, int, int, int, int, int);
+int sg_conv_fprop_tc_stats(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, int, int, int, int,
+                           void*);
+int sg_conv_dgrad_tc_stats(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, int, int, int, int,
+                           void*);
+int sg_col_stats(const void*, double*, int64_t, int, int, int, void*);
+
 static bool tc_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -44,5 +51,25 @@ int sg_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,
     if (dtype == SG_BF16 && tc_enabled() && sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p))
         return sg_conv_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
     return sg_conv_wgrad_ffma(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
+}
+
+// y = conv(x, W) and stats[groups][Co][2] += (sum, sum^2) of y per image group -- the batch statistics of the
+// BatchNorm2d that follows every bias-free conv of the reference (e.g. discrminator_1.py:29-37).  Fused into the
+// tensor-core epilogue when the shape allows, otherwise conv + sg_col_stats.
+int sg_conv_fprop_stats(const void* x, const void* pf, void* y, double* stats, int groups, int N, int H, int W, int Ci,
+                        int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
+    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+        return sg_conv_fprop_tc_stats(x, pf, y, stats, groups, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
+    int e = sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
+    if (e) return e;
+    return sg_col_stats(y, stats, (int64_t)(N / groups) * Ho * Wo, Co, groups, dtype, stream);
+}
+int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats, int groups, int N, int H, int W, int Ci,
+                        int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
+    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+        return sg_conv_dgrad_tc_stats(dy, pd, dx, stats, groups, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
+    int e = sg_conv_dgrad(dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
+    if (e) return e;
+    return sg_col_stats(dx, stats, (int64_t)(N / groups) * H * W, Ci, groups, dtype, stream);
 }
 }

@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <map>
+#include <string.h>
 #include <mutex>
 #include <tuple>
 #include <vector>
@@ -435,6 +436,323 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent kernel
+// conv_tcp_kernel<CG>: the same dataflow as a PERSISTENT kernel -- one CTA (CG=1) or CTA pair (CG=2,
+// cta_group::2) per SM / SM pair walks a static list of output tiles.  The accumulator is double
+// buffered in TMEM (2 x BN columns), so the epilogue warps drain tile i (tcgen05.ld -> bias/act -> bf16
+// NHWC rows, plus the per-channel (sum, sum^2) of the BatchNorm that follows, reduced across the 32 rows
+// of a warp by a shuffle butterfly) while the MMA warp already accumulates tile i+1; barrier set-up, TMEM
+// allocation and the pipeline fill are paid once per SM instead of once per tile.
+//
+//   warp 0    : TMA producer             full[s] / empty[s] ring (up to 8 stages)
+//   warp 1    : MMA issuer (leader CTA)  tcgen05.commit -> empty[s], -> tfull[buf]
+//   warps 2-5 : epilogue                 wait tfull[buf] ... arrive tempty[buf] (on the leader)
+struct TcpParams {
+    int Hq, Wq, n_img;    // output grid handled per phase, images
+    int bw, bh, bn;       // pixel box of one 128-row tile
+    int n_total, BN;      // output channels, tile width
+    int Ck, cblocks;
+    int mode, k, s, p;
+    int outH, outW;
+    int act;
+    int stages;
+    int tmem_cols, acc_stride;
+    int m_tiles, n_tiles, total_tiles;   // m_tiles counts CG*128-row cluster tiles
+    int imgs_per_group;
+    const float* bias;
+    bf16* out;
+    double* stats;        // [groups][n_total][2] or NULL
+};
+
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// per-column sums over the 32 lanes of a warp for 16 columns held as s[0..15]: recursive halving, 16 shuffles.
+// On return s[0] of lane l is the sum of column  8*b4 + 4*b3 + 2*b2 + b1  (b_i = bit i of l); lanes l and l^1 agree.
+__device__ __forceinline__ void warp_colsum16(float (&s)[16], int lane) {
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float send = hi ? s[j] : s[j + 8], keep = hi ? s[j + 8] : s[j];
+            s[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float send = hi ? s[j] : s[j + 4], keep = hi ? s[j + 4] : s[j];
+            s[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float send = hi ? s[j] : s[j + 2], keep = hi ? s[j + 2] : s[j];
+            s[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        float send = hi ? s[0] : s[1], keep = hi ? s[1] : s[0];
+        s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+}
+
+struct PhaseGeo {
+    int ph, pw, nth, ntw, rh, rw, base_h, base_w;
+};
+__device__ __forceinline__ PhaseGeo phase_geo(const TcpParams& P, int phase) {
+    PhaseGeo g;
+    g.ph = phase / P.s; g.pw = phase - g.ph * P.s;
+    g.rh = g.rw = g.base_h = g.base_w = 0;
+    if (P.mode == 0) {
+        g.nth = g.ntw = P.k;
+    } else {
+        g.rh = (g.ph + P.p) % P.s; g.rw = (g.pw + P.p) % P.s;
+        g.nth = (P.k - g.rh + P.s - 1) / P.s; g.ntw = (P.k - g.rw + P.s - 1) / P.s;
+        g.base_h = (g.ph + P.p - g.rh) / P.s; g.base_w = (g.pw + P.p - g.rw) / P.s;
+    }
+    return g;
+}
+
+constexpr int TCP_EPI_WARPS = 8;
+constexpr int TCP_THREADS = 64 + 32 * TCP_EPI_WARPS;
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcpParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float sstat[2][256][2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int b_rows = P.BN / CG;
+    const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
+    const int tiles_per_phase = P.n_tiles * P.m_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TCP_EPI_WARPS * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (P.stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * 256 * 2; i += TCP_THREADS) (&sstat[0][0][0])[i] = 0.f;
+    if (warp == 1) {
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                         "r"((uint32_t)P.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                         "r"((uint32_t)P.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0;
+            uint32_t par = 1;                         // parity to wait for on empty[st]: first round passes
+            for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters) {
+                const int phase = tile / tiles_per_phase, r = tile - phase * tiles_per_phase;
+                const int nt = r / P.m_tiles, mt = r - nt * P.m_tiles;
+                const PhaseGeo g = phase_geo(P, phase);
+                const int m0 = (mt * CG + (int)rank) * 128;
+                const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
+                const int nt0 = nt * P.BN + (int)rank * b_rows;
+                for (int th = 0; th < g.nth; ++th) {
+                    for (int tw = 0; tw < g.ntw; ++tw) {
+                        int ca_w, ca_h, bk;
+                        if (P.mode == 0) {
+                            ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
+                            bk = (th * P.k + tw) * P.Ck;
+                        } else {
+                            ca_w = w0 + g.base_w - tw; ca_h = h0 + g.base_h - th;
+                            bk = ((g.rh + P.s * th) * P.k + (g.rw + P.s * tw)) * P.Ck;
+                        }
+                        for (int cb = 0; cb < P.cblocks; ++cb) {
+                            mbar_wait(&empty_bar[st], par);
+                            uint8_t* sa = smem + (size_t)st * stage_bytes;
+                            if (CG == 2) {
+                                mbar_expect_tx_leader(&full_bar[st], (uint32_t)stage_bytes);
+                                tma2_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
+                                tma2_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
+                            } else {
+                                mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+                                tma_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
+                                tma_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
+                            }
+                            if (++st == P.stages) { st = 0; par ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128*CG
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+                                   ((uint32_t)((128 * CG) >> 4) << 24);
+            int st = 0;
+            uint32_t par = 0, ti = 0;
+            for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters, ++ti) {
+                const int phase = tile / tiles_per_phase;
+                const PhaseGeo g = phase_geo(P, phase);
+                const int nkb = g.nth * g.ntw * P.cblocks;
+                const uint32_t ab = ti & 1;
+                mbar_wait(&tempty_bar[ab], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[st], par);
+                    tc_fence_after();
+                    const uint32_t sa = base + (uint32_t)st * stage_bytes;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        uint64_t ad = make_kmajor_sw128_desc(sa + k4 * 32);
+                        uint64_t bd = make_kmajor_sw128_desc(sb + k4 * 32);
+                        if (CG == 2) tc2_mma_bf16(tacc, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        else tc_mma_bf16(tacc, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+                    }
+                    if (CG == 2) tc2_commit_mc(&empty_bar[st]); else tc_commit(&empty_bar[st]);
+                    if (++st == P.stages) { st = 0; par ^= 1; }
+                }
+                if (CG == 2) tc2_commit_mc(&tfull_bar[ab]); else tc_commit(&tfull_bar[ab]);
+            }
+        }
+    } else {
+        // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and every second 16-column chunk
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const int dn = r / (P.bw * P.bh), rem = r - dn * (P.bw * P.bh);
+        const int dh = rem / P.bw, dw = rem - dh * P.bw;
+        const bool vec_ok = (P.n_total % 8) == 0;
+        const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
+        const int act = P.act;
+        const bool has_stats = P.stats != nullptr;
+        const int scol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        uint32_t ti = 0;
+        for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters, ++ti) {
+            const int phase = tile / tiles_per_phase, rr = tile - phase * tiles_per_phase;
+            const int nt = rr / P.m_tiles, mt = rr - nt * P.m_tiles;
+            const int ph = phase / P.s, pw = phase - ph * P.s;
+            const int m0 = (mt * CG + (int)rank) * 128;
+            const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
+            const int nt0 = nt * P.BN;
+            const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
+            const bool row_ok = n_img < P.n_img && P.out != nullptr;
+            int oh = hh, ow = ww;
+            if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
+            bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
+            const int ncols = min(P.BN, P.n_total - nt0);          // valid columns of this tile
+            const uint32_t ab = ti & 1;
+            mbar_wait(&tfull_bar[ab], (ti >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+                uint32_t v[16];
+                tc_ld16(tacc + (uint32_t)c0, v);
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (P.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < ncols) f[j] += __ldg(P.bias + nt0 + c0 + j);
+                }
+                if (act == SG_ACT_LRELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
+                } else if (act == SG_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (act == SG_ACT_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = tanh_approx(f[j]);
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                if (row_ok) {
+                    if (vec_ok && c0 + 16 <= ncols) {
+                        *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < ncols) orow[c0 + j] = __ushort_as_bfloat16((unsigned short)(pk[j >> 1] >> ((j & 1) * 16)));
+                    }
+                }
+                if (has_stats) {
+                    float sq[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                     // statistics of the STORED (rounded) values
+                        f[2 * j] = row_ok ? __uint_as_float(pk[j] << 16) : 0.f;
+                        f[2 * j + 1] = row_ok ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sq[j] = f[j] * f[j];
+                    warp_colsum16(f, lane);
+                    warp_colsum16(sq, lane);
+                    if ((lane & 1) == 0) {
+                        atomicAdd(&sstat[ab][c0 + scol][0], f[0]);
+                        atomicAdd(&sstat[ab][c0 + scol][1], sq[0]);
+                    }
+                }
+            }
+            // accumulator buffer drained: hand it back to the MMA warp (of the leader CTA)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive_local(&tempty_bar[ab]);
+            }
+            if (has_stats) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int grp = n0 / P.imgs_per_group;
+                for (int i = et; i < ncols * 2; i += 32 * TCP_EPI_WARPS) {
+                    const int col = i >> 1, which = i & 1;
+                    atomicAdd(P.stats + ((int64_t)grp * P.n_total + nt0 + col) * 2 + which, (double)sstat[ab][col][which]);
+                    sstat[ab][col][which] = 0.f;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]  as  D[co][(tap,ci)] = A^T B with the pixel
 // index as the reduction: both operands are "MN-major" (channels contiguous, pixels strided), which
@@ -769,6 +1087,110 @@ static int launch_conv_tc2(int mode, const void* act, const void* wpack, const f
     return check_launch("conv_tc2");
 }
 
+// ---- persistent launch: pick (CTA group, tile width) with a small cost model --------------------------
+// cycles per 64-deep k-block: tcgen05 issue = 2*BN (M=128 per CTA, either group size); operand fetch from L2 =
+// (16 KB of A + BN/CG rows of B) at ~44 B/cycle/SM (the ~12 TB/s L2->SM ceiling shared by 148 SMs).
+int g_use_persist = 1;
+int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
+static bool g_pattr_set = false;
+
+static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out, int* bn_out) {
+    double best = 1e30;
+    int best_cg = 1, best_bn = 16;
+    for (int cg = 1; cg <= 2; ++cg) {
+        if (g_force_cg && cg != g_force_cg) continue;
+        const int step = 16;
+        for (int bn = 16; bn <= 256; bn += step) {
+            if (g_force_bn && bn != g_force_bn) continue;
+            if (cg == 2 && bn < 32) continue;
+            int n_tiles = (n_total + bn - 1) / bn;
+            if (!g_force_bn && n_tiles * bn - n_total >= 16 && bn > 16) {
+                // a narrower tile with the same tile count wastes less
+                int alt = ((n_total + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+                if (alt < bn) continue;
+            }
+            int m_tiles = (M + 128 * cg - 1) / (128 * cg);
+            long tiles = (long)m_tiles * n_tiles * phases;
+            int units = SG_NUM_SMS / cg;
+            long rounds = (tiles + units - 1) / units;
+            double mma = 2.0 * bn;
+            double l2 = (16384.0 + (double)(bn / cg) * 128.0) / 44.0;
+            double t_kb = mma > l2 ? mma : l2;
+            double t_tile = nkb * t_kb + 150.0;
+            double epi = 40.0 * bn / 16.0 + 400.0;                  // drain of the last tile, not overlapped
+            double t_epi_tile = 40.0 * bn / 16.0 + 100.0;           // epilogue pace per tile
+            if (t_epi_tile > t_tile) t_tile = t_epi_tile;
+            double t = rounds * t_tile + epi;
+            if (t < best) { best = t; best_cg = cg; best_bn = bn; }
+        }
+    }
+    *cg_out = best_cg; *bn_out = best_bn;
+}
+
+static int launch_conv_tcp(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
+                           int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, double* stats, int groups,
+                           cudaStream_t st) {
+    int e = ensure_encode();
+    if (e) return e;
+    TcpParams P;
+    int aH, aW;
+    if (mode == 0) {
+        P.Hq = Ho; P.Wq = Wo; P.Ck = Ci; P.n_total = Co; P.outH = Ho; P.outW = Wo; aH = H; aW = W;
+    } else {
+        P.Hq = H / s; P.Wq = W / s; P.Ck = Co; P.n_total = Ci; P.outH = H; P.outW = W; aH = Ho; aW = Wo;
+    }
+    if (!choose_box(P.Hq, P.Wq, &P.bw, &P.bh, &P.bn)) { set_error("conv_tcp: grid %dx%d not tileable", P.Hq, P.Wq); return SG_ERR_UNSUPPORTED; }
+    const int M = N * P.Hq * P.Wq;
+    P.n_img = N;
+    P.cblocks = (P.Ck + 63) / 64;
+    P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
+    P.stats = stats;
+    P.imgs_per_group = groups > 0 ? N / groups : N;
+    const int phases = mode == 0 ? 1 : s * s;
+    const int taps = mode == 0 ? k * k : (k / s) * (k / s);
+    int cg, bn;
+    pick_tcp_config(M, P.n_total, phases, taps * P.cblocks, &cg, &bn);
+    P.BN = bn;
+    P.n_tiles = (P.n_total + bn - 1) / bn;
+    P.m_tiles = (M + 128 * cg - 1) / (128 * cg);
+    P.total_tiles = P.m_tiles * P.n_tiles * phases;
+    P.acc_stride = bn;
+    P.tmem_cols = 32;
+    while (P.tmem_cols < 2 * bn) P.tmem_cols *= 2;
+    const int stage_bytes = A_STAGE_BYTES + (bn / cg) * 128;
+    P.stages = (200 * 1024 - 2048) / stage_bytes;
+    if (P.stages > 8) P.stages = 8;
+    if (g_force_stages && g_force_stages < P.stages) P.stages = g_force_stages;
+    if (g_dbg & 1) P.out = nullptr;
+    CUtensorMap tmA, tmB;
+    const int es = mode == 0 ? s : 1;
+    if ((e = get_act_map(act, N, aH, aW, P.Ck, P.bw, P.bh, P.bn, es, &tmA))) return e;
+    if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, bn / cg, &tmB))) return e;
+    size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    if (!g_pattr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(tcp): %s", cudaGetErrorString(ce)); return (int)ce; }
+        g_pattr_set = true;
+    }
+    int units = SG_NUM_SMS / cg;
+    int clusters = P.total_tiles < units ? P.total_tiles : units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * cg, 1, 1);
+    cfg.blockDim = dim3(TCP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2>, tmA, tmB, P)
+                             : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1>, tmA, tmB, P);
+    if (ce != cudaSuccess) { set_error("conv_tcp launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+    g_launches.fetch_add(1);
+    return check_launch("conv_tcp");
+}
+
 static bool choose_box64(int Ho, int Wo, int* bw, int* bh, int* bn) {
     if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
     if (Wo >= 64) { *bw = 64; *bh = 1; *bn = 1; return true; }
@@ -855,7 +1277,12 @@ int sg_conv_tc_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, 
 }
 
 int sg_set_option(const char* name, int value) {
-    if (name && name[0] == 't' && name[1] == 'c' && name[2] == '2') { g_use_tc2 = value; return 0; }
+    if (name && !strcmp(name, "tc2")) { g_use_tc2 = value; return 0; }
+    if (name && !strcmp(name, "persist")) { g_use_persist = value; return 0; }
+    if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
+    if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
+    if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }
+    if (name && !strcmp(name, "dbg")) { g_dbg = value; return 0; }
     set_error("unknown option");
     return SG_ERR_BAD_ARG;
 }
@@ -866,6 +1293,8 @@ int sg_conv_fprop_tc(const void* x, const void* pf, const float* bias, void* y, 
                      int Co, int k, int s, int p, int act, int dtype, void* stream) {
     SG_REQUIRE(dtype == SG_BF16, "conv_fprop_tc: bf16 only");
     SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc: unsupported shape");
+    if (g_use_persist)
+        return launch_conv_tcp(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream));
     if (want_tc2(Co, N * Ho * Wo))
         return launch_conv_tc2(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
     return launch_conv_tc(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
@@ -876,6 +1305,8 @@ int sg_conv_dgrad_tc(const void* dy, const void* pd, const float* bias, void* dx
     SG_REQUIRE(dtype == SG_BF16, "conv_dgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_dgrad_tc: unsupported shape");
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc: inconsistent sizes");
+    if (g_use_persist)
+        return launch_conv_tcp(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream));
     if (want_tc2(Ci, N * (H / s) * (W / s)))
         return launch_conv_tc2(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
     return launch_conv_tc(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
@@ -895,6 +1326,30 @@ int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int
     SG_REQUIRE(dtype == SG_BF16, "conv_wgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_wgrad_tc: unsupported shape");
     return launch_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
+}
+
+// conv + per-channel (sum, sum^2) of the stored output accumulated into stats[groups][C][2] (the statistics
+// of the BatchNorm that follows), fused into the epilogue.  Returns SG_ERR_UNSUPPORTED (without launching)
+// when the shape cannot be fused; the dispatcher then runs the conv and sg_col_stats separately.
+int sg_conv_tc_stats_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups) {
+    if (!g_use_persist || groups < 1 || N % groups != 0) return 0;
+    if (!sg_conv_tc_supported(mode, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return 0;
+    int Hq = mode == 0 ? Ho : H / s, Wq = mode == 0 ? Wo : W / s;
+    long rows_per_group = (long)(N / groups) * Hq * Wq;
+    return rows_per_group % 128 == 0 ? 1 : 0;
+}
+int sg_conv_fprop_tc_stats(const void* x, const void* pf, void* y, double* stats, int groups, int N, int H, int W, int Ci,
+                           int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
+    SG_REQUIRE(dtype == SG_BF16, "conv_fprop_tc_stats: bf16 only");
+    SG_REQUIRE(sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups), "conv_fprop_tc_stats: unsupported shape");
+    return launch_conv_tcp(0, x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, stats, groups, SG_STREAM(stream));
+}
+int sg_conv_dgrad_tc_stats(const void* dy, const void* pd, void* dx, double* stats, int groups, int N, int H, int W, int Ci,
+                           int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
+    SG_REQUIRE(dtype == SG_BF16, "conv_dgrad_tc_stats: bf16 only");
+    SG_REQUIRE(sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups), "conv_dgrad_tc_stats: unsupported shape");
+    SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc_stats: inconsistent sizes");
+    return launch_conv_tcp(1, dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, stats, groups, SG_STREAM(stream));
 }
 
 }  // extern "C"

@@ -152,15 +152,16 @@ class GenRT:
             if L.bn is None:
                 ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
                 break
-            ops.conv_dgrad(x, L.pd, None, self.y[i], L.k, L.s, L.p)
             bn = L.bn
             if training:
+                # conv + BN batch statistics in one kernel (reduced in the tcgen05 epilogue when the shape allows)
                 ops.zero(self.stats[i])
-                ops.col_stats(self.y[i], self.stats[i], 1)
+                ops.conv_dgrad_stats(x, L.pd, self.y[i], self.stats[i], 1, L.k, L.s, L.p)
                 n = self.y[i].numel() // L.ci
                 ops.bn_finalize(self.stats[i], n, self.mr[i], bn.running_mean, bn.running_var,
                                 bn.num_batches_tracked, 1, True)
             else:
+                ops.conv_dgrad(x, L.pd, None, self.y[i], L.k, L.s, L.p)
                 ops.bn_eval_mr(bn.running_mean, bn.running_var, self.mr[i])
             ops.bn_act(self.y[i], self.mr[i], bn.weight.data, bn.bias.data, self.a[i], 1, ACT_RELU)
             x = self.a[i]
@@ -288,15 +289,15 @@ class CriticRT:
         for l in range(1, self.nl):
             L, bn = self.layers[l], self.layers[l].bn
             y = gv(self.y[l])
-            ops.conv_fprop(gv(self.a[l]), L.pf, None, y, L.k, L.s, L.p)
             mr = self.mr[l][g0:g0 + ng]
             if training:
                 st = self.stats[l][g0:g0 + ng]
                 ops.zero(st)
-                ops.col_stats(y, st, ng)
+                ops.conv_fprop_stats(gv(self.a[l]), L.pf, y, st, ng, L.k, L.s, L.p)
                 ops.bn_finalize(st, y.numel() // (ng * L.co), mr, bn.running_mean, bn.running_var,
                                 bn.num_batches_tracked, dup_first, True)
             else:
+                ops.conv_fprop(gv(self.a[l]), L.pf, None, y, L.k, L.s, L.p)
                 for g in range(ng):
                     ops.bn_eval_mr(bn.running_mean, bn.running_var, mr[g:g + 1])
             ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)

@@ -31,13 +31,23 @@ class _BN:
         self.sums = ops.zeros((1, C, 2), ops.f64)
 
 
-def _bn_forward(ops, bn, buf, out, act, training, residual=None):
+def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=None):
+    """conv (fprop 'f' / transposed 'd') -> train- or eval-mode BN -> activation (+ residual).  In training
+    mode the batch statistics come out of the conv kernel's epilogue (sg_conv_*_stats)."""
+    bn = L.bn
     C = buf.y.shape[-1]
     if training:
         ops.zero(buf.stats)
-        ops.col_stats(buf.y, buf.stats, 1)
+        if direction == "f":
+            ops.conv_fprop_stats(x, L.pf, buf.y, buf.stats, 1, L.k, L.s, L.p)
+        else:
+            ops.conv_dgrad_stats(x, L.pd, buf.y, buf.stats, 1, L.k, L.s, L.p)
         ops.bn_finalize(buf.stats, buf.y.numel() // C, buf.mr, bn.running_mean, bn.running_var, bn.num_batches_tracked, 1, True)
     else:
+        if direction == "f":
+            ops.conv_fprop(x, L.pf, None, buf.y, L.k, L.s, L.p)
+        else:
+            ops.conv_dgrad(x, L.pd, None, buf.y, L.k, L.s, L.p)
         ops.bn_eval_mr(bn.running_mean, bn.running_var, buf.mr)
     ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
@@ -105,23 +115,18 @@ class Gen2RT:
         ops.patchify(self.x_in, self.P0, L.k, L.s, L.p)
         ops.conv_fprop(self.P0, self.pf_ds0, L.conv.bias.data, self.a1, 1, 1, 0, act=ACT_LRELU)
         L = self.ds2
-        ops.conv_fprop(self.a1, L.pf, None, self.b2.y, L.k, L.s, L.p)
-        _bn_forward(ops, L.bn, self.b2, self.b2.a, ACT_LRELU, training)
+        _conv_bn_forward(ops, "f", self.a1, L, self.b2, self.b2.a, ACT_LRELU, training)
         ops.concat_rep(self.b2.a, c_hat, self.X[0])
         for r in range(4):
             l1, l2, l3 = self.res[r]
             b1, b2, b3 = self.rb[r]
-            ops.conv_fprop(self.X[r], l1.pf, None, b1.y, 3, 1, 1)
-            _bn_forward(ops, l1.bn, b1, b1.a, ACT_RELU, training)
-            ops.conv_fprop(b1.a, l2.pf, None, b2.y, 3, 1, 1)
-            _bn_forward(ops, l2.bn, b2, b2.a, ACT_RELU, training)
-            ops.conv_fprop(b2.a, l3.pf, None, b3.y, 3, 1, 1)
-            _bn_forward(ops, l3.bn, b3, self.X[r + 1], ACT_RELU, training, residual=self.X[r])     # x += identity; relu
+            _conv_bn_forward(ops, "f", self.X[r], l1, b1, b1.a, ACT_RELU, training)
+            _conv_bn_forward(ops, "f", b1.a, l2, b2, b2.a, ACT_RELU, training)
+            _conv_bn_forward(ops, "f", b2.a, l3, b3, self.X[r + 1], ACT_RELU, training, residual=self.X[r])   # x += identity; relu
         x = self.X[4]
         for i in range(3):
             L, b = self.ups[i], self.ub[i]
-            ops.conv_dgrad(x, L.pd, None, b.y, L.k, L.s, L.p)
-            _bn_forward(ops, L.bn, b, b.a, ACT_RELU, training)
+            _conv_bn_forward(ops, "d", x, L, b, b.a, ACT_RELU, training)
             x = b.a
         L = self.up3
         ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)

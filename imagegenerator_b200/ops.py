@@ -40,6 +40,10 @@ _SIGS = {
     "sg_conv_fprop_tc": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_dgrad_tc": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_wgrad_tc": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_conv_fprop_stats": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_dgrad_stats": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_fprop_tc_stats": [_P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_dgrad_tc_stats": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_colsum": [_P, _P, _L, _I, _I, _P],
     "sg_col_stats": [_P, _P, _L, _I, _I, _I, _P],
     "sg_bn_finalize": [_P, _L, _P, _P, _P, _P, _I, _I, _F, _F, _I, _I, _P],
@@ -69,7 +73,8 @@ _SIGS = {
     "sg_adam_step": [_P, _P, _P, _P, _P, _L, _P],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option"])
+EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
+                                 "sg_conv_tc_stats_supported"])
 
 
 def load_library(path=LIB_PATH):
@@ -226,6 +231,21 @@ class CudaOps:
         d = self._conv_dims(dx, dy)
         fn = getattr(self.lib, "sg_conv_dgrad" + impl)
         self._ck(fn(_ptr(dy), _ptr(pd), _ptr(bias), _ptr(dx), *d, k, s, p, act, self._dt_of(dy), self._st()))
+
+    def conv_fprop_stats(self, x, pf, y, stats, groups, k, s, p):
+        """y = conv(x); stats[groups][Co][2] += (sum, sum^2) of y per image group (BN batch statistics)."""
+        self._c(x, pf, y, stats)
+        d = self._conv_dims(x, y)
+        assert stats.dtype == torch.float64 and tuple(stats.shape) == (groups, d[6], 2)
+        self._ck(self.lib.sg_conv_fprop_stats(_ptr(x), _ptr(pf), _ptr(y), _ptr(stats), groups, *d, k, s, p,
+                                              self._dt_of(x), self._st()))
+
+    def conv_dgrad_stats(self, dy, pd, dx, stats, groups, k, s, p):
+        self._c(dy, pd, dx, stats)
+        d = self._conv_dims(dx, dy)
+        assert stats.dtype == torch.float64 and tuple(stats.shape) == (groups, d[3], 2)
+        self._ck(self.lib.sg_conv_dgrad_stats(_ptr(dy), _ptr(pd), _ptr(dx), _ptr(stats), groups, *d, k, s, p,
+                                              self._dt_of(dy), self._st()))
 
     def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         self._c(x, dy, dw)

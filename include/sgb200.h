@@ -49,7 +49,8 @@ const char* sg_last_error(void);
 int sg_check_device(void);
 /* number of kernels launched through this library since load (all threads) */
 int64_t sg_launch_count(void);
-/* tuning switches: "tc2" = 1/0 use CTA-pair (cta_group::2) tiles for layers with >= 128 output channels */
+/* tuning switches: "persist" = 1/0 persistent double-buffered conv kernel (default 1); "force_cg" / "force_bn" pin its
+ * CTA-group size / tile width (0 = cost model); "tc2" = 1/0 CTA-pair tiles in the non-persistent kernels */
 int sg_set_option(const char* name, int value);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
@@ -107,6 +108,22 @@ int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int
                      int k, int s, int p, int dtype, void* stream);
 int sg_conv_tc_supported(int mode /*0 fprop, 1 dgrad*/, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
 int sg_conv_wgrad_tc_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
+
+/* conv + statistics of the BatchNorm2d that follows it (every BN layer of the reference sits behind a bias-free
+ * conv: generator_1.py:26-34, generator_2.py:30-38, discrminator_1.py:29-37, discriminator_2.py:44-52):
+ * y = conv(x, W) / dx = conv_transpose(dy, W), and stats[groups][C][2] (fp64) += (sum, sum of squares) of the
+ * stored result per image group (N/groups consecutive images each).  On the tcgen05 path the sums are reduced in
+ * the epilogue (warp shuffles -> shared memory -> one fp64 atomic per channel and tile); other shapes run the conv
+ * followed by sg_col_stats. */
+int sg_conv_fprop_stats(const void* x, const void* pf, void* y, double* stats, int groups,
+                        int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
+int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats, int groups,
+                        int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
+int sg_conv_fprop_tc_stats(const void* x, const void* pf, void* y, double* stats, int groups, int N, int H, int W, int Ci,
+                           int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
+int sg_conv_dgrad_tc_stats(const void* dy, const void* pd, void* dx, double* stats, int groups, int N, int H, int W, int Ci,
+                           int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
+int sg_conv_tc_stats_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups);
 
 /* out[C] (fp32) += column sums of x[rows][C]  (bias gradients) */
 int sg_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream);

@@ -100,6 +100,15 @@ class EmuOps:
         assert out.shape[2] == dx.shape[1], (out.shape, dx.shape)
         dx.copy_(nhwc(_act(out, act)).to(dx.dtype))
 
+    def conv_fprop_stats(self, x, pf, y, stats, groups, k, s, p):
+        """conv + (sum, sum^2) of the STORED result per image group (the statistics of the BN that follows)."""
+        self.conv_fprop(x, pf, None, y, k, s, p)
+        self.col_stats(y, stats, groups)
+
+    def conv_dgrad_stats(self, dy, pd, dx, stats, groups, k, s, p):
+        self.conv_dgrad(dy, pd, None, dx, k, s, p)
+        self.col_stats(dx, stats, groups)
+
     def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         """dw[Co,Ci,kh,kw] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]."""
         g = torch.nn.grad.conv2d_weight(nchw(x).double(), dw.shape, nchw(dy).double(), stride=s, padding=p)

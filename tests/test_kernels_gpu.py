@@ -299,6 +299,54 @@ def test_conv_dgrad_tcgen05(case, act, use_bias):
     run_pair("bf16", "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci)), k, s, p], [3], dict(act=act, impl="_tc"))
 
 
+STATS_CASES = [
+    # N, H, Ci, Co, k, s, p, groups
+    (24, 8, 256, 512, 4, 2, 1, 3),      # critic ds4: 8 images x 16 pixels = one 128-row tile per group -> fused
+    (48, 16, 128, 256, 4, 2, 1, 3),     # critic ds3 (CTA pairs), 3 groups
+    (6, 32, 64, 128, 4, 2, 1, 3),       # critic ds2
+    (4, 16, 640, 320, 3, 1, 1, 1),      # Stage-II residual block
+    (4, 16, 48, 96, 4, 2, 1, 1),        # generator up-layer operator
+    (3, 8, 256, 512, 4, 2, 1, 3),       # 1 image / group: 16 rows -> not fusable, conv + col_stats
+    (2, 16, 40, 24, 3, 1, 1, 2),
+]
+
+
+def _check_stats(y_dev, stats_dev, st0, G):
+    """The statistics must be those of the tensor the kernel STORED (what bn_act will normalise)."""
+    C = y_dev.shape[-1]
+    v = y_dev.double().cpu().reshape(G, -1, C)
+    want = st0.clone()
+    want[:, :, 0] += v.sum(1)
+    want[:, :, 1] += (v * v).sum(1)
+    got = stats_dev.cpu()
+    scale = want.abs().amax(dim=(0, 1), keepdim=True)
+    assert ((got - want).abs() <= 1e-4 * scale + 1e-6).all(), (got - want).abs().max().item()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", STATS_CASES)
+def test_conv_fprop_stats(mode, case):
+    N, H, Ci, Co, k, s, p, G = case
+    Ho = (H + 2 * p - k) // s + 1
+    x, w = rnd(N, H, H, Ci), rnd(Co, Ci, k, k, scale=(Ci * k * k) ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    st0 = torch.ones(G, Co, 2, dtype=torch.float64) * 0.25            # accumulate semantics
+    ea, ca = run_pair(mode, "conv_fprop_stats", [T(x), T(pf), T(torch.zeros(N, Ho, Ho, Co)), D(st0), G, k, s, p], [2])
+    _check_stats(ca[2], ca[3], st0, G)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", STATS_CASES)
+def test_conv_dgrad_stats(mode, case):
+    N, H, Ci, Co, k, s, p, G = case
+    Ho = (H + 2 * p - k) // s + 1
+    dy, w = rnd(N, Ho, Ho, Co), rnd(Co, Ci, k, k, scale=(Co * k * k / (s * s)) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    st0 = torch.zeros(G, Ci, 2, dtype=torch.float64)
+    ea, ca = run_pair(mode, "conv_dgrad_stats", [T(dy), T(pd), T(torch.zeros(N, H, H, Ci)), D(st0), G, k, s, p], [2])
+    _check_stats(ca[2], ca[3], st0, G)
+
+
 def _wtc_ok(case):
     from imagegenerator_b200.ops import CudaOps
     N, H, Ci, Co, k, s, p = case
