@@ -1,0 +1,369 @@
+// bn_fast.cu -- HBM-bound BatchNorm kernels for channel counts that are a multiple of 8 (every BN layer of
+// the StackGAN networks: 16 ... 640 channels), 16-byte accesses.
+//
+// Work decomposition shared by all kernels here: the [rows][C] tensor is a stream of 8-channel vectors;
+// CTA b owns the contiguous range [b*chunk, (b+1)*chunk) (chunk a multiple of CV = C/8) and walks it with
+// `active` = the largest multiple of CV <= 256 threads, so that thread t always meets channel vector
+// t % CV: the per-channel constants (mean, rstd, gamma, the backward sums ...) are folded ONCE into
+// registers and the inner loop is loads -> a few FMAs per element -> store, no integer division.  A CTA's
+// range touches at most two image groups, so per-channel reductions are combined in shared memory and
+// leave the CTA as one fp64 atomic per (group, channel, quantity).
+#include "common.cuh"
+
+namespace sg {
+
+struct V8 {
+    float v[8];
+};
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    V8 r;
+    r.v[0] = __uint_as_float(t.x << 16); r.v[1] = __uint_as_float(t.x & 0xffff0000u);
+    r.v[2] = __uint_as_float(t.y << 16); r.v[3] = __uint_as_float(t.y & 0xffff0000u);
+    r.v[4] = __uint_as_float(t.z << 16); r.v[5] = __uint_as_float(t.z & 0xffff0000u);
+    r.v[6] = __uint_as_float(t.w << 16); r.v[7] = __uint_as_float(t.w & 0xffff0000u);
+    return r;
+}
+__device__ __forceinline__ V8 ld8(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    V8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const V8& r) {
+    uint4 t;
+    t.x = pack_bf16x2(r.v[0], r.v[1]); t.y = pack_bf16x2(r.v[2], r.v[3]);
+    t.z = pack_bf16x2(r.v[4], r.v[5]); t.w = pack_bf16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ void st8(float* p, const V8& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// packed 8-element loads: issue now, unpack at use (keeps 4 vectors per tensor in flight per thread)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 q; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ Raw8<bf16> ldraw(const bf16* p) {
+    Raw8<bf16> r;
+    r.q = __ldg(reinterpret_cast<const uint4*>(p));
+    return r;
+}
+__device__ __forceinline__ Raw8<float> ldraw(const float* p) {
+    Raw8<float> r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    return r;
+}
+__device__ __forceinline__ V8 unpack(const Raw8<bf16>& t) {
+    V8 r;
+    r.v[0] = __uint_as_float(t.q.x << 16); r.v[1] = __uint_as_float(t.q.x & 0xffff0000u);
+    r.v[2] = __uint_as_float(t.q.y << 16); r.v[3] = __uint_as_float(t.q.y & 0xffff0000u);
+    r.v[4] = __uint_as_float(t.q.z << 16); r.v[5] = __uint_as_float(t.q.z & 0xffff0000u);
+    r.v[6] = __uint_as_float(t.q.w << 16); r.v[7] = __uint_as_float(t.q.w & 0xffff0000u);
+    return r;
+}
+__device__ __forceinline__ V8 unpack(const Raw8<float>& t) {
+    V8 r;
+    r.v[0] = t.a.x; r.v[1] = t.a.y; r.v[2] = t.a.z; r.v[3] = t.a.w;
+    r.v[4] = t.b.x; r.v[5] = t.b.y; r.v[6] = t.b.z; r.v[7] = t.b.w;
+    return r;
+}
+template <typename T> struct Unroll { static constexpr int U = 4; };
+template <> struct Unroll<float> { static constexpr int U = 2; };
+
+struct Chunking {
+    int64_t nvec, gvec, chunk;   // vectors in the tensor, per image group, per CTA
+    int CV, active, blocks;
+};
+
+static Chunking make_chunking(int64_t rows_per_group, int C, int groups, int waves) {
+    Chunking k;
+    k.CV = C / 8;
+    k.gvec = rows_per_group * k.CV;
+    k.nvec = k.gvec * groups;
+    k.active = 256 / k.CV * k.CV;
+    int64_t want = (int64_t)SG_NUM_SMS * waves;
+    int64_t per = (k.nvec + want - 1) / want;
+    int64_t min_per = (int64_t)k.active * 4;                       // at least 4 vectors per thread
+    if (per < min_per) per = min_per;
+    k.chunk = (per + k.active - 1) / k.active * k.active;
+    k.blocks = (int)((k.nvec + k.chunk - 1) / k.chunk);
+    return k;
+}
+
+// activation derivative from the stored output for none / ReLU / LeakyReLU: 1 where a > 0, else `slope`
+static inline float act_slope(int act) { return act == SG_ACT_RELU ? 0.f : (act == SG_ACT_LRELU ? 0.1f : 1.f); }
+
+// ---- out = act((y - mean) * rstd*gamma + beta [+ residual])
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_act8_kernel(const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out, Chunking k, int act) {
+    if ((int)threadIdx.x >= k.active) return;
+    int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
+    int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
+    if (end > k.nvec) end = k.nvec;
+    if (i >= end) return;
+    const int c0 = ((int)threadIdx.x % k.CV) * 8, C = k.CV * 8;
+    int g = (int)(i / k.gvec);
+    int64_t next = (int64_t)(g + 1) * k.gvec;
+    float m[8], rg[8], b[8];
+    auto load = [&](int gg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float* q = mr + ((int64_t)gg * C + c0 + j) * 2;
+            m[j] = q[0]; rg[j] = q[1] * gamma[c0 + j]; b[j] = beta[c0 + j];
+        }
+    };
+    load(g);
+    const float slope = act == SG_ACT_RELU ? 0.f : (act == SG_ACT_LRELU ? 0.1f : 1.f);
+    constexpr int U = Unroll<T>::U;
+    auto one = [&](const V8& v, const V8* r, int64_t at) {
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = (v.v[j] - m[j]) * rg[j] + b[j] + (r ? r->v[j] : 0.f);
+        if (act == SG_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = tanhf(o.v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = o.v[j] > 0.f ? o.v[j] : slope * o.v[j];
+        }
+        st8(out + at * 8, o);
+    };
+    while (i < end) {
+        if (i >= next) {
+            do { ++g; next += k.gvec; } while (i >= next);
+            load(g);
+        }
+        const int64_t lim = end < next ? end : next;
+        if (i + (int64_t)(U - 1) * k.active < lim) {
+            Raw8<T> ry[U], rr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) ry[u] = ldraw(y + (i + (int64_t)u * k.active) * 8);
+            if (res != nullptr) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) rr[u] = ldraw(res + (i + (int64_t)u * k.active) * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                V8 v = unpack(ry[u]);
+                if (res != nullptr) { V8 r = unpack(rr[u]); one(v, &r, i + (int64_t)u * k.active); }
+                else one(v, nullptr, i + (int64_t)u * k.active);
+            }
+            i += (int64_t)U * k.active;
+        } else {
+            V8 v = unpack(ldraw(y + i * 8));
+            if (res != nullptr) { V8 r = unpack(ldraw(res + i * 8)); one(v, &r, i); }
+            else one(v, nullptr, i);
+            i += k.active;
+        }
+    }
+}
+
+// ---- sums[g][c] += (sum dz, sum dz*xhat), dz = da * act'(a_out)
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
+                      const float* __restrict__ mr, double* __restrict__ sums, Chunking k, float slope) {
+    extern __shared__ float sacc[];                 // [touched groups][C][2]
+    const int C = k.CV * 8;
+    const int64_t begin = (int64_t)blockIdx.x * k.chunk;
+    int64_t end = begin + k.chunk;
+    if (end > k.nvec) end = k.nvec;
+    const int g_first = (int)(begin / k.gvec), g_last = (int)((end - 1) / k.gvec);
+    const int nacc = (g_last - g_first + 1) * C * 2;
+    for (int t = threadIdx.x; t < nacc; t += 256) sacc[t] = 0.f;
+    __syncthreads();
+    int64_t i = begin + threadIdx.x;
+    if ((int)threadIdx.x < k.active && i < end) {
+        const int c0 = ((int)threadIdx.x % k.CV) * 8;
+        int g = (int)(i / k.gvec);
+        int64_t next = (int64_t)(g + 1) * k.gvec;
+        float m[8], r[8], s1[8], s2[8];
+        auto load = [&](int gg) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* q = mr + ((int64_t)gg * C + c0 + j) * 2;
+                m[j] = q[0]; r[j] = q[1]; s1[j] = 0.f; s2[j] = 0.f;
+            }
+        };
+        auto flush = [&](int gg) {
+            float* dst = sacc + ((gg - g_first) * C + c0) * 2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, s1[j]); atomicAdd(dst + 2 * j + 1, s2[j]); }
+        };
+        load(g);
+        constexpr int U = Unroll<T>::U;
+        auto one = [&](const V8& d, const V8& a, const V8& yy) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float dz = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+                s1[j] += dz;
+                s2[j] += dz * ((yy.v[j] - m[j]) * r[j]);
+            }
+        };
+        while (i < end) {
+            if (i >= next) {
+                flush(g);
+                do { ++g; next += k.gvec; } while (i >= next);
+                load(g);
+            }
+            const int64_t lim = end < next ? end : next;
+            if (i + (int64_t)(U - 1) * k.active < lim) {
+                Raw8<T> rd[U], ra[U], ry[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t at = (i + (int64_t)u * k.active) * 8;
+                    rd[u] = ldraw(da + at); ra[u] = ldraw(a_out + at); ry[u] = ldraw(y + at);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) one(unpack(rd[u]), unpack(ra[u]), unpack(ry[u]));
+                i += (int64_t)U * k.active;
+            } else {
+                one(unpack(ldraw(da + i * 8)), unpack(ldraw(a_out + i * 8)), unpack(ldraw(y + i * 8)));
+                i += k.active;
+            }
+        }
+        flush(g);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nacc; t += 256) atomicAdd(sums + (int64_t)g_first * C * 2 + t, (double)sacc[t]);
+}
+
+// ---- dy = gamma*rstd/n * (n dz - S1 - xhat S2) [+ inject on one group]
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
+                     const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
+                     const T* __restrict__ inject, int inject_group, T* __restrict__ dy, Chunking k, float slope,
+                     float n) {
+    if ((int)threadIdx.x >= k.active) return;
+    int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
+    int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
+    if (end > k.nvec) end = k.nvec;
+    if (i >= end) return;
+    const int c0 = ((int)threadIdx.x % k.CV) * 8, C = k.CV * 8;
+    int g = (int)(i / k.gvec);
+    int64_t next = (int64_t)(g + 1) * k.gvec;
+    float m[8], r[8], gr[8], c1[8], c2[8];
+    auto load = [&](int gg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float* q = mr + ((int64_t)gg * C + c0 + j) * 2;
+            const double* s = sums + ((int64_t)gg * C + c0 + j) * 2;
+            m[j] = q[0]; r[j] = q[1];
+            float coef = gamma[c0 + j] * q[1] / n;
+            gr[j] = coef * n; c1[j] = coef * (float)s[0]; c2[j] = coef * (float)s[1];
+        }
+    };
+    load(g);
+    constexpr int U = Unroll<T>::U;
+    auto one = [&](const V8& d, const V8& a, const V8& yy, int64_t at) {
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float dz = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+            float xh = (yy.v[j] - m[j]) * r[j];
+            o.v[j] = gr[j] * dz - c1[j] - xh * c2[j];
+        }
+        if (inject != nullptr && g == inject_group) {
+            V8 q = unpack(ldraw(inject + (at - (int64_t)inject_group * k.gvec) * 8));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] += q.v[j];
+        }
+        st8(dy + at * 8, o);
+    };
+    while (i < end) {
+        if (i >= next) {
+            do { ++g; next += k.gvec; } while (i >= next);
+            load(g);
+        }
+        const int64_t lim = end < next ? end : next;
+        if (i + (int64_t)(U - 1) * k.active < lim) {
+            Raw8<T> rd[U], ra[U], ry[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t at = (i + (int64_t)u * k.active) * 8;
+                rd[u] = ldraw(da + at); ra[u] = ldraw(a_out + at); ry[u] = ldraw(y + at);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) one(unpack(rd[u]), unpack(ra[u]), unpack(ry[u]), i + (int64_t)u * k.active);
+            i += (int64_t)U * k.active;
+        } else {
+            one(unpack(ldraw(da + i * 8)), unpack(ldraw(a_out + i * 8)), unpack(ldraw(y + i * 8)), i);
+            i += k.active;
+        }
+    }
+}
+
+// ---- out = da * act'(a_out), 8-wide (ReLU / LeakyReLU / Tanh / none)
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+act_bwd8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __restrict__ out, int64_t nvec, int act) {
+    const float slope = act == SG_ACT_RELU ? 0.f : (act == SG_ACT_LRELU ? 0.1f : 1.f);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * 256) {
+        V8 d = ld8(da + i * 8), a = ld8(a_out + i * 8), o;
+        if (act == SG_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = d.v[j] * (1.f - a.v[j] * a.v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+        }
+        st8(out + i * 8, o);
+    }
+}
+
+template <typename T>
+int bn_act8(const void* y, const float* mr, const float* gamma, const float* beta, const void* res, void* out,
+            int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {
+    Chunking k = make_chunking(rows_per_group, C, groups, 8);
+    bn_act8_kernel<T><<<k.blocks, 256, 0, st>>>((const T*)y, mr, gamma, beta, (const T*)res, (T*)out, k, act);
+    g_launches.fetch_add(1);
+    return check_launch("bn_act8");
+}
+template <typename T>
+int bn_bwd_reduce8(const void* da, const void* a_out, const void* y, const float* mr, double* sums, int64_t rows_per_group,
+                   int C, int groups, int act, cudaStream_t st) {
+    Chunking k = make_chunking(rows_per_group, C, groups, 4);
+    size_t smem = (size_t)(groups < 2 ? 1 : 2) * C * 2 * sizeof(float);
+    if (k.chunk >= k.gvec) smem = (size_t)groups * C * 2 * sizeof(float);   // tiny tensors: a CTA may span every group
+    bn_bwd_reduce8_kernel<T><<<k.blocks, 256, smem, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, sums, k,
+                                                          act_slope(act));
+    g_launches.fetch_add(1);
+    return check_launch("bn_bwd_reduce8");
+}
+template <typename T>
+int bn_bwd_apply8(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const double* sums,
+                  const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups, int act,
+                  cudaStream_t st) {
+    Chunking k = make_chunking(rows_per_group, C, groups, 8);
+    bn_bwd_apply8_kernel<T><<<k.blocks, 256, 0, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums,
+                                                      (const T*)inject, inject_group, (T*)dy, k, act_slope(act),
+                                                      (float)rows_per_group);
+    g_launches.fetch_add(1);
+    return check_launch("bn_bwd_apply8");
+}
+template <typename T>
+int act_bwd8(const void* da, const void* a_out, void* out, int64_t n, int act, cudaStream_t st) {
+    int64_t nvec = n / 8;
+    act_bwd8_kernel<T><<<grid_for(nvec, 256, 8), 256, 0, st>>>((const T*)da, (const T*)a_out, (T*)out, nvec, act);
+    g_launches.fetch_add(1);
+    return check_launch("act_bwd8");
+}
+
+// explicit instantiations used by elementwise.cu
+template int bn_act8<float>(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_act8<bf16>(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_reduce8<float>(const void*, const void*, const void*, const float*, double*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_reduce8<bf16>(const void*, const void*, const void*, const float*, double*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_apply8<float>(const void*, const void*, const void*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_apply8<bf16>(const void*, const void*, const void*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template int act_bwd8<float>(const void*, const void*, void*, int64_t, int, cudaStream_t);
+template int act_bwd8<bf16>(const void*, const void*, void*, int64_t, int, cudaStream_t);
+
+}  // namespace sg

@@ -594,6 +594,12 @@ __global__ void ca_bwd_seed_kernel(const T* dcg, const float* eps, const float* 
     }
 }
 
+// 8-wide kernels of bn_fast.cu (C % 8 == 0)
+template <typename T> int bn_act8(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int bn_bwd_reduce8(const void*, const void*, const void*, const float*, double*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
+
 }  // namespace sg
 
 using namespace sg;
@@ -733,6 +739,10 @@ int sg_bn_act(const void* y, const float* mr, const float* gamma, const float* b
               int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream) {
     int64_t n = rows_per_group * C * groups;
     int e = 0;
+    if (C % 8 == 0 && C <= 2048) {
+        SG_DISPATCH_T(dtype, e = bn_act8<T>(y, mr, gamma, beta, residual, out, rows_per_group, C, groups, act, SG_STREAM(stream)));
+        return e;
+    }
     SG_DISPATCH_T(dtype, {
         BnActF<T> f{(const T*)y, mr, gamma, beta, (const T*)residual, (T*)out, rows_per_group, C, act};
         e = launch_ew4(f, n, SG_STREAM(stream), "bn_act");
@@ -745,6 +755,10 @@ int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const flo
     cudaStream_t st = SG_STREAM(stream);
     cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
     int e = 0;
+    if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
+        SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, a_out, y, mr, sums, rows_per_group, C, groups, act, st));
+        return e;
+    }
     SG_DISPATCH_T(dtype, {
         BnBwdReduceF<T> f{(const T*)da, (const T*)a_out, (const T*)y, mr, C, act};
         e = launch_rowreduce<2>(f, sums, rows_per_group, C, groups, st, "bn_bwd_reduce");
@@ -758,6 +772,11 @@ int sg_bn_bwd_apply(const void* da, const void* a_out, const void* y, const floa
     int64_t n = rows_per_group * C * groups;
     SG_REQUIRE((rows_per_group * C) % 4 == 0, "bn_bwd_apply: group size must be a multiple of 4 elements");
     int e = 0;
+    if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
+        SG_DISPATCH_T(dtype, e = bn_bwd_apply8<T>(da, a_out, y, mr, gamma, sums, inject, inject_group, dy, rows_per_group, C,
+                                                  groups, act, SG_STREAM(stream)));
+        return e;
+    }
     SG_DISPATCH_T(dtype, {
         BnBwdApplyF<T> f{(const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, (const T*)inject, inject_group,
                          (T*)dy, rows_per_group, C, act};
@@ -774,6 +793,10 @@ int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups
 
 int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act, int dtype, void* stream) {
     int e = 0;
+    if (n % 8 == 0) {
+        SG_DISPATCH_T(dtype, e = act_bwd8<T>(da, a_out, out, n, act, SG_STREAM(stream)));
+        return e;
+    }
     SG_DISPATCH_T(dtype, {
         ActBwdF<T> f{(const T*)da, (const T*)a_out, (T*)out, act};
         e = launch_ew4(f, n, SG_STREAM(stream), "act_bwd");
