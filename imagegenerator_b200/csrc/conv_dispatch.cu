@@ -24,6 +24,7 @@ int sg_conv_fprop_tc_stats(const void*, const void*, void*, double*, int, int, i
 int sg_conv_dgrad_tc_stats(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, int, int, int, int,
                            void*);
 int sg_col_stats(const void*, double*, int64_t, int, int, int, void*);
+int sg_conv_fprop_tc_f32out(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, void*);
 
 static bool tc_enabled() {
     static int v = -1;
@@ -71,5 +72,16 @@ int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats,
     int e = sg_conv_dgrad(dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;
     return sg_col_stats(dx, stats, (int64_t)(N / groups) * H * W, Ci, groups, dtype, stream);
+}
+
+// y (fp32) = conv(x, W): same operands as sg_conv_fprop, result kept in fp32 (no activation / bias).  In fp32 storage
+// mode this is sg_conv_fprop itself; in bf16 mode the tensor-core kernel stores its accumulators un-rounded.
+int sg_conv_fprop_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
+                         int s, int p, int dtype, void* stream) {
+    if (dtype == SG_F32) return sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
+    if (tc_enabled() && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+        return sg_conv_fprop_tc_f32out(x, pf, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
+    sg::set_error("conv_fprop_f32out: shape not eligible for the tensor-core kernel (Ci %% 8 != 0?)");
+    return SG_ERR_UNSUPPORTED;
 }
 }

@@ -462,6 +462,7 @@ struct TcpParams {
     const float* bias;
     bf16* out;
     double* stats;        // [groups][n_total][2] or NULL
+    float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
 };
 
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
@@ -666,7 +667,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
             const int nt0 = nt * P.BN;
             const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
-            const bool row_ok = n_img < P.n_img && P.out != nullptr;
+            const bool row_ok = n_img < P.n_img && (P.out != nullptr || P.out32 != nullptr);
             int oh = hh, ow = ww;
             if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
             bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
@@ -695,6 +696,21 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 } else if (act == SG_ACT_TANH) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = tanh_approx(f[j]);
+                }
+                if (P.out32 != nullptr) {
+                    if (row_ok) {
+                        float* o32 = P.out32 + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0 + c0;
+                        if ((P.n_total % 4) == 0 && c0 + 16 <= ncols) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<float4*>(o32)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < ncols) o32[j] = f[j];
+                        }
+                    }
+                    continue;
                 }
                 uint32_t pk[8];
 #pragma unroll
@@ -1129,7 +1145,7 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out
 
 static int launch_conv_tcp(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
                            int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, double* stats, int groups,
-                           cudaStream_t st) {
+                           cudaStream_t st, float* out32 = nullptr) {
     int e = ensure_encode();
     if (e) return e;
     TcpParams P;
@@ -1145,6 +1161,8 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     P.cblocks = (P.Ck + 63) / 64;
     P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
     P.stats = stats;
+    P.out32 = out32;
+    if (out32) P.out = nullptr;
     P.imgs_per_group = groups > 0 ? N / groups : N;
     const int phases = mode == 0 ? 1 : s * s;
     const int taps = mode == 0 ? k * k : (k / s) * (k / s);
@@ -1326,6 +1344,15 @@ int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int
     SG_REQUIRE(dtype == SG_BF16, "conv_wgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_wgrad_tc: unsupported shape");
     return launch_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
+}
+
+// y (FP32) = conv(x, W) with bf16 operands: the un-rounded accumulators, for results that are summed again (col2im)
+int sg_conv_fprop_tc_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                            int k, int s, int p, void* stream) {
+    SG_REQUIRE(g_use_persist, "conv_fprop_tc_f32out needs the persistent kernel");
+    SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc_f32out: unsupported shape");
+    return launch_conv_tcp(0, x, pf, nullptr, nullptr, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, nullptr, 1,
+                           SG_STREAM(stream), y);
 }
 
 // conv + per-channel (sum, sum^2) of the stored output accumulated into stats[groups][C][2] (the statistics

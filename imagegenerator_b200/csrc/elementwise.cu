@@ -453,6 +453,64 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ x, 
     }
 }
 
+// k=4, s=2, p=1 (every thin layer of the StackGAN networks): one thread per (output pixel, kernel row) reads the
+// 4 input pixels of that row once and writes the 4 taps of each channel as one vector (8 B in bf16) -- the four
+// threads of a pixel together fill whole 32-byte sectors of its 96-byte record.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) patchify_k4s2_kernel(const T* __restrict__ x, T* __restrict__ P, int H, int W, int Ho,
+                                                            int Wo, unsigned total) {
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned kh = i & 3u, pix = i >> 2;
+        const unsigned ow = pix % (unsigned)Wo, r = pix / (unsigned)Wo;
+        const unsigned oh = r % (unsigned)Ho, n = r / (unsigned)Ho;
+        const int ih = (int)oh * 2 - 1 + (int)kh, iw0 = (int)ow * 2 - 1;
+        const bool row_ok = ih >= 0 && ih < H;
+        const T* src = x + (((int64_t)n * H + ih) * W + iw0) * C;
+        float v[4][C];
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+            const bool ok = row_ok && iw0 + kw >= 0 && iw0 + kw < W;
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[kw][c] = ok ? ldf(src + kw * C + c) : 0.f;
+        }
+        T* dst = P + (int64_t)pix * (C * 16) + kh * 4;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            F4 o;
+            o.v[0] = v[0][c]; o.v[1] = v[1][c]; o.v[2] = v[2][c]; o.v[3] = v[3][c];
+            st4(dst + c * 16, o);
+        }
+    }
+}
+
+// ---- col2im for a thin output (inverse of the patch matrix): out[n,oh,ow,c] = act(bias[c] + sum over the taps
+// (kh,kw) with oh = ih*s-p+kh, ow = iw*s-p+kw of col[n,ih,iw, c*k*k + kh*k + kw]).  With the 1x1 tensor-core GEMM
+// col = x * W^T in front, this is ConvTranspose2d(Cin -> 3) (generator_1.py:20, generator_2.py:55) and the data
+// gradient of the critics' first conv (discrminator_1.py:10) without 3-wide MMA tiles.
+template <typename T>
+__global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ col, const float* __restrict__ bias,
+                                                         T* __restrict__ out, int Hi, int Wi, int Ho, int Wo, int C, int k,
+                                                         int s, int p, int act, unsigned total) {
+    const int kk = k * k, K = C * kk;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned ow = i % (unsigned)Wo, r = i / (unsigned)Wo;
+        const unsigned oh = r % (unsigned)Ho, n = r / (unsigned)Ho;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kh = ((int)oh + p) % s; kh < k; kh += s) {
+            const int ih = ((int)oh + p - kh) / s;
+            if (ih < 0 || ih >= Hi) continue;
+            for (int kw = ((int)ow + p) % s; kw < k; kw += s) {
+                const int iw = ((int)ow + p - kw) / s;
+                if (iw < 0 || iw >= Wi) continue;
+                const float* src = col + (((int64_t)n * Hi + ih) * Wi + iw) * K + kh * k + kw;
+                for (int c = 0; c < C; ++c) acc[c] += __ldg(src + c * kk);
+            }
+        }
+        T* dst = out + (int64_t)i * C;
+        for (int c = 0; c < C; ++c) stf(dst + c, act_fwd(acc[c] + (bias ? bias[c] : 0.f), act));
+    }
+}
+
 // ---- text replicate + channel concat (generator_2.py:61-63) and its backward
 template <typename T>
 __global__ void __launch_bounds__(256) concat_rep_kernel(const T* __restrict__ x, const float* __restrict__ c,
@@ -688,9 +746,28 @@ int sg_split_rep_bwd(const void* dout, void* dx, float* dc, int N, int HW, int C
 int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int dtype,
                 void* stream) {
     int64_t n = (int64_t)N * Ho * Wo * k * k;
+    if (k == 4 && s == 2 && p == 1 && C == 3 && Ho * 2 == H && Wo * 2 == W && (int64_t)N * Ho * Wo * 4 < (1ll << 31)) {
+        unsigned total = (unsigned)((int64_t)N * Ho * Wo * 4);
+        SG_DISPATCH_T(dtype, (patchify_k4s2_kernel<T, 3><<<grid_for(total, 256, 16), 256, 0, SG_STREAM(stream)>>>(
+                                 (const T*)x, (T*)P, H, W, Ho, Wo, total)));
+        SG_LAUNCHED("patchify_k4s2");
+        return 0;
+    }
     SG_DISPATCH_T(dtype, (patchify_kernel<T><<<grid_for(n, 256, 16), 256, 0, SG_STREAM(stream)>>>((const T*)x, (T*)P, N, H, W, C,
                                                                                                 Ho, Wo, k, s, p)));
     SG_LAUNCHED("patchify");
+    return 0;
+}
+
+int sg_unpatchify(const float* col, const float* bias, void* out, int N, int Hi, int Wi, int C, int Ho, int Wo, int k, int s,
+                  int p, int act, int dtype, void* stream) {
+    SG_REQUIRE(C >= 1 && C <= 4, "unpatchify: 1..4 output channels");
+    SG_REQUIRE(Ho == (Hi - 1) * s - 2 * p + k && Wo == (Wi - 1) * s - 2 * p + k, "unpatchify: inconsistent sizes");
+    SG_REQUIRE((int64_t)N * Ho * Wo < (1ll << 31), "unpatchify: too many pixels");
+    unsigned total = (unsigned)((int64_t)N * Ho * Wo);
+    SG_DISPATCH_T(dtype, (unpatchify_kernel<T><<<grid_for(total, 256, 16), 256, 0, SG_STREAM(stream)>>>(
+                             col, bias, (T*)out, Hi, Wi, Ho, Wo, C, k, s, p, act, total)));
+    SG_LAUNCHED("unpatchify");
     return 0;
 }
 

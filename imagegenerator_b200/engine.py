@@ -134,6 +134,8 @@ class GenRT:
             else:
                 self.out = out if out is not None else ops.empty(shp)
                 self.dpre = ops.empty(shp)
+                hin = (h + 2 * L.p - L.k) // L.s + 1
+                self.col = ops.empty((B, hin, hin, L.ci * L.k * L.k), ops.f32)
         self.packed = False
 
     def refresh_weights(self):
@@ -150,7 +152,9 @@ class GenRT:
         x = self.cg
         for i, L in enumerate(self.layers):
             if L.bn is None:
-                ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
+                # ConvT(C -> 3) + Tanh: 1x1 GEMM onto the 48 (channel, tap) columns, then col2im
+                ops.conv_fprop_f32out(x, L.pd.view(L.ci * L.k * L.k, 1, 1, L.co), self.col, 1, 1, 0)
+                ops.unpatchify(self.col, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
                 break
             bn = L.bn
             if training:
@@ -232,6 +236,7 @@ class CriticRT:
         self.K0 = L0.ci * L0.k * L0.k
         self.P = ops.empty((G * B, h1, h1, self.K0))
         self.Pv = ops.empty((B, h1, h1, self.K0))
+        self.colf = ops.empty(((G - 1) * B, h1, h1, self.K0), f32)      # col2im input of d/d image (<= 2 groups)
         self.pf0 = ops.empty((L0.co, 1, 1, self.K0))
         cl, Nd = self.layers[-1].co, module.Nd
         self.A, self.dA = ops.empty((16, cl), f32), ops.zeros((16, cl), f32)
@@ -312,7 +317,15 @@ class CriticRT:
             ops.head_fwd(self.group_view(a4, 0, 1), self.ce[B:], self.A, self.Bv, self.c0, self.score[1])
 
     # ---------------------------------------------------------------- first-order backward
-    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, on_layer_done=None, head_reduce=True):
+    def input_grad(self, dy0, dx):
+        """d/d image of the first conv: 1x1 GEMM of dy0 onto the 48 (channel, tap) columns (fp32), then col2im."""
+        ops, L0 = self.ops, self.layers[0]
+        col = self.colf[:dy0.shape[0]]
+        ops.conv_fprop_f32out(dy0, L0.pd.view(self.K0, 1, 1, L0.co), col, 1, 1, 0)
+        ops.unpatchify(col, None, dx, L0.k, L0.s, L0.p)
+
+    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, on_layer_done=None, head_reduce=True,
+                 input_grad_from=None):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
         d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).
         ``on_layer_done(l)`` is called once the parameter gradients of conv layer l are final."""
@@ -342,7 +355,10 @@ class CriticRT:
             ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
             ops.colsum(dy0, L0.conv.bias.grad)
         if need_input_grad:
-            ops.conv_dgrad(dy0, L0.pd, None, gv(self.dx), L0.k, L0.s, L0.p)
+            # only for the groups [input_grad_from, g0+ng): the real images need no gradient
+            gi = g0 if input_grad_from is None else input_grad_from
+            sl = lambda t: self.group_view(t, gi, g0 + ng - gi)
+            self.input_grad(sl(self.dy[0]), sl(self.dx))
 
     def text_backward(self, coef_text, nt, dc0, param_grads, dtem):
         """Head/text parameter grads for d loss/d score coefficients; dtem (=) d/d tem rows [0,B)."""
@@ -375,7 +391,7 @@ class CriticRT:
             ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
         L0 = self.layers[0]
         ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
-        ops.conv_dgrad(self.gdy[0], L0.pd, None, self.g, L0.k, L0.s, L0.p)
+        self.input_grad(self.gdy[0], self.g)
         ops.sample_sqnorm(self.g, self.sq)
 
     def gp_second_order(self, coef):

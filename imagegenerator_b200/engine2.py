@@ -92,6 +92,7 @@ class Gen2RT:
         self.out = out if out is not None else ops.empty((B, 256, 256, 3))
         self.dpre = ops.empty((B, 256, 256, 3))
         self.Pd = ops.empty((B, 128, 128, self.K0))
+        self.colf = ops.empty((B, 128, 128, self.K0), f32)
         self.ones = torch.ones(B, dtype=f32).to(ops.device)
 
     def all_layers(self):
@@ -129,7 +130,9 @@ class Gen2RT:
             _conv_bn_forward(ops, "d", x, L, b, b.a, ACT_RELU, training)
             x = b.a
         L = self.up3
-        ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
+        # ConvT(80 -> 3) + Tanh (generator_2.py:55-57): 1x1 GEMM onto the 48 (channel, tap) columns (fp32) + col2im
+        ops.conv_fprop_f32out(x, L.pd.view(self.K0, 1, 1, L.co), self.colf, 1, 1, 0)
+        ops.unpatchify(self.colf, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
         return self.out
 
     def backward(self, dout):
@@ -240,7 +243,8 @@ class Stage2Engine:
         d.gp_first_order()
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])     # :148-152
         d.gp_second_order(2.0 * LAMBDA_GP / B)
-        d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=True)       # :154
+        d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=True,      # :154
+                   input_grad_from=1)                               # d/d real images is never used
         d.text_backward(d.coef_text, 2 * B, 0.0, True, None)
         # d loss_critic / d fake_256 = d/d(fake group) + (1 - eps) * d/d(interpolated group)  (utils.py:11, not detached)
         ops.affine_f32(eps_gp, -1.0, 1.0, self.one_minus_eps)

@@ -29,6 +29,9 @@ _SIGS = {
     "sg_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
     "sg_patchify": [_P, _P] + [_I] * 10 + [_P],
+    "sg_unpatchify": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_conv_fprop_f32out": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_conv_fprop_tc_f32out": [_P, _P, _P] + [_I] * 10 + [_P],
     "sg_concat_rep": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "sg_split_rep_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "sg_conv_fprop": [_P, _P, _P, _P] + [_I] * 12 + [_P],
@@ -212,6 +215,22 @@ class CudaOps:
         _, Ho, Wo, K = P.shape
         assert K == C * k * k
         self._ck(self.lib.sg_patchify(_ptr(x), _ptr(P), N, H, W, C, Ho, Wo, k, s, p, self._dt_of(x), self._st()))
+
+    def unpatchify(self, col, bias, out, k, s, p, act=ACT_NONE):
+        """col2im: out[n,oh,ow,c] = act(bias[c] + sum of the taps of col[n,ih,iw, c*k*k+kh*k+kw] landing on (oh,ow))."""
+        self._c(col, bias, out)
+        N, Hi, Wi, K = col.shape
+        _, Ho, Wo, C = out.shape
+        assert K == C * k * k and col.dtype == torch.float32
+        self._ck(self.lib.sg_unpatchify(_ptr(col), _ptr(bias), _ptr(out), N, Hi, Wi, C, Ho, Wo, k, s, p, act,
+                                        self._dt_of(out), self._st()))
+
+    def conv_fprop_f32out(self, x, pf, y, k, s, p):
+        """y (fp32) = conv(x, W) without rounding the accumulators to the storage type."""
+        self._c(x, pf, y)
+        d = self._conv_dims(x, y)
+        assert y.dtype == torch.float32
+        self._ck(self.lib.sg_conv_fprop_f32out(_ptr(x), _ptr(pf), _ptr(y), *d, k, s, p, self._dt_of(x), self._st()))
 
     # ---- convolution operator
     def _conv_dims(self, x, y):

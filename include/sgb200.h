@@ -71,6 +71,20 @@ int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, i
 int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p,
                 int dtype, void* stream);
 
+/* col2im for a thin (<= 4 channel) result: out[n,oh,ow,c] = act(bias[c] + sum of col[n,ih,iw, c*k*k + kh*k + kw] over
+ * the taps with oh = ih*s-p+kh, ow = iw*s-p+kw); col is FP32 (sg_conv_fprop_f32out), out is T.
+ * Behind the 1x1 GEMM col = x W^T on the tensor-core kernels this is
+ * ConvTranspose2d(C -> 3)+Tanh (generator_1.py:20,38-40; generator_2.py:55) and d/d image of the critics' first
+ * conv (discrminator_1.py:10, needed by utils.py:15 and by the generator step) */
+int sg_unpatchify(const float* col, const float* bias, void* out, int N, int Hi, int Wi, int C, int Ho, int Wo,
+                  int k, int s, int p, int act, int dtype, void* stream);
+/* y (FP32) = conv(x, W), operands as in sg_conv_fprop: the accumulators are stored un-rounded (bf16 mode: tcgen05
+ * kernel only) so that a following col2im sums exact partial products */
+int sg_conv_fprop_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, int dtype, void* stream);
+int sg_conv_fprop_tc_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                            int k, int s, int p, void* stream);
+
 /* out[n,hw,:Cx] = x, out[n,hw,Cx:] = c[n]  (generator_2.py:61-63 reshape/repeat/cat);  backward:
  * dx = dout[..., :Cx], dc[n] (fp32) = sum_hw dout[n,hw,Cx:] */
 int sg_concat_rep(const void* x, const float* c, void* out, int N, int HW, int Cx, int Cc, int dtype, void* stream);

@@ -87,12 +87,25 @@ class EmuOps:
         u = F.unfold(nchw(x).double(), k, padding=p, stride=s)          # [N, C*k*k, Ho*Wo]
         P.copy_(u.transpose(1, 2).reshape(N, Ho, Wo, K).to(P.dtype))
 
+    def unpatchify(self, col, bias, out, k, s, p, act=ACT_NONE):
+        """col2im (F.fold) of col[n,ih,iw, c*k*k + kh*k + kw] onto out[n,oh,ow,c], + bias, activation."""
+        N, Hi, Wi, K = col.shape
+        _, Ho, Wo, C = out.shape
+        u = col.reshape(N, Hi * Wi, K).transpose(1, 2).double()
+        o = F.fold(u, (Ho, Wo), k, padding=p, stride=s)                  # [N, C, Ho, Wo]
+        if bias is not None:
+            o = o + bias.double().view(1, C, 1, 1)
+        out.copy_(nhwc(_act(o, act)).to(out.dtype))
+
     # ---- convolutions (Conv2d-layout semantics; ConvTranspose2d layers use them mirrored)
     def conv_fprop(self, x, pf, bias, y, k, s, p, act=ACT_NONE, impl=""):
         # arithmetic is always fp64; only STORAGE follows the emulated mode (ideal-rounding model)
         w = pf.permute(0, 3, 1, 2).double()                         # [Co,Ci,kh,kw]
         out = F.conv2d(nchw(x).double(), w, None if bias is None else bias.double(), s, p)
         y.copy_(nhwc(_act(out, act)).to(y.dtype))
+
+    def conv_fprop_f32out(self, x, pf, y, k, s, p):
+        self.conv_fprop(x, pf, None, y, k, s, p)
 
     def conv_dgrad(self, dy, pd, bias, dx, k, s, p, act=ACT_NONE, impl=""):
         w = pd.permute(3, 0, 1, 2).double()                         # [Co,Ci,kh,kw] (= convT weight [in,out,kh,kw])

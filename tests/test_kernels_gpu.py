@@ -372,6 +372,44 @@ def test_patchify(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_patchify_generic(mode):
+    x = rnd(2, 9, 9, 2)                                   # odd size, 2 channels, k3 s1 p1 -> generic kernel
+    run_pair(mode, "patchify", [T(x), T(torch.zeros(2, 9, 9, 18)), 3, 1, 1], [1])
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", [(3, 8, 3, 4, 2, 1, ACT_TANH, True), (2, 16, 3, 4, 2, 1, ACT_NONE, False),
+                                  (2, 5, 2, 3, 1, 1, ACT_NONE, True), (1, 4, 4, 4, 1, 0, ACT_LRELU, True)])
+def test_unpatchify(mode, case):
+    N, Hi, C, k, s, p, act, use_bias = case
+    Ho = (Hi - 1) * s - 2 * p + k
+    col = rnd(N, Hi, Hi, C * k * k)
+    bias = F(rnd(C)) if use_bias else None
+    run_pair(mode, "unpatchify", [F(col), bias, T(torch.zeros(N, Ho, Ho, C)), k, s, p], [2], dict(act=act))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_thin_conv_transpose_via_col2im(mode):
+    """ConvTranspose2d(Cin -> 3, k4 s2 p1) as 1x1 GEMM + col2im == the direct data-gradient kernel's definition."""
+    N, Hi, Cin = 2, 16, 24
+    x, w = rnd(N, Hi, Hi, Cin), rnd(Cin, 3, 4, 4, scale=(Cin * 4) ** -0.5)      # conv op: Co=Cin, Ci=3
+    pd = w.permute(1, 2, 3, 0).contiguous()                                    # [3][4][4][Cin]
+    bias = rnd(3)
+    ops = _ops(mode)
+    dev = lambda t, d=None: t.to(d or ops.act_dtype).cuda().contiguous()
+    xq, pdq = dev(x), dev(pd)
+    col = ops.empty((N, Hi, Hi, 48), torch.float32)
+    out = ops.empty((N, 2 * Hi, 2 * Hi, 3))
+    ops.conv_fprop_f32out(xq, pdq.view(48, 1, 1, Cin), col, 1, 1, 0)
+    ops.unpatchify(col, dev(bias, torch.float32), out, 4, 2, 1, act=ACT_TANH)
+    ref = torch.tanh(torch.nn.functional.conv_transpose2d(xq.double().cpu().permute(0, 3, 1, 2),
+                                                          pdq.double().cpu().permute(3, 0, 1, 2), bias.double(), 2, 1))
+    got = out.double().cpu().permute(0, 3, 1, 2)
+    t = TOL[mode]
+    assert torch.allclose(got, ref, rtol=t["rtol"], atol=t["atol"] * ref.abs().max().item()), (got - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_concat_split_affine(mode):
     N, H, Cx, Cc = 3, 16, 512, 128
     x, c = rnd(N, H, H, Cx), rnd(N, Cc)
