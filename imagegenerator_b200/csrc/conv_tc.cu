@@ -916,6 +916,224 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, version 2
+// Same GEMM (D[co][(ci,tap)] += dy^T x over pixels, both operands MN-major), re-tiled:
+//   * the N dimension is a list of UNITS u = cib*kk + tap (one 64-channel block of ci at one tap = 64 TMEM
+//     columns); a CTA owns up to 8 consecutive units whatever k is, so a 3x3 layer (9 taps) is 8+8+...
+//     instead of an 8-tap and a 1-tap CTA, and units are dealt out evenly over the CTAs;
+//   * PIX = 32-pixel k-blocks: a stage is 8 KB of dy + 4 KB per unit = 40 KB -> 5 stages in flight
+//     (the 64-pixel version had 2), which is what hides the latency of ten TMA loads per stage;
+//   * split-K sized so that tiles x splits fills the 148 SMs in whole waves.
+struct TcW2Params {
+    int Mpix, Ho, Wo;
+    int Co, Ci, kk, k, s, p;
+    int cblocks, units;        // ci blocks of 64, total units = cblocks*kk
+    int ugroups, ubase, urem;  // unit groups: group g has ubase + (g < urem) units
+    int kb_per_split, total_kb;
+    int stages;
+    float* dw;
+    int dw_cl;                 // 0: dw[Co][Ci][kk] (PyTorch), 1: dw[Co][kk][Ci] (channels-last accumulation buffer)
+};
+
+template <int PIX>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcW2Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int A_BYTES = 2 * PIX * 128;      // dy: two 64-channel blocks x PIX pixels
+    constexpr int B_BYTES = PIX * 128;          // x at one unit: 64 channels x PIX pixels
+
+    const int co0 = blockIdx.x * 128;
+    const int ug = blockIdx.y;
+    const int u0 = ug * P.ubase + min(ug, P.urem);
+    const int nun = P.ubase + (ug < P.urem ? 1 : 0);
+    const int stage_bytes = A_BYTES + 8 * B_BYTES;
+    const int kb0 = blockIdx.z * P.kb_per_split;
+    const int nkb = min(P.kb_per_split, P.total_kb - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            // producer warp: lane 0 owns the barriers, lanes 0..nun-1 each issue the TMA load of one unit and lanes
+            // nun, nun+1 the two dy blocks -- ten loads per stage leave in parallel instead of one after another
+            int uc = 0, ukh = 0, ukw = 0;
+            if (lane < nun) {
+                const int u = u0 + lane, cib = u / P.kk, tap = u - cib * P.kk;
+                uc = cib * 64; ukh = tap / P.k; ukw = tap - ukh * P.k;
+            }
+            int st = 0;
+            uint32_t par = 1;
+            int pix0 = kb0 * PIX;
+            int ow0 = pix0 % P.Wo, oh0 = (pix0 / P.Wo) % P.Ho, n0 = pix0 / (P.Wo * P.Ho);
+            for (int i = 0; i < nkb; ++i) {
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[st], par);
+                    mbar_expect_tx(&full_bar[st], (uint32_t)(A_BYTES + nun * B_BYTES));
+                }
+                __syncwarp();
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                if (lane < nun)
+                    tma_load_4d(&tmX, &full_bar[st], sa + A_BYTES + lane * B_BYTES, uc, ow0 * P.s - P.p + ukw,
+                                oh0 * P.s - P.p + ukh, n0);
+                else if (lane < nun + 2)
+                    tma_load_2d(&tmDy, &full_bar[st], sa + (lane - nun) * (PIX * 128), co0 + (lane - nun) * 64, pix0);
+                if (++st == P.stages) { st = 0; par ^= 1; }
+                // advance the pixel block (blocks never straddle images: Ho*Wo % PIX == 0 or PIX % (Ho*Wo) == 0)
+                pix0 += PIX;
+                ow0 += PIX;
+                if (ow0 >= P.Wo) {
+                    const int rows = ow0 / P.Wo;
+                    ow0 -= rows * P.Wo; oh0 += rows;
+                    if (oh0 >= P.Ho) { const int imgs = oh0 / P.Ho; oh0 -= imgs * P.Ho; n0 += imgs; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                // D=f32, A=B=bf16, both MN-major, M=128; up to FOUR units (N = 256) per instruction: the unit tiles lie
+                // B_BYTES apart in shared memory, which is exactly the descriptor's stride between 64-element blocks
+                // along N, so the 128 x 16 slab of dy is read from shared memory twice per k-step instead of 8 times
+                // (an N=64 MMA re-reads 4 KB of A for 2 KB of B and is shared-memory bound)
+                const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
+                const int n_lo = nun < 4 ? nun : 4, n_hi = nun - n_lo;
+                const uint32_t idesc_lo = idesc0 | ((uint32_t)((n_lo * 64) >> 3) << 17);
+                const uint32_t idesc_hi = idesc0 | ((uint32_t)((n_hi * 64) >> 3) << 17);
+                int st = 0;
+                uint32_t par = 0;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full_bar[st], par);
+                    tc_fence_after();
+                    const uint32_t sa = base + (uint32_t)st * stage_bytes;
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k16 = 0; k16 < PIX / 16; ++k16) {
+                        const uint64_t ad = make_mnmajor_sw128_desc(sa + k16 * 2048, PIX * 128);
+                        const uint64_t b0 = make_mnmajor_sw128_desc(sb + k16 * 2048, B_BYTES);
+                        tc_mma_bf16(tmem_base, ad, b0, idesc_lo, (i | k16) != 0 ? 1u : 0u);
+                        if (n_hi > 0) {
+                            const uint64_t b1 = make_mnmajor_sw128_desc(sb + 4 * B_BYTES + k16 * 2048, B_BYTES);
+                            tc_mma_bf16(tmem_base + 256, ad, b1, idesc_hi, (i | k16) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty_bar[st]);
+                    if (++st == P.stages) { st = 0; par ^= 1; }
+                }
+                tc_commit(&accum_bar);
+            }
+        } else {
+            const int q = warp & 3;
+            const int co = co0 + q * 32 + lane;
+            mbar_wait(&accum_bar, 0);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            const bool co_ok = co < P.Co;
+            if (P.dw_cl) {
+                // channels-last accumulation buffer dw[co][tap][ci]: a chunk's 16 columns are contiguous floats
+                for (int t = 0; t < nun; ++t) {
+                    const int u = u0 + t, cib = u / P.kk, tap = u - cib * P.kk;
+                    const int ci0 = cib * 64;
+                    for (int c16 = 0; c16 < 64 && ci0 + c16 < P.Ci; c16 += 16) {
+                        uint32_t v[16];
+                        tc_ld16(trow + (uint32_t)(t * 64 + c16), v);
+                        if (!co_ok) continue;
+                        float* dst = P.dw + ((int64_t)co * P.kk + tap) * P.Ci + ci0 + c16;
+                        if (ci0 + c16 + 16 <= P.Ci) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                                             "f"(__uint_as_float(v[j + 3])) : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ci0 + c16 + j < P.Ci) atomicAdd(dst + j, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            } else if (P.kk == 1) {
+                // 1x1: the 16 columns of a chunk are 16 consecutive ci -> contiguous floats of dw[co][:]
+                for (int t = 0; t < nun; ++t) {
+                    const int ci0 = (u0 + t) * 64;
+                    for (int c16 = 0; c16 < 64 && ci0 + c16 < P.Ci; c16 += 16) {
+                        uint32_t v[16];
+                        tc_ld16(trow + (uint32_t)(t * 64 + c16), v);
+                        if (!co_ok) continue;
+                        float* dst = P.dw + (int64_t)co * P.Ci + ci0 + c16;
+                        if ((P.Ci & 3) == 0 && ci0 + c16 + 16 <= P.Ci) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                                             "f"(__uint_as_float(v[j + 3])) : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ci0 + c16 + j < P.Ci) atomicAdd(dst + j, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            } else if ((P.kk & 3) == 0 && (u0 & 3) == 0) {
+                // taps in groups of 4 are contiguous in dw[co][ci][tap]: one vector reduction per (ci, 4 taps)
+                for (int t = 0; t < nun; t += 4) {
+                    const int u = u0 + t, cib = u / P.kk, tap = u - cib * P.kk;
+                    const int ci0 = cib * 64;
+                    for (int c16 = 0; c16 < 64 && ci0 + c16 < P.Ci; c16 += 16) {
+                        uint32_t v[4][16];
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) tc_ld16(trow + (uint32_t)((t + w) * 64 + c16), v[w]);
+                        if (!co_ok) continue;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int ci = ci0 + c16 + j;
+                            if (ci >= P.Ci) break;
+                            float* dst = P.dw + ((int64_t)co * P.Ci + ci) * P.kk + tap;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v[0][j])),
+                                         "f"(__uint_as_float(v[1][j])), "f"(__uint_as_float(v[2][j])),
+                                         "f"(__uint_as_float(v[3][j])) : "memory");
+                        }
+                    }
+                }
+            } else {
+                for (int t = 0; t < nun; ++t) {
+                    const int u = u0 + t, cib = u / P.kk, tap = u - cib * P.kk;
+                    const int ci0 = cib * 64;
+                    for (int c16 = 0; c16 < 64 && ci0 + c16 < P.Ci; c16 += 16) {
+                        uint32_t v[16];
+                        tc_ld16(trow + (uint32_t)(t * 64 + c16), v);
+                        if (!co_ok) continue;
+                        float* dst = P.dw + ((int64_t)co * P.Ci + ci0 + c16) * P.kk + tap;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ci0 + c16 + j < P.Ci) atomicAdd(dst + (int64_t)j * P.kk, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1275,6 +1493,91 @@ static int launch_wgrad_tc(const void* x, const void* dy, float* dw, int N, int 
     return check_launch("conv_wgrad_tc");
 }
 
+static bool choose_box_n(int npix, int Ho, int Wo, int* bw, int* bh, int* bn) {
+    if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
+    if (Wo >= npix) { *bw = npix; *bh = 1; *bn = 1; return true; }
+    *bw = Wo;
+    int rows = npix / Wo;
+    if (Ho >= rows) { *bh = rows; *bn = 1; return true; }
+    *bh = Ho;
+    *bn = rows / Ho;
+    return true;
+}
+
+// 2-D [rows][C] bf16 view, box {64, npix}
+static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtensorMap* out) {
+    MapKey key(ptr, (int)rows, C, 64, npix, 0, 0, 0, 0, 23);
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)npix};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rows=%lld C=%d) failed: %d", (long long)rows, C, (int)r); return SG_ERR_UNSUPPORTED; }
+    g_maps[key] = m;
+    *out = m;
+    return 0;
+}
+
+int g_use_wgrad2 = 1;
+static bool g_w2attr_set = false;
+
+static int launch_wgrad2(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, cudaStream_t st, int dw_cl = 0) {
+    int e = ensure_encode();
+    if (e) return e;
+    constexpr int PIX = 32;
+    TcW2Params P;
+    P.Mpix = N * Ho * Wo; P.Ho = Ho; P.Wo = Wo; P.Co = Co; P.Ci = Ci; P.kk = k * k; P.k = k; P.s = s; P.p = p; P.dw = dw;
+    P.dw_cl = dw_cl;
+    int bw, bh, bn;
+    if (!choose_box_n(PIX, Ho, Wo, &bw, &bh, &bn)) { set_error("wgrad2: grid not tileable"); return SG_ERR_UNSUPPORTED; }
+    P.cblocks = (Ci + 63) / 64;
+    P.units = P.cblocks * P.kk;
+    P.ugroups = (P.units + 7) / 8;
+    P.ubase = P.units / P.ugroups;
+    P.urem = P.units % P.ugroups;
+    P.total_kb = (P.Mpix + PIX - 1) / PIX;
+    P.stages = 5;
+    CUtensorMap tmDy, tmX;
+    if ((e = get_rows_map_n(dy, P.Mpix, Co, PIX, &tmDy))) return e;
+    if ((e = get_act_map(x, N, H, W, Ci, bw, bh, bn, s, &tmX))) return e;
+    const int co_tiles = (Co + 127) / 128;
+    const int tiles = co_tiles * P.ugroups;
+    // splits: fill whole waves of 148 CTAs, at least 8 k-blocks per CTA
+    int max_splits = P.total_kb / 8;
+    if (max_splits < 1) max_splits = 1;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+        long ctas = (long)tiles * sp;
+        long waves = (ctas + SG_NUM_SMS - 1) / SG_NUM_SMS;
+        int kbs = (P.total_kb + sp - 1) / sp;
+        // fixed cost per CTA in k-block units (0.6 us each): prologue + the atomics epilogue, ~10 us with vector
+        // reductions, ~40 us with scalar ones (k*k not a multiple of 4 in the PyTorch layout)
+        const bool vec_epi = dw_cl || P.kk == 1 || (P.kk & 3) == 0;
+        double cost = (double)waves * (kbs + (vec_epi ? 18.0 : 66.0));
+        if (cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    P.kb_per_split = (P.total_kb + best - 1) / best;
+    const int splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
+    size_t smem = (size_t)P.stages * (2 * PIX * 128 + 8 * PIX * 128) + 1024;
+    if (!g_w2attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad2): %s", cudaGetErrorString(ce)); return (int)ce; }
+        g_w2attr_set = true;
+    }
+    dim3 grid(co_tiles, P.ugroups, splits);
+    conv_wgrad2_kernel<PIX><<<grid, TC_THREADS, smem, st>>>(tmDy, tmX, P);
+    g_launches.fetch_add(1);
+    return check_launch("conv_wgrad2");
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -1297,6 +1600,7 @@ int sg_conv_tc_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, 
 int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "tc2")) { g_use_tc2 = value; return 0; }
     if (name && !strcmp(name, "persist")) { g_use_persist = value; return 0; }
+    if (name && !strcmp(name, "wgrad2")) { g_use_wgrad2 = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
     if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
     if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }
@@ -1339,10 +1643,30 @@ int sg_conv_wgrad_tc_supported(int N, int H, int W, int Ci, int Ho, int Wo, int 
     return 1;
 }
 
+// accumulate into a channels-last gradient buffer gw[Co][k][k][Ci] (vector reductions for any k); sg_fold_grad_cl
+// adds it into the PyTorch-layout gradient
+int sg_conv_wgrad_cl_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype) {
+    int bw, bh, bn;
+    if (dtype != SG_BF16 || !g_use_wgrad2 || Ci % 4 != 0) return 0;
+    if (!sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p)) return 0;
+    return choose_box_n(32, Ho, Wo, &bw, &bh, &bn) && bw * s <= 256 && bh * s <= 256;
+}
+int sg_conv_wgrad_cl(const void* x, const void* dy, float* gw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
+                     int s, int p, int dtype, void* stream) {
+    SG_REQUIRE(sg_conv_wgrad_cl_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype), "conv_wgrad_cl: unsupported shape/dtype");
+    return launch_wgrad2(x, dy, gw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream), 1);
+}
+
 int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
                      int s, int p, int dtype, void* stream) {
     SG_REQUIRE(dtype == SG_BF16, "conv_wgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_wgrad_tc: unsupported shape");
+    if (g_use_wgrad2) {
+        int bw, bh, bn;
+        // 32-pixel blocks must not straddle images unless whole images fit a block
+        if (choose_box_n(32, Ho, Wo, &bw, &bh, &bn) && bw * s <= 256 && bh * s <= 256)
+            return launch_wgrad2(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
+    }
     return launch_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
 }
 

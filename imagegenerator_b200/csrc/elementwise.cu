@@ -431,6 +431,19 @@ __global__ void pack_weight_kernel(const float* w, T* pf, T* pd, int Co, int Ci,
     }
 }
 
+// dw[co][ci][t] += gw[co][t][ci]; gw = 0   (fold a channels-last accumulation buffer into the PyTorch-layout gradient)
+__global__ void __launch_bounds__(256) fold_grad_cl_kernel(float* __restrict__ gw, float* __restrict__ dw, int Ci, int kk,
+                                                           int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int ci = (int)(i % Ci);
+        const int64_t r = i / Ci;
+        const int t = (int)(r % kk);
+        const int64_t co = r / kk;
+        dw[(co * Ci + ci) * kk + t] += gw[i];
+        gw[i] = 0.f;
+    }
+}
+
 // ---- patch matrix of a thin (<= 4 channel) image: P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci]
 // (the PyTorch weight order, so the layer becomes a 1x1 convolution over P for the tensor-core kernels)
 template <typename T>
@@ -768,6 +781,13 @@ int sg_unpatchify(const float* col, const float* bias, void* out, int N, int Hi,
     SG_DISPATCH_T(dtype, (unpatchify_kernel<T><<<grid_for(total, 256, 16), 256, 0, SG_STREAM(stream)>>>(
                              col, bias, (T*)out, Hi, Wi, Ho, Wo, C, k, s, p, act, total)));
     SG_LAUNCHED("unpatchify");
+    return 0;
+}
+
+int sg_fold_grad_cl(float* gw, float* dw, int Co, int Ci, int kk, void* stream) {
+    int64_t total = (int64_t)Co * Ci * kk;
+    fold_grad_cl_kernel<<<grid_for(total, 256, 8), 256, 0, SG_STREAM(stream)>>>(gw, dw, Ci, kk, total);
+    SG_LAUNCHED("fold_grad_cl");
     return 0;
 }
 

@@ -95,6 +95,24 @@ class Gen2RT:
         self.colf = ops.empty((B, 128, 128, self.K0), f32)
         self.ones = torch.ones(B, dtype=f32).to(ops.device)
 
+    def _wgrad(self, L, x, dy):
+        """Weight gradient of one residual-block conv: 3x3 taps are not a multiple of 4, so in the PyTorch layout
+        the tcgen05 kernel would leave through 4-byte atomics; accumulate channels-last and fold once per step."""
+        ops = self.ops
+        if getattr(L, "gw", None) is None:
+            L.gw = ops.zeros((L.co, L.k, L.k, L.ci), ops.f32) if ops.conv_wgrad_cl_supported(x, dy, L.k, L.s, L.p) else False
+        if not torch.is_tensor(L.gw):
+            ops.conv_wgrad(x, dy, L.conv.weight.grad, L.k, L.s, L.p)
+        else:
+            ops.conv_wgrad_cl(x, dy, L.gw, L.k, L.s, L.p)
+
+    def fold_grads(self):
+        """Add the channels-last accumulation buffers into the parameter gradients and clear them."""
+        for blk in self.res:
+            for L in blk:
+                if torch.is_tensor(getattr(L, "gw", None)):
+                    self.ops.fold_grad_cl(L.gw, L.conv.weight.grad)
+
     def all_layers(self):
         out = [self.ds0, self.ds2]
         for blk in self.res:
@@ -155,13 +173,13 @@ class Gen2RT:
             b1, b2, b3 = self.rb[r]
             dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
-            ops.conv_wgrad(b2.a, dy3, l3.conv.weight.grad, 3, 1, 1)
+            self._wgrad(l3, b2.a, dy3)
             ops.conv_dgrad(dy3, l3.pd, None, b2.da, 3, 1, 1)
             dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU)
-            ops.conv_wgrad(b1.a, dy2, l2.conv.weight.grad, 3, 1, 1)
+            self._wgrad(l2, b1.a, dy2)
             ops.conv_dgrad(dy2, l2.pd, None, b1.da, 3, 1, 1)
             dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU)
-            ops.conv_wgrad(self.X[r], dy1, l1.conv.weight.grad, 3, 1, 1)
+            self._wgrad(l1, self.X[r], dy1)
             ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
             ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)
         ops.split_rep_bwd(self.dX[0], self.b2.da, self.dc_hat)
@@ -173,6 +191,7 @@ class Gen2RT:
         ops.act_bwd(self.da1, self.a1, self.dy0, ACT_LRELU)
         ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
         ops.colsum(self.dy0, L.conv.bias.grad)
+        self.fold_grads()                                           # .grad is complete when backward() returns
         return self.dc_hat
 
 

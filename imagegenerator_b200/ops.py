@@ -37,6 +37,8 @@ _SIGS = {
     "sg_conv_fprop": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_dgrad": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_wgrad": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_conv_wgrad_cl": [_P, _P, _P] + [_I] * 11 + [_P],
+    "sg_fold_grad_cl": [_P, _P, _I, _I, _I, _P],
     "sg_conv_fprop_ffma": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_dgrad_ffma": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "sg_conv_wgrad_ffma": [_P, _P, _P] + [_I] * 11 + [_P],
@@ -77,7 +79,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
-                                 "sg_conv_tc_stats_supported"])
+                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported"])
 
 
 def load_library(path=LIB_PATH):
@@ -95,6 +97,8 @@ def load_library(path=LIB_PATH):
     lib.sg_conv_tc_supported.restype = _I
     lib.sg_conv_wgrad_tc_supported.argtypes = [_I] * 10
     lib.sg_conv_wgrad_tc_supported.restype = _I
+    lib.sg_conv_wgrad_cl_supported.argtypes = [_I] * 11
+    lib.sg_conv_wgrad_cl_supported.restype = _I
     lib.sg_set_option.argtypes = [_c.c_char_p, _I]
     lib.sg_set_option.restype = _I
     lib.sg_version.restype = _I
@@ -272,6 +276,24 @@ class CudaOps:
         assert dw.dtype == torch.float32 and tuple(dw.shape) == (d[6], d[3], k, k), (dw.shape, d)
         fn = getattr(self.lib, "sg_conv_wgrad" + impl)
         self._ck(fn(_ptr(x), _ptr(dy), _ptr(dw), *d, k, s, p, self._dt_of(x), self._st()))
+
+    def conv_wgrad_cl_supported(self, x, dy, k, s, p):
+        d = self._conv_dims(x, dy)
+        return bool(self.lib.sg_conv_wgrad_cl_supported(*d, k, s, p, self._dt_of(x)))
+
+    def conv_wgrad_cl(self, x, dy, gw, k, s, p):
+        """gw[Co][k][k][Ci] (fp32, channels-last accumulation buffer) += weight gradient."""
+        self._c(x, dy, gw)
+        d = self._conv_dims(x, dy)
+        assert gw.dtype == torch.float32 and tuple(gw.shape) == (d[6], k, k, d[3]), (gw.shape, d)
+        self._ck(self.lib.sg_conv_wgrad_cl(_ptr(x), _ptr(dy), _ptr(gw), *d, k, s, p, self._dt_of(x), self._st()))
+
+    def fold_grad_cl(self, gw, dw):
+        """dw[Co][Ci][k][k] += gw[Co][k][k][Ci]; gw = 0."""
+        self._c(gw, dw)
+        Co, k, _, Ci = gw.shape
+        assert tuple(dw.shape) == (Co, Ci, k, k)
+        self._ck(self.lib.sg_fold_grad_cl(_ptr(gw), _ptr(dw), Co, Ci, k * k, self._st()))
 
     def colsum(self, x, out):
         self._c(x, out)

@@ -50,7 +50,8 @@ int sg_check_device(void);
 /* number of kernels launched through this library since load (all threads) */
 int64_t sg_launch_count(void);
 /* tuning switches: "persist" = 1/0 persistent double-buffered conv kernel (default 1); "force_cg" / "force_bn" pin its
- * CTA-group size / tile width (0 = cost model); "tc2" = 1/0 CTA-pair tiles in the non-persistent kernels */
+ * CTA-group size / tile width (0 = cost model); "tc2" = 1/0 CTA-pair tiles in the non-persistent kernels;
+ * "wgrad2" = 1/0 unit-list weight-gradient kernel (default 1) */
 int sg_set_option(const char* name, int value);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
@@ -105,6 +106,14 @@ int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx,
 int sg_conv_wgrad(const void* x, const void* dy, float* dw,
                   int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p,
                   int dtype, void* stream);
+/* weight gradient accumulated in a channels-last buffer gw[Co][k][k][Ci] (fp32, += semantics): every 16 accumulator
+ * columns of the tcgen05 kernel are then 64 contiguous bytes and leave as vector reductions whatever k is (the
+ * PyTorch layout puts the k*k taps innermost, which for 3x3 layers -- generator_2.py:30 -- means 4-byte atomics).
+ * sg_fold_grad_cl adds gw into dw[Co][Ci][k][k] and clears it; call it once before the optimizer step. */
+int sg_conv_wgrad_cl_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype);
+int sg_conv_wgrad_cl(const void* x, const void* dy, float* gw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                     int k, int s, int p, int dtype, void* stream);
+int sg_fold_grad_cl(float* gw, float* dw, int Co, int Ci, int kk, void* stream);
 /* the same three entry points pinned to one implementation: *_ffma = CUDA-core implicit GEMM (fp32 or bf16
  * storage, fp32 accumulate), *_tc = tcgen05/TMEM/TMA (bf16 only; sg_conv_tc_supported / sg_conv_wgrad_tc_supported
  * say whether a shape is eligible).  sg_conv_* above dispatch between them. */

@@ -127,6 +127,19 @@ class EmuOps:
         g = torch.nn.grad.conv2d_weight(nchw(x).double(), dw.shape, nchw(dy).double(), stride=s, padding=p)
         dw.add_(g.to(dw.dtype))
 
+    def conv_wgrad_cl_supported(self, x, dy, k, s, p):
+        return True
+
+    def conv_wgrad_cl(self, x, dy, gw, k, s, p):
+        """channels-last accumulation buffer gw[Co,kh,kw,Ci] += weight gradient."""
+        Co, _, _, Ci = gw.shape
+        g = torch.nn.grad.conv2d_weight(nchw(x).double(), (Co, Ci, k, k), nchw(dy).double(), stride=s, padding=p)
+        gw.add_(g.permute(0, 2, 3, 1).to(gw.dtype))
+
+    def fold_grad_cl(self, gw, dw):
+        dw.add_(gw.permute(0, 3, 1, 2))
+        gw.zero_()
+
     def colsum(self, x, out):
         """out[C] (fp32) += sum over all leading dims of x[..., C]."""
         out.add_(x.reshape(-1, x.shape[-1]).to(out.dtype).sum(0))

@@ -365,6 +365,22 @@ def test_conv_wgrad_tcgen05(case):
     run_pair("bf16", "conv_wgrad", [T(x), T(dy), F(dw0), k, s, p], [2], dict(impl="_tc"), tol=dict(rtol=2e-3, atol=2e-4))
 
 
+@pytest.mark.parametrize("case", [(4, 16, 640, 320, 3, 1, 1), (4, 16, 320, 320, 3, 1, 1), (3, 16, 128, 256, 4, 2, 1),
+                                  (2, 32, 40, 24, 3, 1, 1)])
+def test_conv_wgrad_channels_last_and_fold(case):
+    """wgrad into the channels-last buffer + fold == wgrad into the PyTorch layout (accumulate semantics on both)."""
+    N, H, Ci, Co, k, s, p = case
+    ops = _ops("bf16")
+    Ho = (H + 2 * p - k) // s + 1
+    if not ops.lib.sg_conv_wgrad_cl_supported(N, H, H, Ci, Ho, Ho, Co, k, s, p, 1):
+        pytest.skip("not eligible")
+    x, dy = rnd(N, H, H, Ci), rnd(N, Ho, Ho, Co, scale=(N * Ho * Ho) ** -0.5)
+    gw0, dw0 = rnd(Co, k, k, Ci, scale=0.1), rnd(Co, Ci, k, k, scale=0.1)
+    run_pair("bf16", "conv_wgrad_cl", [T(x), T(dy), F(gw0), k, s, p], [2], tol=dict(rtol=2e-3, atol=2e-4))
+    ea, ca = run_pair("bf16", "fold_grad_cl", [F(gw0), F(dw0)], [0, 1], tol=dict(rtol=1e-6, atol=1e-7))
+    assert float(ca[0].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_patchify(mode):
     x = rnd(3, 16, 16, 3)
