@@ -930,7 +930,7 @@ struct TcW2Params {
     int cblocks, units;        // ci blocks of 64, total units = cblocks*kk
     int ugroups, ubase, urem;  // unit groups: group g has ubase + (g < urem) units
     int kb_per_split, total_kb;
-    int stages;
+    int stages, nun_max;       // pipeline depth; units per stage buffer
     float* dw;
     int dw_cl;                 // 0: dw[Co][Ci][kk] (PyTorch), 1: dw[Co][kk][Ci] (channels-last accumulation buffer)
 };
@@ -951,7 +951,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     const int ug = blockIdx.y;
     const int u0 = ug * P.ubase + min(ug, P.urem);
     const int nun = P.ubase + (ug < P.urem ? 1 : 0);
-    const int stage_bytes = A_BYTES + 8 * B_BYTES;
+    const int stage_bytes = A_BYTES + P.nun_max * B_BYTES;
     const int kb0 = blockIdx.z * P.kb_per_split;
     const int nkb = min(P.kb_per_split, P.total_kb - kb0);
 
@@ -1525,57 +1525,76 @@ static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtens
 }
 
 int g_use_wgrad2 = 1;
-static bool g_w2attr_set = false;
 
-static int launch_wgrad2(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
-                         int k, int s, int p, cudaStream_t st, int dw_cl = 0) {
-    int e = ensure_encode();
-    if (e) return e;
-    constexpr int PIX = 32;
-    TcW2Params P;
-    P.Mpix = N * Ho * Wo; P.Ho = Ho; P.Wo = Wo; P.Co = Co; P.Ci = Ci; P.kk = k * k; P.k = k; P.s = s; P.p = p; P.dw = dw;
-    P.dw_cl = dw_cl;
-    int bw, bh, bn;
+template <int PIX>
+static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                             int s, cudaStream_t st) {
+    int bw, bh, bn, e;
     if (!choose_box_n(PIX, Ho, Wo, &bw, &bh, &bn)) { set_error("wgrad2: grid not tileable"); return SG_ERR_UNSUPPORTED; }
-    P.cblocks = (Ci + 63) / 64;
-    P.units = P.cblocks * P.kk;
-    P.ugroups = (P.units + 7) / 8;
-    P.ubase = P.units / P.ugroups;
-    P.urem = P.units % P.ugroups;
     P.total_kb = (P.Mpix + PIX - 1) / PIX;
-    P.stages = 5;
+    const int stage_bytes = PIX * 128 * (2 + P.nun_max);
+    P.stages = (200 * 1024) / stage_bytes;
+    if (P.stages > 8) P.stages = 8;
     CUtensorMap tmDy, tmX;
     if ((e = get_rows_map_n(dy, P.Mpix, Co, PIX, &tmDy))) return e;
     if ((e = get_act_map(x, N, H, W, Ci, bw, bh, bn, s, &tmX))) return e;
     const int co_tiles = (Co + 127) / 128;
     const int tiles = co_tiles * P.ugroups;
-    // splits: fill whole waves of 148 CTAs, at least 8 k-blocks per CTA
-    int max_splits = P.total_kb / 8;
+    // splits: fill whole waves of 148 CTAs.  Fixed cost per CTA in 32-pixel k-block units (0.6 us each): prologue + the
+    // atomics epilogue, ~10 us with vector reductions, ~40 us with scalar ones (k*k not a multiple of 4, PyTorch layout)
+    const bool vec_epi = P.dw_cl || P.kk == 1 || (P.kk & 3) == 0;
+    const double fixed = (vec_epi ? 18.0 : 66.0) * 32.0 / PIX;
+    int max_splits = P.total_kb / 4;
     if (max_splits < 1) max_splits = 1;
     int best = 1;
     double best_cost = 1e30;
-    for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+    for (int sp = 1; sp <= max_splits && sp <= 148; ++sp) {
         long ctas = (long)tiles * sp;
         long waves = (ctas + SG_NUM_SMS - 1) / SG_NUM_SMS;
         int kbs = (P.total_kb + sp - 1) / sp;
-        // fixed cost per CTA in k-block units (0.6 us each): prologue + the atomics epilogue, ~10 us with vector
-        // reductions, ~40 us with scalar ones (k*k not a multiple of 4 in the PyTorch layout)
-        const bool vec_epi = dw_cl || P.kk == 1 || (P.kk & 3) == 0;
-        double cost = (double)waves * (kbs + (vec_epi ? 18.0 : 66.0));
+        double cost = (double)waves * (kbs + fixed);
         if (cost < best_cost) { best_cost = cost; best = sp; }
     }
     P.kb_per_split = (P.total_kb + best - 1) / best;
     const int splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
-    size_t smem = (size_t)P.stages * (2 * PIX * 128 + 8 * PIX * 128) + 1024;
-    if (!g_w2attr_set) {
+    size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
         cudaError_t ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
         if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad2): %s", cudaGetErrorString(ce)); return (int)ce; }
-        g_w2attr_set = true;
+        attr_set = true;
     }
     dim3 grid(co_tiles, P.ugroups, splits);
     conv_wgrad2_kernel<PIX><<<grid, TC_THREADS, smem, st>>>(tmDy, tmX, P);
     g_launches.fetch_add(1);
     return check_launch("conv_wgrad2");
+}
+
+static bool wgrad2_box_ok(int pix, int Ho, int Wo, int s) {
+    int bw, bh, bn;
+    return choose_box_n(pix, Ho, Wo, &bw, &bh, &bn) && bw * s <= 256 && bh * s <= 256;
+}
+
+static int launch_wgrad2(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, cudaStream_t st, int dw_cl = 0) {
+    int e = ensure_encode();
+    if (e) return e;
+    TcW2Params P;
+    P.Mpix = N * Ho * Wo; P.Ho = Ho; P.Wo = Wo; P.Co = Co; P.Ci = Ci; P.kk = k * k; P.k = k; P.s = s; P.p = p; P.dw = dw;
+    P.dw_cl = dw_cl;
+    P.cblocks = (Ci + 63) / 64;
+    P.units = P.cblocks * P.kk;
+    P.ugroups = (P.units + 7) / 8;
+    P.ubase = P.units / P.ugroups;
+    P.urem = P.units % P.ugroups;
+    P.nun_max = P.ubase + (P.urem > 0 ? 1 : 0);
+    // pixels per k-block: few units per CTA (thin layers) -> longer blocks, so that a stage stays ~40 KB and the
+    // per-stage barrier round trip is amortised
+    if (P.nun_max <= 2 && wgrad2_box_ok(128, Ho, Wo, s) && P.Mpix >= 128 * 8)
+        return launch_wgrad2_pix<128>(x, dy, P, N, H, W, Ci, Ho, Wo, Co, s, st);
+    if (P.nun_max <= 4 && wgrad2_box_ok(64, Ho, Wo, s) && P.Mpix >= 64 * 8)
+        return launch_wgrad2_pix<64>(x, dy, P, N, H, W, Ci, Ho, Wo, Co, s, st);
+    return launch_wgrad2_pix<32>(x, dy, P, N, H, W, Ci, Ho, Wo, Co, s, st);
 }
 
 }  // namespace sg

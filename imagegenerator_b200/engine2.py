@@ -191,7 +191,6 @@ class Gen2RT:
         ops.act_bwd(self.da1, self.a1, self.dy0, ACT_LRELU)
         ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
         ops.colsum(self.dy0, L.conv.bias.grad)
-        self.fold_grads()                                           # .grad is complete when backward() returns
         return self.dc_hat
 
 
@@ -226,7 +225,14 @@ class Stage2Engine:
         self.d.refresh_weights()
         self.g2.refresh_weights()
 
+    def sync_grads(self):
+        """Make every ``.grad`` current (the residual-block weight gradients accumulate in channels-last side
+        buffers during the step and are folded in here; ``optimizer_step`` does it for you)."""
+        self.g2.fold_grads()
+
     def optimizer_step(self, fp):
+        if fp is self.g2.fp:
+            self.g2.fold_grads()
         if self.comm is not None:
             self.comm.allreduce_async(fp.grad)
             self.comm.wait_all()

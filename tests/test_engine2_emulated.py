@@ -66,6 +66,7 @@ def test_stage2_outer_step_fp64_matches_oracle():
     ops_.gen_loss(d.score[2], eng.ca2.st.mu, eng.ca2.st.sigma, eng.losses[2:4])
     d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
     eng._generator_backward(d.group_view(d.dx, 1, 1), 1.0)
+    eng.sync_grads()
     assert abs(eng.losses[2].item() - ref["lossG"].item()) < 1e-8 * abs(ref["lossG"].item())
     for k, v in ms["g2"].named_parameters():
         _close(v.grad, ref["g2_grads"][k], 1e-5, 1e-8, f"g2 grad {k}")

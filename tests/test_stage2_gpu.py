@@ -52,6 +52,7 @@ def _run(ops, b, n_iter):
             out["gp"], out["loss_critic"] = c(eng.losses[1]), c(eng.losses[0])
             for k, v in ms["d2"].named_parameters():
                 out[f"dD2/{k}"] = c(v.grad)
+            eng.sync_grads()
             for k, v in ms["g2"].named_parameters():
                 out[f"dG2/{k}"] = c(v.grad)
             for k, v in ms["ca2"].named_parameters():
