@@ -25,6 +25,9 @@ int sg_conv_dgrad_tc_stats(const void*, const void*, void*, double*, int, int, i
                            void*);
 int sg_col_stats(const void*, double*, int64_t, int, int, int, void*);
 int sg_conv_fprop_tc_f32out(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, void*);
+int sg_conv_fprop_tc_res(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, int,
+                         int, int, void*);
+int sg_add_act(const void*, const void*, void*, int64_t, int, int, void*);
 
 static bool tc_enabled() {
     static int v = -1;
@@ -83,5 +86,15 @@ int sg_conv_fprop_f32out(const void* x, const void* pf, float* y, int N, int H, 
         return sg_conv_fprop_tc_f32out(x, pf, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
     sg::set_error("conv_fprop_f32out: shape not eligible for the tensor-core kernel (Ci %% 8 != 0?)");
     return SG_ERR_UNSUPPORTED;
+}
+
+// y = act(conv(x, W) + bias + residual).  Tensor-core shapes: fused in the epilogue; otherwise conv then sg_add_act.
+int sg_conv_fprop_res(const void* x, const void* pf, const float* bias, const void* residual, void* y, int N, int H, int W,
+                      int Ci, int Ho, int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream) {
+    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+        return sg_conv_fprop_tc_res(x, pf, bias, residual, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, stream);
+    int e = sg_conv_fprop(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
+    if (e) return e;
+    return sg_add_act(y, residual, y, (int64_t)N * Ho * Wo * Co, act, dtype, stream);
 }
 }

@@ -463,6 +463,7 @@ struct TcpParams {
     bf16* out;
     double* stats;        // [groups][n_total][2] or NULL
     float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
+    const bf16* residual; // added before the activation (same layout as out) or NULL
 };
 
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
@@ -686,6 +687,22 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c0 + j < ncols) f[j] += __ldg(P.bias + nt0 + c0 + j);
+                }
+                if (P.residual != nullptr && row_ok) {
+                    const bf16* rrow = P.residual + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0 + c0;
+                    if (vec_ok && c0 + 16 <= ncols) {
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(rrow), r1 = *reinterpret_cast<const uint4*>(rrow + 8);
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            f[2 * j] += __uint_as_float(rr[j] << 16);
+                            f[2 * j + 1] += __uint_as_float(rr[j] & 0xffff0000u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < ncols) f[j] += __bfloat162float(rrow[j]);
+                    }
                 }
                 if (act == SG_ACT_LRELU) {
 #pragma unroll
@@ -1363,7 +1380,7 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out
 
 static int launch_conv_tcp(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
                            int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, double* stats, int groups,
-                           cudaStream_t st, float* out32 = nullptr) {
+                           cudaStream_t st, float* out32 = nullptr, const void* residual = nullptr) {
     int e = ensure_encode();
     if (e) return e;
     TcpParams P;
@@ -1380,6 +1397,7 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
     P.stats = stats;
     P.out32 = out32;
+    P.residual = (const bf16*)residual;
     if (out32) P.out = nullptr;
     P.imgs_per_group = groups > 0 ? N / groups : N;
     const int phases = mode == 0 ? 1 : s * s;
@@ -1687,6 +1705,15 @@ int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int
             return launch_wgrad2(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
     }
     return launch_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
+}
+
+// y = act(conv(x, W) + bias + residual): the closing layer of a residual block (generator_2.py:23-26) in one kernel
+int sg_conv_fprop_tc_res(const void* x, const void* pf, const float* bias, const void* residual, void* y, int N, int H, int W,
+                         int Ci, int Ho, int Wo, int Co, int k, int s, int p, int act, void* stream) {
+    SG_REQUIRE(g_use_persist, "conv_fprop_tc_res needs the persistent kernel");
+    SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc_res: unsupported shape");
+    return launch_conv_tcp(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream), nullptr,
+                           residual);
 }
 
 // y (FP32) = conv(x, W) with bf16 operands: the un-rounded accumulators, for results that are summed again (col2im)

@@ -444,6 +444,42 @@ __global__ void __launch_bounds__(256) fold_grad_cl_kernel(float* __restrict__ g
     }
 }
 
+// ---- inference: eval-mode BatchNorm folded into the conv that precedes it
+__global__ void bn_fold_kernel(const float* rm, const float* rv, const float* gamma, const float* beta, float eps, float* scale,
+                               float* shift, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        float sc = (float)((double)gamma[c] / sqrt((double)rv[c] + (double)eps));
+        scale[c] = sc;
+        shift[c] = beta[c] - rm[c] * sc;
+    }
+}
+template <typename T>
+__global__ void pack_weight_scaled_kernel(const float* w, const float* scale, int axis, T* pf, T* pd, int Co, int Ci, int kk) {
+    int64_t total = (int64_t)Co * Ci * kk;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int t = (int)(i % kk);
+        int64_t r = i / kk;
+        int ci = (int)(r % Ci);
+        int co = (int)(r / Ci);
+        float v = w[i] * scale[axis == 0 ? co : ci];
+        if (pf) stf(pf + ((int64_t)co * kk + t) * Ci + ci, v);
+        if (pd) stf(pd + ((int64_t)ci * kk + t) * Co + co, v);
+    }
+}
+template <typename T>
+struct AddActF {
+    const T* a; const T* b; T* out; int act;
+    __device__ void operator()(int64_t i4) const {
+        int64_t e = i4 * 4;
+        F4 x = ld4(a + e), y = ld4(b + e), r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = act_fwd(x.v[j] + y.v[j], act);
+        st4(out + e, r);
+    }
+};
+
 // ---- patch matrix of a thin (<= 4 channel) image: P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci]
 // (the PyTorch weight order, so the layer becomes a 1x1 convolution over P for the tensor-core kernels)
 template <typename T>
@@ -782,6 +818,30 @@ int sg_unpatchify(const float* col, const float* bias, void* out, int N, int Hi,
                              col, bias, (T*)out, Hi, Wi, Ho, Wo, C, k, s, p, act, total)));
     SG_LAUNCHED("unpatchify");
     return 0;
+}
+
+int sg_bn_fold(const float* running_mean, const float* running_var, const float* gamma, const float* beta, float eps,
+               float* scale, float* shift, int C, void* stream) {
+    bn_fold_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(running_mean, running_var, gamma, beta, eps, scale, shift, C);
+    SG_LAUNCHED("bn_fold");
+    return 0;
+}
+int sg_pack_weight_scaled(const float* w, const float* scale, int axis, void* pf, void* pd, int Co, int Ci, int kk, int dtype,
+                          void* stream) {
+    SG_REQUIRE(axis == 0 || axis == 1, "pack_weight_scaled: axis 0 (Co) or 1 (Ci)");
+    int64_t n = (int64_t)Co * Ci * kk;
+    SG_DISPATCH_T(dtype, (pack_weight_scaled_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(w, scale, axis, (T*)pf,
+                                                                                                          (T*)pd, Co, Ci, kk)));
+    SG_LAUNCHED("pack_weight_scaled");
+    return 0;
+}
+int sg_add_act(const void* a, const void* b, void* out, int64_t n, int act, int dtype, void* stream) {
+    int e = 0;
+    SG_DISPATCH_T(dtype, {
+        AddActF<T> f{(const T*)a, (const T*)b, (T*)out, act};
+        e = launch_ew4(f, n, SG_STREAM(stream), "add_act");
+    });
+    return e;
 }
 
 int sg_fold_grad_cl(float* gw, float* dw, int Co, int Ci, int kk, void* stream) {

@@ -29,6 +29,11 @@ _SIGS = {
     "sg_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
     "sg_patchify": [_P, _P] + [_I] * 10 + [_P],
+    "sg_bn_fold": [_P, _P, _P, _P, _F, _P, _P, _I, _P],
+    "sg_pack_weight_scaled": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "sg_conv_fprop_res": [_P, _P, _P, _P, _P] + [_I] * 12 + [_P],
+    "sg_conv_fprop_tc_res": [_P, _P, _P, _P, _P] + [_I] * 11 + [_P],
+    "sg_add_act": [_P, _P, _P, _L, _I, _I, _P],
     "sg_unpatchify": [_P, _P, _P] + [_I] * 11 + [_P],
     "sg_conv_fprop_f32out": [_P, _P, _P] + [_I] * 11 + [_P],
     "sg_conv_fprop_tc_f32out": [_P, _P, _P] + [_I] * 10 + [_P],
@@ -199,6 +204,28 @@ class CudaOps:
         Co, Ci, k, _ = w.shape
         ref = pf if pf is not None else pd
         self._ck(self.lib.sg_pack_weight(_ptr(w), _ptr(pf), _ptr(pd), Co, Ci, k * k, self._dt_of(ref), self._st()))
+
+    def bn_fold(self, running_mean, running_var, gamma, beta, scale, shift, eps=1e-5):
+        self._c(running_mean, running_var, gamma, beta, scale, shift)
+        self._ck(self.lib.sg_bn_fold(_ptr(running_mean), _ptr(running_var), _ptr(gamma), _ptr(beta), eps, _ptr(scale),
+                                     _ptr(shift), gamma.numel(), self._st()))
+
+    def pack_weight_scaled(self, w, scale, axis, pf, pd):
+        self._c(w, scale, pf, pd)
+        Co, Ci, k, _ = w.shape
+        ref = pf if pf is not None else pd
+        self._ck(self.lib.sg_pack_weight_scaled(_ptr(w), _ptr(scale), axis, _ptr(pf), _ptr(pd), Co, Ci, k * k,
+                                                self._dt_of(ref), self._st()))
+
+    def conv_fprop_res(self, x, pf, bias, residual, y, k, s, p, act=ACT_NONE):
+        self._c(x, pf, bias, residual, y)
+        d = self._conv_dims(x, y)
+        self._ck(self.lib.sg_conv_fprop_res(_ptr(x), _ptr(pf), _ptr(bias), _ptr(residual), _ptr(y), *d, k, s, p, act,
+                                            self._dt_of(x), self._st()))
+
+    def add_act(self, a, b, out, act):
+        self._c(a, b, out)
+        self._ck(self.lib.sg_add_act(_ptr(a), _ptr(b), _ptr(out), a.numel(), act, self._dt_of(a), self._st()))
 
     def concat_rep(self, x, c, out):
         self._c(x, c, out)

@@ -148,6 +148,22 @@ int sg_conv_dgrad_tc_stats(const void* dy, const void* pd, void* dx, double* sta
                            int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
 int sg_conv_tc_stats_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups);
 
+/* ---- forward-only path (sampling, stage_2_train_fn.py:181-195): eval-mode BatchNorm folded into the conv ------ */
+/* scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale */
+int sg_bn_fold(const float* running_mean, const float* running_var, const float* gamma, const float* beta, float eps,
+               float* scale, float* shift, int C, void* stream);
+/* sg_pack_weight with every weight multiplied by scale[co] (axis 0: forward convs) or scale[ci] (axis 1: the
+ * output channels of a ConvTranspose2d run as sg_conv_dgrad) */
+int sg_pack_weight_scaled(const float* w, const float* scale, int axis, void* pf, void* pd, int Co, int Ci, int kk,
+                          int dtype, void* stream);
+/* y = act(conv(x, W) + bias + residual): closing layer of ResidualBlock.forward (generator_2.py:23-26) */
+int sg_conv_fprop_res(const void* x, const void* pf, const float* bias, const void* residual, void* y,
+                      int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream);
+int sg_conv_fprop_tc_res(const void* x, const void* pf, const float* bias, const void* residual, void* y, int N, int H, int W,
+                         int Ci, int Ho, int Wo, int Co, int k, int s, int p, int act, void* stream);
+/* out = act(a + b) */
+int sg_add_act(const void* a, const void* b, void* out, int64_t n, int act, int dtype, void* stream);
+
 /* out[C] (fp32) += column sums of x[rows][C]  (bias gradients) */
 int sg_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream);
 

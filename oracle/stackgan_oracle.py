@@ -215,6 +215,18 @@ def g2_forward(p, img_64, c_hat, training=True):
     return torch.tanh(x)
 
 
+def sample(ca1, g1, ca2, g2, tem, z, eps_ca1, eps_ca2, g2_training=False):
+    """The forward-only preview of stage_2_train_fn.py:181-195: c_hat1 -> gen_1 (eval, :59-63) -> fake_64;
+    c_hat2 -> gen_2 -> fake_256.  ``g2_training=True`` keeps gen_2's BatchNorm on batch statistics, which is what
+    the reference's in-loop call does (gen_2.train() at :90 is never undone); False is plain inference."""
+    with torch.no_grad():
+        c_hat1, _, _ = ca_forward(ca1, tem, eps_ca1)
+        fake_64 = g1_forward(g1, torch.cat((c_hat1, z), dim=1), training=False)
+        c_hat2, _, _ = ca_forward(ca2, tem, eps_ca2)
+        fake_256 = g2_forward(g2, fake_64, c_hat2, training=g2_training)
+    return fake_64, fake_256
+
+
 def gradient_penalty(critic_fn, real, fake, tem, eps):
     """utils.py:8-26; ``eps`` [B] is the torch.rand((B,1,1,1)) draw of :10."""
     e = eps.reshape(-1, 1, 1, 1).to(real.dtype)

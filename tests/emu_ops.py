@@ -81,6 +81,23 @@ class EmuOps:
         if pd is not None:
             pd.copy_(w.permute(1, 2, 3, 0).to(pd.dtype))
 
+    def bn_fold(self, running_mean, running_var, gamma, beta, scale, shift, eps=1e-5):
+        sc = gamma.double() / torch.sqrt(running_var.double() + eps)
+        scale.copy_(sc.to(scale.dtype))
+        shift.copy_((beta.double() - running_mean.double() * sc).to(shift.dtype))
+
+    def pack_weight_scaled(self, w, scale, axis, pf, pd):
+        shp = (-1, 1, 1, 1) if axis == 0 else (1, -1, 1, 1)
+        self.pack_weight(w * scale.to(w.dtype).view(shp), pf, pd)
+
+    def conv_fprop_res(self, x, pf, bias, residual, y, k, s, p, act=ACT_NONE):
+        w = pf.permute(0, 3, 1, 2).double()
+        out = F.conv2d(nchw(x).double(), w, None if bias is None else bias.double(), s, p) + nchw(residual).double()
+        y.copy_(nhwc(_act(out, act)).to(y.dtype))
+
+    def add_act(self, a, b, out, act):
+        out.copy_(_act(a.double() + b.double(), act).to(out.dtype))
+
     def patchify(self, x, P, k, s, p):
         """P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci]  (F.unfold order)."""
         N, Ho, Wo, K = P.shape
