@@ -40,14 +40,44 @@ FLOPS_PER_IMG_REFERENCE_NECESSARY = 77 * F_D1 + 7 * F_G1    # BASELINE.md sectio
 
 
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region: NVML in a thread (every 20 ms), nvidia-smi as fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.stop_flag, self.thread, self.nvml = [], None, index, False, None, None
+        self.max_mhz, self.reason_bits = None, 0
+
+    def _nvml_loop(self):
+        n, h = self.nvml
+        while not self.stop_flag:
+            try:
+                self.rows.append(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            h = n.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            self.nvml = (n, h)
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -61,6 +91,18 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            n = self.nvml[0]
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            busy = sorted(x for x in self.rows if x > 0)
+            return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, bit in names.items() if self.reason_bits & bit), "samples": len(self.rows),
+                    "source": "nvml, 20 ms period, timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -70,7 +112,7 @@ class ClockSampler:
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
         busy = [x for x in sm if x > 0]
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvidia-smi -lms 100"}
 
 
 def build_modules(seed=42):
@@ -160,6 +202,107 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ secondary workloads
+F_D2, F_G2, F_CA = 0.36412e9, 15.14563e9, 0.000393e9
+# executed per image and Stage-II outer step: 5 x (G1 fwd + G2 fwd/dgrad/wgrad (3 F_G2) + critic 12 F_D2 + d/d image F_D2)
+# + generator step (2 F_D2 + 2 F_G2);  reference-necessary: 77 F_D2 + 17 F_G2 + 5 F_G1
+FLOPS2_PER_IMG = 5 * (F_G1 + 3 * F_G2 + 13 * F_D2) + (2 * F_D2 + 2 * F_G2)
+FLOPS2_PER_IMG_REFERENCE_NECESSARY = 77 * F_D2 + 17 * F_G2 + 5 * F_G1
+
+
+def run_stage2(ops, comm, world, rank, dev, steps=5, warmup=3, B=64):
+    """BASELINE.json configs[2]/[3]: Stage-II 256x256 outer step, batch 64 per GPU, bf16 (frozen Stage-I generator)."""
+    import torch.distributed as dist
+    from imagegenerator_b200.con_augment import ConditioningAugmentation
+    from imagegenerator_b200.discriminator_2 import StageIIDiscriminator
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    from imagegenerator_b200.generator_2 import StageIIGenerator
+    from imagegenerator_b200.engine2 import Stage2Engine
+    torch.manual_seed(42)
+    ca1, g1 = ConditioningAugmentation(512, 256, 128), StageIGenerator(128, 100)
+    ca2, d2, g2 = ConditioningAugmentation(512, 256, 128), StageIIDiscriminator(512, 128), StageIIGenerator()
+    eng = Stage2Engine(ca1, g1, ca2, d2, g2, B, ops=ops, comm=comm)
+    g = torch.Generator().manual_seed(3000 + rank)
+    real = torch.randn(B, 3, 256, 256, generator=g).clamp_(-1, 1).to(dev)
+    tem = torch.randn(B, 512, generator=g).to(dev)
+    tem_mis = tem[torch.randperm(B, generator=g).to(dev)].contiguous()
+    gz = torch.Generator().manual_seed(5)
+    z = torch.randn(5, B, 100, generator=gz).to(dev)
+    e1, e2 = torch.randn(5, B, 128, generator=gz).to(dev), torch.randn(5, B, 128, generator=gz).to(dev)
+    egp = torch.rand(5, B, generator=gz).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        eng.step(real, tem, tem_mis, z, e1, e2, egp, use_graph=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eng.step(real, tem, tem_mis, z, e1, e2, egp, use_graph=True); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"metric": "stackgan_stage2_train_images_per_sec", "value": round(B * world / (ms * 1e-3), 2), "unit": "images/s",
+           "ms_per_step": round(ms, 3), "batch_per_gpu": B, "steps": steps, "warmup": warmup,
+           "step_tflops_per_gpu": round(FLOPS2_PER_IMG * B / (ms * 1e-3) / 1e12, 1),
+           "flops_per_image_executed": FLOPS2_PER_IMG, "flops_per_image_reference_necessary": FLOPS2_PER_IMG_REFERENCE_NECESSARY,
+           "gpu_launches_per_step": eng.launches_per_step, "mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sampling(ops, world, rank, dev, reps=20, B=64):
+    """BASELINE.json configs[4]: Stage-I -> Stage-II forward-only sampling, batch sharded over the GPUs."""
+    import torch.distributed as dist
+    from imagegenerator_b200.con_augment import ConditioningAugmentation
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    from imagegenerator_b200.generator_2 import StageIIGenerator
+    from imagegenerator_b200.sampler import StackGANSampler
+    torch.manual_seed(42)
+    smp = StackGANSampler(ConditioningAugmentation(512, 256, 128), StageIGenerator(128, 100),
+                          ConditioningAugmentation(512, 256, 128), StageIIGenerator(), B, ops=ops)
+    g = torch.Generator().manual_seed(4000 + rank)
+    tem = torch.randn(B, 512, generator=g).pin_memory()
+    z, e1, e2 = (torch.randn(B, n, generator=g).pin_memory() for n in (100, 128, 128))
+    host_out = torch.empty(B, 3, 256, 256).pin_memory()
+    for _ in range(3):
+        smp.sample(tem, z, e1, e2)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        smp.graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    ms_dev = a.elapsed_time(b) / reps
+    a.record()
+    for _ in range(reps):
+        _, img = smp.sample(tem, z, e1, e2)
+        host_out.copy_(img, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms_e2e = a.elapsed_time(b) / reps
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    flops = (2 * F_CA + F_G1 + F_G2) * B
+    return {"metric": "stackgan_sampling_images_per_sec", "value": round(B * world / (ms_dev * 1e-3), 1), "unit": "images/s",
+            "batch_per_gpu": B, "ms_per_batch": round(ms_dev, 3), "tflops_per_gpu": round(flops / (ms_dev * 1e-3) / 1e12, 1),
+            "e2e": {"value": round(B * world / (ms_e2e * 1e-3), 1), "ms_per_batch": round(ms_e2e, 3),
+                    "h2d_bytes_per_step": B * (512 + 100 + 256) * 4, "d2h_bytes_per_step": B * 3 * 256 * 256 * 4},
+            "gpu_launches_per_batch": smp.launches, "bn": "eval mode, folded into the packed conv weights"}
+
+
 # ------------------------------------------------------------------------------------------------ kernel roofline
 def time_dominant_kernel(ops, B, reps=20):
     """The critic's heaviest conv (ds3: 128->256, 16x16 -> 8x8, all three image groups batched) timed
@@ -196,6 +339,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Stage-II and sampling sections of the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -311,6 +455,19 @@ def main():
     h2d = B * 3 * 64 * 64 * 4 + B * 8 + 5 * B * 100 * 4 + 5 * B * 4       # images + idx + z + gp eps (fp32)
     d2h = 4 * 4
 
+    s1_bytes_per_step = (comm.bytes_reduced // (W + 2 * K + 2)) if comm else 0
+    extras = {}
+    if not args.no_extras and args.mode == "bf16":
+        del eng
+        torch.cuda.empty_cache()
+        try:
+            extras["stage2"] = run_stage2(ops, comm, world, rank, dev)
+            extras["sampling"] = run_sampling(ops, world, rank, dev)
+        except Exception as e:                                    # secondary sections must not take the headline down
+            extras["extras_error"] = f"{type(e).__name__}: {e}"
+            if world > 1:
+                raise
+
     line = None
     if rank == 0:
         peaks = {}
@@ -330,7 +487,7 @@ def main():
                                    "+ 1 generator/CA update, Adam), batch 128/GPU",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": use_graph, "grad_allreduce": ("NCCL avg, 2 buckets/critic step on a side stream, "
-                                                                    f"{comm.bytes_reduced // (W + 2 * K + 2)} B/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",
+                                                                    f"{s1_bytes_per_step} B/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "flops_per_image_executed": FLOPS_PER_IMG,
                        "flops_per_image_reference_necessary": FLOPS_PER_IMG_REFERENCE_NECESSARY},
             "step_tflops": round(FLOPS_PER_IMG * B / (step_ms * 1e-3) / 1e12, 2),
@@ -344,6 +501,7 @@ def main():
                          "kernel_ms": round(kms, 5)},
             "clocks": clocks,
         }
+        line.update(extras)
     if world > 1:
         dist.barrier()
     if rank == 0:

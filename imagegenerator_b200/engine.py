@@ -15,6 +15,7 @@ feature maps and differs only in the affine head.
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 
 import torch
@@ -489,6 +490,11 @@ class Stage1Engine:
                 off += p.numel()
             self.d_tail_off = off
         self.real_nchw = None
+        # Handing the tail of the critic's gradient to NCCL while the trunk backward still runs was measured to HURT on
+        # B200 (2 GPUs: 12.7-20.8 ms/step vs 10.7 ms with one all-reduce per optimizer step): the persistent conv kernels
+        # want all 148 SMs, and an NCCL kernel that holds a few of them while it waits for its peer stalls whole tile
+        # waves.  Default: one all-reduce right before each Adam step; SG_EARLY_BUCKET=1 restores the overlap.
+        self.early_bucket = os.environ.get("SG_EARLY_BUCKET") == "1"
         self.refresh_all()
 
     def refresh_all(self):
@@ -556,7 +562,7 @@ class Stage1Engine:
         tail = [0]
 
         def bucket(l):
-            if self.comm is not None and l == d.nl - 1:
+            if self.comm is not None and l == d.nl - 1 and self.early_bucket:
                 self._comm_allreduce(d.fp.grad[self.d_tail_off:])
                 tail[0] = self.d_tail_off
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147

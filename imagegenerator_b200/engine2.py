@@ -231,11 +231,17 @@ class Stage2Engine:
         self.g2.fold_grads()
 
     def optimizer_step(self, fp):
+        """xm.optimizer_step (stage_2_train_fn.py:155,164,167): gradient mean over replicas, then Adam.  Under
+        multi-GPU graph capture the NCCL call is issued eagerly between two graph segments (engine._SegmentedGraph)."""
         if fp is self.g2.fp:
             self.g2.fold_grads()
         if self.comm is not None:
-            self.comm.allreduce_async(fp.grad)
-            self.comm.wait_all()
+            seg = getattr(self, "_seg", None)
+            if seg is not None and seg.capturing:
+                seg.cut(lambda: (self.comm.allreduce_async(fp.grad), self.comm.wait_all()))
+            else:
+                self.comm.allreduce_async(fp.grad)
+                self.comm.wait_all()
         self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
 
     def load_batch(self, real_nchw, tem, tem_mis):
@@ -315,11 +321,33 @@ class Stage2Engine:
         def body():
             ops.nchw_to_nhwc(self.s_real, self.d.group_view(self.d.a[0], 0, 1))
             self.outer_step(self.s_z, self.s_e1, self.s_e2, self.s_egp)
-        if not use_graph or getattr(ops, "is_emulator", False) or self.comm is not None:
+        if not use_graph or getattr(ops, "is_emulator", False):
             n0 = ops.launch_count() if hasattr(ops, "launch_count") else 0
             body()
             if hasattr(ops, "launch_count"):
                 self.launches_per_step = ops.launch_count() - n0
+            return
+        if self.comm is not None and self.comm.world > 1:
+            # multi-GPU: graph segments on a private stream, NCCL eager in between (see engine.Stage1Engine.step)
+            from .engine import _SegmentedGraph
+            if getattr(self, "gstream", None) is None:
+                self.gstream = torch.cuda.Stream(device=ops.device)
+            cur = torch.cuda.current_stream(ops.device)
+            self.gstream.wait_stream(cur)
+            with torch.cuda.stream(self.gstream):
+                if self.graph is None:
+                    torch.cuda.synchronize()
+                    n0 = ops.launch_count()
+                    self._seg = _SegmentedGraph(ops)
+                    self._seg.begin()
+                    try:
+                        body()
+                    finally:
+                        self._seg.end()
+                    self.launches_per_step = ops.launch_count() - n0
+                    self.graph = self._seg
+                self.graph.replay()
+            cur.wait_stream(self.gstream)
             return
         if self.graph is None:
             torch.cuda.synchronize()
