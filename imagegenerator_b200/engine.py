@@ -44,6 +44,43 @@ def _conv_out(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
+class SideStream:
+    """Fork/join helper: ``run(fn)`` queues ``fn``'s kernels on a second CUDA stream behind everything already queued
+    on the current one, ``join()`` makes the current stream wait for them.  Used for the parameter-gradient kernels
+    (wgrad, BN gamma/beta, bias sums), which nothing reads before the optimizer step: the data-gradient chain keeps
+    the main stream, and the weight-gradient kernels fill the SMs its tile waves leave idle.  Works under CUDA-graph
+    capture (the fork/join become graph edges).  No-op for the CPU emulator or with SG_NO_SIDE_STREAM=1."""
+
+    def __init__(self, ops):
+        self.ops = ops
+        self.enabled = (not getattr(ops, "is_emulator", False)) and os.environ.get("SG_NO_SIDE_STREAM") != "1"
+        self.stream, self.pending = None, False
+
+    def run(self, fn):
+        if not self.enabled:
+            fn()
+            return
+        dev = self.ops.device
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.pending = True
+
+    def join(self):
+        if self.enabled and self.pending:
+            torch.cuda.current_stream(self.ops.device).wait_stream(self.stream)
+            self.pending = False
+
+
+def _side_run(side, fn):
+    if side is None:
+        fn()
+    else:
+        side.run(fn)
+
+
 class _LayerRT:
     """One conv operator (Conv2d orientation: ``co`` x ``ci`` x k x k weight) + optional BN."""
 
@@ -172,22 +209,29 @@ class GenRT:
             x = self.a[i]
         return self.out
 
-    def backward(self, dout):
-        """dout: d loss / d out (T, NHWC).  Accumulates parameter grads, leaves d/d cg in self.dcg."""
+    def backward(self, dout, side=None):
+        """dout: d loss / d out (T, NHWC).  Accumulates parameter grads, leaves d/d cg in self.dcg.  ``side``: optional
+        SideStream for the parameter-gradient kernels (join before the optimizer step)."""
         ops = self.ops
         last = self.layers[-1]
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
-        ops.colsum(self.dpre, last.conv.bias.grad)
-        ops.conv_wgrad(self.dpre, self.a[-1], last.conv.weight.grad, last.k, last.s, last.p)
+
+        def pgrad_last():
+            ops.colsum(self.dpre, last.conv.bias.grad)
+            ops.conv_wgrad(self.dpre, self.a[-1], last.conv.weight.grad, last.k, last.s, last.p)
+        _side_run(side, pgrad_last)
         ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
             ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU)
             ops.bn_bwd_apply(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i],
                              self.dy[i], 1, ACT_RELU)
-            ops.bn_param_grad(self.sums[i], bn.weight.grad, bn.bias.grad)
             x_in = self.a[i - 1] if i > 0 else self.cg
-            ops.conv_wgrad(self.dy[i], x_in, L.conv.weight.grad, L.k, L.s, L.p)
+
+            def pgrad(i=i, L=L, bn=bn, x_in=x_in):
+                ops.bn_param_grad(self.sums[i], bn.weight.grad, bn.bias.grad)
+                ops.conv_wgrad(self.dy[i], x_in, L.conv.weight.grad, L.k, L.s, L.p)
+            _side_run(side, pgrad)
             ops.conv_fprop(self.dy[i], L.pf, None, self.da[i - 1] if i > 0 else self.dcg, L.k, L.s, L.p)
         return self.dcg
 
@@ -326,7 +370,7 @@ class CriticRT:
         ops.unpatchify(col, None, dx, L0.k, L0.s, L0.p)
 
     def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, on_layer_done=None, head_reduce=True,
-                 input_grad_from=None):
+                 input_grad_from=None, side=None):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
         d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).
         ``on_layer_done(l)`` is called once the parameter gradients of conv layer l are final."""
@@ -344,8 +388,10 @@ class CriticRT:
             ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
                              inject=self.gy[l] if inject else None, inject_group=2 - g0)
             if param_grads:
-                ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
-                ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p)
+                def pgrad(l=l, L=L, bn=bn, sums=sums, dy=dy):
+                    ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
+                    ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p)
+                _side_run(side, pgrad)
                 if on_layer_done is not None:
                     on_layer_done(l)
             ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
@@ -353,8 +399,10 @@ class CriticRT:
         dy0 = gv(self.dy[0])
         ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU)
         if param_grads:
-            ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
-            ops.colsum(dy0, L0.conv.bias.grad)
+            def pgrad0():
+                ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
+                ops.colsum(dy0, L0.conv.bias.grad)
+            _side_run(side, pgrad0)
         if need_input_grad:
             # only for the groups [input_grad_from, g0+ng): the real images need no gradient
             gi = g0 if input_grad_from is None else input_grad_from
@@ -395,7 +443,7 @@ class CriticRT:
         self.input_grad(self.gdy[0], self.g)
         ops.sample_sqnorm(self.g, self.sq)
 
-    def gp_second_order(self, coef):
+    def gp_second_order(self, coef, side=None):
         """Backward of coef/2 * sum_b (||g_b||-1)^2 through the first-order graph: parameter grads
         via wgrad / gamma / head, and gy[l] = d/d y_l for the plain backward to pick up."""
         ops, nl = self.ops, self.nl
@@ -404,12 +452,12 @@ class CriticRT:
         L0 = self.layers[0]
         ops.patchify(self.v0, self.Pv, L0.k, L0.s, L0.p)
         ops.conv_fprop(self.Pv, self.pf0, None, self.v[0], 1, 1, 0)
-        ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
+        _side_run(side, lambda: ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0))
         ops.act_bwd(self.v[0], i2(self.a[1]), self.w[1], ACT_LRELU)
         for l in range(1, nl):
             L, bn = self.layers[l], self.layers[l].bn
             ops.conv_fprop(self.w[l], L.pf, None, self.v[l], L.k, L.s, L.p)
-            ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p)
+            _side_run(side, lambda l=l, L=L: ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p))
             mr = self.mr[l][2:3]
             ops.gp_bn_reduce(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.tsums[l], ACT_LRELU)
             ops.gp_bn_apply(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
@@ -475,6 +523,7 @@ class Stage1Engine:
         for fp in (self.d.fp, self.g.fp, self.ca.fp):
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)       # [loss_critic, gp, lossG, kl]
+        self.side = SideStream(ops)
         self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
         self.comm = comm                             # comm.DistComm or None
         self.world = world_size
@@ -504,6 +553,7 @@ class Stage1Engine:
     def optimizer_step(self, fp, already_reduced=0):
         """xm.optimizer_step: average gradients over replicas, then Adam.  ``already_reduced`` = offset
         from which the flat buffer has been handed to the communicator by the backward pass."""
+        self.side.join()
         if self.comm is not None:
             self._comm_allreduce(fp.grad[:already_reduced] if already_reduced > 0 else fp.grad)
             self._comm_wait()
@@ -554,19 +604,20 @@ class Stage1Engine:
         ops.zero(d.dA); ops.zero(d.dBv)
         d.gp_first_order()                                       # utils.py:15-24
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])   # :140-144
-        d.gp_second_order(2.0 * LAMBDA_GP / B)
+        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
         # head/text gradients first (dA is complete once the plain backward has added its head term), so
         # that the tail of the flat gradient buffer can go to NCCL while the trunk backward still runs
         ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA)
-        d.text_backward(d.coef_text, 2 * B, 0.0, True, None)
+        self.side.run(lambda: d.text_backward(d.coef_text, 2 * B, 0.0, True, None))
         tail = [0]
 
         def bucket(l):
             if self.comm is not None and l == d.nl - 1 and self.early_bucket:
+                self.side.join()
                 self._comm_allreduce(d.fp.grad[self.d_tail_off:])
                 tail[0] = self.d_tail_off
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
-                   on_layer_done=bucket, head_reduce=False)
+                   on_layer_done=bucket, head_reduce=False, side=self.side)
         self.optimizer_step(d.fp, already_reduced=tail[0])       # :149
         d.refresh_weights()
 
@@ -578,7 +629,7 @@ class Stage1Engine:
         ops.zero(self.g.fp.grad); ops.zero(self.ca.fp.grad)      # :161-164
         d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
         d.text_backward(d.coef_gen, B, -1.0, False, d.dtem)      # d lossG/d tem through the critic head
-        self.g.backward(d.group_view(d.dx, 1, 1))
+        self.g.backward(d.group_view(d.dx, 1, 1), side=self.side)
         self.ca.backward(self.g.dcg, 1.0, d.dtem, True)
         self.optimizer_step(self.g.fp)                           # :166
         self.optimizer_step(self.ca.fp)                          # :172

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 
 from .engine import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, LAMBDA_GP, N_CRITIC, Z_DIM, CART, CriticRT, GenRT,
-                     _LayerRT, _conv_out, default_ops)
+                     SideStream, _LayerRT, _conv_out, _side_run, default_ops)
 from .layers import FlatParams
 
 
@@ -52,11 +52,11 @@ def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=Non
     ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
 
-def _bn_backward(ops, bn, buf, da, a_out, act):
+def _bn_backward(ops, bn, buf, da, a_out, act, side=None):
     """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads."""
     ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act)
     ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act)
-    ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad)
+    _side_run(side, lambda: ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad))
     return buf.dy
 
 
@@ -153,44 +153,52 @@ class Gen2RT:
         ops.unpatchify(self.colf, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
         return self.out
 
-    def backward(self, dout):
-        """Accumulates parameter gradients; leaves d/d c_hat in self.dc_hat (fp32)."""
+    def backward(self, dout, side=None):
+        """Accumulates parameter gradients; leaves d/d c_hat in self.dc_hat (fp32).  ``side``: optional SideStream for
+        the parameter-gradient kernels (the caller joins before the optimizer step)."""
         ops = self.ops
+        sr = lambda fn: _side_run(side, fn)
         L = self.up3
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
-        ops.colsum(self.dpre, L.conv.bias.grad)
         ops.patchify(self.dpre, self.Pd, L.k, L.s, L.p)
-        ops.conv_wgrad(self.Pd, self.ub[2].a, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
+
+        def pgrad_up3(L=L):
+            ops.colsum(self.dpre, L.conv.bias.grad)
+            ops.conv_wgrad(self.Pd, self.ub[2].a, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
+        sr(pgrad_up3)
         ops.conv_fprop(self.Pd, self.pf_up3, None, self.ub[2].da, 1, 1, 0)
         for i in range(2, -1, -1):
             L, b = self.ups[i], self.ub[i]
-            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU)
+            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side)
             x_in = self.ub[i - 1].a if i > 0 else self.X[4]
-            ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p)
+            sr(lambda L=L, dy=dy, x_in=x_in: ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p))
             ops.conv_fprop(dy, L.pf, None, self.ub[i - 1].da if i > 0 else self.dX[4], L.k, L.s, L.p)
         for r in range(3, -1, -1):
             l1, l2, l3 = self.res[r]
             b1, b2, b3 = self.rb[r]
-            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU)
+            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
-            self._wgrad(l3, b2.a, dy3)
+            sr(lambda l3=l3, b2=b2, dy3=dy3: self._wgrad(l3, b2.a, dy3))
             ops.conv_dgrad(dy3, l3.pd, None, b2.da, 3, 1, 1)
-            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU)
-            self._wgrad(l2, b1.a, dy2)
+            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side)
+            sr(lambda l2=l2, b1=b1, dy2=dy2: self._wgrad(l2, b1.a, dy2))
             ops.conv_dgrad(dy2, l2.pd, None, b1.da, 3, 1, 1)
-            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU)
-            self._wgrad(l1, self.X[r], dy1)
+            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side)
+            sr(lambda l1=l1, r=r, dy1=dy1: self._wgrad(l1, self.X[r], dy1))
             ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
             ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)
         ops.split_rep_bwd(self.dX[0], self.b2.da, self.dc_hat)
         L = self.ds2
-        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU)
-        ops.conv_wgrad(self.a1, dy2, L.conv.weight.grad, L.k, L.s, L.p)
+        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU, side)
+        sr(lambda L=L, dy2=dy2: ops.conv_wgrad(self.a1, dy2, L.conv.weight.grad, L.k, L.s, L.p))
         ops.conv_dgrad(dy2, L.pd, None, self.da1, L.k, L.s, L.p)
         L = self.ds0
         ops.act_bwd(self.da1, self.a1, self.dy0, ACT_LRELU)
-        ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
-        ops.colsum(self.dy0, L.conv.bias.grad)
+
+        def pgrad_ds0(L=L):
+            ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
+            ops.colsum(self.dy0, L.conv.bias.grad)
+        sr(pgrad_ds0)
         return self.dc_hat
 
 
@@ -210,6 +218,7 @@ class Stage2Engine:
         for fp in (self.d.fp, self.g2.fp, self.ca2.fp):
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)
+        self.side = SideStream(ops)
         self.comm = comm
         self.one_minus_eps = ops.empty((B,), ops.f32)
         self.dcg2 = ops.zeros((B, 1, 1, ca2.c_dim), ops.f32)
@@ -226,6 +235,10 @@ class Stage2Engine:
         self.g2.refresh_weights()
 
     def sync_grads(self):
+        self.side.join()
+        self._sync_grads()
+
+    def _sync_grads(self):
         """Make every ``.grad`` current (the residual-block weight gradients accumulate in channels-last side
         buffers during the step and are folded in here; ``optimizer_step`` does it for you)."""
         self.g2.fold_grads()
@@ -233,6 +246,7 @@ class Stage2Engine:
     def optimizer_step(self, fp):
         """xm.optimizer_step (stage_2_train_fn.py:155,164,167): gradient mean over replicas, then Adam.  Under
         multi-GPU graph capture the NCCL call is issued eagerly between two graph segments (engine._SegmentedGraph)."""
+        self.side.join()
         if fp is self.g2.fp:
             self.g2.fold_grads()
         if self.comm is not None:
@@ -260,7 +274,7 @@ class Stage2Engine:
     def _generator_backward(self, dfake, kl_scale):
         """Back-propagate d loss / d fake_256 into G2 and CA2 (accumulating)."""
         ops = self.ops
-        dc = self.g2.backward(dfake)                                # fp32 [B,128]
+        dc = self.g2.backward(dfake, side=self.side)                # fp32 [B,128]
         self.ca2.backward_from_dc(dc, kl_scale)
 
     def critic_iteration(self, z, eps_ca1, eps_ca2, eps_gp):
@@ -273,10 +287,10 @@ class Stage2Engine:
         ops.zero(d.dA); ops.zero(d.dBv)
         d.gp_first_order()
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])     # :148-152
-        d.gp_second_order(2.0 * LAMBDA_GP / B)
+        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=True,      # :154
-                   input_grad_from=1)                               # d/d real images is never used
-        d.text_backward(d.coef_text, 2 * B, 0.0, True, None)
+                   input_grad_from=1, side=self.side)               # d/d real images is never used
+        self.side.run(lambda: d.text_backward(d.coef_text, 2 * B, 0.0, True, None))
         # d loss_critic / d fake_256 = d/d(fake group) + (1 - eps) * d/d(interpolated group)  (utils.py:11, not detached)
         ops.affine_f32(eps_gp, -1.0, 1.0, self.one_minus_eps)
         dfake = d.group_view(d.dx, 1, 1)
