@@ -524,6 +524,8 @@ class Stage1Engine:
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)       # [loss_critic, gp, lossG, kl]
         self.side = SideStream(ops)
+        self.gen_side = SideStream(ops)               # next iteration's generator forward (critic_iteration)
+        self._fake_ready = False
         self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
         self.comm = comm                             # comm.DistComm or None
         self.world = world_size
@@ -575,6 +577,7 @@ class Stage1Engine:
     def _comm_allreduce(self, t):
         seg = getattr(self, "_seg", None)
         if seg is not None and seg.capturing:
+            self.gen_side.join()                                # a graph segment must end with every fork joined
             seg.cut(lambda: self.comm.allreduce_async(t))       # eager NCCL between two graph segments
         else:
             self.comm.allreduce_async(t)
@@ -592,14 +595,27 @@ class Stage1Engine:
         self.ops.nchw_to_nhwc(real_nchw, d.group_view(d.a[0], 0, 1))
         d.set_text(tem, tem_mis)
 
-    def critic_iteration(self, z, eps_ca, eps_gp):
-        ops, d, B = self.ops, self.d, self.B
-        tem = d.tem_all[:B]
-        self.ca.forward(tem, eps_ca, z, cg=self.g.cg)           # stage_1_train_fn.py:120-122
+    def _generate(self, z, eps_ca):
+        self.ca.forward(self.d.tem_all[:self.B], eps_ca, z, cg=self.g.cg)   # stage_1_train_fn.py:120-122
         self.g.forward(training=True)                            # :123 -> critic group 1
+
+    def critic_iteration(self, z, eps_ca, eps_gp, next_noise=None):
+        """One critic update (stage_1_train_fn.py:120-149).  ``next_noise = (z, eps_ca)`` of the FOLLOWING iteration,
+        if given, lets its fake batch be generated on a second stream while this iteration's gradient penalty and
+        backward run: the generator's weights do not change between critic updates, and once the critic forward has
+        consumed the image buffer nothing reads it until the next iteration."""
+        ops, d, B = self.ops, self.d, self.B
+        if self._fake_ready:
+            self.gen_side.join()
+            self._fake_ready = False
+        else:
+            self._generate(z, eps_ca)
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True)    # :125-132 + utils.py:13
+        if next_noise is not None and self.gen_side.enabled:
+            self.gen_side.run(lambda: self._generate(*next_noise))
+            self._fake_ready = True
         ops.zero(d.fp.grad)                                      # :146
         ops.zero(d.dA); ops.zero(d.dBv)
         d.gp_first_order()                                       # utils.py:15-24
@@ -638,7 +654,8 @@ class Stage1Engine:
     def outer_step(self, z, eps_ca, eps_gp):
         """z [5,B,100], eps_ca [5,B,128], eps_gp [5,B] (fp32, device)."""
         for it in range(N_CRITIC):
-            self.critic_iteration(z[it], eps_ca[it], eps_gp[it])
+            nxt = (z[it + 1], eps_ca[it + 1]) if it + 1 < N_CRITIC else None
+            self.critic_iteration(z[it], eps_ca[it], eps_gp[it], next_noise=nxt)
         self.generator_step()
 
     # -- whole step behind static buffers, replayed as one CUDA graph
