@@ -164,11 +164,13 @@ bn_act8_kernel(const T* __restrict__ y, const float* __restrict__ mr, const floa
     }
 }
 
-// ---- sums[g][c] += (sum dz, sum dz*xhat), dz = da * act'(a_out)
-template <typename T>
+// ---- sums[g][c] += (sum dz, sum dz*xhat), dz = da * act'(a_out).  HAS_A = false: the activation output is not read;
+// its sign is recomputed from y (a = act(gamma*xhat + beta) has the sign of its argument), one tensor less to stream
+template <typename T, bool HAS_A>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
-                      const float* __restrict__ mr, double* __restrict__ sums, Chunking k, float slope) {
+                      const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      double* __restrict__ sums, Chunking k, float slope) {
     extern __shared__ float sacc[];                 // [touched groups][C][2]
     const int C = k.CV * 8;
     const int64_t begin = (int64_t)blockIdx.x * k.chunk;
@@ -183,12 +185,13 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
         const int c0 = ((int)threadIdx.x % k.CV) * 8;
         int g = (int)(i / k.gvec);
         int64_t next = (int64_t)(g + 1) * k.gvec;
-        float m[8], r[8], s1[8], s2[8];
+        float m[8], r[8], s1[8], s2[8], rg[HAS_A ? 1 : 8], bt[HAS_A ? 1 : 8];
         auto load = [&](int gg) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float* q = mr + ((int64_t)gg * C + c0 + j) * 2;
                 m[j] = q[0]; r[j] = q[1]; s1[j] = 0.f; s2[j] = 0.f;
+                if (!HAS_A) { rg[j] = q[1] * gamma[c0 + j]; bt[j] = beta[c0 + j]; }
             }
         };
         auto flush = [&](int gg) {
@@ -201,7 +204,8 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
         auto one = [&](const V8& d, const V8& a, const V8& yy) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float dz = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+                const float sgn = HAS_A ? a.v[j] : (yy.v[j] - m[j]) * rg[HAS_A ? 0 : j] + bt[HAS_A ? 0 : j];
+                float dz = sgn > 0.f ? d.v[j] : slope * d.v[j];
                 s1[j] += dz;
                 s2[j] += dz * ((yy.v[j] - m[j]) * r[j]);
             }
@@ -214,17 +218,22 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
             }
             const int64_t lim = end < next ? end : next;
             if (i + (int64_t)(U - 1) * k.active < lim) {
-                Raw8<T> rd[U], ra[U], ry[U];
+                Raw8<T> rd[U], ra[HAS_A ? U : 1], ry[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int64_t at = (i + (int64_t)u * k.active) * 8;
-                    rd[u] = ldraw(da + at); ra[u] = ldraw(a_out + at); ry[u] = ldraw(y + at);
+                    rd[u] = ldraw(da + at); ry[u] = ldraw(y + at);
+                    if (HAS_A) ra[u] = ldraw(a_out + at);
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) one(unpack(rd[u]), unpack(ra[u]), unpack(ry[u]));
+                for (int u = 0; u < U; ++u) {
+                    const V8 yy = unpack(ry[u]);
+                    one(unpack(rd[u]), HAS_A ? unpack(ra[HAS_A ? u : 0]) : yy, yy);
+                }
                 i += (int64_t)U * k.active;
             } else {
-                one(unpack(ldraw(da + i * 8)), unpack(ldraw(a_out + i * 8)), unpack(ldraw(y + i * 8)));
+                const V8 yy = unpack(ldraw(y + i * 8));
+                one(unpack(ldraw(da + i * 8)), HAS_A ? unpack(ldraw(a_out + i * 8)) : yy, yy);
                 i += k.active;
             }
         }
@@ -235,12 +244,12 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
 }
 
 // ---- dy = gamma*rstd/n * (n dz - S1 - xhat S2) [+ inject on one group]
-template <typename T>
+template <typename T, bool HAS_A>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
-                     const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
-                     const T* __restrict__ inject, int inject_group, T* __restrict__ dy, Chunking k, float slope,
-                     float n) {
+                     const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const double* __restrict__ sums, const T* __restrict__ inject, int inject_group, T* __restrict__ dy,
+                     Chunking k, float slope, float n) {
     if ((int)threadIdx.x >= k.active) return;
     int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
     int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
@@ -249,7 +258,7 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
     const int c0 = ((int)threadIdx.x % k.CV) * 8, C = k.CV * 8;
     int g = (int)(i / k.gvec);
     int64_t next = (int64_t)(g + 1) * k.gvec;
-    float m[8], r[8], gr[8], c1[8], c2[8];
+    float m[8], r[8], gr[8], c1[8], c2[8], rg[HAS_A ? 1 : 8], bt[HAS_A ? 1 : 8];
     auto load = [&](int gg) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -258,6 +267,7 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
             m[j] = q[0]; r[j] = q[1];
             float coef = gamma[c0 + j] * q[1] / n;
             gr[j] = coef * n; c1[j] = coef * (float)s[0]; c2[j] = coef * (float)s[1];
+            if (!HAS_A) { rg[j] = q[1] * gamma[c0 + j]; bt[j] = beta[c0 + j]; }
         }
     };
     load(g);
@@ -266,7 +276,8 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
         V8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float dz = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+            const float sgn = HAS_A ? a.v[j] : (yy.v[j] - m[j]) * rg[HAS_A ? 0 : j] + bt[HAS_A ? 0 : j];
+            float dz = sgn > 0.f ? d.v[j] : slope * d.v[j];
             float xh = (yy.v[j] - m[j]) * r[j];
             o.v[j] = gr[j] * dz - c1[j] - xh * c2[j];
         }
@@ -284,17 +295,22 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
         }
         const int64_t lim = end < next ? end : next;
         if (i + (int64_t)(U - 1) * k.active < lim) {
-            Raw8<T> rd[U], ra[U], ry[U];
+            Raw8<T> rd[U], ra[HAS_A ? U : 1], ry[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t at = (i + (int64_t)u * k.active) * 8;
-                rd[u] = ldraw(da + at); ra[u] = ldraw(a_out + at); ry[u] = ldraw(y + at);
+                rd[u] = ldraw(da + at); ry[u] = ldraw(y + at);
+                if (HAS_A) ra[u] = ldraw(a_out + at);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) one(unpack(rd[u]), unpack(ra[u]), unpack(ry[u]), i + (int64_t)u * k.active);
+            for (int u = 0; u < U; ++u) {
+                const V8 yy = unpack(ry[u]);
+                one(unpack(rd[u]), HAS_A ? unpack(ra[HAS_A ? u : 0]) : yy, yy, i + (int64_t)u * k.active);
+            }
             i += (int64_t)U * k.active;
         } else {
-            one(unpack(ldraw(da + i * 8)), unpack(ldraw(a_out + i * 8)), unpack(ldraw(y + i * 8)), i);
+            const V8 yy = unpack(ldraw(y + i * 8));
+            one(unpack(ldraw(da + i * 8)), HAS_A ? unpack(ldraw(a_out + i * 8)) : yy, yy, i);
             i += k.active;
         }
     }
@@ -327,24 +343,33 @@ int bn_act8(const void* y, const float* mr, const float* gamma, const float* bet
     return check_launch("bn_act8");
 }
 template <typename T>
-int bn_bwd_reduce8(const void* da, const void* a_out, const void* y, const float* mr, double* sums, int64_t rows_per_group,
-                   int C, int groups, int act, cudaStream_t st) {
+int bn_bwd_reduce8(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta,
+                   double* sums, int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {
     Chunking k = make_chunking(rows_per_group, C, groups, 4);
     size_t smem = (size_t)(groups < 2 ? 1 : 2) * C * 2 * sizeof(float);
     if (k.chunk >= k.gvec) smem = (size_t)groups * C * 2 * sizeof(float);   // tiny tensors: a CTA may span every group
-    bn_bwd_reduce8_kernel<T><<<k.blocks, 256, smem, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, sums, k,
-                                                          act_slope(act));
+    if (a_out != nullptr)
+        bn_bwd_reduce8_kernel<T, true><<<k.blocks, 256, smem, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, gamma, beta,
+                                                                    sums, k, act_slope(act));
+    else
+        bn_bwd_reduce8_kernel<T, false><<<k.blocks, 256, smem, st>>>((const T*)da, nullptr, (const T*)y, mr, gamma, beta, sums, k,
+                                                                     act_slope(act));
     g_launches.fetch_add(1);
     return check_launch("bn_bwd_reduce8");
 }
 template <typename T>
-int bn_bwd_apply8(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const double* sums,
-                  const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups, int act,
-                  cudaStream_t st) {
+int bn_bwd_apply8(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta,
+                  const double* sums, const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups,
+                  int act, cudaStream_t st) {
     Chunking k = make_chunking(rows_per_group, C, groups, 8);
-    bn_bwd_apply8_kernel<T><<<k.blocks, 256, 0, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums,
-                                                      (const T*)inject, inject_group, (T*)dy, k, act_slope(act),
-                                                      (float)rows_per_group);
+    if (a_out != nullptr)
+        bn_bwd_apply8_kernel<T, true><<<k.blocks, 256, 0, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, gamma, beta, sums,
+                                                                (const T*)inject, inject_group, (T*)dy, k, act_slope(act),
+                                                                (float)rows_per_group);
+    else
+        bn_bwd_apply8_kernel<T, false><<<k.blocks, 256, 0, st>>>((const T*)da, nullptr, (const T*)y, mr, gamma, beta, sums,
+                                                                 (const T*)inject, inject_group, (T*)dy, k, act_slope(act),
+                                                                 (float)rows_per_group);
     g_launches.fetch_add(1);
     return check_launch("bn_bwd_apply8");
 }
@@ -359,10 +384,10 @@ int act_bwd8(const void* da, const void* a_out, void* out, int64_t n, int act, c
 // explicit instantiations used by elementwise.cu
 template int bn_act8<float>(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
 template int bn_act8<bf16>(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
-template int bn_bwd_reduce8<float>(const void*, const void*, const void*, const float*, double*, int64_t, int, int, int, cudaStream_t);
-template int bn_bwd_reduce8<bf16>(const void*, const void*, const void*, const float*, double*, int64_t, int, int, int, cudaStream_t);
-template int bn_bwd_apply8<float>(const void*, const void*, const void*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
-template int bn_bwd_apply8<bf16>(const void*, const void*, const void*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_reduce8<float>(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_reduce8<bf16>(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_apply8<float>(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_bwd_apply8<bf16>(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
 template int act_bwd8<float>(const void*, const void*, void*, int64_t, int, cudaStream_t);
 template int act_bwd8<bf16>(const void*, const void*, void*, int64_t, int, cudaStream_t);
 

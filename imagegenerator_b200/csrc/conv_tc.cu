@@ -267,9 +267,31 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0
+// relaxed: the producer publishes nothing of its own through this arrival (the TMA's complete_tx carries the data), and the
+// default release.cluster form costs a MEMBAR + ERRBAR per k-block on the producer's critical path (ncu source page)
 __device__ __forceinline__ void mbar_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & PEER_BIT_MASK), "r"(bytes)
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & PEER_BIT_MASK),
+                 "r"(bytes)
                  : "memory");
+}
+// wait with back-off: the epilogue warps wait a whole mainloop for their accumulator; polling flat out they steal issue
+// slots from the MMA-issuing warp that shares their scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
 }
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -674,7 +696,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
             const int ncols = min(P.BN, P.n_total - nt0);          // valid columns of this tile
             const uint32_t ab = ti & 1;
-            mbar_wait(&tfull_bar[ab], (ti >> 1) & 1);
+            mbar_wait_backoff(&tfull_bar[ab], (ti >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride + ((uint32_t)(q * 32) << 16);
             for (int c0 = half * 16; c0 < ncols; c0 += 32) {

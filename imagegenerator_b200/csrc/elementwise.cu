@@ -703,8 +703,8 @@ __global__ void ca_bwd_seed_kernel(const T* dcg, const float* eps, const float* 
 
 // 8-wide kernels of bn_fast.cu (C % 8 == 0)
 template <typename T> int bn_act8(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
-template <typename T> int bn_bwd_reduce8(const void*, const void*, const void*, const float*, double*, int64_t, int, int, int, cudaStream_t);
-template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int bn_bwd_reduce8(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
 
 }  // namespace sg
@@ -913,7 +913,7 @@ int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const flo
     cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
     int e = 0;
     if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
-        SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, a_out, y, mr, sums, rows_per_group, C, groups, act, st));
+        SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, a_out, y, mr, nullptr, nullptr, sums, rows_per_group, C, groups, act, st));
         return e;
     }
     SG_DISPATCH_T(dtype, {
@@ -930,8 +930,8 @@ int sg_bn_bwd_apply(const void* da, const void* a_out, const void* y, const floa
     SG_REQUIRE((rows_per_group * C) % 4 == 0, "bn_bwd_apply: group size must be a multiple of 4 elements");
     int e = 0;
     if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
-        SG_DISPATCH_T(dtype, e = bn_bwd_apply8<T>(da, a_out, y, mr, gamma, sums, inject, inject_group, dy, rows_per_group, C,
-                                                  groups, act, SG_STREAM(stream)));
+        SG_DISPATCH_T(dtype, e = bn_bwd_apply8<T>(da, a_out, y, mr, gamma, nullptr, sums, inject, inject_group, dy, rows_per_group,
+                                                  C, groups, act, SG_STREAM(stream)));
         return e;
     }
     SG_DISPATCH_T(dtype, {
@@ -939,6 +939,27 @@ int sg_bn_bwd_apply(const void* da, const void* a_out, const void* y, const floa
                          (T*)dy, rows_per_group, C, act};
         e = launch_ew4(f, n, SG_STREAM(stream), "bn_bwd_apply");
     });
+    return e;
+}
+
+// the same two kernels without the activation tensor: act'(a) is taken from the sign of gamma*xhat+beta recomputed from
+// y (valid for ReLU / LeakyReLU / none directly behind the BN, i.e. every BN layer except the one closing a residual block)
+int sg_bn_bwd_reduce_y(const void* da, const void* y, const float* mr, const float* gamma, const float* beta, double* sums,
+                       int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream) {
+    SG_REQUIRE(C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH, "bn_bwd_reduce_y: C %% 8 == 0, act in {none, relu, lrelu}");
+    cudaStream_t st = SG_STREAM(stream);
+    cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
+    int e = 0;
+    SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, nullptr, y, mr, gamma, beta, sums, rows_per_group, C, groups, act, st));
+    return e;
+}
+int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const float* gamma, const float* beta, const double* sums,
+                      const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups, int act,
+                      int dtype, void* stream) {
+    SG_REQUIRE(C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH, "bn_bwd_apply_y: C %% 8 == 0, act in {none, relu, lrelu}");
+    int e = 0;
+    SG_DISPATCH_T(dtype, e = bn_bwd_apply8<T>(da, nullptr, y, mr, gamma, beta, sums, inject, inject_group, dy, rows_per_group, C,
+                                              groups, act, SG_STREAM(stream)));
     return e;
 }
 

@@ -223,9 +223,10 @@ class GenRT:
         ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
-            ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU)
+            ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,
+                              gamma=bn.weight.data, beta=bn.bias.data)
             ops.bn_bwd_apply(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i],
-                             self.dy[i], 1, ACT_RELU)
+                             self.dy[i], 1, ACT_RELU, beta=bn.bias.data)
             x_in = self.a[i - 1] if i > 0 else self.cg
 
             def pgrad(i=i, L=L, bn=bn, x_in=x_in):
@@ -384,9 +385,9 @@ class CriticRT:
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
             da, a_out, y, dy = gv(self.da[l + 1]), gv(self.a[l + 1]), gv(self.y[l]), gv(self.dy[l])
-            ops.bn_bwd_reduce(da, a_out, y, mr, sums, ng, ACT_LRELU)
+            ops.bn_bwd_reduce(da, a_out, y, mr, sums, ng, ACT_LRELU, gamma=bn.weight.data, beta=bn.bias.data)
             ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
-                             inject=self.gy[l] if inject else None, inject_group=2 - g0)
+                             inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data)
             if param_grads:
                 def pgrad(l=l, L=L, bn=bn, sums=sums, dy=dy):
                     ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
@@ -434,9 +435,10 @@ class CriticRT:
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr = self.mr[l][2:3]
-            ops.bn_bwd_reduce(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.gsums[l], 1, ACT_LRELU)
+            ops.bn_bwd_reduce(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.gsums[l], 1, ACT_LRELU,
+                              gamma=bn.weight.data, beta=bn.bias.data)
             ops.bn_bwd_apply(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
-                             self.gdy[l], 1, ACT_LRELU)
+                             self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data)
             ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
         L0 = self.layers[0]
         ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)

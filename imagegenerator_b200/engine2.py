@@ -52,10 +52,13 @@ def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=Non
     ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
 
-def _bn_backward(ops, bn, buf, da, a_out, act, side=None):
-    """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads."""
-    ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act)
-    ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act)
+def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True):
+    """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads.  ``from_y``: the activation follows
+    the BN directly, so the kernels take its sign from y and do not stream a_out (False for the layer that closes a
+    residual block, whose ReLU sees bn(y) + identity)."""
+    gb = dict(gamma=bn.weight.data, beta=bn.bias.data) if from_y else {}
+    ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act, **gb)
+    ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act, **({"beta": bn.bias.data} if from_y else {}))
     _side_run(side, lambda: ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad))
     return buf.dy
 
@@ -176,7 +179,7 @@ class Gen2RT:
         for r in range(3, -1, -1):
             l1, l2, l3 = self.res[r]
             b1, b2, b3 = self.rb[r]
-            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side)
+            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
             sr(lambda l3=l3, b2=b2, dy3=dy3: self._wgrad(l3, b2.a, dy3))
             ops.conv_dgrad(dy3, l3.pd, None, b2.da, 3, 1, 1)

@@ -61,6 +61,8 @@ _SIGS = {
     "sg_bn_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
+    "sg_bn_bwd_reduce_y": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "sg_bn_bwd_apply_y": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_param_grad": [_P, _P, _P, _I, _I, _P],
     "sg_act_bwd": [_P, _P, _P, _L, _I, _I, _P],
     "sg_gp_bn_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
@@ -351,15 +353,26 @@ class CudaOps:
         self._ck(self.lib.sg_bn_act(_ptr(y), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(out),
                                     y.numel() // (C * groups), C, groups, act, self._dt_of(y), self._st()))
 
-    def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act):
-        self._c(da, a_out, y, mr, sums)
+    def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act, gamma=None, beta=None):
+        """``gamma``/``beta`` given (BN directly followed by the activation): the activation tensor is not streamed, its
+        sign is recomputed from y."""
+        self._c(da, a_out, y, mr, sums, gamma, beta)
         C = y.shape[-1]
+        if gamma is not None and C % 8 == 0 and act != ACT_TANH:
+            self._ck(self.lib.sg_bn_bwd_reduce_y(_ptr(da), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
+                                                 y.numel() // (C * groups), C, groups, act, self._dt_of(y), self._st()))
+            return
         self._ck(self.lib.sg_bn_bwd_reduce(_ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(sums),
                                            y.numel() // (C * groups), C, groups, act, self._dt_of(y), self._st()))
 
-    def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0):
-        self._c(da, a_out, y, mr, gamma, sums, dy, inject)
+    def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None):
+        self._c(da, a_out, y, mr, gamma, sums, dy, inject, beta)
         C = y.shape[-1]
+        if beta is not None and C % 8 == 0 and act != ACT_TANH:
+            self._ck(self.lib.sg_bn_bwd_apply_y(_ptr(da), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
+                                                _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C, groups,
+                                                act, self._dt_of(y), self._st()))
+            return
         self._ck(self.lib.sg_bn_bwd_apply(_ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(sums),
                                           _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C, groups,
                                           act, self._dt_of(y), self._st()))

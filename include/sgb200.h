@@ -187,6 +187,13 @@ int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const flo
 int sg_bn_bwd_apply(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
                     const double* sums, const void* inject, int inject_group, void* dy,
                     int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+/* sg_bn_bwd_reduce / sg_bn_bwd_apply without the activation tensor: act'(a) comes from the sign of gamma*xhat+beta,
+ * recomputed from y -- one tensor less to stream (C % 8 == 0; ReLU / LeakyReLU / none directly behind the BN) */
+int sg_bn_bwd_reduce_y(const void* da, const void* y, const float* mr, const float* gamma, const float* beta, double* sums,
+                       int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const float* gamma, const float* beta,
+                      const double* sums, const void* inject, int inject_group, void* dy,
+                      int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
 /* dgamma += sum_g S2, dbeta += sum_g S1 */
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream);
 /* out = da * act'(a_out)   (LeakyReLU / ReLU / Tanh backward without BN) */

@@ -203,18 +203,29 @@ class EmuOps:
             z = z + residual.double()
         out.copy_(_act(z, act).to(out.dtype))
 
-    def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act):
-        """sums[G,C,2] (f64) = (S1, S2) = (sum dz, sum dz*xhat), dz = da * act'(.) from a_out."""
+    def _act_sign_from_y(self, y, mr, gamma, beta, groups):
+        """what the *_y kernels use instead of the stored activation: gamma*xhat+beta (same sign as act(...))."""
         C = y.shape[-1]
+        z = self._xhat(y, mr, groups).to(torch.float64) * gamma.double()[None, None, :] + beta.double()[None, None, :]
+        return z.reshape(y.shape)
+
+    def bn_bwd_reduce(self, da, a_out, y, mr, sums, groups, act, gamma=None, beta=None):
+        """sums[G,C,2] (f64) = (S1, S2) = (sum dz, sum dz*xhat), dz = da * act'(.) from a_out -- or, when gamma/beta
+        are given (BN directly followed by the activation), from the sign of gamma*xhat+beta recomputed from y."""
+        C = y.shape[-1]
+        if gamma is not None and C % 8 == 0 and act != ACT_TANH:
+            a_out = self._act_sign_from_y(y, mr, gamma, beta, groups)
         dz = (da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).reshape(groups, -1, C)
         xh = self._xhat(y, mr, groups).to(torch.float64)
         sums[:, :, 0] = dz.sum(1)
         sums[:, :, 1] = (dz * xh).sum(1)
 
-    def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0):
+    def bn_bwd_apply(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None):
         """dy = gamma*rstd/N * (N dz - S1 - xhat S2)  [+ inject on rows of group inject_group]."""
         C = y.shape[-1]
         ft = torch.float64
+        if beta is not None and C % 8 == 0 and act != ACT_TANH:
+            a_out = self._act_sign_from_y(y, mr, gamma, beta, groups)
         dz = (da.to(ft) * _mask(a_out, act).to(ft)).reshape(groups, -1, C)
         n = dz.shape[1]
         xh = self._xhat(y, mr, groups)

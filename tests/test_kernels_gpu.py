@@ -176,6 +176,22 @@ def test_bn_chain(mode, C, rows, G):
 
 
 @pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("C,rows,G,act", [(24, 1024, 1, ACT_RELU), (128, 512, 3, ACT_LRELU), (640, 256, 1, ACT_RELU), (80, 4096, 1, ACT_NONE)])
+def test_bn_backward_without_activation_tensor(mode, C, rows, G, act):
+    """sg_bn_bwd_reduce_y / sg_bn_bwd_apply_y: the activation's sign recomputed from y == the stored activation's."""
+    y = rnd(G * rows, C)
+    mr = torch.stack([rnd(G, C, scale=0.1), torch.rand(G, C) + 0.5], dim=-1)
+    gamma, beta = torch.rand(C) + 0.5, rnd(C, scale=0.3)
+    da = rnd(G * rows, C, seed=3)
+    inj = rnd(rows, C, seed=5)
+    sums0 = torch.zeros(G, C, 2, dtype=torch.float64)
+    ea, ca = run_pair(mode, "bn_bwd_reduce", [T(da), None, T(y), F(mr), D(sums0), G, act], [4],
+                      dict(gamma=F(gamma), beta=F(beta)), tol=dict(rtol=1e-3, atol=1e-4))
+    run_pair(mode, "bn_bwd_apply", [T(da), None, T(y), F(mr), F(gamma), D(ea[4]), T(torch.zeros(G * rows, C)), G, act], [6],
+             dict(inject=T(inj), inject_group=G - 1, beta=F(beta)))
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_bn_eval_mr(mode):
     C = 96
     run_pair(mode, "bn_eval_mr", [F(rnd(C)), F(torch.rand(C) + 0.1), F(torch.zeros(1, C, 2))], [2],
