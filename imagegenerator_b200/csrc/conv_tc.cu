@@ -88,6 +88,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -478,7 +487,7 @@ struct TcpParams {
     int outH, outW;
     int act;
     int stages;
-    int tmem_cols, acc_stride;
+    int tmem_cols, acc_stride, nbuf;      // TMEM columns allocated, columns per accumulator buffer, buffers in the ring
     int m_tiles, n_tiles, total_tiles;   // m_tiles counts CG*128-row cluster tiles
     int imgs_per_group;
     const float* bias;
@@ -486,6 +495,9 @@ struct TcpParams {
     double* stats;        // [groups][n_total][2] or NULL
     float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
     const bf16* residual; // added before the activation (same layout as out) or NULL
+    int full_tiles, split, kb_slice;   // tail-wave K-split: tiles below full_tiles are whole; see next_work()
+    float* ws;            // fp32 partial tiles of the split tail wave
+    int* flags;           // one per (leftover tile, non-owner slice, CTA of the pair)
 };
 
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
@@ -557,13 +569,36 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 
+// Work list of one cluster: whole tiles c, c+C, c+2C, ... below P.full_tiles, then -- when the last round would be
+// only partly full -- ONE K-slice of a leftover tile: the R = total - full leftover tiles are each cut into P.split
+// slices of P.kb_slice k-blocks, slice s of leftover tile t goes to cluster t*split + s.  Slice 0 is the tile's owner:
+// the other slices store their fp32 partial accumulators in a workspace and raise a flag, the owner adds them in its
+// epilogue.  Non-owners never wait, every cluster holds at most one slice, all clusters are co-resident: no deadlock.
+struct Work {
+    int tile, kb0, kb1, slice;
+};
+
+__device__ __forceinline__ bool next_work(const TcpParams& P, int cluster_id, int num_clusters, int nkb, int i, Work* w) {
+    const int t = cluster_id + i * num_clusters;
+    if (t < P.full_tiles) { w->tile = t; w->kb0 = 0; w->kb1 = nkb; w->slice = 0; return true; }
+    // split mode: full_tiles is a multiple of num_clusters (or 0), so every cluster reaches this point at the same i
+    if (P.split > 1 && t - cluster_id == P.full_tiles) {
+        const int lt = cluster_id / P.split, sl = cluster_id - lt * P.split;
+        if (P.full_tiles + lt >= P.total_tiles) return false;
+        w->tile = P.full_tiles + lt; w->slice = sl;
+        w->kb0 = sl * P.kb_slice; w->kb1 = min(nkb, w->kb0 + P.kb_slice);
+        return w->kb0 < w->kb1;
+    }
+    return false;
+}
+
 template <int CG>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcpParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[8], tempty_bar[8];
     __shared__ uint32_t tmem_slot;
-    __shared__ float sstat[2][256][2];
+    __shared__ float sstat[2][256][2];          // statistics staging, double-buffered by tile parity
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -573,10 +608,11 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int b_rows = P.BN / CG;
     const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
     const int tiles_per_phase = P.n_tiles * P.m_tiles;
+    const int nkb_tile = (P.mode == 0 ? P.k * P.k : (P.k / P.s) * (P.k / P.s)) * P.cblocks;   // equal for every phase
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TCP_EPI_WARPS * CG); }
+        for (int i = 0; i < P.nbuf; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TCP_EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (P.stats != nullptr)
@@ -601,38 +637,38 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             int st = 0;
             uint32_t par = 1;                         // parity to wait for on empty[st]: first round passes
-            for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters) {
-                const int phase = tile / tiles_per_phase, r = tile - phase * tiles_per_phase;
+            Work w;
+            for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w); ++wi) {
+                const int phase = w.tile / tiles_per_phase, r = w.tile - phase * tiles_per_phase;
                 const int nt = r / P.m_tiles, mt = r - nt * P.m_tiles;
                 const PhaseGeo g = phase_geo(P, phase);
                 const int m0 = (mt * CG + (int)rank) * 128;
                 const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
                 const int nt0 = nt * P.BN + (int)rank * b_rows;
-                for (int th = 0; th < g.nth; ++th) {
-                    for (int tw = 0; tw < g.ntw; ++tw) {
-                        int ca_w, ca_h, bk;
-                        if (P.mode == 0) {
-                            ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
-                            bk = (th * P.k + tw) * P.Ck;
-                        } else {
-                            ca_w = w0 + g.base_w - tw; ca_h = h0 + g.base_h - th;
-                            bk = ((g.rh + P.s * th) * P.k + (g.rw + P.s * tw)) * P.Ck;
-                        }
-                        for (int cb = 0; cb < P.cblocks; ++cb) {
-                            mbar_wait(&empty_bar[st], par);
-                            uint8_t* sa = smem + (size_t)st * stage_bytes;
-                            if (CG == 2) {
-                                mbar_expect_tx_leader(&full_bar[st], (uint32_t)stage_bytes);
-                                tma2_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
-                                tma2_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
-                            } else {
-                                mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
-                                tma_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
-                                tma_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
-                            }
-                            if (++st == P.stages) { st = 0; par ^= 1; }
-                        }
+                int tap = w.kb0 / P.cblocks, cb = w.kb0 - tap * P.cblocks;
+                int th = tap / g.ntw, tw = tap - th * g.ntw;
+                for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                    int ca_w, ca_h, bk;
+                    if (P.mode == 0) {
+                        ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
+                        bk = (th * P.k + tw) * P.Ck;
+                    } else {
+                        ca_w = w0 + g.base_w - tw; ca_h = h0 + g.base_h - th;
+                        bk = ((g.rh + P.s * th) * P.k + (g.rw + P.s * tw)) * P.Ck;
                     }
+                    mbar_wait(&empty_bar[st], par);
+                    uint8_t* sa = smem + (size_t)st * stage_bytes;
+                    if (CG == 2) {
+                        mbar_expect_tx_leader(&full_bar[st], (uint32_t)stage_bytes);
+                        tma2_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
+                        tma2_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
+                    } else {
+                        mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+                        tma_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
+                        tma_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
+                    }
+                    if (++st == P.stages) { st = 0; par ^= 1; }
+                    if (++cb == P.cblocks) { cb = 0; if (++tw == g.ntw) { tw = 0; ++th; } }
                 }
             }
         }
@@ -642,16 +678,13 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)((128 * CG) >> 4) << 24);
             int st = 0;
-            uint32_t par = 0, ti = 0;
-            for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters, ++ti) {
-                const int phase = tile / tiles_per_phase;
-                const PhaseGeo g = phase_geo(P, phase);
-                const int nkb = g.nth * g.ntw * P.cblocks;
-                const uint32_t ab = ti & 1;
-                mbar_wait(&tempty_bar[ab], ((ti >> 1) & 1) ^ 1);
+            uint32_t par = 0, ab = 0, abpar = 1;       // accumulator buffer ring: P.nbuf buffers of acc_stride TMEM columns
+            Work w;
+            for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w); ++wi) {
+                mbar_wait(&tempty_bar[ab], abpar);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = w.kb0; kb < w.kb1; ++kb) {
                     mbar_wait(&full_bar[st], par);
                     tc_fence_after();
                     const uint32_t sa = base + (uint32_t)st * stage_bytes;
@@ -660,13 +693,15 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int k4 = 0; k4 < 4; ++k4) {
                         uint64_t ad = make_kmajor_sw128_desc(sa + k4 * 32);
                         uint64_t bd = make_kmajor_sw128_desc(sb + k4 * 32);
-                        if (CG == 2) tc2_mma_bf16(tacc, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
-                        else tc_mma_bf16(tacc, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        const uint32_t acc = ((kb - w.kb0) | k4) != 0 ? 1u : 0u;
+                        if (CG == 2) tc2_mma_bf16(tacc, ad, bd, idesc, acc);
+                        else tc_mma_bf16(tacc, ad, bd, idesc, acc);
                     }
                     if (CG == 2) tc2_commit_mc(&empty_bar[st]); else tc_commit(&empty_bar[st]);
                     if (++st == P.stages) { st = 0; par ^= 1; }
                 }
                 if (CG == 2) tc2_commit_mc(&tfull_bar[ab]); else tc_commit(&tfull_bar[ab]);
+                if (++ab == (uint32_t)P.nbuf) { ab = 0; abpar ^= 1; }
             }
         }
     } else {
@@ -681,8 +716,11 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int act = P.act;
         const bool has_stats = P.stats != nullptr;
         const int scol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        uint32_t ti = 0;
-        for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters, ++ti) {
+        uint32_t ti = 0, ab = 0, abpar = 0;
+        Work w;
+        for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w);
+             ++wi, ++ti, ab = (ab + 1 == (uint32_t)P.nbuf ? 0 : ab + 1), abpar ^= (ab == 0 ? 1u : 0u)) {
+            const int tile = w.tile;
             const int phase = tile / tiles_per_phase, rr = tile - phase * tiles_per_phase;
             const int nt = rr / P.m_tiles, mt = rr - nt * P.m_tiles;
             const int ph = phase / P.s, pw = phase - ph * P.s;
@@ -695,16 +733,68 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
             bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
             const int ncols = min(P.BN, P.n_total - nt0);          // valid columns of this tile
-            const uint32_t ab = ti & 1;
-            mbar_wait_backoff(&tfull_bar[ab], (ti >> 1) & 1);
+            const uint32_t sb2 = ti & 1;           // statistics staging buffer
+            // K-split bookkeeping: partial tiles of leftover tile lt live at ws[((lt*(split-1) + slice-1)*CG + rank)][128][BN]
+            const bool is_split = tile >= P.full_tiles && P.split > 1;
+            const int lt = tile - P.full_tiles;
+            float* wsrow = nullptr;
+            if (is_split) {
+                const int first = w.slice > 0 ? w.slice - 1 : 0;
+                // layout [partial tile][16-column chunk][row][16]: the 32 lanes of a warp (32 rows) touch 2 KB contiguous
+                wsrow = P.ws + ((int64_t)(lt * (P.split - 1) + first) * CG + rank) * (128 * P.BN) + (int64_t)r * 16;
+            }
+            if (nkb_tile >= 8) mbar_wait_backoff(&tfull_bar[ab], abpar);     // long mainloop: sleep between polls
+            else mbar_wait(&tfull_bar[ab], abpar);                          // short tiles: the sleep would be the latency
             tc_fence_after();
             const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride + ((uint32_t)(q * 32) << 16);
-            for (int c0 = half * 16; c0 < ncols; c0 += 32) {
-                uint32_t v[16];
-                tc_ld16(tacc + (uint32_t)c0, v);
+            if (is_split && w.slice > 0) {
+                // ---- non-owner slice: fp32 partial accumulators to the workspace, then raise the flag
+                for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+                    uint32_t v[16];
+                    tc_ld16(tacc + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<uint4*>(wsrow + c0 * 128)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive_local(&tempty_bar[ab]);
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) {
+                    int* flag = P.flags + (lt * (P.split - 1) + (w.slice - 1)) * CG + (int)rank;
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+                }
+                continue;
+            }
+            if (is_split) {
+                // ---- owner: wait for the other slices of this tile
+                if (et < P.split - 1) {
+                    const int* flag = P.flags + (lt * (P.split - 1) + et) * CG + (int)rank;
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (!v) __nanosleep(64);
+                    } while (!v);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            auto process = [&](const int c0, const uint32_t (&v)[16]) {
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (is_split) {
+                    for (int sl = 0; sl < P.split - 1; ++sl) {
+                        const float4* pp = reinterpret_cast<const float4*>(wsrow + (int64_t)sl * CG * (128 * P.BN) + c0 * 128);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t4 = __ldcg(pp + j);
+                            f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
+                        }
+                    }
+                }
                 if (P.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -714,11 +804,11 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const bf16* rrow = P.residual + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0 + c0;
                     if (vec_ok && c0 + 16 <= ncols) {
                         const uint4 r0 = *reinterpret_cast<const uint4*>(rrow), r1 = *reinterpret_cast<const uint4*>(rrow + 8);
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        const uint32_t rr2[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            f[2 * j] += __uint_as_float(rr[j] << 16);
-                            f[2 * j + 1] += __uint_as_float(rr[j] & 0xffff0000u);
+                            f[2 * j] += __uint_as_float(rr2[j] << 16);
+                            f[2 * j + 1] += __uint_as_float(rr2[j] & 0xffff0000u);
                         }
                     } else {
 #pragma unroll
@@ -749,7 +839,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if (c0 + j < ncols) o32[j] = f[j];
                         }
                     }
-                    continue;
+                    return;
                 }
                 uint32_t pk[8];
 #pragma unroll
@@ -776,9 +866,73 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     warp_colsum16(f, lane);
                     warp_colsum16(sq, lane);
                     if ((lane & 1) == 0) {
-                        atomicAdd(&sstat[ab][c0 + scol][0], f[0]);
-                        atomicAdd(&sstat[ab][c0 + scol][1], sq[0]);
+                        atomicAdd(&sstat[sb2][c0 + scol][0], f[0]);
+                        atomicAdd(&sstat[sb2][c0 + scol][1], sq[0]);
                     }
+                }
+            };
+            // ---- fast path (every BatchNorm'ed conv of the training step): no bias / residual / fp32 output / K-split,
+            // whole 32-column groups.  Straight-line code over 32 columns per iteration -- two independent 16-column
+            // chains for the scheduler to interleave, since only two epilogue warps share an SM sub-partition and the
+            // drain is issue-latency bound -- with the activation and the statistics decided once per tile.
+            const bool plain = P.bias == nullptr && P.residual == nullptr && P.out32 == nullptr && !is_split && vec_ok &&
+                               (ncols & 31) == 0 && P.out != nullptr;
+            if (plain) {
+                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                    uint32_t v[32];
+                    tc_ld16_nowait(tacc + (uint32_t)c0, v);
+                    tc_ld16_nowait(tacc + (uint32_t)c0 + 16, v + 16);
+                    tc_wait_ld();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (act == SG_ACT_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
+                    } else if (act == SG_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    } else if (act == SG_ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = tanh_approx(f[j]);
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    if (n_img < P.n_img) {
+                        uint4* o = reinterpret_cast<uint4*>(orow + c0);
+                        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        o[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+                        o[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                    }
+                    if (has_stats) {
+                        const bool ok = n_img < P.n_img;
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            float a[16], sq[16];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {             // statistics of the STORED (rounded) values
+                                a[2 * j] = ok ? __uint_as_float(pk[h2 * 8 + j] << 16) : 0.f;
+                                a[2 * j + 1] = ok ? __uint_as_float(pk[h2 * 8 + j] & 0xffff0000u) : 0.f;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) sq[j] = a[j] * a[j];
+                            warp_colsum16(a, lane);
+                            warp_colsum16(sq, lane);
+                            if ((lane & 1) == 0) {
+                                atomicAdd(&sstat[sb2][c0 + h2 * 16 + scol][0], a[0]);
+                                atomicAdd(&sstat[sb2][c0 + h2 * 16 + scol][1], sq[0]);
+                            }
+                        }
+                    }
+                }
+            } else
+            {
+                for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+                    uint32_t v[16];
+                    tc_ld16(tacc + (uint32_t)c0, v);
+                    process(c0, v);
                 }
             }
             // accumulator buffer drained: hand it back to the MMA warp (of the leader CTA)
@@ -787,13 +941,18 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive_local(&tempty_bar[ab]);
             }
+            if (is_split) {
+                // every epilogue thread has read its partials: clear the flags for the next launch on this stream
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < P.split - 1) P.flags[(lt * (P.split - 1) + et) * CG + (int)rank] = 0;
+            }
             if (has_stats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int grp = n0 / P.imgs_per_group;
                 for (int i = et; i < ncols * 2; i += 32 * TCP_EPI_WARPS) {
                     const int col = i >> 1, which = i & 1;
-                    atomicAdd(P.stats + ((int64_t)grp * P.n_total + nt0 + col) * 2 + which, (double)sstat[ab][col][which]);
-                    sstat[ab][col][which] = 0.f;
+                    atomicAdd(P.stats + ((int64_t)grp * P.n_total + nt0 + col) * 2 + which, (double)sstat[sb2][col][which]);
+                    sstat[sb2][col][which] = 0.f;
                 }
             }
         }
@@ -1367,6 +1526,66 @@ int g_use_persist = 1;
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
 static bool g_pattr_set = false;
 
+// ---- tail-wave K-split scratch: fp32 partial tiles + flags, one slot per stream that launches split kernels (kernels of
+// one stream are ordered; kernels of different streams may overlap and must not share partials).  Allocated once per
+// device by sg_check_device() -- never inside a launch, so launches stay capturable.
+constexpr int WS_SLOTS = 4;
+constexpr size_t WS_BYTES = (size_t)SG_NUM_SMS * 128 * 256 * sizeof(float);     // >= (split-1)*R*CG partial tiles of 128 x 256
+struct WsSlot {
+    float* ws = nullptr;
+    int* flags = nullptr;
+    cudaStream_t stream = nullptr;
+    bool used = false;
+};
+static WsSlot g_ws[16][WS_SLOTS];
+static std::mutex g_ws_mu;
+int g_use_split = 1;
+
+int tcp_workspace_init() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (int i = 0; i < WS_SLOTS; ++i) {
+        if (g_ws[dev][i].ws) continue;
+        if (cudaMalloc(&g_ws[dev][i].ws, WS_BYTES) != cudaSuccess) { g_ws[dev][i].ws = nullptr; cudaGetLastError(); return 0; }
+        if (cudaMalloc(&g_ws[dev][i].flags, 4 * SG_NUM_SMS * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cudaMemset(g_ws[dev][i].flags, 0, 4 * SG_NUM_SMS * sizeof(int));
+    }
+    return 0;
+}
+static WsSlot* ws_slot_for(cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (int i = 0; i < WS_SLOTS; ++i)
+        if (g_ws[dev][i].used && g_ws[dev][i].stream == st) return g_ws[dev][i].ws ? &g_ws[dev][i] : nullptr;
+    for (int i = 0; i < WS_SLOTS; ++i)
+        if (!g_ws[dev][i].used && g_ws[dev][i].ws) { g_ws[dev][i].used = true; g_ws[dev][i].stream = st; return &g_ws[dev][i]; }
+    return nullptr;
+}
+// slices per leftover tile: as many as there are idle clusters per leftover tile, >= 4 k-blocks each
+// returns S and the estimated duration of the split round in cycles (t_kb: cycles per k-block)
+static int split_factor(long tiles, int units, int nkb, int bn = 256, double t_kb = 600.0, double* t_round = nullptr) {
+    const int R = (int)(tiles % units);
+    double best_t = nkb * t_kb;
+    int best = 1;
+    if (g_use_split && R != 0) {
+        int smax = units / R;
+        if (smax > nkb / 4) smax = nkb / 4;
+        if (smax > 6) smax = 6;
+        // a slice costs its share of the mainloop; a non-owner then drains its accumulator to the workspace (measured
+        // ~5.5 us for 128 x 256 fp32), the owner's drain grows by ~3 us per partial it adds (critic ds3 trace)
+        const double c_store = 10000.0 * bn / 256.0, c_read = 5700.0 * bn / 256.0;
+        for (int S = 2; S <= smax; ++S) {
+            const int kbs = (nkb + S - 1) / S;
+            const double t = kbs * t_kb + c_store + (S - 1) * c_read + 1000.0;
+            if (t < best_t * 0.9) { best_t = t; best = S; }
+        }
+    }
+    if (t_round) *t_round = best_t;
+    return best;
+}
+
 static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out, int* bn_out) {
     double best = 1e30;
     int best_cg = 1, best_bn = 16;
@@ -1385,7 +1604,6 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out
             int m_tiles = (M + 128 * cg - 1) / (128 * cg);
             long tiles = (long)m_tiles * n_tiles * phases;
             int units = SG_NUM_SMS / cg;
-            long rounds = (tiles + units - 1) / units;
             double mma = 2.0 * bn;
             double l2 = (16384.0 + (double)(bn / cg) * 128.0) / 44.0;
             double t_kb = mma > l2 ? mma : l2;
@@ -1393,7 +1611,13 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out
             double epi = 40.0 * bn / 16.0 + 400.0;                  // drain of the last tile, not overlapped
             double t_epi_tile = 40.0 * bn / 16.0 + 100.0;           // epilogue pace per tile
             if (t_epi_tile > t_tile) t_tile = t_epi_tile;
-            double t = rounds * t_tile + epi;
+            // rounds of the persistent tile loop; a partly filled last round may be cut along K over the idle clusters
+            double t_last = 0.0;
+            if (tiles % units) {
+                split_factor(tiles, units, nkb, bn, t_kb, &t_last);
+                t_last += 150.0;
+            }
+            double t = (double)(tiles / units) * t_tile + t_last + epi;
             if (t < best) { best = t; best_cg = cg; best_bn = bn; }
         }
     }
@@ -1431,8 +1655,13 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     P.m_tiles = (M + 128 * cg - 1) / (128 * cg);
     P.total_tiles = P.m_tiles * P.n_tiles * phases;
     P.acc_stride = bn;
+    // accumulator ring in TMEM: 2 buffers for wide tiles, up to 8 for narrow ones -- with short mainloops (thin layers,
+    // 1x1 GEMMs) the MMA warp must be able to run several tiles ahead of the epilogue to hide the barrier round trips
+    P.nbuf = 512 / bn;
+    if (P.nbuf > 8) P.nbuf = 8;
+    if (P.nbuf < 2) P.nbuf = 2;
     P.tmem_cols = 32;
-    while (P.tmem_cols < 2 * bn) P.tmem_cols *= 2;
+    while (P.tmem_cols < P.nbuf * bn) P.tmem_cols *= 2;
     const int stage_bytes = A_STAGE_BYTES + (bn / cg) * 128;
     P.stages = (200 * 1024 - 2048) / stage_bytes;
     if (P.stages > 8) P.stages = 8;
@@ -1451,6 +1680,22 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     }
     int units = SG_NUM_SMS / cg;
     int clusters = P.total_tiles < units ? P.total_tiles : units;
+    P.full_tiles = P.total_tiles; P.split = 1; P.kb_slice = taps * P.cblocks; P.ws = nullptr; P.flags = nullptr;
+    {
+        const int nkb = taps * P.cblocks;
+        const double mma_c = 2.0 * bn, l2_c = (16384.0 + (double)(bn / cg) * 128.0) / 44.0;
+        int S = split_factor(P.total_tiles, units, nkb, bn, mma_c > l2_c ? mma_c : l2_c);
+        WsSlot* slot = S > 1 ? ws_slot_for(st) : nullptr;
+        if (slot != nullptr) {
+            const int F = P.total_tiles / units, R = P.total_tiles % units;
+            P.kb_slice = (nkb + S - 1) / S;
+            S = (nkb + P.kb_slice - 1) / P.kb_slice;
+            if (S > 1 && (size_t)(S - 1) * R * cg * 128 * bn * sizeof(float) <= WS_BYTES) {
+                P.split = S; P.full_tiles = F * units; P.ws = slot->ws; P.flags = slot->flags;
+                clusters = F > 0 ? units : R * S;
+            }
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * cg, 1, 1);
     cfg.blockDim = dim3(TCP_THREADS);
@@ -1660,6 +1905,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "tc2")) { g_use_tc2 = value; return 0; }
     if (name && !strcmp(name, "persist")) { g_use_persist = value; return 0; }
     if (name && !strcmp(name, "wgrad2")) { g_use_wgrad2 = value; return 0; }
+    if (name && !strcmp(name, "split")) { g_use_split = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
     if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
     if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }

@@ -10,6 +10,8 @@ namespace sg {
 std::atomic<long long> g_launches{0};
 static thread_local char g_err[512] = "";
 
+int tcp_workspace_init();
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -729,6 +731,7 @@ int sg_check_device(void) {
         set_error("libsgb200 is built for sm_100a (B200) only; device is sm_%d%d", p.major, p.minor);
         return SG_ERR_NO_DEVICE;
     }
+    sg::tcp_workspace_init();     // the one allocation of the library: scratch for the conv kernel's tail-wave K-split
     return 0;
 }
 

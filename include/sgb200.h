@@ -8,7 +8,8 @@
  * Conventions
  *   - every function returns 0 on success, a cudaError_t (> 0) or SG_ERR_* (< 0) otherwise;
  *     sg_last_error() returns a thread-local message for the last non-zero return.
- *   - all buffers are caller-owned DEVICE pointers; nothing is allocated or freed across the ABI,
+ *   - all buffers are caller-owned DEVICE pointers; nothing is allocated or freed across the ABI (one exception:
+ *     sg_check_device() allocates, once per device, 4 x 19 MB of scratch for the conv kernel's tail-wave K-split),
  *     no host synchronisation happens inside, every call is asynchronous on `stream`
  *     (a cudaStream_t passed as void*) and is CUDA-graph capturable.
  *   - "T" tensors are activations/packed weights in the storage type selected by `dtype`
@@ -51,7 +52,8 @@ int sg_check_device(void);
 int64_t sg_launch_count(void);
 /* tuning switches: "persist" = 1/0 persistent double-buffered conv kernel (default 1); "force_cg" / "force_bn" pin its
  * CTA-group size / tile width (0 = cost model); "tc2" = 1/0 CTA-pair tiles in the non-persistent kernels;
- * "wgrad2" = 1/0 unit-list weight-gradient kernel (default 1) */
+ * "wgrad2" = 1/0 unit-list weight-gradient kernel (default 1); "split" = 1/0 cut a partly filled last tile wave of the
+ * persistent conv kernel along K over the idle SMs (default 1) */
 int sg_set_option(const char* name, int value);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
