@@ -405,10 +405,10 @@ def main():
     for _ in range(W):
         eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
     dbg("warm-up done")
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # before the barrier: NVML start-up on rank 0 must not delay the other ranks' first all-reduce
+    barrier()
     n0 = ops.launch_count()
     evs = []
     t_wall0 = time.perf_counter()
@@ -419,9 +419,12 @@ def main():
         eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
         e1.record()
         evs.append((e0, e1))
+        if os.environ.get("SG_BENCH_SYNC") == "1":
+            e1.synchronize()
     barrier()
     wall = time.perf_counter() - t_wall0
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    dbg("per-step ms: " + " ".join(f"{a.elapsed_time(b):.2f}" for a, b in evs))
     launches = (eng.launches_per_step or 0) * K if use_graph else ops.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
