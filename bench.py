@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+WORKLOAD = ("StackGAN Stage-I 64x64 G+D outer step (5 critic updates w/ WGAN-GP double backward "
+            "+ 1 generator/CA update, Adam), batch 128/GPU")
 F_D1, F_G1 = 0.21037e9, 0.03207e9          # forward FLOPs / image
 # FLOPs this implementation must execute per image and outer step (DESIGN.md "Work per step"):
 # critic iteration = G fwd + 3 trunk fwd (real, fake, interp; the mismatched call reuses real's
@@ -39,80 +41,84 @@ FLOPS_PER_IMG = 5 * (F_G1 + 12 * F_D1) + (2 * F_D1 + 2 * F_G1)
 FLOPS_PER_IMG_REFERENCE_NECESSARY = 77 * F_D1 + 7 * F_G1
 
 
+_SAMPLER_SRC = r"""
+import sys, time, os
+idx = int(sys.argv[1])
+try:
+    import pynvml as n
+    n.nvmlInit()
+    h = n.nvmlDeviceGetHandleByIndex(idx)
+    mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+    while True:
+        try:
+            sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            sm, rs = -1, 0
+        sys.stdout.write("%.6f,%d,%d,%d\n" % (time.time(), sm, mx, rs))
+        sys.stdout.flush()
+        time.sleep(0.02)
+except Exception as e:
+    sys.stdout.write("ERR %r\n" % (e,))
+    sys.stdout.flush()
+"""
+
+
 class ClockSampler:
-    """SM clock / throttle-reason samples DURING the timed region: NVML in a thread (every 20 ms), nvidia-smi as fallback."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region.  A separate process polls NVML every 20 ms from before the
+    warm-up on (a thread in this process starves on the GIL while the main thread enqueues launches flat out); ``stop``
+    keeps the samples whose wall-clock stamps fall inside [mark_begin, mark_end]."""
+    BITS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index, self.stop_flag, self.thread, self.nvml = [], None, index, False, None, None
-        self.max_mhz, self.reason_bits = None, 0
-
-    def _nvml_loop(self):
-        n, h = self.nvml
-        while not self.stop_flag:
-            try:
-                self.rows.append(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
-                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
-            except Exception:
-                pass
-            time.sleep(0.02)
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
 
     def start(self):
+        idx = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
         try:
-            import pynvml as n
-            n.nvmlInit()
-            idx = self.index
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            if vis:
-                try:
-                    idx = int(vis.split(",")[self.index])
-                except Exception:
-                    pass
-            h = n.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
-            self.nvml = (n, h)
-            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
-            self.thread.start()
-            return
-        except Exception:
-            self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        if self.nvml is not None:
-            self.stop_flag = True
-            self.thread.join(timeout=1.0)
-            n = self.nvml[0]
-            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-            busy = sorted(x for x in self.rows if x > 0)
-            return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": sorted(k for k, bit in names.items() if self.reason_bits & bit), "samples": len(self.rows),
-                    "source": "nvml, 20 ms period, timed region"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
-        busy = [x for x in sm if x > 0]
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows), "source": "nvidia-smi -lms 100"}
+        try:
+            out = self.proc.communicate(timeout=2)[0]
+        except Exception:
+            out = ""
+        rows = []
+        for line in out.splitlines():
+            p = line.split(",")
+            if len(p) == 4:
+                try:
+                    rows.append((float(p[0]), int(p[1]), int(p[2]), int(p[3])))
+                except ValueError:
+                    pass
+        t0, t1 = self.t0 or 0.0, self.t1 or 1e30
+        inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02] or rows[-3:]
+        sm = sorted(r[1] for r in inside if r[1] > 0)
+        bits = 0
+        for r in inside:
+            bits |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "reasons": sorted(k for k, b in self.BITS.items() if bits & b), "samples": len(inside),
+                "source": "NVML polled every 20 ms by a side process; samples inside the timed region"}
 
 
 def build_modules(seed=42):
@@ -193,8 +199,9 @@ def run_reference(args):
         "unit": "images/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1),
         "ms_per_step": round(med * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "StackGAN Stage-I 64x64 G+D outer step (5 critic + 1 generator update), CPU sample",
-                   "batch_per_step": B},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": 128, "cpu_sample_batch_per_step": B,
+                   "note": "the reference's own CPU path (torch CPU operators) on a bounded sample of the workload: "
+                           "outer steps at batch 16 instead of 128 (a batch-128 step is ~2.7 s on 16 cores)"},
         "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"oracle (torch-CPU restatement of stage_1_train_fn.py:93-196) B={B} fp32 outer steps, median"},
         "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -386,6 +393,9 @@ def main():
         if os.environ.get("SG_BENCH_DEBUG"):
             print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # a side process, started before the warm-up so that it is polling when the timed region begins
     ok = 1
     if use_graph:
         try:
@@ -405,10 +415,8 @@ def main():
     for _ in range(W):
         eng.step(real, tem, tem_mis, z, eca, egp, use_graph=use_graph)
     dbg("warm-up done")
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()          # before the barrier: NVML start-up on rank 0 must not delay the other ranks' first all-reduce
     barrier()
+    sampler.mark_begin()
     n0 = ops.launch_count()
     evs = []
     t_wall0 = time.perf_counter()
@@ -422,6 +430,7 @@ def main():
         if os.environ.get("SG_BENCH_SYNC") == "1":
             e1.synchronize()
     barrier()
+    sampler.mark_end()
     wall = time.perf_counter() - t_wall0
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / K
     dbg("per-step ms: " + " ".join(f"{a.elapsed_time(b):.2f}" for a, b in evs))
@@ -486,8 +495,7 @@ def main():
             "metric": "stackgan_stage1_train_images_per_sec", "value": round(value, 2), "unit": "images/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
-            "config": {"workload": "StackGAN Stage-I 64x64 G+D outer step (5 critic updates w/ WGAN-GP double backward "
-                                   "+ 1 generator/CA update, Adam), batch 128/GPU",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": use_graph, "grad_allreduce": ("NCCL avg, 2 buckets/critic step on a side stream, "
                                                                     f"{s1_bytes_per_step} B/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",

@@ -334,6 +334,116 @@ act_bwd8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __rest
     }
 }
 
+// ---- gradient-penalty double backward through a train-mode BN (one image group), 8-wide.
+// reduce: tsums[c] += (sum v, sum v*xhat, sum v*dz)
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+gp_bn_reduce8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
+                     const float* __restrict__ mr, double* __restrict__ tsums, Chunking k, float slope) {
+    extern __shared__ float sacc[];                 // [C][3]
+    const int C = k.CV * 8;
+    for (int t = threadIdx.x; t < C * 3; t += 256) sacc[t] = 0.f;
+    __syncthreads();
+    const int64_t begin = (int64_t)blockIdx.x * k.chunk;
+    int64_t end = begin + k.chunk;
+    if (end > k.nvec) end = k.nvec;
+    int64_t i = begin + threadIdx.x;
+    if ((int)threadIdx.x < k.active && i < end) {
+        const int c0 = ((int)threadIdx.x % k.CV) * 8;
+        float m[8], r[8], t1[8], t2[8], t3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m[j] = mr[(c0 + j) * 2]; r[j] = mr[(c0 + j) * 2 + 1]; t1[j] = t2[j] = t3[j] = 0.f; }
+        for (; i < end; i += k.active) {
+            const V8 vv = unpack(ldraw(v + i * 8)), d = unpack(ldraw(da + i * 8)), a = unpack(ldraw(a_out + i * 8)),
+                     yy = unpack(ldraw(y + i * 8));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dz = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+                t1[j] += vv.v[j];
+                t2[j] += vv.v[j] * ((yy.v[j] - m[j]) * r[j]);
+                t3[j] += vv.v[j] * dz;
+            }
+        }
+        float* dst = sacc + c0 * 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 3 * j, t1[j]); atomicAdd(dst + 3 * j + 1, t2[j]); atomicAdd(dst + 3 * j + 2, t3[j]); }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < C * 3; t += 256) atomicAdd(tsums + t, (double)sacc[t]);
+}
+
+// apply: w = u*act', gy = d/dy of the penalty term; the 8 per-channel constants live in shared memory
+//   u = A v - B1 - xhat B2,  G = -(E v + B2 dz),  gy = r (G - K1 - xhat K2)
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+gp_bn_apply8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
+                    const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
+                    const double* __restrict__ tsums, T* __restrict__ w_out, T* __restrict__ gy_out, Chunking k, float slope,
+                    float n) {
+    extern __shared__ float cst[];                  // [8][C]: mean, r, A, B1, B2, E, K1, K2
+    const int C = k.CV * 8;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float mean = mr[c * 2], r = mr[c * 2 + 1];
+        const float S1 = (float)sums[c * 2], S2 = (float)sums[c * 2 + 1];
+        const float T1 = (float)tsums[c * 3], T2 = (float)tsums[c * 3 + 1], T3 = (float)tsums[c * 3 + 2];
+        const float al = gamma[c] * r / n;
+        const float P = al * (n * T3 - S1 * T1 - S2 * T2);
+        const float sG = -al * (S2 * T1 + S1 * T2), sGx = -2.f * al * S2 * T2;
+        cst[c] = mean; cst[C + c] = r; cst[2 * C + c] = al * n; cst[3 * C + c] = al * T1; cst[4 * C + c] = al * T2;
+        cst[5 * C + c] = al * S2; cst[6 * C + c] = sG / n; cst[7 * C + c] = sGx / n + P / n;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= k.active) return;
+    int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
+    int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
+    if (end > k.nvec) end = k.nvec;
+    const int c0 = ((int)threadIdx.x % k.CV) * 8;
+    for (; i < end; i += k.active) {
+        const V8 vv = unpack(ldraw(v + i * 8)), d = unpack(ldraw(da + i * 8)), a = unpack(ldraw(a_out + i * 8)),
+                 yy = unpack(ldraw(y + i * 8));
+        V8 w, gy;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float mk = a.v[j] > 0.f ? 1.f : slope;
+            const float dz = d.v[j] * mk;
+            const float r = cst[C + c];
+            const float xh = (yy.v[j] - cst[c]) * r;
+            const float u = cst[2 * C + c] * vv.v[j] - cst[3 * C + c] - xh * cst[4 * C + c];
+            w.v[j] = u * mk;
+            const float G = -(cst[5 * C + c] * vv.v[j] + cst[4 * C + c] * dz);
+            gy.v[j] = r * (G - cst[6 * C + c] - xh * cst[7 * C + c]);
+        }
+        st8(w_out + i * 8, w);
+        st8(gy_out + i * 8, gy);
+    }
+}
+
+template <typename T>
+int gp_bn_reduce8(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums, int64_t rows,
+                  int C, int act, cudaStream_t st) {
+    Chunking k = make_chunking(rows, C, 1, 4);
+    gp_bn_reduce8_kernel<T><<<k.blocks, 256, (size_t)C * 3 * sizeof(float), st>>>((const T*)v, (const T*)da, (const T*)a_out,
+                                                                                  (const T*)y, mr, tsums, k, act_slope(act));
+    g_launches.fetch_add(1);
+    return check_launch("gp_bn_reduce8");
+}
+template <typename T>
+int gp_bn_apply8(const void* v, const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
+                 const double* sums, const double* tsums, void* w_out, void* gy_out, int64_t rows, int C, int act,
+                 cudaStream_t st) {
+    Chunking k = make_chunking(rows, C, 1, 8);
+    gp_bn_apply8_kernel<T><<<k.blocks, 256, (size_t)C * 8 * sizeof(float), st>>>(
+        (const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, tsums, (T*)w_out, (T*)gy_out, k,
+        act_slope(act), (float)rows);
+    g_launches.fetch_add(1);
+    return check_launch("gp_bn_apply8");
+}
+template int gp_bn_reduce8<float>(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
+template int gp_bn_reduce8<bf16>(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
+template int gp_bn_apply8<float>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
+template int gp_bn_apply8<bf16>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
+
 template <typename T>
 int bn_act8(const void* y, const float* mr, const float* gamma, const float* beta, const void* res, void* out,
             int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {

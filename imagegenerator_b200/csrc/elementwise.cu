@@ -708,6 +708,8 @@ template <typename T> int bn_act8(const void*, const float*, const float*, const
 template <typename T> int bn_bwd_reduce8(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
+template <typename T> int gp_bn_reduce8(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
+template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
 
 }  // namespace sg
 
@@ -990,6 +992,10 @@ int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void
     cudaStream_t st = SG_STREAM(stream);
     cudaMemsetAsync(tsums, 0, (size_t)C * 3 * sizeof(double), st);
     int e = 0;
+    if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
+        SG_DISPATCH_T(dtype, e = gp_bn_reduce8<T>(v, da, a_out, y, mr, tsums, rows, C, act, st));
+        return e;
+    }
     SG_DISPATCH_T(dtype, {
         GpBnReduceF<T> f{(const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, C, act};
         e = launch_rowreduce<3>(f, tsums, rows, C, 1, st, "gp_bn_reduce");
@@ -1001,6 +1007,14 @@ int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void*
                    const float* gamma, const double* sums, const double* tsums, void* w_out, void* gy_out,
                    float* dgamma, int64_t rows, int C, int act, int dtype, void* stream) {
     int e = 0;
+    if (C % 8 == 0 && C <= 1024 && act != SG_ACT_TANH) {
+        SG_DISPATCH_T(dtype, e = gp_bn_apply8<T>(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, rows, C, act,
+                                                 SG_STREAM(stream)));
+        if (e) return e;
+        gp_bn_dgamma_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(mr, sums, tsums, dgamma, (double)rows, C);
+        SG_LAUNCHED("gp_bn_dgamma");
+        return 0;
+    }
     SG_DISPATCH_T(dtype, {
         GpBnApplyF<T> f{(const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, tsums,
                         (T*)w_out, (T*)gy_out, rows, C, act};
