@@ -1122,6 +1122,27 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
 //   * PIX = 32-pixel k-blocks: a stage is 8 KB of dy + 4 KB per unit = 40 KB -> 5 stages in flight
 //     (the 64-pixel version had 2), which is what hides the latency of ten TMA loads per stage;
 //   * split-K sized so that tiles x splits fills the 148 SMs in whole waves.
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 struct TcW2Params {
     int Mpix, Ho, Wo;
     int Co, Ci, kk, k, s, p;
@@ -1133,7 +1154,12 @@ struct TcW2Params {
     int dw_cl;                 // 0: dw[Co][Ci][kk] (PyTorch), 1: dw[Co][kk][Ci] (channels-last accumulation buffer)
 };
 
-template <int PIX>
+// MC = true: clusters of two CTAs along the co-tile axis (same units, same pixel range, different 128 output channels).
+// The x tiles are the same for both, so each CTA fetches every second unit and TMA-multicasts it into both CTAs' shared
+// memory: x is 80 % of a stage, so the L2 -> SM operand traffic per CTA drops from 40 KB to 24 KB per k-block.  A stage
+// may be refilled once BOTH CTAs' MMAs have retired it (empty barriers count 2, commits are multicast).  When the number
+// of co tiles is odd the last cluster's second CTA owns no channels: it only keeps the barrier protocol going.
+template <int PIX, bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcW2Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -1152,9 +1178,11 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     const int stage_bytes = A_BYTES + P.nun_max * B_BYTES;
     const int kb0 = blockIdx.z * P.kb_per_split;
     const int nkb = min(P.kb_per_split, P.total_kb - kb0);
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    const bool has_rows = co0 < P.Co;                // false only for the padding CTA of an odd co-tile count (MC)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], MC ? 2 : 1); }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1164,7 +1192,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
@@ -1184,15 +1212,20 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             for (int i = 0; i < nkb; ++i) {
                 if (lane == 0) {
                     mbar_wait(&empty_bar[st], par);
-                    mbar_expect_tx(&full_bar[st], (uint32_t)(A_BYTES + nun * B_BYTES));
+                    mbar_expect_tx(&full_bar[st], (uint32_t)((has_rows ? A_BYTES : 0) + nun * B_BYTES));
                 }
                 __syncwarp();
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
-                if (lane < nun)
-                    tma_load_4d(&tmX, &full_bar[st], sa + A_BYTES + lane * B_BYTES, uc, ow0 * P.s - P.p + ukw,
-                                oh0 * P.s - P.p + ukh, n0);
-                else if (lane < nun + 2)
+                if (lane < nun) {
+                    if (!MC)
+                        tma_load_4d(&tmX, &full_bar[st], sa + A_BYTES + lane * B_BYTES, uc, ow0 * P.s - P.p + ukw,
+                                    oh0 * P.s - P.p + ukh, n0);
+                    else if ((lane & 1) == (int)rank)            // every second unit, delivered to both CTAs
+                        tma_load_4d_mc(&tmX, &full_bar[st], sa + A_BYTES + lane * B_BYTES, uc, ow0 * P.s - P.p + ukw,
+                                       oh0 * P.s - P.p + ukh, n0, (uint16_t)3);
+                } else if (lane < nun + 2 && has_rows) {
                     tma_load_2d(&tmDy, &full_bar[st], sa + (lane - nun) * (PIX * 128), co0 + (lane - nun) * 64, pix0);
+                }
                 if (++st == P.stages) { st = 0; par ^= 1; }
                 // advance the pixel block (blocks never straddle images: Ho*Wo % PIX == 0 or PIX % (Ho*Wo) == 0)
                 pix0 += PIX;
@@ -1218,6 +1251,13 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(&full_bar[st], par);
                     tc_fence_after();
+                    if (MC && !has_rows) {
+                        // padding CTA: nothing to multiply, but both CTAs must release the stage
+                        mbar_arrive_cta(&empty_bar[st], 0);
+                        mbar_arrive_cta(&empty_bar[st], 1);
+                        if (++st == P.stages) { st = 0; par ^= 1; }
+                        continue;
+                    }
                     const uint32_t sa = base + (uint32_t)st * stage_bytes;
                     const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -1230,12 +1270,12 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
                             tc_mma_bf16(tmem_base + 256, ad, b1, idesc_hi, (i | k16) != 0 ? 1u : 0u);
                         }
                     }
-                    tc_commit(&empty_bar[st]);
+                    if (MC) tc_commit_mc(&empty_bar[st], (uint16_t)3); else tc_commit(&empty_bar[st]);
                     if (++st == P.stages) { st = 0; par ^= 1; }
                 }
-                tc_commit(&accum_bar);
+                if (!MC || has_rows) tc_commit(&accum_bar);
             }
-        } else {
+        } else if (!MC || has_rows) {
             const int q = warp & 3;
             const int co = co0 + q * 32 + lane;
             mbar_wait(&accum_bar, 0);
@@ -1326,7 +1366,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();      // MC: no CTA may exit while its peer can still multicast into it
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -1810,6 +1850,7 @@ static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtens
 }
 
 int g_use_wgrad2 = 1;
+int g_use_wgrad_mc = 1;
 
 template <int PIX>
 static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
@@ -1824,7 +1865,10 @@ static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N,
     if ((e = get_rows_map_n(dy, P.Mpix, Co, PIX, &tmDy))) return e;
     if ((e = get_act_map(x, N, H, W, Ci, bw, bh, bn, s, &tmX))) return e;
     const int co_tiles = (Co + 127) / 128;
-    const int tiles = co_tiles * P.ugroups;
+    // pairs of co tiles share their x tiles through TMA multicast when there are at least two of them
+    // (even tile counts only: with a padding CTA in the last cluster the launch measured up to 1.9x slower than unicast)
+    const bool mc = g_use_wgrad_mc && co_tiles >= 2 && (co_tiles % 2) == 0;
+    const int tiles = (mc ? (co_tiles + 1) / 2 * 2 : co_tiles) * P.ugroups;
     // splits: fill whole waves of 148 CTAs.  Fixed cost per CTA in 32-pixel k-block units (0.6 us each): prologue + the
     // atomics epilogue, ~10 us with vector reductions, ~40 us with scalar ones (k*k not a multiple of 4, PyTorch layout)
     const bool vec_epi = P.dw_cl || P.kk == 1 || (P.kk & 3) == 0;
@@ -1845,12 +1889,28 @@ static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N,
     size_t smem = (size_t)P.stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+        if (ce == cudaSuccess)
+            ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
         if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad2): %s", cudaGetErrorString(ce)); return (int)ce; }
         attr_set = true;
     }
-    dim3 grid(co_tiles, P.ugroups, splits);
-    conv_wgrad2_kernel<PIX><<<grid, TC_THREADS, smem, st>>>(tmDy, tmX, P);
+    if (mc) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((co_tiles + 1) / 2 * 2, P.ugroups, splits);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_wgrad2_kernel<PIX, true>, tmDy, tmX, P);
+        if (ce != cudaSuccess) { set_error("conv_wgrad2 (multicast) launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+    } else {
+        dim3 grid(co_tiles, P.ugroups, splits);
+        conv_wgrad2_kernel<PIX, false><<<grid, TC_THREADS, smem, st>>>(tmDy, tmX, P);
+    }
     g_launches.fetch_add(1);
     return check_launch("conv_wgrad2");
 }
@@ -1906,6 +1966,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "persist")) { g_use_persist = value; return 0; }
     if (name && !strcmp(name, "wgrad2")) { g_use_wgrad2 = value; return 0; }
     if (name && !strcmp(name, "split")) { g_use_split = value; return 0; }
+    if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
     if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
     if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }
