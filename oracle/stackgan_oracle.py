@@ -336,13 +336,14 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None, 
 
 
 # --------------------------------------------------------------------------- Stage-II outer step
-def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_gp, tr):
+def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_gp, tr, sync=None):
     """One outer step of stage_2_train_fn.py:101-173 (with the :67 / discriminator_2.py:28 fixes).
 
     ca1/g1 are frozen and in eval mode (:52-63: running-stat BN in gen_1, CA still samples).
     G2/CA2 gradients ACCUMULATE over the five critic backward passes because
     fake_256 is not detached and opt_gen_2.zero_grad() only runs after the step
-    (:131,:154,:163-168) -- reproduced here.  tr = dict(ca2=, d2=, g2=)."""
+    (:131,:154,:163-168) -- reproduced here.  tr = dict(ca2=, d2=, g2=).  ``sync(trainer)``, if given, runs right
+    before each optimizer step: the gradient mean over replicas of xm.optimizer_step (:155,:164,:167)."""
     out = {"loss_critic": [], "critic_grads": []}
     tem_mis = tem[perm]
     for it in range(N_CRITIC):
@@ -366,6 +367,8 @@ def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_
             out["first"] = dict(fake_64=fake_64.detach().clone(), fake=fake.detach().clone(),
                                 s_real=s_real.detach().clone(), s_mis=s_mis.detach().clone(),
                                 s_fake=s_fake.detach().clone(), gp=gp.detach().clone())
+        if sync is not None:
+            sync(tr["d2"])
         tr["d2"].opt.step()                                     # :155
     s = d2_forward(d2, fake, tem).view(-1)                      # :157
     lossG = -torch.mean(s) + kl_term(mu2, sigma2)               # :158-162
@@ -373,8 +376,12 @@ def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_
     out["lossG"] = lossG.detach().clone()
     out["g2_grads"] = tr["g2"].grads()
     out["ca2_grads"] = tr["ca2"].grads()
+    if sync is not None:
+        sync(tr["g2"])
     tr["g2"].opt.step()                                         # :164
     tr["g2"].opt.zero_grad()                                    # :165
+    if sync is not None:
+        sync(tr["ca2"])
     tr["ca2"].opt.step()                                        # :167
     tr["ca2"].opt.zero_grad()                                   # :168
     for k in ("d2", "g2", "ca2"):                               # :170-173

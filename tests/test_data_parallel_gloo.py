@@ -73,6 +73,73 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker2(rank, world, port, q):
+    """Stage-II: the generator's gradients accumulate over the five critic backward passes and are averaged over
+    replicas once, right before its step (stage_2_train_fn.py:154-168)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    try:
+        from oracle import stackgan_oracle as O
+        from emu_ops import EmuOps
+        from imagegenerator_b200.comm import DistComm
+        from imagegenerator_b200.engine2 import Stage2Engine
+        from test_engine2_emulated import build_all
+        dt, B = torch.float64, 1
+        ms = build_all(42 + rank)                              # rank-dependent init: the broadcast must fix it
+        ps = O.init_all(42)                                    # what rank 0 holds
+        p = {k: O.to_dtype(ps[k], dt) for k in ps}
+        mine = O.synthetic_batch(B, 2, 200 + rank, dtype=dt)
+        shared = O.synthetic_batch(B, 2, 9, dtype=dt)
+        tr = dict(ca2=O.Trainer(p["con_augment_2"]), d2=O.Trainer(p["critic_2"]), g2=O.Trainer(p["gen_2"]))
+
+        def sync(t):
+            for q_ in t.params.values():
+                dist.all_reduce(q_.grad)
+                q_.grad.div_(world)
+        ref = O.stage2_step(p["con_augment_1"], p["gen_1"], p["con_augment_2"], p["critic_2"], p["gen_2"], mine["real"],
+                            mine["tem"], shared["perm"], shared["z"], shared["eps_ca"], shared["eps_ca2"], shared["eps_gp"],
+                            tr, sync=sync)
+        eng = Stage2Engine(ms["ca1"], ms["g1"], ms["ca2"], ms["d2"], ms["g2"], B, ops=EmuOps(dt), comm=DistComm())
+        eng.load_batch(mine["real"], mine["tem"], mine["tem"][shared["perm"]])
+        eng.outer_step(shared["z"], shared["eps_ca"], shared["eps_ca2"], shared["eps_gp"])
+        worst = 0.0
+        for m, key in ((ms["ca2"], "ca2"), (ms["d2"], "d2"), (ms["g2"], "g2")):
+            sd = m.state_dict()
+            for k, v in ref["after"][key].items():
+                if v.is_floating_point():
+                    err = (sd[k].double() - v).abs().max().item() / max(v.abs().max().item(), 1e-12)
+                    worst = max(worst, err)
+                    assert err < 1e-5, (key, k, err)
+        q.put((rank, "ok", worst))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_world2(worker):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", f"rank {rank}: {info}"
+
+
+@pytest.mark.slow
+def test_stage2_data_parallel_world2_gloo():
+    _run_world2(_worker2)
+
+
 @pytest.mark.slow
 def test_stage1_data_parallel_world2_gloo():
     ctx = mp.get_context("spawn")
