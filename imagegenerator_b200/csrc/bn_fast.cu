@@ -102,6 +102,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 bn_act8_kernel(const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out, Chunking k, int act) {
+    SG_PDL_SYNC();
     if ((int)threadIdx.x >= k.active) return;
     int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
     int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                       const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
                       double* __restrict__ sums, Chunking k, float slope) {
+    SG_PDL_SYNC();
     extern __shared__ float sacc[];                 // [touched groups][C][2]
     const int C = k.CV * 8;
     const int64_t begin = (int64_t)blockIdx.x * k.chunk;
@@ -250,6 +252,7 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
                      const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const double* __restrict__ sums, const T* __restrict__ inject, int inject_group, T* __restrict__ dy,
                      Chunking k, float slope, float n) {
+    SG_PDL_SYNC();
     if ((int)threadIdx.x >= k.active) return;
     int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
     int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
@@ -320,6 +323,7 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
 act_bwd8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __restrict__ out, int64_t nvec, int act) {
+    SG_PDL_SYNC();
     const float slope = act == SG_ACT_RELU ? 0.f : (act == SG_ACT_LRELU ? 0.1f : 1.f);
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * 256) {
         V8 d = ld8(da + i * 8), a = ld8(a_out + i * 8), o;
@@ -340,6 +344,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 gp_bn_reduce8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                      const float* __restrict__ mr, double* __restrict__ tsums, Chunking k, float slope) {
+    SG_PDL_SYNC();
     extern __shared__ float sacc[];                 // [C][3]
     const int C = k.CV * 8;
     for (int t = threadIdx.x; t < C * 3; t += 256) sacc[t] = 0.f;
@@ -380,6 +385,7 @@ gp_bn_apply8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* 
                     const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
                     const double* __restrict__ tsums, T* __restrict__ w_out, T* __restrict__ gy_out, Chunking k, float slope,
                     float n) {
+    SG_PDL_SYNC();
     extern __shared__ float cst[];                  // [8][C]: mean, r, A, B1, B2, E, K1, K2
     const int C = k.CV * 8;
     for (int c = threadIdx.x; c < C; c += 256) {
@@ -423,7 +429,7 @@ template <typename T>
 int gp_bn_reduce8(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums, int64_t rows,
                   int C, int act, cudaStream_t st) {
     Chunking k = make_chunking(rows, C, 1, 4);
-    gp_bn_reduce8_kernel<T><<<k.blocks, 256, (size_t)C * 3 * sizeof(float), st>>>((const T*)v, (const T*)da, (const T*)a_out,
+    launch_pdl(gp_bn_reduce8_kernel<T>, dim3(k.blocks), dim3(256), (size_t)C * 3 * sizeof(float), st, (const T*)v, (const T*)da, (const T*)a_out,
                                                                                   (const T*)y, mr, tsums, k, act_slope(act));
     g_launches.fetch_add(1);
     return check_launch("gp_bn_reduce8");
@@ -433,7 +439,7 @@ int gp_bn_apply8(const void* v, const void* da, const void* a_out, const void* y
                  const double* sums, const double* tsums, void* w_out, void* gy_out, int64_t rows, int C, int act,
                  cudaStream_t st) {
     Chunking k = make_chunking(rows, C, 1, 8);
-    gp_bn_apply8_kernel<T><<<k.blocks, 256, (size_t)C * 8 * sizeof(float), st>>>(
+    launch_pdl(gp_bn_apply8_kernel<T>, dim3(k.blocks), dim3(256), (size_t)C * 8 * sizeof(float), st, 
         (const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, tsums, (T*)w_out, (T*)gy_out, k,
         act_slope(act), (float)rows);
     g_launches.fetch_add(1);
@@ -448,7 +454,7 @@ template <typename T>
 int bn_act8(const void* y, const float* mr, const float* gamma, const float* beta, const void* res, void* out,
             int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {
     Chunking k = make_chunking(rows_per_group, C, groups, 8);
-    bn_act8_kernel<T><<<k.blocks, 256, 0, st>>>((const T*)y, mr, gamma, beta, (const T*)res, (T*)out, k, act);
+    launch_pdl(bn_act8_kernel<T>, dim3(k.blocks), dim3(256), 0, st, (const T*)y, mr, gamma, beta, (const T*)res, (T*)out, k, act);
     g_launches.fetch_add(1);
     return check_launch("bn_act8");
 }
@@ -459,10 +465,10 @@ int bn_bwd_reduce8(const void* da, const void* a_out, const void* y, const float
     size_t smem = (size_t)(groups < 2 ? 1 : 2) * C * 2 * sizeof(float);
     if (k.chunk >= k.gvec) smem = (size_t)groups * C * 2 * sizeof(float);   // tiny tensors: a CTA may span every group
     if (a_out != nullptr)
-        bn_bwd_reduce8_kernel<T, true><<<k.blocks, 256, smem, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, gamma, beta,
+        launch_pdl(bn_bwd_reduce8_kernel<T, true>, dim3(k.blocks), dim3(256), smem, st, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, beta,
                                                                     sums, k, act_slope(act));
     else
-        bn_bwd_reduce8_kernel<T, false><<<k.blocks, 256, smem, st>>>((const T*)da, nullptr, (const T*)y, mr, gamma, beta, sums, k,
+        launch_pdl(bn_bwd_reduce8_kernel<T, false>, dim3(k.blocks), dim3(256), smem, st, (const T*)da, nullptr, (const T*)y, mr, gamma, beta, sums, k,
                                                                      act_slope(act));
     g_launches.fetch_add(1);
     return check_launch("bn_bwd_reduce8");
@@ -473,11 +479,11 @@ int bn_bwd_apply8(const void* da, const void* a_out, const void* y, const float*
                   int act, cudaStream_t st) {
     Chunking k = make_chunking(rows_per_group, C, groups, 8);
     if (a_out != nullptr)
-        bn_bwd_apply8_kernel<T, true><<<k.blocks, 256, 0, st>>>((const T*)da, (const T*)a_out, (const T*)y, mr, gamma, beta, sums,
+        launch_pdl(bn_bwd_apply8_kernel<T, true>, dim3(k.blocks), dim3(256), 0, st, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, beta, sums,
                                                                 (const T*)inject, inject_group, (T*)dy, k, act_slope(act),
                                                                 (float)rows_per_group);
     else
-        bn_bwd_apply8_kernel<T, false><<<k.blocks, 256, 0, st>>>((const T*)da, nullptr, (const T*)y, mr, gamma, beta, sums,
+        launch_pdl(bn_bwd_apply8_kernel<T, false>, dim3(k.blocks), dim3(256), 0, st, (const T*)da, nullptr, (const T*)y, mr, gamma, beta, sums,
                                                                  (const T*)inject, inject_group, (T*)dy, k, act_slope(act),
                                                                  (float)rows_per_group);
     g_launches.fetch_add(1);
@@ -486,7 +492,7 @@ int bn_bwd_apply8(const void* da, const void* a_out, const void* y, const float*
 template <typename T>
 int act_bwd8(const void* da, const void* a_out, void* out, int64_t n, int act, cudaStream_t st) {
     int64_t nvec = n / 8;
-    act_bwd8_kernel<T><<<grid_for(nvec, 256, 8), 256, 0, st>>>((const T*)da, (const T*)a_out, (T*)out, nvec, act);
+    launch_pdl(act_bwd8_kernel<T>, dim3(grid_for(nvec, 256, 8)), dim3(256), 0, st, (const T*)da, (const T*)a_out, (T*)out, nvec, act);
     g_launches.fetch_add(1);
     return check_launch("act_bwd8");
 }

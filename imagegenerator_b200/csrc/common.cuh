@@ -115,6 +115,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- programmatic dependent launch (PDL): kernels launched through launch_pdl may be scheduled while the previous
+// kernel of their stream is still draining its last wave (the hardware releases them once every CTA of that kernel has
+// executed launch_dependents or exited); SG_PDL_SYNC() is the point up to which a kernel touches no global memory --
+// it lets ITS successor go and then blocks until everything it depends on has completed and is visible.  In a captured
+// step this hides the ~2-3 us launch latency between dependent kernels (600 launches per Stage-I step).
+#define SG_PDL_SYNC()                                                   \
+    do {                                                                \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+        asm volatile("griddepcontrol.wait;" ::: "memory");              \
+    } while (0)
+
+extern int g_use_pdl;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
     int64_t blocks = (work_items + threads - 1) / threads;
     int64_t cap = (int64_t)SG_NUM_SMS * max_waves;

@@ -632,6 +632,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    SG_PDL_SYNC();        // barriers, TMEM and the stats staging are set up: from here on global memory is touched
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1741,10 +1742,12 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     cfg.blockDim = dim3(TCP_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     cudaError_t ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2>, tmA, tmB, P)
                              : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1>, tmA, tmB, P);
     if (ce != cudaSuccess) { set_error("conv_tcp launch: %s", cudaGetErrorString(ce)); return (int)ce; }
@@ -1967,6 +1970,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "wgrad2")) { g_use_wgrad2 = value; return 0; }
     if (name && !strcmp(name, "split")) { g_use_split = value; return 0; }
     if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }
+    if (name && !strcmp(name, "pdl")) { g_use_pdl = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
     if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
     if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }

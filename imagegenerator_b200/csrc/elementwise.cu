@@ -4,10 +4,12 @@
 // reductions finished with one fp64 atomic per channel per CTA.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace sg {
 
 std::atomic<long long> g_launches{0};
+int g_use_pdl = 1;
 static thread_local char g_err[512] = "";
 
 int tcp_workspace_init();
@@ -33,6 +35,7 @@ int check_launch(const char* what) {
 // ------------------------------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(256) ew4_kernel(F f, int64_t n4) {
+    SG_PDL_SYNC();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) f(i);
 }
@@ -45,7 +48,7 @@ static int launch_ew4(F f, int64_t n, cudaStream_t st, const char* what) {
     }
     int64_t n4 = n / 4;
     if (n4 == 0) return 0;
-    ew4_kernel<F><<<grid_for(n4, 256, 16), 256, 0, st>>>(f, n4);
+    launch_pdl(ew4_kernel<F>, dim3(grid_for(n4, 256, 16)), dim3(256), 0, st, f, n4);
     g_launches.fetch_add(1);
     return check_launch(what);
 }
@@ -259,6 +262,7 @@ __global__ void fill_tail_kernel(float* p, float v, int64_t from, int64_t n) {
 template <int NV, typename F, typename OutT>
 __global__ void __launch_bounds__(256) rowreduce_kernel(F f, OutT* out, int64_t rows_per_group, int C,
                                                          int64_t rows_per_block, int out_group_stride) {
+    SG_PDL_SYNC();
     __shared__ double sh[NV][256];
     int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
     int c = blockIdx.z * TX + tx;
@@ -306,7 +310,7 @@ static int launch_rowreduce(F f, OutT* out, int64_t rows_per_group, int C, int g
     if (rpb > (int64_t)TY * 256) rpb = (int64_t)TY * 256;   // bound the fp32 partial length per thread
     int64_t rblocks = (rows_per_group + rpb - 1) / rpb;
     dim3 grid((unsigned)rblocks, groups, cchunks), block(TX, TY);
-    rowreduce_kernel<NV, F, OutT><<<grid, block, 0, st>>>(f, out, rows_per_group, C, rpb, C * NV);
+    launch_pdl(rowreduce_kernel<NV, F, OutT>, grid, block, 0, st, f, out, rows_per_group, C, rpb, C * NV);
     g_launches.fetch_add(1);
     return check_launch(what);
 }
@@ -351,6 +355,7 @@ struct GpBnReduceF {
 __global__ void bn_finalize_kernel(const double* stats, double count, float* mr, float* rm, float* rv,
                                    long long* nbt, int dup_first, int update_running, float momentum, float eps,
                                    int G, int C) {
+    SG_PDL_SYNC();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && update_running && nbt) *nbt += dup_first + G - 1;
     if (c >= C) return;
@@ -384,6 +389,7 @@ __global__ void bn_eval_mr_kernel(const float* rm, const float* rv, float* mr, f
 }
 
 __global__ void bn_param_grad_kernel(const double* sums, float* dgamma, float* dbeta, int G, int C) {
+    SG_PDL_SYNC();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s1 = 0, s2 = 0;
@@ -510,6 +516,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ x, 
 template <typename T, int C>
 __global__ void __launch_bounds__(256) patchify_k4s2_kernel(const T* __restrict__ x, T* __restrict__ P, int H, int W, int Ho,
                                                             int Wo, unsigned total) {
+    SG_PDL_SYNC();
     for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
         const unsigned kh = i & 3u, pix = i >> 2;
         const unsigned ow = pix % (unsigned)Wo, r = pix / (unsigned)Wo;
@@ -542,6 +549,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ col, const float* __restrict__ bias,
                                                          T* __restrict__ out, int Hi, int Wi, int Ho, int Wo, int C, int k,
                                                          int s, int p, int act, unsigned total) {
+    SG_PDL_SYNC();
     const int kk = k * k, K = C * kk;
     for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
         const unsigned ow = i % (unsigned)Wo, r = i / (unsigned)Wo;
@@ -733,6 +741,7 @@ int sg_check_device(void) {
         set_error("libsgb200 is built for sm_100a (B200) only; device is sm_%d%d", p.major, p.minor);
         return SG_ERR_NO_DEVICE;
     }
+    if (const char* e = getenv("SG_PDL")) sg::g_use_pdl = atoi(e);      // 0 disables programmatic dependent launch
     sg::tcp_workspace_init();     // the one allocation of the library: scratch for the conv kernel's tail-wave K-split
     return 0;
 }
@@ -802,8 +811,8 @@ int sg_patchify(const void* x, void* P, int N, int H, int W, int C, int Ho, int 
     int64_t n = (int64_t)N * Ho * Wo * k * k;
     if (k == 4 && s == 2 && p == 1 && C == 3 && Ho * 2 == H && Wo * 2 == W && (int64_t)N * Ho * Wo * 4 < (1ll << 31)) {
         unsigned total = (unsigned)((int64_t)N * Ho * Wo * 4);
-        SG_DISPATCH_T(dtype, (patchify_k4s2_kernel<T, 3><<<grid_for(total, 256, 16), 256, 0, SG_STREAM(stream)>>>(
-                                 (const T*)x, (T*)P, H, W, Ho, Wo, total)));
+        SG_DISPATCH_T(dtype, (launch_pdl(patchify_k4s2_kernel<T, 3>, dim3(grid_for(total, 256, 16)), dim3(256), 0, SG_STREAM(stream),
+                                         (const T*)x, (T*)P, H, W, Ho, Wo, total)));
         SG_LAUNCHED("patchify_k4s2");
         return 0;
     }
@@ -819,8 +828,8 @@ int sg_unpatchify(const float* col, const float* bias, void* out, int N, int Hi,
     SG_REQUIRE(Ho == (Hi - 1) * s - 2 * p + k && Wo == (Wi - 1) * s - 2 * p + k, "unpatchify: inconsistent sizes");
     SG_REQUIRE((int64_t)N * Ho * Wo < (1ll << 31), "unpatchify: too many pixels");
     unsigned total = (unsigned)((int64_t)N * Ho * Wo);
-    SG_DISPATCH_T(dtype, (unpatchify_kernel<T><<<grid_for(total, 256, 16), 256, 0, SG_STREAM(stream)>>>(
-                             col, bias, (T*)out, Hi, Wi, Ho, Wo, C, k, s, p, act, total)));
+    SG_DISPATCH_T(dtype, (launch_pdl(unpatchify_kernel<T>, dim3(grid_for(total, 256, 16)), dim3(256), 0, SG_STREAM(stream), col, bias,
+                                     (T*)out, Hi, Wi, Ho, Wo, C, k, s, p, act, total)));
     SG_LAUNCHED("unpatchify");
     return 0;
 }
@@ -885,9 +894,8 @@ int sg_col_stats(const void* y, double* stats, int64_t rows_per_group, int C, in
 int sg_bn_finalize(const double* stats, int64_t count, float* mr, float* running_mean, float* running_var,
                    int64_t* nbt, int dup_first, int update_running, float momentum, float eps, int groups, int C,
                    void* stream) {
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(stats, (double)count, mr, running_mean,
-                                                                       running_var, (long long*)nbt, dup_first,
-                                                                       update_running, momentum, eps, groups, C);
+    launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, SG_STREAM(stream), stats, (double)count, mr, running_mean,
+               running_var, (long long*)nbt, dup_first, update_running, momentum, eps, groups, C);
     SG_LAUNCHED("bn_finalize");
     return 0;
 }
@@ -969,7 +977,7 @@ int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const floa
 }
 
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream) {
-    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(sums, dgamma, dbeta, groups, C);
+    launch_pdl(bn_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, SG_STREAM(stream), sums, dgamma, dbeta, groups, C);
     SG_LAUNCHED("bn_param_grad");
     return 0;
 }

@@ -336,6 +336,8 @@ class Stage2Engine:
             dst.copy_(src, non_blocking=True)
 
         def body():
+            if hasattr(ops, "set_option"):
+                ops.set_option("pdl", 1)          # programmatic dependent launch: +2 % on this step (see engine.Stage1Engine._body)
             ops.nchw_to_nhwc(self.s_real, self.d.group_view(self.d.a[0], 0, 1))
             self.outer_step(self.s_z, self.s_e1, self.s_e2, self.s_egp)
         if not use_graph or getattr(ops, "is_emulator", False):
