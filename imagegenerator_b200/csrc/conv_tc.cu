@@ -503,8 +503,11 @@ struct TcpParams {
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// default (.release.cta) semantics on the cluster address, as CUTLASS's ClusterBarrier::arrive does: the explicit
+// .release.cluster form costs a cluster-scope MEMBAR (~2600 cycles per tile, measured), and nothing but the TMEM reads --
+// already complete after tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync -- is handed over here
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -599,6 +602,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[8], tempty_bar[8];
     __shared__ uint32_t tmem_slot;
     __shared__ float sstat[2][256][2];          // statistics staging, double-buffered by tile parity
+    __shared__ uint4 sstage[TCP_EPI_WARPS][32 * 4];   // per epilogue warp: 32 rows x 64 B, for the coalesced store
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -717,6 +721,18 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int act = P.act;
         const bool has_stats = P.stats != nullptr;
         const int scol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        // coalesced store (fast path): a lane's 64 B of a row go through shared memory so that FOUR lanes write one
+        // row's 64 contiguous bytes and a store instruction touches 8 rows, not 32 (the drain of a 128x256 tile was
+        // bound by its 4096 L1 wavefronts: one per lane and instruction).  Lane l stores rows q*32 + i*8 + l/4, i<4.
+        uint4* const stg = sstage[warp - 2];
+        int cdn[4], cdh[4], cdw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = q * 32 + i * 8 + (lane >> 2);
+            cdn[i] = rr / (P.bw * P.bh);
+            const int rm = rr - cdn[i] * (P.bw * P.bh);
+            cdh[i] = rm / P.bw; cdw[i] = rm - cdh[i] * P.bw;
+        }
         uint32_t ti = 0, ab = 0, abpar = 0;
         Work w;
         for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w);
@@ -879,6 +895,15 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool plain = P.bias == nullptr && P.residual == nullptr && P.out32 == nullptr && !is_split && vec_ok &&
                                (ncols & 31) == 0 && P.out != nullptr;
             if (plain) {
+                bf16* crow[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ni = n0 + cdn[i];
+                    int oh2 = h0 + cdh[i], ow2 = w0 + cdw[i];
+                    if (P.mode == 1) { oh2 = oh2 * P.s + ph; ow2 = ow2 * P.s + pw; }
+                    crow[i] = ni < P.n_img ? P.out + (((int64_t)ni * P.outH + oh2) * P.outW + ow2) * P.n_total + nt0 + (lane & 3) * 8
+                                           : nullptr;
+                }
                 for (int c0 = half * 32; c0 < ncols; c0 += 64) {
                     uint32_t v[32];
                     tc_ld16_nowait(tacc + (uint32_t)c0, v);
@@ -900,12 +925,21 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                    if (n_img < P.n_img) {
-                        uint4* o = reinterpret_cast<uint4*>(orow + c0);
-                        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                        o[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-                        o[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                    {
+                        // row = lane: 16-byte chunk j goes to slot j ^ ((lane >> 1) & 3) (bank-conflict-free both ways)
+                        const int sw = (lane >> 1) & 3;
+                        __syncwarp();
+                        stg[lane * 4 + (0 ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        stg[lane * 4 + (1 ^ sw)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        stg[lane * 4 + (2 ^ sw)] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+                        stg[lane * 4 + (3 ^ sw)] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = i * 8 + (lane >> 2);
+                            const uint4 val = stg[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
+                            if (crow[i] != nullptr) *reinterpret_cast<uint4*>(crow[i] + c0) = val;
+                        }
                     }
                     if (has_stats) {
                         const bool ok = n_img < P.n_img;
@@ -1616,7 +1650,8 @@ static int split_factor(long tiles, int units, int nkb, int bn = 256, double t_k
         if (smax > 6) smax = 6;
         // a slice costs its share of the mainloop; a non-owner then drains its accumulator to the workspace (measured
         // ~5.5 us for 128 x 256 fp32), the owner's drain grows by ~3 us per partial it adds (critic ds3 trace)
-        const double c_store = 10000.0 * bn / 256.0, c_read = 5700.0 * bn / 256.0;
+        const double cs = g_use_split == 2 ? 0.0 : 1.0;      // option split=2: ignore the costs (experiments)
+        const double c_store = cs * 10000.0 * bn / 256.0, c_read = cs * 5700.0 * bn / 256.0;
         for (int S = 2; S <= smax; ++S) {
             const int kbs = (nkb + S - 1) / S;
             const double t = kbs * t_kb + c_store + (S - 1) * c_read + 1000.0;
