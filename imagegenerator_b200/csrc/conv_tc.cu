@@ -495,6 +495,7 @@ struct TcpParams {
     double* stats;        // [groups][n_total][2] or NULL
     float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
     const bf16* residual; // added before the activation (same layout as out) or NULL
+    int lgW, lgHW;        // log2(Wq), log2(Hq*Wq)
     int full_tiles, split, kb_slice;   // tail-wave K-split: tiles below full_tiles are whole; see next_work()
     float* ws;            // fp32 partial tiles of the split tail wave
     int* flags;           // one per (leftover tile, non-owner slice, CTA of the pair)
@@ -648,7 +649,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int nt = r / P.m_tiles, mt = r - nt * P.m_tiles;
                 const PhaseGeo g = phase_geo(P, phase);
                 const int m0 = (mt * CG + (int)rank) * 128;
-                const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
+                const int w0 = m0 & (P.Wq - 1), h0 = (m0 >> P.lgW) & (P.Hq - 1), n0 = m0 >> P.lgHW;   // Hq, Wq are powers of two
                 const int nt0 = nt * P.BN + (int)rank * b_rows;
                 int tap = w.kb0 / P.cblocks, cb = w.kb0 - tap * P.cblocks;
                 int th = tap / g.ntw, tw = tap - th * g.ntw;
@@ -742,7 +743,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int nt = rr / P.m_tiles, mt = rr - nt * P.m_tiles;
             const int ph = phase / P.s, pw = phase - ph * P.s;
             const int m0 = (mt * CG + (int)rank) * 128;
-            const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
+            const int w0 = m0 & (P.Wq - 1), h0 = (m0 >> P.lgW) & (P.Hq - 1), n0 = m0 >> P.lgHW;   // Hq, Wq are powers of two
             const int nt0 = nt * P.BN;
             const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
             const bool row_ok = n_img < P.n_img && (P.out != nullptr || P.out32 != nullptr);
@@ -1715,6 +1716,8 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     if (!choose_box(P.Hq, P.Wq, &P.bw, &P.bh, &P.bn)) { set_error("conv_tcp: grid %dx%d not tileable", P.Hq, P.Wq); return SG_ERR_UNSUPPORTED; }
     const int M = N * P.Hq * P.Wq;
     P.n_img = N;
+    P.lgW = 0; while ((1 << P.lgW) < P.Wq) ++P.lgW;
+    P.lgHW = P.lgW; while ((1 << P.lgHW) < P.Hq * P.Wq) ++P.lgHW;
     P.cblocks = (P.Ck + 63) / 64;
     P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
     P.stats = stats;
