@@ -329,13 +329,17 @@ class CriticRT:
             self.tem_all[self.B:].copy_(tem_mis)
 
     # ---------------------------------------------------------------- forward
-    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False):
+    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False, before_weights=None):
         """Trunk + head on groups [g0, g0+ng).  BN running statistics are updated once per group,
-        group g0 ``dup_first`` times (the mismatched-text call sees the real images again)."""
+        group g0 ``dup_first`` times (the mismatched-text call sees the real images again).
+        ``before_weights()`` is called right before the first kernel that reads packed weights (the engines re-pack
+        them on a side stream after each optimizer step and join here)."""
         ops, m, B = self.ops, self.m, self.B
         gv = lambda t: self.group_view(t, g0, ng)
         L0 = self.layers[0]
         ops.patchify(gv(self.a[0]), gv(self.P), L0.k, L0.s, L0.p)
+        if before_weights is not None:
+            before_weights()
         ops.conv_fprop(gv(self.P), self.pf0, L0.conv.bias.data, gv(self.a[1]), 1, 1, 0, act=ACT_LRELU)
         for l in range(1, self.nl):
             L, bn = self.layers[l], self.layers[l].bn
@@ -527,6 +531,7 @@ class Stage1Engine:
         self.losses = ops.zeros((4,), ops.f32)       # [loss_critic, gp, lossG, kl]
         self.side = SideStream(ops)
         self.gen_side = SideStream(ops)               # next iteration's generator forward (critic_iteration)
+        self.pack_side = SideStream(ops)              # weight re-packing after the critic's optimizer step
         self._fake_ready = False
         self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
         self.comm = comm                             # comm.DistComm or None
@@ -580,6 +585,7 @@ class Stage1Engine:
         seg = getattr(self, "_seg", None)
         if seg is not None and seg.capturing:
             self.gen_side.join()                                # a graph segment must end with every fork joined
+            self.pack_side.join()
             seg.cut(lambda: self.comm.allreduce_async(t))       # eager NCCL between two graph segments
         else:
             self.comm.allreduce_async(t)
@@ -614,7 +620,8 @@ class Stage1Engine:
             self._generate(z, eps_ca)
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
-        d.forward(0, 3, dup_first=2, training=True, with_mismatched=True)    # :125-132 + utils.py:13
+        d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,    # :125-132 + utils.py:13
+                  before_weights=self.pack_side.join)
         if next_noise is not None and self.gen_side.enabled:
             self.gen_side.run(lambda: self._generate(*next_noise))
             self._fake_ready = True
@@ -637,11 +644,12 @@ class Stage1Engine:
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
                    on_layer_done=bucket, head_reduce=False, side=self.side)
         self.optimizer_step(d.fp, already_reduced=tail[0])       # :149
-        d.refresh_weights()
+        # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
+        self.pack_side.run(d.refresh_weights)
 
     def generator_step(self):
         ops, d, B = self.ops, self.d, self.B
-        d.forward(1, 1, dup_first=1, training=True)              # :154 (updated critic, last fake)
+        d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join)   # :154 (updated critic, last fake)
         st = self.ca.st
         ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])          # :155-159
         ops.zero(self.g.fp.grad); ops.zero(self.ca.fp.grad)      # :161-164

@@ -222,6 +222,7 @@ class Stage2Engine:
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)
         self.side = SideStream(ops)
+        self.pack_side = SideStream(ops)              # critic weight re-packing, overlapped with the next generator forward
         self.comm = comm
         self.one_minus_eps = ops.empty((B,), ops.f32)
         self.dcg2 = ops.zeros((B, 1, 1, ca2.c_dim), ops.f32)
@@ -255,6 +256,7 @@ class Stage2Engine:
         if self.comm is not None:
             seg = getattr(self, "_seg", None)
             if seg is not None and seg.capturing:
+                self.pack_side.join()                               # a graph segment must end with every fork joined
                 seg.cut(lambda: (self.comm.allreduce_async(fp.grad), self.comm.wait_all()))
             else:
                 self.comm.allreduce_async(fp.grad)
@@ -285,7 +287,8 @@ class Stage2Engine:
         self._generate(z, eps_ca1, eps_ca2)
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
-        d.forward(0, 3, dup_first=2, training=True, with_mismatched=True)        # :133-140 + utils.py:13
+        d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,        # :133-140 + utils.py:13
+                  before_weights=self.pack_side.join)
         ops.zero(d.fp.grad)                                         # :153
         ops.zero(d.dA); ops.zero(d.dBv)
         d.gp_first_order()
@@ -300,11 +303,11 @@ class Stage2Engine:
         ops.scale_rows_add(d.group_view(d.dx, 2, 1), self.one_minus_eps, dfake, True)
         self._generator_backward(dfake, 0.0)                        # accumulates into G2 / CA2 (:154, no zero_grad)
         self.optimizer_step(d.fp)                                   # :155
-        d.refresh_weights()
+        self.pack_side.run(d.refresh_weights)                       # joined before the next critic forward reads the packs
 
     def generator_step(self):
         ops, d, B = self.ops, self.d, self.B
-        d.forward(1, 1, dup_first=1, training=True)                 # :157
+        d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join)     # :157
         st = self.ca2.st
         ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])  # :158-162
         d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
