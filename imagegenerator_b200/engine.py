@@ -694,7 +694,30 @@ class Stage1Engine:
         static device buffers, then the ~650 kernels of the step run as one CUDA-graph replay
         (Stage-I kernels are microseconds long: launch-bound otherwise, SURVEY.md section 7 hard part 3)."""
         self._ensure_static()
-        self.s_real.copy_(real_nchw, non_blocking=True)
+        if (not real_nchw.is_cuda) and real_nchw.is_pinned() and not getattr(self.ops, "is_emulator", False):
+            # host batch: the 6 MB image upload goes over a copy stream into one of two staging buffers, so that batch
+            # k+1 crosses PCIe while step k still computes; the compute stream only does a device-to-device copy
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.ops.device)
+                self._stage = [torch.empty_like(self.s_real) for _ in range(2)]
+                self._stage_free = [None, None]
+                self._stage_i = 0
+            i = self._stage_i
+            self._stage_i ^= 1
+            cur = torch.cuda.current_stream(self.ops.device)
+            with torch.cuda.stream(self._copy_stream):
+                if self._stage_free[i] is not None:
+                    self._copy_stream.wait_event(self._stage_free[i])      # the step that last read this buffer
+                self._stage[i].copy_(real_nchw, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(self._copy_stream)
+            cur.wait_event(up)
+            self.s_real.copy_(self._stage[i], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._stage_free[i] = done
+        else:
+            self.s_real.copy_(real_nchw, non_blocking=True)
         self.d.tem_all[:self.B].copy_(tem, non_blocking=True)
         self.d.tem_all[self.B:].copy_(tem_mis, non_blocking=True)
         self.s_z.copy_(z, non_blocking=True)

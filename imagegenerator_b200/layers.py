@@ -108,4 +108,9 @@ class FlatParams:
                     mod._buffers[name] = buf.to(device=device, dtype=dtype if buf.is_floating_point() else buf.dtype)
 
     def set_lr(self, lr):
+        # a scalar write from pageable host memory synchronises the stream: only touch the device when the value
+        # changes (StepLR: every 100 batches), or the train loop would stall on every batch
+        if getattr(self, "_lr_host", None) == lr:
+            return
+        self._lr_host = lr
         self.hyper[0] = lr

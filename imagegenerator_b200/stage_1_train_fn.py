@@ -52,6 +52,14 @@ def make_allreduce(world):
     return allreduce
 
 
+def _report(pending, log, rank, num_epochs, n_batches):
+    epoch, batch_idx, host, ev = pending
+    ev.synchronize()
+    if rank == 0:
+        log(f"Epoch [{epoch}/{num_epochs}] Batch {batch_idx}/{n_batches} "
+            f"Loss D: {float(host[0]):.4f}, loss G: {float(host[2]):.4f}")
+
+
 def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_size, start_epoch=0,
             bucket_name="data-and-checkpoints-bucket", save_dir="./checkpoints/Stage1",
             log=print, use_graph=True, engine=None):
@@ -83,19 +91,25 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
     for fp, opt in ((eng.ca.fp, opt_con_augment_1), (eng.d.fp, opt_critic_1), (eng.g.fp, opt_gen_1)):
         lr, b1, b2, eps = _adam_hyper(opt)
         fp.hyper[:4] = torch.tensor([lr, b1, b2, eps], dtype=torch.float32)
+        fp._lr_host = lr
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 
+    loss_bufs = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending = None
     for epoch in range(start_epoch, num_epochs):
         for batch_idx, (tokenized_texts, real_img_64) in enumerate(loader):
-            tokenized_texts = {k: v.to(dev, non_blocking=True) for k, v in tokenized_texts.items()}
+            # pageable host tensors are copied synchronously with the stream (the host would wait for the previous
+            # step on every batch): go through pinned memory
+            tokenized_texts = {k: pin(v).to(dev, non_blocking=True) for k, v in tokenized_texts.items()}
             seed_t = torch.randint(0, 2 ** 32 - 1, (1,))      # :98-105: the master's seed for every replica
             if world > 1:
                 seed_t = seed_t.to(dev)
                 dist.broadcast(seed_t, 0)
             generator = torch.Generator().manual_seed(int(seed_t.item()))
             perm = torch.randperm(batch_size, generator=generator)        # :108-111
-            mismatched = {k: v[perm.to(v.device)] for k, v in tokenized_texts.items()}
+            perm_dev = pin(perm).to(dev, non_blocking=True)
+            mismatched = {k: v[perm_dev] for k, v in tokenized_texts.items()}
 
             tem = projection_head(textEncoder(**tokenized_texts).last_hidden_state[:, 0, :])     # :117-119
             with torch.no_grad():
@@ -120,16 +134,25 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
                                     p.grad.div_(world)
                     opt.step()
 
-            losses = eng.losses.tolist()                       # device -> host read (the reference's print, :178-181)
-            if rank == 0:
-                log(f"Epoch [{epoch}/{num_epochs}] Batch {batch_idx}/{len(loader)} "
-                    f"Loss D: {losses[0]:.4f}, loss G: {losses[2]:.4f}")
+            # the reference prints both losses after every batch (:178-181), a device -> host read.  Here the read is a
+            # non-blocking copy into pinned memory; the line for batch k is printed while batch k+1 is already running
+            # on the GPU (and after the loop for the last one), so the host never stalls the stream
+            if pending is not None:
+                _report(pending, log, rank, num_epochs, len(loader))
+            host = loss_bufs[batch_idx % 2]
+            host.copy_(eng.losses, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            pending = (epoch, batch_idx, host, ev)
             for s in schedulers:                               # :187-192 (per batch)
                 s.step()
             eng.d.fp.set_lr(opt_critic_1.param_groups[0]["lr"])
             eng.g.fp.set_lr(opt_gen_1.param_groups[0]["lr"])
             eng.ca.fp.set_lr(opt_con_augment_1.param_groups[0]["lr"])
 
+        if pending is not None:                                # last batch of the epoch
+            _report(pending, log, rank, num_epochs, len(loader))
+            pending = None
         if rank == 0 and epoch % 10 == 0:                     # :211-238
             eng.export_optimizer_state(opt_con_augment_1, eng.ca.fp)
             eng.export_optimizer_state(opt_critic_1, eng.d.fp)

@@ -64,19 +64,23 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
     for fp, opt in ((eng.ca2.fp, opt_con_augment_2), (eng.d.fp, opt_critic_2), (eng.g2.fp, opt_gen_2)):
         lr, b1, b2, eps = _adam_hyper(opt)
         fp.hyper[:4] = torch.tensor([lr, b1, b2, eps], dtype=torch.float32)
+        fp._lr_host = lr
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 
     for epoch in range(start_epoch, num_epochs):
         for batch_idx, (tokenized_texts, real_img_256) in enumerate(loader):
-            tokenized_texts = {k: v.to(dev, non_blocking=True) for k, v in tokenized_texts.items()}
+            # pageable host tensors are copied synchronously with the stream (the host would wait for the previous
+            # step on every batch): go through pinned memory
+            tokenized_texts = {k: pin(v).to(dev, non_blocking=True) for k, v in tokenized_texts.items()}
             seed_t = torch.randint(0, 2 ** 32 - 1, (1,))               # :105-113
             if world > 1:
                 seed_t = seed_t.to(dev)
                 dist.broadcast(seed_t, 0)
             generator = torch.Generator().manual_seed(int(seed_t.item()))
             perm = torch.randperm(batch_size, generator=generator)     # :115-118
-            mismatched = {k: v[perm.to(v.device)] for k, v in tokenized_texts.items()}
+            perm_dev = pin(perm).to(dev, non_blocking=True)
+            mismatched = {k: v[perm_dev] for k, v in tokenized_texts.items()}
             with torch.no_grad():                                       # text side is frozen
                 tem = projection_head(textEncoder(**tokenized_texts).last_hidden_state[:, 0, :])      # :121-123
                 tem_mis = projection_head(textEncoder(**mismatched).last_hidden_state[:, 0, :])       # :135-137
