@@ -310,6 +310,37 @@ def run_sampling(ops, world, rank, dev, reps=20, B=64):
             "gpu_launches_per_batch": smp.launches, "bn": "eval mode, folded into the packed conv weights"}
 
 
+def time_hbm_kernel(ops, peaks, reps=10):
+    """Dominant HBM-bound kernel of the Stage-II step: BatchNorm backward (apply) on the generator's 64x128x128x80
+    activation (generator_2.py:55 `up2` block): three 168 MB tensors in, one out, each exactly once."""
+    rows, C = 64 * 128 * 128, 80
+    mk = lambda: torch.randn(rows, C, device=ops.device).to(ops.act_dtype)
+    da, a, y, dy = mk(), mk(), mk(), mk()
+    mr = torch.rand(1, C, 2, device=ops.device) + 0.5
+    gamma = torch.rand(C, device=ops.device) + 0.5
+    sums = torch.zeros(1, C, 2, dtype=torch.float64, device=ops.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=ops.device)
+    fn = lambda: ops.bn_bwd_apply(da, a, y, mr, gamma, sums, dy, 1, 1)
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    byts = 4.0 * rows * C * 2
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = byts / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "sg_bn_bwd_apply (bn_bwd_apply8_kernel) on the 64x128x128x80 bf16 activation of G2 up2",
+            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+            "traffic": 648091136, "traffic_unit": "B per launch (dram read 503.4 MB + write 144.7 MB, profiles/ncu_bn_r1b_summary.txt; "
+                                                  "algorithmic 671.1 MB, the tail of the output is still in L2 at kernel end)",
+            "algorithmic_bytes": int(byts), "kernel_ms": round(ms, 5),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
+
+
 # ------------------------------------------------------------------------------------------------ kernel roofline
 def time_dominant_kernel(ops, B, reps=20):
     """The critic's heaviest conv (ds3: 128->256, 16x16 -> 8x8, all three image groups batched) timed
@@ -473,6 +504,15 @@ def main():
         del eng
         torch.cuda.empty_cache()
         try:
+            if rank == 0:
+                pk = {}
+                try:
+                    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                        pk = json.load(f)
+                except Exception:
+                    pass
+                extras["roofline_hbm"] = time_hbm_kernel(ops, pk)
+                torch.cuda.empty_cache()
             extras["stage2"] = run_stage2(ops, comm, world, rank, dev)
             extras["sampling"] = run_sampling(ops, world, rank, dev)
         except Exception as e:                                    # secondary sections must not take the headline down
