@@ -615,6 +615,10 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tiles_per_phase = P.n_tiles * P.m_tiles;
     const int nkb_tile = (P.mode == 0 ? P.k * P.k : (P.k / P.s) * (P.k / P.s)) * P.cblocks;   // equal for every phase
 
+    if (threadIdx.x == 32) {          // fetch both TMA descriptors while the barriers and TMEM are being set up
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < P.nbuf; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TCP_EPI_WARPS * CG); }
