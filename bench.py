@@ -537,7 +537,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "cuda_graph": use_graph, "grad_allreduce": ("NCCL avg, 2 buckets/critic step on a side stream, "
+                       "cuda_graph": use_graph, "grad_allreduce": ("NCCL avg, one all-reduce of the flat gradient buffer per optimizer step, "
                                                                     f"{s1_bytes_per_step} B/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "flops_per_image_executed": FLOPS_PER_IMG,
                        "flops_per_image_reference_necessary": FLOPS_PER_IMG_REFERENCE_NECESSARY},
