@@ -255,7 +255,38 @@ def run_stage2(ops, comm, world, rank, dev, steps=5, warmup=3, B=64):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # ---- end to end through train_2 with pinned host batches (image upload + noise inside the timed region)
+    from imagegenerator_b200.stage_2_train_fn import train_2
+    table = torch.randn(B, 512, generator=torch.Generator().manual_seed(5000 + rank)).to(dev)
+    enc, head = TableEncoder(table).to(dev), IdentityHead().to(dev)
+    mk = lambda m_: torch.optim.Adam(m_.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    opts = [mk(ca2), mk(d2), mk(g2)]
+    scheds = [torch.optim.lr_scheduler.StepLR(o, step_size=100, gamma=0.5) for o in opts]
+
+    def host_batches(n, seed):
+        gg = torch.Generator().manual_seed(seed)
+        return [({"idx": torch.arange(B)}, torch.randn(B, 3, 256, 256, generator=gg).clamp_(-1, 1).pin_memory()) for _ in range(n)]
+    ck_dir = f"/tmp/sgb200_bench_ckpt2_{os.getpid()}"
+    quiet = lambda *a, **k: None
+    args2 = dict(start_epoch=1, save_dir=ck_dir, stage1_checkpoint=None, log=quiet, use_graph=True, engine=eng)
+    train_2([enc, head, ca1, ca2, g1, d2, g2], opts, scheds, host_batches(2, 1), 2, dev, B, **args2)     # warm-up pass
+    hb = host_batches(steps, 2)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    train_2([enc, head, ca1, ca2, g1, d2, g2], opts, scheds, hb, 2, dev, B, **args2)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
     out = {"metric": "stackgan_stage2_train_images_per_sec", "value": round(B * world / (ms * 1e-3), 2), "unit": "images/s",
+           "e2e": {"value": round(B * world / (e2e_ms * 1e-3), 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 3),
+                   "h2d_bytes_per_step": B * 3 * 256 * 256 * 4 + B * 8 + 5 * B * 100 * 4 + 5 * B * 4, "d2h_bytes_per_step": 0,
+                   "api": "imagegenerator_b200.stage_2_train_fn.train_2 (loss read every 100 batches, like the reference)"},
            "ms_per_step": round(ms, 3), "batch_per_gpu": B, "steps": steps, "warmup": warmup,
            "step_tflops_per_gpu": round(FLOPS2_PER_IMG * B / (ms * 1e-3) / 1e12, 1),
            "flops_per_image_executed": FLOPS2_PER_IMG, "flops_per_image_reference_necessary": FLOPS2_PER_IMG_REFERENCE_NECESSARY,

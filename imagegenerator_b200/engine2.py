@@ -334,7 +334,30 @@ class Stage2Engine:
             self.s_e2 = ops.empty((N_CRITIC, B, self.ca2.m.c_dim), f)
             self.s_egp = ops.empty((N_CRITIC, B), f)
             self.graph, self.launches_per_step = None, None
-        for dst, src in ((self.s_real, real_nchw), (self.d.tem_all[:B], tem), (self.d.tem_all[B:], tem_mis), (self.s_z, z),
+        if (not real_nchw.is_cuda) and real_nchw.is_pinned() and not getattr(ops, "is_emulator", False):
+            # host batch (50 MB of fp32 images): upload over a copy stream into one of two staging buffers, so that batch
+            # k+1 crosses PCIe while step k computes; the compute stream only does a device-to-device copy
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=ops.device)
+                self._stage = [torch.empty_like(self.s_real) for _ in range(2)]
+                self._stage_free, self._stage_i = [None, None], 0
+            i = self._stage_i
+            self._stage_i ^= 1
+            cur = torch.cuda.current_stream(ops.device)
+            with torch.cuda.stream(self._copy_stream):
+                if self._stage_free[i] is not None:
+                    self._copy_stream.wait_event(self._stage_free[i])
+                self._stage[i].copy_(real_nchw, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(self._copy_stream)
+            cur.wait_event(up)
+            self.s_real.copy_(self._stage[i], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._stage_free[i] = done
+        else:
+            self.s_real.copy_(real_nchw, non_blocking=True)
+        for dst, src in ((self.d.tem_all[:B], tem), (self.d.tem_all[B:], tem_mis), (self.s_z, z),
                          (self.s_e1, eps_ca1), (self.s_e2, eps_ca2), (self.s_egp, eps_gp)):
             dst.copy_(src, non_blocking=True)
 
