@@ -276,6 +276,26 @@ class Stage2Engine:
         st2 = self.ca2.forward(tem, eps_ca2, None)                  # :130
         self.g2.forward(st2.c_hat, training=True)                   # :131 -> critic group 1
 
+    def preview(self, tem, z, eps_ca1, eps_ca2):
+        """The in-loop sample of stage_2_train_fn.py:181-195: con_augment_1 -> gen_1 (eval) -> con_augment_2 -> gen_2, with
+        gen_2 still in TRAIN mode as in the reference (batch statistics, running statistics updated, :90 is never undone).
+        Returns (fake_64, fake_256) as fp32 NCHW tensors.  Overwrites the generator's activations and the critic's fake
+        image buffer, which the next train step recomputes anyway."""
+        ops, B = self.ops, self.B
+        tem_d = self.d.tem_all[:B]
+        tem_d.copy_(tem, non_blocking=True)
+        f32 = ops.f32
+        dv = lambda t: t.to(device=ops.device, dtype=f32, non_blocking=True).contiguous()
+        self.ca1.forward(tem_d, dv(eps_ca1), dv(z), cg=self.g1.cg)
+        self.g1.forward(training=False)
+        st2 = self.ca2.forward(tem_d, dv(eps_ca2), None)
+        self.g2.forward(st2.c_hat, training=True)
+        out64 = ops.empty((B, 3, self.g1.out.shape[1], self.g1.out.shape[2]), f32)
+        out256 = ops.empty((B, 3, 256, 256), f32)
+        ops.nhwc_to_nchw(self.g1.out, out64)
+        ops.nhwc_to_nchw(self.g2.out, out256)
+        return out64, out256
+
     def _generator_backward(self, dfake, kl_scale):
         """Back-propagate d loss / d fake_256 into G2 and CA2 (accumulating)."""
         ops = self.ops

@@ -26,7 +26,8 @@ z_dim = Z_DIM
 
 def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_size,
             bucket_name="data-and-checkpoints-bucket", start_epoch=0, save_dir="./checkpoints/Stage2",
-            stage1_checkpoint="./checkpoints/Stage1/latest_checkpoint_stage1.pth", log=print, use_graph=True, engine=None):
+            stage1_checkpoint="./checkpoints/Stage1/latest_checkpoint_stage1.pth", log=print, use_graph=True, engine=None,
+            preview_every=100, preview_dir=None):
     textEncoder, projection_head, con_augment_1, con_augment_2, gen_1, critic_2, gen_2 = models
     opt_con_augment_2, opt_critic_2, opt_gen_2 = optimizers
     lr_scheduler_con_augment_2, lr_scheduler_critic_2, lr_scheduler_gen_2 = schedulers
@@ -68,6 +69,7 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 
+    preview_step = 0                                                    # :33 (`step`)
     for epoch in range(start_epoch, num_epochs):
         for batch_idx, (tokenized_texts, real_img_256) in enumerate(loader):
             # pageable host tensors are copied synchronously with the stream (the host would wait for the previous
@@ -94,10 +96,28 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
             eng.d.fp.set_lr(opt_critic_2.param_groups[0]["lr"])
             eng.g2.fp.set_lr(opt_gen_2.param_groups[0]["lr"])
             eng.ca2.fp.set_lr(opt_con_augment_2.param_groups[0]["lr"])
-            if rank == 0 and batch_idx % 100 == 0 and batch_idx > 0:    # :175-179
+            if rank == 0 and batch_idx % preview_every == 0 and batch_idx > 0:    # :175-212
                 losses = eng.losses.tolist()
                 log(f"Epoch [{epoch}/{num_epochs}] Batch {batch_idx}/{len(loader)} "
                     f"Loss D: {losses[0]:.4f}, loss G: {losses[2]:.4f}")
+                # the fixed-noise preview of :181-195 (gen_2 in train mode, like the reference) and the two scalars of
+                # :208-210; instead of TensorBoard event files on GCS (:36-38) they go to save_dir/previews
+                fixed_generator = torch.Generator().manual_seed(456)                                   # :186
+                fixed_noise = torch.randn(batch_size, z_dim, generator=fixed_generator)                # :187-189
+                e1 = torch.randn(batch_size, con_augment_1.c_dim, device=dev)                          # con_augment.py:20
+                e2 = torch.randn(batch_size, con_augment_2.c_dim, device=dev)
+                fake_64, fake_256 = eng.preview(tem.float(), fixed_noise, e1, e2)
+                pdir = preview_dir or os.path.join(save_dir, "previews")
+                os.makedirs(pdir, exist_ok=True)
+                img = fake_256[0]                                                                       # :200 (first image)
+                lo, hi = img.min(), img.max()
+                img = ((img - lo) / (hi - lo).clamp_min(1e-5)).cpu()                                    # make_grid(normalize=True)
+                torch.save({"epoch": epoch, "batch": batch_idx, "step": preview_step, "fake_256": img,
+                            "critic_2_loss": losses[0], "generator_2_loss": losses[2]},
+                           os.path.join(pdir, f"preview_{preview_step:06d}.pt"))
+                with open(os.path.join(pdir, "scalars.csv"), "a") as f:
+                    f.write(f"{preview_step},{epoch},{batch_idx},{losses[0]},{losses[2]}\n")
+                preview_step += 1                                                                       # :211
         if rank == 0 and epoch % 10 == 0:                               # :214-235
             checkpoint = {
                 "con_augment_2": con_augment_2.state_dict(), "critic_2": critic_2.state_dict(), "gen_2": gen_2.state_dict(),

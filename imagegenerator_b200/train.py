@@ -93,7 +93,7 @@ def build(device, text_encoder=None, n_rows=4096):
 
 
 def run(stage, device, epochs=num_epochs, batch=batch_size, loader=None, text_encoder=None, save_dir="./checkpoints",
-        synthetic=0, log=print, use_graph=True):
+        synthetic=0, log=print, use_graph=True, preview_every=100):
     n_rows = 4096
     m, o, s = build(device, text_encoder, n_rows)
     if loader is None:
@@ -107,7 +107,7 @@ def run(stage, device, epochs=num_epochs, batch=batch_size, loader=None, text_en
     keys = ["con_augment_2", "critic_2", "gen_2"]
     models = [m[k] for k in ("textEncoder", "projection_head", "con_augment_1", "con_augment_2", "gen_1", "critic_2", "gen_2")]
     return train_2(models, [o[k] for k in keys], [s[k] for k in keys], loader, epochs, device, batch,
-                   save_dir=os.path.join(save_dir, "Stage2"), log=log, use_graph=use_graph,
+                   save_dir=os.path.join(save_dir, "Stage2"), log=log, use_graph=use_graph, preview_every=preview_every,
                    stage1_checkpoint=os.path.join(save_dir, "Stage1", "latest_checkpoint_stage1.pth")), m
 
 

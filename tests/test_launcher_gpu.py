@@ -25,7 +25,12 @@ def test_stage1_then_stage2_with_checkpoints(tmp_path):
     assert len(logs) == 3 and all("Loss D" in l for l in logs)
     g1_trained = {k: v.clone() for k, v in m1["gen_1"].state_dict().items()}
 
-    eng2, m2 = T.run(2, dev, epochs=1, batch=2, save_dir=save, synthetic=2, log=logs.append)
+    eng2, m2 = T.run(2, dev, epochs=1, batch=2, save_dir=save, synthetic=2, log=logs.append, preview_every=1)
+    # the fixed-noise preview + scalars of stage_2_train_fn.py:181-212 (written for batch 1; batch 0 is skipped like :175)
+    pv = torch.load(os.path.join(save, "Stage2", "previews", "preview_000000.pt"), weights_only=False)
+    assert pv["fake_256"].shape == (3, 256, 256) and float(pv["fake_256"].min()) >= 0.0 and float(pv["fake_256"].max()) <= 1.0
+    assert torch.isfinite(pv["fake_256"]).all() and pv["batch"] == 1
+    assert open(os.path.join(save, "Stage2", "previews", "scalars.csv")).read().count("\n") == 1
     for k, v in m2["gen_1"].state_dict().items():                              # frozen Stage-I generator = the trained one
         assert torch.equal(v.cpu(), g1_trained[k].cpu()), k
     ck2 = torch.load(os.path.join(save, "Stage2", "latest_checkpoint_stage2.pth"), map_location="cpu", weights_only=False)
