@@ -12,7 +12,10 @@ inside the engines (pjrt.broadcast_master_param, :78-85); checkpoints go to ``--
 
 The text side (SpanBERT + COCO captions, train.py:68, data_loader.py) needs weights and data this box does not
 have: ``--synthetic N`` trains on N random batches (a fixed embedding table stands in for the encoder's CLS state),
-which is what the tests and benchmarks use.  Pass your own ``(textEncoder, loader)`` to ``run`` for real data.
+which is what the benchmarks use.  With the files on local disk, ``--coco-root DIR --ann-file captions.json
+--tokenizer DIR --text-encoder DIR`` runs the reference's real pipeline (``data_loader.get_loader`` + a BERT encoder
+trained through ``d lossG / d tem``, stage_1_train_fn.py:161-171); ``--text-encoder spanbert-random`` gives the same
+architecture with random weights.
 """
 import argparse
 import os
@@ -57,6 +60,31 @@ class SyntheticEncoder(nn.Module):
         return o
 
 
+def load_text_encoder(spec=None, n_rows=4096):
+    """``train.py:68``'s ``AutoModel.from_pretrained("SpanBERT/spanbert-base-cased")`` without a network: ``None`` ->
+    the synthetic table above; ``"spanbert-random"`` -> a randomly initialised BERT of SpanBERT-base-cased's shape
+    (12 layers, 768 hidden, 12 heads, vocabulary 28996); anything else -> a local directory for ``AutoModel``;
+    a module passes through."""
+    if spec is None:
+        return SyntheticEncoder(n_rows)
+    if isinstance(spec, nn.Module):
+        return spec
+    if spec == "spanbert-random":
+        from transformers import BertConfig, BertModel
+        return BertModel(BertConfig(vocab_size=28996, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                                    intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2),
+                         add_pooling_layer=False)
+    from transformers import AutoModel
+    return AutoModel.from_pretrained(spec, local_files_only=True)
+
+
+def image_transform(hw):
+    """``my_transform_1`` / ``my_transform_2`` of train.py:40-54."""
+    import torchvision.transforms as transforms
+    return transforms.Compose([transforms.ToTensor(), transforms.Resize((hw, hw)),
+                               transforms.Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])
+
+
 class SyntheticLoader:
     """``n_batches`` batches shaped like the reference loader's items (data_loader.py:64-108): a dict of tensors for
     the text encoder and an image batch normalised to (-1, 1) (train.py:40-54)."""
@@ -77,7 +105,7 @@ def build(device, text_encoder=None, n_rows=4096):
     """Models, optimizers and schedulers in the reference's order (train.py:66-113)."""
     torch.manual_seed(42)
     m = {}
-    m["textEncoder"] = (text_encoder if text_encoder is not None else SyntheticEncoder(n_rows)).to(device)
+    m["textEncoder"] = load_text_encoder(text_encoder, n_rows).to(device)
     m["projection_head"] = nn.Linear(768, TEM_SIZE).to(device)
     m["con_augment_1"] = ConditioningAugmentation(TEM_SIZE, 256, c_dim)
     m["critic_1"] = StageIDiscriminator(TEM_SIZE, Nd)
@@ -118,13 +146,25 @@ def main():
     ap.add_argument("--batch-size", type=int, default=batch_size)
     ap.add_argument("--save-dir", default="./checkpoints")
     ap.add_argument("--synthetic", type=int, default=0, help="train on N random batches instead of the COCO loader")
+    ap.add_argument("--coco-root", help="directory with the images (train.py:118 'dataset/train2017', on local disk)")
+    ap.add_argument("--ann-file", help="COCO captions JSON (train.py:119)")
+    ap.add_argument("--tokenizer", help="local directory with the SpanBERT tokenizer files")
+    ap.add_argument("--text-encoder", help="local directory with the SpanBERT weights, or 'spanbert-random'")
+    ap.add_argument("--num-workers", type=int, default=8)
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device(f"cuda:{local}")
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         dist.init_process_group("nccl", device_id=device)
-    run(args.stage, device, args.epochs, args.batch_size, save_dir=args.save_dir, synthetic=args.synthetic)
+    loader = None
+    if args.coco_root:
+        from .data_loader import get_loader
+        loader = get_loader("local", args.coco_root, args.ann_file, image_transform(64 if args.stage == 1 else 256),
+                            batch_size=args.batch_size, shuffle=True, tokenizer=args.tokenizer,
+                            num_workers=args.num_workers)
+    run(args.stage, device, args.epochs, args.batch_size, loader=loader, text_encoder=args.text_encoder,
+        save_dir=args.save_dir, synthetic=args.synthetic)
     if dist.is_initialized():
         dist.destroy_process_group()
 

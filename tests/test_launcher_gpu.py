@@ -41,3 +41,36 @@ def test_stage1_then_stage2_with_checkpoints(tmp_path):
     assert any("Loaded checkpoint" in l for l in logs)
     for k, v in m3["gen_2"].state_dict().items():
         assert torch.equal(v.cpu(), ck2["gen_2"][k]), k
+
+
+def test_stage1_on_captions_with_a_bert_encoder(tmp_path):
+    """f3: the reference's real pipeline shape -- COCO-style files -> tokenizer -> BERT CLS state -> projection head ->
+    train_1 -- with the encoder and the head trained through d lossG / d tem (stage_1_train_fn.py:117-119, :161-171)."""
+    from _util import make_coco_dir, tiny_bert
+    from imagegenerator_b200 import train as T
+    from imagegenerator_b200.data_loader import get_loader
+    dev = torch.device("cuda:0")
+    root, ann, tok, _ = make_coco_dir(tmp_path, n_images=6, captions_per_image=2)
+    loader = get_loader("local", root, ann, T.image_transform(64), batch_size=4, shuffle=True, tokenizer=tok,
+                        num_workers=2, prefetch_factor=2)
+    enc = tiny_bert(tok)
+    before = {k: v.clone() for k, v in enc.state_dict().items()}
+    logs = []
+    save = str(tmp_path / "ck")
+    eng, m = T.run(1, dev, epochs=1, batch=4, loader=loader, text_encoder=enc, save_dir=save, log=logs.append)
+    assert len(logs) == 3 and all("Loss D" in l for l in logs)               # 12 captions / 4, drop_last
+    assert torch.isfinite(eng.losses).all()
+    after = m["textEncoder"].state_dict()
+    moved = [k for k, v in before.items() if v.is_floating_point() and not torch.equal(v, after[k].cpu())]
+    assert "embeddings.word_embeddings.weight" in moved and len(moved) > 10  # AdamW stepped on the encoder
+    ck = torch.load(os.path.join(save, "Stage1", "latest_checkpoint_stage1.pth"), map_location="cpu", weights_only=False)
+    assert set(ck["textEncoder"]) == set(before)
+    # Stage-II reads the same loader items at 256x256 and keeps the text side frozen (stage_2_train_fn.py:52-63)
+    loader2 = get_loader("local", root, ann, T.image_transform(256), batch_size=2, shuffle=True, tokenizer=tok,
+                         num_workers=0)
+    enc2 = tiny_bert(tok)
+    eng2, m2 = T.run(2, dev, epochs=1, batch=2, loader=loader2, text_encoder=enc2, save_dir=save, log=logs.append,
+                     preview_every=10 ** 9)
+    assert torch.isfinite(eng2.losses).all()
+    for k, v in m2["textEncoder"].state_dict().items():                       # restored from the Stage-I checkpoint
+        assert torch.equal(v.cpu(), ck["textEncoder"][k]), k
