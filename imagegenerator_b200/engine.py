@@ -160,6 +160,9 @@ class GenRT:
         self.dcg = ops.empty((B, 1, 1, self.layers[0].co))
         h = 1
         self.y, self.a, self.dy, self.da, self.mr, self.stats, self.sums = [], [], [], [], [], [], []
+        # BN statistics accumulators of all layers in one buffer: one memset per forward instead of one per layer
+        self.stats_flat = ops.zeros((2 * sum(L.ci for L in self.layers if L.bn is not None),), ops.f64)
+        soff = 0
         for L in self.layers:
             h = (h - 1) * L.s - 2 * L.p + L.k
             shp = (B, h, h, L.ci)
@@ -167,7 +170,8 @@ class GenRT:
                 self.y.append(ops.empty(shp)); self.a.append(ops.empty(shp))
                 self.dy.append(ops.empty(shp)); self.da.append(ops.empty(shp))
                 self.mr.append(ops.empty((1, L.ci, 2), ops.f32))
-                self.stats.append(ops.zeros((1, L.ci, 2), ops.f64))
+                self.stats.append(self.stats_flat[soff:soff + 2 * L.ci].view(1, L.ci, 2))
+                soff += 2 * L.ci
                 self.sums.append(ops.zeros((1, L.ci, 2), ops.f64))
             else:
                 self.out = out if out is not None else ops.empty(shp)
@@ -188,6 +192,8 @@ class GenRT:
     def forward(self, training=True):
         ops = self.ops
         x = self.cg
+        if training:
+            ops.zero(self.stats_flat)
         for i, L in enumerate(self.layers):
             if L.bn is None:
                 # ConvT(C -> 3) + Tanh: 1x1 GEMM onto the 48 (channel, tap) columns, then col2im
@@ -197,7 +203,6 @@ class GenRT:
             bn = L.bn
             if training:
                 # conv + BN batch statistics in one kernel (reduced in the tcgen05 epilogue when the shape allows)
-                ops.zero(self.stats[i])
                 ops.conv_dgrad_stats(x, L.pd, self.y[i], self.stats[i], 1, L.k, L.s, L.p)
                 n = self.y[i].numel() // L.ci
                 ops.bn_finalize(self.stats[i], n, self.mr[i], bn.running_mean, bn.running_var,
@@ -254,6 +259,10 @@ class CriticRT:
         self.mr, self.stats, self.sums = [None], [None], [None]
         # gradient-penalty chain buffers (one group)
         self.gda, self.gdy, self.gsums, self.tsums, self.v, self.w, self.gy = [None], [], [None], [None], [], [None], [None]
+        # BN statistics accumulators of all layers in one buffer (consumed by bn_finalize right after each conv): one
+        # memset per forward instead of one per layer
+        self.stats_flat = ops.zeros((2 * G * sum(L.co for L in self.layers[1:]),), f64)
+        soff = 0
         for l, L in enumerate(self.layers):
             h = _conv_out(h, L.k, L.s, L.p)
             shp, shp1 = (G * B, h, h, L.co), (B, h, h, L.co)
@@ -267,7 +276,8 @@ class CriticRT:
             if l > 0:
                 self.y.append(ops.empty(shp))
                 self.mr.append(ops.empty((G, L.co, 2), f32))
-                self.stats.append(ops.zeros((G, L.co, 2), f64))
+                self.stats.append(self.stats_flat[soff:soff + 2 * G * L.co].view(G, L.co, 2))
+                soff += 2 * G * L.co
                 self.sums.append(ops.zeros((G, L.co, 2), f64))
                 self.gsums.append(ops.zeros((1, L.co, 2), f64))
                 self.tsums.append(ops.zeros((L.co, 3), f64))
@@ -285,8 +295,9 @@ class CriticRT:
         self.colf = ops.empty(((G - 1) * B, h1, h1, self.K0), f32)      # col2im input of d/d image (<= 2 groups)
         self.pf0 = ops.empty((L0.co, 1, 1, self.K0))
         cl, Nd = self.layers[-1].co, module.Nd
-        self.A, self.dA = ops.empty((16, cl), f32), ops.zeros((16, cl), f32)
-        self.Bv, self.dBv = ops.empty((Nd,), f32), ops.zeros((Nd,), f32)
+        self.head_grads = ops.zeros((16 * cl + Nd,), f32)            # dA and dBv: zeroed together every iteration
+        self.A, self.dA = ops.empty((16, cl), f32), self.head_grads[:16 * cl].view(16, cl)
+        self.Bv, self.dBv = ops.empty((Nd,), f32), self.head_grads[16 * cl:]
         self.c0, self.dc0 = ops.empty((1,), f32), ops.zeros((1,), f32)
         self.tem_all = ops.empty((2 * B, module.tem_size), f32)     # rows [0,B) tem, [B,2B) mismatched
         self.ce = ops.empty((2 * B, Nd), f32)
@@ -338,6 +349,8 @@ class CriticRT:
         gv = lambda t: self.group_view(t, g0, ng)
         L0 = self.layers[0]
         ops.patchify(gv(self.a[0]), gv(self.P), L0.k, L0.s, L0.p)
+        if training:
+            ops.zero(self.stats_flat)
         if before_weights is not None:
             before_weights()
         ops.conv_fprop(gv(self.P), self.pf0, L0.conv.bias.data, gv(self.a[1]), 1, 1, 0, act=ACT_LRELU)
@@ -347,7 +360,6 @@ class CriticRT:
             mr = self.mr[l][g0:g0 + ng]
             if training:
                 st = self.stats[l][g0:g0 + ng]
-                ops.zero(st)
                 ops.conv_fprop_stats(gv(self.a[l]), L.pf, y, st, ng, L.k, L.s, L.p)
                 ops.bn_finalize(st, y.numel() // (ng * L.co), mr, bn.running_mean, bn.running_var,
                                 bn.num_batches_tracked, dup_first, True)
@@ -626,7 +638,7 @@ class Stage1Engine:
             self.gen_side.run(lambda: self._generate(*next_noise))
             self._fake_ready = True
         ops.zero(d.fp.grad)                                      # :146
-        ops.zero(d.dA); ops.zero(d.dBv)
+        ops.zero(d.head_grads)                                   # dA, dBv
         d.gp_first_order()                                       # utils.py:15-24
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])   # :140-144
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)

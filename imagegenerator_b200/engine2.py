@@ -310,7 +310,7 @@ class Stage2Engine:
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,        # :133-140 + utils.py:13
                   before_weights=self.pack_side.join)
         ops.zero(d.fp.grad)                                         # :153
-        ops.zero(d.dA); ops.zero(d.dBv)
+        ops.zero(d.head_grads)                                      # dA, dBv
         d.gp_first_order()
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])     # :148-152
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
