@@ -424,18 +424,24 @@ __global__ void nhwc_to_nchw_kernel(const T* src, float* dst, int N, int C, int6
         for (int c = 0; c < C; ++c) d[(int64_t)c * HW] = ldf(s + c);
     }
 }
+// w[co][ci][t] (fp32 master) -> pf[co][t][ci] and pd[ci][t][co] in the storage type.  A thread owns one (co, ci) pair
+// and reads its kk contiguous taps; blockIdx.y = 0 runs with ci fastest across threads (pf stores coalesced), = 1 with
+// co fastest (pd stores coalesced) -- element-order stores were 2-byte scatters at stride Ci / Co (32 us for the 2 M
+// element critic layer, on the path between the optimizer step and the next forward).
 template <typename T>
-__global__ void pack_weight_kernel(const float* w, T* pf, T* pd, int Co, int Ci, int kk) {
-    int64_t total = (int64_t)Co * Ci * kk;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        int t = (int)(i % kk);
-        int64_t r = i / kk;
-        int ci = (int)(r % Ci);
-        int co = (int)(r / Ci);
-        float v = w[i];
-        if (pf) stf(pf + ((int64_t)co * kk + t) * Ci + ci, v);
-        if (pd) stf(pd + ((int64_t)ci * kk + t) * Co + co, v);
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, T* __restrict__ pf,
+                                                          T* __restrict__ pd, int Co, int Ci, int kk, int first_dir) {
+    const int dir = first_dir + blockIdx.y;
+    const int64_t pairs = (int64_t)Co * Ci;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        int co, ci;
+        if (dir == 0) { co = (int)(i / Ci); ci = (int)(i - (int64_t)co * Ci); }
+        else          { ci = (int)(i / Co); co = (int)(i - (int64_t)ci * Co); }
+        const float* src = w + ((int64_t)co * Ci + ci) * kk;
+        T* dst = dir == 0 ? pf + (int64_t)co * kk * Ci + ci : pd + (int64_t)ci * kk * Co + co;
+        const int64_t ds = dir == 0 ? Ci : Co;
+        for (int t = 0; t < kk; ++t) stf(dst + t * ds, src[t]);
     }
 }
 
@@ -866,9 +872,11 @@ int sg_fold_grad_cl(float* gw, float* dw, int Co, int Ci, int kk, void* stream) 
 }
 
 int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream) {
-    int64_t n = (int64_t)Co * Ci * kk;
-    SG_DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(w, (T*)pf, (T*)pd, Co,
-                                                                                                   Ci, kk)));
+    if (!pf && !pd) return 0;
+    int64_t n = (int64_t)Co * Ci;
+    dim3 grid(grid_for(n, 256), (pf && pd) ? 2 : 1);
+    SG_DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid, 256, 0, SG_STREAM(stream)>>>(w, (T*)pf, (T*)pd, Co, Ci, kk,
+                                                                                      pf ? 0 : 1)));
     SG_LAUNCHED("pack_weight");
     return 0;
 }

@@ -123,6 +123,12 @@ def test_layout_and_pack(mode):
     run_pair(mode, "nhwc_to_nchw", [T(rnd(3, 8, 12, 5)), F(torch.zeros(3, 5, 8, 12))], [1])
     w = rnd(24, 10, 4, 4)
     run_pair(mode, "pack_weight", [F(w), T(torch.zeros(24, 4, 4, 10)), T(torch.zeros(10, 4, 4, 24))], [1, 2])
+    for Co, Ci, k in ((512, 256, 4), (320, 640, 3), (64, 48, 1), (37, 70, 3)):      # both store directions, every tap count
+        w = rnd(Co, Ci, k, k)
+        run_pair(mode, "pack_weight", [F(w), T(torch.zeros(Co, k, k, Ci)), T(torch.zeros(Ci, k, k, Co))], [1, 2],
+                 tol=dict(rtol=0, atol=0))                                           # a rounding + a permutation: exact
+        run_pair(mode, "pack_weight", [F(w), T(torch.zeros(Co, k, k, Ci)), None], [1], tol=dict(rtol=0, atol=0))
+        run_pair(mode, "pack_weight", [F(w), None, T(torch.zeros(Ci, k, k, Co))], [2], tol=dict(rtol=0, atol=0))
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -199,8 +205,8 @@ def test_bn_eval_mr(mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32"])
-def test_linear(mode):
-    N, K, M = 9, 512, 256
+@pytest.mark.parametrize("N,K,M", [(9, 512, 256), (256, 512, 128), (128, 256, 128), (70, 300, 37)])
+def test_linear(mode, N, K, M):
     x, w, b = rnd(N, K), rnd(M, K, scale=K ** -0.5), rnd(M)
     ea, _ = run_pair(mode, "linear_fwd", [F(x), F(w), F(b), F(torch.zeros(N, M))], [3], dict(relu=True))
     h = ea[3].float()
