@@ -98,25 +98,86 @@ static Chunking make_chunking(int64_t rows_per_group, int C, int groups, int wav
 static inline float act_slope(int act) { return act == SG_ACT_RELU ? 0.f : (act == SG_ACT_LRELU ? 0.1f : 1.f); }
 
 // ---- out = act((y - mean) * rstd*gamma + beta [+ residual])
-template <typename T>
+// FIN = true: the batch statistics are still raw sums (BnFinalize::stats, straight out of the conv epilogue).  Every CTA
+// turns the sums of the image groups it touches into (mean, rstd*gamma, beta) in shared memory; CTA 0 also does what the
+// separate sg_bn_finalize launch did (writes mr for the backward pass, updates the running statistics) -- one launch and
+// one kernel-to-kernel dependency less per BatchNorm layer.
+struct BnFinalize {
+    const double* stats;
+    double count;
+    float* mr;
+    float* rm;
+    float* rv;
+    long long* nbt;
+    int dup_first, update_running, G;
+    float momentum, eps;
+};
+__device__ __forceinline__ void bn_mean_var(const double* stats, int64_t gc, double count, double& mean, double& var) {
+    const double s = stats[gc * 2], q = stats[gc * 2 + 1];
+    mean = s / count;
+    var = q / count - mean * mean;
+    if (var < 0) var = 0;
+}
+template <typename T, bool FIN>
 __global__ void __launch_bounds__(256, 2)
 bn_act8_kernel(const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
-               const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out, Chunking k, int act) {
+               const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out, Chunking k, int act,
+               BnFinalize f) {
     SG_PDL_SYNC();
-    if ((int)threadIdx.x >= k.active) return;
+    extern __shared__ float fin_sm[];                // FIN: [groups of this CTA][C][3]
+    const int C = k.CV * 8;
     int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
     int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
     if (end > k.nvec) end = k.nvec;
+    int gbase = 0;
+    if (FIN) {
+        int g_lo = (int)(((int64_t)blockIdx.x * k.chunk) / k.gvec), g_hi = (int)((end - 1) / k.gvec);
+        if (blockIdx.x == 0) { g_lo = 0; g_hi = f.G - 1; }
+        gbase = g_lo;
+        for (int idx = threadIdx.x; idx < (g_hi - g_lo + 1) * C; idx += 256) {
+            const int c = idx % C;
+            const int64_t gc = (int64_t)g_lo * C + idx;
+            double mean, var;
+            bn_mean_var(f.stats, gc, f.count, mean, var);
+            const float mf = (float)mean, rf = (float)(1.0 / sqrt(var + (double)f.eps));
+            fin_sm[idx * 3] = mf; fin_sm[idx * 3 + 1] = rf * gamma[c]; fin_sm[idx * 3 + 2] = beta[c];
+            if (blockIdx.x == 0) { f.mr[gc * 2] = mf; f.mr[gc * 2 + 1] = rf; }
+        }
+        if (blockIdx.x == 0 && f.update_running) {
+            if (threadIdx.x == 0 && f.nbt) *f.nbt += f.dup_first + f.G - 1;
+            for (int c = threadIdx.x; c < C; c += 256) {
+                float m_run = f.rm[c], v_run = f.rv[c];
+                for (int g = 0; g < f.G; ++g) {
+                    double mean, var;
+                    bn_mean_var(f.stats, (int64_t)g * C + c, f.count, mean, var);
+                    const float unb = (float)(var * f.count / (f.count > 1 ? f.count - 1 : 1));
+                    const int reps = g == 0 ? f.dup_first : 1;
+                    for (int r = 0; r < reps; ++r) {
+                        m_run = (1.f - f.momentum) * m_run + f.momentum * (float)mean;
+                        v_run = (1.f - f.momentum) * v_run + f.momentum * unb;
+                    }
+                }
+                f.rm[c] = m_run; f.rv[c] = v_run;
+            }
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x >= k.active) return;
     if (i >= end) return;
-    const int c0 = ((int)threadIdx.x % k.CV) * 8, C = k.CV * 8;
+    const int c0 = ((int)threadIdx.x % k.CV) * 8;
     int g = (int)(i / k.gvec);
     int64_t next = (int64_t)(g + 1) * k.gvec;
     float m[8], rg[8], b[8];
     auto load = [&](int gg) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float* q = mr + ((int64_t)gg * C + c0 + j) * 2;
-            m[j] = q[0]; rg[j] = q[1] * gamma[c0 + j]; b[j] = beta[c0 + j];
+            if (FIN) {
+                const float* q = fin_sm + ((int64_t)(gg - gbase) * C + c0 + j) * 3;
+                m[j] = q[0]; rg[j] = q[1]; b[j] = q[2];
+            } else {
+                const float* q = mr + ((int64_t)gg * C + c0 + j) * 2;
+                m[j] = q[0]; rg[j] = q[1] * gamma[c0 + j]; b[j] = beta[c0 + j];
+            }
         }
     };
     load(g);
@@ -454,9 +515,24 @@ template <typename T>
 int bn_act8(const void* y, const float* mr, const float* gamma, const float* beta, const void* res, void* out,
             int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {
     Chunking k = make_chunking(rows_per_group, C, groups, 8);
-    launch_pdl(bn_act8_kernel<T>, dim3(k.blocks), dim3(256), 0, st, (const T*)y, mr, gamma, beta, (const T*)res, (T*)out, k, act);
+    launch_pdl(bn_act8_kernel<T, false>, dim3(k.blocks), dim3(256), 0, st, (const T*)y, mr, gamma, beta, (const T*)res, (T*)out, k, act,
+               BnFinalize{});
     g_launches.fetch_add(1);
     return check_launch("bn_act8");
+}
+// finalize + apply in one launch; returns -1 (nothing launched) when the per-CTA table would not fit
+template <typename T>
+int bn_finalize_act8(const double* stats, double count, float* mr, float* rm, float* rv, long long* nbt, int dup_first,
+                     int update_running, float momentum, float eps, const void* y, const float* gamma, const float* beta,
+                     const void* res, void* out, int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {
+    Chunking k = make_chunking(rows_per_group, C, groups, 8);
+    size_t smem = (size_t)groups * C * 3 * sizeof(float);
+    if (smem > 40 * 1024) return -1;
+    BnFinalize f{stats, count, mr, rm, rv, nbt, dup_first, update_running, groups, momentum, eps};
+    launch_pdl(bn_act8_kernel<T, true>, dim3(k.blocks), dim3(256), smem, st, (const T*)y, (const float*)nullptr, gamma, beta, (const T*)res,
+               (T*)out, k, act, f);
+    g_launches.fetch_add(1);
+    return check_launch("bn_finalize_act8");
 }
 template <typename T>
 int bn_bwd_reduce8(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta,
@@ -504,6 +580,8 @@ template int bn_bwd_reduce8<float>(const void*, const void*, const void*, const 
 template int bn_bwd_reduce8<bf16>(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
 template int bn_bwd_apply8<float>(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
 template int bn_bwd_apply8<bf16>(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_finalize_act8<float>(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_finalize_act8<bf16>(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
 template int act_bwd8<float>(const void*, const void*, void*, int64_t, int, cudaStream_t);
 template int act_bwd8<bf16>(const void*, const void*, void*, int64_t, int, cudaStream_t);
 

@@ -719,6 +719,7 @@ __global__ void ca_bwd_seed_kernel(const T* dcg, const float* eps, const float* 
 
 // 8-wide kernels of bn_fast.cu (C % 8 == 0)
 template <typename T> int bn_act8(const void*, const float*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int bn_finalize_act8(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int bn_bwd_reduce8(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
@@ -926,6 +927,23 @@ int sg_bn_act(const void* y, const float* mr, const float* gamma, const float* b
         e = launch_ew4(f, n, SG_STREAM(stream), "bn_act");
     });
     return e;
+}
+
+int sg_bn_finalize_act(const double* stats, int64_t count, float* mr, float* running_mean, float* running_var, int64_t* nbt,
+                       int dup_first, int update_running, float momentum, float eps, const void* y, const float* gamma,
+                       const float* beta, const void* residual, void* out, int64_t rows_per_group, int C, int groups, int act,
+                       int dtype, void* stream) {
+    if (C % 8 == 0 && C <= 2048) {
+        int e = 0;
+        SG_DISPATCH_T(dtype, e = bn_finalize_act8<T>(stats, (double)count, mr, running_mean, running_var, (long long*)nbt,
+                                                     dup_first, update_running, momentum, eps, y, gamma, beta, residual, out,
+                                                     rows_per_group, C, groups, act, SG_STREAM(stream)));
+        if (e >= 0) return e;
+    }
+    int e = sg_bn_finalize(stats, count, mr, running_mean, running_var, nbt, dup_first, update_running, momentum, eps, groups,
+                           C, stream);
+    if (e) return e;
+    return sg_bn_act(y, mr, gamma, beta, residual, out, rows_per_group, C, groups, act, dtype, stream);
 }
 
 int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const float* mr, double* sums,

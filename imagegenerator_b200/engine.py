@@ -205,12 +205,12 @@ class GenRT:
                 # conv + BN batch statistics in one kernel (reduced in the tcgen05 epilogue when the shape allows)
                 ops.conv_dgrad_stats(x, L.pd, self.y[i], self.stats[i], 1, L.k, L.s, L.p)
                 n = self.y[i].numel() // L.ci
-                ops.bn_finalize(self.stats[i], n, self.mr[i], bn.running_mean, bn.running_var,
-                                bn.num_batches_tracked, 1, True)
+                ops.bn_finalize_act(self.stats[i], n, self.mr[i], bn.running_mean, bn.running_var,
+                                    bn.num_batches_tracked, 1, self.y[i], bn.weight.data, bn.bias.data, self.a[i], ACT_RELU)
             else:
                 ops.conv_dgrad(x, L.pd, None, self.y[i], L.k, L.s, L.p)
                 ops.bn_eval_mr(bn.running_mean, bn.running_var, self.mr[i])
-            ops.bn_act(self.y[i], self.mr[i], bn.weight.data, bn.bias.data, self.a[i], 1, ACT_RELU)
+                ops.bn_act(self.y[i], self.mr[i], bn.weight.data, bn.bias.data, self.a[i], 1, ACT_RELU)
             x = self.a[i]
         return self.out
 
@@ -361,13 +361,14 @@ class CriticRT:
             if training:
                 st = self.stats[l][g0:g0 + ng]
                 ops.conv_fprop_stats(gv(self.a[l]), L.pf, y, st, ng, L.k, L.s, L.p)
-                ops.bn_finalize(st, y.numel() // (ng * L.co), mr, bn.running_mean, bn.running_var,
-                                bn.num_batches_tracked, dup_first, True)
+                ops.bn_finalize_act(st, y.numel() // (ng * L.co), mr, bn.running_mean, bn.running_var,
+                                    bn.num_batches_tracked, dup_first, y, bn.weight.data, bn.bias.data,
+                                    gv(self.a[l + 1]), ACT_LRELU)
             else:
                 ops.conv_fprop(gv(self.a[l]), L.pf, None, y, L.k, L.s, L.p)
                 for g in range(ng):
                     ops.bn_eval_mr(bn.running_mean, bn.running_var, mr[g:g + 1])
-            ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)
+                ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)
         # head: compressed text, then the collapsed affine score
         nt = 2 * B if with_mismatched else B
         ops.linear_fwd(self.tem_all[:nt], m.compress.weight.data, m.compress.bias.data, self.ce[:nt])

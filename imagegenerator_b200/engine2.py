@@ -42,14 +42,15 @@ def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=Non
             ops.conv_fprop_stats(x, L.pf, buf.y, buf.stats, 1, L.k, L.s, L.p)
         else:
             ops.conv_dgrad_stats(x, L.pd, buf.y, buf.stats, 1, L.k, L.s, L.p)
-        ops.bn_finalize(buf.stats, buf.y.numel() // C, buf.mr, bn.running_mean, bn.running_var, bn.num_batches_tracked, 1, True)
+        ops.bn_finalize_act(buf.stats, buf.y.numel() // C, buf.mr, bn.running_mean, bn.running_var, bn.num_batches_tracked, 1,
+                            buf.y, bn.weight.data, bn.bias.data, out, act, residual=residual)
     else:
         if direction == "f":
             ops.conv_fprop(x, L.pf, None, buf.y, L.k, L.s, L.p)
         else:
             ops.conv_dgrad(x, L.pd, None, buf.y, L.k, L.s, L.p)
         ops.bn_eval_mr(bn.running_mean, bn.running_var, buf.mr)
-    ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
+        ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
 
 def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True):

@@ -57,6 +57,7 @@ _SIGS = {
     "sg_colsum": [_P, _P, _L, _I, _I, _P],
     "sg_col_stats": [_P, _P, _L, _I, _I, _I, _P],
     "sg_bn_finalize": [_P, _L, _P, _P, _P, _P, _I, _I, _F, _F, _I, _I, _P],
+    "sg_bn_finalize_act": [_P, _L, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_eval_mr": [_P, _P, _P, _F, _I, _P],
     "sg_bn_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
@@ -342,6 +343,16 @@ class CudaOps:
         G, C, _ = stats.shape
         self._ck(self.lib.sg_bn_finalize(_ptr(stats), int(count), _ptr(mr), _ptr(running_mean), _ptr(running_var),
                                          _ptr(nbt), dup_first, int(update_running), momentum, eps, G, C, self._st()))
+
+    def bn_finalize_act(self, stats, count, mr, running_mean, running_var, nbt, dup_first, y, gamma, beta, out, act,
+                        residual=None, update_running=True, momentum=0.1, eps=1e-5):
+        """``bn_finalize`` + ``bn_act`` in one launch (training-mode BatchNorm forward from the conv epilogue's sums)."""
+        self._c(stats, mr, running_mean, running_var, nbt, y, gamma, beta, out, residual)
+        G, C, _ = stats.shape
+        self._ck(self.lib.sg_bn_finalize_act(_ptr(stats), int(count), _ptr(mr), _ptr(running_mean), _ptr(running_var),
+                                             _ptr(nbt), dup_first, int(update_running), momentum, eps, _ptr(y), _ptr(gamma),
+                                             _ptr(beta), _ptr(residual), _ptr(out), y.numel() // (C * G), C, G, act,
+                                             self._dt_of(y), self._st()))
 
     def bn_eval_mr(self, running_mean, running_var, mr, eps=1e-5):
         self._c(running_mean, running_var, mr)

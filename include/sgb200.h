@@ -182,6 +182,12 @@ int sg_bn_eval_mr(const float* running_mean, const float* running_var, float* mr
 /* out = act(gamma*(y-mean)*rstd + beta [+ residual]) */
 int sg_bn_act(const void* y, const float* mr, const float* gamma, const float* beta, const void* residual,
               void* out, int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+/* sg_bn_finalize followed by sg_bn_act in ONE launch (the training-mode forward of nn.BatchNorm2d + activation):
+ * every CTA derives (mean, rstd) of the groups it touches from the raw sums, CTA 0 writes mr and the running statistics */
+int sg_bn_finalize_act(const double* stats, int64_t count, float* mr, float* running_mean, float* running_var,
+                       int64_t* nbt, int dup_first, int update_running, float momentum, float eps, const void* y,
+                       const float* gamma, const float* beta, const void* residual, void* out,
+                       int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
 /* sums[G][C][2] (fp64) = (sum dz, sum dz*xhat),  dz = da * act'(a_out) */
 int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const float* mr, double* sums,
                      int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);

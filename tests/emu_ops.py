@@ -185,6 +185,11 @@ class EmuOps:
                 running_var.mul_(1 - momentum).add_(momentum * (var[g] * count / max(count - 1, 1)).to(running_var.dtype))
             nbt += len(order)
 
+    def bn_finalize_act(self, stats, count, mr, running_mean, running_var, nbt, dup_first, y, gamma, beta, out, act,
+                        residual=None, update_running=True, momentum=0.1, eps=1e-5):
+        self.bn_finalize(stats, count, mr, running_mean, running_var, nbt, dup_first, update_running, momentum, eps)
+        self.bn_act(y, mr, gamma, beta, out, stats.shape[0], act, residual)
+
     def bn_eval_mr(self, running_mean, running_var, mr, eps=1e-5):
         mr[0, :, 0] = running_mean.to(mr.dtype)
         mr[0, :, 1] = (1.0 / torch.sqrt(running_var.to(torch.float64) + eps)).to(mr.dtype)
