@@ -8,6 +8,7 @@
 // registers and the inner loop is loads -> a few FMAs per element -> store, no integer division.  A CTA's
 // range touches at most two image groups, so per-channel reductions are combined in shared memory and
 // leave the CTA as one fp64 atomic per (group, channel, quantity).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sg {
@@ -87,7 +88,16 @@ static Chunking make_chunking(int64_t rows_per_group, int C, int groups, int wav
     k.active = 256 / k.CV * k.CV;
     int64_t want = (int64_t)SG_NUM_SMS * waves;
     int64_t per = (k.nvec + want - 1) / want;
-    int64_t min_per = (int64_t)k.active * 4;                       // at least 4 vectors per thread
+    // Short CTAs are latency-bound (per-channel constants, first loads, final atomics: ~3 us each whatever the chunk),
+    // so mid-size tensors want about one round of CTAs (measured optimum ~192 for 6-25 MB tensors: 1.5-2x faster than
+    // 4-8 waves of 4-vector threads); large tensors keep `waves` rounds for load balance.
+    static const int minvec = getenv("SG_BN_MINVEC") ? atoi(getenv("SG_BN_MINVEC")) : 0;
+    int64_t min_per = (int64_t)k.active * minvec;
+    if (minvec == 0) {
+        min_per = k.nvec / 192;                                     // <= ~50 MB: one round of ~192 CTAs
+        if (min_per < (int64_t)k.active * 4) min_per = (int64_t)k.active * 4;
+        if (min_per > (int64_t)k.active * 64) min_per = (int64_t)k.active * 32;
+    }
     if (per < min_per) per = min_per;
     k.chunk = (per + k.active - 1) / k.active * k.active;
     k.blocks = (int)((k.nvec + k.chunk - 1) / k.chunk);
@@ -244,11 +254,19 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
     for (int t = threadIdx.x; t < nacc; t += 256) sacc[t] = 0.f;
     __syncthreads();
     int64_t i = begin + threadIdx.x;
+    // The threads' partial sums meet in shared memory: part[16][256(+1)] -> one owner per (channel, sum) adds the column
+    // entries of its channel vector.  (Shared-memory atomics serialise C/8-fold: 85 threads per address for the
+    // 24-channel generator layer, 36 us for a 6 MB tensor.)
+    __shared__ float part[16][257];
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    int g_mine = -1;
     if ((int)threadIdx.x < k.active && i < end) {
         const int c0 = ((int)threadIdx.x % k.CV) * 8;
         int g = (int)(i / k.gvec);
         int64_t next = (int64_t)(g + 1) * k.gvec;
-        float m[8], r[8], s1[8], s2[8], rg[HAS_A ? 1 : 8], bt[HAS_A ? 1 : 8];
+        float m[8], r[8], rg[HAS_A ? 1 : 8], bt[HAS_A ? 1 : 8];
         auto load = [&](int gg) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -300,7 +318,22 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
                 i += k.active;
             }
         }
-        flush(g);
+        g_mine = g;
+        if (g != g_last) {                           // (only when the group boundary falls into the CTA's last stride)
+            flush(g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        }
+    }
+    (void)g_mine;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { part[2 * j][threadIdx.x] = s1[j]; part[2 * j + 1][threadIdx.x] = s2[j]; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < C * 2; o += 256) {
+        const int c = o >> 1, row = 2 * (c & 7) + (o & 1);
+        float acc = 0.f;
+        for (int t = c >> 3; t < k.active; t += k.CV) acc += part[row][t];
+        sacc[(g_last - g_first) * C * 2 + o] += acc;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nacc; t += 256) atomicAdd(sums + (int64_t)g_first * C * 2 + t, (double)sacc[t]);
