@@ -722,6 +722,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int dn = r / (P.bw * P.bh), rem = r - dn * (P.bw * P.bh);
         const int dh = rem / P.bw, dw = rem - dh * P.bw;
         const bool vec_ok = (P.n_total % 8) == 0;
+        const bool bias_vec_ok = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0 && (P.BN & 3) == 0;   // float4 loads of the bias
         const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
         const int act = P.act;
         const bool has_stats = P.stats != nullptr;
@@ -849,17 +850,32 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int j = 0; j < 16; ++j) f[j] = tanh_approx(f[j]);
                 }
                 if (P.out32 != nullptr) {
-                    if (row_ok) {
-                        float* o32 = P.out32 + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0 + c0;
-                        if ((P.n_total % 4) == 0 && c0 + 16 <= ncols) {
+                    if ((P.n_total % 4) == 0 && c0 + 16 <= ncols) {
+                        // a lane's 64 B go through shared memory so that four lanes write one row's 64 contiguous bytes
+                        // (8 rows per store instruction instead of 32 half-used sectors)
+                        const int sw = (lane >> 1) & 3;
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                reinterpret_cast<float4*>(o32)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                        } else {
+                        for (int j = 0; j < 4; ++j)
+                            stg[lane * 4 + (j ^ sw)] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                                                  __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < ncols) o32[j] = f[j];
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = i * 8 + (lane >> 2);
+                            const uint4 val = stg[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
+                            const int ni = n0 + cdn[i];
+                            int oh2 = h0 + cdh[i], ow2 = w0 + cdw[i];
+                            if (P.mode == 1) { oh2 = oh2 * P.s + ph; ow2 = ow2 * P.s + pw; }
+                            if (ni < P.n_img)
+                                *reinterpret_cast<uint4*>(P.out32 + (((int64_t)ni * P.outH + oh2) * P.outW + ow2) * P.n_total + nt0 +
+                                                          c0 + (lane & 3) * 4) = val;
                         }
+                    } else if (row_ok) {
+                        float* o32 = P.out32 + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < ncols) o32[j] = f[j];
                     }
                     return;
                 }
@@ -897,8 +913,8 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // whole 32-column groups.  Straight-line code over 32 columns per iteration -- two independent 16-column
             // chains for the scheduler to interleave, since only two epilogue warps share an SM sub-partition and the
             // drain is issue-latency bound -- with the activation and the statistics decided once per tile.
-            const bool plain = P.bias == nullptr && P.residual == nullptr && P.out32 == nullptr && !is_split && vec_ok &&
-                               (ncols & 31) == 0 && P.out != nullptr;
+            const bool plain = P.residual == nullptr && P.out32 == nullptr && !is_split && vec_ok &&
+                               (ncols & 31) == 0 && P.out != nullptr && (P.bias == nullptr || bias_vec_ok);
             if (plain) {
                 bf16* crow[4];
 #pragma unroll
@@ -917,6 +933,14 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (P.bias != nullptr) {                          // (first layers: the same 32 values for every lane)
+                        const float4* bp = reinterpret_cast<const float4*>(P.bias + nt0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(bp + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                        }
+                    }
                     if (act == SG_ACT_LRELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);

@@ -576,6 +576,65 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict
     }
 }
 
+// The k4 s2 p1 case (every thin layer of StackGAN) tiled through shared memory: a CTA stages the col rows of an 8x16
+// block of input pixels plus a one-pixel halo with coalesced 16-byte loads (the per-pixel gather above touches every
+// 32-byte sector about four times: 1.4 TB/s on the 201 MB col matrix of G2's last layer), then each thread gathers two
+// output pixels of the 16x32 output block from shared memory.  Output (oh, ow) takes taps kh = (oh+1)%2 + {0,2} from
+// input rows ih = (oh+1-kh)/2, likewise in w.
+constexpr int UP_TH = 8, UP_TW = 16, UP_RS = 52;          // row stride 52 floats: 16-byte aligned, 2-way bank conflicts
+template <typename T, int C>
+__global__ void __launch_bounds__(256) unpatchify_k4s2p1_kernel(const float* __restrict__ col, const float* __restrict__ bias,
+                                                                T* __restrict__ out, int Hi, int Wi, int act, int tiles_w,
+                                                                int tiles_h) {
+    SG_PDL_SYNC();
+    constexpr int K = C * 16, K4 = K / 4, HR = UP_TH + 2, HC = UP_TW + 2;
+    __shared__ __align__(16) float tile[HR * HC * UP_RS];
+    int b = blockIdx.x;
+    const int tw = b % tiles_w; b /= tiles_w;
+    const int th = b % tiles_h;
+    const int n = b / tiles_h;
+    const int ih0 = th * UP_TH - 1, iw0 = tw * UP_TW - 1;
+    for (int q = threadIdx.x; q < HR * HC * K4; q += 256) {
+        const int pix = q / K4, k4 = q - pix * K4;
+        const int r = pix / HC, c = pix - r * HC;
+        const int ih = ih0 + r, iw = iw0 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && ih < Hi && iw >= 0 && iw < Wi)
+            v = __ldg(reinterpret_cast<const float4*>(col + (((int64_t)n * Hi + ih) * Wi + iw) * K) + k4);
+        *reinterpret_cast<float4*>(tile + pix * UP_RS + k4 * 4) = v;
+    }
+    __syncthreads();
+    const int Ho = 2 * Hi, Wo = 2 * Wi;
+    const int owl = threadIdx.x & 31, ow = tw * (2 * UP_TW) + owl;
+    const int kw0 = (owl + 1) & 1;                               // tile origin is even, so parity of ow = parity of owl
+    const int c0 = (owl + 1 - kw0) / 2 + 1;                      // halo column of tap kw0; tap kw0+2 sits one column left
+    float bs[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) bs[ch] = bias ? bias[ch] : 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int ohl = (threadIdx.x >> 5) + half * 8, oh = th * (2 * UP_TH) + ohl;
+        if (oh >= Ho || ow >= Wo) continue;
+        const int kh0 = (ohl + 1) & 1;
+        const int r0 = (ohl + 1 - kh0) / 2 + 1;
+        float acc[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) acc[ch] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int bq = 0; bq < 2; ++bq) {
+                const float* src = tile + ((r0 - a) * HC + (c0 - bq)) * UP_RS + (kh0 + 2 * a) * 4 + kw0 + 2 * bq;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) acc[ch] += src[ch * 16];
+            }
+        }
+        T* dst = out + (((int64_t)n * Ho + oh) * Wo + ow) * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) stf(dst + ch, act_fwd(acc[ch] + bs[ch], act));
+    }
+}
+
 // ---- text replicate + channel concat (generator_2.py:61-63) and its backward
 template <typename T>
 __global__ void __launch_bounds__(256) concat_rep_kernel(const T* __restrict__ x, const float* __restrict__ c,
@@ -835,6 +894,14 @@ int sg_unpatchify(const float* col, const float* bias, void* out, int N, int Hi,
     SG_REQUIRE(Ho == (Hi - 1) * s - 2 * p + k && Wo == (Wi - 1) * s - 2 * p + k, "unpatchify: inconsistent sizes");
     SG_REQUIRE((int64_t)N * Ho * Wo < (1ll << 31), "unpatchify: too many pixels");
     unsigned total = (unsigned)((int64_t)N * Ho * Wo);
+    if (k == 4 && s == 2 && p == 1 && C == 3 && (reinterpret_cast<uintptr_t>(col) & 15) == 0) {
+        const int tiles_w = (Wi + UP_TW - 1) / UP_TW, tiles_h = (Hi + UP_TH - 1) / UP_TH;
+        SG_REQUIRE((int64_t)N * tiles_w * tiles_h < (1ll << 31), "unpatchify: too many tiles");
+        SG_DISPATCH_T(dtype, (launch_pdl(unpatchify_k4s2p1_kernel<T, 3>, dim3((unsigned)(N * tiles_w * tiles_h)), dim3(256), 0,
+                                         SG_STREAM(stream), col, bias, (T*)out, Hi, Wi, act, tiles_w, tiles_h)));
+        SG_LAUNCHED("unpatchify");
+        return 0;
+    }
     SG_DISPATCH_T(dtype, (launch_pdl(unpatchify_kernel<T>, dim3(grid_for(total, 256, 16)), dim3(256), 0, SG_STREAM(stream), col, bias,
                                      (T*)out, Hi, Wi, Ho, Wo, C, k, s, p, act, total)));
     SG_LAUNCHED("unpatchify");

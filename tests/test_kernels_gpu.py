@@ -422,6 +422,7 @@ def test_patchify_generic(mode):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case", [(3, 8, 3, 4, 2, 1, ACT_TANH, True), (2, 16, 3, 4, 2, 1, ACT_NONE, False),
+                                  (2, 37, 3, 4, 2, 1, ACT_TANH, True), (1, 64, 3, 4, 2, 1, ACT_NONE, False),
                                   (2, 5, 2, 3, 1, 1, ACT_NONE, True), (1, 4, 4, 4, 1, 0, ACT_LRELU, True)])
 def test_unpatchify(mode, case):
     N, Hi, C, k, s, p, act, use_bias = case
