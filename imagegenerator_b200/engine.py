@@ -698,7 +698,7 @@ class Stage1Engine:
         # programmatic dependent launch measured -1.5 % on this step (many short kernels on three streams) and +2 % on
         # the Stage-II step; the attribute is baked into the launches (and the captured graph) issued below
         if hasattr(self.ops, "set_option"):
-            self.ops.set_option("pdl", 0)
+            self.ops.set_option("pdl", int(os.environ.get("SG_PDL_S1", "0")))
         self.ops.nchw_to_nhwc(self.s_real, d.group_view(d.a[0], 0, 1))
         self.outer_step(self.s_z, self.s_eca, self.s_egp)
 
