@@ -139,6 +139,37 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a4,
     }
 }
 
+// several head_fwd calls of one critic forward (real / mismatched / fake / interpolated rows) in one launch:
+// job j scores rows a4[a_row0[j] + n] with text rows ce[ce_row0[j] + n] into score[s_off[j] + n]
+struct HeadJobs {
+    int a_row0[4], ce_row0[4], s_off[4];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) head_fwd_multi_kernel(const T* __restrict__ a4, const float* __restrict__ ce,
+                                                             const float* __restrict__ A, const float* __restrict__ Bv,
+                                                             const float* __restrict__ c0, float* __restrict__ score,
+                                                             HeadJobs jobs, int M, int Nd) {
+    const int n = blockIdx.x, j = blockIdx.y;
+    const T* a = a4 + (int64_t)(jobs.a_row0[j] + n) * M;
+    const float* cr = ce + (int64_t)(jobs.ce_row0[j] + n) * Nd;
+    float acc = 0.f;
+    for (int i = threadIdx.x * 4; i < M; i += 256 * 4) {
+        F4 v = ld4(a + i);
+        float4 w = *reinterpret_cast<const float4*>(A + i);
+        acc += v.v[0] * w.x + v.v[1] * w.y + v.v[2] * w.z + v.v[3] * w.w;
+    }
+    for (int q = threadIdx.x; q < Nd; q += 256) acc += cr[q] * Bv[q];
+    __shared__ float sh[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = c0[0];
+        for (int i = 0; i < 8; ++i) t += sh[i];
+        score[jobs.s_off[j] + n] = t;
+    }
+}
+
 // out[m] += sum_n coef[n] x[n][m]; grid.y splits n
 template <typename T>
 __global__ void __launch_bounds__(256) wsum_rows_kernel(const float* __restrict__ coef, const T* __restrict__ x,
@@ -260,6 +291,19 @@ int sg_head_fwd(const void* a4, const float* ce, const float* A, const float* Bv
     SG_REQUIRE(M % 4 == 0, "head_fwd: M %% 4 != 0");
     SG_DISPATCH_T(dtype, (head_fwd_kernel<T><<<N, 256, 0, SG_STREAM(stream)>>>((const T*)a4, ce, A, Bv, c0, score, M, Nd)));
     SG_LAUNCHED("head_fwd");
+    return 0;
+}
+
+int sg_head_fwd_multi(const void* a4, const float* ce, const float* A, const float* Bv, const float* c0, float* score,
+                      int n_jobs, const int* a_row0, const int* ce_row0, const int* score_off, int N, int M, int Nd, int dtype,
+                      void* stream) {
+    SG_REQUIRE(M % 4 == 0, "head_fwd_multi: M %% 4 != 0");
+    SG_REQUIRE(n_jobs >= 1 && n_jobs <= 4, "head_fwd_multi: 1..4 jobs");
+    HeadJobs jobs{};
+    for (int j = 0; j < n_jobs; ++j) { jobs.a_row0[j] = a_row0[j]; jobs.ce_row0[j] = ce_row0[j]; jobs.s_off[j] = score_off[j]; }
+    SG_DISPATCH_T(dtype, (head_fwd_multi_kernel<T><<<dim3(N, n_jobs), 256, 0, SG_STREAM(stream)>>>((const T*)a4, ce, A, Bv, c0,
+                                                                                                   score, jobs, M, Nd)));
+    SG_LAUNCHED("head_fwd_multi");
     return 0;
 }
 

@@ -325,7 +325,9 @@ class CriticRT:
         B = self.B
         return t[g0 * B:(g0 + ng) * B]
 
-    def refresh_weights(self):
+    def refresh_weights(self, with_text=False):
+        """bf16 operand packs + the collapsed head from the fp32 masters.  ``with_text``: also the compressed text of the
+        current batch (it depends on the compress weights only), so that the next forward finds it ready."""
         ops, m = self.ops, self.m
         for L in self.layers:
             L.pack(ops)
@@ -333,6 +335,8 @@ class CriticRT:
         ops.pack_weight(L0.conv.weight.data.view(L0.co, self.K0, 1, 1), self.pf0, None)
         ops.head_prepare(m.channel_resize.weight.data, m.channel_resize.bias.data, m.critic_score.weight.data,
                          m.critic_score.bias.data, self.A, self.Bv, self.c0)
+        if with_text:
+            ops.linear_fwd(self.tem_all, m.compress.weight.data, m.compress.bias.data, self.ce)
 
     def set_text(self, tem, tem_mis):
         self.tem_all[:self.B].copy_(tem)
@@ -340,11 +344,12 @@ class CriticRT:
             self.tem_all[self.B:].copy_(tem_mis)
 
     # ---------------------------------------------------------------- forward
-    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False, before_weights=None):
+    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False, before_weights=None, ce_ready=False):
         """Trunk + head on groups [g0, g0+ng).  BN running statistics are updated once per group,
         group g0 ``dup_first`` times (the mismatched-text call sees the real images again).
         ``before_weights()`` is called right before the first kernel that reads packed weights (the engines re-pack
-        them on a side stream after each optimizer step and join here)."""
+        them on a side stream after each optimizer step and join here).  ``ce_ready``: the compressed text was already
+        computed by ``refresh_weights(with_text=True)`` for the current weights and batch."""
         ops, m, B = self.ops, self.m, self.B
         gv = lambda t: self.group_view(t, g0, ng)
         L0 = self.layers[0]
@@ -371,13 +376,13 @@ class CriticRT:
                 ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)
         # head: compressed text, then the collapsed affine score
         nt = 2 * B if with_mismatched else B
-        ops.linear_fwd(self.tem_all[:nt], m.compress.weight.data, m.compress.bias.data, self.ce[:nt])
-        a4 = self.a[self.nl]
-        for g in range(g0, g0 + ng):
-            row = {0: 0, 1: 2, 2: 3}[g]
-            ops.head_fwd(self.group_view(a4, g, 1), self.ce[:B], self.A, self.Bv, self.c0, self.score[row])
+        if not ce_ready:
+            ops.linear_fwd(self.tem_all[:nt], m.compress.weight.data, m.compress.bias.data, self.ce[:nt])
+        # one launch for all score rows: (first activation row, first text row, first score element) per job
+        jobs = [(g * B, 0, {0: 0, 1: 2, 2: 3}[g] * B) for g in range(g0, g0 + ng)]
         if with_mismatched:
-            ops.head_fwd(self.group_view(a4, 0, 1), self.ce[B:], self.A, self.Bv, self.c0, self.score[1])
+            jobs.append((0, B, B))
+        ops.head_fwd_multi(self.a[self.nl], self.ce, self.A, self.Bv, self.c0, self.score, jobs, B)
 
     # ---------------------------------------------------------------- first-order backward
     def input_grad(self, dy0, dx):
@@ -545,6 +550,7 @@ class Stage1Engine:
         self.side = SideStream(ops)
         self.gen_side = SideStream(ops)               # next iteration's generator forward (critic_iteration)
         self.pack_side = SideStream(ops)              # weight re-packing after the critic's optimizer step
+        self._ce_ready = False                        # compressed text valid for the current weights + batch
         self._fake_ready = False
         self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
         self.comm = comm                             # comm.DistComm or None
@@ -615,6 +621,7 @@ class Stage1Engine:
         d = self.d
         self.ops.nchw_to_nhwc(real_nchw, d.group_view(d.a[0], 0, 1))
         d.set_text(tem, tem_mis)
+        self._ce_ready = False
 
     def _generate(self, z, eps_ca):
         self.ca.forward(self.d.tem_all[:self.B], eps_ca, z, cg=self.g.cg)   # stage_1_train_fn.py:120-122
@@ -634,7 +641,7 @@ class Stage1Engine:
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,    # :125-132 + utils.py:13
-                  before_weights=self.pack_side.join)
+                  before_weights=self.pack_side.join, ce_ready=self._ce_ready)
         if next_noise is not None and self.gen_side.enabled:
             self.gen_side.run(lambda: self._generate(*next_noise))
             self._fake_ready = True
@@ -658,11 +665,13 @@ class Stage1Engine:
                    on_layer_done=bucket, head_reduce=False, side=self.side)
         self.optimizer_step(d.fp, already_reduced=tail[0])       # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
-        self.pack_side.run(d.refresh_weights)
+        self.pack_side.run(lambda: d.refresh_weights(with_text=True))
+        self._ce_ready = True                                    # until the text changes (load_batch / next outer step)
 
     def generator_step(self):
         ops, d, B = self.ops, self.d, self.B
-        d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join)   # :154 (updated critic, last fake)
+        d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join,   # :154 (updated critic, last fake)
+                  ce_ready=self._ce_ready)
         st = self.ca.st
         ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])          # :155-159
         ops.zero(self.g.fp.grad); ops.zero(self.ca.fp.grad)      # :161-164
@@ -676,6 +685,7 @@ class Stage1Engine:
 
     def outer_step(self, z, eps_ca, eps_gp):
         """z [5,B,100], eps_ca [5,B,128], eps_gp [5,B] (fp32, device)."""
+        self._ce_ready = False                                   # a new batch: its text has not been compressed yet
         for it in range(N_CRITIC):
             nxt = (z[it + 1], eps_ca[it + 1]) if it + 1 < N_CRITIC else None
             self.critic_iteration(z[it], eps_ca[it], eps_gp[it], next_noise=nxt)

@@ -224,6 +224,7 @@ class Stage2Engine:
         self.losses = ops.zeros((4,), ops.f32)
         self.side = SideStream(ops)
         self.pack_side = SideStream(ops)              # critic weight re-packing, overlapped with the next generator forward
+        self._ce_ready = False                        # compressed text valid for the current weights + batch
         self.comm = comm
         self.one_minus_eps = ops.empty((B,), ops.f32)
         self.dcg2 = ops.zeros((B, 1, 1, ca2.c_dim), ops.f32)
@@ -268,6 +269,7 @@ class Stage2Engine:
         d = self.d
         self.ops.nchw_to_nhwc(real_nchw, d.group_view(d.a[0], 0, 1))
         d.set_text(tem, tem_mis)
+        self._ce_ready = False
 
     def _generate(self, z, eps_ca1, eps_ca2):
         d, B = self.d, self.B
@@ -309,7 +311,7 @@ class Stage2Engine:
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,        # :133-140 + utils.py:13
-                  before_weights=self.pack_side.join)
+                  before_weights=self.pack_side.join, ce_ready=self._ce_ready)
         ops.zero(d.fp.grad)                                         # :153
         ops.zero(d.head_grads)                                      # dA, dBv
         d.gp_first_order()
@@ -324,11 +326,13 @@ class Stage2Engine:
         ops.scale_rows_add(d.group_view(d.dx, 2, 1), self.one_minus_eps, dfake, True)
         self._generator_backward(dfake, 0.0)                        # accumulates into G2 / CA2 (:154, no zero_grad)
         self.optimizer_step(d.fp)                                   # :155
-        self.pack_side.run(d.refresh_weights)                       # joined before the next critic forward reads the packs
+        self.pack_side.run(lambda: d.refresh_weights(with_text=True))   # joined before the next critic forward reads the packs
+        self._ce_ready = True                                       # until the text changes (load_batch / next outer step)
 
     def generator_step(self):
         ops, d, B = self.ops, self.d, self.B
-        d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join)     # :157
+        d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join,     # :157
+                  ce_ready=self._ce_ready)
         st = self.ca2.st
         ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])  # :158-162
         d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
@@ -340,6 +344,7 @@ class Stage2Engine:
         self.g2.refresh_weights()
 
     def outer_step(self, z, eps_ca1, eps_ca2, eps_gp):
+        self._ce_ready = False                                      # a new batch: its text has not been compressed yet
         for it in range(N_CRITIC):
             self.critic_iteration(z[it], eps_ca1[it], eps_ca2[it], eps_gp[it])
         self.generator_step()

@@ -72,6 +72,7 @@ _SIGS = {
     "sg_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "sg_head_prepare": [_P] * 7 + [_I, _I, _I, _P],
     "sg_head_fwd": [_P] * 6 + [_I, _I, _I, _I, _P],
+    "sg_head_fwd_multi": [_P] * 6 + [_I, _P, _P, _P, _I, _I, _I, _I, _P],
     "sg_outer": [_P, _P, _P, _I, _I, _I, _P],
     "sg_wsum_rows": [_P, _P, _P, _I, _I, _I, _P],
     "sg_head_param_grads": [_P] * 10 + [_I, _I, _I, _P],
@@ -437,6 +438,15 @@ class CudaOps:
         N = a4.shape[0]
         self._ck(self.lib.sg_head_fwd(_ptr(a4), _ptr(ce), _ptr(A), _ptr(Bv), _ptr(c0), _ptr(score), N,
                                       a4.numel() // N, Bv.shape[0], self._dt_of(a4), self._st()))
+
+    def head_fwd_multi(self, a4, ce, A, Bv, c0, score, jobs, N):
+        """``jobs``: up to four ``(first row of a4, first row of ce, first element of score)``; each scores N rows."""
+        self._c(a4, ce, A, Bv, c0, score)
+        n = len(jobs)
+        arr = lambda k: (_c.c_int * n)(*[int(j[k]) for j in jobs])
+        a0, c0r, s0 = arr(0), arr(1), arr(2)
+        self._ck(self.lib.sg_head_fwd_multi(_ptr(a4), _ptr(ce), _ptr(A), _ptr(Bv), _ptr(c0), _ptr(score), n, a0, c0r, s0, N,
+                                            a4.numel() // a4.shape[0], Bv.shape[0], self._dt_of(a4), self._st()))
 
     def head_bwd_data(self, coef, A, da4):
         self._c(coef, A, da4)

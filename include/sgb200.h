@@ -229,6 +229,12 @@ int sg_head_prepare(const float* wcr, const float* bcr, const float* wcs, const 
                     float* A, float* Bv, float* c0, int K, int Cx, int Nd, void* stream);
 int sg_head_fwd(const void* a4, const float* ce, const float* A, const float* Bv, const float* c0,
                 float* score, int N, int M, int Nd, int dtype, void* stream);
+/* up to four sg_head_fwd calls of one critic forward in one launch (discrminator_1.py:41-52 is evaluated on the real,
+ * mismatched, fake and interpolated rows of the same activation buffer): job j scores rows a4[a_row0[j]+n] with text rows
+ * ce[ce_row0[j]+n] into score[score_off[j]+n], n < N.  The three index arrays are HOST arrays of n_jobs ints. */
+int sg_head_fwd_multi(const void* a4, const float* ce, const float* A, const float* Bv, const float* c0, float* score,
+                      int n_jobs, const int* a_row0, const int* ce_row0, const int* score_off, int N, int M, int Nd,
+                      int dtype, void* stream);
 /* out[n][m] = coef[n] * vec[m]   (out in T when out_dtype says so, else fp32) */
 int sg_outer(const float* coef, const float* vec, void* out, int N, int M, int out_dtype, void* stream);
 /* out[m] (fp32) += sum_n coef[n] * x[n][m] */

@@ -324,6 +324,11 @@ class EmuOps:
         s = (a4.reshape(n, -1).double() * A.double().reshape(1, -1)).sum(1) + ce.double() @ Bv.double() + c0.double()
         score.copy_(s.to(score.dtype))
 
+    def head_fwd_multi(self, a4, ce, A, Bv, c0, score, jobs, N):
+        flat = score.reshape(-1)
+        for a0, c0r, s0 in jobs:
+            self.head_fwd(a4[a0:a0 + N], ce[c0r:c0r + N], A, Bv, c0, flat[s0:s0 + N])
+
     def head_bwd_data(self, coef, A, da4):
         """da4[n] = coef[n] * A."""
         da4.copy_((coef.double()[:, None, None] * A.double()[None]).reshape(da4.shape).to(da4.dtype))

@@ -86,3 +86,29 @@ def test_stage1_outer_step_fp64_matches_oracle(B):
                 _close(sd[k], v, 1e-6, 1e-9, f"after {key}.{k}")
             else:
                 assert int(sd[k]) == int(v), (key, k, int(sd[k]), int(v))
+
+
+def test_compressed_text_is_recomputed_for_every_new_batch():
+    """The critic's compressed text is computed on the weight re-pack stream after each critic update and reused by the
+    following forwards -- but never across batches: the first critic forward of every outer step (and of every
+    load_batch) must compress the new text itself."""
+    B = 2
+    ca, d1, g1 = build_modules()
+    eng = Stage1Engine(ca, d1, g1, B, ops=EmuOps(torch.float64))
+    seen = []
+    orig = eng.d.forward
+
+    def spy(*a, **k):
+        seen.append(bool(k.get("ce_ready", False)))
+        return orig(*a, **k)
+    eng.d.forward = spy
+    for step in range(2):
+        b = O.synthetic_batch(B, 1, step, dtype=torch.float64)
+        eng.load_batch(b["real"], b["tem"], b["tem"][b["perm"]])
+        if step == 1:                                    # the graph path writes the text buffer directly, then outer_step
+            eng.d.tem_all[:B].copy_(b["tem"])
+        eng.outer_step(b["z"], b["eps_ca"], b["eps_gp"])
+        # what the last forward used == compress(current text) with the current weights
+        want = b["tem"] @ d1.compress.weight.data.double().t() + d1.compress.bias.data.double()
+        assert torch.allclose(eng.d.ce[:B], want, rtol=1e-9, atol=1e-12)
+    assert seen == [False, True, True, True, True, True] * 2, seen

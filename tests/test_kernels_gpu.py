@@ -233,6 +233,13 @@ def test_head(mode, K, Cx, Nd):
     a4, ce = rnd(N, 4, 4, Cx), rnd(N, Nd)
     run_pair(mode, "head_fwd", [T(a4), F(ce), F(A), F(Bv), F(c0), F(torch.zeros(N))], [5],
              tol=dict(rtol=1e-3, atol=1e-4))
+    # the four score rows of a critic forward in one launch (real, mismatched, fake, interpolated)
+    a_all, ce2 = rnd(3 * N, 4, 4, Cx, seed=7), rnd(2 * N, Nd, seed=8)
+    jobs = [(0, 0, 0), (N, 0, 2 * N), (2 * N, 0, 3 * N), (0, N, N)]
+    run_pair(mode, "head_fwd_multi", [T(a_all), F(ce2), F(A), F(Bv), F(c0), F(torch.zeros(4, N)), jobs, N], [5],
+             tol=dict(rtol=1e-3, atol=1e-4))
+    run_pair(mode, "head_fwd_multi", [T(a_all), F(ce2), F(A), F(Bv), F(c0), F(torch.zeros(4, N)), jobs[2:3], N], [5],
+             tol=dict(rtol=1e-3, atol=1e-4))
     coef = rnd(N)
     coef[2] = 0.0
     run_pair(mode, "head_bwd_data", [F(coef), F(A), T(torch.zeros(N, 4, 4, Cx))], [2])
