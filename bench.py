@@ -579,9 +579,9 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "imagegenerator_b200.stage_1_train_fn.train_1"},
             "roofline": {"bound": "tensor", "kernel": "sg_conv_fprop critic ds3 (128->256, k4 s2, 3 groups batched)",
                          "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                         "traffic": 26263808, "traffic_unit": "B per launch (dram read + write, profiles/ncu_conv_tcp_r1b_summary.txt; "
+                         "traffic": 26289152, "traffic_unit": "B per launch (dram read + write, profiles/ncu_conv_tcp_r1g_summary.txt; "
                                                               "algorithmic 38.8 MB incl. the 12.6 MB result that stays in L2)",
-                         "tensor_pipe_active_pct": 57.05, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PF",
+                         "tensor_pipe_active_pct": 59.5, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PF",
                          "kernel_ms": round(kms, 5)},
             "clocks": clocks,
         }
