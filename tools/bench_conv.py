@@ -47,6 +47,9 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     dirs = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fprop", "dgrad", "wgrad"]
     ops = CudaOps("bf16")
+    for kv in filter(None, os.environ.get("SG_OPTS", "").split(",")):      # e.g. SG_OPTS=force_cg=1,force_stages=4
+        key, val = kv.split("=")
+        ops.set_option(key, int(val))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     print(f"{'layer':14s} {'dir':6s} {'M':>8s} {'N':>5s} {'K':>6s} {'us':>9s} {'TFLOP/s':>9s} {'GB/s':>8s}")
     for name, N, H, Ci, Co, k, s, p in SHAPES:
