@@ -744,9 +744,14 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w);
              ++wi, ++ti, ab = (ab + 1 == (uint32_t)P.nbuf ? 0 : ab + 1), abpar ^= (ab == 0 ? 1u : 0u)) {
             const int tile = w.tile;
-            const int phase = tile / tiles_per_phase, rr = tile - phase * tiles_per_phase;
-            const int nt = rr / P.m_tiles, mt = rr - nt * P.m_tiles;
-            const int ph = phase / P.s, pw = phase - ph * P.s;
+            // tile decode: the divisions are ~30 instructions each and this code runs per tile and warp (the thin layers'
+            // 128x64 tiles were bound by exactly this: 445 instructions per warp and tile, 16 of them the bf16 packs) --
+            // the single-phase / single-column-tile cases (warp-uniform) skip them
+            int phase = 0, rr = tile, nt = 0, ph = 0, pw = 0;
+            if (tiles_per_phase != P.total_tiles) { phase = tile / tiles_per_phase; rr = tile - phase * tiles_per_phase; }
+            int mt = rr;
+            if (P.n_tiles != 1) { nt = rr / P.m_tiles; mt = rr - nt * P.m_tiles; }
+            if (phase != 0) { ph = phase / P.s; pw = phase - ph * P.s; }
             const int m0 = (mt * CG + (int)rank) * 128;
             const int w0 = m0 & (P.Wq - 1), h0 = (m0 >> P.lgW) & (P.Hq - 1), n0 = m0 >> P.lgHW;   // Hq, Wq are powers of two
             const int nt0 = nt * P.BN;
@@ -754,7 +759,8 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool row_ok = n_img < P.n_img && (P.out != nullptr || P.out32 != nullptr);
             int oh = hh, ow = ww;
             if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
-            bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
+            // pixel indices fit 32 bits (checked on the host); one widening multiply per pointer
+            bf16* orow = P.out + (int64_t)((n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
             const int ncols = min(P.BN, P.n_total - nt0);          // valid columns of this tile
             const uint32_t sb2 = ti & 1;           // statistics staging buffer
             // K-split bookkeeping: partial tiles of leftover tile lt live at ws[((lt*(split-1) + slice-1)*CG + rank)][128][BN]
@@ -922,7 +928,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int ni = n0 + cdn[i];
                     int oh2 = h0 + cdh[i], ow2 = w0 + cdw[i];
                     if (P.mode == 1) { oh2 = oh2 * P.s + ph; ow2 = ow2 * P.s + pw; }
-                    crow[i] = ni < P.n_img ? P.out + (((int64_t)ni * P.outH + oh2) * P.outW + ow2) * P.n_total + nt0 + (lane & 3) * 8
+                    crow[i] = ni < P.n_img ? P.out + (int64_t)((ni * P.outH + oh2) * P.outW + ow2) * P.n_total + nt0 + (lane & 3) * 8
                                            : nullptr;
                 }
                 for (int c0 = half * 32; c0 < ncols; c0 += 64) {
@@ -1743,6 +1749,10 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     }
     if (!choose_box(P.Hq, P.Wq, &P.bw, &P.bh, &P.bn)) { set_error("conv_tcp: grid %dx%d not tileable", P.Hq, P.Wq); return SG_ERR_UNSUPPORTED; }
     const int M = N * P.Hq * P.Wq;
+    if ((int64_t)(N + 128) * P.outH * P.outW >= (1ll << 31)) {       // the epilogue indexes output pixels with 32 bits
+        set_error("conv_tcp: %d x %d x %d output pixels exceed the 32-bit pixel index", N, P.outH, P.outW);
+        return SG_ERR_UNSUPPORTED;
+    }
     P.n_img = N;
     P.lgW = 0; while ((1 << P.lgW) < P.Wq) ++P.lgW;
     P.lgHW = P.lgW; while ((1 << P.lgHW) < P.Hq * P.Wq) ++P.lgHW;
