@@ -18,6 +18,7 @@
 #include <cudaTypedefs.h>
 #include <map>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <tuple>
 #include <vector>
@@ -499,6 +500,7 @@ struct TcpParams {
     int full_tiles, split, kb_slice;   // tail-wave K-split: tiles below full_tiles are whole; see next_work()
     float* ws;            // fp32 partial tiles of the split tail wave
     int* flags;           // one per (leftover tile, non-owner slice, CTA of the pair)
+    int epi_alt;          // narrow tiles: the two epilogue warp groups drain ALTERNATE tiles (see the epilogue)
 };
 
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
@@ -621,7 +623,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < P.nbuf; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TCP_EPI_WARPS * CG); }
+        for (int i = 0; i < P.nbuf; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (P.epi_alt ? TCP_EPI_WARPS / 2 : TCP_EPI_WARPS) * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (P.stats != nullptr)
@@ -743,6 +745,11 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         Work w;
         for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w);
              ++wi, ++ti, ab = (ab + 1 == (uint32_t)P.nbuf ? 0 : ab + 1), abpar ^= (ab == 0 ? 1u : 0u)) {
+            // epi_alt (narrow tiles without statistics / K-split): warps 2-5 drain the even work items, warps 6-9 the odd
+            // ones, each warp all columns of its 32 rows -- the per-tile fixed cost (decode, row pointers, barrier round
+            // trip: ~350 of the ~450 instructions a warp spends on a 128x64 tile) is paid by four warps instead of eight
+            // and two tiles drain concurrently
+            if (P.epi_alt && (int)(ti & 1u) != half) continue;
             const int tile = w.tile;
             // tile decode: the divisions are ~30 instructions each and this code runs per tile and warp (the thin layers'
             // 128x64 tiles were bound by exactly this: 445 instructions per warp and tile, 16 of them the bf16 packs) --
@@ -931,7 +938,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     crow[i] = ni < P.n_img ? P.out + (int64_t)((ni * P.outH + oh2) * P.outW + ow2) * P.n_total + nt0 + (lane & 3) * 8
                                            : nullptr;
                 }
-                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                for (int c0 = P.epi_alt ? 0 : half * 32; c0 < ncols; c0 += P.epi_alt ? 32 : 64) {
                     uint32_t v[32];
                     tc_ld16_nowait(tacc + (uint32_t)c0, v);
                     tc_ld16_nowait(tacc + (uint32_t)c0 + 16, v + 16);
@@ -999,7 +1006,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             } else
             {
-                for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+                for (int c0 = P.epi_alt ? 0 : half * 16; c0 < ncols; c0 += P.epi_alt ? 16 : 32) {
                     uint32_t v[16];
                     tc_ld16(tacc + (uint32_t)c0, v);
                     process(c0, v);
@@ -1634,6 +1641,9 @@ static int launch_conv_tc2(int mode, const void* act, const void* wpack, const f
 // (16 KB of A + BN/CG rows of B) at ~44 B/cycle/SM (the ~12 TB/s L2->SM ceiling shared by 148 SMs).
 int g_use_persist = 1;
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
+// alternate-tile epilogue for narrow tiles: OFF by default (option "epi_alt" / env SG_EPI_ALT=1) until it has been through the
+// full GPU test suite
+int g_epi_alt = getenv("SG_EPI_ALT") ? atoi(getenv("SG_EPI_ALT")) : 0;
 static bool g_pattr_set = false;
 
 // ---- tail-wave K-split scratch: fp32 partial tiles + flags, one slot per stream that launches split kernels (kernels of
@@ -1813,6 +1823,8 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
             }
         }
     }
+    // two tiles in flight in the epilogue need two accumulator buffers beyond the one being filled: nbuf >= 4 (bn <= 128)
+    P.epi_alt = (g_epi_alt && stats == nullptr && P.split == 1 && bn <= 64 && P.nbuf >= 4) ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * cg, 1, 1);
     cfg.blockDim = dim3(TCP_THREADS);
@@ -2048,6 +2060,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }
     if (name && !strcmp(name, "pdl")) { g_use_pdl = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
+    if (name && !strcmp(name, "epi_alt")) { g_epi_alt = value; return 0; }
     if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
     if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }
     if (name && !strcmp(name, "dbg")) { g_dbg = value; return 0; }
