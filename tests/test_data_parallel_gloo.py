@@ -153,3 +153,41 @@ def test_stage1_data_parallel_world2_gloo():
         p.join(timeout=60)
     for rank, status, info in res:
         assert status == "ok", f"rank {rank}: {info}"
+
+
+def _worker_loader(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import tempfile
+        from _util import make_coco_dir
+        from imagegenerator_b200.data_loader import get_loader
+        from imagegenerator_b200.train import image_transform
+        # every rank writes the same (seeded) directory for itself; the captions are unique strings
+        with tempfile.TemporaryDirectory() as tmp:
+            root, ann, tok, rows = make_coco_dir(tmp, n_images=6, captions_per_image=2)
+            loader = get_loader("b", root, ann, image_transform(64), batch_size=2, shuffle=True, tokenizer=tok, num_workers=0)
+            assert len(loader) == 3                                   # 12 captions / 2 ranks / batch 2
+            mine = []
+            for tokenized, imgs in loader:
+                assert imgs.shape == (2, 3, 64, 64)
+                mine += [tuple(r.tolist()) for r in tokenized["input_ids"]]
+        got = [None] * world
+        dist.all_gather_object(got, mine)
+        a, b = got
+        enc = tok([c for c, _ in rows], padding="max_length", truncation=True, max_length=128, return_tensors="pt")["input_ids"]
+        every = sorted(tuple(r.tolist()) for r in enc)
+        # DistributedSampler over torch.distributed ranks: the two shards are disjoint and together cover the dataset
+        assert len(a) == len(b) == 6 and sorted(a + b) == every, (len(a), len(b))
+        q.put((rank, "ok", ""))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_caption_loader_shards_over_ranks_world2_gloo():
+    _run_world2(_worker_loader)
