@@ -49,6 +49,12 @@ class _Blob:
         with open(fn, "rb") as f:
             self._store[self._path] = f.read()
 
+    def download_as_bytes(self):              # data_loader.py:38
+        return self._store[self._path]
+
+    def download_as_text(self):               # data_loader.py:50
+        return self._store[self._path].decode("utf-8")
+
 
 class FakeBucketStore(dict):
     """path -> bytes; shared by every storage.Client() the reference creates."""

@@ -102,3 +102,27 @@ def test_stage2_step_matches_fixed_train_2():
     assert_digest_dict(out["ca2_grads"], g["ca2_grads"], 5e-3, 1e-5, "ca2 grads")
     for k in ("ca2", "d2", "g2"):
         assert_digest_dict(out["after"][k], g["after"][k], 5e-3, 5e-5, f"weights after [{k}]")
+
+
+def test_caption_loader_matches_the_reference_loader(tmp_path):
+    """tests/golden/loader.pt holds what the UNMODIFIED reference ``data_loader.get_loader`` yields (oracle/
+    make_golden_loader.py: fake GCS bucket, 8 workers, DistributedSampler) on the seeded directory
+    ``_util.make_coco_dir`` writes; ``imagegenerator_b200.data_loader.get_loader`` must yield the same batches."""
+    from _util import make_coco_dir
+    from imagegenerator_b200.data_loader import get_loader
+    from imagegenerator_b200.train import image_transform
+    gold = load_golden("loader")
+    root, ann, tok, rows = make_coco_dir(tmp_path, n_images=gold["n_images"], captions_per_image=gold["captions_per_image"])
+    assert [tuple(r) for r in rows] == [tuple(r) for r in gold["rows"]]
+    for key, shuffle in (("ordered", False), ("shuffled", True)):
+        loader = get_loader("data-and-checkpoints-bucket", root, ann, image_transform(64), batch_size=gold["batch"],
+                            shuffle=shuffle, tokenizer=tok, num_workers=0)
+        assert len(loader) == gold[key + "_len"] and len(loader.dataset) == gold[key + "_dataset_len"]
+        for (tokenized, imgs), want in zip(loader, gold[key]):
+            assert set(tokenized.keys()) == set(want["tokenized"].keys())
+            for k, v in want["tokenized"].items():
+                assert torch.equal(tokenized[k], v), (key, k)                     # same captions in the same order
+            if want["imgs"] is not None:
+                assert torch.allclose(imgs, want["imgs"], rtol=0, atol=1e-6)
+            assert abs(imgs.double().sum().item() - want["img_sum"]) <= 1e-4 * want["img_abs"]
+            assert abs(imgs.double().abs().sum().item() - want["img_abs"]) <= 1e-5 * want["img_abs"]
