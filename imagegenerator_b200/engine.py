@@ -489,6 +489,40 @@ class CriticRT:
         ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA)
 
 
+def export_optimizer_state(opt, fp):
+    """Mirror the fused Adam state (flat moments + device step counter) into a torch.optim.Adam so that
+    ``opt.state_dict()`` checkpoints carry exp_avg / exp_avg_sq / step like the reference's
+    (stage_1_train_fn.py:218-222, stage_2_train_fn.py:219-221)."""
+    step = float(fp.hyper[4].item())
+    off = 0
+    for p in fp.params:
+        k = p.numel()
+        opt.state[p] = {"step": torch.tensor(step), "exp_avg": fp.m[off:off + k].view(p.shape).clone(),
+                        "exp_avg_sq": fp.v[off:off + k].view(p.shape).clone()}
+        off += k
+
+
+def import_optimizer_state(opt, fp):
+    """The inverse, for resuming (the reference restores its optimizers, stage_1_train_fn.py:69-73,
+    stage_2_train_fn.py:84-86): after ``opt.load_state_dict(checkpoint[...])`` copy exp_avg / exp_avg_sq / step of every
+    parameter into the flat moment buffers and the device step counter the fused Adam kernel uses.  Returns the number of
+    parameters that had state."""
+    off, step, found = 0, None, 0
+    for p in fp.params:
+        k = p.numel()
+        st = opt.state.get(p)
+        if st is not None and "exp_avg" in st:
+            fp.m[off:off + k].copy_(st["exp_avg"].detach().reshape(-1))
+            fp.v[off:off + k].copy_(st["exp_avg_sq"].detach().reshape(-1))
+            t = float(st["step"])
+            assert step is None or step == t, "parameters of one optimizer carry different step counts"
+            step, found = t, found + 1
+        off += k
+    if step is not None:
+        fp.hyper[4] = step
+    return found
+
+
 class _SegmentedGraph:
     """A train step captured as a SEQUENCE of CUDA graphs with the NCCL calls issued eagerly between them.
 
@@ -590,15 +624,10 @@ class Stage1Engine:
         self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
 
     def export_optimizer_state(self, opt, fp):
-        """Mirror the fused Adam state into a torch.optim.Adam so ``opt.state_dict()`` checkpoints
-        carry exp_avg / exp_avg_sq / step like the reference's (stage_1_train_fn.py:218-222)."""
-        step = float(fp.hyper[4].item())
-        off = 0
-        for p in fp.params:
-            k = p.numel()
-            opt.state[p] = {"step": torch.tensor(step), "exp_avg": fp.m[off:off + k].view(p.shape).clone(),
-                            "exp_avg_sq": fp.v[off:off + k].view(p.shape).clone()}
-            off += k
+        export_optimizer_state(opt, fp)
+
+    def import_optimizer_state(self, opt, fp):
+        import_optimizer_state(opt, fp)
 
     def _comm_allreduce(self, t):
         seg = getattr(self, "_seg", None)

@@ -70,15 +70,20 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
     world, rank = _world(), _rank()
 
     checkpoint_path = os.path.join(save_dir, "latest_checkpoint_stage1.pth")
+    resumed = False
     if os.path.exists(checkpoint_path):                       # :55-82
         ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
         start_epoch = ck["epoch"] + 1
         for m, k in ((textEncoder, "textEncoder"), (projection_head, "projection_head"),
                      (con_augment_1, "con_augment_1"), (critic_1, "critic_1"), (gen_1, "gen_1")):
             m.load_state_dict(ck[k])
+        for o, k in zip(optimizers, ("opt_encoder", "opt_projection_head", "opt_con_augment_1", "opt_critic_1",
+                                     "opt_gen_1")):        # :69-73; the fused-Adam moments are taken over below
+            o.load_state_dict(ck[k])
         for s, k in zip(schedulers, ("lr_scheduler_encoder", "lr_scheduler_projection_head",
                                      "lr_scheduler_con_augment_1", "lr_scheduler_critic_1", "lr_scheduler_gen_1")):
             s.load_state_dict(ck[k])
+        resumed = True
         log(f"Loaded checkpoint at epoch {start_epoch - 1}")
 
     for m in models:
@@ -92,6 +97,8 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         lr, b1, b2, eps = _adam_hyper(opt)
         fp.hyper[:4] = torch.tensor([lr, b1, b2, eps], dtype=torch.float32)
         fp._lr_host = lr
+        if resumed:
+            eng.import_optimizer_state(opt, fp)                # Adam moments + step count of the checkpoint
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 

@@ -15,7 +15,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from .engine import N_CRITIC, LAMBDA_GP, Z_DIM
+from .engine import N_CRITIC, LAMBDA_GP, Z_DIM, export_optimizer_state, import_optimizer_state
 from .engine2 import Stage2Engine
 from .stage_1_train_fn import _world, _rank, _adam_hyper
 
@@ -44,14 +44,18 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         con_augment_1.load_state_dict(ck1["con_augment_1"])
         gen_1.load_state_dict(ck1["gen_1"])
     checkpoint_path = os.path.join(save_dir, "latest_checkpoint_stage2.pth")
+    resumed = False
     if os.path.exists(checkpoint_path):                                 # :74-92
         ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
         start_epoch = ck["epoch"] + 1
         con_augment_2.load_state_dict(ck["con_augment_2"])
         critic_2.load_state_dict(ck["critic_2"])
         gen_2.load_state_dict(ck["gen_2"])
+        for o, k in zip(optimizers, ("opt_con_augment_2", "opt_critic_2", "opt_gen_2")):    # :84-86
+            o.load_state_dict(ck[k])
         for s, k in zip(schedulers, ("lr_scheduler_con_augment_2", "lr_scheduler_critic_2", "lr_scheduler_gen_2")):
             s.load_state_dict(ck[k])
+        resumed = True
         log(f"Loaded checkpoint at epoch {start_epoch - 1}")
     con_augment_2.train(); critic_2.train(); gen_2.train()              # :96-98
 
@@ -66,6 +70,8 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         lr, b1, b2, eps = _adam_hyper(opt)
         fp.hyper[:4] = torch.tensor([lr, b1, b2, eps], dtype=torch.float32)
         fp._lr_host = lr
+        if resumed:
+            import_optimizer_state(opt, fp)                    # Adam moments + step count of the checkpoint
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 
@@ -119,6 +125,8 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
                     f.write(f"{preview_step},{epoch},{batch_idx},{losses[0]},{losses[2]}\n")
                 preview_step += 1                                                                       # :211
         if rank == 0 and epoch % 10 == 0:                               # :214-235
+            for opt, fp in ((opt_con_augment_2, eng.ca2.fp), (opt_critic_2, eng.d.fp), (opt_gen_2, eng.g2.fp)):
+                export_optimizer_state(opt, fp)                # exp_avg / exp_avg_sq / step of the fused Adam
             checkpoint = {
                 "con_augment_2": con_augment_2.state_dict(), "critic_2": critic_2.state_dict(), "gen_2": gen_2.state_dict(),
                 "opt_con_augment_2": opt_con_augment_2.state_dict(), "opt_critic_2": opt_critic_2.state_dict(),

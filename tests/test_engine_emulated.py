@@ -112,3 +112,47 @@ def test_compressed_text_is_recomputed_for_every_new_batch():
         want = b["tem"] @ d1.compress.weight.data.double().t() + d1.compress.bias.data.double()
         assert torch.allclose(eng.d.ce[:B], want, rtol=1e-9, atol=1e-12)
     assert seen == [False, True, True, True, True, True] * 2, seen
+
+
+def test_optimizer_state_round_trip_through_torch_adam():
+    """Checkpoints carry the fused Adam's moments as a torch.optim.Adam state_dict (stage_1_train_fn.py:218-222) and a
+    resumed run takes them over again (:69-73): export -> state_dict -> load_state_dict -> import gives a replica that
+    continues exactly like the original."""
+    from imagegenerator_b200.engine import export_optimizer_state, import_optimizer_state
+    dt, B = torch.float64, 2
+    b = O.synthetic_batch(B, 1, 0, dtype=dt)
+
+    def fresh():
+        ca, d1, g1 = build_modules()
+        return ca, d1, g1
+
+    ca, d1, g1 = fresh()
+    eng = Stage1Engine(ca, d1, g1, B, ops=EmuOps(dt))
+    eng.load_batch(b["real"], b["tem"], b["tem"][b["perm"]])
+    eng.critic_iteration(b["z"][0], b["eps_ca"][0], b["eps_gp"][0])
+    eng.critic_iteration(b["z"][1], b["eps_ca"][1], b["eps_gp"][1])
+    opt = torch.optim.Adam(d1.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    export_optimizer_state(opt, eng.d.fp)
+    ck = {"critic_1": {k: v.clone() for k, v in d1.state_dict().items()}, "opt_critic_1": opt.state_dict()}
+    st = ck["opt_critic_1"]["state"]
+    assert len(st) == len(list(d1.parameters())) and float(st[0]["step"]) == 2.0
+    assert set(st[0]) == {"step", "exp_avg", "exp_avg_sq"} and st[0]["exp_avg"].shape == d1.down_sampler[0].weight.shape
+
+    ca2, d2, g2 = fresh()
+    d2.double()                    # (load_state_dict casts the moments to the parameters' type: fp32 in the product, where
+    d2.load_state_dict(ck["critic_1"])         # the fused Adam's moments are fp32 too; the emulator runs in fp64)
+    opt2 = torch.optim.Adam(d2.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    opt2.load_state_dict(ck["opt_critic_1"])
+    eng2 = Stage1Engine(ca2, d2, g2, B, ops=EmuOps(dt))
+    assert import_optimizer_state(opt2, eng2.d.fp) == len(list(d2.parameters()))
+    assert torch.equal(eng2.d.fp.m, eng.d.fp.m) and torch.equal(eng2.d.fp.v, eng.d.fp.v)
+    assert float(eng2.d.fp.hyper[4]) == float(eng.d.fp.hyper[4]) == 2.0
+    # an optimizer without state (a fresh run, or a checkpoint written before the state was exported) changes nothing
+    assert import_optimizer_state(torch.optim.Adam(g2.parameters()), eng2.g.fp) == 0 and float(eng2.g.fp.hyper[4]) == 0.0
+    eng2.load_batch(b["real"], b["tem"], b["tem"][b["perm"]])
+    for e in (eng, eng2):
+        e._ce_ready = False
+        e.critic_iteration(b["z"][2], b["eps_ca"][2], b["eps_gp"][2])
+    for (k, v), (_, w) in zip(d1.state_dict().items(), d2.state_dict().items()):
+        if v.is_floating_point():
+            assert torch.allclose(v, w, rtol=1e-10, atol=1e-12), k

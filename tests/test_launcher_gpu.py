@@ -24,6 +24,10 @@ def test_stage1_then_stage2_with_checkpoints(tmp_path):
     assert int(ck["critic_1"]["down_sampler.2.1.num_batches_tracked"]) == 3 * 21
     assert len(logs) == 3 and all("Loss D" in l for l in logs)
     g1_trained = {k: v.clone() for k, v in m1["gen_1"].state_dict().items()}
+    # resume (:55-82): weights, schedulers AND optimizer state come back -- the fused Adam continues at step 15 / 3
+    eng1b, _ = T.run(1, dev, epochs=2, batch=8, save_dir=save, synthetic=3, log=logs.append)
+    assert any("Loaded checkpoint at epoch 0" in l for l in logs)
+    assert float(eng1b.d.fp.hyper[4]) == 30.0 and float(eng1b.g.fp.hyper[4]) == 6.0 and float(eng1b.ca.fp.hyper[4]) == 6.0
 
     eng2, m2 = T.run(2, dev, epochs=1, batch=2, save_dir=save, synthetic=2, log=logs.append, preview_every=1)
     # the fixed-noise preview + scalars of stage_2_train_fn.py:181-212 (written for batch 1; batch 0 is skipped like :175)
@@ -36,11 +40,16 @@ def test_stage1_then_stage2_with_checkpoints(tmp_path):
     ck2 = torch.load(os.path.join(save, "Stage2", "latest_checkpoint_stage2.pth"), map_location="cpu", weights_only=False)
     assert {"con_augment_2", "critic_2", "gen_2", "epoch"} <= set(ck2)          # stage_2_train_fn.py:214-228
     assert all(torch.isfinite(v).all() for v in ck2["gen_2"].values() if v.is_floating_point())
+    st = ck2["opt_gen_2"]["state"]                                             # the fused Adam's moments, exported (:219-221)
+    assert len(st) == len(list(m2["gen_2"].parameters())) and float(st[0]["step"]) == 2.0 and st[0]["exp_avg"].abs().sum() > 0
+    assert float(ck2["opt_critic_2"]["state"][0]["step"]) == 10.0
     # resume: nothing left to do for epochs=1, weights come back from the checkpoint
     eng3, m3 = T.run(2, dev, epochs=1, batch=2, save_dir=save, synthetic=1, log=logs.append)
     assert any("Loaded checkpoint" in l for l in logs)
     for k, v in m3["gen_2"].state_dict().items():
         assert torch.equal(v.cpu(), ck2["gen_2"][k]), k
+    assert float(eng3.g2.fp.hyper[4]) == 2.0 and float(eng3.d.fp.hyper[4]) == 10.0   # optimizer state restored (:84-86)
+    assert torch.equal(eng3.g2.fp.m[:st[0]["exp_avg"].numel()].cpu(), st[0]["exp_avg"].reshape(-1))
 
 
 def test_stage1_on_captions_with_a_bert_encoder(tmp_path):
