@@ -53,7 +53,9 @@ int64_t sg_launch_count(void);
 /* tuning switches: "persist" = 1/0 persistent double-buffered conv kernel (default 1); "force_cg" / "force_bn" pin its
  * CTA-group size / tile width (0 = cost model); "tc2" = 1/0 CTA-pair tiles in the non-persistent kernels;
  * "wgrad2" = 1/0 unit-list weight-gradient kernel (default 1); "split" = 1/0 cut a partly filled last tile wave of the
- * persistent conv kernel along K over the idle SMs (default 1) */
+ * persistent conv kernel along K over the idle SMs (default 1); "pdl" = 1/0 programmatic dependent launch for the
+ * launches that follow; "wgrad_mc" = 1/0 TMA multicast in the weight-gradient kernel; "force_stages" caps the conv
+ * pipeline depth; "epi_alt" = 1/0 alternate-tile epilogue for conv tiles <= 64 columns wide (default 0, env SG_EPI_ALT) */
 int sg_set_option(const char* name, int value);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
