@@ -34,3 +34,21 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         CudaOps("bf16")
+
+
+def test_product_package_never_imports_the_oracle_or_the_tests():
+    """oracle/ and tests/emu_ops.py are the checker, never the thing shipped: no module of the package may import them
+    (bench.py may, for its cpu_baseline / --impl reference leg only; __graft_entry__.smoke() for its check)."""
+    import re
+    pkg = os.path.join(ROOT, "imagegenerator_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                for m in re.finditer(r"^\s*(from|import)\s+(oracle|emu_ops|tests)\b", src, re.M):
+                    bad.append((f, m.group(0).strip()))
+    assert not bad, bad
+    # and the ctypes binding has no CPU fallback: constructing the backend without the library / a device raises
+    src = open(os.path.join(pkg, "ops.py")).read()
+    assert "raise" in src and "libsgb200" in src
