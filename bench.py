@@ -12,10 +12,11 @@ augmentation update, Adam included, on synthetic text embeddings and images.  On
   e2e     the same metric through the public ``train_1`` call with HOST (pinned) batches: H2D copies of
           images / embeddings / noise and the D2H loss read are inside the timed region
   roofline  dominant kernel timed live with CUDA events on its launch stream
-  cpu_baseline  the oracle (torch-CPU restatement of the reference; /root/reference does not exist on
-          the GPU box) on a bounded sample: B=16 fp32 outer steps
+  cpu_baseline  the UNMODIFIED reference ``train_1`` (sources carried by oracle/make_ref.py; under the torch_xla / GCS
+          stubs of oracle/ref_harness.py) on the box's host cores, batch 128, a bounded number of steps; the
+          ``stage2`` section carries the same for ``train_2`` at batch 8
 
-``--impl reference`` times that CPU path alone with all host threads.
+``--impl reference`` times that CPU path alone with all host threads at the same batch / steps / warm-up.
 """
 import argparse
 import json
@@ -166,44 +167,138 @@ class IdentityHead(torch.nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_steps(B, steps, warmup, threads):
-    """Oracle outer steps on the host cores (fp32, like the reference on CPU).  Returns img/s."""
+class _TimedLoader:
+    """The loader handed to the reference's train function: yields pre-built host batches and stamps the wall clock at
+    every ``__next__`` -- the time between two stamps is one whole outer step of the reference's loop body."""
+
+    def __init__(self, batches):
+        self.batches, self.stamps = batches, []
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __iter__(self):
+        for b in self.batches:
+            self.stamps.append(time.perf_counter())
+            yield b
+        self.stamps.append(time.perf_counter())
+
+    def step_seconds(self):
+        return [b - a for a, b in zip(self.stamps[:-1], self.stamps[1:])]
+
+
+def cpu_reference_train(stage, B, steps, warmup, threads):
+    """The reference's OWN train function on the host cores.
+
+    kind "reference": the unmodified ``train_1`` (``train_2`` with the two one-token fixes of SURVEY.md section 0) compiled
+    from the reference's sources -- /root/reference in the build container, the archive packed by oracle/make_ref.py on the
+    GPU box -- under the torch_xla / google.cloud.storage / SummaryWriter stubs of oracle/ref_harness.py, synthetic text
+    table, no checkpoint I/O in the timed region.
+    kind "port": the oracle's restatement (oracle/stackgan_oracle.py), only when neither source is present.
+    Returns dict(ips, mean_s, kind, steps_s)."""
+    from oracle import ref_harness as H
     from oracle import stackgan_oracle as O
     torch.set_num_threads(threads)
-    ps = O.init_all(42, with_stage2=False)
-    ca, d1, g1 = ps["con_augment_1"], ps["critic_1"], ps["gen_1"]
-    tr = dict(ca=O.Trainer(ca), d1=O.Trainer(d1), g1=O.Trainer(g1))
-    times = []
-    for s in range(warmup + steps):
-        b = O.synthetic_batch(B, 1, s)
-        tem = b["tem"].clone().requires_grad_(True)
-        t0 = time.perf_counter()
-        O.stage1_step(ca, d1, g1, b["real"], tem, b["perm"], b["z"], b["eps_ca"], b["eps_gp"], tr)
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt)
-    times.sort()
-    med = times[len(times) // 2]
-    return B / med, med
+    n = warmup + steps
+    if not H.reference_available():
+        ps = O.init_all(42, with_stage2=(stage == 2))
+        times = []
+        if stage == 1:
+            ca, d1, g1 = ps["con_augment_1"], ps["critic_1"], ps["gen_1"]
+            tr = dict(ca=O.Trainer(ca), d1=O.Trainer(d1), g1=O.Trainer(g1))
+        else:
+            tr = dict(ca2=O.Trainer(ps["con_augment_2"]), d2=O.Trainer(ps["critic_2"]), g2=O.Trainer(ps["gen_2"]))
+        for s in range(n):
+            b = O.synthetic_batch(B, stage, s)
+            t0 = time.perf_counter()
+            if stage == 1:
+                O.stage1_step(ca, d1, g1, b["real"], b["tem"].clone().requires_grad_(True), b["perm"], b["z"], b["eps_ca"],
+                              b["eps_gp"], tr)
+            else:
+                O.stage2_step(ps["con_augment_1"], ps["gen_1"], ps["con_augment_2"], ps["critic_2"], ps["gen_2"], b["real"],
+                              b["tem"], b["perm"], b["z"], b["eps_ca"], b["eps_ca2"], b["eps_gp"], tr)
+            times.append(time.perf_counter() - t0)
+        ts = times[warmup:]
+        mean = sum(ts) / len(ts)
+        return dict(ips=B / mean, mean_s=mean, kind="port", steps_s=ts)
+    # ---- the unmodified reference
+    import random
+    H.reset_store()
+    H.seed_everything(1234)
+    torch.manual_seed(42)                                                    # train.py:66
+    CA = H.load("con_augment").ConditioningAugmentation
+    ca1 = CA(512, 256, 128)
+    d1 = H.load("discrminator_1").StageIDiscriminator(512, 128)
+    g1 = H.load("generator_1").StageIGenerator(128, 100)
+    gd = torch.Generator().manual_seed(0)
+    hw = 64 if stage == 1 else 256
+    table = torch.randn(B, 512, generator=gd)
+    enc, head = H.TableEncoder(table), H.IdentityHead()
+    batches = [({"idx": torch.arange(B)}, torch.randn(B, 3, hw, hw, generator=gd).clamp_(-1, 1)) for _ in range(n)]
+    loader = _TimedLoader(batches)
+    mk = lambda m, lr=1e-3: torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.999))       # train.py:92-102
+    sch = lambda o: torch.optim.lr_scheduler.StepLR(o, step_size=100, gamma=0.5)               # train.py:105-113
+    if stage == 1:
+        opts = [mk(enc, 0.0), mk(head, 0.0), mk(ca1), mk(d1), mk(g1)]
+        fn = H.load("stage_1_train_fn").train_1
+        models = [enc, head, ca1, d1, g1]
+    else:
+        ca2 = CA(512, 256, 128)
+        d2 = H.load("discriminator_2").StageIIDiscriminator(512, 128)
+        g2 = H.load("generator_2").StageIIGenerator()
+        import tempfile
+        with tempfile.NamedTemporaryFile() as tmp:                           # the Stage-I checkpoint train_2 loads (:65-72)
+            torch.save(dict(textEncoder=enc.state_dict(), projection_head=head.state_dict(),
+                            con_augment_1=ca1.state_dict(), gen_1=g1.state_dict()), tmp.name)
+            with open(tmp.name, "rb") as f:
+                H.store()["./checkpoint/Stage1/latest_checkpoint_stage1.pth"] = f.read()
+        opts = [mk(ca2), mk(d2), mk(g2)]
+        fn = H.load("stage_2_train_fn").train_2
+        models = [enc, head, ca1, ca2, g1, d2, g2]
+        random.seed(99)
+    scheds = [sch(o) for o in opts]
+    with H.quiet():
+        # epoch 1 of 2: one pass over the loader, and no checkpoint upload (the reference saves when epoch % 10 == 0)
+        fn(models, opts, scheds, loader, 2, "cpu", B, start_epoch=1)
+    ts = loader.step_seconds()[warmup:]
+    mean = sum(ts) / len(ts)
+    return dict(ips=B / mean, mean_s=mean, kind="reference", steps_s=ts)
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 def run_reference(args):
+    """``--impl reference``: the reference's own CPU path on this arm's config -- Stage-I, batch 128 per step, the same
+    --steps / --warmup.  A batch-128 outer step is ~2.1 TFLOP as executed (~3 s on 16 host cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = 16
-    ips, med = cpu_reference_steps(B, max(1, min(args.steps, 5)), min(args.warmup, 1), threads)
+    B, K, W = args.batch, args.steps, args.warmup
+    r = cpu_reference_train(1, B, K, W, threads)
+    ips, mean = r["ips"], r["mean_s"]
+    what = ("unmodified reference train_1 (stage_1_train_fn.py:19-240 under the torch_xla / GCS stubs, synthetic text table)"
+            if r["kind"] == "reference" else "oracle port (torch-CPU restatement of stage_1_train_fn.py:93-196)")
     line = {
         "impl": "reference", "metric": "stackgan_stage1_train_images_per_sec", "value": round(ips, 3),
-        "unit": "images/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1),
-        "ms_per_step": round(med * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": round(mean * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": 128, "cpu_sample_batch_per_step": B,
-                   "note": "the reference's own CPU path (torch CPU operators) on a bounded sample of the workload: "
-                           "outer steps at batch 16 instead of 128 (a batch-128 step is ~2.7 s on 16 cores)"},
-        "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle (torch-CPU restatement of stage_1_train_fn.py:93-196) B={B} fp32 outer steps, median"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B, "parallelism": "cpu",
+                   "note": "the reference's own CPU path on the box's host cores at the SAME batch (128) and step counts as "
+                           "the GPU arm; one process (the reference's data parallelism is one process per TPU core)"},
+        "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": threads, "kind": r["kind"],
+                         "cpu_model": _cpu_model(), "torch_threads": torch.get_num_threads(), "torch": torch.__version__,
+                         "sample": f"{what}: B={B} fp32, {W} warm-up + {K} timed outer steps, mean"},
         "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -529,6 +624,22 @@ def main():
     h2d = B * 3 * 64 * 64 * 4 + B * 8 + 5 * B * 100 * 4 + 5 * B * 4       # images + idx + z + gp eps (fp32)
     d2h = 4 * 4
 
+    # ---- data-parallel check on the hardware path just timed: after W + 2K + 2 outer steps (graph segments + NCCL) every
+    # parameter must be bit-identical on all ranks (xm.optimizer_step semantics: same averaged gradient, same Adam state)
+    dp_check = None
+    if world > 1:
+        worst = torch.zeros(1, device=dev, dtype=torch.float64)
+        for fp in (eng.d.fp, eng.g.fp, eng.ca.fp):
+            root = fp.flat.clone()
+            dist.broadcast(root, 0)
+            worst = torch.maximum(worst, (fp.flat.double() - root.double()).abs().max().reshape(1))
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        finite = torch.tensor([float(all(torch.isfinite(fp.flat).all().item() for fp in (eng.d.fp, eng.g.fp, eng.ca.fp)))], device=dev)
+        dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+        dp_check = {"params_bit_identical_across_ranks": bool(worst.item() == 0.0), "max_abs_diff": float(worst.item()),
+                    "params_finite": bool(finite.item() == 1.0), "outer_steps": W + 2 * K + 3,
+                    "oracle_check": "tests/dp_nccl_worker.py (averaged-gradient oracle, 2 ranks)"}
+
     s1_bytes_per_step = (comm.bytes_reduced // (W + 2 * K + 2)) if comm else 0
     extras = {}
     if not args.no_extras and args.mode == "bf16":
@@ -585,15 +696,28 @@ def main():
                          "kernel_ms": round(kms, 5)},
             "clocks": clocks,
         }
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         line.update(extras)
     if world > 1:
         dist.barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            ips, med = cpu_reference_steps(16, 3, 1, threads)
-            line["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle (torch-CPU restatement of the reference step) B=16 fp32, 1 warm-up + 3 outer steps, median"}
+            r = cpu_reference_train(1, B, 3, 1, threads)
+            line["cpu_baseline"] = {"value": round(r["ips"], 3), "unit": "images/s", "cores": threads, "kind": r["kind"],
+                                    "cpu_model": _cpu_model(),
+                                    "sample": f"{'unmodified reference train_1' if r['kind'] == 'reference' else 'oracle port'} on the host "
+                                              f"cores, Stage-I B={B} fp32, 1 warm-up + 3 timed outer steps, mean "
+                                              f"({r['mean_s']:.2f} s/step)"}
+            if "stage2" in line:
+                B2 = 8
+                r2 = cpu_reference_train(2, B2, 2, 1, threads)
+                line["stage2"]["cpu_baseline"] = {
+                    "value": round(r2["ips"], 4), "unit": "images/s", "cores": threads, "kind": r2["kind"],
+                    "sample": f"{'reference train_2 (two one-token fixes)' if r2['kind'] == 'reference' else 'oracle port'} on the host "
+                              f"cores, Stage-II B={B2} fp32 (the GPU figure is at B=64; a B=64 step is ~18 TFLOP), 1 warm-up + 2 "
+                              f"timed outer steps, mean ({r2['mean_s']:.1f} s/step)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

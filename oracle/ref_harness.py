@@ -11,8 +11,10 @@ and two one-token in-memory patches are applied to the Stage-II sources
 (never copied to disk): ``stage_2_train_fn.py:67`` ``blob.`` -> ``blob_1.`` and
 ``discriminator_2.py:28`` ``self.down_sampler(x)`` -> ``self.down_sampler(img)``.
 
-/root/reference does not exist on the GPU box: everything here is used only by
-``oracle/make_golden.py`` and by CPU tests that skip when it is absent.
+/root/reference does not exist on the GPU box: there the same sources come from the archive
+oracle/_ref/reference_src.zip packed by ``oracle/make_ref.py`` (git-ignored, travels with gpurun).  Used by
+``oracle/make_golden*.py``, by CPU tests that skip when neither is present, and by ``bench.py --impl reference`` /
+its ``cpu_baseline`` leg (the unmodified reference timed on the host cores).
 """
 from __future__ import annotations
 
@@ -27,10 +29,23 @@ import types
 import torch
 
 REFERENCE_ROOT = os.environ.get("SG_REFERENCE_ROOT", "/root/reference")
+# where /root/reference is absent (the GPU box): the archive of the same files packed by oracle/make_ref.py
+REFERENCE_ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_src.zip")
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "stage_1_train_fn.py"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "stage_1_train_fn.py")) or os.path.isfile(REFERENCE_ARCHIVE)
+
+
+def reference_source(name: str):
+    """(source text, origin path) of reference module ``name``: from the tree when it is here, else from the archive."""
+    path = os.path.join(REFERENCE_ROOT, name + ".py")
+    if os.path.isfile(path):
+        with open(path, "r") as f:
+            return f.read(), path
+    import zipfile
+    with zipfile.ZipFile(REFERENCE_ARCHIVE) as z:
+        return z.read(name + ".py").decode("utf-8"), REFERENCE_ARCHIVE + "/" + name + ".py"
 
 
 # --------------------------------------------------------------------------- stubs
@@ -165,9 +180,7 @@ def load(name: str) -> types.ModuleType:
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     _install_stubs()
-    path = os.path.join(REFERENCE_ROOT, name + ".py")
-    with open(path, "r") as f:
-        src = f.read()
+    src, path = reference_source(name)
     for old, new in _PATCHES.get(name, []):
         if old not in src:
             raise RuntimeError("patch anchor not found in %s" % path)

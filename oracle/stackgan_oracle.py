@@ -4,9 +4,9 @@ The reference's arithmetic lives in un-vendored, un-pinned PyTorch (SURVEY.md
 section 8c); this file restates every function on the hot path as a pure function
 of (parameter dict keyed by the reference's state_dict names, inputs, explicit
 noise) on torch CPU ops, so it can travel to the GPU box where /root/reference
-does not exist.  It is pinned against the real reference by
-tests/test_oracle_vs_reference.py (build container) and by the golden fixtures
-under tests/golden/ (everywhere).
+does not exist.  It is pinned against the real reference by the golden fixtures under tests/golden/
+(recorded from the unmodified reference by oracle/make_golden*.py through
+oracle/ref_harness.py; checked by tests/test_oracle_golden.py everywhere).
 
 All citations are relative to /root/reference/.
 """
@@ -336,17 +336,23 @@ def stage1_step(ca, d1, g1, real, tem, perm, z, eps_ca, eps_gp, tr, force=None, 
 
 
 # --------------------------------------------------------------------------- Stage-II outer step
-def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_gp, tr, sync=None):
+def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_gp, tr, sync=None, force=None):
     """One outer step of stage_2_train_fn.py:101-173 (with the :67 / discriminator_2.py:28 fixes).
 
     ca1/g1 are frozen and in eval mode (:52-63: running-stat BN in gen_1, CA still samples).
     G2/CA2 gradients ACCUMULATE over the five critic backward passes because
     fake_256 is not detached and opt_gen_2.zero_grad() only runs after the step
     (:131,:154,:163-168) -- reproduced here.  tr = dict(ca2=, d2=, g2=).  ``sync(trainer)``, if given, runs right
-    before each optimizer step: the gradient mean over replicas of xm.optimizer_step (:155,:164,:167)."""
-    out = {"loss_critic": [], "critic_grads": []}
+    before each optimizer step: the gradient mean over replicas of xm.optimizer_step (:155,:164,:167).
+    ``force``: six critic snapshots (before each critic iteration and before the generator step) to overwrite the
+    critic with -- re-synchronises a lower-precision run with a reference trajectory in the parity tests; the
+    snapshots of this run are returned as ``critic_before``."""
+    out = {"loss_critic": [], "critic_grads": [], "critic_before": [], "scores": []}
     tem_mis = tem[perm]
     for it in range(N_CRITIC):
+        if force is not None:
+            _force(d2, force[it])
+        out["critic_before"].append(_snap(d2))
         with torch.no_grad():                                   # frozen params => no graph needed
             c_hat1, _, _ = ca_forward(ca1, tem, eps_ca1[it])    # :124
             fake_64 = g1_forward(g1, torch.cat((c_hat1, z[it]), dim=1), training=False)  # :126-128
@@ -361,6 +367,8 @@ def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_
         loss_c.backward(retain_graph=True)                      # :154 (also accumulates into g2/ca2)
         out["critic_grads"].append(tr["d2"].grads())
         out["loss_critic"].append(loss_c.detach().clone())
+        out["scores"].append(dict(s_real=s_real.detach().clone(), s_mis=s_mis.detach().clone(),
+                                  s_fake=s_fake.detach().clone(), gp=gp.detach().clone()))
         if it == 0:
             out["g2_grads_it0"] = tr["g2"].grads()             # what one critic backward leaves in G2
             out["ca2_grads_it0"] = tr["ca2"].grads()
@@ -370,10 +378,14 @@ def stage2_step(ca1, g1, ca2, d2, g2, real, tem, perm, z, eps_ca1, eps_ca2, eps_
         if sync is not None:
             sync(tr["d2"])
         tr["d2"].opt.step()                                     # :155
+    if force is not None:
+        _force(d2, force[N_CRITIC])
+    out["critic_before"].append(_snap(d2))
     s = d2_forward(d2, fake, tem).view(-1)                      # :157
     lossG = -torch.mean(s) + kl_term(mu2, sigma2)               # :158-162
     lossG.backward()                                            # :163 (no zero_grad before)
     out["lossG"] = lossG.detach().clone()
+    out["s_gen"] = s.detach().clone()
     out["g2_grads"] = tr["g2"].grads()
     out["ca2_grads"] = tr["ca2"].grads()
     if sync is not None:

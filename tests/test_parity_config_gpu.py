@@ -1,0 +1,222 @@
+"""Parity at the BENCHMARKED configurations (BASELINE.json configs[1] and configs[2]): the CUDA train step against the
+oracle at Stage-I batch 128 and Stage-II batch 64, in bf16 (tensor-core) and fp32 (validation) mode.
+
+Checker: the oracle itself (oracle/stackgan_oracle.py, pinned to the unmodified reference by tests/golden) run on the
+GPU in fp64 -- tests/gpu_oracle.py.  Every quantity the reference's step produces is compared: fake images, the four
+critic scores, the gradient penalty, both losses, and -- per parameter tensor -- the gradients each optimizer sees at
+its step (for Stage-II's generator that is the sum over the five critic backward passes plus lossG's,
+stage_2_train_fn.py:131,154,163-168).  The critic is re-synchronised to the fp64 trajectory before each iteration
+(see tests/test_stage1_gpu.py) so that iterations 2..5 compare kernels, not Adam's sign(g) amplification.
+
+Three numbers per tensor go into the report (gpurun_out/parity_<stage>_<mode>_B<batch>.txt, copied to profiles/):
+  rel_l2      ||got - ref|| / ||ref||
+  yardstick   the same for the *reference precision*: the fp32 oracle (fp32 mode) or the engine's dataflow evaluated
+              exactly with ideal bf16 storage rounding (bf16 mode, tests/emu_ops.py on the GPU) -- what no
+              implementation storing bf16 activations can beat
+  worst/bound max |got-ref| / (rtol |ref| + atol max|ref| + 3 yardstick_max)   with BASELINE.json's rtol / atol
+
+A gradient bound can never go vacuous here: the test ASSERTS that the yardstick itself is small (< YARD_MAX of the
+tensor's max, < YARD_L2 in relative L2) before it accepts `3 x yardstick` as slack, and independently requires
+rel_l2(got) <= L2_FACTOR x rel_l2(yardstick) + L2_FLOOR.
+"""
+import os
+
+import pytest
+import torch
+
+import gpu_oracle as GO
+from test_stage1_gpu import _modules as _modules1, _ref_table as _ref_table1, _run_teacher_forced as _run_tf1
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": (1e-4, 1e-4), "bf16": (2e-2, 1e-3)}
+YARD_MAX = 0.2         # yardstick max-error / max|ref| must stay below this for the 3x-yardstick slack to count
+YARD_L2 = 0.2          # and its relative L2 below this
+L2_FACTOR = 3.0        # rel_l2(got) <= L2_FACTOR * rel_l2(yardstick) + L2_FLOOR[mode]
+L2_FLOOR = {"fp32": 2e-4, "bf16": 2e-2}
+ZERO_RMS = {"fp32": 1e-7, "bf16": 1e-4}
+REPORT_ONLY = os.environ.get("SG_PARITY_REPORT_ONLY") == "1"
+
+
+def _is_grad(k):
+    return "/" in k or k == "dtem"
+
+
+def compare(mode, want, got, yard, tag):
+    """Returns (report lines, failures); the last report line summarises the gradient rows."""
+    import math
+    rt, at = TOL[mode]
+    lines, fails, grels = [], [], []
+    hdr = f"{'tensor':58s} {'rel_l2':>10s} {'yardstick':>10s} {'worst/bound':>11s} {'max|ref|':>10s} {'yard/max':>9s}"
+    lines.append(hdr)
+    for k, r in want.items():
+        if r is None or k not in got:
+            continue
+        g = got[k].detach().double().cpu().reshape(-1)
+        r = r.detach().double().cpu().reshape(-1)
+        y = yard[k].detach().double().cpu().reshape(-1) if k in yard and yard[k] is not None else None
+        isg = _is_grad(k)
+        if isg and r.norm().item() / max(r.numel(), 1) ** 0.5 < 1e-12:
+            # exactly zero in exact arithmetic (the critic's compress.* gradients: the real / mismatched / fake text terms
+            # cancel, stage_1_train_fn.py:140-144) -- nothing to be relative to; hold the result to an absolute rms
+            rms = g.norm().item() / max(g.numel(), 1) ** 0.5
+            lines.append(f"{k:58s} zero in exact arithmetic; rms(got) {rms:.3e}")
+            if rms > ZERO_RMS[mode]:
+                fails.append(f"[{tag}] {k}: reference is exactly zero, got rms {rms:.3e} > {ZERO_RMS[mode]}")
+            continue
+        scale = max(r.abs().max().item(), 1e-30)
+        rn = max(r.norm().item(), 1e-30)
+        rel = (g - r).norm().item() / rn
+        yrel = (y - r).norm().item() / rn if y is not None else 0.0
+        ymax = (y - r).abs().max().item() if y is not None else 0.0
+        bound = rt * r.abs() + at * (scale if isg else 1.0) + 3.0 * ymax + 1e-7
+        worst = ((g - r).abs() / bound).max().item()
+        lines.append(f"{k:58s} {rel:10.3e} {yrel:10.3e} {worst:11.3f} {scale:10.3e} {ymax / scale:9.2e}")
+        if isg:
+            grels.append(rel)
+            if ymax / scale > YARD_MAX or yrel > YARD_L2:
+                fails.append(f"[{tag}] {k}: yardstick too coarse to judge with (max {ymax / scale:.2e} of max|ref|, rel_l2 {yrel:.2e})")
+            if rel > L2_FACTOR * yrel + L2_FLOOR[mode]:
+                fails.append(f"[{tag}] {k}: rel_l2 {rel:.3e} > {L2_FACTOR} x yardstick {yrel:.3e} + {L2_FLOOR[mode]}")
+        if worst > 1.0:
+            fails.append(f"[{tag}] {k}: max err / bound = {worst:.3f} (rel_l2 {rel:.3e}, yardstick {yrel:.3e})")
+    if grels:
+        gm = math.exp(sum(math.log(max(v, 1e-30)) for v in grels) / len(grels))
+        lines.append(f"# {tag}: {len(grels)} gradient tensors, geometric-mean rel_l2 {gm:.3e}, max {max(grels):.3e}; "
+                     f"{len(fails)} failures")
+    return lines, fails
+
+
+def _dump(name, lines):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", name), "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------ Stage-I, B=128
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_stage1_batch128(mode):
+    from imagegenerator_b200.ops import CudaOps
+    from emu_ops import EmuOps
+    B = 128
+    b, ref = GO.stage1(B, torch.float64)
+    want = _ref_table1(ref)
+    if mode == "fp32":
+        _, r32 = GO.stage1(B, torch.float32, force=ref["critic_before"])
+        yard = _ref_table1(r32)
+    else:
+        yard = _run_tf1(EmuOps(torch.bfloat16, device="cuda"), b, ref)
+    got = _run_tf1(CudaOps(mode), b, ref)
+    torch.cuda.synchronize()
+    lines, fails = compare(mode, want, got, yard, f"stage1 {mode} B{B}")
+    _dump(f"parity_stage1_{mode}_B{B}.txt", lines)
+    assert REPORT_ONLY or not fails, "\n".join(fails[:12])
+
+
+# ------------------------------------------------------------------------------------------------ Stage-II
+def _modules2():
+    from imagegenerator_b200.con_augment import ConditioningAugmentation
+    from imagegenerator_b200.discrminator_1 import StageIDiscriminator
+    from imagegenerator_b200.discriminator_2 import StageIIDiscriminator
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    from imagegenerator_b200.generator_2 import StageIIGenerator
+    torch.manual_seed(42)
+    return dict(ca1=ConditioningAugmentation(512, 256, 128), d1=StageIDiscriminator(512, 128), g1=StageIGenerator(128, 100),
+                ca2=ConditioningAugmentation(512, 256, 128), d2=StageIIDiscriminator(512, 128), g2=StageIIGenerator())
+
+
+def _run_tf2(ops, b, ref):
+    """One Stage-II outer step with the critic re-synchronised to ``ref``'s trajectory before every iteration."""
+    from imagegenerator_b200.engine2 import Stage2Engine
+    ms = _modules2()
+    eng = Stage2Engine(ms["ca1"], ms["g1"], ms["ca2"], ms["d2"], ms["g2"], b["real"].shape[0], ops=ops)
+    dv = lambda t: t.to(ops.device).to(ops.f32).contiguous()
+    eng.load_batch(dv(b["real"]), dv(b["tem"]), dv(b["tem"][b["perm"]]))
+    z, e1, e2, eg = dv(b["z"]), dv(b["eps_ca"]), dv(b["eps_ca2"]), dv(b["eps_gp"])
+    c = lambda t: t.detach().double().cpu().clone()
+    load = lambda m, sd: m.load_state_dict({k: v.float() for k, v in sd.items()})
+    out = {}
+    for it in range(5):
+        if it > 0:
+            load(ms["d2"], ref["critic_before"][it])
+            eng.d.refresh_weights()
+        eng.critic_iteration(z[it], e1[it], e2[it], eg[it])
+        out[f"it{it} s_real"], out[f"it{it} s_mis"], out[f"it{it} s_fake"] = c(eng.d.score[0]), c(eng.d.score[1]), c(eng.d.score[2])
+        out[f"it{it} gp"], out[f"it{it} loss_critic"] = c(eng.losses[1]), c(eng.losses[0])
+        for k, v in ms["d2"].named_parameters():
+            out[f"it{it} dD2/{k}"] = c(v.grad)
+        if it == 0:
+            out["it0 fake_64"] = c(eng.g1.out.permute(0, 3, 1, 2))
+            out["it0 fake_256"] = c(eng.g2.out.permute(0, 3, 1, 2))
+            eng.sync_grads()
+            for k, v in ms["g2"].named_parameters():
+                out[f"it0 dG2/{k}"] = c(v.grad)
+            for k, v in ms["ca2"].named_parameters():
+                out[f"it0 dCA2/{k}"] = c(v.grad)
+    load(ms["d2"], ref["critic_before"][5])
+    eng.d.refresh_weights()
+    # the generator step with its optimizer steps held back, so that the gradients G2 / CA2 are stepped with can be read
+    ops_step = eng.optimizer_step
+    grads = {}
+
+    def capture(fp):
+        eng.side.join()
+        if fp is eng.g2.fp:
+            eng.g2.fold_grads()
+            for k, v in ms["g2"].named_parameters():
+                grads[f"G dG2/{k}"] = c(v.grad)
+        else:
+            for k, v in ms["ca2"].named_parameters():
+                grads[f"G dCA2/{k}"] = c(v.grad)
+        ops_step(fp)
+    eng.optimizer_step = capture
+    eng.generator_step()
+    out.update(grads)
+    out["G s_fake"], out["lossG"] = c(eng.d.score[2]), c(eng.losses[2])
+    return out
+
+
+def _ref_table2(ref):
+    t = {}
+    f = ref["first"]
+    t["it0 fake_64"], t["it0 fake_256"] = f["fake_64"], f["fake"]
+    for it in range(5):
+        sc = ref["scores"][it]
+        for k in ("s_real", "s_mis", "s_fake", "gp"):
+            t[f"it{it} {k}"] = sc[k]
+        t[f"it{it} loss_critic"] = ref["loss_critic"][it]
+        for k, v in ref["critic_grads"][it].items():
+            t[f"it{it} dD2/{k}"] = v
+    for k, v in ref["g2_grads_it0"].items():
+        t[f"it0 dG2/{k}"] = v
+    for k, v in ref["ca2_grads_it0"].items():
+        t[f"it0 dCA2/{k}"] = v
+    t["G s_fake"], t["lossG"] = ref["s_gen"], ref["lossG"]
+    for k, v in ref["g2_grads"].items():
+        t[f"G dG2/{k}"] = v
+    for k, v in ref["ca2_grads"].items():
+        t[f"G dCA2/{k}"] = v
+    return t
+
+
+@pytest.mark.parametrize("mode,B", [("bf16", 64), ("fp32", 64), ("bf16", 16)])
+def test_stage2_config_batch(mode, B):
+    from imagegenerator_b200.ops import CudaOps
+    from emu_ops import EmuOps
+    b, ref = GO.stage2(B, torch.float64)
+    want = {k: (v.detach().double().cpu() if torch.is_tensor(v) else v) for k, v in _ref_table2(ref).items()}
+    force = ref["critic_before"]
+    del ref
+    torch.cuda.empty_cache()
+    if mode == "fp32":
+        _, r32 = GO.stage2(B, torch.float32, force=force)
+        yard = {k: (v.detach().double().cpu() if torch.is_tensor(v) else v) for k, v in _ref_table2(r32).items()}
+        del r32
+    else:
+        yard = _run_tf2(EmuOps(torch.bfloat16, device="cuda"), b, {"critic_before": force})
+    torch.cuda.empty_cache()
+    got = _run_tf2(CudaOps(mode), b, {"critic_before": force})
+    torch.cuda.synchronize()
+    lines, fails = compare(mode, want, got, yard, f"stage2 {mode} B{B}")
+    _dump(f"parity_stage2_{mode}_B{B}.txt", lines)
+    assert REPORT_ONLY or not fails, "\n".join(fails[:12])
