@@ -9,7 +9,7 @@ The arithmetic runs in the CUDA kernels behind ``imagegenerator_b200.ops`` (no C
 import torch
 from torch import nn
 
-from .layers import DenseParams
+from .layers import DenseParams, no_autograd
 
 
 class ConditioningAugmentation(nn.Module):
@@ -37,4 +37,4 @@ class ConditioningAugmentation(nn.Module):
         if eps is None:
             eps = torch.randn(tem.shape[0], self.c_dim, device=tem.device, dtype=torch.float32)
         st = rt.forward(tem, eps, None)
-        return st.c_hat.clone(), st.mu.clone(), st.sigma.clone()
+        return tuple(no_autograd(t.clone(), self) for t in (st.c_hat, st.mu, st.sigma))

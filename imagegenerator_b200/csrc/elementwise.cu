@@ -181,7 +181,9 @@ struct GpSeedF {
     const T* g; const float* sq; float coef; T* v; int64_t per_sample;
     __device__ void operator()(int64_t i4) const {
         int64_t e = i4 * 4;
-        float f = coef * (1.f - rsqrtf(sq[e / per_sample]));
+        // d||g||/dg at g = 0 is taken as 0, like torch's norm backward (1 - 1/0 would seed NaNs through g * -inf)
+        const float q = sq[e / per_sample];
+        float f = q > 0.f ? coef * (1.f - rsqrtf(q)) : 0.f;
         F4 a = ld4(g + e), r;
 #pragma unroll
         for (int j = 0; j < 4; ++j) r.v[j] = a.v[j] * f;
@@ -236,7 +238,14 @@ struct AdamF {
     }
 };
 
-__global__ void adam_tick_kernel(float* hyper) { hyper[4] += 1.f; }
+// hyper[4]: the step as a float (bias correction; saturates harmlessly at 2^24, where beta^t == 0 anyway);
+// hyper[5], hyper[6]: the exact count as lo + 2^23 * hi for checkpoints
+__global__ void adam_tick_kernel(float* hyper) {
+    hyper[4] += 1.f;
+    float lo = hyper[5] + 1.f;
+    if (lo >= 8388608.f) { lo = 0.f; hyper[6] += 1.f; }
+    hyper[5] = lo;
+}
 
 struct FillF {
     float* p; float val;

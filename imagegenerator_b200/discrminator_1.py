@@ -9,7 +9,7 @@ head is affine in (features, compressed text) and is evaluated without materiali
 import torch
 from torch import nn
 
-from .layers import ConvParams, DenseParams, Slot, block
+from .layers import ConvParams, DenseParams, Slot, block, no_autograd
 
 
 class _CriticBase(nn.Module):
@@ -46,7 +46,7 @@ class _CriticBase(nn.Module):
         rt.ops.nchw_to_nhwc(img.contiguous().float(), rt.group_view(rt.a[0], 0, 1))
         rt.set_text(tem.contiguous().float(), None)
         rt.forward(0, 1, dup_first=1, training=self.training)
-        return rt.score[0].clone().reshape(-1, 1)
+        return no_autograd(rt.score[0].clone().reshape(-1, 1), self)
 
 
 class StageIDiscriminator(_CriticBase):

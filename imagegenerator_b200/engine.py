@@ -108,7 +108,7 @@ class CART:
     def ensure(self, B):
         ops, m = self.ops, self.m
         if self.fp is None:
-            self.fp = FlatParams(m, ops.device, dtype=ops.f32)
+            self.fp = FlatParams.of(m, ops.device, dtype=ops.f32)
         if self.st is None or self.st.B != B:
             f = ops.f32
             self.st = SimpleNamespace(
@@ -154,7 +154,7 @@ class GenRT:
 
     def __init__(self, ops, module, B, out=None):
         self.ops, self.m, self.B = ops, module, B
-        self.fp = FlatParams(module, ops.device, dtype=ops.f32)
+        self.fp = FlatParams.of(module, ops.device, dtype=ops.f32)
         self.layers = [_LayerRT(ops, c, bn) for c, bn in module.conv_layers()]
         self.cg = ops.empty((B, 1, 1, self.layers[0].co))
         self.dcg = ops.empty((B, 1, 1, self.layers[0].co))
@@ -250,7 +250,7 @@ class CriticRT:
 
     def __init__(self, ops, module, B):
         self.ops, self.m, self.B = ops, module, B
-        self.fp = FlatParams(module, ops.device, dtype=ops.f32)
+        self.fp = FlatParams.of(module, ops.device, dtype=ops.f32)
         self.layers = [_LayerRT(ops, c, bn) for c, bn in module.conv_layers()]
         G, f32, f64 = self.NG, ops.f32, ops.f64
         h = module.in_hw
@@ -493,7 +493,7 @@ def export_optimizer_state(opt, fp):
     """Mirror the fused Adam state (flat moments + device step counter) into a torch.optim.Adam so that
     ``opt.state_dict()`` checkpoints carry exp_avg / exp_avg_sq / step like the reference's
     (stage_1_train_fn.py:218-222, stage_2_train_fn.py:219-221)."""
-    step = float(fp.hyper[4].item())
+    step = float(fp.step_count())
     off = 0
     for p in fp.params:
         k = p.numel()
@@ -519,7 +519,7 @@ def import_optimizer_state(opt, fp):
             step, found = t, found + 1
         off += k
     if step is not None:
-        fp.hyper[4] = step
+        fp.set_step(step)
     return found
 
 

@@ -69,7 +69,7 @@ class Gen2RT:
 
     def __init__(self, ops, module, B, x_in=None, out=None):
         self.ops, self.m, self.B = ops, module, B
-        self.fp = FlatParams(module, ops.device, dtype=ops.f32)
+        self.fp = FlatParams.of(module, ops.device, dtype=ops.f32)
         m = module
         f32 = ops.f32
         self.ds0 = _LayerRT(ops, m.down_sampler[0], None)

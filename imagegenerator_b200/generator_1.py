@@ -9,7 +9,7 @@ parities x 2x2 taps); BN statistics/apply/ReLU and Tanh are CUDA kernels (imageg
 import torch
 from torch import nn
 
-from .layers import ConvParams, Slot, block
+from .layers import ConvParams, Slot, block, no_autograd
 
 G1_CHANNELS = (192, 96, 48, 24)
 
@@ -49,4 +49,4 @@ class StageIGenerator(nn.Module):
         rt.forward(training=self.training)
         out = torch.empty(x.shape[0], 3, 64, 64, device=x.device, dtype=torch.float32)
         rt.ops.nhwc_to_nchw(rt.out, out)
-        return out
+        return no_autograd(out, self)

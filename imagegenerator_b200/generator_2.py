@@ -11,7 +11,7 @@ tcgen05 implicit-GEMM kernel, ConvT as its data-gradient direction).
 import torch
 from torch import nn
 
-from .layers import ConvParams, BNParams, Slot, block
+from .layers import ConvParams, BNParams, Slot, block, no_autograd
 
 
 class ResidualBlock(nn.Module):
@@ -61,4 +61,4 @@ class StageIIGenerator(nn.Module):
         rt.forward(c_hat.contiguous().float(), training=self.training)
         out = torch.empty(B, 3, 256, 256, device=img_64.device, dtype=torch.float32)
         rt.ops.nhwc_to_nchw(rt.out, out)
-        return out
+        return no_autograd(out, self)

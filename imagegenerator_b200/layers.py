@@ -75,10 +75,61 @@ def block(conv, c_bn):
     return nn.Sequential(conv, BNParams(c_bn), Slot())
 
 
+class _NoAutograd(torch.autograd.Function):
+    """Identity whose backward explains itself.  The module-level forwards run hand-written kernels and carry no autograd
+    graph; the reference's callers differentiate through them (``loss.backward(retain_graph=True)``, and the critic twice
+    with ``create_graph=True``, stage_1_train_fn.py:147, utils.py:15-21).  Instead of torch's generic "element 0 of tensors
+    does not require grad", a caller who tries gets told where the gradients are produced."""
+
+    @staticmethod
+    def forward(ctx, out, anchor, name):
+        ctx.name = name
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise RuntimeError(
+            f"{ctx.name}.forward() runs hand-written CUDA kernels and does not record an autograd graph: "
+            "backward()/autograd.grad through it is not supported.  The gradients of the StackGAN step (including the "
+            "WGAN-GP double backward) are produced by imagegenerator_b200.stage_1_train_fn.train_1 / "
+            "stage_2_train_fn.train_2 (engine.Stage1Engine / engine2.Stage2Engine), which write .grad of every parameter.")
+
+
+def no_autograd(out, module):
+    """Tag ``out`` so that differentiating through ``module.forward`` raises a clear error (only when grad mode is on and the
+    module has trainable parameters; otherwise ``out`` is returned as is)."""
+    if not torch.is_grad_enabled():
+        return out
+    anchor = next((p for p in module.parameters() if p.requires_grad), None)
+    if anchor is None:
+        return out
+    return _NoAutograd.apply(out, anchor, type(module).__name__)
+
+
 class FlatParams:
     """All trainable parameters of a module re-pointed into ONE contiguous fp32 buffer, with a
     matching flat gradient buffer and Adam moments: one fused Adam launch and one all-reduce per
     optimizer, and ``module.state_dict()`` keeps working because the Parameters are views."""
+
+    @classmethod
+    def of(cls, module, device, dtype=torch.float32):
+        """THE flat buffer of ``module``: created on first use, then shared by every runtime built on that module (the
+        train engine, the module-level ``forward`` / ``gradient_penalty`` API, the sampler).  A second ``FlatParams`` would
+        re-point ``p.data`` / ``p.grad`` away from the buffers a live engine's Adam, all-reduce and captured CUDA graph
+        keep using -- training would silently stop while ``state_dict()`` reads the new copy."""
+        fp = module.__dict__.get("_flat")
+        if fp is not None:
+            if fp.flat.device != torch.device(device) or fp.flat.dtype != dtype:
+                raise RuntimeError(
+                    f"{type(module).__name__} already lives in a flat parameter buffer on {fp.flat.device} ({fp.flat.dtype}); "
+                    f"it cannot also be driven by an ops object on {torch.device(device)} ({dtype}) -- build a separate module")
+            if any(p.data.data_ptr() != v.data_ptr() for p, v in zip(fp.params, fp.views)):
+                raise RuntimeError(f"the parameters of {type(module).__name__} were re-pointed behind its flat buffer "
+                                   "(module.to(...) / p.data = ... after an engine was built)")
+            return fp
+        fp = cls(module, device, dtype=dtype)
+        module.__dict__["_flat"] = fp              # not a submodule / buffer: invisible to state_dict() and .to()
+        return fp
 
     def __init__(self, module, device, opt_hyper=None, dtype=torch.float32):
         ps = [p for p in module.parameters()]
@@ -92,20 +143,33 @@ class FlatParams:
         self.m = torch.zeros(npad, dtype=dtype, device=device)
         self.v = torch.zeros(npad, dtype=dtype, device=device)
         off = 0
-        self.views = {}
+        self.views = []
         for p in ps:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1).to(device=device, dtype=dtype))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
+            self.views.append(p.data)
             off += k
         lr, b1, b2, eps = opt_hyper or (1e-3, 0.9, 0.999, 1e-8)
-        # [lr, beta1, beta2, eps, step]: lives on the device so a captured CUDA graph sees updates
-        self.hyper = torch.tensor([lr, b1, b2, eps, 0.0], dtype=dtype, device=device)
+        # [lr, beta1, beta2, eps, step, step_lo, step_hi, -]: lives on the device so a captured CUDA graph sees updates.
+        # ``step`` (what the kernel's bias correction reads) is a float and stops counting exactly at 2^24; the exact count
+        # for checkpoints is step_hi * 2^23 + step_lo (``step_count`` / ``set_step``)
+        self.hyper = torch.tensor([lr, b1, b2, eps, 0.0, 0.0, 0.0, 0.0], dtype=dtype, device=device)
         for mod in module.modules():               # buffers follow to the device
             for name, buf in list(mod._buffers.items()):
                 if buf is not None:
                     mod._buffers[name] = buf.to(device=device, dtype=dtype if buf.is_floating_point() else buf.dtype)
+
+    def step_count(self):
+        h = self.hyper[4:7].tolist()
+        return int(h[2]) * (1 << 23) + int(h[1]) if (h[1] or h[2]) else int(h[0])
+
+    def set_step(self, t):
+        t = int(t)
+        self.hyper[4] = float(t)
+        self.hyper[5] = float(t % (1 << 23))
+        self.hyper[6] = float(t // (1 << 23))
 
     def set_lr(self, lr):
         # a scalar write from pageable host memory synchronises the stream: only touch the device when the value

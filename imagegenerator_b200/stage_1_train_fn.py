@@ -9,8 +9,8 @@ yields ``(dict_of_tensors, real_img_64)`` (:93).  What changes underneath:
     of hand-written sm_100a kernels (``Stage1Engine``); autograd is only used for the caller's text
     encoder / projection head, which receive d lossG / d tem from the kernels (:162-171);
   * ``xm.optimizer_step`` (gradient all-reduce over replicas + step) becomes an NCCL all-reduce of the
-    flat gradient buffer + a fused Adam kernel; the per-batch seed all-reduce (:98-105) becomes a
-    broadcast from rank 0;
+    flat gradient buffer + a fused Adam kernel; the per-batch seed all-reduce (:98-105) becomes ONE broadcast of
+    the master's base seed per call, from which every rank derives the same per-batch seeds (``_shared_seed_stream``);
   * checkpoints (:211-238) keep the reference's dictionary keys but go to ``save_dir`` on local disk
     instead of a GCS bucket (``bucket_name`` is accepted and ignored);
   * LR schedulers are stepped on every rank (the reference steps them on rank 0 only, :187-192, which
@@ -39,6 +39,20 @@ def _rank():
 def _adam_hyper(opt):
     g = opt.param_groups[0]
     return g["lr"], g["betas"][0], g["betas"][1], g["eps"]
+
+
+def _shared_seed_stream(world, dev):
+    """Where the per-batch seeds come from.  The reference draws one on the master and all-reduces it to every replica on
+    EVERY batch (stage_1_train_fn.py:98-105) -- a collective plus a device-to-host read in the middle of the step.  Here the
+    master's RNG is shared ONCE per call: rank 0 draws a base seed, it is broadcast, and every rank then draws the per-batch
+    seeds from its own copy of that generator -- identical on all ranks with no further communication.  World size 1 keeps
+    the reference's draw from the global RNG (None), so seeded single-process runs consume the RNG exactly like the
+    reference does."""
+    if world == 1:
+        return None
+    base = torch.randint(0, 2 ** 32 - 1, (1,)).to(dev)
+    dist.broadcast(base, 0)
+    return torch.Generator().manual_seed(int(base.item()))
 
 
 def make_allreduce(world):
@@ -99,9 +113,12 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         fp._lr_host = lr
         if resumed:
             eng.import_optimizer_state(opt, fp)                # Adam moments + step count of the checkpoint
+    if resumed:
+        eng.refresh_all()        # a caller-supplied engine packed its bf16 operands / collapsed head before the weights were loaded
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 
+    seed_stream = _shared_seed_stream(world, dev)
     loss_bufs = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
     pending = None
     for epoch in range(start_epoch, num_epochs):
@@ -109,10 +126,7 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
             # pageable host tensors are copied synchronously with the stream (the host would wait for the previous
             # step on every batch): go through pinned memory
             tokenized_texts = {k: pin(v).to(dev, non_blocking=True) for k, v in tokenized_texts.items()}
-            seed_t = torch.randint(0, 2 ** 32 - 1, (1,))      # :98-105: the master's seed for every replica
-            if world > 1:
-                seed_t = seed_t.to(dev)
-                dist.broadcast(seed_t, 0)
+            seed_t = torch.randint(0, 2 ** 32 - 1, (1,), generator=seed_stream)   # :98-105: the master's seed for every replica
             generator = torch.Generator().manual_seed(int(seed_t.item()))
             perm = torch.randperm(batch_size, generator=generator)        # :108-111
             perm_dev = pin(perm).to(dev, non_blocking=True)

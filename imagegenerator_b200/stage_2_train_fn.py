@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from .engine import N_CRITIC, LAMBDA_GP, Z_DIM, export_optimizer_state, import_optimizer_state
 from .engine2 import Stage2Engine
-from .stage_1_train_fn import _world, _rank, _adam_hyper
+from .stage_1_train_fn import _world, _rank, _adam_hyper, _shared_seed_stream
 
 n_critic = N_CRITIC
 lambda_gp = LAMBDA_GP
@@ -37,7 +37,13 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         m.eval()
         for p in m.parameters():
             p.requires_grad = False
-    if stage1_checkpoint and os.path.exists(stage1_checkpoint):         # :65-72
+    loaded_stage1 = False
+    if stage1_checkpoint:                                               # :65-72 (the reference loads it unconditionally)
+        if not os.path.exists(stage1_checkpoint):
+            raise FileNotFoundError(
+                f"Stage-I checkpoint {stage1_checkpoint!r} not found: Stage-II would train against a randomly initialised, "
+                "frozen gen_1 / con_augment_1 / text side.  Pass stage1_checkpoint=None to do that on purpose.")
+        loaded_stage1 = True
         ck1 = torch.load(stage1_checkpoint, map_location="cpu", weights_only=False)
         textEncoder.load_state_dict(ck1["textEncoder"])
         projection_head.load_state_dict(ck1["projection_head"])
@@ -72,19 +78,21 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         fp._lr_host = lr
         if resumed:
             import_optimizer_state(opt, fp)                    # Adam moments + step count of the checkpoint
+    if resumed:
+        eng.refresh_all()        # a caller-supplied engine packed its operands before the weights were loaded
+    if loaded_stage1:
+        eng.g1.refresh_weights()
     dev = eng.ops.device
     pin = lambda t: t.pin_memory() if not t.is_cuda else t
 
+    seed_stream = _shared_seed_stream(world, dev)
     preview_step = 0                                                    # :33 (`step`)
     for epoch in range(start_epoch, num_epochs):
         for batch_idx, (tokenized_texts, real_img_256) in enumerate(loader):
             # pageable host tensors are copied synchronously with the stream (the host would wait for the previous
             # step on every batch): go through pinned memory
             tokenized_texts = {k: pin(v).to(dev, non_blocking=True) for k, v in tokenized_texts.items()}
-            seed_t = torch.randint(0, 2 ** 32 - 1, (1,))               # :105-113
-            if world > 1:
-                seed_t = seed_t.to(dev)
-                dist.broadcast(seed_t, 0)
+            seed_t = torch.randint(0, 2 ** 32 - 1, (1,), generator=seed_stream)   # :105-113
             generator = torch.Generator().manual_seed(int(seed_t.item()))
             perm = torch.randperm(batch_size, generator=generator)     # :115-118
             perm_dev = pin(perm).to(dev, non_blocking=True)

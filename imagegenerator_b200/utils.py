@@ -11,6 +11,10 @@ import torch
 
 
 def gradient_penalty(critic, real, fake, tem, device, eps=None):
+    if not critic.training:
+        # the reference's penalty differentiates whatever mode the critic is in; only the train-mode BatchNorm backward
+        # (batch statistics) is implemented by the kernels, which is the mode both train functions call it in
+        raise RuntimeError("gradient_penalty: the critic must be in train() mode (eval-mode BatchNorm backward is not implemented)")
     B = real.shape[0]
     rt = critic.runtime(B)
     ops = rt.ops
@@ -28,4 +32,5 @@ def gradient_penalty(critic, real, fake, tem, device, eps=None):
     out = torch.zeros(2, device=ops.device, dtype=torch.float32)
     zero = torch.zeros(B, device=ops.device, dtype=torch.float32)
     ops.critic_loss(zero, zero, zero, rt.sq, 1.0, out)
-    return out[1].clone()
+    from .layers import no_autograd
+    return no_autograd(out[1].clone(), critic)

@@ -405,7 +405,8 @@ class EmuOps:
     def adam_step(self, p, g, m, v, hyper):
         """hyper (fp32, device) = [lr, beta1, beta2, eps, step]; step is incremented first (torch Adam)."""
         hyper[4] += 1
-        lr, b1, b2, eps, t = (float(x) for x in hyper)
+        hyper[5] += 1            # exact count (lo word; the kernel carries into hyper[6] at 2^23)
+        lr, b1, b2, eps, t = (float(x) for x in hyper[:5])
         m.mul_(b1).add_(g, alpha=1 - b1)
         v.mul_(b2).addcmul_(g, g, value=1 - b2)
         bc1 = 1 - b1 ** t

@@ -50,9 +50,28 @@ def stage1(B, dtype=torch.float64, device="cuda", force=None, seed=0):
     return b, ref
 
 
-def stage2(B, dtype=torch.float64, device="cuda", force=None, seed=0):
-    """One Stage-II outer step of the oracle at batch B on ``device``."""
+def trained_stats_g1(ps, device="cuda", passes=60, B=64):
+    """The state gen_1 is in when Stage-II starts after a Stage-I run (stage_2_train_fn.py:65-72 loads that checkpoint):
+    its BatchNorm running statistics have converged to the batch statistics of its own activations.  Emulated by ``passes``
+    train-mode forwards of the oracle's gen_1 (momentum 0.1 -> 0.9^60 = 2e-3 of the initial (0, 1) left) on seeded
+    conditioning vectors; weights stay at their seeded initial values.  Returns the gen_1 state dict (fp32, CPU)."""
+    p = params_on({"g": ps["gen_1"], "ca": ps["con_augment_1"]}, torch.float64, device)
+    g = torch.Generator().manual_seed(777)
+    with torch.no_grad():
+        for _ in range(passes):
+            tem = torch.randn(B, 512, generator=g).to(device, torch.float64)
+            eps = torch.randn(B, 128, generator=g).to(device, torch.float64)
+            z = torch.randn(B, O.Z_DIM, generator=g).to(device, torch.float64)
+            c_hat, _, _ = O.ca_forward(p["ca"], tem, eps)
+            O.g1_forward(p["g"], torch.cat((c_hat, z), dim=1), training=True)
+    return {k: (v.float().cpu() if v.is_floating_point() else v.cpu()) for k, v in p["g"].items()}
+
+
+def stage2(B, dtype=torch.float64, device="cuda", force=None, seed=0, g1_state=None):
+    """One Stage-II outer step of the oracle at batch B on ``device``.  ``g1_state``: state dict to load into gen_1 first."""
     ps = O.init_all(42)
+    if g1_state is not None:
+        ps["gen_1"] = type(ps["gen_1"])((k, g1_state[k].clone()) for k in ps["gen_1"])
     p = params_on(ps, dtype, device)
     b = O.synthetic_batch(B, 2, seed)
     bd = batch_on(b, dtype, device)

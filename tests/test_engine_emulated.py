@@ -156,3 +156,41 @@ def test_optimizer_state_round_trip_through_torch_adam():
     for (k, v), (_, w) in zip(d1.state_dict().items(), d2.state_dict().items()):
         if v.is_floating_point():
             assert torch.allclose(v, w, rtol=1e-10, atol=1e-12), k
+
+
+def test_one_flat_buffer_per_module_shared_by_every_runtime():
+    """a second runtime on a module a live engine owns must not re-point p.data / p.grad away from the buffers the
+    engine's Adam, all-reduce and captured graph use -- every runtime shares the module's one FlatParams."""
+    from emu_ops import EmuOps
+    from imagegenerator_b200.con_augment import ConditioningAugmentation
+    from imagegenerator_b200.discrminator_1 import StageIDiscriminator
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    from imagegenerator_b200.engine import CART, CriticRT, GenRT, Stage1Engine
+    torch.manual_seed(0)
+    ca, d, g = ConditioningAugmentation(512, 256, 128), StageIDiscriminator(512, 128), StageIGenerator(128, 100)
+    ops = EmuOps(torch.float64)
+    eng = Stage1Engine(ca, d, g, 2, ops=ops)
+    w = d.down_sampler[2][0].weight
+    ptr, gptr = w.data.data_ptr(), w.grad.data_ptr()
+    rt2 = d.runtime(4, ops)                      # what critic.forward / utils.gradient_penalty build
+    g2 = GenRT(ops, g, 4)
+    c2 = CART(ops, ca)
+    c2.ensure(4)
+    assert rt2.fp is eng.d.fp and g2.fp is eng.g.fp and c2.fp is eng.ca.fp
+    assert w.data.data_ptr() == ptr and w.grad.data_ptr() == gptr
+    assert w.data.data_ptr() >= eng.d.fp.flat.data_ptr() and w.data.data_ptr() < eng.d.fp.flat.data_ptr() + eng.d.fp.flat.numel() * 8
+    # an ops object of another precision on the same module is refused instead of silently detaching the engine
+    with pytest.raises(RuntimeError, match="already lives in a flat parameter buffer"):
+        CriticRT(EmuOps(torch.float32), d, 2)
+
+
+def test_module_forward_refuses_autograd_with_a_clear_message():
+    from imagegenerator_b200.layers import no_autograd
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    m = StageIGenerator(128, 100)
+    out = no_autograd(torch.zeros(2, 3), m)
+    assert out.requires_grad
+    with pytest.raises(RuntimeError, match="does not record an autograd graph"):
+        out.sum().backward()
+    with torch.no_grad():
+        assert not no_autograd(torch.zeros(2, 3), m).requires_grad
