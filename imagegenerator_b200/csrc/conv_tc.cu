@@ -63,6 +63,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// one lane of a CONVERGED warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded code runs on exactly one
+// lane and issues the TMA / tcgen05 instructions straight from uniform registers -- under `if (lane == 0)` ptxas wraps
+// every one of them in an ELECT / BRA.U.ANY loop (4 extra instructions and a convergence branch per MMA on the thread
+// whose instruction stream paces the mainloop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -109,158 +124,8 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     return d;
 }
 
-struct TcParams {
-    int M, Hq, Wq;        // output grid handled by this launch (per phase): N*Hq*Wq rows
-    int bw, bh, bn;       // pixel box of one 128-row tile (bw*bh*bn == 128)
-    int n_total, BN;      // output channels, tile width
-    int Ck, cblocks;      // reduction channels per tap, ceil(Ck/64)
-    int mode;             // 0 fprop, 1 dgrad
-    int k, s, p;
-    int outH, outW;       // spatial dims of the output tensor
-    int act;
-    int stages;
-    int tmem_cols;
-    const float* bias;
-    bf16* out;
-};
-
 constexpr int TC_THREADS = 192;
 constexpr int A_STAGE_BYTES = 128 * 128;
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[4], empty_bar[4], accum_bar;
-    __shared__ uint32_t tmem_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    const int b_stage_bytes = P.BN * 128;
-    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-
-    // ---- tile / phase bookkeeping (warp-uniform)
-    const int phase = blockIdx.z;
-    const int ph = phase / P.s, pw = phase - ph * P.s;
-    int nth, ntw, rh = 0, rw = 0, base_h = 0, base_w = 0;
-    if (P.mode == 0) {
-        nth = ntw = P.k;
-    } else {
-        rh = (ph + P.p) % P.s; rw = (pw + P.p) % P.s;
-        nth = (P.k - rh + P.s - 1) / P.s; ntw = (P.k - rw + P.s - 1) / P.s;
-        base_h = (ph + P.p - rh) / P.s; base_w = (pw + P.p - rw) / P.s;
-    }
-    const int nkb = nth * ntw * P.cblocks;
-    const int m0 = blockIdx.x * 128;
-    const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
-    const int nt0 = blockIdx.y * P.BN;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        mbar_init(&accum_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                     "r"((uint32_t)P.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % P.stages, it = kb / P.stages;
-                mbar_wait(&empty_bar[st], (it & 1) ^ 1);
-                mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
-                const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
-                const int th = tap / ntw, tw = tap - th * ntw;
-                int ca_w, ca_h, bk;
-                if (P.mode == 0) {
-                    ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
-                    bk = (th * P.k + tw) * P.Ck + cb * 64;
-                } else {
-                    ca_w = w0 + base_w - tw; ca_h = h0 + base_h - th;
-                    bk = ((rh + P.s * th) * P.k + (rw + P.s * tw)) * P.Ck + cb * 64;
-                }
-                uint8_t* sa = smem + (size_t)st * stage_bytes;
-                tma_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
-                tma_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk, nt0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((128u >> 4) << 24);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % P.stages, it = kb / P.stages;
-                mbar_wait(&full_bar[st], it & 1);
-                tc_fence_after();
-                const uint32_t sa = base + (uint32_t)st * stage_bytes;
-                const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    uint64_t ad = make_kmajor_sw128_desc(sa + k4 * 32);
-                    uint64_t bd = make_kmajor_sw128_desc(sb + k4 * 32);
-                    tc_mma_bf16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
-                }
-                tc_commit(&empty_bar[st]);      // frees the smem stage when these MMAs retire
-            }
-            tc_commit(&accum_bar);              // accumulator complete
-        }
-    } else {
-        // ---- epilogue: TMEM -> registers -> bias/act -> bf16 NHWC rows
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;            // row of the tile
-        const int dn = r / (P.bw * P.bh), rem = r - dn * (P.bw * P.bh);
-        const int dh = rem / P.bw, dw = rem - dh * P.bw;
-        const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
-        const bool row_ok = n_img < P.M / (P.Hq * P.Wq);   // tiles divide the [Hq][Wq] grid; only the image index can run out
-        int oh = hh, ow = ww;
-        if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
-        bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total;
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const bool vec_ok = (P.n_total % 8) == 0;
-        for (int c0 = 0; c0 < P.BN; c0 += 16) {
-            uint32_t v[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int n_base = nt0 + c0;
-            if (!row_ok || n_base >= P.n_total) continue;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]);
-                int n = n_base + j;
-                if (P.bias && n < P.n_total) x += P.bias[n];
-                f[j] = act_fwd(x, P.act);
-            }
-            if (vec_ok && n_base + 16 <= P.n_total) {
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
-                o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-                o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
-                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                *reinterpret_cast<uint4*>(orow + n_base) = o0;
-                *reinterpret_cast<uint4*>(orow + n_base + 8) = o1;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n_base + j < P.n_total) orow[n_base + j] = __float2bfloat16_rn(f[j]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
-                     : "memory");
-    }
-}
 
 // ------------------------------------------------------------------------------------------------ 2-CTA variant
 // Same dataflow with a CTA PAIR (cluster 2x1x1, tcgen05 cta_group::2): the pair owns a 256-row x BN tile,
@@ -317,6 +182,38 @@ __device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* b
         "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same with shared-memory addresses already converted (the producer keeps them as 32-bit integers and advances them
+// by adds: no generic-to-shared conversion on its critical path)
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_leader_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar & PEER_BIT_MASK), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
@@ -334,174 +231,75 @@ __device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, ui
         : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[4], empty_bar[4], accum_bar;
-    __shared__ uint32_t tmem_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    const int half_n = P.BN / 2;
-    const int b_stage_bytes = half_n * 128;
-    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-
-    const int phase = blockIdx.z;
-    const int ph = phase / P.s, pw = phase - ph * P.s;
-    int nth, ntw, rh = 0, rw = 0, base_h = 0, base_w = 0;
-    if (P.mode == 0) {
-        nth = ntw = P.k;
-    } else {
-        rh = (ph + P.p) % P.s; rw = (pw + P.p) % P.s;
-        nth = (P.k - rh + P.s - 1) / P.s; ntw = (P.k - rw + P.s - 1) / P.s;
-        base_h = (ph + P.p - rh) / P.s; base_w = (pw + P.p - rw) / P.s;
-    }
-    const int nkb = nth * ntw * P.cblocks;
-    const int m0 = blockIdx.x * 128;                 // this CTA's 128 rows (blockIdx.x = 2*pair + rank)
-    const int w0 = m0 % P.Wq, h0 = (m0 / P.Wq) % P.Hq, n0 = m0 / (P.Wq * P.Hq);
-    const int nt0 = blockIdx.y * P.BN;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
-        mbar_init(&accum_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                     "r"((uint32_t)P.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % P.stages, it = kb / P.stages;
-                mbar_wait(&empty_bar[st], (it & 1) ^ 1);
-                mbar_expect_tx_leader(&full_bar[st], (uint32_t)stage_bytes);
-                const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
-                const int th = tap / ntw, tw = tap - th * ntw;
-                int ca_w, ca_h, bk;
-                if (P.mode == 0) {
-                    ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
-                    bk = (th * P.k + tw) * P.Ck + cb * 64;
-                } else {
-                    ca_w = w0 + base_w - tw; ca_h = h0 + base_h - th;
-                    bk = ((rh + P.s * th) * P.k + (rw + P.s * tw)) * P.Ck + cb * 64;
-                }
-                uint8_t* sa = smem + (size_t)st * stage_bytes;
-                tma2_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
-                tma2_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk, nt0 + (int)rank * half_n);
-            }
-        }
-    } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((256u >> 4) << 24);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % P.stages, it = kb / P.stages;
-                mbar_wait(&full_bar[st], it & 1);
-                tc_fence_after();
-                const uint32_t sa = base + (uint32_t)st * stage_bytes;
-                const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    uint64_t ad = make_kmajor_sw128_desc(sa + k4 * 32);
-                    uint64_t bd = make_kmajor_sw128_desc(sb + k4 * 32);
-                    tc2_mma_bf16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
-                }
-                tc2_commit_mc(&empty_bar[st]);
-            }
-            tc2_commit_mc(&accum_bar);
-        }
-    } else {
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int dn = r / (P.bw * P.bh), rem = r - dn * (P.bw * P.bh);
-        const int dh = rem / P.bw, dw = rem - dh * P.bw;
-        const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
-        const bool row_ok = n_img < P.M / (P.Hq * P.Wq);
-        int oh = hh, ow = ww;
-        if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
-        bf16* orow = P.out + (((int64_t)n_img * P.outH + oh) * P.outW + ow) * P.n_total;
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const bool vec_ok = (P.n_total % 8) == 0;
-        for (int c0 = 0; c0 < P.BN; c0 += 16) {
-            uint32_t v[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int n_base = nt0 + c0;
-            if (!row_ok || n_base >= P.n_total) continue;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]);
-                int n = n_base + j;
-                if (P.bias && n < P.n_total) x += P.bias[n];
-                f[j] = act_fwd(x, P.act);
-            }
-            if (vec_ok && n_base + 16 <= P.n_total) {
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
-                o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-                o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
-                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                *reinterpret_cast<uint4*>(orow + n_base) = o0;
-                *reinterpret_cast<uint4*>(orow + n_base + 8) = o1;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n_base + j < P.n_total) orow[n_base + j] = __float2bfloat16_rn(f[j]);
-            }
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
-                     : "memory");
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ persistent kernel
-// conv_tcp_kernel<CG>: the same dataflow as a PERSISTENT kernel -- one CTA (CG=1) or CTA pair (CG=2,
-// cta_group::2) per SM / SM pair walks a static list of output tiles.  The accumulator is double
-// buffered in TMEM (2 x BN columns), so the epilogue warps drain tile i (tcgen05.ld -> bias/act -> bf16
-// NHWC rows, plus the per-channel (sum, sum^2) of the BatchNorm that follows, reduced across the 32 rows
-// of a warp by a shuffle butterfly) while the MMA warp already accumulates tile i+1; barrier set-up, TMEM
-// allocation and the pipeline fill are paid once per SM instead of once per tile.
+// conv_tcp_kernel<CG>: PERSISTENT implicit-GEMM convolution -- one CTA (CG=1) or CTA pair (CG=2, cta_group::2) per SM /
+// SM pair walks a list of work items (output tiles).  The accumulator is multi-buffered in TMEM, so the epilogue warps
+// drain tile i (tcgen05.ld -> bias/act -> bf16 NHWC rows, plus the per-channel (sum, sum^2) of the BatchNorm that
+// follows) while the MMA warp already accumulates tile i+1.
 //
-//   warp 0    : TMA producer             full[s] / empty[s] ring (up to 8 stages)
+//   warp 0    : TMA producer             full[s] / empty[s] ring
 //   warp 1    : MMA issuer (leader CTA)  tcgen05.commit -> empty[s], -> tfull[buf]
-//   warps 2-5 : epilogue                 wait tfull[buf] ... arrive tempty[buf] (on the leader)
+//   warps 2-9 : epilogue                 wait tfull[buf] ... arrive tempty[buf] (on the leader)
+//
+// What bounds this kernel is the L2 -> SM operand stream: at full occupancy the 148 SMs share
+// ~6.3 KB/cycle, i.e. ~44 B/cycle/SM, and a 128 x 256 x 64 k-block wants 32 KB in the 512 cycles its MMAs take.  Two
+// things cut the bytes per FLOP:
+//
+//  * SHARED ACTIVATION SLABS.  The taps of a filter column that hit the same input-row parity read the SAME input rows,
+//    shifted by one output row: for k4 s2 p1, tap kh=2 at output row oh reads what tap kh=0 reads at oh+1.  A stage is
+//    therefore not one (tap, 64-channel block) but one SLAB: the (bh + nv - 1) input rows that nv vertically adjacent
+//    taps need, loaded by ONE TMA box, plus the nv weight tiles.  The tile's 128 rows are ordered (h, n, w) -- the tensor
+//    map's dimensions are (C, W, N, H) -- so that "one output row further down" is the same byte offset bn*bw*128 for
+//    every row of the tile even when the tile spans several images; that offset is a multiple of the 1024-byte swizzle
+//    atom (bn*bw >= 8), so tap i's A operand is the SAME shared-memory slab read through a UMMA descriptor whose start
+//    address is advanced by i*bn*bw*128 bytes.  A bytes: x9/16 (k4 s2, 8-row tiles), x10/24 (3x3 s1), x(bh+1)/2bh
+//    (ConvTranspose phases).
+//  * COLUMN SLICES FOR THE LAST ROUND.  With T tiles on U clusters the last round holds R = T mod U tiles; when R <= U/2
+//    those tiles are cut into S = U/R column slices of BN2 columns (a second weight tensor map with a BN2/CG-row box and
+//    a narrower instruction descriptor), so the round's critical path shrinks from one full tile to one slice without
+//    any partial-sum exchange (the K-split this replaces paid ~8 us per partial tile in workspace traffic).
+struct SlabEnt {
+    int16_t dw, dh;       // first input column / row of the slab, relative to (w0*es, h0*es)
+    int16_t nv, pad_;     // taps sharing this slab (<= 4)
+    int32_t bk[4];        // K offset of tap i's weights in the packed matrix (elements)
+    int32_t roff[4];      // byte offset of tap i's first row inside the slab (multiples of 1024)
+};
+
 struct TcpParams {
     int Hq, Wq, n_img;    // output grid handled per phase, images
-    int bw, bh, bn;       // pixel box of one 128-row tile
-    int n_total, BN;      // output channels, tile width
+    int bw, bh, bn;       // pixel box of one 128-row tile; rows ordered (h, n, w)
+    int lgBW, lgNW;       // log2(bw), log2(bn*bw)
+    int n_total, BN, BN2; // output channels, tile width, width of a last-round column slice
     int Ck, cblocks;
-    int mode, k, s, p;
+    int mode, s, es;      // es: element stride of the activation tensor map (s for fprop, 1 for dgrad)
     int outH, outW;
     int act;
-    int stages;
+    int stages, stage_bytes, slab_bytes, slab_pad, b_bytes;   // slab_pad: slab_bytes rounded up to 1024; b_bytes: one full-width weight tile
     int tmem_cols, acc_stride, nbuf;      // TMEM columns allocated, columns per accumulator buffer, buffers in the ring
-    int m_tiles, n_tiles, total_tiles;   // m_tiles counts CG*128-row cluster tiles
+    int m_tiles, n_tiles, total_tiles, tiles_per_phase;   // m_tiles counts CG*128-row cluster tiles
+    int full_tiles, nslices, total_work;  // work items: full_tiles whole tiles, then (total_tiles - full_tiles) * nslices slices
+    int kiters;           // stages consumed per work item, per phase equal: nslab * cblocks
+    int rotate;           // clusters start the reduction at different slabs (spreads the weight reads over L2)
     int imgs_per_group;
+    int lgW, lgHW;        // log2(Wq), log2(Hq*Wq)
+    int epi_alt;          // narrow tiles: the two epilogue warp groups drain ALTERNATE tiles (see the epilogue)
+    int nslab[4];         // slabs per phase
     const float* bias;
     bf16* out;
     double* stats;        // [groups][n_total][2] or NULL
     float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
     const bf16* residual; // added before the activation (same layout as out) or NULL
-    int lgW, lgHW;        // log2(Wq), log2(Hq*Wq)
-    int full_tiles, split, kb_slice;   // tail-wave K-split: tiles below full_tiles are whole; see next_work()
-    float* ws;            // fp32 partial tiles of the split tail wave
-    int* flags;           // one per (leftover tile, non-owner slice, CTA of the pair)
-    int epi_alt;          // narrow tiles: the two epilogue warp groups drain ALTERNATE tiles (see the epilogue)
+    unsigned long long* trace;   // profiling hook (sg_debug_conv_trace): 16 globaltimer stamps per CTA, or NULL
+    SlabEnt slab[4][16];
 };
+
+__device__ __forceinline__ void trace_stamp(const TcpParams& P, int slot) {
+    if (P.trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -512,7 +310,6 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // per-column sums over the 32 lanes of a warp for 16 columns held as s[0..15]: recursive halving, 16 shuffles.
 // On return s[0] of lane l is the sum of column  8*b4 + 4*b3 + 2*b2 + b1  (b_i = bit i of l); lanes l and l^1 agree.
@@ -549,23 +346,6 @@ __device__ __forceinline__ void warp_colsum16(float (&s)[16], int lane) {
     s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
 }
 
-struct PhaseGeo {
-    int ph, pw, nth, ntw, rh, rw, base_h, base_w;
-};
-__device__ __forceinline__ PhaseGeo phase_geo(const TcpParams& P, int phase) {
-    PhaseGeo g;
-    g.ph = phase / P.s; g.pw = phase - g.ph * P.s;
-    g.rh = g.rw = g.base_h = g.base_w = 0;
-    if (P.mode == 0) {
-        g.nth = g.ntw = P.k;
-    } else {
-        g.rh = (g.ph + P.p) % P.s; g.rw = (g.pw + P.p) % P.s;
-        g.nth = (P.k - g.rh + P.s - 1) / P.s; g.ntw = (P.k - g.rw + P.s - 1) / P.s;
-        g.base_h = (g.ph + P.p - g.rh) / P.s; g.base_w = (g.pw + P.p - g.rw) / P.s;
-    }
-    return g;
-}
-
 constexpr int TCP_EPI_WARPS = 8;
 constexpr int TCP_THREADS = 64 + 32 * TCP_EPI_WARPS;
 
@@ -575,32 +355,38 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 
-// Work list of one cluster: whole tiles c, c+C, c+2C, ... below P.full_tiles, then -- when the last round would be
-// only partly full -- ONE K-slice of a leftover tile: the R = total - full leftover tiles are each cut into P.split
-// slices of P.kb_slice k-blocks, slice s of leftover tile t goes to cluster t*split + s.  Slice 0 is the tile's owner:
-// the other slices store their fp32 partial accumulators in a workspace and raise a flag, the owner adds them in its
-// epilogue.  Non-owners never wait, every cluster holds at most one slice, all clusters are co-resident: no deadlock.
+// Work item i of a cluster: whole tiles  c, c+C, c+2C, ...  below P.full_tiles, then the column slices of the leftover
+// tiles (slice sl of leftover tile lt is item  full_tiles + lt*nslices + sl: the slices of one tile run on neighbouring
+// clusters at the same time, so its activation slabs are fetched from DRAM once and hit L2 after that).
 struct Work {
-    int tile, kb0, kb1, slice;
+    int tile, nt0, width, sliced;     // tile index; first output column; columns this item computes; 1 = a column slice
 };
 
-__device__ __forceinline__ bool next_work(const TcpParams& P, int cluster_id, int num_clusters, int nkb, int i, Work* w) {
+__device__ __forceinline__ bool next_work(const TcpParams& P, int cluster_id, int num_clusters, int i, Work* w) {
     const int t = cluster_id + i * num_clusters;
-    if (t < P.full_tiles) { w->tile = t; w->kb0 = 0; w->kb1 = nkb; w->slice = 0; return true; }
-    // split mode: full_tiles is a multiple of num_clusters (or 0), so every cluster reaches this point at the same i
-    if (P.split > 1 && t - cluster_id == P.full_tiles) {
-        const int lt = cluster_id / P.split, sl = cluster_id - lt * P.split;
-        if (P.full_tiles + lt >= P.total_tiles) return false;
-        w->tile = P.full_tiles + lt; w->slice = sl;
-        w->kb0 = sl * P.kb_slice; w->kb1 = min(nkb, w->kb0 + P.kb_slice);
-        return w->kb0 < w->kb1;
+    if (t >= P.total_work) return false;
+    int tile = t, sl = 0;
+    w->sliced = 0;
+    if (t >= P.full_tiles) {
+        const int idx = t - P.full_tiles;
+        const int lt = idx / P.nslices;
+        sl = idx - lt * P.nslices;
+        tile = P.full_tiles + lt;
+        w->sliced = P.nslices > 1 ? 1 : 0;
     }
-    return false;
+    w->tile = tile;
+    int r = tile;
+    if (P.tiles_per_phase != P.total_tiles) r = tile % P.tiles_per_phase;
+    const int nt = P.n_tiles != 1 ? r / P.m_tiles : 0;
+    w->nt0 = nt * P.BN + sl * P.BN2;
+    w->width = w->sliced ? min(P.BN2, P.BN - sl * P.BN2) : P.BN;
+    return true;
 }
 
 template <int CG>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
-conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcpParams P) {
+conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcpParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[8], tempty_bar[8];
     __shared__ uint32_t tmem_slot;
@@ -612,14 +398,12 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    const int b_rows = P.BN / CG;
-    const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
-    const int tiles_per_phase = P.n_tiles * P.m_tiles;
-    const int nkb_tile = (P.mode == 0 ? P.k * P.k : (P.k / P.s) * (P.k / P.s)) * P.cblocks;   // equal for every phase
+    if (threadIdx.x == 0) trace_stamp(P, 0);
 
-    if (threadIdx.x == 32) {          // fetch both TMA descriptors while the barriers and TMEM are being set up
+    if (threadIdx.x == 32) {          // fetch the TMA descriptors while the barriers and TMEM are being set up
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (P.nslices > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
@@ -643,88 +427,144 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    if (threadIdx.x == 0) trace_stamp(P, 1);
     SG_PDL_SYNC();        // barriers, TMEM and the stats staging are set up: from here on global memory is touched
+    if (threadIdx.x == 0) trace_stamp(P, 2);
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            // ONE thread issues every TMA of this CTA, and its instruction stream is on the critical path: measured with
+            // the kernel's own timeline (tools/exp_conv_trace.py), a stage cost ~1100 cycles whatever its bytes while this
+            // loop re-derived coordinates, re-read the slab table from constant memory and walked a prefetch cursor per
+            // stage -- the producer, not L2, paced the mainloop.  So: everything that does not change between stages is
+            // hoisted to the work item / slab, the inner loop is wait -> expect_tx -> 1 + nv TMA issues, and shared-memory
+            // addresses advance by adds.
             int st = 0;
             uint32_t par = 1;                         // parity to wait for on empty[st]: first round passes
+            const uint32_t ring = smem_u32(smem);
             Work w;
-            for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w); ++wi) {
-                const int phase = w.tile / tiles_per_phase, r = w.tile - phase * tiles_per_phase;
-                const int nt = r / P.m_tiles, mt = r - nt * P.m_tiles;
-                const PhaseGeo g = phase_geo(P, phase);
+            for (int wi = 0; next_work(P, cluster_id, num_clusters, wi, &w); ++wi) {
+                int phase = 0, r = w.tile;
+                if (P.tiles_per_phase != P.total_tiles) { phase = w.tile / P.tiles_per_phase; r = w.tile - phase * P.tiles_per_phase; }
+                const int mt = P.n_tiles != 1 ? r % P.m_tiles : r;
                 const int m0 = (mt * CG + (int)rank) * 128;
-                const int w0 = m0 & (P.Wq - 1), h0 = (m0 >> P.lgW) & (P.Hq - 1), n0 = m0 >> P.lgHW;   // Hq, Wq are powers of two
-                const int nt0 = nt * P.BN + (int)rank * b_rows;
-                int tap = w.kb0 / P.cblocks, cb = w.kb0 - tap * P.cblocks;
-                int th = tap / g.ntw, tw = tap - th * g.ntw;
-                for (int kb = w.kb0; kb < w.kb1; ++kb) {
-                    int ca_w, ca_h, bk;
-                    if (P.mode == 0) {
-                        ca_w = w0 * P.s - P.p + tw; ca_h = h0 * P.s - P.p + th;
-                        bk = (th * P.k + tw) * P.Ck;
-                    } else {
-                        ca_w = w0 + g.base_w - tw; ca_h = h0 + g.base_h - th;
-                        bk = ((g.rh + P.s * th) * P.k + (g.rw + P.s * tw)) * P.Ck;
+                const int w0 = (m0 & (P.Wq - 1)) * P.es, h0 = ((m0 >> P.lgW) & (P.Hq - 1)) * P.es, n0 = m0 >> P.lgHW;   // Hq, Wq are powers of two
+                const int b_rows = w.sliced ? P.BN2 / CG : P.BN / CG;      // weight rows this CTA stages per tap
+                const int nt0 = w.nt0 + (int)rank * b_rows;                // CTA 1 of a pair holds the upper half of the MMA's N
+                const CUtensorMap* mapB = w.sliced ? &tmB2 : &tmB;
+                const int nsl = P.nslab[phase];
+                // every cluster starts the reduction at a different slab (and walks it cyclically): otherwise all 74-148
+                // CTAs ask L2 for the SAME weight lines at the same moment, a hot spot on a few L2 slices
+                int sbr = P.rotate ? (cluster_id + wi) % nsl : 0;
+                for (int sb = 0; sb < nsl; ++sb, sbr = (sbr + 1 == nsl ? 0 : sbr + 1)) {
+                    const SlabEnt& e = P.slab[phase][sbr];
+                    const int ca_w = w0 + e.dw, ca_h = h0 + e.dh, nv = e.nv;
+                    const int bk0 = e.bk[0], bk1 = e.bk[1], bk2 = e.bk[2], bk3 = e.bk[3];
+                    const uint32_t tx = (uint32_t)(P.slab_bytes + nv * b_rows * 128);
+                    for (int cb = 0; cb < P.cblocks; ++cb) {
+                        const int c0 = cb * 64;
+                        mbar_wait(&empty_bar[st], par);
+                        const uint32_t sa = ring + (uint32_t)st * (uint32_t)P.stage_bytes, sb0 = sa + (uint32_t)P.slab_pad;
+                        const uint32_t fb = smem_u32(&full_bar[st]);
+                        if (!elect_one()) {
+                        } else if (CG == 2) {
+                            mbar_expect_tx_leader_u32(fb, tx);
+                            tma2_load_4d_u32(&tmA, fb, sa, c0, ca_w, n0, ca_h);
+                            tma2_load_2d_u32(mapB, fb, sb0, bk0 + c0, nt0);
+                            if (nv > 1) tma2_load_2d_u32(mapB, fb, sb0 + (uint32_t)P.b_bytes, bk1 + c0, nt0);
+                            if (nv > 2) tma2_load_2d_u32(mapB, fb, sb0 + 2u * (uint32_t)P.b_bytes, bk2 + c0, nt0);
+                            if (nv > 3) tma2_load_2d_u32(mapB, fb, sb0 + 3u * (uint32_t)P.b_bytes, bk3 + c0, nt0);
+                        } else {
+                            mbar_expect_tx_u32(fb, tx);
+                            tma_load_4d_u32(&tmA, fb, sa, c0, ca_w, n0, ca_h);
+                            tma_load_2d_u32(mapB, fb, sb0, bk0 + c0, nt0);
+                            if (nv > 1) tma_load_2d_u32(mapB, fb, sb0 + (uint32_t)P.b_bytes, bk1 + c0, nt0);
+                            if (nv > 2) tma_load_2d_u32(mapB, fb, sb0 + 2u * (uint32_t)P.b_bytes, bk2 + c0, nt0);
+                            if (nv > 3) tma_load_2d_u32(mapB, fb, sb0 + 3u * (uint32_t)P.b_bytes, bk3 + c0, nt0);
+                        }
+                        if (++st == P.stages) { st = 0; par ^= 1; }
                     }
-                    mbar_wait(&empty_bar[st], par);
-                    uint8_t* sa = smem + (size_t)st * stage_bytes;
-                    if (CG == 2) {
-                        mbar_expect_tx_leader(&full_bar[st], (uint32_t)stage_bytes);
-                        tma2_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
-                        tma2_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
-                    } else {
-                        mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
-                        tma_load_4d(&tmA, &full_bar[st], sa, cb * 64, ca_w, ca_h, n0);
-                        tma_load_2d(&tmB, &full_bar[st], sa + A_STAGE_BYTES, bk + cb * 64, nt0);
-                    }
-                    if (++st == P.stages) { st = 0; par ^= 1; }
-                    if (++cb == P.cblocks) { cb = 0; if (++tw == g.ntw) { tw = 0; ++th; } }
                 }
             }
         }
     } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128*CG
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
-                                   ((uint32_t)((128 * CG) >> 4) << 24);
+        if (rank == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = tile or slice width, M=128*CG
+            const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((128 * CG) >> 4) << 24);
+            // K-major 128B-swizzled operand descriptors (make_kmajor_sw128_desc) differ only in the 14-bit start address
+            // (16-byte units) of their low word; everything per-MMA is an integer add on that word.  This loop is what
+            // paces narrow tiles: measured ~157 cycles per tcgen05.mma whatever its N when each descriptor was rebuilt with
+            // shifts and masks and the slab table was re-read from constant memory per tap (tools/exp_conv_trace.py).
+            constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t dlo_ring = ((base >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t stage16 = (uint32_t)P.stage_bytes >> 4, slab16 = (uint32_t)P.slab_pad >> 4, b16 = (uint32_t)P.b_bytes >> 4;
+            auto mma = [&](uint32_t tacc, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+                const uint64_t ad = ((uint64_t)DESC_HI << 32) | alo, bd = ((uint64_t)DESC_HI << 32) | blo;
+                if (CG == 2) tc2_mma_bf16(tacc, ad, bd, idesc, acc);
+                else tc_mma_bf16(tacc, ad, bd, idesc, acc);
+            };
             int st = 0;
             uint32_t par = 0, ab = 0, abpar = 1;       // accumulator buffer ring: P.nbuf buffers of acc_stride TMEM columns
             Work w;
-            for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w); ++wi) {
+            for (int wi = 0; next_work(P, cluster_id, num_clusters, wi, &w); ++wi) {
+                const int phase = P.tiles_per_phase != P.total_tiles ? w.tile / P.tiles_per_phase : 0;
+                // the MMA's N: the slice width rounded up to what the staged weight rows cover (a trailing slice narrower
+                // than BN2 still multiplies BN2 staged rows -- rows past the layer's channels are TMA zero fill -- and the
+                // epilogue ignores the surplus columns)
+                const uint32_t nmma = (uint32_t)(w.sliced ? P.BN2 : P.BN);
+                const uint32_t idesc = idesc0 | ((nmma >> 3) << 17);
                 mbar_wait(&tempty_bar[ab], abpar);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride;
-                for (int kb = w.kb0; kb < w.kb1; ++kb) {
-                    mbar_wait(&full_bar[st], par);
-                    tc_fence_after();
-                    const uint32_t sa = base + (uint32_t)st * stage_bytes;
-                    const uint32_t sb = sa + A_STAGE_BYTES;
+                const int nsl = P.nslab[phase];
+                uint32_t acc = 0;
+                int sbr = P.rotate ? (cluster_id + wi) % nsl : 0;        // the producer's slab order
+                for (int sb = 0; sb < nsl; ++sb, sbr = (sbr + 1 == nsl ? 0 : sbr + 1)) {
+                    const SlabEnt& e = P.slab[phase][sbr];
+                    const int nv = e.nv;
+                    const uint32_t ro1 = (uint32_t)e.roff[1] >> 4, ro2 = (uint32_t)e.roff[2] >> 4, ro3 = (uint32_t)e.roff[3] >> 4;
+                    for (int cb = 0; cb < P.cblocks; ++cb) {
+                        mbar_wait(&full_bar[st], par);
+                        const uint32_t a0 = dlo_ring + (uint32_t)st * stage16, b0 = a0 + slab16;
+                        if (elect_one()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        uint64_t ad = make_kmajor_sw128_desc(sa + k4 * 32);
-                        uint64_t bd = make_kmajor_sw128_desc(sb + k4 * 32);
-                        const uint32_t acc = ((kb - w.kb0) | k4) != 0 ? 1u : 0u;
-                        if (CG == 2) tc2_mma_bf16(tacc, ad, bd, idesc, acc);
-                        else tc_mma_bf16(tacc, ad, bd, idesc, acc);
+                            for (int k4 = 0; k4 < 4; ++k4) mma(tacc, a0 + 2 * k4, b0 + 2 * k4, idesc, k4 == 0 ? acc : 1u);
+                            if (nv > 1) {
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) mma(tacc, a0 + ro1 + 2 * k4, b0 + b16 + 2 * k4, idesc, 1u);
+                            }
+                            if (nv > 2) {
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) mma(tacc, a0 + ro2 + 2 * k4, b0 + 2 * b16 + 2 * k4, idesc, 1u);
+                            }
+                            if (nv > 3) {
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) mma(tacc, a0 + ro3 + 2 * k4, b0 + 3 * b16 + 2 * k4, idesc, 1u);
+                            }
+                            if (CG == 2) tc2_commit_mc(&empty_bar[st]); else tc_commit(&empty_bar[st]);
+                        }
+                        acc = 1u;
+                        __syncwarp();
+                        if (++st == P.stages) { st = 0; par ^= 1; }
                     }
-                    if (CG == 2) tc2_commit_mc(&empty_bar[st]); else tc_commit(&empty_bar[st]);
-                    if (++st == P.stages) { st = 0; par ^= 1; }
                 }
-                if (CG == 2) tc2_commit_mc(&tfull_bar[ab]); else tc_commit(&tfull_bar[ab]);
+                if (elect_one()) {
+                    if (CG == 2) tc2_commit_mc(&tfull_bar[ab]); else tc_commit(&tfull_bar[ab]);
+                }
+                __syncwarp();
                 if (++ab == (uint32_t)P.nbuf) { ab = 0; abpar ^= 1; }
+                if (lane == 0) trace_stamp(P, wi == 0 ? 4 : 5);
             }
         }
     } else {
-        // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and every second 16-column chunk
+        // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and every second 32-column chunk
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int r = q * 32 + lane;
-        const int dn = r / (P.bw * P.bh), rem = r - dn * (P.bw * P.bh);
-        const int dh = rem / P.bw, dw = rem - dh * P.bw;
+        // rows of a tile are ordered (h, n, w)
+        const int dw = r & (P.bw - 1), dn = (r >> P.lgBW) & (P.bn - 1), dh = r >> P.lgNW;
         const bool vec_ok = (P.n_total % 8) == 0;
-        const bool bias_vec_ok = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0 && (P.BN & 3) == 0;   // float4 loads of the bias
+        const bool bias_vec_ok = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0 && (P.BN & 3) == 0 && (P.BN2 & 3) == 0;   // float4 loads of the bias
         const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
         const int act = P.act;
         const bool has_stats = P.stats != nullptr;
@@ -737,100 +577,45 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int rr = q * 32 + i * 8 + (lane >> 2);
-            cdn[i] = rr / (P.bw * P.bh);
-            const int rm = rr - cdn[i] * (P.bw * P.bh);
-            cdh[i] = rm / P.bw; cdw[i] = rm - cdh[i] * P.bw;
+            cdw[i] = rr & (P.bw - 1); cdn[i] = (rr >> P.lgBW) & (P.bn - 1); cdh[i] = rr >> P.lgNW;
         }
         uint32_t ti = 0, ab = 0, abpar = 0;
         Work w;
-        for (int wi = 0; next_work(P, cluster_id, num_clusters, nkb_tile, wi, &w);
+        for (int wi = 0; next_work(P, cluster_id, num_clusters, wi, &w);
              ++wi, ++ti, ab = (ab + 1 == (uint32_t)P.nbuf ? 0 : ab + 1), abpar ^= (ab == 0 ? 1u : 0u)) {
-            // epi_alt (narrow tiles without statistics / K-split): warps 2-5 drain the even work items, warps 6-9 the odd
+            // epi_alt (narrow tiles without statistics): warps 2-5 drain the even work items, warps 6-9 the odd
             // ones, each warp all columns of its 32 rows -- the per-tile fixed cost (decode, row pointers, barrier round
             // trip: ~350 of the ~450 instructions a warp spends on a 128x64 tile) is paid by four warps instead of eight
             // and two tiles drain concurrently
             if (P.epi_alt && (int)(ti & 1u) != half) continue;
             const int tile = w.tile;
-            // tile decode: the divisions are ~30 instructions each and this code runs per tile and warp (the thin layers'
-            // 128x64 tiles were bound by exactly this: 445 instructions per warp and tile, 16 of them the bf16 packs) --
-            // the single-phase / single-column-tile cases (warp-uniform) skip them
-            int phase = 0, rr = tile, nt = 0, ph = 0, pw = 0;
-            if (tiles_per_phase != P.total_tiles) { phase = tile / tiles_per_phase; rr = tile - phase * tiles_per_phase; }
+            // tile decode: the divisions are ~30 instructions each and this code runs per tile and warp -- the
+            // single-phase / single-column-tile cases (warp-uniform) skip them
+            int phase = 0, rr = tile, ph = 0, pw = 0;
+            if (P.tiles_per_phase != P.total_tiles) { phase = tile / P.tiles_per_phase; rr = tile - phase * P.tiles_per_phase; }
             int mt = rr;
-            if (P.n_tiles != 1) { nt = rr / P.m_tiles; mt = rr - nt * P.m_tiles; }
+            if (P.n_tiles != 1) mt = rr % P.m_tiles;
             if (phase != 0) { ph = phase / P.s; pw = phase - ph * P.s; }
             const int m0 = (mt * CG + (int)rank) * 128;
             const int w0 = m0 & (P.Wq - 1), h0 = (m0 >> P.lgW) & (P.Hq - 1), n0 = m0 >> P.lgHW;   // Hq, Wq are powers of two
-            const int nt0 = nt * P.BN;
+            const int nt0 = w.nt0;
             const int n_img = n0 + dn, hh = h0 + dh, ww = w0 + dw;
             const bool row_ok = n_img < P.n_img && (P.out != nullptr || P.out32 != nullptr);
             int oh = hh, ow = ww;
             if (P.mode == 1) { oh = hh * P.s + ph; ow = ww * P.s + pw; }
             // pixel indices fit 32 bits (checked on the host); one widening multiply per pointer
             bf16* orow = P.out + (int64_t)((n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
-            const int ncols = min(P.BN, P.n_total - nt0);          // valid columns of this tile
+            const int ncols = min(w.width, P.n_total - nt0);          // valid columns of this work item
             const uint32_t sb2 = ti & 1;           // statistics staging buffer
-            // K-split bookkeeping: partial tiles of leftover tile lt live at ws[((lt*(split-1) + slice-1)*CG + rank)][128][BN]
-            const bool is_split = tile >= P.full_tiles && P.split > 1;
-            const int lt = tile - P.full_tiles;
-            float* wsrow = nullptr;
-            if (is_split) {
-                const int first = w.slice > 0 ? w.slice - 1 : 0;
-                // layout [partial tile][16-column chunk][row][16]: the 32 lanes of a warp (32 rows) touch 2 KB contiguous
-                wsrow = P.ws + ((int64_t)(lt * (P.split - 1) + first) * CG + rank) * (128 * P.BN) + (int64_t)r * 16;
-            }
-            if (nkb_tile >= 8) mbar_wait_backoff(&tfull_bar[ab], abpar);     // long mainloop: sleep between polls
+            if (P.kiters >= 8) mbar_wait_backoff(&tfull_bar[ab], abpar);     // long mainloop: sleep between polls
             else mbar_wait(&tfull_bar[ab], abpar);                          // short tiles: the sleep would be the latency
             tc_fence_after();
+            if (et == 0) trace_stamp(P, wi == 0 ? 6 : 8);
             const uint32_t tacc = tmem_base + ab * (uint32_t)P.acc_stride + ((uint32_t)(q * 32) << 16);
-            if (is_split && w.slice > 0) {
-                // ---- non-owner slice: fp32 partial accumulators to the workspace, then raise the flag
-                for (int c0 = half * 16; c0 < ncols; c0 += 32) {
-                    uint32_t v[16];
-                    tc_ld16(tacc + (uint32_t)c0, v);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<uint4*>(wsrow + c0 * 128)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive_local(&tempty_bar[ab]);
-                }
-                __threadfence();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (et == 0) {
-                    int* flag = P.flags + (lt * (P.split - 1) + (w.slice - 1)) * CG + (int)rank;
-                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
-                }
-                continue;
-            }
-            if (is_split) {
-                // ---- owner: wait for the other slices of this tile
-                if (et < P.split - 1) {
-                    const int* flag = P.flags + (lt * (P.split - 1) + et) * CG + (int)rank;
-                    int v;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                        if (!v) __nanosleep(64);
-                    } while (!v);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
             auto process = [&](const int c0, const uint32_t (&v)[16]) {
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                if (is_split) {
-                    for (int sl = 0; sl < P.split - 1; ++sl) {
-                        const float4* pp = reinterpret_cast<const float4*>(wsrow + (int64_t)sl * CG * (128 * P.BN) + c0 * 128);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 t4 = __ldcg(pp + j);
-                            f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
-                        }
-                    }
-                }
                 if (P.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -875,8 +660,8 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int rr = i * 8 + (lane >> 2);
-                            const uint4 val = stg[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
+                            const int r8 = i * 8 + (lane >> 2);
+                            const uint4 val = stg[r8 * 4 + ((lane & 3) ^ ((r8 >> 1) & 3))];
                             const int ni = n0 + cdn[i];
                             int oh2 = h0 + cdh[i], ow2 = w0 + cdw[i];
                             if (P.mode == 1) { oh2 = oh2 * P.s + ph; ow2 = ow2 * P.s + pw; }
@@ -922,11 +707,11 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             };
-            // ---- fast path (every BatchNorm'ed conv of the training step): no bias / residual / fp32 output / K-split,
+            // ---- fast path (every BatchNorm'ed conv of the training step): no bias / residual / fp32 output,
             // whole 32-column groups.  Straight-line code over 32 columns per iteration -- two independent 16-column
             // chains for the scheduler to interleave, since only two epilogue warps share an SM sub-partition and the
             // drain is issue-latency bound -- with the activation and the statistics decided once per tile.
-            const bool plain = P.residual == nullptr && P.out32 == nullptr && !is_split && vec_ok &&
+            const bool plain = P.residual == nullptr && P.out32 == nullptr && vec_ok &&
                                (ncols & 31) == 0 && P.out != nullptr && (P.bias == nullptr || bias_vec_ok);
             if (plain) {
                 bf16* crow[4];
@@ -978,8 +763,8 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int rr = i * 8 + (lane >> 2);
-                            const uint4 val = stg[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
+                            const int r8 = i * 8 + (lane >> 2);
+                            const uint4 val = stg[r8 * 4 + ((lane & 3) ^ ((r8 >> 1) & 3))];
                             if (crow[i] != nullptr) *reinterpret_cast<uint4*>(crow[i] + c0) = val;
                         }
                     }
@@ -1018,11 +803,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive_local(&tempty_bar[ab]);
             }
-            if (is_split) {
-                // every epilogue thread has read its partials: clear the flags for the next launch on this stream
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (et < P.split - 1) P.flags[(lt * (P.split - 1) + et) * CG + (int)rank] = 0;
-            }
+            if (et == 0) trace_stamp(P, wi == 0 ? 7 : 9);
             if (has_stats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int grp = n0 / P.imgs_per_group;
@@ -1036,6 +817,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(P, 10);
     if (warp == 1) {
         if (CG == 2)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
@@ -1047,10 +829,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]  as  D[co][(tap,ci)] = A^T B with the pixel
 // index as the reduction: both operands are "MN-major" (channels contiguous, pixels strided), which
-// UMMA reads directly through MN-major 128B-swizzled descriptors -- no transposes.  One CTA owns a
-// 128-channel slab of co, one 64-channel block of ci and up to 8 taps (8 x 64 fp32 columns = all 512
-// TMEM columns) and walks a slice of the pixels 64 at a time; slices are combined with vector
-// fp32 reductions (red.global.add.v4.f32) into the PyTorch-layout gradient.
+// UMMA reads directly through MN-major 128B-swizzled descriptors -- no transposes.
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -1059,136 +838,6 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
-}
-
-struct TcWParams {
-    int Mpix, Ho, Wo;      // pixels of dy
-    int bw, bh, bn;        // pixel box of one 64-pixel k-block
-    int Co, Ci, kk, k, s, p;
-    int tpg;               // taps per group (<= 8)
-    int tap_groups;
-    int kb_per_split;      // 64-pixel blocks per split
-    float* dw;
-};
-
-constexpr int W_A_BYTES = 2 * 64 * 128;     // dy: two 64-channel blocks x 64 pixels
-constexpr int W_B_BYTES = 64 * 128;         // x at one tap: 64 channels x 64 pixels
-constexpr int W_STAGES = 2;
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[W_STAGES], empty_bar[W_STAGES], accum_bar;
-    __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    const int stage_bytes = W_A_BYTES + P.tpg * W_B_BYTES;
-
-    const int co0 = blockIdx.x * 128;
-    const int cib = blockIdx.y / P.tap_groups, tg = blockIdx.y - cib * P.tap_groups;
-    const int ci0 = cib * 64, tap0 = tg * P.tpg;
-    const int ntap = min(P.tpg, P.kk - tap0);
-    const int total_kb = (P.Mpix + 63) / 64;
-    const int kb0 = blockIdx.z * P.kb_per_split;
-    const int nkb = min(P.kb_per_split, total_kb - kb0);
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < W_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        mbar_init(&accum_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    if (nkb > 0) {
-        if (warp == 0) {
-            if (lane == 0) {
-                for (int i = 0; i < nkb; ++i) {
-                    const int st = i % W_STAGES, it = i / W_STAGES;
-                    mbar_wait(&empty_bar[st], (it & 1) ^ 1);
-                    mbar_expect_tx(&full_bar[st], (uint32_t)(W_A_BYTES + ntap * W_B_BYTES));
-                    const int pix0 = (kb0 + i) * 64;
-                    const int ow0 = pix0 % P.Wo, oh0 = (pix0 / P.Wo) % P.Ho, n0 = pix0 / (P.Wo * P.Ho);
-                    uint8_t* sa = smem + (size_t)st * stage_bytes;
-                    tma_load_2d(&tmDy, &full_bar[st], sa, co0, pix0);
-                    tma_load_2d(&tmDy, &full_bar[st], sa + 64 * 128, co0 + 64, pix0);
-                    for (int t = 0; t < ntap; ++t) {
-                        const int tap = tap0 + t, kh = tap / P.k, kw = tap - kh * P.k;
-                        tma_load_4d(&tmX, &full_bar[st], sa + W_A_BYTES + t * W_B_BYTES, ci0, ow0 * P.s - P.p + kw,
-                                    oh0 * P.s - P.p + kh, n0);
-                    }
-                }
-            }
-        } else if (warp == 1) {
-            if (lane == 0) {
-                // D=f32, A=B=bf16, both MN-major, N=64, M=128
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) |
-                                       ((128u >> 4) << 24);
-                for (int i = 0; i < nkb; ++i) {
-                    const int st = i % W_STAGES, it = i / W_STAGES;
-                    mbar_wait(&full_bar[st], it & 1);
-                    tc_fence_after();
-                    const uint32_t sa = base + (uint32_t)st * stage_bytes;
-                    for (int t = 0; t < ntap; ++t) {
-                        const uint32_t sb = sa + W_A_BYTES + t * W_B_BYTES;
-#pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16) {
-                            uint64_t ad = make_mnmajor_sw128_desc(sa + k16 * 2048, 64 * 128);
-                            uint64_t bd = make_mnmajor_sw128_desc(sb + k16 * 2048, 64 * 128);
-                            tc_mma_bf16(tmem_base + t * 64, ad, bd, idesc, (i | k16) != 0 ? 1u : 0u);
-                        }
-                    }
-                    tc_commit(&empty_bar[st]);
-                }
-                tc_commit(&accum_bar);
-            }
-        } else {
-            const int q = warp & 3;
-            const int co = co0 + q * 32 + lane;
-            mbar_wait(&accum_bar, 0);
-            tc_fence_after();
-            const bool vec = (P.kk == 16) && (P.tpg == 8);
-            for (int c16 = 0; c16 < 64; c16 += 16) {
-                if (ci0 + c16 >= P.Ci) break;            // warp-uniform
-                for (int t = 0; t < ntap; t += 4) {
-                    uint32_t v[4][16];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (t + u < ntap) tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t + u) * 64 + c16), v[u]);
-                    if (co >= P.Co) continue;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int ci = ci0 + c16 + j;
-                        if (ci >= P.Ci) break;
-                        float* dst = P.dw + ((int64_t)co * P.Ci + ci) * P.kk + tap0 + t;
-                        if (vec) {
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v[0][j])),
-                                         "f"(__uint_as_float(v[1][j])), "f"(__uint_as_float(v[2][j])),
-                                         "f"(__uint_as_float(v[3][j]))
-                                         : "memory");
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (t + u < ntap) atomicAdd(dst + u, __uint_as_float(v[u][j]));
-                        }
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad, version 2
@@ -1496,6 +1145,31 @@ static int get_act_map(const void* ptr, int N, int H, int W, int C, int bw, int 
     return 0;
 }
 
+// The same tensor seen as (C, W, N, H) -- H outermost -- so that a box {64, bw*es, bn, rows*es} lands in shared memory as
+// [row][image][column][64 ch]: the slab layout of conv_tcp_kernel (rows of a tile ordered (h, n, w)).
+static int get_slab_map(const void* ptr, int N, int H, int W, int C, int bw, int rows, int bn, int es, CUtensorMap* out) {
+    MapKey key(ptr, N, H, W, C, bw, rows, bn, es, 5);
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)H};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(bw * es), (cuuint32_t)bn, (cuuint32_t)(rows * es)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)es, 1, (cuuint32_t)es};
+    CUtensorMap m;
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(slab N=%d H=%d W=%d C=%d box=%d,%d,%d es=%d) failed: %d", N, H, W, C, bw, rows, bn, es,
+                  (int)r);
+        return SG_ERR_UNSUPPORTED;
+    }
+    g_maps[key] = m;
+    *out = m;
+    return 0;
+}
+
 // packed weights [rows][Ktot] bf16 (K contiguous), box {64, BN}
 static int get_w_map(const void* ptr, int rows, int Ktot, int BN, CUtensorMap* out) {
     MapKey key(ptr, rows, Ktot, BN, 0, 0, 0, 0, 0, 2);
@@ -1520,6 +1194,7 @@ static int get_w_map(const void* ptr, int rows, int Ktot, int BN, CUtensorMap* o
 }
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
 // choose the pixel box of a 128-row tile over an [N][Hq][Wq] grid
 static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
@@ -1533,181 +1208,37 @@ static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
     return true;
 }
 
-static int pick_bn(int n_total) {
-    if (n_total <= 256) return (n_total + 15) / 16 * 16;
-    return 128;
-}
-
-static bool g_attr_set = false;
-static bool g_attr2_set = false;
-int g_use_tc2 = 1;     // 2-CTA (cta_group::2) tiles for wide layers; sg_set_option("tc2", 0) disables
-
-// mode 0: fprop (act = x [N][H][W][Ck], out = y [N][Ho][Wo][n_total]);
-// mode 1: dgrad (act = dy [N][Ho][Wo][Ck], out = dx [N][H][W][n_total])
-static int launch_conv_tc(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
-                          int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, cudaStream_t st) {
-    int e = ensure_encode();
-    if (e) return e;
-    TcParams P;
-    int aH, aW;                 // spatial dims of the operand tensor the TMA reads
-    if (mode == 0) {
-        P.Hq = Ho; P.Wq = Wo; P.Ck = Ci; P.n_total = Co; P.outH = Ho; P.outW = Wo; aH = H; aW = W;
-    } else {
-        P.Hq = H / s; P.Wq = W / s; P.Ck = Co; P.n_total = Ci; P.outH = H; P.outW = W; aH = Ho; aW = Wo;
-    }
-    if (!choose_box(P.Hq, P.Wq, &P.bw, &P.bh, &P.bn)) { set_error("conv_tc: grid %dx%d not tileable", P.Hq, P.Wq); return SG_ERR_UNSUPPORTED; }
-    P.M = N * P.Hq * P.Wq;
-    P.BN = pick_bn(P.n_total);
-    P.cblocks = (P.Ck + 63) / 64;
-    P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
-    P.stages = P.BN <= 128 ? 3 : 4;
-    P.tmem_cols = 32;
-    while (P.tmem_cols < P.BN) P.tmem_cols *= 2;
-    CUtensorMap tmA, tmB;
-    int es = mode == 0 ? s : 1;
-    if ((e = get_act_map(act, N, aH, aW, P.Ck, P.bw, P.bh, P.bn, es, &tmA))) return e;
-    int rows = P.n_total, Ktot = k * k * P.Ck;
-    if ((e = get_w_map(wpack, rows, Ktot, P.BN, &tmB))) return e;
-    size_t smem = (size_t)P.stages * (A_STAGE_BYTES + P.BN * 128) + 1024;
-    if (!g_attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return (int)ce; }
-        g_attr_set = true;
-    }
-    int phases = mode == 0 ? 1 : s * s;
-    dim3 grid((P.M + 127) / 128, (P.n_total + P.BN - 1) / P.BN, phases);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P);
-    g_launches.fetch_add(1);
-    return check_launch("conv_tc");
-}
-
-// CTA-pair launch: 256-row x BN tiles (BN = 128 or 256)
-static int launch_conv_tc2(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
-                           int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, cudaStream_t st) {
-    int e = ensure_encode();
-    if (e) return e;
-    TcParams P;
-    int aH, aW;
-    if (mode == 0) {
-        P.Hq = Ho; P.Wq = Wo; P.Ck = Ci; P.n_total = Co; P.outH = Ho; P.outW = Wo; aH = H; aW = W;
-    } else {
-        P.Hq = H / s; P.Wq = W / s; P.Ck = Co; P.n_total = Ci; P.outH = H; P.outW = W; aH = Ho; aW = Wo;
-    }
-    if (!choose_box(P.Hq, P.Wq, &P.bw, &P.bh, &P.bn)) { set_error("conv_tc2: grid not tileable"); return SG_ERR_UNSUPPORTED; }
-    P.M = N * P.Hq * P.Wq;
-    {   // widest tile (<= 256, multiple of 32) that wastes the fewest padded columns
-        int best = 128, best_waste = 1 << 30;
-        for (int bn = 256; bn >= 128; bn -= 32) {
-            int waste = (P.n_total + bn - 1) / bn * bn - P.n_total;
-            if (waste < best_waste) { best_waste = waste; best = bn; }
-        }
-        P.BN = best;
-    }
-    P.cblocks = (P.Ck + 63) / 64;
-    P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
-    P.stages = 3;
-    P.tmem_cols = 32;
-    while (P.tmem_cols < P.BN) P.tmem_cols *= 2;
-    CUtensorMap tmA, tmB;
-    int es = mode == 0 ? s : 1;
-    if ((e = get_act_map(act, N, aH, aW, P.Ck, P.bw, P.bh, P.bn, es, &tmA))) return e;
-    if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, P.BN / 2, &tmB))) return e;
-    size_t smem = (size_t)P.stages * (A_STAGE_BYTES + (P.BN / 2) * 128) + 1024;
-    if (!g_attr2_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(tc2): %s", cudaGetErrorString(ce)); return (int)ce; }
-        g_attr2_set = true;
-    }
-    int phases = mode == 0 ? 1 : s * s;
-    int mt = (P.M + 127) / 128;
-    mt = (mt + 1) / 2 * 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(mt, (P.n_total + P.BN - 1) / P.BN, phases);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, tmA, tmB, P);
-    if (ce != cudaSuccess) { set_error("conv_tc2 launch: %s", cudaGetErrorString(ce)); return (int)ce; }
-    g_launches.fetch_add(1);
-    return check_launch("conv_tc2");
-}
-
 // ---- persistent launch: pick (CTA group, tile width) with a small cost model --------------------------
 // cycles per 64-deep k-block: tcgen05 issue = 2*BN (M=128 per CTA, either group size); operand fetch from L2 =
-// (16 KB of A + BN/CG rows of B) at ~44 B/cycle/SM (the ~12 TB/s L2->SM ceiling shared by 148 SMs).
-int g_use_persist = 1;
+// (the tap's share of the activation slab + BN/CG rows of B) at ~44 B/cycle/SM (the ~12 TB/s L2->SM ceiling shared by
+// 148 SMs).
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
-// alternate-tile epilogue for narrow tiles: OFF by default (option "epi_alt" / env SG_EPI_ALT=1) until it has been through the
-// full GPU test suite
-int g_epi_alt = getenv("SG_EPI_ALT") ? atoi(getenv("SG_EPI_ALT")) : 0;
+int g_use_slab = 1;      // option "slab": 0 = one activation box per tap (no sharing), for A/B measurements
+int g_use_nsplit = 1;    // option "nsplit": 0 = no column slices in the last round
+unsigned long long* g_trace = nullptr;   // sg_debug_conv_trace
+int g_rotate = 0;        // option "rotate": measured neutral on B200 (gpurun_out/bench_conv_r2i.txt), off
+// alternate-tile epilogue for narrow tiles (option "epi_alt" / env SG_EPI_ALT)
+int g_epi_alt = getenv("SG_EPI_ALT") ? atoi(getenv("SG_EPI_ALT")) : 1;
 static bool g_pattr_set = false;
+constexpr int TCP_SMEM_BYTES = 205 * 1024;
 
-// ---- tail-wave K-split scratch: fp32 partial tiles + flags, one slot per stream that launches split kernels (kernels of
-// one stream are ordered; kernels of different streams may overlap and must not share partials).  Allocated once per
-// device by sg_check_device() -- never inside a launch, so launches stay capturable.
-constexpr int WS_SLOTS = 4;
-constexpr size_t WS_BYTES = (size_t)SG_NUM_SMS * 128 * 256 * sizeof(float);     // >= (split-1)*R*CG partial tiles of 128 x 256
-struct WsSlot {
-    float* ws = nullptr;
-    int* flags = nullptr;
-    cudaStream_t stream = nullptr;
-    bool used = false;
-};
-static WsSlot g_ws[16][WS_SLOTS];
-static std::mutex g_ws_mu;
-int g_use_split = 1;
-
-int tcp_workspace_init() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
-    std::lock_guard<std::mutex> lk(g_ws_mu);
-    for (int i = 0; i < WS_SLOTS; ++i) {
-        if (g_ws[dev][i].ws) continue;
-        if (cudaMalloc(&g_ws[dev][i].ws, WS_BYTES) != cudaSuccess) { g_ws[dev][i].ws = nullptr; cudaGetLastError(); return 0; }
-        if (cudaMalloc(&g_ws[dev][i].flags, 4 * SG_NUM_SMS * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 0; }
-        cudaMemset(g_ws[dev][i].flags, 0, 4 * SG_NUM_SMS * sizeof(int));
-    }
-    return 0;
-}
-static WsSlot* ws_slot_for(cudaStream_t st) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    std::lock_guard<std::mutex> lk(g_ws_mu);
-    for (int i = 0; i < WS_SLOTS; ++i)
-        if (g_ws[dev][i].used && g_ws[dev][i].stream == st) return g_ws[dev][i].ws ? &g_ws[dev][i] : nullptr;
-    for (int i = 0; i < WS_SLOTS; ++i)
-        if (!g_ws[dev][i].used && g_ws[dev][i].ws) { g_ws[dev][i].used = true; g_ws[dev][i].stream = st; return &g_ws[dev][i]; }
-    return nullptr;
-}
-// slices per leftover tile: as many as there are idle clusters per leftover tile, >= 4 k-blocks each
-// returns S and the estimated duration of the split round in cycles (t_kb: cycles per k-block)
-static int split_factor(long tiles, int units, int nkb, int bn = 256, double t_kb = 600.0, double* t_round = nullptr) {
+// column slices for the leftover tiles of the last round: returns S (1 = none) and the slice width
+static int nsplit_plan(long tiles, int units, int bn, int cg, int* bn2) {
+    *bn2 = bn;
+    if (!g_use_nsplit) return 1;
     const int R = (int)(tiles % units);
-    double best_t = nkb * t_kb;
-    int best = 1;
-    if (g_use_split && R != 0) {
-        int smax = units / R;
-        if (smax > nkb / 4) smax = nkb / 4;
-        if (smax > 6) smax = 6;
-        // a slice costs its share of the mainloop; a non-owner then drains its accumulator to the workspace (measured
-        // ~5.5 us for 128 x 256 fp32), the owner's drain grows by ~3 us per partial it adds (critic ds3 trace)
-        const double cs = g_use_split == 2 ? 0.0 : 1.0;      // option split=2: ignore the costs (experiments)
-        const double c_store = cs * 10000.0 * bn / 256.0, c_read = cs * 5700.0 * bn / 256.0;
-        for (int S = 2; S <= smax; ++S) {
-            const int kbs = (nkb + S - 1) / S;
-            const double t = kbs * t_kb + c_store + (S - 1) * c_read + 1000.0;
-            if (t < best_t * 0.9) { best_t = t; best = S; }
-        }
-    }
-    if (t_round) *t_round = best_t;
-    return best;
+    if (R == 0) return 1;
+    int S = units / R;
+    if (S > bn / 32) S = bn / 32;
+    if (S < 2) return 1;
+    int w = ((bn + S - 1) / S + 31) / 32 * 32;      // multiple of 32: whole 32-column epilogue groups, 16*CG for the MMA
+    S = (bn + w - 1) / w;
+    if (S < 2) return 1;
+    *bn2 = w;
+    return S;
 }
 
-static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out, int* bn_out) {
+static void pick_tcp_config(int M, int n_total, int phases, int nkb, double a_share, int* cg_out, int* bn_out) {
     double best = 1e30;
     int best_cg = 1, best_bn = 16;
     for (int cg = 1; cg <= 2; ++cg) {
@@ -1725,18 +1256,22 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out
             int m_tiles = (M + 128 * cg - 1) / (128 * cg);
             long tiles = (long)m_tiles * n_tiles * phases;
             int units = SG_NUM_SMS / cg;
-            double mma = 2.0 * bn;
-            double l2 = (16384.0 + (double)(bn / cg) * 128.0) / 44.0;
-            double t_kb = mma > l2 ? mma : l2;
-            double t_tile = nkb * t_kb + 150.0;
+            auto t_kblock = [&](int width) {
+                double mma = 2.0 * width;
+                double l2 = (16384.0 * a_share + (double)(width / cg) * 128.0) / 44.0;
+                return mma > l2 ? mma : l2;
+            };
+            double t_tile = nkb * t_kblock(bn) + 150.0;
             double epi = 40.0 * bn / 16.0 + 400.0;                  // drain of the last tile, not overlapped
             double t_epi_tile = 40.0 * bn / 16.0 + 100.0;           // epilogue pace per tile
             if (t_epi_tile > t_tile) t_tile = t_epi_tile;
-            // rounds of the persistent tile loop; a partly filled last round may be cut along K over the idle clusters
+            // rounds of the persistent tile loop; a partly filled last round may be cut into column slices
             double t_last = 0.0;
             if (tiles % units) {
-                split_factor(tiles, units, nkb, bn, t_kb, &t_last);
-                t_last += 150.0;
+                int bn2;
+                const int S = nsplit_plan(tiles, units, bn, cg, &bn2);
+                t_last = nkb * t_kblock(S > 1 ? bn2 : bn) + 150.0;
+                if (S > 1) epi = 40.0 * bn2 / 16.0 + 400.0;
             }
             double t = (double)(tiles / units) * t_tile + t_last + epi;
             if (t < best) { best = t; best_cg = cg; best_bn = bn; }
@@ -1745,12 +1280,15 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, int* cg_out
     *cg_out = best_cg; *bn_out = best_bn;
 }
 
+// mode 0: fprop (act = x [N][H][W][Ck], out = y [N][Ho][Wo][n_total]);
+// mode 1: dgrad (act = dy [N][Ho][Wo][Ck], out = dx [N][H][W][n_total])
 static int launch_conv_tcp(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
                            int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, double* stats, int groups,
                            cudaStream_t st, float* out32 = nullptr, const void* residual = nullptr) {
     int e = ensure_encode();
     if (e) return e;
-    TcpParams P;
+    static TcpParams Pz;        // zero-initialised template (the slab table has padding the compiler would not clear)
+    TcpParams P = Pz;
     int aH, aW;
     if (mode == 0) {
         P.Hq = Ho; P.Wq = Wo; P.Ck = Ci; P.n_total = Co; P.outH = Ho; P.outW = Wo; aH = H; aW = W;
@@ -1764,23 +1302,82 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
         return SG_ERR_UNSUPPORTED;
     }
     P.n_img = N;
-    P.lgW = 0; while ((1 << P.lgW) < P.Wq) ++P.lgW;
-    P.lgHW = P.lgW; while ((1 << P.lgHW) < P.Hq * P.Wq) ++P.lgHW;
+    P.lgW = ilog2(P.Wq); P.lgHW = ilog2(P.Hq * P.Wq);
+    P.lgBW = ilog2(P.bw); P.lgNW = ilog2(P.bn * P.bw);
     P.cblocks = (P.Ck + 63) / 64;
-    P.mode = mode; P.k = k; P.s = s; P.p = p; P.act = actf; P.bias = bias; P.out = (bf16*)out;
+    P.mode = mode; P.s = s; P.es = mode == 0 ? s : 1; P.act = actf; P.bias = bias; P.out = (bf16*)out;
     P.stats = stats;
     P.out32 = out32;
     P.residual = (const bf16*)residual;
+    P.trace = g_trace;
     if (out32) P.out = nullptr;
     P.imgs_per_group = groups > 0 ? N / groups : N;
     const int phases = mode == 0 ? 1 : s * s;
-    const int taps = mode == 0 ? k * k : (k / s) * (k / s);
+    // ---- slab table: which taps share one activation slab (see the kernel's header comment)
+    const int row_bytes = P.bn * P.bw * 128;                  // one output row of the tile, all its images
+    const bool share = g_use_slab && (P.bn * P.bw) % 8 == 0;  // tap offsets must be whole 1024-byte swizzle atoms
+    int nv_max = 1, taps_per_phase = 0;
+    for (int ph = 0; ph < phases; ++ph) {
+        int n = 0, taps = 0;
+        if (mode == 0) {
+            const int nclass = share ? (s < k ? s : k) : k;   // sharing: one class per input-row parity; else one per tap row
+            for (int c = 0; c < nclass; ++c) {
+                const int nv = share ? (k - c + s - 1) / s : 1;
+                for (int kw = 0; kw < k; ++kw) {
+                    SlabEnt& E = P.slab[ph][n++];
+                    E.dw = (int16_t)(-p + kw); E.dh = (int16_t)(-p + c); E.nv = (int16_t)nv;
+                    for (int i = 0; i < nv; ++i) {
+                        const int kh = share ? c + i * s : c;
+                        E.bk[i] = (kh * k + kw) * P.Ck;
+                        E.roff[i] = i * row_bytes;
+                    }
+                    taps += nv;
+                }
+                if (nv > nv_max) nv_max = nv;
+            }
+        } else {
+            const int phh = ph / s, pww = ph - phh * s;
+            const int rh = (phh + p) % s, rw = (pww + p) % s;
+            const int nth = (k - rh + s - 1) / s, ntw = (k - rw + s - 1) / s;
+            const int base_h = (phh + p - rh) / s, base_w = (pww + p - rw) / s;
+            const int nclass = share ? 1 : nth;
+            for (int c = 0; c < nclass; ++c) {
+                const int nv = share ? nth : 1;
+                for (int tw = 0; tw < ntw; ++tw) {
+                    SlabEnt& E = P.slab[ph][n++];
+                    E.dw = (int16_t)(base_w - tw);
+                    E.dh = (int16_t)(share ? base_h - (nth - 1) : base_h - c);
+                    E.nv = (int16_t)nv;
+                    for (int i = 0; i < nv; ++i) {
+                        // sharing: tap th reads rows h0 + base_h - th + j = slab row (nth - 1 - th) + j; store the taps in
+                        // slab-row order (i = nth - 1 - th)
+                        const int th = share ? nth - 1 - i : c;
+                        E.bk[i] = ((rh + s * th) * k + (rw + s * tw)) * P.Ck;
+                        E.roff[i] = i * row_bytes;
+                    }
+                    taps += nv;
+                }
+                if (nv > nv_max) nv_max = nv;
+            }
+        }
+        if (n > 16) { set_error("conv_tcp: %d slabs per phase exceed the table", n); return SG_ERR_UNSUPPORTED; }
+        P.nslab[ph] = n;
+        if (ph == 0) taps_per_phase = taps;
+        else if (taps != taps_per_phase || n != P.nslab[0]) { set_error("conv_tcp: phases with unequal tap counts"); return SG_ERR_UNSUPPORTED; }
+    }
+    const int slab_rows = P.bh + nv_max - 1;
+    P.slab_bytes = slab_rows * row_bytes;
+    P.slab_pad = (P.slab_bytes + 1023) / 1024 * 1024;
+    P.kiters = P.nslab[0] * P.cblocks;
+    P.rotate = g_rotate;
+    const int nkb = taps_per_phase * P.cblocks;               // 64-deep k-blocks per tile
     int cg, bn;
-    pick_tcp_config(M, P.n_total, phases, taps * P.cblocks, &cg, &bn);
+    pick_tcp_config(M, P.n_total, phases, nkb, (double)slab_rows / (double)(nv_max * P.bh), &cg, &bn);
     P.BN = bn;
     P.n_tiles = (P.n_total + bn - 1) / bn;
     P.m_tiles = (M + 128 * cg - 1) / (128 * cg);
-    P.total_tiles = P.m_tiles * P.n_tiles * phases;
+    P.tiles_per_phase = P.m_tiles * P.n_tiles;
+    P.total_tiles = P.tiles_per_phase * phases;
     P.acc_stride = bn;
     // accumulator ring in TMEM: 2 buffers for wide tiles, up to 8 for narrow ones -- with short mainloops (thin layers,
     // 1x1 GEMMs) the MMA warp must be able to run several tiles ahead of the epilogue to hide the barrier round trips
@@ -1789,42 +1386,39 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     if (P.nbuf < 2) P.nbuf = 2;
     P.tmem_cols = 32;
     while (P.tmem_cols < P.nbuf * bn) P.tmem_cols *= 2;
-    const int stage_bytes = A_STAGE_BYTES + (bn / cg) * 128;
-    P.stages = (200 * 1024 - 2048) / stage_bytes;
+    P.b_bytes = (bn / cg) * 128;
+    P.stage_bytes = P.slab_pad + nv_max * P.b_bytes;
+    P.stages = (TCP_SMEM_BYTES - 1024) / P.stage_bytes;
     if (P.stages > 8) P.stages = 8;
     if (g_force_stages && g_force_stages < P.stages) P.stages = g_force_stages;
+    if (P.stages < 2) { set_error("conv_tcp: a %d-byte stage does not fit twice", P.stage_bytes); return SG_ERR_UNSUPPORTED; }
     if (g_dbg & 1) P.out = nullptr;
-    CUtensorMap tmA, tmB;
-    const int es = mode == 0 ? s : 1;
-    if ((e = get_act_map(act, N, aH, aW, P.Ck, P.bw, P.bh, P.bn, es, &tmA))) return e;
+    // ---- work list: whole tiles, then the column slices of the last round's leftover tiles
+    const int units = SG_NUM_SMS / cg;
+    P.full_tiles = P.total_tiles; P.nslices = 1; P.BN2 = bn;
+    {
+        int bn2;
+        const int S = nsplit_plan(P.total_tiles, units, bn, cg, &bn2);
+        if (S > 1) {
+            P.full_tiles = P.total_tiles - P.total_tiles % units;
+            P.nslices = S; P.BN2 = bn2;
+        }
+    }
+    P.total_work = P.full_tiles + (P.total_tiles - P.full_tiles) * P.nslices;
+    const int clusters = P.total_work < units ? P.total_work : units;
+    CUtensorMap tmA, tmB, tmB2;
+    if ((e = get_slab_map(act, N, aH, aW, P.Ck, P.bw, slab_rows, P.bn, P.es, &tmA))) return e;
     if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, bn / cg, &tmB))) return e;
-    size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, P.BN2 / cg, &tmB2))) return e;
+    size_t smem = (size_t)P.stages * P.stage_bytes + 1024;
     if (!g_pattr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
         if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(tcp): %s", cudaGetErrorString(ce)); return (int)ce; }
         g_pattr_set = true;
     }
-    int units = SG_NUM_SMS / cg;
-    int clusters = P.total_tiles < units ? P.total_tiles : units;
-    P.full_tiles = P.total_tiles; P.split = 1; P.kb_slice = taps * P.cblocks; P.ws = nullptr; P.flags = nullptr;
-    {
-        const int nkb = taps * P.cblocks;
-        const double mma_c = 2.0 * bn, l2_c = (16384.0 + (double)(bn / cg) * 128.0) / 44.0;
-        int S = split_factor(P.total_tiles, units, nkb, bn, mma_c > l2_c ? mma_c : l2_c);
-        WsSlot* slot = S > 1 ? ws_slot_for(st) : nullptr;
-        if (slot != nullptr) {
-            const int F = P.total_tiles / units, R = P.total_tiles % units;
-            P.kb_slice = (nkb + S - 1) / S;
-            S = (nkb + P.kb_slice - 1) / P.kb_slice;
-            if (S > 1 && (size_t)(S - 1) * R * cg * 128 * bn * sizeof(float) <= WS_BYTES) {
-                P.split = S; P.full_tiles = F * units; P.ws = slot->ws; P.flags = slot->flags;
-                clusters = F > 0 ? units : R * S;
-            }
-        }
-    }
     // two tiles in flight in the epilogue need two accumulator buffers beyond the one being filled: nbuf >= 4 (bn <= 128)
-    P.epi_alt = (g_epi_alt && stats == nullptr && P.split == 1 && bn <= 64 && P.nbuf >= 4) ? 1 : 0;
+    P.epi_alt = (g_epi_alt && stats == nullptr && bn <= 64 && P.nbuf >= 4) ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * cg, 1, 1);
     cfg.blockDim = dim3(TCP_THREADS);
@@ -1836,77 +1430,11 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 2;
-    cudaError_t ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2>, tmA, tmB, P)
-                             : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1>, tmA, tmB, P);
+    cudaError_t ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2>, tmA, tmB, tmB2, P)
+                             : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1>, tmA, tmB, tmB2, P);
     if (ce != cudaSuccess) { set_error("conv_tcp launch: %s", cudaGetErrorString(ce)); return (int)ce; }
     g_launches.fetch_add(1);
     return check_launch("conv_tcp");
-}
-
-static bool choose_box64(int Ho, int Wo, int* bw, int* bh, int* bn) {
-    if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
-    if (Wo >= 64) { *bw = 64; *bh = 1; *bn = 1; return true; }
-    *bw = Wo;
-    int rows = 64 / Wo;
-    if (Ho >= rows) { *bh = rows; *bn = 1; return true; }
-    *bh = Ho;
-    *bn = rows / Ho;
-    return true;
-}
-
-// 2-D [rows][C] bf16 view, box {64, 64}
-static int get_rows_map(const void* ptr, int64_t rows, int C, CUtensorMap* out) {
-    MapKey key(ptr, (int)rows, C, 64, 64, 0, 0, 0, 0, 22);
-    std::lock_guard<std::mutex> lk(g_maps_mu);
-    auto it = g_maps.find(key);
-    if (it != g_maps.end()) { *out = it->second; return 0; }
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {64, 64};
-    cuuint32_t estr[2] = {1, 1};
-    CUtensorMap m;
-    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rows=%lld C=%d) failed: %d", (long long)rows, C, (int)r); return SG_ERR_UNSUPPORTED; }
-    g_maps[key] = m;
-    *out = m;
-    return 0;
-}
-
-static bool g_wattr_set = false;
-
-static int launch_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
-                           int k, int s, int p, cudaStream_t st) {
-    int e = ensure_encode();
-    if (e) return e;
-    TcWParams P;
-    P.Mpix = N * Ho * Wo; P.Ho = Ho; P.Wo = Wo; P.Co = Co; P.Ci = Ci; P.kk = k * k; P.k = k; P.s = s; P.p = p; P.dw = dw;
-    if (!choose_box64(Ho, Wo, &P.bw, &P.bh, &P.bn)) { set_error("wgrad_tc: grid not tileable"); return SG_ERR_UNSUPPORTED; }
-    P.tpg = P.kk < 8 ? P.kk : 8;
-    P.tap_groups = (P.kk + P.tpg - 1) / P.tpg;
-    CUtensorMap tmDy, tmX;
-    if ((e = get_rows_map(dy, P.Mpix, Co, &tmDy))) return e;
-    if ((e = get_act_map(x, N, H, W, Ci, P.bw, P.bh, P.bn, s, &tmX))) return e;
-    int co_tiles = (Co + 127) / 128, ci_blocks = (Ci + 63) / 64;
-    int tiles = co_tiles * ci_blocks * P.tap_groups;
-    int total_kb = (P.Mpix + 63) / 64;
-    int want = (SG_NUM_SMS + tiles - 1) / tiles;          // about one wave of CTAs
-    int max_splits = (total_kb + 3) / 4;                  // at least 4 k-blocks per CTA
-    int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
-    if (splits < 1) splits = 1;
-    P.kb_per_split = (total_kb + splits - 1) / splits;
-    splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
-    size_t smem = (size_t)W_STAGES * (W_A_BYTES + P.tpg * W_B_BYTES) + 1024;
-    if (!g_wattr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(ce)); return (int)ce; }
-        g_wattr_set = true;
-    }
-    dim3 grid(co_tiles, ci_blocks * P.tap_groups, splits);
-    conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmDy, tmX, P);
-    g_launches.fetch_add(1);
-    return check_launch("conv_wgrad_tc");
 }
 
 static bool choose_box_n(int npix, int Ho, int Wo, int* bw, int* bh, int* bn) {
@@ -1940,7 +1468,6 @@ static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtens
     return 0;
 }
 
-int g_use_wgrad2 = 1;
 int g_use_wgrad_mc = 1;
 
 template <int PIX>
@@ -2048,15 +1575,22 @@ int sg_conv_tc_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, 
     if (s < 1 || s > 2 || k % s != 0 || k > 4) return 0;
     if (mode == 1 && (H % s != 0 || W % s != 0)) return 0;
     if (!choose_box(Hq, Wq, &bw, &bh, &bn)) return 0;
-    if (bw * s > 256 || bh * s > 256) return 0;
+    if (bw * s > 256 || (bh + 3) * s > 256) return 0;          // TMA box extents (a slab is up to bh + 3 rows)
     return 1;
 }
 
+// Profiling hook: while ``buf`` (device memory, >= 296 * 16 uint64) is set, every persistent conv launch writes 16
+// %globaltimer stamps per CTA into it (kernel entry, set-up done, first operands landed, first / last work item issued,
+// drained, exit -- see trace_stamp() call sites); NULL switches it off.  tools/exp_conv_trace.py prints the timeline.
+int sg_debug_conv_trace(void* buf) {
+    g_trace = reinterpret_cast<unsigned long long*>(buf);
+    return 0;
+}
+
 int sg_set_option(const char* name, int value) {
-    if (name && !strcmp(name, "tc2")) { g_use_tc2 = value; return 0; }
-    if (name && !strcmp(name, "persist")) { g_use_persist = value; return 0; }
-    if (name && !strcmp(name, "wgrad2")) { g_use_wgrad2 = value; return 0; }
-    if (name && !strcmp(name, "split")) { g_use_split = value; return 0; }
+    if (name && !strcmp(name, "slab")) { g_use_slab = value; return 0; }
+    if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
+    if (name && !strcmp(name, "rotate")) { g_rotate = value; return 0; }
     if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }
     if (name && !strcmp(name, "pdl")) { g_use_pdl = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
@@ -2068,17 +1602,11 @@ int sg_set_option(const char* name, int value) {
     return SG_ERR_BAD_ARG;
 }
 
-static bool want_tc2(int n_total, int M) { return g_use_tc2 && n_total >= 128 && n_total % 32 == 0 && M >= 256; }
-
 int sg_conv_fprop_tc(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho, int Wo,
                      int Co, int k, int s, int p, int act, int dtype, void* stream) {
     SG_REQUIRE(dtype == SG_BF16, "conv_fprop_tc: bf16 only");
     SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc: unsupported shape");
-    if (g_use_persist)
-        return launch_conv_tcp(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream));
-    if (want_tc2(Co, N * Ho * Wo))
-        return launch_conv_tc2(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
-    return launch_conv_tc(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
+    return launch_conv_tcp(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream));
 }
 
 int sg_conv_dgrad_tc(const void* dy, const void* pd, const float* bias, void* dx, int N, int H, int W, int Ci, int Ho,
@@ -2086,18 +1614,14 @@ int sg_conv_dgrad_tc(const void* dy, const void* pd, const float* bias, void* dx
     SG_REQUIRE(dtype == SG_BF16, "conv_dgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_dgrad_tc: unsupported shape");
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc: inconsistent sizes");
-    if (g_use_persist)
-        return launch_conv_tcp(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream));
-    if (want_tc2(Ci, N * (H / s) * (W / s)))
-        return launch_conv_tc2(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
-    return launch_conv_tc(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, SG_STREAM(stream));
+    return launch_conv_tcp(1, dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream));
 }
 
 int sg_conv_wgrad_tc_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p) {
     int bw, bh, bn;
     if (Ci % 8 != 0 || Co % 8 != 0) return 0;
     if (s < 1 || s > 2 || k > 4) return 0;
-    if (!choose_box64(Ho, Wo, &bw, &bh, &bn)) return 0;
+    if (!choose_box_n(32, Ho, Wo, &bw, &bh, &bn)) return 0;       // 32-pixel k-blocks must not straddle images
     if (bw * s > 256 || bh * s > 256) return 0;
     return 1;
 }
@@ -2106,9 +1630,9 @@ int sg_conv_wgrad_tc_supported(int N, int H, int W, int Ci, int Ho, int Wo, int 
 // adds it into the PyTorch-layout gradient
 int sg_conv_wgrad_cl_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype) {
     int bw, bh, bn;
-    if (dtype != SG_BF16 || !g_use_wgrad2 || Ci % 4 != 0) return 0;
-    if (!sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p)) return 0;
-    return choose_box_n(32, Ho, Wo, &bw, &bh, &bn) && bw * s <= 256 && bh * s <= 256;
+    if (dtype != SG_BF16 || Ci % 4 != 0) return 0;
+    (void)bw; (void)bh; (void)bn;
+    return sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p);
 }
 int sg_conv_wgrad_cl(const void* x, const void* dy, float* gw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
                      int s, int p, int dtype, void* stream) {
@@ -2120,19 +1644,12 @@ int sg_conv_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int
                      int s, int p, int dtype, void* stream) {
     SG_REQUIRE(dtype == SG_BF16, "conv_wgrad_tc: bf16 only");
     SG_REQUIRE(sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_wgrad_tc: unsupported shape");
-    if (g_use_wgrad2) {
-        int bw, bh, bn;
-        // 32-pixel blocks must not straddle images unless whole images fit a block
-        if (choose_box_n(32, Ho, Wo, &bw, &bh, &bn) && bw * s <= 256 && bh * s <= 256)
-            return launch_wgrad2(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
-    }
-    return launch_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
+    return launch_wgrad2(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_STREAM(stream));
 }
 
 // y = act(conv(x, W) + bias + residual): the closing layer of a residual block (generator_2.py:23-26) in one kernel
 int sg_conv_fprop_tc_res(const void* x, const void* pf, const float* bias, const void* residual, void* y, int N, int H, int W,
                          int Ci, int Ho, int Wo, int Co, int k, int s, int p, int act, void* stream) {
-    SG_REQUIRE(g_use_persist, "conv_fprop_tc_res needs the persistent kernel");
     SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc_res: unsupported shape");
     return launch_conv_tcp(0, x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, nullptr, 1, SG_STREAM(stream), nullptr,
                            residual);
@@ -2141,7 +1658,6 @@ int sg_conv_fprop_tc_res(const void* x, const void* pf, const float* bias, const
 // y (FP32) = conv(x, W) with bf16 operands: the un-rounded accumulators, for results that are summed again (col2im)
 int sg_conv_fprop_tc_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                             int k, int s, int p, void* stream) {
-    SG_REQUIRE(g_use_persist, "conv_fprop_tc_f32out needs the persistent kernel");
     SG_REQUIRE(sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p), "conv_fprop_tc_f32out: unsupported shape");
     return launch_conv_tcp(0, x, pf, nullptr, nullptr, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, nullptr, 1,
                            SG_STREAM(stream), y);
@@ -2151,7 +1667,7 @@ int sg_conv_fprop_tc_f32out(const void* x, const void* pf, float* y, int N, int 
 // of the BatchNorm that follows), fused into the epilogue.  Returns SG_ERR_UNSUPPORTED (without launching)
 // when the shape cannot be fused; the dispatcher then runs the conv and sg_col_stats separately.
 int sg_conv_tc_stats_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups) {
-    if (!g_use_persist || groups < 1 || N % groups != 0) return 0;
+    if (groups < 1 || N % groups != 0) return 0;
     if (!sg_conv_tc_supported(mode, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return 0;
     int Hq = mode == 0 ? Ho : H / s, Wq = mode == 0 ? Wo : W / s;
     long rows_per_group = (long)(N / groups) * Hq * Wq;

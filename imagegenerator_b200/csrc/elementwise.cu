@@ -12,7 +12,6 @@ std::atomic<long long> g_launches{0};
 int g_use_pdl = 1;
 static thread_local char g_err[512] = "";
 
-int tcp_workspace_init();
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -757,8 +756,9 @@ __global__ void __launch_bounds__(256) gen_loss_kernel(const float* s, const flo
 // ---- conditioning augmentation elementwise parts
 template <typename T>
 __global__ void ca_reparam_kernel(const float* mu, const float* sigma, const float* eps, const float* z, float* c_hat,
-                                  T* cg, int N, int C, int nz) {
-    int W = C + nz;
+                                  T* cg, int N, int C, int nz, int W) {
+    // W = row length of cg >= C + nz: columns past C + nz are zero padding (the generator's first layer runs as a GEMM
+    // over K = W channels, a multiple of 64)
     int64_t total = (int64_t)N * W;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int n = (int)(i / W), j = (int)(i - (int64_t)n * W);
@@ -767,8 +767,10 @@ __global__ void ca_reparam_kernel(const float* mu, const float* sigma, const flo
             float c = mu[k] + sigma[k] * eps[k];
             c_hat[k] = c;
             if (cg) stf(cg + i, c);
-        } else if (cg && z) {
+        } else if (cg && z && j < C + nz) {
             stf(cg + i, z[(int64_t)n * nz + (j - C)]);
+        } else if (cg && j >= C + nz) {
+            stf(cg + i, 0.f);
         }
     }
 }
@@ -817,7 +819,6 @@ int sg_check_device(void) {
         return SG_ERR_NO_DEVICE;
     }
     if (const char* e = getenv("SG_PDL")) sg::g_use_pdl = atoi(e);      // 0 disables programmatic dependent launch
-    sg::tcp_workspace_init();     // the one allocation of the library: scratch for the conv kernel's tail-wave K-split
     return 0;
 }
 
@@ -1147,10 +1148,11 @@ int sg_outer(const float* coef, const float* vec, void* out, int N, int M, int o
 }
 
 int sg_ca_reparam(const float* mu, const float* sigma, const float* eps, const float* z, float* c_hat, void* cg, int N,
-                  int C, int nz, int dtype, void* stream) {
-    int64_t n = (int64_t)N * (C + nz);
+                  int C, int nz, int ld, int dtype, void* stream) {
+    SG_REQUIRE(ld >= C + nz, "ca_reparam: row length %d < %d + %d", ld, C, nz);
+    int64_t n = (int64_t)N * ld;
     SG_DISPATCH_T(dtype, (ca_reparam_kernel<T><<<grid_for(n, 256), 256, 0, SG_STREAM(stream)>>>(mu, sigma, eps, z, c_hat,
-                                                                                               (T*)cg, N, C, nz)));
+                                                                                               (T*)cg, N, C, nz, ld)));
     SG_LAUNCHED("ca_reparam");
     return 0;
 }

@@ -84,16 +84,60 @@ def _side_run(side, fn):
 class _LayerRT:
     """One conv operator (Conv2d orientation: ``co`` x ``ci`` x k x k weight) + optional BN."""
 
-    def __init__(self, ops, conv, bn):
+    def __init__(self, ops, conv, bn, packs=True):
         self.conv, self.bn = conv, bn
         w = conv.weight
         self.co, self.ci, self.k = w.shape[0], w.shape[1], w.shape[2]
         self.s, self.p = conv.stride, conv.pad
-        self.pf = ops.empty((self.co, self.k, self.k, self.ci))
-        self.pd = ops.empty((self.ci, self.k, self.k, self.co))
+        self.pf = ops.empty((self.co, self.k, self.k, self.ci)) if packs else None
+        self.pd = ops.empty((self.ci, self.k, self.k, self.co)) if packs else None
 
     def pack(self, ops):
         ops.pack_weight(self.conv.weight.data, self.pf, self.pd)
+
+
+class Up0Gemm:
+    """The Stage-I generator's first layer, ConvTranspose2d(228 -> 192, k4, s1, p0) on a 1x1 input (generator_1.py:9-13,
+    :38-39), as what it is: a GEMM  [B, 228] x [228, 16*192]  whose output row IS the NHWC [4][4][192] feature map.
+
+    The conv kernels read 64-channel blocks through TMA, and 228 is not a multiple of 8 -- as a convolution this layer
+    (and only this layer) used to fall back to the CUDA-core kernel.  Here the reduction is zero-padded to Kp = 256
+    channels ([c_hat, z, 0...] rows, sg_ca_reparam) and all three directions run as 1x1 convolutions on the tensor-core
+    kernels:
+        forward      y[B, (h,w,ci)]   = cg[B, Kp]        . wf[(h,w,ci)][Kp]^T
+        input grad   dcg[B, Kp]       = dy[B, (h,w,ci)]  . wb[Kp][(h,w,ci)]^T
+        weight grad  gw[Kp][(h,w,ci)] += cg^T dy   -> folded into the PyTorch-layout .grad [228][192][4][4]
+    """
+
+    def __init__(self, ops, conv, B):
+        w = conv.weight
+        self.ops, self.conv, self.B = ops, conv, B
+        self.co, self.ci, self.k = w.shape[0], w.shape[1], w.shape[2]
+        self.Kp = (self.co + 63) // 64 * 64
+        self.NO = self.ci * self.k * self.k
+        f32 = ops.f32
+        self.w_cl32 = ops.zeros((self.Kp, self.k, self.k, self.ci), f32)      # [co][h][w][ci], rows >= co stay zero
+        self.wf = ops.empty((self.NO, 1, 1, self.Kp))
+        self.wb = ops.zeros((self.Kp, 1, 1, self.NO))
+        self.gw = ops.zeros((self.Kp, self.NO, 1, 1), f32)
+
+    def pack(self):
+        ops, W = self.ops, self.conv.weight.data
+        ops.nchw_to_nhwc(W, self.w_cl32[:self.co])                                             # fp32 [co][h][w][ci]
+        ops.nchw_to_nhwc(self.w_cl32.view(1, self.Kp, self.NO, 1), self.wf.view(1, self.NO, 1, self.Kp))   # transpose
+        ops.nchw_to_nhwc(W, self.wb.view(self.Kp, self.k, self.k, self.ci)[:self.co])
+
+    def forward(self, cg, y):
+        self.ops.conv_fprop(cg, self.wf, None, y.view(y.shape[0], 1, 1, self.NO), 1, 1, 0)
+
+    def input_grad(self, dy, dcg):
+        self.ops.conv_fprop(dy.view(dy.shape[0], 1, 1, self.NO), self.wb, None, dcg, 1, 1, 0)
+
+    def weight_grad(self, cg, dy):
+        """``conv.weight.grad`` += the gradient (accumulated in gw, then folded and cleared)."""
+        ops = self.ops
+        ops.conv_wgrad(dy.view(dy.shape[0], 1, 1, self.NO), cg, self.gw, 1, 1, 0)
+        ops.fold_grad_cl(self.gw.view(self.Kp, self.k, self.k, self.ci)[:self.co], self.conv.weight.grad)
 
 
 # ============================================================================================ CA
@@ -155,9 +199,11 @@ class GenRT:
     def __init__(self, ops, module, B, out=None):
         self.ops, self.m, self.B = ops, module, B
         self.fp = FlatParams.of(module, ops.device, dtype=ops.f32)
-        self.layers = [_LayerRT(ops, c, bn) for c, bn in module.conv_layers()]
-        self.cg = ops.empty((B, 1, 1, self.layers[0].co))
-        self.dcg = ops.empty((B, 1, 1, self.layers[0].co))
+        cl = module.conv_layers()
+        self.layers = [_LayerRT(ops, c, bn, packs=(i > 0)) for i, (c, bn) in enumerate(cl)]
+        self.up0 = Up0Gemm(ops, cl[0][0], B)             # first layer: a GEMM over the zero-padded [c_hat, z] rows
+        self.cg = ops.zeros((B, 1, 1, self.up0.Kp))
+        self.dcg = ops.empty((B, 1, 1, self.up0.Kp))
         h = 1
         self.y, self.a, self.dy, self.da, self.mr, self.stats, self.sums = [], [], [], [], [], [], []
         # BN statistics accumulators of all layers in one buffer: one memset per forward instead of one per layer
@@ -181,13 +227,16 @@ class GenRT:
         self.packed = False
 
     def refresh_weights(self):
-        for L in self.layers:
+        self.up0.pack()
+        for L in self.layers[1:]:
             L.pack(self.ops)
         self.packed = True
 
     def set_input(self, x):
         """x [B, c_dim+z_dim] fp32 -> cg buffer (module-level API only; the engine writes cg directly)."""
-        self.ops.nchw_to_nhwc(x.reshape(self.B, -1, 1, 1).contiguous().float(), self.cg)
+        xp = torch.zeros(self.B, self.up0.Kp, 1, 1, dtype=self.ops.f32, device=self.cg.device)
+        xp[:, :x.shape[1], 0, 0] = x.to(device=xp.device, dtype=xp.dtype)
+        self.ops.nchw_to_nhwc(xp, self.cg)
 
     def forward(self, training=True):
         ops = self.ops
@@ -201,14 +250,20 @@ class GenRT:
                 ops.unpatchify(self.col, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
                 break
             bn = L.bn
-            if training:
+            if i == 0:
+                self.up0.forward(x, self.y[0])
+                if training:
+                    ops.col_stats(self.y[0], self.stats[0], 1)
+            elif training:
                 # conv + BN batch statistics in one kernel (reduced in the tcgen05 epilogue when the shape allows)
                 ops.conv_dgrad_stats(x, L.pd, self.y[i], self.stats[i], 1, L.k, L.s, L.p)
+            else:
+                ops.conv_dgrad(x, L.pd, None, self.y[i], L.k, L.s, L.p)
+            if training:
                 n = self.y[i].numel() // L.ci
                 ops.bn_finalize_act(self.stats[i], n, self.mr[i], bn.running_mean, bn.running_var,
                                     bn.num_batches_tracked, 1, self.y[i], bn.weight.data, bn.bias.data, self.a[i], ACT_RELU)
             else:
-                ops.conv_dgrad(x, L.pd, None, self.y[i], L.k, L.s, L.p)
                 ops.bn_eval_mr(bn.running_mean, bn.running_var, self.mr[i])
                 ops.bn_act(self.y[i], self.mr[i], bn.weight.data, bn.bias.data, self.a[i], 1, ACT_RELU)
             x = self.a[i]
@@ -236,9 +291,15 @@ class GenRT:
 
             def pgrad(i=i, L=L, bn=bn, x_in=x_in):
                 ops.bn_param_grad(self.sums[i], bn.weight.grad, bn.bias.grad)
-                ops.conv_wgrad(self.dy[i], x_in, L.conv.weight.grad, L.k, L.s, L.p)
+                if i == 0:
+                    self.up0.weight_grad(x_in, self.dy[0])
+                else:
+                    ops.conv_wgrad(self.dy[i], x_in, L.conv.weight.grad, L.k, L.s, L.p)
             _side_run(side, pgrad)
-            ops.conv_fprop(self.dy[i], L.pf, None, self.da[i - 1] if i > 0 else self.dcg, L.k, L.s, L.p)
+            if i == 0:
+                self.up0.input_grad(self.dy[0], self.dcg)
+            else:
+                ops.conv_fprop(self.dy[i], L.pf, None, self.da[i - 1], L.k, L.s, L.p)
         return self.dcg
 
 

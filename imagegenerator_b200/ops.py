@@ -76,7 +76,7 @@ _SIGS = {
     "sg_outer": [_P, _P, _P, _I, _I, _I, _P],
     "sg_wsum_rows": [_P, _P, _P, _I, _I, _I, _P],
     "sg_head_param_grads": [_P] * 10 + [_I, _I, _I, _P],
-    "sg_ca_reparam": [_P] * 6 + [_I, _I, _I, _I, _P],
+    "sg_ca_reparam": [_P] * 6 + [_I, _I, _I, _I, _I, _P],
     "sg_ca_bwd_seed": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
     "sg_interp": [_P, _P, _P, _P, _I, _L, _I, _P],
     "sg_sample_sqnorm": [_P, _P, _I, _L, _I, _P],
@@ -88,7 +88,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
-                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported"])
+                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace"])
 
 
 def load_library(path=LIB_PATH):
@@ -110,6 +110,8 @@ def load_library(path=LIB_PATH):
     lib.sg_conv_wgrad_cl_supported.restype = _I
     lib.sg_set_option.argtypes = [_c.c_char_p, _I]
     lib.sg_set_option.restype = _I
+    lib.sg_debug_conv_trace.argtypes = [_P]
+    lib.sg_debug_conv_trace.restype = _I
     lib.sg_version.restype = _I
     lib.sg_last_error.restype = _c.c_char_p
     lib.sg_check_device.restype = _I
@@ -155,6 +157,10 @@ class CudaOps:
 
     def launch_count(self):
         return int(self.lib.sg_launch_count())
+
+    def conv_trace(self, buf):
+        """Profiling hook: ``buf`` = int64 CUDA tensor of >= 296*16 elements receiving %globaltimer stamps, or None."""
+        self._ck(self.lib.sg_debug_conv_trace(_ptr(buf)))
 
     def empty(self, shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.act_dtype, device=self.device)
@@ -468,10 +474,12 @@ class CudaOps:
 
     # ---- conditioning augmentation
     def ca_reparam(self, mu, sigma, eps, z, c_hat, cg):
+        """c_hat = mu + sigma*eps; cg rows = [c_hat, z, zero padding up to cg's row length]."""
         self._c(mu, sigma, eps, z, c_hat, cg)
         N, C = mu.shape
-        nz = (cg.numel() // N - C) if cg is not None else 0
-        self._ck(self.lib.sg_ca_reparam(_ptr(mu), _ptr(sigma), _ptr(eps), _ptr(z), _ptr(c_hat), _ptr(cg), N, C, nz,
+        ld = cg.numel() // N if cg is not None else C
+        nz = z.shape[1] if (z is not None and cg is not None) else 0
+        self._ck(self.lib.sg_ca_reparam(_ptr(mu), _ptr(sigma), _ptr(eps), _ptr(z), _ptr(c_hat), _ptr(cg), N, C, nz, ld,
                                         self._dt_of(cg) if cg is not None else SG_F32, self._st()))
 
     def ca_bwd_seed(self, dcg, eps, mu, sigma, kl_scale, dmu, dsigma):

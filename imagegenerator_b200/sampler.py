@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import torch
 
-from .engine import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, CART, GenRT, Z_DIM, default_ops
+from .engine import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, CART, GenRT, Up0Gemm, Z_DIM, default_ops
 
 
 class _Folded:
@@ -68,10 +68,16 @@ class StackGANSampler:
                     if buf is not None:
                         mod._buffers[name] = buf.to(device=ops.device, dtype=f32 if buf.is_floating_point() else buf.dtype)
         # ---- Stage-I generator (generator_1.py:38-40), always eval here (stage_2_train_fn.py:59-63)
-        self.g1 = [_Folded(ops, c, bn, "d") for c, bn in gen_1.conv_layers()]
-        self.cg = ops.empty((B, 1, 1, self.g1[0].co))
-        self.a1, h = [], 1
-        for L in self.g1[:-1]:
+        cl1 = gen_1.conv_layers()
+        # first layer: the GEMM of engine.Up0Gemm over the zero-padded [c_hat, z] rows + eval-mode BN as its own small pass
+        # (its BN cannot be folded into per-output-column weights without a second transposed pack; the tensor is 4x4x192)
+        self.up0, self.bn0 = Up0Gemm(ops, cl1[0][0], B), cl1[0][1]
+        self.g1 = [None] + [_Folded(ops, c, bn, "d") for c, bn in cl1[1:]]
+        self.cg = ops.zeros((B, 1, 1, self.up0.Kp))
+        self.y0 = ops.empty((B, self.up0.k, self.up0.k, self.up0.ci))
+        self.mr0 = ops.empty((1, self.up0.ci, 2), f32)
+        self.a1, h = [ops.empty((B, self.up0.k, self.up0.k, self.up0.ci))], self.up0.k
+        for L in self.g1[1:-1]:
             h = (h - 1) * L.s - 2 * L.p + L.k
             self.a1.append(ops.empty((B, h, h, L.ci)))
         L = self.g1[-1]
@@ -110,7 +116,8 @@ class StackGANSampler:
     def refresh_weights(self):
         """Re-pack after the parameters / running statistics changed (e.g. a checkpoint was loaded)."""
         ops = self.ops
-        for L in self.g1:
+        self.up0.pack()
+        for L in self.g1[1:]:
             L.refresh(ops)
         if self.bn_batch_stats:
             self.g2rt.refresh_weights()
@@ -127,8 +134,12 @@ class StackGANSampler:
     def _body(self):
         ops = self.ops
         self.ca1.forward(self.s_tem, self.s_e1, self.s_z, cg=self.cg)                 # :184-189
-        x = self.cg
-        for L, a in zip(self.g1[:-1], self.a1):                                       # :190 gen_1 (eval)
+        bn0 = self.bn0                                                                 # :190 gen_1 (eval)
+        self.up0.forward(self.cg, self.y0)
+        ops.bn_eval_mr(bn0.running_mean, bn0.running_var, self.mr0)
+        ops.bn_act(self.y0, self.mr0, bn0.weight.data, bn0.bias.data, self.a1[0], 1, ACT_RELU)
+        x = self.a1[0]
+        for L, a in zip(self.g1[1:-1], self.a1[1:]):
             L.run(ops, x, a, ACT_RELU)
             x = a
         L = self.g1[-1]

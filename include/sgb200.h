@@ -246,9 +246,10 @@ int sg_head_param_grads(const float* dA, const float* dBv, const float* dc0, con
                         int K, int Cx, int Nd, void* stream);
 
 /* ---- conditioning augmentation (con_augment.py:18-22; stage_1_train_fn.py:120-122,156-159) ---- */
-/* c_hat = mu + sigma*eps; cg[N][C+nz] (T) = [c_hat, z] when cg != NULL (z may be NULL) */
+/* c_hat = mu + sigma*eps; cg[N][ld] (T) = [c_hat, z, 0...] when cg != NULL (z may be NULL; ld >= C+nz, the columns past
+   C+nz are zero padding so that the generator's first layer sees a K that is a multiple of 64) */
 int sg_ca_reparam(const float* mu, const float* sigma, const float* eps, const float* z, float* c_hat,
-                  void* cg, int N, int C, int nz, int dtype, void* stream);
+                  void* cg, int N, int C, int nz, int ld, int dtype, void* stream);
 /* dmu = dc + kl*(-2mu); dsigma = dc*eps + kl*(2/sigma-2sigma); dc = first C of each dcg row (ld = row length) */
 int sg_ca_bwd_seed(const void* dcg, const float* eps, const float* mu, const float* sigma, float kl_scale,
                    float* dmu, float* dsigma, int N, int C, int ld, int dtype, void* stream);
@@ -264,8 +265,14 @@ int sg_gen_loss(const float* s_fake, const float* mu, const float* sigma, float*
 int sg_scale_rows_add(const void* x, const float* scale, void* out, int accumulate, int N, int64_t per_sample, int dtype, void* stream);
 
 /* ---- Adam (train.py:92-102; torch.optim.Adam semantics, bias-corrected, eps outside sqrt/bc2) -- */
-/* hyper (device) = [lr, beta1, beta2, eps, step]; the kernel increments step first */
+/* hyper (device, 8 floats) = [lr, beta1, beta2, eps, step, step_lo, step_hi, -]; the kernel increments step first
+   (step as a float for the bias correction; the exact count is step_hi * 2^23 + step_lo) */
 int sg_adam_step(float* p, const float* g, float* m, float* v, float* hyper, int64_t n, void* stream);
+
+/* ---- profiling hook -------------------------------------------------------------------------- */
+/* While buf (device, >= 296*16 uint64) is set, every persistent conv launch writes 16 %globaltimer stamps per CTA into
+   it; NULL switches the hook off (tools/exp_conv_trace.py). */
+int sg_debug_conv_trace(void* buf);
 
 #ifdef __cplusplus
 }

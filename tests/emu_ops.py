@@ -361,9 +361,12 @@ class EmuOps:
         c_hat.copy_(c.to(c_hat.dtype))
         if cg is not None:
             n = c.shape[0]
-            cg.reshape(n, -1)[:, :c.shape[1]] = c.to(cg.dtype)
+            row = cg.reshape(n, -1)
+            row[:, :c.shape[1]] = c.to(cg.dtype)
+            nz = z.shape[1] if z is not None else 0
             if z is not None:
-                cg.reshape(n, -1)[:, c.shape[1]:] = z.to(cg.dtype)
+                row[:, c.shape[1]:c.shape[1] + nz] = z.to(cg.dtype)
+            row[:, c.shape[1] + nz:] = 0          # zero padding up to the row length
 
     def ca_bwd_seed(self, dcg, eps, mu, sigma, kl_scale, dmu, dsigma):
         """dmu = dc + kl_scale*(-2 mu); dsigma = dc*eps + kl_scale*(2/sigma - 2 sigma);

@@ -279,7 +279,7 @@ def test_adam_matches_torch():
     ref = p.clone().requires_grad_(True)
     opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999))
     m, v = torch.zeros_like(p), torch.zeros_like(p)
-    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0], device="cuda")
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0, 0.0, 0.0, 0.0], device="cuda")
     for step in range(5):
         g = torch.randn(n, device="cuda") * (0.1 ** step)
         ref.grad = g.clone()
