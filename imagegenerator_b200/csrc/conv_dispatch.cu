@@ -1,5 +1,7 @@
-// conv_dispatch.cu -- public convolution entry points: route each call to the tcgen05 kernels
-// (bf16, tensor-core-shaped layers) or to the CUDA-core implicit GEMM (fp32 mode, thin layers).
+// conv_dispatch.cu -- public convolution entry points.  bf16 storage = the tcgen05 kernels, and ONLY those: a shape they
+// cannot take is an error (SG_ERR_UNSUPPORTED), not a silent switch to the CUDA-core kernels -- a second backend hides
+// 10-50x performance cliffs (round 1: the generator's 228-channel first layer ran on FFMA unnoticed).  fp32 storage = the
+// CUDA-core implicit GEMM of conv_ffma.cu, the validation mode.  The sg_conv_*_ffma entry points stay callable by name.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -29,31 +31,36 @@ int sg_conv_fprop_tc_res(const void*, const void*, const float*, const void*, vo
                          int, int, void*);
 int sg_add_act(const void*, const void*, void*, int64_t, int, int, void*);
 
-static bool tc_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SG_DISABLE_TC");
-        v = (e && e[0] == '1') ? 0 : 1;
-    }
-    return v == 1;
+static int unsupported(const char* what, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p) {
+    sg::set_error("%s: the tensor-core kernels cannot take N=%d %dx%dx%d -> %dx%dx%d k%d s%d p%d in bf16 mode (reduction channels must "
+                  "be a multiple of 8, grids powers of two); there is no CUDA-core fallback in bf16 mode -- pad the operand "
+                  "(engine.Up0Gemm), go through a patch matrix (sg_patchify), or call the _ffma entry point explicitly",
+                  what, N, H, W, Ci, Ho, Wo, Co, k, s, p);
+    return SG_ERR_UNSUPPORTED;
 }
 
 int sg_conv_fprop(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho, int Wo,
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
-    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+    if (dtype == SG_BF16) {
+        if (!sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_fprop", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_fprop_tc(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
+    }
     return sg_conv_fprop_ffma(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
 }
 int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int H, int W, int Ci, int Ho, int Wo,
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
-    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+    if (dtype == SG_BF16) {
+        if (!sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_dgrad", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_dgrad_tc(dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
+    }
     return sg_conv_dgrad_ffma(dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
 }
 int sg_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
                   int s, int p, int dtype, void* stream) {
-    if (dtype == SG_BF16 && tc_enabled() && sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p))
+    if (dtype == SG_BF16) {
+        if (!sg_conv_wgrad_tc_supported(N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_wgrad", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_wgrad_tc(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
+    }
     return sg_conv_wgrad_ffma(x, dy, dw, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
 }
 
@@ -62,7 +69,7 @@ int sg_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,
 // tensor-core epilogue when the shape allows, otherwise conv + sg_col_stats.
 int sg_conv_fprop_stats(const void* x, const void* pf, void* y, double* stats, int groups, int N, int H, int W, int Ci,
                         int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
-    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+    if (dtype == SG_BF16 && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
         return sg_conv_fprop_tc_stats(x, pf, y, stats, groups, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
     int e = sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;
@@ -70,7 +77,7 @@ int sg_conv_fprop_stats(const void* x, const void* pf, void* y, double* stats, i
 }
 int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats, int groups, int N, int H, int W, int Ci,
                         int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
-    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+    if (dtype == SG_BF16 && sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
         return sg_conv_dgrad_tc_stats(dy, pd, dx, stats, groups, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
     int e = sg_conv_dgrad(dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;
@@ -82,7 +89,7 @@ int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats,
 int sg_conv_fprop_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k,
                          int s, int p, int dtype, void* stream) {
     if (dtype == SG_F32) return sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
-    if (tc_enabled() && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+    if (sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
         return sg_conv_fprop_tc_f32out(x, pf, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
     sg::set_error("conv_fprop_f32out: shape not eligible for the tensor-core kernel (Ci %% 8 != 0?)");
     return SG_ERR_UNSUPPORTED;
@@ -91,7 +98,7 @@ int sg_conv_fprop_f32out(const void* x, const void* pf, float* y, int N, int H, 
 // y = act(conv(x, W) + bias + residual).  Tensor-core shapes: fused in the epilogue; otherwise conv then sg_add_act.
 int sg_conv_fprop_res(const void* x, const void* pf, const float* bias, const void* residual, void* y, int N, int H, int W,
                       int Ci, int Ho, int Wo, int Co, int k, int s, int p, int act, int dtype, void* stream) {
-    if (dtype == SG_BF16 && tc_enabled() && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+    if (dtype == SG_BF16 && sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
         return sg_conv_fprop_tc_res(x, pf, bias, residual, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, stream);
     int e = sg_conv_fprop(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;

@@ -856,6 +856,13 @@ __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t*
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_mc_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3,
+                                                   uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
@@ -907,8 +914,12 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     const uint32_t rank = MC ? cluster_ctarank() : 0u;
     const bool has_rows = co0 < P.Co;                // false only for the padding CTA of an odd co-tile count (MC)
 
+    // FIVE warps feed a stage: warp 0 the two dy blocks, warps 2-5 (the epilogue warps, idle during the mainloop) two x units
+    // each.  One thread issuing all ten TMA loads of a k-block was the critical path of this kernel (its instruction stream
+    // took longer than the k-block's MMAs); every feeding warp waits for the stage itself and posts its own expect_tx.
+    constexpr int FEEDERS = 5;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], MC ? 2 : 1); }
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], FEEDERS); mbar_init(&empty_bar[i], MC ? 2 : 1); }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -923,35 +934,46 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     const uint32_t tmem_base = tmem_slot;
 
     if (nkb > 0) {
-        if (warp == 0) {
-            // producer warp: lane 0 owns the barriers, lanes 0..nun-1 each issue the TMA load of one unit and lanes
-            // nun, nun+1 the two dy blocks -- ten loads per stage leave in parallel instead of one after another
-            int uc = 0, ukh = 0, ukw = 0;
-            if (lane < nun) {
-                const int u = u0 + lane, cib = u / P.kk, tap = u - cib * P.kk;
-                uc = cib * 64; ukh = tap / P.k; ukw = tap - ukh * P.k;
-            }
+        if (warp != 1) {
+            // ---- feeding warps (converged; the TMA issue is done by one elected lane)
+            const int fw = warp == 0 ? -1 : warp - 2;          // -1: dy; 0..3: x units 2*fw, 2*fw + 1
+            const int ua = fw < 0 ? 0 : 2 * fw, ub = ua + 1;
+            const bool has_a = fw >= 0 && ua < nun, has_b = fw >= 0 && ub < nun;
+            int ca = 0, ha = 0, wa = 0, cb2 = 0, hb = 0, wb = 0;
+            if (has_a) { const int u = u0 + ua, cib = u / P.kk, tap = u - cib * P.kk; ca = cib * 64; ha = tap / P.k; wa = tap - ha * P.k; ha -= P.p; wa -= P.p; }
+            if (has_b) { const int u = u0 + ub, cib = u / P.kk, tap = u - cib * P.kk; cb2 = cib * 64; hb = tap / P.k; wb = tap - hb * P.k; hb -= P.p; wb -= P.p; }
+            // bytes this warp's loads put into a stage (multicast: the peer CTA delivers the units of the other parity)
+            const uint32_t my_tx = fw < 0 ? (has_rows ? (uint32_t)A_BYTES : 0u) : (uint32_t)(((has_a ? 1 : 0) + (has_b ? 1 : 0)) * B_BYTES);
+            const bool issue_a = has_a && (!MC || (ua & 1) == (int)rank), issue_b = has_b && (!MC || (ub & 1) == (int)rank);
+            const uint32_t ring = smem_u32(smem);
             int st = 0;
             uint32_t par = 1;
             int pix0 = kb0 * PIX;
             int ow0 = pix0 % P.Wo, oh0 = (pix0 / P.Wo) % P.Ho, n0 = pix0 / (P.Wo * P.Ho);
             for (int i = 0; i < nkb; ++i) {
-                if (lane == 0) {
-                    mbar_wait(&empty_bar[st], par);
-                    mbar_expect_tx(&full_bar[st], (uint32_t)((has_rows ? A_BYTES : 0) + nun * B_BYTES));
+                mbar_wait(&empty_bar[st], par);
+                if (elect_one()) {
+                    const uint32_t fb = smem_u32(&full_bar[st]);
+                    const uint32_t sa = ring + (uint32_t)st * (uint32_t)stage_bytes;
+                    mbar_expect_tx_u32(fb, my_tx);
+                    if (fw < 0) {
+                        if (has_rows) {
+                            tma_load_2d_u32(&tmDy, fb, sa, co0, pix0);
+                            tma_load_2d_u32(&tmDy, fb, sa + PIX * 128, co0 + 64, pix0);
+                        }
+                    } else {
+                        const int w0 = ow0 * P.s, h0 = oh0 * P.s;
+                        if (issue_a) {
+                            if (!MC) tma_load_4d_u32(&tmX, fb, sa + A_BYTES + ua * B_BYTES, ca, w0 + wa, h0 + ha, n0);
+                            else tma_load_4d_mc_u32(&tmX, fb, sa + A_BYTES + ua * B_BYTES, ca, w0 + wa, h0 + ha, n0, (uint16_t)3);
+                        }
+                        if (issue_b) {
+                            if (!MC) tma_load_4d_u32(&tmX, fb, sa + A_BYTES + ub * B_BYTES, cb2, w0 + wb, h0 + hb, n0);
+                            else tma_load_4d_mc_u32(&tmX, fb, sa + A_BYTES + ub * B_BYTES, cb2, w0 + wb, h0 + hb, n0, (uint16_t)3);
+                        }
+                    }
                 }
                 __syncwarp();
-                uint8_t* sa = smem + (size_t)st * stage_bytes;
-                if (lane < nun) {
-                    if (!MC)
-                        tma_load_4d(&tmX, &full_bar[st], sa + A_BYTES + lane * B_BYTES, uc, ow0 * P.s - P.p + ukw,
-                                    oh0 * P.s - P.p + ukh, n0);
-                    else if ((lane & 1) == (int)rank)            // every second unit, delivered to both CTAs
-                        tma_load_4d_mc(&tmX, &full_bar[st], sa + A_BYTES + lane * B_BYTES, uc, ow0 * P.s - P.p + ukw,
-                                       oh0 * P.s - P.p + ukh, n0, (uint16_t)3);
-                } else if (lane < nun + 2 && has_rows) {
-                    tma_load_2d(&tmDy, &full_bar[st], sa + (lane - nun) * (PIX * 128), co0 + (lane - nun) * 64, pix0);
-                }
                 if (++st == P.stages) { st = 0; par ^= 1; }
                 // advance the pixel block (blocks never straddle images: Ho*Wo % PIX == 0 or PIX % (Ho*Wo) == 0)
                 pix0 += PIX;
@@ -962,46 +984,56 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
                     if (oh0 >= P.Ho) { const int imgs = oh0 / P.Ho; oh0 -= imgs * P.Ho; n0 += imgs; }
                 }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {
-                // D=f32, A=B=bf16, both MN-major, M=128; up to FOUR units (N = 256) per instruction: the unit tiles lie
-                // B_BYTES apart in shared memory, which is exactly the descriptor's stride between 64-element blocks
-                // along N, so the 128 x 16 slab of dy is read from shared memory twice per k-step instead of 8 times
-                // (an N=64 MMA re-reads 4 KB of A for 2 KB of B and is shared-memory bound)
-                const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
-                const int n_lo = nun < 4 ? nun : 4, n_hi = nun - n_lo;
-                const uint32_t idesc_lo = idesc0 | ((uint32_t)((n_lo * 64) >> 3) << 17);
-                const uint32_t idesc_hi = idesc0 | ((uint32_t)((n_hi * 64) >> 3) << 17);
-                int st = 0;
-                uint32_t par = 0;
-                for (int i = 0; i < nkb; ++i) {
-                    mbar_wait(&full_bar[st], par);
-                    tc_fence_after();
-                    if (MC && !has_rows) {
-                        // padding CTA: nothing to multiply, but both CTAs must release the stage
+        } else {
+            // ---- MMA warp (converged; issue by one elected lane)
+            // D=f32, A=B=bf16, both MN-major, M=128; up to FOUR units (N = 256) per instruction: the unit tiles lie
+            // B_BYTES apart in shared memory, which is exactly the descriptor's stride between 64-element blocks
+            // along N, so the 128 x 16 slab of dy is read from shared memory twice per k-step instead of 8 times
+            // (an N=64 MMA re-reads 4 KB of A for 2 KB of B and is shared-memory bound)
+            const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
+            const int n_lo = nun < 4 ? nun : 4, n_hi = nun - n_lo;
+            const uint32_t idesc_lo = idesc0 | ((uint32_t)((n_lo * 64) >> 3) << 17);
+            const uint32_t idesc_hi = idesc0 | ((uint32_t)((n_hi * 64) >> 3) << 17);
+            // MN-major 128B-swizzled descriptors (make_mnmajor_sw128_desc): only the 14-bit start address in the low word
+            // changes from MMA to MMA -- everything per instruction is an add on that word
+            constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t LBO16 = (uint32_t)((PIX * 128) >> 4) << 16;          // stride between 64-element blocks along M/N
+            const uint32_t dlo_ring = ((base >> 4) & 0x3FFFu) | LBO16;
+            const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+            auto mma = [&](uint32_t tacc, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+                tc_mma_bf16(tacc, ((uint64_t)DESC_HI << 32) | alo, ((uint64_t)DESC_HI << 32) | blo, idesc, acc);
+            };
+            int st = 0;
+            uint32_t par = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&full_bar[st], par);
+                if (MC && !has_rows) {
+                    // padding CTA: nothing to multiply, but both CTAs must release the stage
+                    if (elect_one()) {
                         mbar_arrive_cta(&empty_bar[st], 0);
                         mbar_arrive_cta(&empty_bar[st], 1);
-                        if (++st == P.stages) { st = 0; par ^= 1; }
-                        continue;
                     }
-                    const uint32_t sa = base + (uint32_t)st * stage_bytes;
-                    const uint32_t sb = sa + A_BYTES;
+                    __syncwarp();
+                    if (++st == P.stages) { st = 0; par ^= 1; }
+                    continue;
+                }
+                const uint32_t a0 = dlo_ring + (uint32_t)st * stage16, b0 = a0 + (uint32_t)(A_BYTES >> 4), b1 = b0 + (uint32_t)((4 * B_BYTES) >> 4);
+                if (elect_one()) {
 #pragma unroll
                     for (int k16 = 0; k16 < PIX / 16; ++k16) {
-                        const uint64_t ad = make_mnmajor_sw128_desc(sa + k16 * 2048, PIX * 128);
-                        const uint64_t b0 = make_mnmajor_sw128_desc(sb + k16 * 2048, B_BYTES);
-                        tc_mma_bf16(tmem_base, ad, b0, idesc_lo, (i | k16) != 0 ? 1u : 0u);
-                        if (n_hi > 0) {
-                            const uint64_t b1 = make_mnmajor_sw128_desc(sb + 4 * B_BYTES + k16 * 2048, B_BYTES);
-                            tc_mma_bf16(tmem_base + 256, ad, b1, idesc_hi, (i | k16) != 0 ? 1u : 0u);
-                        }
+                        const uint32_t acc = (i | k16) != 0 ? 1u : 0u;
+                        mma(tmem_base, a0 + k16 * 128, b0 + k16 * 128, idesc_lo, acc);
+                        if (n_hi > 0) mma(tmem_base + 256, a0 + k16 * 128, b1 + k16 * 128, idesc_hi, acc);
                     }
                     if (MC) tc_commit_mc(&empty_bar[st], (uint16_t)3); else tc_commit(&empty_bar[st]);
-                    if (++st == P.stages) { st = 0; par ^= 1; }
                 }
-                if (!MC || has_rows) tc_commit(&accum_bar);
+                __syncwarp();
+                if (++st == P.stages) { st = 0; par ^= 1; }
             }
-        } else if (!MC || has_rows) {
+            if ((!MC || has_rows) && elect_one()) tc_commit(&accum_bar);
+            __syncwarp();
+        }
+        if (warp >= 2 && (!MC || has_rows)) {
             const int q = warp & 3;
             const int co = co0 + q * 32 + lane;
             mbar_wait(&accum_bar, 0);

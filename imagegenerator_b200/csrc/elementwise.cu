@@ -432,6 +432,25 @@ __global__ void nhwc_to_nchw_kernel(const T* src, float* dst, int N, int C, int6
         for (int c = 0; c < C; ++c) d[(int64_t)c * HW] = ldf(s + c);
     }
 }
+// w[co][ci][t] (fp32 master) -> wt[(t, ci)][Kp] in the storage type, columns co >= Co zero: the forward operand of a
+// ConvTranspose2d on a 1x1 input run as a GEMM (engine.Up0Gemm).  Block = one ci; a thread owns one co, reads its kk <= 16
+// contiguous taps and stores them kk rows apart -- consecutive threads write consecutive columns.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_gemm_t_kernel(const float* __restrict__ w, T* __restrict__ wt, int Co, int Ci, int kk,
+                                                          int Kp) {
+    const int ci = blockIdx.x;
+    for (int co = threadIdx.x; co < Kp; co += blockDim.x) {
+        float v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = 0.f;
+        if (co < Co) {
+            const float* src = w + ((int64_t)co * Ci + ci) * kk;
+            for (int t = 0; t < kk; ++t) v[t] = src[t];
+        }
+        for (int t = 0; t < kk; ++t) stf(wt + ((int64_t)t * Ci + ci) * Kp + co, v[t]);
+    }
+}
+
 // w[co][ci][t] (fp32 master) -> pf[co][t][ci] and pd[ci][t][co] in the storage type.  A thread owns one (co, ci) pair
 // and reads its kk contiguous taps; blockIdx.y = 0 runs with ci fastest across threads (pf stores coalesced), = 1 with
 // co fastest (pd stores coalesced) -- element-order stores were 2-byte scatters at stride Ci / Co (32 us for the 2 M
@@ -853,6 +872,12 @@ int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int
     SG_DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for((int64_t)N * HW, 256), 256, 0, SG_STREAM(stream)>>>(
                              src, (T*)dst, N, C, HW)));
     SG_LAUNCHED("nchw_to_nhwc");
+    return 0;
+}
+int sg_pack_gemm_t(const float* w, void* wt, int Co, int Ci, int kk, int Kp, int dtype, void* stream) {
+    SG_REQUIRE(kk >= 1 && kk <= 16 && Kp >= Co, "pack_gemm_t: kk %d (<= 16), Kp %d >= Co %d", kk, Kp, Co);
+    SG_DISPATCH_T(dtype, (pack_gemm_t_kernel<T><<<Ci, 256, 0, SG_STREAM(stream)>>>(w, (T*)wt, Co, Ci, kk, Kp)));
+    SG_LAUNCHED("pack_gemm_t");
     return 0;
 }
 int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int dtype, void* stream) {

@@ -115,17 +115,14 @@ class Up0Gemm:
         self.co, self.ci, self.k = w.shape[0], w.shape[1], w.shape[2]
         self.Kp = (self.co + 63) // 64 * 64
         self.NO = self.ci * self.k * self.k
-        f32 = ops.f32
-        self.w_cl32 = ops.zeros((self.Kp, self.k, self.k, self.ci), f32)      # [co][h][w][ci], rows >= co stay zero
         self.wf = ops.empty((self.NO, 1, 1, self.Kp))
-        self.wb = ops.zeros((self.Kp, 1, 1, self.NO))
-        self.gw = ops.zeros((self.Kp, self.NO, 1, 1), f32)
+        self.wb = ops.zeros((self.Kp, 1, 1, self.NO))                          # rows >= co stay zero
+        self.gw = ops.zeros((self.Kp, self.NO, 1, 1), ops.f32)
 
     def pack(self):
         ops, W = self.ops, self.conv.weight.data
-        ops.nchw_to_nhwc(W, self.w_cl32[:self.co])                                             # fp32 [co][h][w][ci]
-        ops.nchw_to_nhwc(self.w_cl32.view(1, self.Kp, self.NO, 1), self.wf.view(1, self.NO, 1, self.Kp))   # transpose
-        ops.nchw_to_nhwc(W, self.wb.view(self.Kp, self.k, self.k, self.ci)[:self.co])
+        ops.pack_gemm_t(W, self.wf)                                                            # [(h,w,ci)][Kp]
+        ops.pack_weight(W, self.wb.view(self.Kp, self.k, self.k, self.ci)[:self.co], None)      # [co][(h,w,ci)]
 
     def forward(self, cg, y):
         self.ops.conv_fprop(cg, self.wf, None, y.view(y.shape[0], 1, 1, self.NO), 1, 1, 0)
@@ -223,13 +220,19 @@ class GenRT:
                 self.out = out if out is not None else ops.empty(shp)
                 self.dpre = ops.empty(shp)
                 hin = (h + 2 * L.p - L.k) // L.s + 1
-                self.col = ops.empty((B, hin, hin, L.ci * L.k * L.k), ops.f32)
+                self.K_last = L.ci * L.k * L.k
+                self.col = ops.empty((B, hin, hin, self.K_last), ops.f32)
+                # backward of the 3-channel layer: 1x1 GEMMs over the patch matrix of d/d(pre-tanh) (like Gen2RT's up3)
+                self.Pd = ops.empty((B, hin, hin, self.K_last))
+                self.pf_last = ops.empty((L.co, 1, 1, self.K_last))
         self.packed = False
 
     def refresh_weights(self):
         self.up0.pack()
         for L in self.layers[1:]:
             L.pack(self.ops)
+        last = self.layers[-1]
+        self.ops.pack_weight(last.conv.weight.data.view(last.co, self.K_last, 1, 1), self.pf_last, None)
         self.packed = True
 
     def set_input(self, x):
@@ -275,12 +278,13 @@ class GenRT:
         ops = self.ops
         last = self.layers[-1]
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
+        ops.patchify(self.dpre, self.Pd, last.k, last.s, last.p)
 
         def pgrad_last():
             ops.colsum(self.dpre, last.conv.bias.grad)
-            ops.conv_wgrad(self.dpre, self.a[-1], last.conv.weight.grad, last.k, last.s, last.p)
+            ops.conv_wgrad(self.Pd, self.a[-1], last.conv.weight.grad.view(last.co, self.K_last, 1, 1), 1, 1, 0)
         _side_run(side, pgrad_last)
-        ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
+        ops.conv_fprop(self.Pd, self.pf_last, None, self.da[-1], 1, 1, 0)
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
             ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,

@@ -28,6 +28,7 @@ _SIGS = {
     "sg_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "sg_pack_gemm_t": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_patchify": [_P, _P] + [_I] * 10 + [_P],
     "sg_bn_fold": [_P, _P, _P, _P, _F, _P, _P, _I, _P],
     "sg_pack_weight_scaled": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
@@ -214,6 +215,14 @@ class CudaOps:
         Co, Ci, k, _ = w.shape
         ref = pf if pf is not None else pd
         self._ck(self.lib.sg_pack_weight(_ptr(w), _ptr(pf), _ptr(pd), Co, Ci, k * k, self._dt_of(ref), self._st()))
+
+    def pack_gemm_t(self, w, wt):
+        """wt[(t, ci)][Kp] = w[co][ci][t] (columns co >= Co zero)."""
+        self._c(w, wt)
+        Co, Ci, k, _ = w.shape
+        Kp = wt.shape[-1]
+        assert wt.numel() == Ci * k * k * Kp
+        self._ck(self.lib.sg_pack_gemm_t(_ptr(w), _ptr(wt), Co, Ci, k * k, Kp, self._dt_of(wt), self._st()))
 
     def bn_fold(self, running_mean, running_var, gamma, beta, scale, shift, eps=1e-5):
         self._c(running_mean, running_var, gamma, beta, scale, shift)

@@ -69,6 +69,9 @@ int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int
 int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int dtype, void* stream);
 /* w [Co][Ci][k*k] fp32 -> pf [Co][k*k][Ci] and pd [Ci][k*k][Co] in T (either may be NULL) */
 int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream);
+/* wt[(t, ci)][Kp] (T) = w[co][ci][t], columns co >= Co zero: forward operand of ConvTranspose2d(Co -> Ci, k, s1, p0) on a 1x1
+   input run as the GEMM [B, Kp] x [Kp, kk*Ci] (generator_1.py:9-13; imagegenerator_b200.engine.Up0Gemm) */
+int sg_pack_gemm_t(const float* w, void* wt, int Co, int Ci, int kk, int Kp, int dtype, void* stream);
 
 /* P[n,oh,ow, ci*k*k + kh*k + kw] = x[n, oh*s-p+kh, ow*s-p+kw, ci] (0 outside): patch matrix of a thin
  * (3-channel) image in the PyTorch weight order, so that discrminator_1.py:10 / discriminator_2.py:9 run as

@@ -81,6 +81,14 @@ class EmuOps:
         if pd is not None:
             pd.copy_(w.permute(1, 2, 3, 0).to(pd.dtype))
 
+    def pack_gemm_t(self, w, wt):
+        """wt[(t, ci)][Kp] = w[co][ci][t], columns co >= Co zero."""
+        Co, Ci, k, _ = w.shape
+        Kp = wt.shape[-1]
+        out = torch.zeros(k * k * Ci, Kp, dtype=wt.dtype, device=wt.device)
+        out[:, :Co] = w.reshape(Co, Ci, k * k).permute(2, 1, 0).reshape(k * k * Ci, Co).to(wt.dtype)
+        wt.copy_(out.reshape(wt.shape))
+
     def bn_fold(self, running_mean, running_var, gamma, beta, scale, shift, eps=1e-5):
         sc = gamma.double() / torch.sqrt(running_var.double() + eps)
         scale.copy_(sc.to(scale.dtype))

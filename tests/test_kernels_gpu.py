@@ -82,6 +82,38 @@ CONV_CASES = [
 ]
 
 
+def _impl_for(mode, direction, case):
+    """bf16 mode has ONE backend: shapes the tcgen05 kernels cannot take are an error at the dispatcher (checked by
+    test_bf16_dispatch_refuses_unsupported_shapes), and the CUDA-core kernels are only reachable by their own entry points --
+    which is how their bf16-storage instantiation stays covered here."""
+    if mode != "bf16":
+        return ""
+    from imagegenerator_b200.ops import CudaOps
+    N, H, Ci, Co, k, s, p = case
+    Ho = (H + 2 * p - k) // s + 1
+    lib = CudaOps("bf16").lib
+    ok = (lib.sg_conv_wgrad_tc_supported(N, H, H, Ci, Ho, Ho, Co, k, s, p) if direction == 2
+          else lib.sg_conv_tc_supported(direction, N, H, H, Ci, Ho, Ho, Co, k, s, p))
+    return "" if ok else "_ffma"
+
+
+def test_bf16_dispatch_refuses_unsupported_shapes():
+    from imagegenerator_b200.ops import CudaOps
+    ops = CudaOps("bf16")
+    x = torch.zeros(2, 8, 8, 3, device="cuda", dtype=torch.bfloat16)          # 3 input channels: not a TMA shape
+    pf = torch.zeros(16, 4, 4, 3, device="cuda", dtype=torch.bfloat16)
+    y = torch.zeros(2, 4, 4, 16, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CUDA-core fallback in bf16 mode"):
+        ops.conv_fprop(x, pf, None, y, 4, 2, 1)
+    with pytest.raises(RuntimeError, match="no CUDA-core fallback in bf16 mode"):
+        ops.conv_wgrad(x, y, torch.zeros(16, 3, 4, 4, device="cuda"), 4, 2, 1)
+    pd = torch.zeros(3, 4, 4, 16, device="cuda", dtype=torch.bfloat16)
+    dy228 = torch.zeros(2, 1, 1, 228, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CUDA-core fallback in bf16 mode"):
+        ops.conv_dgrad(dy228, torch.zeros(192, 4, 4, 228, device="cuda", dtype=torch.bfloat16), None,
+                       torch.zeros(2, 4, 4, 192, device="cuda", dtype=torch.bfloat16), 4, 1, 0)
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True), (ACT_TANH, True)])
@@ -91,7 +123,8 @@ def test_conv_fprop(mode, case, act, use_bias):
     x, w = rnd(N, H, H, Ci), rnd(Co, Ci, k, k, scale=(Ci * k * k) ** -0.5)
     pf = w.permute(0, 2, 3, 1).contiguous()
     bias = F(rnd(Co)) if use_bias else None
-    run_pair(mode, "conv_fprop", [T(x), T(pf), bias, T(torch.zeros(N, Ho, Ho, Co)), k, s, p], [3], dict(act=act))
+    run_pair(mode, "conv_fprop", [T(x), T(pf), bias, T(torch.zeros(N, Ho, Ho, Co)), k, s, p], [3],
+             dict(act=act, impl=_impl_for(mode, 0, case)))
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -103,7 +136,8 @@ def test_conv_dgrad(mode, case, act, use_bias):
     dy, w = rnd(N, Ho, Ho, Co), rnd(Co, Ci, k, k, scale=(Co * k * k / (s * s)) ** -0.5)
     pd = w.permute(1, 2, 3, 0).contiguous()
     bias = F(rnd(Ci)) if use_bias else None
-    run_pair(mode, "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci)), k, s, p], [3], dict(act=act))
+    run_pair(mode, "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci)), k, s, p], [3],
+             dict(act=act, impl=_impl_for(mode, 1, case)))
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -113,7 +147,8 @@ def test_conv_wgrad(mode, case):
     Ho = (H + 2 * p - k) // s + 1
     x, dy = rnd(N, H, H, Ci), rnd(N, Ho, Ho, Co, scale=(N * Ho * Ho) ** -0.5)
     dw0 = rnd(Co, Ci, k, k, scale=0.1)          # accumulate semantics
-    run_pair(mode, "conv_wgrad", [T(x), T(dy), F(dw0), k, s, p], [2], tol=dict(rtol=2e-3) if mode == "fp32" else None)
+    run_pair(mode, "conv_wgrad", [T(x), T(dy), F(dw0), k, s, p], [2], dict(impl=_impl_for(mode, 2, case)),
+             tol=dict(rtol=2e-3) if mode == "fp32" else None)
 
 
 @pytest.mark.parametrize("mode", MODES)
