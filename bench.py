@@ -512,7 +512,7 @@ def main():
     from imagegenerator_b200.engine import Stage1Engine
     from imagegenerator_b200.ops import CudaOps
     from imagegenerator_b200.stage_1_train_fn import train_1
-    from imagegenerator_b200.comm import DistComm
+    from imagegenerator_b200.comm import make_comm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -525,7 +525,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     ops = CudaOps(args.mode, device=dev)
     ca, d1, g1 = build_modules()
-    comm = DistComm(device=dev) if world > 1 else None
+    comm = make_comm(ops, device=dev) if world > 1 else None
     eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, comm=comm)
     use_graph = not args.no_graph
 
@@ -640,7 +640,8 @@ def main():
                     "params_finite": bool(finite.item() == 1.0), "outer_steps": W + 2 * K + 3,
                     "oracle_check": "tests/dp_nccl_worker.py (averaged-gradient oracle, 2 ranks)"}
 
-    s1_bytes_per_step = (comm.bytes_reduced // (W + 2 * K + 2)) if comm else 0
+    # gradient bytes every replica contributes per outer step: 5 critic steps + the generator's + the conditioning augmentation's
+    s1_bytes_per_step = 4 * (5 * eng.d.fp.grad.numel() + eng.g.fp.grad.numel() + eng.ca.fp.grad.numel()) if comm else 0
     extras = {}
     if not args.no_extras and args.mode == "bf16":
         del eng
@@ -679,8 +680,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "cuda_graph": use_graph, "grad_allreduce": ("NCCL avg, one all-reduce of the flat gradient buffer per optimizer step, "
-                                                                    f"{s1_bytes_per_step} B/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "cuda_graph": use_graph, "grad_allreduce": (("fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (sg_dp_adam_step), "
+                                                                     "one launch per optimizer step inside the CUDA graph, " if comm.peer else
+                                                                     "NCCL avg, one all-reduce of the flat gradient buffer per optimizer step, ") +
+                                                                    f"{s1_bytes_per_step} B of gradients/step") if comm else "none (1 GPU)", "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "flops_per_image_executed": FLOPS_PER_IMG,
                        "flops_per_image_reference_necessary": FLOPS_PER_IMG_REFERENCE_NECESSARY},
             "step_tflops": round(FLOPS_PER_IMG * B / (step_ms * 1e-3) / 1e12, 2),

@@ -15,12 +15,18 @@ feature maps and differs only in the affine head.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from types import SimpleNamespace
 
 import torch
 
-from .layers import FlatParams
+from .layers import FlatParams, flat_allocator
+
+
+def _alloc_ctx(comm):
+    """Parameter / gradient buffers in symmetric memory when the transport addresses peers directly (comm.PeerComm)."""
+    return flat_allocator(comm.alloc) if (comm is not None and getattr(comm, "peer", False)) else contextlib.nullcontext()
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 N_CRITIC = 5       # stage_1_train_fn.py:14
@@ -638,11 +644,12 @@ class Stage1Engine:
         ops = ops or default_ops()
         self.ops, self.B = ops, batch_size
         self.ca_m, self.d_m, self.g_m = ca, critic, gen
-        self.d = CriticRT(ops, critic, batch_size)
-        self.ca = CART(ops, ca)
-        self.ca.ensure(batch_size)
-        # the generator writes its tanh output straight into the critic's "fake" group
-        self.g = GenRT(ops, gen, batch_size, out=self.d.group_view(self.d.a[0], 1, 1))
+        with _alloc_ctx(comm):
+            self.d = CriticRT(ops, critic, batch_size)
+            self.ca = CART(ops, ca)
+            self.ca.ensure(batch_size)
+            # the generator writes its tanh output straight into the critic's "fake" group
+            self.g = GenRT(ops, gen, batch_size, out=self.d.group_view(self.d.a[0], 1, 1))
         for fp in (self.d.fp, self.g.fp, self.ca.fp):
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)       # [loss_critic, gp, lossG, kl]
@@ -652,7 +659,7 @@ class Stage1Engine:
         self._ce_ready = False                        # compressed text valid for the current weights + batch
         self._fake_ready = False
         self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
-        self.comm = comm                             # comm.DistComm or None
+        self.comm = comm                             # comm.PeerComm / comm.DistComm or None
         self.world = world_size
         if comm is not None:
             for fp in (self.d.fp, self.g.fp, self.ca.fp):
@@ -681,12 +688,21 @@ class Stage1Engine:
         """xm.optimizer_step: average gradients over replicas, then Adam.  ``already_reduced`` = offset
         from which the flat buffer has been handed to the communicator by the backward pass."""
         self.side.join()
+        if self.comm is not None and self.comm.peer:
+            self.comm.step(fp)               # reduce-scatter + Adam + all-gather over peer memory, one kernel, in the graph
+            return
         if self.comm is not None:
             self._comm_allreduce(fp.grad[:already_reduced] if already_reduced > 0 else fp.grad)
             self._comm_wait()
         elif self.allreduce is not None:
             self.allreduce(fp.grad)
         self.ops.adam_step(fp.flat, fp.grad, fp.m, fp.v, fp.hyper)
+
+    def gather_optimizer_state(self):
+        """COLLECTIVE (every rank): make the sharded Adam moments whole before a checkpoint is written."""
+        if self.comm is not None and self.comm.peer:
+            for fp in (self.d.fp, self.g.fp, self.ca.fp):
+                self.comm.gather_state(fp)
 
     def export_optimizer_state(self, opt, fp):
         export_optimizer_state(opt, fp)
@@ -751,7 +767,7 @@ class Stage1Engine:
         tail = [0]
 
         def bucket(l):
-            if self.comm is not None and l == d.nl - 1 and self.early_bucket:
+            if self.comm is not None and not self.comm.peer and l == d.nl - 1 and self.early_bucket:
                 self.side.join()
                 self._comm_allreduce(d.fp.grad[self.d_tail_off:])
                 tail[0] = self.d_tail_off
@@ -846,8 +862,8 @@ class Stage1Engine:
             if hasattr(self.ops, "launch_count"):
                 self.launches_per_step = self.ops.launch_count() - n0
             return
-        if self.comm is not None and self.comm.world > 1:
-            # multi-GPU: graph segments on a private stream, NCCL eager in between
+        if self.comm is not None and self.comm.world > 1 and not self.comm.peer:
+            # multi-GPU over NCCL / gloo all-reduce: graph segments on a private stream, the collective eager in between
             if getattr(self, "gstream", None) is None:
                 self.gstream = torch.cuda.Stream(device=self.ops.device)
             cur = torch.cuda.current_stream(self.ops.device)

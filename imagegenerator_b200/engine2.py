@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 
 from .engine import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, LAMBDA_GP, N_CRITIC, Z_DIM, CART, CriticRT, GenRT,
-                     SideStream, _LayerRT, _conv_out, _side_run, default_ops)
+                     SideStream, _LayerRT, _alloc_ctx, _conv_out, _side_run, default_ops)
 from .layers import FlatParams
 
 
@@ -213,12 +213,13 @@ class Stage2Engine:
         ops = ops or default_ops()
         self.ops, self.B = ops, batch_size
         B = batch_size
-        self.d = CriticRT(ops, critic2, B)
-        self.ca1, self.ca2 = CART(ops, ca1), CART(ops, ca2)
-        self.ca1.ensure(B)
-        self.ca2.ensure(B)
-        self.g1 = GenRT(ops, gen1, B)                                   # frozen, eval mode
-        self.g2 = Gen2RT(ops, gen2, B, x_in=self.g1.out, out=self.d.group_view(self.d.a[0], 1, 1))
+        with _alloc_ctx(comm):
+            self.d = CriticRT(ops, critic2, B)
+            self.ca1, self.ca2 = CART(ops, ca1), CART(ops, ca2)
+            self.ca1.ensure(B)
+            self.ca2.ensure(B)
+            self.g1 = GenRT(ops, gen1, B)                               # frozen, eval mode
+            self.g2 = Gen2RT(ops, gen2, B, x_in=self.g1.out, out=self.d.group_view(self.d.a[0], 1, 1))
         for fp in (self.d.fp, self.g2.fp, self.ca2.fp):
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)
@@ -240,6 +241,12 @@ class Stage2Engine:
         self.d.refresh_weights()
         self.g2.refresh_weights()
 
+    def gather_optimizer_state(self):
+        """COLLECTIVE (every rank): make the sharded Adam moments whole before a checkpoint is written."""
+        if self.comm is not None and self.comm.peer:
+            for fp in (self.d.fp, self.g2.fp, self.ca2.fp):
+                self.comm.gather_state(fp)
+
     def sync_grads(self):
         self.side.join()
         self._sync_grads()
@@ -255,6 +262,9 @@ class Stage2Engine:
         self.side.join()
         if fp is self.g2.fp:
             self.g2.fold_grads()
+        if self.comm is not None and self.comm.peer:
+            self.comm.step(fp)               # one kernel over peer memory, inside the captured graph
+            return
         if self.comm is not None:
             seg = getattr(self, "_seg", None)
             if seg is not None and seg.capturing:
@@ -398,8 +408,8 @@ class Stage2Engine:
             if hasattr(ops, "launch_count"):
                 self.launches_per_step = ops.launch_count() - n0
             return
-        if self.comm is not None and self.comm.world > 1:
-            # multi-GPU: graph segments on a private stream, NCCL eager in between (see engine.Stage1Engine.step)
+        if self.comm is not None and self.comm.world > 1 and not self.comm.peer:
+            # all-reduce transport: graph segments on a private stream, the collective eager in between (engine.Stage1Engine.step)
             from .engine import _SegmentedGraph
             if getattr(self, "gstream", None) is None:
                 self.gstream = torch.cuda.Stream(device=ops.device)

@@ -9,6 +9,7 @@ arithmetic is done by the CUDA kernels behind ``imagegenerator_b200.ops``.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import torch
@@ -106,6 +107,21 @@ def no_autograd(out, module):
     return _NoAutograd.apply(out, anchor, type(module).__name__)
 
 
+_FLAT_ALLOC = None      # callable(numel) -> zeroed fp32 CUDA tensor, or None (torch.zeros)
+
+
+@contextlib.contextmanager
+def flat_allocator(fn):
+    """Within this context ``FlatParams`` takes its parameter and gradient buffers from ``fn(numel)`` -- the data-parallel
+    engines pass ``comm.PeerComm.alloc`` so that the buffers live in symmetric memory every peer GPU can address."""
+    global _FLAT_ALLOC
+    prev, _FLAT_ALLOC = _FLAT_ALLOC, fn
+    try:
+        yield
+    finally:
+        _FLAT_ALLOC = prev
+
+
 class FlatParams:
     """All trainable parameters of a module re-pointed into ONE contiguous fp32 buffer, with a
     matching flat gradient buffer and Adam moments: one fused Adam launch and one all-reduce per
@@ -138,8 +154,11 @@ class FlatParams:
         # pad to a multiple of 4 floats so the vectorised Adam kernel needs no tail
         self.n = n
         npad = (n + 3) // 4 * 4
-        self.flat = torch.zeros(npad, dtype=dtype, device=device)
-        self.grad = torch.zeros(npad, dtype=dtype, device=device)
+        if _FLAT_ALLOC is not None and dtype == torch.float32:
+            self.flat, self.grad = _FLAT_ALLOC(npad), _FLAT_ALLOC(npad)
+        else:
+            self.flat = torch.zeros(npad, dtype=dtype, device=device)
+            self.grad = torch.zeros(npad, dtype=dtype, device=device)
         self.m = torch.zeros(npad, dtype=dtype, device=device)
         self.v = torch.zeros(npad, dtype=dtype, device=device)
         off = 0

@@ -89,7 +89,8 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
-                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace"])
+                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace",
+                                 "sg_dp_max_world", "sg_dp_flag_ints", "sg_dp_sync_ints", "sg_dp_adam_step"])
 
 
 def load_library(path=LIB_PATH):
@@ -113,6 +114,11 @@ def load_library(path=LIB_PATH):
     lib.sg_set_option.restype = _I
     lib.sg_debug_conv_trace.argtypes = [_P]
     lib.sg_debug_conv_trace.restype = _I
+    for name in ("sg_dp_max_world", "sg_dp_flag_ints", "sg_dp_sync_ints"):
+        getattr(lib, name).argtypes = []
+        getattr(lib, name).restype = _I
+    lib.sg_dp_adam_step.argtypes = [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]
+    lib.sg_dp_adam_step.restype = _I
     lib.sg_version.restype = _I
     lib.sg_last_error.restype = _c.c_char_p
     lib.sg_check_device.restype = _I
@@ -533,6 +539,13 @@ class CudaOps:
                                             self._dt_of(x), self._st()))
 
     # ---- optimiser
+    def dp_adam_step(self, grad_ptrs, param_ptrs, flag_ptrs, m, v, hyper, sync, n, rank, world, slot, write_avg=False):
+        """Data-parallel optimizer step over peer memory (csrc/dp_adam.cu).  ``*_ptrs``: ctypes arrays of ``world`` device
+        pointers (comm.PeerComm keeps them alive)."""
+        self._c(m, v, hyper, sync)
+        self._ck(self.lib.sg_dp_adam_step(grad_ptrs, param_ptrs, flag_ptrs, _ptr(m), _ptr(v), _ptr(hyper), _ptr(sync), int(n),
+                                          rank, world, slot, int(write_avg), self._st()))
+
     def adam_step(self, p, g, m, v, hyper):
         self._c(p, g, m, v, hyper)
         self._ck(self.lib.sg_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(hyper), p.numel(), self._st()))

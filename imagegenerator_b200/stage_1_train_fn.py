@@ -103,8 +103,9 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
     for m in models:
         m.train()                                              # :86-90
     if engine is None:
-        from .comm import DistComm
-        comm = DistComm(device=torch.device(device) if not isinstance(device, torch.device) else device) if world > 1 else None
+        from .comm import make_comm
+        from .engine import default_ops
+        comm = make_comm(default_ops(), device=torch.device(device) if not isinstance(device, torch.device) else device)
         engine = Stage1Engine(con_augment_1, critic_1, gen_1, batch_size, world_size=world, comm=comm)
     eng = engine
     for fp, opt in ((eng.ca.fp, opt_con_augment_1), (eng.d.fp, opt_critic_1), (eng.g.fp, opt_gen_1)):
@@ -174,6 +175,8 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
         if pending is not None:                                # last batch of the epoch
             _report(pending, log, rank, num_epochs, len(loader))
             pending = None
+        if epoch % 10 == 0:
+            eng.gather_optimizer_state()                       # every rank: the Adam moments are sharded over replicas
         if rank == 0 and epoch % 10 == 0:                     # :211-238
             eng.export_optimizer_state(opt_con_augment_1, eng.ca.fp)
             eng.export_optimizer_state(opt_critic_1, eng.d.fp)

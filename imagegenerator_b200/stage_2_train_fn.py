@@ -68,8 +68,9 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
     if engine is None:
         comm = None
         if world > 1:
-            from .comm import DistComm
-            comm = DistComm(device=torch.device(device) if not isinstance(device, torch.device) else device)
+            from .comm import make_comm
+            from .engine import default_ops
+            comm = make_comm(default_ops(), device=torch.device(device) if not isinstance(device, torch.device) else device)
         engine = Stage2Engine(con_augment_1, gen_1, con_augment_2, critic_2, gen_2, batch_size, comm=comm)
     eng = engine
     for fp, opt in ((eng.ca2.fp, opt_con_augment_2), (eng.d.fp, opt_critic_2), (eng.g2.fp, opt_gen_2)):
@@ -132,6 +133,8 @@ def train_2(models, optimizers, schedulers, loader, num_epochs, device, batch_si
                 with open(os.path.join(pdir, "scalars.csv"), "a") as f:
                     f.write(f"{preview_step},{epoch},{batch_idx},{losses[0]},{losses[2]}\n")
                 preview_step += 1                                                                       # :211
+        if epoch % 10 == 0:
+            eng.gather_optimizer_state()                                 # every rank: the Adam moments are sharded over replicas
         if rank == 0 and epoch % 10 == 0:                               # :214-235
             for opt, fp in ((opt_con_augment_2, eng.ca2.fp), (opt_critic_2, eng.d.fp), (opt_gen_2, eng.g2.fp)):
                 export_optimizer_state(opt, fp)                # exp_avg / exp_avg_sq / step of the fused Adam

@@ -272,6 +272,18 @@ int sg_scale_rows_add(const void* x, const float* scale, void* out, int accumula
    (step as a float for the bias correction; the exact count is step_hi * 2^23 + step_lo) */
 int sg_adam_step(float* p, const float* g, float* m, float* v, float* hyper, int64_t n, void* stream);
 
+/* ---- data-parallel optimizer step over NVLink peer memory (xm.optimizer_step: stage_1_train_fn.py:149,166-172) -------- */
+/* One kernel = reduce-scatter of the replicas' gradients (P2P loads of the owned shard) + Adam on the shard (optimizer
+   state sharded over ranks) + all-gather of the new parameters (P2P stores).  grad_ptrs / param_ptrs / flag_ptrs: host
+   arrays of `world` device pointers to the peers' symmetric buffers; flag block = sg_dp_flag_ints() int32, zeroed once;
+   sync = sg_dp_sync_ints() local int32, zeroed once (its last word is raised when a peer did not answer within ~2 s).
+   Graph-capturable; replicas end bit-identical.  write_avg != 0 also stores the averaged gradient into every replica. */
+int sg_dp_max_world(void);
+int sg_dp_flag_ints(void);
+int sg_dp_sync_ints(void);
+int sg_dp_adam_step(const void* const* grad_ptrs, const void* const* param_ptrs, const void* const* flag_ptrs, float* m, float* v,
+                    float* hyper, int* sync, int64_t n, int rank, int world, int slot, int write_avg, void* stream);
+
 /* ---- profiling hook -------------------------------------------------------------------------- */
 /* While buf (device, >= 296*16 uint64) is set, every persistent conv launch writes 16 %globaltimer stamps per CTA into
    it; NULL switches the hook off (tools/exp_conv_trace.py). */

@@ -31,7 +31,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from oracle import stackgan_oracle as O
     import gpu_oracle as GO
-    from imagegenerator_b200.comm import DistComm
+    from imagegenerator_b200.comm import make_comm
     from imagegenerator_b200.con_augment import ConditioningAugmentation
     from imagegenerator_b200.discrminator_1 import StageIDiscriminator
     from imagegenerator_b200.generator_1 import StageIGenerator
@@ -61,7 +61,9 @@ def main():
         want0[k] = g / world
 
     ops = CudaOps(mode, device=dev)
-    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, comm=DistComm(device=dev))
+    comm = make_comm(ops, device=dev)
+    comm.write_avg = True          # PeerComm: also leave the averaged gradient in every replica's .grad (this check reads it)
+    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, comm=comm)
     f = lambda t: t.float().contiguous()
     real, temf, tem_mis = f(mine["real"]), f(mine["tem"]), f(mine["tem"][shared["perm"]])
     z, eca, egp = f(shared["z"]), f(shared["eps_ca"]), f(shared["eps_gp"])
@@ -86,7 +88,8 @@ def main():
     # 2./3. whole outer steps through the graph-segment path, from a fresh state
     torch.manual_seed(42 + rank)
     ca, d1, g1 = ConditioningAugmentation(512, 256, 128), StageIDiscriminator(512, 128), StageIGenerator(128, 100)
-    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, comm=DistComm(device=dev))
+    comm.write_avg = False
+    eng = Stage1Engine(ca, d1, g1, B, ops=ops, world_size=world, comm=comm)
     eng.step(real, temf, tem_mis, z, eca, egp, use_graph=True)
     torch.cuda.synchronize()
     worst_p, lr = 0.0, 1e-3
@@ -110,9 +113,11 @@ def main():
     dist.broadcast(rm0, 0)
     if rank == 1:
         assert not torch.equal(rm, rm0), "BatchNorm running statistics must stay per replica"
+    if comm.peer:
+        comm.check()
     dist.barrier()
     if rank == 0:
-        print(f"DP_NCCL_OK mode={mode} world={world} worst_rel_l2_avg_grad={worst_g:.3e} worst_param_err_over_lr_steps={worst_p:.3f}",
+        print(f"DP_NCCL_OK transport={'peer' if comm.peer else 'nccl'} mode={mode} world={world} worst_rel_l2_avg_grad={worst_g:.3e} worst_param_err_over_lr_steps={worst_p:.3f}",
               flush=True)
     dist.destroy_process_group()
 
