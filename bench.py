@@ -459,38 +459,83 @@ def time_hbm_kernel(ops, peaks, reps=10):
     byts = 4.0 * rows * C * 2
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = byts / (ms * 1e-3) / 1e9
+    prof_file = "profiles/ncu_bn_r2_summary.txt"
+    prof = read_profile_metrics(os.path.join(ROOT, prof_file), "bn_bwd_apply8_kernel")
+    traffic = (int(prof["dram__bytes_read.sum"] + prof["dram__bytes_write.sum"])
+               if "dram__bytes_read.sum" in prof and "dram__bytes_write.sum" in prof else None)
     return {"bound": "hbm", "kernel": "sg_bn_bwd_apply (bn_bwd_apply8_kernel) on the 64x128x128x80 bf16 activation of G2 up2",
             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-            "traffic": 648091136, "traffic_unit": "B per launch (dram read 503.4 MB + write 144.7 MB, profiles/ncu_bn_r1b_summary.txt; "
-                                                  "algorithmic 671.1 MB, the tail of the output is still in L2 at kernel end)",
+            "traffic": traffic, "traffic_unit": f"B per launch (dram__bytes_read.sum + dram__bytes_write.sum parsed from {prof_file}; "
+                                                "algorithmic 671.1 MB, the tail of the output is still in L2 at kernel end)",
             "algorithmic_bytes": int(byts), "kernel_ms": round(ms, 5),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
 
 
 # ------------------------------------------------------------------------------------------------ kernel roofline
-def time_dominant_kernel(ops, B, reps=20):
-    """The critic's heaviest conv (ds3: 128->256, 16x16 -> 8x8, all three image groups batched) timed
-    alone with CUDA events on its launch stream; algorithmic FLOPs = 2*M*N*K."""
+def time_dominant_kernel(ops, B, reps=20, sets=8):
+    """The critic's heaviest conv (ds3: 128->256, 16x16 -> 8x8, all three image groups batched) timed alone with CUDA
+    events on its launch stream; algorithmic FLOPs = 2*M*N*K.  Two figures:
+
+    * ``ms``: average launch duration over ``reps * sets`` launches queued back to back between ONE pair of events -- the
+      way the kernel runs inside the captured step.  The launches walk through ``sets`` separate (input, weights, output)
+      buffer sets, 38.8 MB each: 8 sets = 310 MB > the 126 MB L2, so every launch finds its operands in HBM, not in L2;
+    * ``ms_isolated``: one launch between its own pair of events after a 256 MiB L2 flush (this adds the ~2 us an event
+      pair around a single short launch costs; the ncu duration of the same launch sits between the two figures)."""
     N, H, Ci, Co, k = 3 * B, 16, 128, 256, 4
-    x = torch.randn(N, H, H, Ci, device="cuda").to(ops.act_dtype)
-    pf = (torch.randn(Co, k, k, Ci, device="cuda") * 0.02).to(ops.act_dtype)
-    y = torch.empty(N, H // 2, H // 2, Co, device="cuda", dtype=ops.act_dtype)
+    xs = [torch.randn(N, H, H, Ci, device="cuda").to(ops.act_dtype) for _ in range(sets)]
+    pfs = [(torch.randn(Co, k, k, Ci, device="cuda") * 0.02).to(ops.act_dtype) for _ in range(sets)]
+    ys = [torch.empty(N, H // 2, H // 2, Co, device="cuda", dtype=ops.act_dtype) for _ in range(sets)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        ops.conv_fprop(x, pf, None, y, k, 2, 1)
+    for i in range(sets):
+        ops.conv_fprop(xs[i], pfs[i], None, ys[i], k, 2, 1)
     ts = []
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv_fprop(x, pf, None, y, k, 2, 1)
+        ops.conv_fprop(xs[0], pfs[0], None, ys[0], k, 2, 1)
         e1.record()
         e1.synchronize()
         ts.append(e0.elapsed_time(e1))
-    ts.sort()
-    ms = sum(ts) / len(ts)
+    ms_iso = sum(ts) / len(ts)
+    flush.zero_()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for i in range(sets):
+            ops.conv_fprop(xs[i], pfs[i], None, ys[i], k, 2, 1)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * sets)
     flops = 2.0 * (N * (H // 2) ** 2) * Co * (k * k * Ci)
-    return flops, ms
+    return flops, ms, ms_iso
+
+
+def read_profile_metrics(path, kernel_substr):
+    """Metrics of the first launch of ``kernel_substr`` in a profiles/ncu_*_summary.txt file (tools/ncu_summary.py format:
+    `  metric   value unit` lines under `-- launch N`).  Returns {} when the file is missing or holds no such launch."""
+    out, active = {}, False
+    try:
+        with open(path) as f:
+            for ln in f:
+                if ln.startswith("-- launch"):
+                    if out:
+                        break
+                    active = False
+                    continue
+                parts = ln.split()
+                if len(parts) >= 2 and parts[0] == "Kernel" and parts[1] == "Name":
+                    active = kernel_substr in ln
+                    continue
+                if active and len(parts) >= 2:
+                    try:
+                        out[parts[0]] = float(parts[1])
+                    except ValueError:
+                        pass
+    except OSError:
+        return {}
+    return out
 
 
 def main():
@@ -671,9 +716,13 @@ def main():
                 peaks = json.load(f)
         except Exception:
             pass
-        kflops, kms = time_dominant_kernel(ops, B)
+        kflops, kms, kms_iso = time_dominant_kernel(ops, B)
         peak_tf = float(peaks.get("bf16_tflops", 1590.0))
         ach = kflops / (kms * 1e-3) / 1e12
+        prof_file = "profiles/ncu_conv_tcp_r2_summary.txt"
+        prof = read_profile_metrics(os.path.join(ROOT, prof_file), "conv_tcp_kernel")
+        traffic = (int(prof["dram__bytes_read.sum"] + prof["dram__bytes_write.sum"])
+                   if "dram__bytes_read.sum" in prof and "dram__bytes_write.sum" in prof else None)
         line = {
             "metric": "stackgan_stage1_train_images_per_sec", "value": round(value, 2), "unit": "images/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
@@ -691,12 +740,19 @@ def main():
             "gpu_launches": int(launches),
             "e2e": {"value": round(B * world / (e2e_ms * 1e-3), 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "imagegenerator_b200.stage_1_train_fn.train_1"},
-            "roofline": {"bound": "tensor", "kernel": "sg_conv_fprop critic ds3 (128->256, k4 s2, 3 groups batched)",
+            "roofline": {"bound": "tensor", "kernel": "sg_conv_fprop critic ds3 (128->256, k4 s2, 3 groups batched), conv_tcp_kernel<2>",
                          "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                         "traffic": 26289152, "traffic_unit": "B per launch (dram read + write, profiles/ncu_conv_tcp_r1g_summary.txt; "
-                                                              "algorithmic 38.8 MB incl. the 12.6 MB result that stays in L2)",
-                         "tensor_pipe_active_pct": 59.5, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PF",
-                         "kernel_ms": round(kms, 5)},
+                         "traffic": traffic,
+                         "traffic_unit": f"B per launch (dram__bytes_read.sum + dram__bytes_write.sum parsed from {prof_file}; "
+                                         "algorithmic 38.8 MB incl. the 12.6 MB result, which is still in L2 at kernel end)",
+                         "tensor_pipe_active_pct_of_elapsed": prof.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                         "ncu_duration_us": prof.get("gpu__time_duration.sum"),
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PF",
+                         "kernel_ms": round(kms, 5),
+                         "timing": "average launch duration of 160 back-to-back launches between one event pair, rotating through 8 "
+                                   "buffer sets (310 MB > L2: operands come from HBM)",
+                         "kernel_ms_isolated": round(kms_iso, 5),
+                         "frac_isolated": round(kflops / (kms_iso * 1e-3) / 1e12 / peak_tf, 4)},
             "clocks": clocks,
         }
         if dp_check is not None:

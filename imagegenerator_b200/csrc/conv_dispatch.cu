@@ -30,6 +30,9 @@ int sg_conv_fprop_tc_f32out(const void*, const void*, float*, int, int, int, int
 int sg_conv_fprop_tc_res(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, int,
                          int, int, void*);
 int sg_add_act(const void*, const void*, void*, int64_t, int, int, void*);
+int sg_conv_thin_supported(int, int, int, int, int, int, int, int, int, int, int);
+int sg_conv_thin_fprop(const void*, const void*, const float*, void*, int, int, int, int, int, void*);
+int sg_conv_thin_dgrad(const void*, const void*, const float*, void*, int, int, int, int, int, void*);
 
 static int unsupported(const char* what, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p) {
     sg::set_error("%s: the tensor-core kernels cannot take N=%d %dx%dx%d -> %dx%dx%d k%d s%d p%d in bf16 mode (reduction channels must "
@@ -42,6 +45,8 @@ static int unsupported(const char* what, int N, int H, int W, int Ci, int Ho, in
 int sg_conv_fprop(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Ci, int Ho, int Wo,
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
     if (dtype == SG_BF16) {
+        // the 3-channel image side: direct kernel (thin_conv.cu), the 128-row tcgen05 tiles have nothing to contract there
+        if (sg_conv_thin_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return sg_conv_thin_fprop(x, pf, bias, y, N, H, W, Co, act, stream);
         if (!sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_fprop", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_fprop_tc(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
     }
@@ -50,6 +55,7 @@ int sg_conv_fprop(const void* x, const void* pf, const float* bias, void* y, int
 int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int H, int W, int Ci, int Ho, int Wo,
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
     if (dtype == SG_BF16) {
+        if (sg_conv_thin_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return sg_conv_thin_dgrad(dy, pd, bias, dx, N, Ho, Wo, Co, act, stream);
         if (!sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_dgrad", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_dgrad_tc(dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
     }

@@ -873,7 +873,7 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 struct TcW2Params {
@@ -885,13 +885,16 @@ struct TcW2Params {
     int stages, nun_max;       // pipeline depth; units per stage buffer
     float* dw;
     int dw_cl;                 // 0: dw[Co][Ci][kk] (PyTorch), 1: dw[Co][kk][Ci] (channels-last accumulation buffer)
+    int cs;                    // multicast launches: CTAs per cluster (2..5 co tiles sharing their x tiles)
 };
 
-// MC = true: clusters of two CTAs along the co-tile axis (same units, same pixel range, different 128 output channels).
-// The x tiles are the same for both, so each CTA fetches every second unit and TMA-multicasts it into both CTAs' shared
-// memory: x is 80 % of a stage, so the L2 -> SM operand traffic per CTA drops from 40 KB to 24 KB per k-block.  A stage
-// may be refilled once BOTH CTAs' MMAs have retired it (empty barriers count 2, commits are multicast).  When the number
-// of co tiles is odd the last cluster's second CTA owns no channels: it only keeps the barrier protocol going.
+// MC = true: clusters of P.cs = 2..5 CTAs along the co-tile axis (same units, same pixel range, different 128 output
+// channels).  The x tiles are the same for all of them, so CTA r fetches the units u with u % cs == r and TMA-multicasts
+// them into every CTA's shared memory: x is 80 % of a stage, so the L2 -> SM operand traffic per CTA drops from 40 KB per
+// k-block to 8 + 32/cs KB (24 KB for pairs, 18.7 KB for the three co tiles of the 320-channel residual convs, 14.4 KB for
+// the five of the 640-channel ones: below the ~22 KB that 512 cycles of MMA can absorb at the L2 -> SM ceiling).  A stage
+// may be refilled once ALL CTAs' MMAs have retired it (empty barriers count cs, commits are multicast).  A cluster CTA
+// whose co tile lies past the layer's channels (only when the host pads) just keeps the barrier protocol going.
 template <int PIX, bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcW2Params P) {
@@ -919,7 +922,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     // took longer than the k-block's MMAs); every feeding warp waits for the stage itself and posts its own expect_tx.
     constexpr int FEEDERS = 5;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], FEEDERS); mbar_init(&empty_bar[i], MC ? 2 : 1); }
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], FEEDERS); mbar_init(&empty_bar[i], MC ? P.cs : 1); }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -944,7 +947,8 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             if (has_b) { const int u = u0 + ub, cib = u / P.kk, tap = u - cib * P.kk; cb2 = cib * 64; hb = tap / P.k; wb = tap - hb * P.k; hb -= P.p; wb -= P.p; }
             // bytes this warp's loads put into a stage (multicast: the peer CTA delivers the units of the other parity)
             const uint32_t my_tx = fw < 0 ? (has_rows ? (uint32_t)A_BYTES : 0u) : (uint32_t)(((has_a ? 1 : 0) + (has_b ? 1 : 0)) * B_BYTES);
-            const bool issue_a = has_a && (!MC || (ua & 1) == (int)rank), issue_b = has_b && (!MC || (ub & 1) == (int)rank);
+            const bool issue_a = has_a && (!MC || (ua % P.cs) == (int)rank), issue_b = has_b && (!MC || (ub % P.cs) == (int)rank);
+            const uint16_t mc_mask = (uint16_t)((1u << P.cs) - 1u);
             const uint32_t ring = smem_u32(smem);
             int st = 0;
             uint32_t par = 1;
@@ -965,11 +969,11 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
                         const int w0 = ow0 * P.s, h0 = oh0 * P.s;
                         if (issue_a) {
                             if (!MC) tma_load_4d_u32(&tmX, fb, sa + A_BYTES + ua * B_BYTES, ca, w0 + wa, h0 + ha, n0);
-                            else tma_load_4d_mc_u32(&tmX, fb, sa + A_BYTES + ua * B_BYTES, ca, w0 + wa, h0 + ha, n0, (uint16_t)3);
+                            else tma_load_4d_mc_u32(&tmX, fb, sa + A_BYTES + ua * B_BYTES, ca, w0 + wa, h0 + ha, n0, mc_mask);
                         }
                         if (issue_b) {
                             if (!MC) tma_load_4d_u32(&tmX, fb, sa + A_BYTES + ub * B_BYTES, cb2, w0 + wb, h0 + hb, n0);
-                            else tma_load_4d_mc_u32(&tmX, fb, sa + A_BYTES + ub * B_BYTES, cb2, w0 + wb, h0 + hb, n0, (uint16_t)3);
+                            else tma_load_4d_mc_u32(&tmX, fb, sa + A_BYTES + ub * B_BYTES, cb2, w0 + wb, h0 + hb, n0, mc_mask);
                         }
                     }
                 }
@@ -1008,10 +1012,9 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(&full_bar[st], par);
                 if (MC && !has_rows) {
-                    // padding CTA: nothing to multiply, but both CTAs must release the stage
+                    // padding CTA: nothing to multiply, but every CTA of the cluster must see this one release the stage
                     if (elect_one()) {
-                        mbar_arrive_cta(&empty_bar[st], 0);
-                        mbar_arrive_cta(&empty_bar[st], 1);
+                        for (int c = 0; c < P.cs; ++c) mbar_arrive_cta(&empty_bar[st], (uint32_t)c);
                     }
                     __syncwarp();
                     if (++st == P.stages) { st = 0; par ^= 1; }
@@ -1025,7 +1028,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
                         mma(tmem_base, a0 + k16 * 128, b0 + k16 * 128, idesc_lo, acc);
                         if (n_hi > 0) mma(tmem_base + 256, a0 + k16 * 128, b1 + k16 * 128, idesc_hi, acc);
                     }
-                    if (MC) tc_commit_mc(&empty_bar[st], (uint16_t)3); else tc_commit(&empty_bar[st]);
+                    if (MC) tc_commit_mc(&empty_bar[st], (uint16_t)((1u << P.cs) - 1u)); else tc_commit(&empty_bar[st]);
                 }
                 __syncwarp();
                 if (++st == P.stages) { st = 0; par ^= 1; }
@@ -1501,6 +1504,8 @@ static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtens
 }
 
 int g_use_wgrad_mc = 1;
+int g_wgrad_mc_max = 5;      // option "wgrad_mc_max": largest cluster formed from all co tiles of a layer
+int g_wgrad_mc_odd = 1;      // option "wgrad_mc_odd": 0 = pairs only (the round-1 behaviour), for A/B measurements
 
 template <int PIX>
 static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
@@ -1515,45 +1520,76 @@ static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N,
     if ((e = get_rows_map_n(dy, P.Mpix, Co, PIX, &tmDy))) return e;
     if ((e = get_act_map(x, N, H, W, Ci, bw, bh, bn, s, &tmX))) return e;
     const int co_tiles = (Co + 127) / 128;
-    // pairs of co tiles share their x tiles through TMA multicast when there are at least two of them
-    // (even tile counts only: with a padding CTA in the last cluster the launch measured up to 1.9x slower than unicast)
-    const bool mc = g_use_wgrad_mc && co_tiles >= 2 && (co_tiles % 2) == 0;
-    const int tiles = (mc ? (co_tiles + 1) / 2 * 2 : co_tiles) * P.ugroups;
-    // splits: fill whole waves of 148 CTAs.  Fixed cost per CTA in 32-pixel k-block units (0.6 us each): prologue + the
-    // atomics epilogue, ~10 us with vector reductions, ~40 us with scalar ones (k*k not a multiple of 4, PyTorch layout)
-    const bool vec_epi = P.dw_cl || P.kk == 1 || (P.kk & 3) == 0;
-    const double fixed = (vec_epi ? 18.0 : 66.0) * 32.0 / PIX;
-    int max_splits = P.total_kb / 4;
-    if (max_splits < 1) max_splits = 1;
-    int best = 1;
-    double best_cost = 1e30;
-    for (int sp = 1; sp <= max_splits && sp <= 148; ++sp) {
-        long ctas = (long)tiles * sp;
-        long waves = (ctas + SG_NUM_SMS - 1) / SG_NUM_SMS;
-        int kbs = (P.total_kb + sp - 1) / sp;
-        double cost = (double)waves * (kbs + fixed);
-        if (cost < best_cost) { best_cost = cost; best = sp; }
-    }
-    P.kb_per_split = (P.total_kb + best - 1) / best;
-    const int splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
     size_t smem = (size_t)P.stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
         if (ce == cudaSuccess)
             ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+        if (ce == cudaSuccess)
+            ce = cudaFuncSetAttribute(conv_wgrad2_kernel<PIX, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad2): %s", cudaGetErrorString(ce)); return (int)ce; }
         attr_set = true;
     }
+    // ---- cluster size x split-K.  The co tiles of a layer share their x tiles: a cluster of cs co tiles multicasts them
+    // (kernel header), which cuts the operand bytes per k-block from 8 + 4*nun KB to 8 + 4*nun/cs KB.  But a cluster needs cs
+    // free SMs in ONE GPC (16-20 SMs each, one CTA per SM at this shared-memory footprint): only cap(cs) clusters are
+    // co-resident (measured through the occupancy API: ~46 triples, 33 quads), and a grid one cluster over that runs a
+    // second wave -- round 2's first cut (always cluster all co tiles) made the 320-channel layers 1.7x SLOWER that way.
+    // So: cost(cs, splits) = waves(cs) * (k-blocks per split * max(MMA, L2) cycles + fixed), minimised over both.
+    static int cap_cache[9] = {0};
+    auto cluster_cap = [&](int c) -> int {
+        if (c == 1) return SG_NUM_SMS;
+        if (cap_cache[c] > 0) return cap_cache[c];
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(c * 64, 1, 1); q.blockDim = dim3(TC_THREADS); q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute a[1];
+        a[0].id = cudaLaunchAttributeClusterDimension;
+        a[0].val.clusterDim.x = c; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+        q.attrs = a; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_wgrad2_kernel<PIX, true>, &q) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = SG_NUM_SMS / c * 3 / 4;          // conservative guess if the query is unavailable
+        }
+        cap_cache[c] = n;
+        return n;
+    };
+    const bool vec_epi = P.dw_cl || P.kk == 1 || (P.kk & 3) == 0;
+    // fixed cost per CTA (prologue + the atomics epilogue): ~10 us with vector reductions, ~40 us with scalar ones
+    const double fixed_cycles = (vec_epi ? 18.0 : 66.0) * 1150.0;
+    const double mma_cycles = 2.0 * PIX * P.nun_max;                       // (PIX/16) MMAs of N = 64*nun columns at N/2 cycles
+    int max_splits = P.total_kb / 4;
+    if (max_splits < 1) max_splits = 1;
+    int best = 1, cs = 1;
+    double best_cost = 1e30;
+    for (int c = 1; c <= 8 && c <= co_tiles; ++c) {
+        if (co_tiles % c != 0) continue;
+        if (c > 1 && (!g_use_wgrad_mc || c > g_wgrad_mc_max || (!g_wgrad_mc_odd && c != 2))) continue;
+        const int cap = cluster_cap(c);
+        const double l2_cycles = (double)PIX * 128.0 * (2.0 + (double)P.nun_max / c) / 44.0;
+        const double t_kb = mma_cycles > l2_cycles ? mma_cycles : l2_cycles;
+        const long clusters1 = (long)(co_tiles / c) * P.ugroups;
+        for (int sp = 1; sp <= max_splits && sp <= 148; ++sp) {
+            const long waves = (clusters1 * sp + cap - 1) / cap;
+            const int kbs = (P.total_kb + sp - 1) / sp;
+            const double cost = (double)waves * (kbs * t_kb + fixed_cycles);
+            if (cost < best_cost * 0.999) { best_cost = cost; best = sp; cs = c; }
+        }
+    }
+    const bool mc = cs > 1;
+    P.cs = cs;
+    P.kb_per_split = (P.total_kb + best - 1) / best;
+    const int splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
     if (mc) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((co_tiles + 1) / 2 * 2, P.ugroups, splits);
+        cfg.gridDim = dim3(co_tiles, P.ugroups, splits);
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_wgrad2_kernel<PIX, true>, tmDy, tmX, P);
         if (ce != cudaSuccess) { set_error("conv_wgrad2 (multicast) launch: %s", cudaGetErrorString(ce)); return (int)ce; }
@@ -1576,7 +1612,7 @@ static int launch_wgrad2(const void* x, const void* dy, float* dw, int N, int H,
     if (e) return e;
     TcW2Params P;
     P.Mpix = N * Ho * Wo; P.Ho = Ho; P.Wo = Wo; P.Co = Co; P.Ci = Ci; P.kk = k * k; P.k = k; P.s = s; P.p = p; P.dw = dw;
-    P.dw_cl = dw_cl;
+    P.dw_cl = dw_cl; P.cs = 1;
     P.cblocks = (Ci + 63) / 64;
     P.units = P.cblocks * P.kk;
     P.ugroups = (P.units + 7) / 8;
@@ -1624,6 +1660,8 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
     if (name && !strcmp(name, "rotate")) { g_rotate = value; return 0; }
     if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }
+    if (name && !strcmp(name, "wgrad_mc_max")) { g_wgrad_mc_max = value; return 0; }
+    if (name && !strcmp(name, "wgrad_mc_odd")) { g_wgrad_mc_odd = value; return 0; }
     if (name && !strcmp(name, "pdl")) { g_use_pdl = value; return 0; }
     if (name && !strcmp(name, "force_cg")) { g_force_cg = value; return 0; }
     if (name && !strcmp(name, "epi_alt")) { g_epi_alt = value; return 0; }

@@ -69,6 +69,156 @@ __global__ void __launch_bounds__(256) linear_dx_kernel(const float* __restrict_
     *o = acc_flag ? *o + acc : acc;
 }
 
+// ---- conditioning augmentation, fused (reference con_augment.py:13-22 + the concat of stage_1_train_fn.py:120-122)
+// forward: tem -> h = relu(Wh tem + bh) -> (mu, sigma) -> c_hat = mu + sigma * eps -> row [c_hat, z, 0...] of the generator's
+// input, ONE launch, one CTA per sample: the 197 k parameters stream through each CTA once (L2 hits after the first CTA),
+// nothing but the tensors the backward needs (h, mu, sigma, c_hat) goes back to memory.  A warp computes four outputs at a
+// time so that 16 independent 16-byte weight loads per lane are in flight (the chain is latency-bound, not FLOP-bound).
+template <typename T>
+__global__ void __launch_bounds__(256) ca_forward_kernel(const float* __restrict__ tem, const float* __restrict__ Wh,
+                                                         const float* __restrict__ bh, const float* __restrict__ Wmu,
+                                                         const float* __restrict__ bmu, const float* __restrict__ Wsg,
+                                                         const float* __restrict__ bsg, const float* __restrict__ eps,
+                                                         const float* __restrict__ z, float* __restrict__ h,
+                                                         float* __restrict__ mu, float* __restrict__ sigma,
+                                                         float* __restrict__ c_hat, T* __restrict__ cg, int Tm, int Hd, int C,
+                                                         int nz, int ld) {
+    extern __shared__ float ca_sm[];
+    float* xs = ca_sm;                 // [Tm]
+    float* hs = xs + Tm;               // [Hd]
+    float* ms = hs + Hd;               // [2C]: mu, sigma
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < Tm; i += 256) xs[i] = tem[(int64_t)n * Tm + i];
+    __syncthreads();
+    auto dot4 = [&](const float* w0, const float* w1, const float* w2, const float* w3, const float* xv, int K, float (&acc)[4]) {
+        const float4* x4 = reinterpret_cast<const float4*>(xv);
+        const float4 *a = reinterpret_cast<const float4*>(w0), *b = reinterpret_cast<const float4*>(w1),
+                     *c = reinterpret_cast<const float4*>(w2), *d = reinterpret_cast<const float4*>(w3);
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        for (int k = lane; k < (K >> 2); k += 32) {
+            const float4 xx = x4[k], wa = __ldg(a + k), wb = __ldg(b + k), wc = __ldg(c + k), wd = __ldg(d + k);
+            acc[0] += wa.x * xx.x + wa.y * xx.y + wa.z * xx.z + wa.w * xx.w;
+            acc[1] += wb.x * xx.x + wb.y * xx.y + wb.z * xx.z + wb.w * xx.w;
+            acc[2] += wc.x * xx.x + wc.y * xx.y + wc.z * xx.z + wc.w * xx.w;
+            acc[3] += wd.x * xx.x + wd.y * xx.y + wd.z * xx.z + wd.w * xx.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+    };
+    for (int m0 = warp * 4; m0 < Hd; m0 += 32) {
+        float acc[4];
+        dot4(Wh + (int64_t)m0 * Tm, Wh + (int64_t)(m0 + 1) * Tm, Wh + (int64_t)(m0 + 2) * Tm, Wh + (int64_t)(m0 + 3) * Tm, xs, Tm, acc);
+        if (lane < 4) {
+            const float sel = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+            const float v = fmaxf(sel + bh[m0 + lane], 0.f);
+            hs[m0 + lane] = v;
+            h[(int64_t)n * Hd + m0 + lane] = v;
+        }
+    }
+    __syncthreads();
+    for (int m0 = warp * 4; m0 < 2 * C; m0 += 32) {
+        const bool sg = m0 >= C;
+        const float* W = sg ? Wsg : Wmu;
+        const int r = sg ? m0 - C : m0;
+        float acc[4];
+        dot4(W + (int64_t)r * Hd, W + (int64_t)(r + 1) * Hd, W + (int64_t)(r + 2) * Hd, W + (int64_t)(r + 3) * Hd, hs, Hd, acc);
+        if (lane < 4) {
+            const float sel = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+            const float v = sel + (sg ? bsg : bmu)[r + lane];
+            ms[m0 + lane] = v;
+            (sg ? sigma : mu)[(int64_t)n * C + r + lane] = v;
+        }
+    }
+    if (eps == nullptr) return;
+    __syncthreads();
+    for (int j = tid; j < ld; j += 256) {
+        if (j < C) {
+            const float c = ms[j] + ms[C + j] * eps[(int64_t)n * C + j];
+            c_hat[(int64_t)n * C + j] = c;
+            if (cg) stf(cg + (int64_t)n * ld + j, c);
+        } else if (cg) {
+            stf(cg + (int64_t)n * ld + j, (z != nullptr && j < C + nz) ? z[(int64_t)n * nz + (j - C)] : 0.f);
+        }
+    }
+}
+
+// backward, data part, one CTA per sample:
+//   dmu = dc + kl * (-2 mu), dsigma = dc * eps + kl * (2/sigma - 2 sigma)         (dc = d loss / d c_hat, row n of dcg)
+//   dh  = relu'(h) * (Wmu^T dmu + Wsigma^T dsigma)                                  [stored MASKED]
+//   dtem (+)= Wh^T dh                                                               (optional)
+template <typename T>
+__global__ void __launch_bounds__(256) ca_backward_data_kernel(const T* __restrict__ dcg, const float* __restrict__ eps,
+                                                               const float* __restrict__ mu, const float* __restrict__ sigma,
+                                                               float kl, const float* __restrict__ h,
+                                                               const float* __restrict__ Wmu, const float* __restrict__ Wsg,
+                                                               const float* __restrict__ Wh, float* __restrict__ dmu,
+                                                               float* __restrict__ dsigma, float* __restrict__ dh,
+                                                               float* __restrict__ dtem, int dtem_acc, int Tm, int Hd, int C,
+                                                               int ld) {
+    extern __shared__ float ca_sm[];
+    float* dm = ca_sm;                 // [2C]: dmu, dsigma
+    float* dhs = dm + 2 * C;           // [Hd]
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int j = tid; j < C; j += 256) {
+        const int64_t i = (int64_t)n * C + j;
+        const float dc = dcg ? ldf(dcg + (int64_t)n * ld + j) : 0.f;
+        const float s = sigma[i];
+        const float a = dc + kl * (-2.f * mu[i]), b = dc * eps[i] + kl * (2.f / s - 2.f * s);
+        dm[j] = a; dm[C + j] = b;
+        dmu[i] = a; dsigma[i] = b;
+    }
+    __syncthreads();
+    for (int k = tid; k < Hd; k += 256) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < C; ++j) acc += dm[j] * __ldg(Wmu + (int64_t)j * Hd + k) + dm[C + j] * __ldg(Wsg + (int64_t)j * Hd + k);
+        acc = h[(int64_t)n * Hd + k] > 0.f ? acc : 0.f;
+        dhs[k] = acc;
+        dh[(int64_t)n * Hd + k] = acc;
+    }
+    if (dtem == nullptr) return;
+    __syncthreads();
+    for (int k = tid; k < Tm; k += 256) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int m = 0; m < Hd; ++m) acc += dhs[m] * __ldg(Wh + (int64_t)m * Tm + k);
+        float* o = dtem + (int64_t)n * Tm + k;
+        *o = dtem_acc ? *o + acc : acc;
+    }
+}
+
+// backward, parameter part: the three weight / bias gradients in ONE launch.  grid (ceil(Tm/256), 2C + Hd, splits): row
+// r < C: mu layer (x = h, d = dmu); r < 2C: sigma layer; else the hidden layer (x = tem, d = masked dh).
+__global__ void __launch_bounds__(256) ca_backward_params_kernel(const float* __restrict__ tem, const float* __restrict__ h,
+                                                                 const float* __restrict__ dmu, const float* __restrict__ dsigma,
+                                                                 const float* __restrict__ dh, float* __restrict__ gWmu,
+                                                                 float* __restrict__ gbmu, float* __restrict__ gWsg,
+                                                                 float* __restrict__ gbsg, float* __restrict__ gWh,
+                                                                 float* __restrict__ gbh, int N, int Tm, int Hd, int C,
+                                                                 int n_per_split) {
+    const int r = blockIdx.y;
+    const float *x, *d;
+    float *gw, *gb;
+    int K, M, m;
+    if (r < C) { x = h; d = dmu; gw = gWmu; gb = gbmu; K = Hd; M = C; m = r; }
+    else if (r < 2 * C) { x = h; d = dsigma; gw = gWsg; gb = gbsg; K = Hd; M = C; m = r - C; }
+    else { x = tem; d = dh; gw = gWh; gb = gbh; K = Tm; M = Hd; m = r - 2 * C; }
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x * 256 >= K) return;
+    const int n0 = blockIdx.z * n_per_split, n1 = min(N, n0 + n_per_split);
+    const bool live = k < K;
+    const float* xp = x + (live ? k : 0);
+    float acc = 0.f, dsum = 0.f;
+#pragma unroll 8
+    for (int n = n0; n < n1; ++n) {
+        const float dv = d[(int64_t)n * M + m];
+        acc += dv * xp[(int64_t)n * K];
+        dsum += dv;
+    }
+    if (live) atomicAdd(gw + (int64_t)m * K + k, acc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(gb + m, dsum);
+}
+
 // ---- head: A[hw][c] = sum_k wcs[k][hw] wcr[k][c]; Bv[j] = sum_k sw[k] wcr[k][Cx+j]; c0 = sum_k sw[k] bcr[k] + bcs,
 // sw[k] = sum_hw wcs[k][hw].  Blocks [0, gridDim.x-1) compute A (thread per element, K independent coalesced loads);
 // the last block computes sw in shared memory, then Bv and c0.
@@ -274,6 +424,47 @@ int sg_linear_bwd(const float* x, const float* w, const float* dout, const float
             linear_dx_kernel<false><<<grid, 256, smem, st>>>(w, dout, relu_out, dx, dx_acc, N, K, M);
         SG_LAUNCHED("linear_dx");
     }
+    return 0;
+}
+
+// Conditioning augmentation, fused (con_augment.py:13-22 + the [c_hat, z] concat of stage_1_train_fn.py:120-122): see the
+// kernels above.  eps NULL = encode only (h, mu, sigma); z / cg NULL = no generator input row.
+int sg_ca_forward(const float* tem, const float* Wh, const float* bh, const float* Wmu, const float* bmu, const float* Wsg,
+                  const float* bsg, const float* eps, const float* z, float* h, float* mu, float* sigma, float* c_hat, void* cg,
+                  int N, int Tm, int Hd, int C, int nz, int ld, int dtype, void* stream) {
+    SG_REQUIRE(Tm % 4 == 0 && Hd % 4 == 0 && C % 4 == 0, "ca_forward: sizes must be multiples of 4");
+    SG_REQUIRE(cg == nullptr || ld >= C + nz, "ca_forward: row length %d < %d + %d", ld, C, nz);
+    const size_t smem = (size_t)(Tm + Hd + 2 * C) * sizeof(float);
+    SG_REQUIRE(smem <= 48 * 1024, "ca_forward: sizes exceed the shared-memory staging");
+    SG_DISPATCH_T(dtype, (ca_forward_kernel<T><<<N, 256, smem, SG_STREAM(stream)>>>(tem, Wh, bh, Wmu, bmu, Wsg, bsg, eps, z, h, mu,
+                                                                                    sigma, c_hat, (T*)cg, Tm, Hd, C, nz,
+                                                                                    cg ? ld : C)));
+    SG_LAUNCHED("ca_forward");
+    return 0;
+}
+
+// d loss / d(mu, sigma, h, tem) and the six parameter gradients (accumulated) in two launches.  dcg: gradient of the
+// generator input rows (T, row length ld; only its first C columns are read) or NULL; kl_scale multiplies the gradient of
+// sum(1 + log sigma^2 - mu^2 - sigma^2) (stage_1_train_fn.py:156-159); dtem NULL = the text side is frozen.
+int sg_ca_backward(const void* dcg, const float* eps, const float* mu, const float* sigma, float kl_scale, const float* h,
+                   const float* tem, const float* Wmu, const float* Wsg, const float* Wh, float* dmu, float* dsigma, float* dh,
+                   float* gWmu, float* gbmu, float* gWsg, float* gbsg, float* gWh, float* gbh, float* dtem, int dtem_acc, int N,
+                   int Tm, int Hd, int C, int ld, int dtype, void* stream) {
+    cudaStream_t st = SG_STREAM(stream);
+    const size_t smem = (size_t)(2 * C + Hd) * sizeof(float);
+    SG_REQUIRE(smem <= 48 * 1024, "ca_backward: sizes exceed the shared-memory staging");
+    SG_DISPATCH_T(dtype, (ca_backward_data_kernel<T><<<N, 256, smem, st>>>((const T*)dcg, eps, mu, sigma, kl_scale, h, Wmu, Wsg, Wh,
+                                                                            dmu, dsigma, dh, dtem, dtem_acc, Tm, Hd, C, ld)));
+    SG_LAUNCHED("ca_backward_data");
+    int splits = (N + 31) / 32;
+    if (splits > 8) splits = 8;
+    if (splits < 1) splits = 1;
+    const int nps = (N + splits - 1) / splits;
+    splits = (N + nps - 1) / nps;
+    const int kmax = Tm > Hd ? Tm : Hd;
+    ca_backward_params_kernel<<<dim3((kmax + 255) / 256, 2 * C + Hd, splits), 256, 0, st>>>(tem, h, dmu, dsigma, dh, gWmu, gbmu, gWsg,
+                                                                                            gbsg, gWh, gbh, N, Tm, Hd, C, nps);
+    SG_LAUNCHED("ca_backward_params");
     return 0;
 }
 

@@ -170,23 +170,18 @@ class CART:
         ops, m = self.ops, self.m
         st = self.ensure(tem.shape[0])
         st.tem, st.eps = tem, eps
-        ops.linear_fwd(tem, m.h.weight.data, m.h.bias.data, st.h, relu=True)
-        ops.linear_fwd(st.h, m.mu.weight.data, m.mu.bias.data, st.mu)
-        ops.linear_fwd(st.h, m.sigma.weight.data, m.sigma.bias.data, st.sigma)
-        if eps is not None:
-            ops.ca_reparam(st.mu, st.sigma, eps, z, st.c_hat, cg)
+        ops.ca_forward(tem, m.h.weight.data, m.h.bias.data, m.mu.weight.data, m.mu.bias.data, m.sigma.weight.data,
+                       m.sigma.bias.data, eps, z, st.h, st.mu, st.sigma, st.c_hat, cg)      # one launch
         return st
 
     def backward(self, dcg, kl_scale, dtem, dtem_acc):
         """Accumulates parameter grads; dtem (+)= d/d tem.  dcg: grad of the [c_hat, z] buffer
         (T) or None; kl_scale multiplies d/d(mu,sigma) of sum(1+log s^2-mu^2-s^2)
-        (stage_1_train_fn.py:156-159)."""
+        (stage_1_train_fn.py:156-159).  Two launches: per-sample data gradients, then all six parameter gradients."""
         ops, m, st = self.ops, self.m, self.st
-        ops.ca_bwd_seed(dcg, st.eps, st.mu, st.sigma, kl_scale, st.dmu, st.dsigma)
-        ops.linear_bwd(st.h, m.mu.weight.data, st.dmu, m.mu.weight.grad, m.mu.bias.grad, st.dh, dx_acc=False)
-        ops.linear_bwd(st.h, m.sigma.weight.data, st.dsigma, m.sigma.weight.grad, m.sigma.bias.grad, st.dh, dx_acc=True)
-        ops.linear_bwd(st.tem, m.h.weight.data, st.dh, m.h.weight.grad, m.h.bias.grad, dtem, dx_acc=dtem_acc,
-                       relu_out=st.h)
+        ops.ca_backward(dcg, st.eps, st.mu, st.sigma, kl_scale, st.h, st.tem, m.mu.weight.data, m.sigma.weight.data,
+                        m.h.weight.data, st.dmu, st.dsigma, st.dh, m.mu.weight.grad, m.mu.bias.grad, m.sigma.weight.grad,
+                        m.sigma.bias.grad, m.h.weight.grad, m.h.bias.grad, dtem, dtem_acc)
 
     def backward_from_dc(self, dc, kl_scale):
         """Same with d loss / d c_hat given directly as an fp32 [B,c_dim] tensor and no d/d tem wanted
@@ -227,18 +222,14 @@ class GenRT:
                 self.dpre = ops.empty(shp)
                 hin = (h + 2 * L.p - L.k) // L.s + 1
                 self.K_last = L.ci * L.k * L.k
-                self.col = ops.empty((B, hin, hin, self.K_last), ops.f32)
-                # backward of the 3-channel layer: 1x1 GEMMs over the patch matrix of d/d(pre-tanh) (like Gen2RT's up3)
+                # weight gradient of the 3-channel layer: a 1x1 GEMM over the patch matrix of d/d(pre-tanh)
                 self.Pd = ops.empty((B, hin, hin, self.K_last))
-                self.pf_last = ops.empty((L.co, 1, 1, self.K_last))
         self.packed = False
 
     def refresh_weights(self):
         self.up0.pack()
         for L in self.layers[1:]:
             L.pack(self.ops)
-        last = self.layers[-1]
-        self.ops.pack_weight(last.conv.weight.data.view(last.co, self.K_last, 1, 1), self.pf_last, None)
         self.packed = True
 
     def set_input(self, x):
@@ -254,9 +245,8 @@ class GenRT:
             ops.zero(self.stats_flat)
         for i, L in enumerate(self.layers):
             if L.bn is None:
-                # ConvT(C -> 3) + Tanh: 1x1 GEMM onto the 48 (channel, tap) columns, then col2im
-                ops.conv_fprop_f32out(x, L.pd.view(L.ci * L.k * L.k, 1, 1, L.co), self.col, 1, 1, 0)
-                ops.unpatchify(self.col, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
+                # ConvT(C -> 3) + bias + Tanh: one direct kernel (thin_conv.cu), the col matrix stays on the SM
+                ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
                 break
             bn = L.bn
             if i == 0:
@@ -284,13 +274,13 @@ class GenRT:
         ops = self.ops
         last = self.layers[-1]
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
-        ops.patchify(self.dpre, self.Pd, last.k, last.s, last.p)
 
         def pgrad_last():
+            ops.patchify(self.dpre, self.Pd, last.k, last.s, last.p)
             ops.colsum(self.dpre, last.conv.bias.grad)
             ops.conv_wgrad(self.Pd, self.a[-1], last.conv.weight.grad.view(last.co, self.K_last, 1, 1), 1, 1, 0)
         _side_run(side, pgrad_last)
-        ops.conv_fprop(self.Pd, self.pf_last, None, self.da[-1], 1, 1, 0)
+        ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
             ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,
@@ -355,16 +345,13 @@ class CriticRT:
                 self.gy.append(ops.empty(shp1))
         assert h == 4, h
         self.nl = len(self.layers)
-        # first layer (3-channel image): run as a 1x1 conv over the patch matrix P[pix][ci*16+tap] -- the
-        # PyTorch weight order, so the weight itself (viewed [Co,48,1,1]) is the packed operand and the
-        # weight gradient lands in place.  P is shared by fprop and wgrad.
+        # first layer (3-channel image): forward and input gradient are direct kernels (thin_conv.cu); its WEIGHT gradient
+        # is a 1x1 GEMM over the patch matrix P[pix][ci*16+tap] -- the PyTorch weight order, so the gradient lands in place
         L0 = self.layers[0]
         h1 = _conv_out(module.in_hw, L0.k, L0.s, L0.p)
         self.K0 = L0.ci * L0.k * L0.k
         self.P = ops.empty((G * B, h1, h1, self.K0))
         self.Pv = ops.empty((B, h1, h1, self.K0))
-        self.colf = ops.empty(((G - 1) * B, h1, h1, self.K0), f32)      # col2im input of d/d image (<= 2 groups)
-        self.pf0 = ops.empty((L0.co, 1, 1, self.K0))
         cl, Nd = self.layers[-1].co, module.Nd
         self.head_grads = ops.zeros((16 * cl + Nd,), f32)            # dA and dBv: zeroed together every iteration
         self.A, self.dA = ops.empty((16, cl), f32), self.head_grads[:16 * cl].view(16, cl)
@@ -402,8 +389,6 @@ class CriticRT:
         ops, m = self.ops, self.m
         for L in self.layers:
             L.pack(ops)
-        L0 = self.layers[0]
-        ops.pack_weight(L0.conv.weight.data.view(L0.co, self.K0, 1, 1), self.pf0, None)
         ops.head_prepare(m.channel_resize.weight.data, m.channel_resize.bias.data, m.critic_score.weight.data,
                          m.critic_score.bias.data, self.A, self.Bv, self.c0)
         if with_text:
@@ -415,21 +400,26 @@ class CriticRT:
             self.tem_all[self.B:].copy_(tem_mis)
 
     # ---------------------------------------------------------------- forward
-    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False, before_weights=None, ce_ready=False):
+    def forward(self, g0, ng, dup_first, training=True, with_mismatched=False, before_weights=None, ce_ready=False,
+                patches_on=None):
         """Trunk + head on groups [g0, g0+ng).  BN running statistics are updated once per group,
         group g0 ``dup_first`` times (the mismatched-text call sees the real images again).
         ``before_weights()`` is called right before the first kernel that reads packed weights (the engines re-pack
         them on a side stream after each optimizer step and join here).  ``ce_ready``: the compressed text was already
-        computed by ``refresh_weights(with_text=True)`` for the current weights and batch."""
+        computed by ``refresh_weights(with_text=True)`` for the current weights and batch.  ``patches_on``: a SideStream (or
+        False for "this stream") on which to build the patch matrix of the input images that the first layer's weight
+        gradient will read -- it must be built NOW when the image buffer is overwritten before the backward pass runs
+        (Stage-I generates the next fake batch early); None: no weight gradient will be asked for."""
         ops, m, B = self.ops, self.m, self.B
         gv = lambda t: self.group_view(t, g0, ng)
         L0 = self.layers[0]
-        ops.patchify(gv(self.a[0]), gv(self.P), L0.k, L0.s, L0.p)
+        if patches_on is not None:
+            _side_run(patches_on or None, lambda: ops.patchify(gv(self.a[0]), gv(self.P), L0.k, L0.s, L0.p))
         if training:
             ops.zero(self.stats_flat)
         if before_weights is not None:
             before_weights()
-        ops.conv_fprop(gv(self.P), self.pf0, L0.conv.bias.data, gv(self.a[1]), 1, 1, 0, act=ACT_LRELU)
+        ops.conv_fprop(gv(self.a[0]), L0.pf, L0.conv.bias.data, gv(self.a[1]), L0.k, L0.s, L0.p, act=ACT_LRELU)
         for l in range(1, self.nl):
             L, bn = self.layers[l], self.layers[l].bn
             y = gv(self.y[l])
@@ -457,11 +447,9 @@ class CriticRT:
 
     # ---------------------------------------------------------------- first-order backward
     def input_grad(self, dy0, dx):
-        """d/d image of the first conv: 1x1 GEMM of dy0 onto the 48 (channel, tap) columns (fp32), then col2im."""
+        """d/d image of the first conv: ConvTranspose2d(C0 -> 3) as one direct kernel (thin_conv.cu)."""
         ops, L0 = self.ops, self.layers[0]
-        col = self.colf[:dy0.shape[0]]
-        ops.conv_fprop_f32out(dy0, L0.pd.view(self.K0, 1, 1, L0.co), col, 1, 1, 0)
-        ops.unpatchify(col, None, dx, L0.k, L0.s, L0.p)
+        ops.conv_dgrad(dy0, L0.pd, None, dx, L0.k, L0.s, L0.p)
 
     def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, on_layer_done=None, head_reduce=True,
                  input_grad_from=None, side=None):
@@ -545,9 +533,12 @@ class CriticRT:
         i2 = lambda t: self.group_view(t, 2, 1)
         ops.gp_seed(self.g, self.sq, coef, self.v0)
         L0 = self.layers[0]
-        ops.patchify(self.v0, self.Pv, L0.k, L0.s, L0.p)
-        ops.conv_fprop(self.Pv, self.pf0, None, self.v[0], 1, 1, 0)
-        _side_run(side, lambda: ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0))
+        ops.conv_fprop(self.v0, L0.pf, None, self.v[0], L0.k, L0.s, L0.p)
+
+        def pgrad_v0():
+            ops.patchify(self.v0, self.Pv, L0.k, L0.s, L0.p)
+            ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
+        _side_run(side, pgrad_v0)
         ops.act_bwd(self.v[0], i2(self.a[1]), self.w[1], ACT_LRELU)
         for l in range(1, nl):
             L, bn = self.layers[l], self.layers[l].bn
@@ -751,8 +742,9 @@ class Stage1Engine:
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,    # :125-132 + utils.py:13
-                  before_weights=self.pack_side.join, ce_ready=self._ce_ready)
+                  before_weights=self.pack_side.join, ce_ready=self._ce_ready, patches_on=self.side)
         if next_noise is not None and self.gen_side.enabled:
+            self.side.join()                 # the patch matrix of this iteration's images is built: group 1 may be overwritten
             self.gen_side.run(lambda: self._generate(*next_noise))
             self._fake_ready = True
         ops.zero(d.fp.grad)                                      # :146

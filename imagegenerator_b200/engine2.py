@@ -77,10 +77,9 @@ class Gen2RT:
         self.res = [[_LayerRT(ops, c, bn) for c, bn in blk.conv_layers()] for blk in m.residual_blocks]
         self.ups = [_LayerRT(ops, m.up_sampler[i][0], m.up_sampler[i][1]) for i in range(3)]
         self.up3 = _LayerRT(ops, m.up_sampler[3], None)
-        # thin (3-channel) operators run as 1x1 convs over a patch matrix
+        # thin (3-channel) operators: forward / data gradient are direct kernels (thin_conv.cu); their weight gradients
+        # are 1x1 GEMMs over a patch matrix in the PyTorch weight order
         self.K0 = 3 * 16
-        self.pf_ds0 = ops.empty((self.ds0.co, 1, 1, self.K0))
-        self.pf_up3 = ops.empty((self.up3.co, 1, 1, self.K0))
         self.x_in = x_in if x_in is not None else ops.empty((B, 64, 64, 3))
         self.P0 = ops.empty((B, 32, 32, self.K0))
         self.a1, self.da1, self.dy0 = ops.empty((B, 32, 32, 128)), ops.empty((B, 32, 32, 128)), ops.empty((B, 32, 32, 128))
@@ -96,7 +95,6 @@ class Gen2RT:
         self.out = out if out is not None else ops.empty((B, 256, 256, 3))
         self.dpre = ops.empty((B, 256, 256, 3))
         self.Pd = ops.empty((B, 128, 128, self.K0))
-        self.colf = ops.empty((B, 128, 128, self.K0), f32)
         self.ones = torch.ones(B, dtype=f32).to(ops.device)
 
     def _wgrad(self, L, x, dy):
@@ -127,16 +125,13 @@ class Gen2RT:
         ops = self.ops
         for L in self.all_layers():
             L.pack(ops)
-        ops.pack_weight(self.ds0.conv.weight.data.view(self.ds0.co, self.K0, 1, 1), self.pf_ds0, None)
-        ops.pack_weight(self.up3.conv.weight.data.view(self.up3.co, self.K0, 1, 1), self.pf_up3, None)
 
     def forward(self, c_hat, training=True):
         """x_in (NHWC T) and c_hat [B,128] fp32 -> self.out [B,256,256,3] (generator_2.py:59-67)."""
         ops = self.ops
         self.c_hat = c_hat
         L = self.ds0
-        ops.patchify(self.x_in, self.P0, L.k, L.s, L.p)
-        ops.conv_fprop(self.P0, self.pf_ds0, L.conv.bias.data, self.a1, 1, 1, 0, act=ACT_LRELU)
+        ops.conv_fprop(self.x_in, L.pf, L.conv.bias.data, self.a1, L.k, L.s, L.p, act=ACT_LRELU)
         L = self.ds2
         _conv_bn_forward(ops, "f", self.a1, L, self.b2, self.b2.a, ACT_LRELU, training)
         ops.concat_rep(self.b2.a, c_hat, self.X[0])
@@ -152,9 +147,8 @@ class Gen2RT:
             _conv_bn_forward(ops, "d", x, L, b, b.a, ACT_RELU, training)
             x = b.a
         L = self.up3
-        # ConvT(80 -> 3) + Tanh (generator_2.py:55-57): 1x1 GEMM onto the 48 (channel, tap) columns (fp32) + col2im
-        ops.conv_fprop_f32out(x, L.pd.view(self.K0, 1, 1, L.co), self.colf, 1, 1, 0)
-        ops.unpatchify(self.colf, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
+        # ConvT(80 -> 3) + bias + Tanh (generator_2.py:55-57): one direct kernel, the col matrix never leaves the SM
+        ops.conv_dgrad(x, L.pd, L.conv.bias.data, self.out, L.k, L.s, L.p, act=ACT_TANH)
         return self.out
 
     def backward(self, dout, side=None):
@@ -164,13 +158,13 @@ class Gen2RT:
         sr = lambda fn: _side_run(side, fn)
         L = self.up3
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
-        ops.patchify(self.dpre, self.Pd, L.k, L.s, L.p)
 
         def pgrad_up3(L=L):
+            ops.patchify(self.dpre, self.Pd, L.k, L.s, L.p)
             ops.colsum(self.dpre, L.conv.bias.grad)
             ops.conv_wgrad(self.Pd, self.ub[2].a, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
         sr(pgrad_up3)
-        ops.conv_fprop(self.Pd, self.pf_up3, None, self.ub[2].da, 1, 1, 0)
+        ops.conv_fprop(self.dpre, L.pf, None, self.ub[2].da, L.k, L.s, L.p)
         for i in range(2, -1, -1):
             L, b = self.ups[i], self.ub[i]
             dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side)
@@ -200,6 +194,7 @@ class Gen2RT:
         ops.act_bwd(self.da1, self.a1, self.dy0, ACT_LRELU)
 
         def pgrad_ds0(L=L):
+            ops.patchify(self.x_in, self.P0, L.k, L.s, L.p)
             ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
             ops.colsum(self.dy0, L.conv.bias.grad)
         sr(pgrad_ds0)
@@ -321,7 +316,7 @@ class Stage2Engine:
         X = d.a[0]
         ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,        # :133-140 + utils.py:13
-                  before_weights=self.pack_side.join, ce_ready=self._ce_ready)
+                  before_weights=self.pack_side.join, ce_ready=self._ce_ready, patches_on=self.side)
         ops.zero(d.fp.grad)                                         # :153
         ops.zero(d.head_grads)                                      # dA, dBv
         d.gp_first_order()

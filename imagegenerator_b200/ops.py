@@ -79,6 +79,8 @@ _SIGS = {
     "sg_head_param_grads": [_P] * 10 + [_I, _I, _I, _P],
     "sg_ca_reparam": [_P] * 6 + [_I, _I, _I, _I, _I, _P],
     "sg_ca_bwd_seed": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
+    "sg_ca_forward": [_P] * 14 + [_I] * 7 + [_P],
+    "sg_ca_backward": [_P] * 4 + [_F] + [_P] * 15 + [_I] * 7 + [_P],
     "sg_interp": [_P, _P, _P, _P, _I, _L, _I, _P],
     "sg_sample_sqnorm": [_P, _P, _I, _L, _I, _P],
     "sg_gp_seed": [_P, _P, _F, _P, _I, _L, _I, _P],
@@ -86,10 +88,12 @@ _SIGS = {
     "sg_gen_loss": [_P, _P, _P, _P, _I, _I, _P],
     "sg_scale_rows_add": [_P, _P, _P, _I, _I, _L, _I, _P],
     "sg_adam_step": [_P, _P, _P, _P, _P, _L, _P],
+    "sg_conv_thin_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "sg_conv_thin_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
 }
 
 EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
-                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace",
+                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace", "sg_conv_thin_supported",
                                  "sg_dp_max_world", "sg_dp_flag_ints", "sg_dp_sync_ints", "sg_dp_adam_step"])
 
 
@@ -504,6 +508,30 @@ class CudaOps:
         self._ck(self.lib.sg_ca_bwd_seed(_ptr(dcg), _ptr(eps), _ptr(mu), _ptr(sigma), float(kl_scale), _ptr(dmu),
                                          _ptr(dsigma), N, C, ld, self._dt_of(dcg) if dcg is not None else SG_F32,
                                          self._st()))
+
+    def ca_forward(self, tem, Wh, bh, Wmu, bmu, Wsg, bsg, eps, z, h, mu, sigma, c_hat, cg):
+        """The whole conditioning-augmentation forward in one launch (con_augment.py:13-22 + the [c_hat, z] row)."""
+        self._c(tem, Wh, bh, Wmu, bmu, Wsg, bsg, eps, z, h, mu, sigma, c_hat, cg)
+        N, Tm = tem.shape
+        Hd, C = Wh.shape[0], Wmu.shape[0]
+        ld = cg.numel() // N if cg is not None else C
+        nz = z.shape[1] if (z is not None and cg is not None) else 0
+        self._ck(self.lib.sg_ca_forward(_ptr(tem), _ptr(Wh), _ptr(bh), _ptr(Wmu), _ptr(bmu), _ptr(Wsg), _ptr(bsg), _ptr(eps),
+                                        _ptr(z if cg is not None else None), _ptr(h), _ptr(mu), _ptr(sigma), _ptr(c_hat), _ptr(cg),
+                                        N, Tm, Hd, C, nz, ld, self._dt_of(cg) if cg is not None else SG_F32, self._st()))
+
+    def ca_backward(self, dcg, eps, mu, sigma, kl_scale, h, tem, Wmu, Wsg, Wh, dmu, dsigma, dh, gWmu, gbmu, gWsg, gbsg, gWh,
+                    gbh, dtem, dtem_acc):
+        """Backward of ca_forward in two launches; parameter gradients accumulate, dtem (may be None) (+)=."""
+        self._c(dcg, eps, mu, sigma, h, tem, Wmu, Wsg, Wh, dmu, dsigma, dh, gWmu, gbmu, gWsg, gbsg, gWh, gbh, dtem)
+        N, Tm = tem.shape
+        Hd, C = Wh.shape[0], Wmu.shape[0]
+        ld = dcg.numel() // N if dcg is not None else 0
+        self._ck(self.lib.sg_ca_backward(_ptr(dcg), _ptr(eps), _ptr(mu), _ptr(sigma), float(kl_scale), _ptr(h), _ptr(tem),
+                                         _ptr(Wmu), _ptr(Wsg), _ptr(Wh), _ptr(dmu), _ptr(dsigma), _ptr(dh), _ptr(gWmu),
+                                         _ptr(gbmu), _ptr(gWsg), _ptr(gbsg), _ptr(gWh), _ptr(gbh), _ptr(dtem),
+                                         1 if dtem_acc else 0, N, Tm, Hd, C, ld,
+                                         self._dt_of(dcg) if dcg is not None else SG_F32, self._st()))
 
     # ---- losses
     def interp(self, real, fake, eps, out):

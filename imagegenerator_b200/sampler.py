@@ -80,8 +80,6 @@ class StackGANSampler:
         for L in self.g1[1:-1]:
             h = (h - 1) * L.s - 2 * L.p + L.k
             self.a1.append(ops.empty((B, h, h, L.ci)))
-        L = self.g1[-1]
-        self.col1 = ops.empty((B, h, h, L.ci * L.k * L.k), f32)
         self.fake_64 = ops.empty((B, 2 * h, 2 * h, 3))
         # ---- Stage-II generator (generator_2.py:59-67)
         m = gen_2
@@ -90,19 +88,16 @@ class StackGANSampler:
             self.g2rt = Gen2RT(ops, gen_2, B, x_in=self.fake_64)
             self.fake_256 = self.g2rt.out
         else:
-            self.ds0 = m.down_sampler[0]
-            self.pf_ds0 = ops.empty((self.ds0.weight.shape[0], 1, 1, 48))
+            self.ds0 = _Folded(ops, m.down_sampler[0], None, "f")
             self.ds2 = _Folded(ops, m.down_sampler[2][0], m.down_sampler[2][1], "f")
             self.res = [[_Folded(ops, c, bn, "f") for c, bn in blk.conv_layers()] for blk in m.residual_blocks]
             self.ups = [_Folded(ops, m.up_sampler[i][0], m.up_sampler[i][1], "d") for i in range(3)]
             self.up3 = _Folded(ops, m.up_sampler[3], None, "d")
-            self.P0 = ops.empty((B, 32, 32, 48))
             self.x1 = ops.empty((B, 32, 32, 128))
             self.x2 = ops.empty((B, 16, 16, 512))
             self.X = [ops.empty((B, 16, 16, 640)) for _ in range(2)]       # residual-block boundaries, ping-pong
             self.r1, self.r2 = ops.empty((B, 16, 16, 320)), ops.empty((B, 16, 16, 320))
             self.u = [ops.empty((B, 32, 32, 320)), ops.empty((B, 64, 64, 160)), ops.empty((B, 128, 128, 80))]
-            self.col2 = ops.empty((B, 128, 128, 48), f32)
             self.fake_256 = ops.empty((B, 256, 256, 3))
         self.s_tem = ops.empty((B, con_augment_1.h.weight.shape[1]), f32)
         self.s_z = ops.empty((B, Z_DIM), f32)
@@ -122,7 +117,7 @@ class StackGANSampler:
         if self.bn_batch_stats:
             self.g2rt.refresh_weights()
             return
-        ops.pack_weight(self.ds0.weight.data.view(self.ds0.weight.shape[0], 48, 1, 1), self.pf_ds0, None)
+        self.ds0.refresh(ops)
         self.ds2.refresh(ops)
         for blk in self.res:
             for L in blk:
@@ -142,15 +137,12 @@ class StackGANSampler:
         for L, a in zip(self.g1[1:-1], self.a1[1:]):
             L.run(ops, x, a, ACT_RELU)
             x = a
-        L = self.g1[-1]
-        ops.conv_fprop_f32out(x, L.pack.view(L.ci * L.k * L.k, 1, 1, L.co), self.col1, 1, 1, 0)
-        ops.unpatchify(self.col1, L.conv.bias.data, self.fake_64, L.k, L.s, L.p, act=ACT_TANH)
+        self.g1[-1].run(ops, x, self.fake_64, ACT_TANH)                                # ConvT(C -> 3) + Tanh, direct kernel
         st2 = self.ca2.forward(self.s_tem, self.s_e2, None)                            # :192
         if self.bn_batch_stats:
             self.g2rt.forward(st2.c_hat, training=True)                                # :193, gen_2 in train mode
         else:
-            ops.patchify(self.fake_64, self.P0, 4, 2, 1)
-            ops.conv_fprop(self.P0, self.pf_ds0, self.ds0.bias.data, self.x1, 1, 1, 0, act=ACT_LRELU)
+            self.ds0.run(ops, self.fake_64, self.x1, ACT_LRELU)                        # Conv2d(3 -> 128), direct kernel
             self.ds2.run(ops, self.x1, self.x2, ACT_LRELU)
             ops.concat_rep(self.x2, st2.c_hat, self.X[0])
             cur = 0
@@ -163,9 +155,7 @@ class StackGANSampler:
             for L, u in zip(self.ups, self.u):
                 L.run(ops, x, u, ACT_RELU)
                 x = u
-            L = self.up3
-            ops.conv_fprop_f32out(x, L.pack.view(48, 1, 1, L.co), self.col2, 1, 1, 0)
-            ops.unpatchify(self.col2, L.conv.bias.data, self.fake_256, L.k, L.s, L.p, act=ACT_TANH)
+            self.up3.run(ops, x, self.fake_256, ACT_TANH)
         ops.nhwc_to_nchw(self.fake_64, self.out_64)
         ops.nhwc_to_nchw(self.fake_256, self.out_256)
 

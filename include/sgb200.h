@@ -93,6 +93,20 @@ int sg_conv_fprop_f32out(const void* x, const void* pf, float* y, int N, int H, 
 int sg_conv_fprop_tc_f32out(const void* x, const void* pf, float* y, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                             int k, int s, int p, void* stream);
 
+/* ---- the 3-channel image side as direct kernels (thin_conv.cu; bf16 only) --------------------------------------------
+ * sg_conv_fprop / sg_conv_dgrad route here by themselves when Ci == 3, k4 s2 p1 and the output grid tiles (rows % 8,
+ * columns % 32 == 0, Co % 8 == 0, Co <= 128): every activation byte is read once, no patch / col matrix in HBM.
+ *   fprop: Conv2d(3 -> Co) + bias + act  -- critics' first layer (discrminator_1.py:17-18, discriminator_2.py:11-12),
+ *          G2's first layer (generator_2.py:9-10), the input gradient of the generators' ConvT(C -> 3);
+ *   dgrad: ConvTranspose2d(Co -> 3) + bias + act -- the generators' output layer + Tanh (generator_1.py:30-33,
+ *          generator_2.py:55-57), d/d image of the critics (utils.py:15-21).
+ * mode: 0 fprop, 1 dgrad; shapes in Conv2d orientation like every sg_conv_* call. */
+int sg_conv_thin_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
+int sg_conv_thin_fprop(const void* x, const void* pf, const float* bias, void* y, int N, int H, int W, int Co, int act,
+                       void* stream);
+int sg_conv_thin_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Ho, int Wo, int Co, int act,
+                       void* stream);
+
 /* out[n,hw,:Cx] = x, out[n,hw,Cx:] = c[n]  (generator_2.py:61-63 reshape/repeat/cat);  backward:
  * dx = dout[..., :Cx], dc[n] (fp32) = sum_hw dout[n,hw,Cx:] */
 int sg_concat_rep(const void* x, const float* c, void* out, int N, int HW, int Cx, int Cc, int dtype, void* stream);
@@ -256,6 +270,20 @@ int sg_ca_reparam(const float* mu, const float* sigma, const float* eps, const f
 /* dmu = dc + kl*(-2mu); dsigma = dc*eps + kl*(2/sigma-2sigma); dc = first C of each dcg row (ld = row length) */
 int sg_ca_bwd_seed(const void* dcg, const float* eps, const float* mu, const float* sigma, float kl_scale,
                    float* dmu, float* dsigma, int N, int C, int ld, int dtype, void* stream);
+
+/* The whole module in one launch each way (dense.cu): tem [N][Tm] -> h = relu(Wh tem + bh) [N][Hd] -> mu, sigma [N][C]
+   -> c_hat = mu + sigma*eps -> cg row [c_hat, z, 0...] (con_augment.py:13-22, stage_1_train_fn.py:120-122).  eps NULL =
+   encode only; z / cg NULL = no generator input row.  h, mu, sigma, c_hat are kept for the backward. */
+int sg_ca_forward(const float* tem, const float* Wh, const float* bh, const float* Wmu, const float* bmu, const float* Wsg,
+                  const float* bsg, const float* eps, const float* z, float* h, float* mu, float* sigma, float* c_hat, void* cg,
+                  int N, int Tm, int Hd, int C, int nz, int ld, int dtype, void* stream);
+/* backward of the above in two launches (per-sample data gradients, then the six parameter gradients together):
+   dmu/dsigma as sg_ca_bwd_seed, dh = relu'(h)*(Wmu^T dmu + Wsg^T dsigma) [stored masked], dtem (+)= Wh^T dh (dtem NULL: text
+   side frozen, stage_2_train_fn.py:52-57), gW*, gb* += the weight / bias gradients. */
+int sg_ca_backward(const void* dcg, const float* eps, const float* mu, const float* sigma, float kl_scale, const float* h,
+                   const float* tem, const float* Wmu, const float* Wsg, const float* Wh, float* dmu, float* dsigma, float* dh,
+                   float* gWmu, float* gbmu, float* gWsg, float* gbsg, float* gWh, float* gbh, float* dtem, int dtem_acc, int N,
+                   int Tm, int Hd, int C, int ld, int dtype, void* stream);
 
 /* ---- losses (utils.py:8-26; stage_1_train_fn.py:134-144,154-159) ------------------------------ */
 int sg_interp(const void* real, const void* fake, const float* eps, void* out, int N, int64_t per_sample, int dtype, void* stream);

@@ -385,6 +385,22 @@ class EmuOps:
         dmu.copy_((dc + kl_scale * (-2 * mu)).to(dmu.dtype))
         dsigma.copy_((dc * eps + kl_scale * (2 / sigma - 2 * sigma)).to(dsigma.dtype))
 
+    def ca_forward(self, tem, Wh, bh, Wmu, bmu, Wsg, bsg, eps, z, h, mu, sigma, c_hat, cg):
+        """con_augment.py:13-22 in one call: the composition of the statements above."""
+        self.linear_fwd(tem, Wh, bh, h, relu=True)
+        self.linear_fwd(h, Wmu, bmu, mu)
+        self.linear_fwd(h, Wsg, bsg, sigma)
+        if eps is not None:
+            self.ca_reparam(mu, sigma, eps, z, c_hat, cg)
+
+    def ca_backward(self, dcg, eps, mu, sigma, kl_scale, h, tem, Wmu, Wsg, Wh, dmu, dsigma, dh, gWmu, gbmu, gWsg, gbsg, gWh,
+                    gbh, dtem, dtem_acc):
+        self.ca_bwd_seed(dcg, eps, mu, sigma, kl_scale, dmu, dsigma)
+        self.linear_bwd(h, Wmu, dmu, gWmu, gbmu, dh, dx_acc=False)
+        self.linear_bwd(h, Wsg, dsigma, gWsg, gbsg, dh, dx_acc=True)
+        dh.mul_((h > 0).to(dh.dtype))                               # stored masked, like the kernel
+        self.linear_bwd(tem, Wh, dh, gWh, gbh, dtem, dx_acc=dtem_acc)
+
     # ---- losses / gradient penalty
     def interp(self, real, fake, eps, out):
         e = eps.to(torch.float64)[:, None, None, None]

@@ -93,8 +93,48 @@ def _impl_for(mode, direction, case):
     Ho = (H + 2 * p - k) // s + 1
     lib = CudaOps("bf16").lib
     ok = (lib.sg_conv_wgrad_tc_supported(N, H, H, Ci, Ho, Ho, Co, k, s, p) if direction == 2
-          else lib.sg_conv_tc_supported(direction, N, H, H, Ci, Ho, Ho, Co, k, s, p))
+          else (lib.sg_conv_tc_supported(direction, N, H, H, Ci, Ho, Ho, Co, k, s, p) or
+                lib.sg_conv_thin_supported(direction, N, H, H, Ci, Ho, Ho, Co, k, s, p)))
     return "" if ok else "_ffma"
+
+
+# the 3-channel image side: direct kernels of thin_conv.cu behind sg_conv_fprop / sg_conv_dgrad (bf16 mode)
+THIN_CASES = [
+    # N, H (image side), Co
+    (3, 64, 64),        # Stage-I critic ds0 / its input gradient
+    (2, 128, 16),       # Stage-II critic ds0 (4 x 2 tiles per image)
+    (1, 256, 16),       # ... at full size
+    (2, 64, 24),        # G1 output layer (channels padded 24 -> 32 inside the transposed kernel)
+    (1, 128, 80),       # G2 output layer
+    (2, 64, 128),       # G2 ds0
+    (1, 64, 8),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", THIN_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True), (ACT_TANH, True)])
+def test_thin_conv_fprop_direct(case, act, use_bias):
+    N, H, Co = case
+    from imagegenerator_b200.ops import CudaOps
+    assert CudaOps("bf16").lib.sg_conv_thin_supported(0, N, H, H, 3, H // 2, H // 2, Co, 4, 2, 1)
+    x, w = rnd(N, H, H, 3), rnd(Co, 3, 4, 4, scale=48 ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    bias = F(rnd(Co)) if use_bias else None
+    run_pair("bf16", "conv_fprop", [T(x), T(pf), bias, T(torch.zeros(N, H // 2, H // 2, Co)), 4, 2, 1], [3], dict(act=act))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", THIN_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_TANH, True)])
+def test_thin_conv_dgrad_direct(case, act, use_bias):
+    N, H, Co = case
+    from imagegenerator_b200.ops import CudaOps
+    assert CudaOps("bf16").lib.sg_conv_thin_supported(1, N, H, H, 3, H // 2, H // 2, Co, 4, 2, 1)
+    dy, w = rnd(N, H // 2, H // 2, Co), rnd(Co, 3, 4, 4, scale=(Co * 4) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    bias = F(rnd(3)) if use_bias else None
+    run_pair("bf16", "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, 3)), 4, 2, 1], [3], dict(act=act))
 
 
 def test_bf16_dispatch_refuses_unsupported_shapes():
@@ -283,6 +323,39 @@ def test_head(mode, K, Cx, Nd):
     run_pair(mode, "head_param_grads", [F(rnd(16, Cx)), F(rnd(Nd)), F(rnd(1)), F(wcr), F(bcr), F(wcs),
                                         F(torch.zeros(K, Cx + Nd, 1, 1)), F(torch.zeros(K)), F(torch.zeros(1, K * 16)),
                                         F(torch.zeros(1))], [6, 7, 8, 9], tol=dict(rtol=1e-3, atol=1e-4))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("N", [7, 128])
+def test_ca_fused(mode, N):
+    """con_augment.py:13-22 in one launch / its backward in two, against the composition of the per-op statements."""
+    Tm, Hd, C, nz, ld = 512, 256, 128, 100, 256
+    tem, eps, z = rnd(N, Tm), rnd(N, C, seed=2), rnd(N, nz, seed=3)
+    Wh, bh = rnd(Hd, Tm, scale=Tm ** -0.5), rnd(Hd, seed=5, scale=0.1)
+    Wmu, bmu = rnd(C, Hd, seed=6, scale=Hd ** -0.5), rnd(C, seed=7, scale=0.1)
+    Wsg, bsg = rnd(C, Hd, seed=8, scale=Hd ** -0.5), rnd(C, seed=9, scale=0.1) + 1.0
+    z0 = lambda *sh: torch.zeros(*sh)
+    t = dict(rtol=1e-4, atol=1e-5)
+    ea, _ = run_pair(mode, "ca_forward", [F(tem), F(Wh), F(bh), F(Wmu), F(bmu), F(Wsg), F(bsg), F(eps), F(z), F(z0(N, Hd)),
+                                          F(z0(N, C)), F(z0(N, C)), F(z0(N, C)), T(torch.ones(N, 1, 1, ld))], [9, 10, 11, 12], tol=t)
+    run_pair(mode, "ca_forward", [F(tem), F(Wh), F(bh), F(Wmu), F(bmu), F(Wsg), F(bsg), F(eps), F(z), F(z0(N, Hd)),
+                                  F(z0(N, C)), F(z0(N, C)), F(z0(N, C)), T(torch.ones(N, 1, 1, ld))], [13])
+    # encode only (eps None), no generator row
+    run_pair(mode, "ca_forward", [F(tem), F(Wh), F(bh), F(Wmu), F(bmu), F(Wsg), F(bsg), None, None, F(z0(N, Hd)),
+                                  F(z0(N, C)), F(z0(N, C)), F(z0(N, C)), None], [9, 10, 11], tol=t)
+    h, mu, sigma = ea[9].float(), ea[10].float(), ea[11].float()
+    dcg = rnd(N, 1, 1, ld, seed=11)
+    g0 = lambda *sh: rnd(*sh, seed=13, scale=0.1)                    # gradients accumulate into non-zero buffers
+    for dtem_acc in (False, True):
+        run_pair(mode, "ca_backward", [T(dcg), F(eps), F(mu), F(sigma), 0.7, F(h), F(tem), F(Wmu), F(Wsg), F(Wh), F(z0(N, C)),
+                                       F(z0(N, C)), F(z0(N, Hd)), F(g0(C, Hd)), F(g0(C)), F(g0(C, Hd)), F(g0(C)), F(g0(Hd, Tm)),
+                                       F(g0(Hd)), F(g0(N, Tm)), dtem_acc], [10, 11, 12, 13, 14, 15, 16, 17, 18, 19],
+                 tol=dict(rtol=1e-4, atol=2e-5))
+    # Stage-II form: d loss / d c_hat given as fp32 [N, C], text side frozen (no dtem)
+    run_pair(mode, "ca_backward", [F(rnd(N, C, seed=12)), F(eps), F(mu), F(sigma), 0.0, F(h), F(tem), F(Wmu), F(Wsg), F(Wh),
+                                   F(z0(N, C)), F(z0(N, C)), F(z0(N, Hd)), F(g0(C, Hd)), F(g0(C)), F(g0(C, Hd)), F(g0(C)),
+                                   F(g0(Hd, Tm)), F(g0(Hd)), None, False], [10, 11, 12, 13, 14, 15, 16, 17, 18],
+             tol=dict(rtol=1e-4, atol=2e-5))
 
 
 @pytest.mark.parametrize("mode", MODES)

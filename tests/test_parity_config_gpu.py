@@ -19,7 +19,8 @@ Three numbers per tensor go into the report (gpurun_out/parity_<stage>_<mode>_B<
 
 A gradient bound cannot go vacuous silently: where the yardstick is claimed small (Stage-I in both modes, Stage-II in
 fp32) the test ASSERTS rel_l2(yardstick) < YARD_L2 for every gradient tensor before `3 x yardstick` counts as slack, and
-independently requires rel_l2(got) <= L2_FACTOR x rel_l2(yardstick) + L2_FLOOR.  Stage-II in bf16 is the one case where
+independently requires rel_l2(got) <= L2_FACTOR x rel_l2(yardstick) + L2_FLOOR (both taken without the max(1, numel/1000)
+largest-error elements -- mask flips, which the elementwise criterion bounds separately by OUTLIER_MAX).  Stage-II in bf16 is the one case where
 the yardstick is NOT small (measured: bf16 rounding of the FORWARD activations alone -- backward tensors kept exact --
 leaves the generator's gradients 0.3-0.9 away from fp64 in relative L2, the fp32 reference itself is 1e-2 away;
 profiles/exp_bf16_sensitivity_r2.txt): there the report says so, fp32 mode at the same batch is the numerical gate, and
@@ -120,8 +121,21 @@ def compare(mode, want, got, yard, tag, yard_small=True):
                 d[3] += (y * r).sum().item(); d[4] += (y * y).sum().item()
             if yard_small and yrel > YARD_L2:
                 fails.append(f"[{tag}] {k}: yardstick too coarse to judge with (rel_l2 {yrel:.2e} > {YARD_L2})")
-            if rel > L2_FACTOR[mode] * yrel + L2_FLOOR[mode]:
-                fails.append(f"[{tag}] {k}: rel_l2 {rel:.3e} > {L2_FACTOR[mode]} x yardstick {yrel:.3e} + {L2_FLOOR[mode]}")
+            # the L2 criterion is taken over all but the `allowed` largest-error elements of BOTH sides (the same elements the
+            # elementwise criterion sets aside as mask flips, bounded by OUTLIER_MAX there): one flipped element of a 512-element
+            # BatchNorm gradient is 80 % of that tensor's squared error, and whether the flip lands in the CUDA run or in the
+            # fp32 yardstick run is chance -- the untrimmed figure made this test pass or fail on the yardstick's own
+            # run-to-run noise (3.49e-3 against 3 x 1.008e-3 + 5e-4 one run, 3 x 8.88e-4 + 5e-4 the next)
+            allowed = max(1, r.numel() // 1000)
+            def trimmed(e):
+                if e.numel() <= allowed:
+                    return 0.0
+                e2 = e * e
+                return math.sqrt(max(e2.sum().item() - torch.topk(e2, allowed).values.sum().item(), 0.0)) / rn
+            rel_t, yrel_t = trimmed(g - r), (trimmed(y - r) if y is not None else 0.0)
+            if rel_t > L2_FACTOR[mode] * yrel_t + L2_FLOOR[mode]:
+                fails.append(f"[{tag}] {k}: rel_l2 {rel_t:.3e} (all elements: {rel:.3e}) > {L2_FACTOR[mode]} x yardstick "
+                             f"{yrel_t:.3e} + {L2_FLOOR[mode]}  [both without their {allowed} largest-error element(s)]")
         if worst_for_assert > 1.0:
             fails.append(f"[{tag}] {k}: max err / bound = {worst:.3f} (rel_l2 {rel:.3e}, yardstick {yrel:.3e})")
     for grp, (gr, gg, rr, yr, yy) in dots.items():

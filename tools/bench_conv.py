@@ -2,6 +2,7 @@
 
     python tools/bench_conv.py [filter-substring] [reps]
 
+Directions: fprop,dgrad,wgrad (default) and wgrad_cl (channels-last accumulation, the 3x3 residual convs' path).
 Each line: layer, direction, M x N x K of the implicit GEMM, mean time over ``reps`` launches with the L2
 flushed between launches (CUDA events on the launch stream), algorithmic TFLOP/s (2*M*N*K) and bytes/s
 of the compulsory traffic (each operand/result once)."""
@@ -17,6 +18,8 @@ from imagegenerator_b200.ops import CudaOps  # noqa: E402
 B1, B2 = 128, 64
 SHAPES = [
     ("s1.D1.ds0p", 3 * B1, 32, 48, 64, 1, 1, 0),
+    ("s1.D1.ds0", 3 * B1, 64, 3, 64, 4, 2, 1),
+    ("s1.G1.up4", B1, 64, 3, 24, 4, 2, 1),
     ("s1.D1.ds2", 3 * B1, 32, 64, 128, 4, 2, 1),
     ("s1.D1.ds3", 3 * B1, 16, 128, 256, 4, 2, 1),
     ("s1.D1.ds4", 3 * B1, 8, 256, 512, 4, 2, 1),
@@ -69,6 +72,11 @@ def main():
                 fn, M, Nn, K = (lambda: ops.conv_fprop(x, pf, None, y, k, s, p)), N * Ho * Ho, Co, Ci * k * k
             elif d == "dgrad":
                 fn, M, Nn, K = (lambda: ops.conv_dgrad(y, pd, None, x, k, s, p)), N * H * H, Ci, Co * k * k // (s * s)
+            elif d == "wgrad_cl":      # channels-last accumulation buffer (what engine2 uses for the 3x3 residual convs)
+                if not ops.conv_wgrad_cl_supported(x, y, k, s, p):
+                    continue
+                gw = torch.zeros(Co, k, k, Ci, device="cuda")
+                fn, M, Nn, K = (lambda: ops.conv_wgrad_cl(x, y, gw, k, s, p)), Co, Ci * k * k, N * Ho * Ho
             else:
                 fn, M, Nn, K = (lambda: ops.conv_wgrad(x, y, dw, k, s, p)), Co, Ci * k * k, N * Ho * Ho
             try:
