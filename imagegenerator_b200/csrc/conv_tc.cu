@@ -1504,7 +1504,11 @@ static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtens
 }
 
 int g_use_wgrad_mc = 1;
-int g_wgrad_mc_max = 5;      // option "wgrad_mc_max": largest cluster formed from all co tiles of a layer
+// option "wgrad_mc_max": largest co-tile cluster the launcher may pick.  The kernel takes 2..8; the default stays at PAIRS:
+// measured on B200 (profiles/bench_wgrad_r2c.txt, bench_wgrad_r2d.txt) clusters of 3-5 co tiles never beat unicast even when
+// the whole grid is co-resident (res1: 75.9 us as triples, 64.4 us unicast; res3 / up0 as quintuples 65.5 / 107.6 vs
+// 62.6 / 102.7) -- every stage then waits for the slowest of cs producers and is released by the slowest of cs consumers
+int g_wgrad_mc_max = 2;
 int g_wgrad_mc_odd = 1;      // option "wgrad_mc_odd": 0 = pairs only (the round-1 behaviour), for A/B measurements
 
 template <int PIX>

@@ -25,9 +25,21 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// activation of the thin kernels: tanh through the MUFU approximation like the tcgen05 epilogue (2^-11 relative error, below
+// the 2^-9 of the bf16 result; tanhf() was ~25 of the 100 instructions a thread spent per output pixel pair)
+template <int ACT>
+__device__ __forceinline__ float thin_act(float x) {
+    if (ACT == SG_ACT_TANH) {
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    return act_fwd(x, ACT);
+}
+
 // ------------------------------------------------------------------------------------------------ Conv2d(3 -> Co)
-// CTA = 8 x 32 output pixels of one image; warp w owns output row w (two 16-pixel m-tiles).  The 18 x 66-pixel input
-// tile sits in shared memory as 18 rows of C3_RS bf16, copied with 8-byte loads: element s of a row is element
+// CTA = 16 x 32 output pixels of one image; warp w owns output rows 2w, 2w+1 (two 16-pixel m-tiles each).  The 34 x 66-pixel input
+// tile sits in shared memory as 34 rows of C3_RS bf16, copied with 8-byte loads: element s of a row is element
 // 6*ow0 - 4 + s of the image row (a multiple of 4, so every 4-element chunk is aligned and lies wholly inside or outside
 // the row).  The 12 values (kw, ci) a tap row of output pixel p needs are s = 6p + 1 .. 6p + 12; the reduction is laid
 // out as K = 4 x 16: k = kh*16 + jj covers s = 6p + jj, with ZERO weights at jj = 0, 13, 14, 15 -- one k16 step per tap
@@ -35,7 +47,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 // (the first version gathered K = 48 exactly and spent its time on 2-byte copies and index arithmetic: 840 warp
 // instructions per warp, 1.7 IPC, 175 us on the Stage-II critic's first layer; ncu in profiles/).  Results are staged
 // per warp in shared memory and leave as 16-byte stores: a tile row's 32 pixels x Co channels are contiguous in NHWC.
-constexpr int C3_TH = 8, C3_TW = 32, C3_IR = 2 * C3_TH + 2, C3_RS = 208, C3_CH = 51, C3_WS = 72;
+constexpr int C3_RW = 2, C3_TH = 8 * C3_RW, C3_TW = 32, C3_IR = 2 * C3_TH + 2, C3_RS = 208, C3_CH = 51, C3_WS = 72;
 
 template <int ACT>
 __global__ void __launch_bounds__(256)
@@ -78,54 +90,57 @@ conv3_k4s2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp, const
         }
     }
     __syncthreads();
-    // A fragments of this warp's two m-tiles: k-step kh reads tile row 2*warp + kh, elements 6p + 2q (+1), 6p + 2q + 8 (+1)
-    uint32_t a[2][4][4];
-#pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-        const bf16* base = tile + (2 * warp + kh) * C3_RS + 2 * q;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int p0 = mt * 16 + g;
-            a[mt][kh][0] = *reinterpret_cast<const uint32_t*>(base + 6 * p0);
-            a[mt][kh][1] = *reinterpret_cast<const uint32_t*>(base + 6 * (p0 + 8));
-            a[mt][kh][2] = *reinterpret_cast<const uint32_t*>(base + 6 * p0 + 8);
-            a[mt][kh][3] = *reinterpret_cast<const uint32_t*>(base + 6 * (p0 + 8) + 8);
-        }
-    }
     bf16* stw = stage + warp * 32 * SS;
-    for (int nt = 0; nt < (Co >> 3); ++nt) {
-        const bf16* wr = wsm + (nt * 8 + g) * C3_WS + 2 * q;
-        uint32_t bf[4][2];
+    const int c8 = Co >> 3, total = 32 * c8;
+    const int row0 = lane / c8, col0 = lane - row0 * c8, drow = 32 / c8, dcol = 32 - drow * c8;
+#pragma unroll 1
+    for (int rr = 0; rr < C3_RW; ++rr) {
+        const int ohl = warp * C3_RW + rr;
+        // A fragments of this row's two m-tiles: k-step kh reads tile row 2*ohl + kh, elements 6p + 2q (+1), 6p + 2q + 8 (+1)
+        uint32_t a[2][4][4];
 #pragma unroll
         for (int kh = 0; kh < 4; ++kh) {
-            bf[kh][0] = *reinterpret_cast<const uint32_t*>(wr + kh * 16);
-            bf[kh][1] = *reinterpret_cast<const uint32_t*>(wr + kh * 16 + 8);
+            const bf16* base = tile + (2 * ohl + kh) * C3_RS + 2 * q;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int p0 = mt * 16 + g;
+                a[mt][kh][0] = *reinterpret_cast<const uint32_t*>(base + 6 * p0);
+                a[mt][kh][1] = *reinterpret_cast<const uint32_t*>(base + 6 * (p0 + 8));
+                a[mt][kh][2] = *reinterpret_cast<const uint32_t*>(base + 6 * p0 + 8);
+                a[mt][kh][3] = *reinterpret_cast<const uint32_t*>(base + 6 * (p0 + 8) + 8);
+            }
         }
-        float b0 = 0.f, b1 = 0.f;
-        if (bias != nullptr) { b0 = __ldg(bias + nt * 8 + 2 * q); b1 = __ldg(bias + nt * 8 + 2 * q + 1); }
+        for (int nt = 0; nt < c8; ++nt) {
+            const bf16* wr = wsm + (nt * 8 + g) * C3_WS + 2 * q;
+            uint32_t bf[4][2];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            float c[4] = {b0, b1, b0, b1};
+            for (int kh = 0; kh < 4; ++kh) {
+                bf[kh][0] = *reinterpret_cast<const uint32_t*>(wr + kh * 16);
+                bf[kh][1] = *reinterpret_cast<const uint32_t*>(wr + kh * 16 + 8);
+            }
+            float b0 = 0.f, b1 = 0.f;
+            if (bias != nullptr) { b0 = __ldg(bias + nt * 8 + 2 * q); b1 = __ldg(bias + nt * 8 + 2 * q + 1); }
 #pragma unroll
-            for (int kh = 0; kh < 4; ++kh) mma16816(c, a[mt][kh][0], a[mt][kh][1], a[mt][kh][2], a[mt][kh][3], bf[kh][0], bf[kh][1]);
+            for (int mt = 0; mt < 2; ++mt) {
+                float c[4] = {b0, b1, b0, b1};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = act_fwd(c[j], ACT);
-            *reinterpret_cast<uint32_t*>(stw + (mt * 16 + g) * SS + nt * 8 + 2 * q) = pack_bf16x2(c[0], c[1]);
-            *reinterpret_cast<uint32_t*>(stw + (mt * 16 + g + 8) * SS + nt * 8 + 2 * q) = pack_bf16x2(c[2], c[3]);
+                for (int kh = 0; kh < 4; ++kh) mma16816(c, a[mt][kh][0], a[mt][kh][1], a[mt][kh][2], a[mt][kh][3], bf[kh][0], bf[kh][1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[j] = thin_act<ACT>(c[j]);
+                *reinterpret_cast<uint32_t*>(stw + (mt * 16 + g) * SS + nt * 8 + 2 * q) = pack_bf16x2(c[0], c[1]);
+                *reinterpret_cast<uint32_t*>(stw + (mt * 16 + g + 8) * SS + nt * 8 + 2 * q) = pack_bf16x2(c[2], c[3]);
+            }
         }
-    }
-    __syncwarp();
-    // copy-out: the warp's 32 pixels x Co channels are one contiguous run of the NHWC output
-    {
-        const int c8 = Co >> 3, total = 32 * c8;
-        uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)(n * Ho + oh0 + warp) * Wo + ow0) * Co);
-        int row = lane / c8, col = lane - row * c8;
-        const int drow = 32 / c8, dcol = 32 - drow * c8;
+        __syncwarp();
+        // copy-out: the row's 32 pixels x Co channels are one contiguous run of the NHWC output
+        uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)(n * Ho + oh0 + ohl) * Wo + ow0) * Co);
+        int row = row0, col = col0;
         for (int j = lane; j < total; j += 32) {
             dst[j] = *reinterpret_cast<const uint4*>(stw + row * SS + col * 8);
             row += drow; col += dcol;
             if (col >= c8) { col -= c8; ++row; }
         }
+        __syncwarp();                  // the staging rows are rewritten by the next output row
     }
 }
 
@@ -254,9 +269,9 @@ convt3_k4s2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ pd, cons
                              (rB[(kh1 * 4 + 2) * 3 + c] + rB[(kh1 * 4 + 0) * 3 + c + CT_CS]));
         }
         uint32_t* o = reinterpret_cast<uint32_t*>(obase + (size_t)ohl * Wo * 3);
-        o[0] = pack_bf16x2(act_fwd(s0[0], ACT), act_fwd(s0[1], ACT));
-        o[1] = pack_bf16x2(act_fwd(s0[2], ACT), act_fwd(s1[0], ACT));
-        o[2] = pack_bf16x2(act_fwd(s1[1], ACT), act_fwd(s1[2], ACT));
+        o[0] = pack_bf16x2(thin_act<ACT>(s0[0]), thin_act<ACT>(s0[1]));
+        o[1] = pack_bf16x2(thin_act<ACT>(s0[2]), thin_act<ACT>(s1[0]));
+        o[2] = pack_bf16x2(thin_act<ACT>(s1[1]), thin_act<ACT>(s1[2]));
     }
 }
 

@@ -451,11 +451,11 @@ class CriticRT:
         ops, L0 = self.ops, self.layers[0]
         ops.conv_dgrad(dy0, L0.pd, None, dx, L0.k, L0.s, L0.p)
 
-    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, on_layer_done=None, head_reduce=True,
-                 input_grad_from=None, side=None):
+    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, head_reduce=True, input_grad_from=None, side=None):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
-        d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).
-        ``on_layer_done(l)`` is called once the parameter gradients of conv layer l are final."""
+        d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).  ``coef`` holds the ng*B
+        coefficients of these groups.  Groups are independent (own BN statistics, disjoint buffer slices; parameter gradients
+        accumulate with atomic adds), so two calls on disjoint groups may run on different streams."""
         ops, nl = self.ops, self.nl
         gv = lambda t: self.group_view(t, g0, ng)
         a4 = gv(self.a[nl])
@@ -474,8 +474,6 @@ class CriticRT:
                     ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
                     ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p)
                 _side_run(side, pgrad)
-                if on_layer_done is not None:
-                    on_layer_done(l)
             ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
         L0 = self.layers[0]
         dy0 = gv(self.dy[0])
@@ -655,35 +653,21 @@ class Stage1Engine:
         if comm is not None:
             for fp in (self.d.fp, self.g.fp, self.ca.fp):
                 comm.broadcast_params(fp.flat)       # train.py:78-85
-            # critic bucket boundary: everything from the LAST conv layer's weight to the end of the flat
-            # buffer (ds4/ds6 weight + its BN + compress + channel_resize + critic_score) is final first
-            first_tail, off = self.d.layers[-1].conv.weight, 0
-            for p in self.d.fp.params:
-                if p is first_tail:
-                    break
-                off += p.numel()
-            self.d_tail_off = off
         self.real_nchw = None
-        # Handing the tail of the critic's gradient to NCCL while the trunk backward still runs was measured to HURT on
-        # B200 (2 GPUs: 12.7-20.8 ms/step vs 10.7 ms with one all-reduce per optimizer step): the persistent conv kernels
-        # want all 148 SMs, and an NCCL kernel that holds a few of them while it waits for its peer stalls whole tile
-        # waves.  Default: one all-reduce right before each Adam step; SG_EARLY_BUCKET=1 restores the overlap.
-        self.early_bucket = os.environ.get("SG_EARLY_BUCKET") == "1"
         self.refresh_all()
 
     def refresh_all(self):
         self.d.refresh_weights()
         self.g.refresh_weights()
 
-    def optimizer_step(self, fp, already_reduced=0):
-        """xm.optimizer_step: average gradients over replicas, then Adam.  ``already_reduced`` = offset
-        from which the flat buffer has been handed to the communicator by the backward pass."""
+    def optimizer_step(self, fp):
+        """xm.optimizer_step (stage_1_train_fn.py:149,166,172): average gradients over replicas, then Adam."""
         self.side.join()
         if self.comm is not None and self.comm.peer:
             self.comm.step(fp)               # reduce-scatter + Adam + all-gather over peer memory, one kernel, in the graph
             return
         if self.comm is not None:
-            self._comm_allreduce(fp.grad[:already_reduced] if already_reduced > 0 else fp.grad)
+            self._comm_allreduce(fp.grad)
             self._comm_wait()
         elif self.allreduce is not None:
             self.allreduce(fp.grad)
@@ -752,20 +736,16 @@ class Stage1Engine:
         d.gp_first_order()                                       # utils.py:15-24
         ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])   # :140-144
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
-        # head/text gradients first (dA is complete once the plain backward has added its head term), so
-        # that the tail of the flat gradient buffer can go to NCCL while the trunk backward still runs
+        # head/text gradients first (dA is complete once the plain backward has added its head term)
         ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA)
         self.side.run(lambda: d.text_backward(d.coef_text, 2 * B, 0.0, True, None))
-        tail = [0]
-
-        def bucket(l):
-            if self.comm is not None and not self.comm.peer and l == d.nl - 1 and self.early_bucket:
-                self.side.join()
-                self._comm_allreduce(d.fp.grad[self.d_tail_off:])
-                tail[0] = self.d_tail_off
+        # One batched backward over all three groups.  Running the gradient-penalty chain (one group) and the interpolated
+        # group's backward on a second stream next to a two-group backward was measured and REJECTED (B200, round 2:
+        # Stage-I 5.56 -> 5.98 ms, Stage-II 34.6 -> 36.1 ms, 508 -> 603 launches): the persistent conv kernels take every SM
+        # they can get, so the two chains do not really overlap, and every split launch pays its fixed ~10 us again.
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
-                   on_layer_done=bucket, head_reduce=False, side=self.side)
-        self.optimizer_step(d.fp, already_reduced=tail[0])       # :149
+                   head_reduce=False, side=self.side)
+        self.optimizer_step(d.fp)                                # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
         self.pack_side.run(lambda: d.refresh_weights(with_text=True))
         self._ce_ready = True                                    # until the text changes (load_batch / next outer step)

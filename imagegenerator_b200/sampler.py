@@ -159,6 +159,41 @@ class StackGANSampler:
         ops.nhwc_to_nchw(self.fake_64, self.out_64)
         ops.nhwc_to_nchw(self.fake_256, self.out_256)
 
+    def sample_to_host(self, tem, z, eps_ca1, eps_ca2, host_256, host_64=None):
+        """``sample`` + the device-to-host copy of the images, off the compute stream: the batch is generated by the graph
+        replay, parked in one of two device staging buffers (a 50 MB device-to-device copy, ~35 us) and sent to the
+        caller's PINNED host tensors over a copy stream while the next batch is already being generated.  Returns a CUDA
+        event; ``event.synchronize()`` (or a stream wait) before the host tensors are read.  Without this the 50 MB
+        fp32 read-back of a 64-image batch sat on the compute stream and halved the end-to-end rate."""
+        dev = self.ops.device
+        if getattr(self, "_d2h_stream", None) is None:
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+            self._park = [(torch.empty_like(self.out_64), torch.empty_like(self.out_256)) for _ in range(2)]
+            self._park_free = [None, None]
+            self._park_i = 0
+        assert host_256.is_pinned() and (host_64 is None or host_64.is_pinned()), "host buffers must be pinned"
+        out_64, out_256 = self.sample(tem, z, eps_ca1, eps_ca2)
+        i = self._park_i
+        self._park_i ^= 1
+        cur = torch.cuda.current_stream(dev)
+        if self._park_free[i] is not None:
+            cur.wait_event(self._park_free[i])                  # the copy that last read this staging pair has finished
+        p64, p256 = self._park[i]
+        p256.copy_(out_256, non_blocking=True)
+        if host_64 is not None:
+            p64.copy_(out_64, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(ready)
+            host_256.copy_(p256, non_blocking=True)
+            if host_64 is not None:
+                host_64.copy_(p64, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._d2h_stream)
+        self._park_free[i] = done
+        return done
+
     def sample(self, tem, z, eps_ca1, eps_ca2, use_graph=True):
         """tem [B,512], z [B,100], eps_ca1/eps_ca2 [B,128] (host or device, fp32) -> (fake_64 [B,3,64,64],
         fake_256 [B,3,256,256]) fp32 NCHW device tensors (static buffers, overwritten by the next call)."""

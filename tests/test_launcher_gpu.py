@@ -83,3 +83,94 @@ def test_stage1_on_captions_with_a_bert_encoder(tmp_path):
     assert torch.isfinite(eng2.losses).all()
     for k, v in m2["textEncoder"].state_dict().items():                       # restored from the Stage-I checkpoint
         assert torch.equal(v.cpu(), ck["textEncoder"][k]), k
+
+
+def test_checkpoints_cross_the_boundary_to_and_from_the_unmodified_reference(tmp_path):
+    """f2, both directions, against the REAL reference (oracle/ref_harness.py runs it on CPU under stubs):
+
+    1. the unmodified ``train_1`` (stage_1_train_fn.py:19-238) trains one epoch and writes its checkpoint into the (fake)
+       bucket; those bytes, dropped where this package's ``train_1`` looks, must resume it: epoch counter, every weight and
+       BatchNorm buffer bit-identical, the fused Adam's moments and step counts taken over from the reference's
+       ``torch.optim.Adam`` state (:55-82), and training continues from there with finite losses;
+    2. the checkpoint THIS package then writes must load into the reference's own modules and optimizers with strict
+       ``load_state_dict`` (:63-73) -- a user can go back."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import ref_harness as H
+    if not H.reference_available():
+        pytest.skip("neither /root/reference nor oracle/_ref/reference_src.zip is here")
+    from imagegenerator_b200.con_augment import ConditioningAugmentation
+    from imagegenerator_b200.discrminator_1 import StageIDiscriminator
+    from imagegenerator_b200.engine import Stage1Engine
+    from imagegenerator_b200.generator_1 import StageIGenerator
+    from imagegenerator_b200.ops import CudaOps
+    from imagegenerator_b200.stage_1_train_fn import train_1
+
+    B, dev = 4, torch.device("cuda:0")
+    mk = lambda m, lr=1e-3: torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.999))
+    sched = lambda opts: [torch.optim.lr_scheduler.StepLR(o, step_size=100, gamma=0.5) for o in opts]
+    table = torch.randn(B, 512, generator=torch.Generator().manual_seed(3))
+    real = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(4)).clamp_(-1, 1)
+    loader = [({"idx": torch.arange(B)}, real), ({"idx": torch.arange(B)}, real.flip(0))]
+
+    # ---- 1. the reference writes
+    H.reset_store()
+    torch.manual_seed(11)
+    r_ca = H.load("con_augment").ConditioningAugmentation(512, 256, 128)
+    r_d1 = H.load("discrminator_1").StageIDiscriminator(512, 128)
+    r_g1 = H.load("generator_1").StageIGenerator(128, 100)
+    r_enc, r_head = H.TableEncoder(table), H.IdentityHead()
+    r_opts = [mk(r_enc, 0.0), mk(r_head, 0.0), mk(r_ca), mk(r_d1), mk(r_g1)]
+    with H.quiet():
+        H.load("stage_1_train_fn").train_1([r_enc, r_head, r_ca, r_d1, r_g1], r_opts, sched(r_opts), loader, 1, "cpu", B)
+    blob = H.store()["./checkpoints/Stage1/latest_checkpoint_stage1.pth"]
+    save = str(tmp_path / "Stage1")
+    os.makedirs(save)
+    with open(os.path.join(save, "latest_checkpoint_stage1.pth"), "wb") as f:
+        f.write(blob)
+    ck = torch.load(os.path.join(save, "latest_checkpoint_stage1.pth"), map_location="cpu", weights_only=False)
+    assert ck["epoch"] == 0 and float(ck["opt_critic_1"]["state"][0]["step"]) == 10.0      # 2 batches x 5 critic steps
+
+    # ---- ... and this package resumes from it (differently initialised modules: everything must come from the file)
+    torch.manual_seed(99)
+    ca, d1, g1 = ConditioningAugmentation(512, 256, 128), StageIDiscriminator(512, 128), StageIGenerator(128, 100)
+    enc, head = H.TableEncoder(torch.zeros(B, 512)).to(dev), H.IdentityHead().to(dev)
+    opts = [mk(enc, 0.0), mk(head, 0.0), mk(ca), mk(d1), mk(g1)]
+    eng = Stage1Engine(ca, d1, g1, B, ops=CudaOps("fp32"))
+    logs = []
+    train_1([enc, head, ca, d1, g1], opts, sched(opts), loader, 1, dev, B, save_dir=save, log=logs.append, engine=eng,
+            use_graph=False)                                    # epochs=1: resume only, nothing left to train
+    assert any("Loaded checkpoint at epoch 0" in l for l in logs)
+    for ours, key in ((ca, "con_augment_1"), (d1, "critic_1"), (g1, "gen_1"), (enc, "textEncoder")):
+        for k, v in ours.state_dict().items():
+            assert torch.equal(v.cpu(), ck[key][k]), (key, k)
+    for fp, key, steps in ((eng.d.fp, "opt_critic_1", 10.0), (eng.g.fp, "opt_gen_1", 2.0), (eng.ca.fp, "opt_con_augment_1", 2.0)):
+        st = ck[key]["state"]
+        assert float(fp.hyper[4]) == steps, (key, float(fp.hyper[4]))
+        m = torch.cat([st[i]["exp_avg"].reshape(-1) for i in range(len(st))])
+        v = torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in range(len(st))])
+        assert torch.equal(fp.m.cpu()[:m.numel()], m) and torch.equal(fp.v.cpu()[:v.numel()], v), key
+    # the packed bf16/fp32 operands were refreshed from the loaded weights: one more epoch trains on from here
+    w_before = d1.down_sampler[2][0].weight.detach().clone()
+    train_1([enc, head, ca, d1, g1], opts, sched(opts), loader, 11, dev, B, save_dir=save, log=logs.append, engine=eng,
+            use_graph=False)                                    # epochs 1..10; epoch 10 writes a checkpoint (:211)
+    assert sum("Loss D" in l for l in logs) == 20 and all("nan" not in l.lower() for l in logs)
+    assert not torch.equal(w_before, d1.down_sampler[2][0].weight.detach())
+
+    # ---- 2. this package writes, the reference reads
+    ck2 = torch.load(os.path.join(save, "latest_checkpoint_stage1.pth"), map_location="cpu", weights_only=False)
+    assert ck2["epoch"] == 10 and set(ck2) == set(ck)
+    torch.manual_seed(5)
+    r_ca2 = H.load("con_augment").ConditioningAugmentation(512, 256, 128)
+    r_d12 = H.load("discrminator_1").StageIDiscriminator(512, 128)
+    r_g12 = H.load("generator_1").StageIGenerator(128, 100)
+    r_ca2.load_state_dict(ck2["con_augment_1"])                 # strict
+    r_d12.load_state_dict(ck2["critic_1"])
+    r_g12.load_state_dict(ck2["gen_1"])
+    for m, key in ((r_ca2, "opt_con_augment_1"), (r_d12, "opt_critic_1"), (r_g12, "opt_gen_1")):
+        o = mk(m)
+        o.load_state_dict(ck2[key])
+        st = o.state_dict()["state"]
+        assert len(st) == len(list(m.parameters())) and float(st[0]["step"]) == float(ck2[key]["state"][0]["step"])
+    assert float(ck2["opt_critic_1"]["state"][0]["step"]) == 10.0 + 10 * 2 * 5
+    assert int(ck2["critic_1"]["down_sampler.2.1.num_batches_tracked"]) == 11 * 2 * 21       # :125-154: 21 BN passes per batch
