@@ -30,6 +30,11 @@ int sg_conv_fprop_tc_f32out(const void*, const void*, float*, int, int, int, int
 int sg_conv_fprop_tc_res(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, int,
                          int, int, void*);
 int sg_add_act(const void*, const void*, void*, int64_t, int, int, void*);
+int sg_conv_fprop_tc_bstats(const void*, const void*, void*, const void*, const float*, const float*, const float*, double*, int, int,
+                            int, int, int, int, int, int, int, int, int, int, void*);
+int sg_conv_dgrad_tc_bstats(const void*, const void*, void*, const void*, const float*, const float*, const float*, double*, int, int,
+                            int, int, int, int, int, int, int, int, int, int, void*);
+int sg_bn_bwd_reduce_y(const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, int, void*);
 int sg_conv_thin_supported(int, int, int, int, int, int, int, int, int, int, int);
 int sg_conv_thin_fprop(const void*, const void*, const float*, void*, int, int, int, int, int, void*);
 int sg_conv_thin_dgrad(const void*, const void*, const float*, void*, int, int, int, int, int, void*);
@@ -88,6 +93,28 @@ int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats,
     int e = sg_conv_dgrad(dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;
     return sg_col_stats(dx, stats, (int64_t)(N / groups) * H * W, Ci, groups, dtype, stream);
+}
+
+// y = conv(x, W) is d loss / d a of the BatchNorm'ed layer below (a = act(bn(ybn))): also reduce that layer's backward
+// statistics sums[groups][Co][2] = (sum dz, sum dz * xhat) -- in the tensor-core epilogue when the shape allows (bf16), otherwise
+// conv + sg_bn_bwd_reduce_y.  act in {none, relu, lrelu}; Co % 8 == 0.
+int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
+                         const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, int dtype, void* stream) {
+    if (dtype == SG_BF16 && Co <= 256 * 8 && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+        return sg_conv_fprop_tc_bstats(x, pf, y, ybn, mr, gamma, beta, sums, groups, act, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
+    int e = sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
+    if (e) return e;
+    return sg_bn_bwd_reduce_y(y, ybn, mr, gamma, beta, sums, (int64_t)(N / groups) * Ho * Wo, Co, groups, act, dtype, stream);
+}
+int sg_conv_dgrad_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
+                         const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, int dtype, void* stream) {
+    if (dtype == SG_BF16 && sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+        return sg_conv_dgrad_tc_bstats(dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
+    int e = sg_conv_dgrad(dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
+    if (e) return e;
+    return sg_bn_bwd_reduce_y(dx, ybn, mr, gamma, beta, sums, (int64_t)(N / groups) * H * W, Ci, groups, act, dtype, stream);
 }
 
 // y (fp32) = conv(x, W): same operands as sg_conv_fprop, result kept in fp32 (no activation / bias).  In fp32 storage

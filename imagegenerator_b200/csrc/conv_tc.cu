@@ -290,6 +290,14 @@ struct TcpParams {
     float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
     const bf16* residual; // added before the activation (same layout as out) or NULL
     unsigned long long* trace;   // profiling hook (sg_debug_conv_trace): 16 globaltimer stamps per CTA, or NULL
+    // BatchNorm-BACKWARD statistics fused into the epilogue (sg_conv_*_bstats): this launch's result is da = d loss / d a of
+    // the layer below, a = act(bn(y)); with bs_y != NULL `stats` receives (S1, S2) = (sum dz, sum dz * xhat) per (group, channel),
+    // dz = da * act'(gamma * xhat + beta), xhat = (y - mean) * rstd -- what sg_bn_bwd_reduce_y computes in a pass of its own
+    const bf16* bs_y;            // pre-BN tensor of that layer, same layout as `out`
+    const float* bs_mr;          // [groups][n_total][2] mean, rstd
+    const float* bs_gamma;
+    const float* bs_beta;
+    float bs_slope;              // activation slope for negative pre-activations (0 ReLU, 0.1 LeakyReLU, 1 none)
     SlabEnt slab[4][16];
 };
 
@@ -392,6 +400,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint32_t tmem_slot;
     __shared__ float sstat[2][256][2];          // statistics staging, double-buffered by tile parity
     __shared__ uint4 sstage[TCP_EPI_WARPS][32 * 4];   // per epilogue warp: 32 rows x 64 B, for the coalesced store
+    __shared__ float4 sconst[256];              // backward statistics: (mean, rstd*gamma, beta, rstd) of the tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -607,6 +616,20 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             bf16* orow = P.out + (int64_t)((n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
             const int ncols = min(w.width, P.n_total - nt0);          // valid columns of this work item
             const uint32_t sb2 = ti & 1;           // statistics staging buffer
+            const bool bwd = P.bs_y != nullptr;
+            if (bwd) {
+                // per-column constants of this tile's image group; the bar.sync that closed the previous tile guarantees that
+                // no warp still reads the previous tile's table
+                if (et < ncols) {
+                    const int c = nt0 + et;
+                    const float* mq = P.bs_mr + ((int64_t)(n0 / P.imgs_per_group) * P.n_total + c) * 2;
+                    const float mean = __ldg(mq), rstd = __ldg(mq + 1);
+                    sconst[et] = make_float4(mean, rstd * __ldg(P.bs_gamma + c), __ldg(P.bs_beta + c), rstd);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const bf16* yrow = bwd ? P.bs_y + (int64_t)((n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0 : nullptr;
+            const float slope = P.bs_slope;
             if (P.kiters >= 8) mbar_wait_backoff(&tfull_bar[ab], abpar);     // long mainloop: sleep between polls
             else mbar_wait(&tfull_bar[ab], abpar);                          // short tiles: the sleep would be the latency
             tc_fence_after();
@@ -697,6 +720,19 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         f[2 * j] = row_ok ? __uint_as_float(pk[j] << 16) : 0.f;
                         f[2 * j + 1] = row_ok ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
                     }
+                    if (bwd) {
+                        // f = da (as stored); turn it into dz and pair it with xhat
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float yv = 0.f;
+                            if (row_ok && c0 + j < ncols) yv = __bfloat162float(yrow[c0 + j]);
+                            const float4 cst = sconst[min(c0 + j, 255)];
+                            const float t = yv - cst.x;
+                            const float dz = (t * cst.y + cst.z > 0.f) ? f[j] : slope * f[j];
+                            f[j] = (c0 + j < ncols) ? dz : 0.f;
+                            sq[j] = f[j] * (t * cst.w);
+                        }
+                    } else
 #pragma unroll
                     for (int j = 0; j < 16; ++j) sq[j] = f[j] * f[j];
                     warp_colsum16(f, lane);
@@ -770,6 +806,17 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (has_stats) {
                         const bool ok = n_img < P.n_img;
+                        uint32_t yk[16];
+                        if (bwd) {
+                            // the row's 32 pre-BN values (64 contiguous bytes per lane)
+                            uint4 y0 = make_uint4(0u, 0u, 0u, 0u), y1 = y0, y2 = y0, y3 = y0;
+                            if (ok) {
+                                const uint4* yp = reinterpret_cast<const uint4*>(yrow + c0);
+                                y0 = __ldg(yp); y1 = __ldg(yp + 1); y2 = __ldg(yp + 2); y3 = __ldg(yp + 3);
+                            }
+                            yk[0] = y0.x; yk[1] = y0.y; yk[2] = y0.z; yk[3] = y0.w; yk[4] = y1.x; yk[5] = y1.y; yk[6] = y1.z; yk[7] = y1.w;
+                            yk[8] = y2.x; yk[9] = y2.y; yk[10] = y2.z; yk[11] = y2.w; yk[12] = y3.x; yk[13] = y3.y; yk[14] = y3.z; yk[15] = y3.w;
+                        }
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
                             float a[16], sq[16];
@@ -778,6 +825,17 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 a[2 * j] = ok ? __uint_as_float(pk[h2 * 8 + j] << 16) : 0.f;
                                 a[2 * j + 1] = ok ? __uint_as_float(pk[h2 * 8 + j] & 0xffff0000u) : 0.f;
                             }
+                            if (bwd) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const uint32_t w2 = yk[h2 * 8 + (j >> 1)];
+                                    const float yv = __uint_as_float((j & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
+                                    const float4 cst = sconst[c0 + h2 * 16 + j];
+                                    const float t = yv - cst.x;
+                                    a[j] = (t * cst.y + cst.z > 0.f) ? a[j] : slope * a[j];
+                                    sq[j] = a[j] * (t * cst.w);
+                                }
+                            } else
 #pragma unroll
                             for (int j = 0; j < 16; ++j) sq[j] = a[j] * a[j];
                             warp_colsum16(a, lane);
@@ -1255,7 +1313,7 @@ int g_rotate = 0;        // option "rotate": measured neutral on B200 (gpurun_ou
 // alternate-tile epilogue for narrow tiles (option "epi_alt" / env SG_EPI_ALT)
 int g_epi_alt = getenv("SG_EPI_ALT") ? atoi(getenv("SG_EPI_ALT")) : 1;
 static bool g_pattr_set = false;
-constexpr int TCP_SMEM_BYTES = 205 * 1024;
+constexpr int TCP_SMEM_BYTES = 201 * 1024;      // + ~24 KB static (statistics staging, store transposes, BN constants) <= 227 KB
 
 // column slices for the leftover tiles of the last round: returns S (1 = none) and the slice width
 static int nsplit_plan(long tiles, int units, int bn, int cg, int* bn2) {
@@ -1317,9 +1375,13 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, double a_sh
 
 // mode 0: fprop (act = x [N][H][W][Ck], out = y [N][Ho][Wo][n_total]);
 // mode 1: dgrad (act = dy [N][Ho][Wo][Ck], out = dx [N][H][W][n_total])
+struct BsArgs {            // BatchNorm-backward statistics in the epilogue (TcpParams::bs_*)
+    const void* y; const float* mr; const float* gamma; const float* beta; float slope;
+};
+
 static int launch_conv_tcp(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
                            int Ci, int Ho, int Wo, int Co, int k, int s, int p, int actf, double* stats, int groups,
-                           cudaStream_t st, float* out32 = nullptr, const void* residual = nullptr) {
+                           cudaStream_t st, float* out32 = nullptr, const void* residual = nullptr, const BsArgs* bs = nullptr) {
     int e = ensure_encode();
     if (e) return e;
     static TcpParams Pz;        // zero-initialised template (the slab table has padding the compiler would not clear)
@@ -1344,6 +1406,7 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     P.stats = stats;
     P.out32 = out32;
     P.residual = (const bf16*)residual;
+    if (bs != nullptr) { P.bs_y = (const bf16*)bs->y; P.bs_mr = bs->mr; P.bs_gamma = bs->gamma; P.bs_beta = bs->beta; P.bs_slope = bs->slope; }
     P.trace = g_trace;
     if (out32) P.out = nullptr;
     P.imgs_per_group = groups > 0 ? N / groups : N;
@@ -1759,6 +1822,32 @@ int sg_conv_dgrad_tc_stats(const void* dy, const void* pd, void* dx, double* sta
     SG_REQUIRE(sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups), "conv_dgrad_tc_stats: unsupported shape");
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc_stats: inconsistent sizes");
     return launch_conv_tcp(1, dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, stats, groups, SG_STREAM(stream));
+}
+
+// conv + the BatchNorm-BACKWARD statistics of the layer below in the epilogue: the result da (T) is d loss / d a for
+// a = act(bn(ybn)); sums[groups][C][2] (zeroed here) += (sum dz, sum dz * xhat), dz = da * act'(gamma * xhat + beta).  Replaces the
+// sg_bn_bwd_reduce_y pass over (da, ybn) that followed every data-gradient conv of a BatchNorm'ed layer.
+static float bs_slope_of(int act) { return act == SG_ACT_RELU ? 0.f : act == SG_ACT_LRELU ? 0.1f : 1.f; }
+int sg_conv_fprop_tc_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
+                            const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo,
+                            int Co, int k, int s, int p, void* stream) {
+    SG_REQUIRE(sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups) && Co <= 2048, "conv_fprop_tc_bstats: unsupported shape");
+    SG_REQUIRE(act == SG_ACT_NONE || act == SG_ACT_RELU || act == SG_ACT_LRELU, "conv_fprop_tc_bstats: act in {none, relu, lrelu}");
+    cudaMemsetAsync(sums, 0, (size_t)groups * Co * 2 * sizeof(double), SG_STREAM(stream));
+    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act)};
+    return launch_conv_tcp(0, x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, sums, groups, SG_STREAM(stream), nullptr,
+                           nullptr, &bs);
+}
+int sg_conv_dgrad_tc_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
+                            const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo,
+                            int Co, int k, int s, int p, void* stream) {
+    SG_REQUIRE(sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups) && Ci <= 2048, "conv_dgrad_tc_bstats: unsupported shape");
+    SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc_bstats: inconsistent sizes");
+    SG_REQUIRE(act == SG_ACT_NONE || act == SG_ACT_RELU || act == SG_ACT_LRELU, "conv_dgrad_tc_bstats: act in {none, relu, lrelu}");
+    cudaMemsetAsync(sums, 0, (size_t)groups * Ci * 2 * sizeof(double), SG_STREAM(stream));
+    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act)};
+    return launch_conv_tcp(1, dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, sums, groups, SG_STREAM(stream), nullptr,
+                           nullptr, &bs);
 }
 
 }  // extern "C"

@@ -409,6 +409,30 @@ __global__ void bn_param_grad_kernel(const double* sums, float* dgamma, float* d
     dbeta[c] += (float)s1;
 }
 
+// the same for every BatchNorm layer of a network in ONE launch (blockIdx.y = layer): a backward pass used to end in one tiny
+// launch per layer (20 per Stage-I step, 121 per Stage-II step)
+constexpr int BN_PG_MAX = 24;
+struct BnParamGradArgs {
+    const double* sums[BN_PG_MAX];
+    float* dgamma[BN_PG_MAX];
+    float* dbeta[BN_PG_MAX];
+    int G[BN_PG_MAX], C[BN_PG_MAX];
+};
+__global__ void bn_param_grad_multi_kernel(const BnParamGradArgs A) {
+    SG_PDL_SYNC();
+    const int l = blockIdx.y, C = A.C[l], G = A.G[l];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double* sums = A.sums[l];
+    double s1 = 0, s2 = 0;
+    for (int g = 0; g < G; ++g) {
+        s1 += sums[((int64_t)g * C + c) * 2];
+        s2 += sums[((int64_t)g * C + c) * 2 + 1];
+    }
+    A.dgamma[l][c] += (float)s2;
+    A.dbeta[l][c] += (float)s1;
+}
+
 // ---- layout
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* src, T* dst, int N, int C, int64_t HW) {
@@ -1107,6 +1131,20 @@ int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const floa
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream) {
     launch_pdl(bn_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, SG_STREAM(stream), sums, dgamma, dbeta, groups, C);
     SG_LAUNCHED("bn_param_grad");
+    return 0;
+}
+
+int sg_bn_param_grad_multi(const double* const* sums, float* const* dgamma, float* const* dbeta, const int* groups, const int* C,
+                           int n_layers, void* stream) {
+    SG_REQUIRE(n_layers >= 1 && n_layers <= BN_PG_MAX, "bn_param_grad_multi: 1..%d layers per launch", BN_PG_MAX);
+    BnParamGradArgs A;
+    int cmax = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        A.sums[l] = sums[l]; A.dgamma[l] = dgamma[l]; A.dbeta[l] = dbeta[l]; A.G[l] = groups[l]; A.C[l] = C[l];
+        if (C[l] > cmax) cmax = C[l];
+    }
+    launch_pdl(bn_param_grad_multi_kernel, dim3((cmax + 127) / 128, n_layers), dim3(128), 0, SG_STREAM(stream), A);
+    SG_LAUNCHED("bn_param_grad_multi");
     return 0;
 }
 

@@ -281,6 +281,7 @@ class GenRT:
             ops.conv_wgrad(self.Pd, self.a[-1], last.conv.weight.grad.view(last.co, self.K_last, 1, 1), 1, 1, 0)
         _side_run(side, pgrad_last)
         ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
+        bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
             ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,
@@ -289,8 +290,9 @@ class GenRT:
                              self.dy[i], 1, ACT_RELU, beta=bn.bias.data)
             x_in = self.a[i - 1] if i > 0 else self.cg
 
+            bn_items.append((self.sums[i], bn.weight.grad, bn.bias.grad))
+
             def pgrad(i=i, L=L, bn=bn, x_in=x_in):
-                ops.bn_param_grad(self.sums[i], bn.weight.grad, bn.bias.grad)
                 if i == 0:
                     self.up0.weight_grad(x_in, self.dy[0])
                 else:
@@ -300,6 +302,7 @@ class GenRT:
                 self.up0.input_grad(self.dy[0], self.dcg)
             else:
                 ops.conv_fprop(self.dy[i], L.pf, None, self.da[i - 1], L.k, L.s, L.p)
+        _side_run(side, lambda: ops.bn_param_grad_multi(bn_items))
         return self.dcg
 
 
@@ -462,6 +465,7 @@ class CriticRT:
         ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
         if param_grads and head_reduce:
             ops.head_bwd_reduce(coef, a4, self.dA)
+        bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
@@ -470,16 +474,15 @@ class CriticRT:
             ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
                              inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data)
             if param_grads:
-                def pgrad(l=l, L=L, bn=bn, sums=sums, dy=dy):
-                    ops.bn_param_grad(sums, bn.weight.grad, bn.bias.grad)
-                    ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p)
-                _side_run(side, pgrad)
+                bn_items.append((sums, bn.weight.grad, bn.bias.grad))
+                _side_run(side, lambda l=l, L=L, dy=dy: ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p))
             ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
         L0 = self.layers[0]
         dy0 = gv(self.dy[0])
         ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU)
         if param_grads:
             def pgrad0():
+                ops.bn_param_grad_multi(bn_items)
                 ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
                 ops.colsum(dy0, L0.conv.bias.grad)
             _side_run(side, pgrad0)

@@ -53,14 +53,18 @@ def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=Non
         ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
 
-def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True):
+def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=None):
     """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads.  ``from_y``: the activation follows
     the BN directly, so the kernels take its sign from y and do not stream a_out (False for the layer that closes a
-    residual block, whose ReLU sees bn(y) + identity)."""
+    residual block, whose ReLU sees bn(y) + identity).  ``bn_items``: list collecting (sums, gamma.grad, beta.grad) instead of
+    launching the per-layer parameter-gradient kernel."""
     gb = dict(gamma=bn.weight.data, beta=bn.bias.data) if from_y else {}
     ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act, **gb)
     ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act, **({"beta": bn.bias.data} if from_y else {}))
-    _side_run(side, lambda: ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad))
+    if bn_items is not None:
+        bn_items.append((buf.sums, bn.weight.grad, bn.bias.grad))       # the caller ends its pass with ONE launch for all layers
+    else:
+        _side_run(side, lambda: ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad))
     return buf.dy
 
 
@@ -157,6 +161,7 @@ class Gen2RT:
         ops = self.ops
         sr = lambda fn: _side_run(side, fn)
         L = self.up3
+        bn_items = []             # (sums, gamma.grad, beta.grad) of the 16 BatchNorm layers: one launch at the end of the pass
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
 
         def pgrad_up3(L=L):
@@ -167,33 +172,34 @@ class Gen2RT:
         ops.conv_fprop(self.dpre, L.pf, None, self.ub[2].da, L.k, L.s, L.p)
         for i in range(2, -1, -1):
             L, b = self.ups[i], self.ub[i]
-            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side)
+            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side, bn_items=bn_items)
             x_in = self.ub[i - 1].a if i > 0 else self.X[4]
             sr(lambda L=L, dy=dy, x_in=x_in: ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p))
             ops.conv_fprop(dy, L.pf, None, self.ub[i - 1].da if i > 0 else self.dX[4], L.k, L.s, L.p)
         for r in range(3, -1, -1):
             l1, l2, l3 = self.res[r]
             b1, b2, b3 = self.rb[r]
-            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False)
+            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False, bn_items=bn_items)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
             sr(lambda l3=l3, b2=b2, dy3=dy3: self._wgrad(l3, b2.a, dy3))
             ops.conv_dgrad(dy3, l3.pd, None, b2.da, 3, 1, 1)
-            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side)
+            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items)
             sr(lambda l2=l2, b1=b1, dy2=dy2: self._wgrad(l2, b1.a, dy2))
             ops.conv_dgrad(dy2, l2.pd, None, b1.da, 3, 1, 1)
-            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side)
+            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items)
             sr(lambda l1=l1, r=r, dy1=dy1: self._wgrad(l1, self.X[r], dy1))
             ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
             ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)
         ops.split_rep_bwd(self.dX[0], self.b2.da, self.dc_hat)
         L = self.ds2
-        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU, side)
+        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU, side, bn_items=bn_items)
         sr(lambda L=L, dy2=dy2: ops.conv_wgrad(self.a1, dy2, L.conv.weight.grad, L.k, L.s, L.p))
         ops.conv_dgrad(dy2, L.pd, None, self.da1, L.k, L.s, L.p)
         L = self.ds0
         ops.act_bwd(self.da1, self.a1, self.dy0, ACT_LRELU)
 
         def pgrad_ds0(L=L):
+            ops.bn_param_grad_multi(bn_items)
             ops.patchify(self.x_in, self.P0, L.k, L.s, L.p)
             ops.conv_wgrad(self.P0, self.dy0, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
             ops.colsum(self.dy0, L.conv.bias.grad)

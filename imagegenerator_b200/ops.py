@@ -79,6 +79,7 @@ _SIGS = {
     "sg_head_param_grads": [_P] * 10 + [_I, _I, _I, _P],
     "sg_ca_reparam": [_P] * 6 + [_I, _I, _I, _I, _I, _P],
     "sg_ca_bwd_seed": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
+    "sg_bn_param_grad_multi": [_P, _P, _P, _P, _P, _I, _P],
     "sg_ca_forward": [_P] * 14 + [_I] * 7 + [_P],
     "sg_ca_backward": [_P] * 4 + [_F] + [_P] * 15 + [_I] * 7 + [_P],
     "sg_interp": [_P, _P, _P, _P, _I, _L, _I, _P],
@@ -418,6 +419,19 @@ class CudaOps:
         self._c(sums, dgamma, dbeta)
         G, C, _ = sums.shape
         self._ck(self.lib.sg_bn_param_grad(_ptr(sums), _ptr(dgamma), _ptr(dbeta), G, C, self._st()))
+
+    def bn_param_grad_multi(self, items):
+        """``items``: [(sums [G,C,2] fp64, dgamma [C], dbeta [C]), ...] -- every BatchNorm layer of a backward pass in one launch."""
+        for i in range(0, len(items), 24):
+            part = items[i:i + 24]
+            n = len(part)
+            for t in part:
+                self._c(*t)
+            P = ctypes.c_void_p * n
+            I = ctypes.c_int * n
+            self._ck(self.lib.sg_bn_param_grad_multi(P(*[_ptr(t[0]) for t in part]), P(*[_ptr(t[1]) for t in part]),
+                                                     P(*[_ptr(t[2]) for t in part]), I(*[t[0].shape[0] for t in part]),
+                                                     I(*[t[0].shape[1] for t in part]), n, self._st()))
 
     def act_bwd(self, da, a_out, out, act):
         self._c(da, a_out, out)

@@ -223,6 +223,10 @@ int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const floa
                       int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
 /* dgamma += sum_g S2, dbeta += sum_g S1 */
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream);
+/* the same for n_layers BatchNorm layers in one launch (host arrays of device pointers / sizes, <= 24 layers): a network's
+   backward pass queues every layer's (sums, gamma.grad, beta.grad) and ends with ONE of these */
+int sg_bn_param_grad_multi(const double* const* sums, float* const* dgamma, float* const* dbeta, const int* groups, const int* C,
+                           int n_layers, void* stream);
 /* out = da * act'(a_out)   (LeakyReLU / ReLU / Tanh backward without BN) */
 int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act, int dtype, void* stream);
 

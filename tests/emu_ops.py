@@ -252,6 +252,10 @@ class EmuOps:
         dgamma.add_(sums[:, :, 1].sum(0).to(dgamma.dtype))
         dbeta.add_(sums[:, :, 0].sum(0).to(dbeta.dtype))
 
+    def bn_param_grad_multi(self, items):
+        for sums, dgamma, dbeta in items:
+            self.bn_param_grad(sums, dgamma, dbeta)
+
     def act_bwd(self, da, a_out, out, act):
         out.copy_((da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).to(out.dtype))
 

@@ -577,3 +577,20 @@ def test_concat_split_affine(mode):
     run_pair(mode, "split_rep_bwd", [T(dout), T(torch.zeros(N, H, H, Cx)), F(torch.zeros(N, Cc))], [1, 2],
              tol=dict(rtol=1e-3, atol=1e-4))
     run_pair("fp32", "affine_f32", [F(torch.rand(37)), -1.0, 1.0, F(torch.zeros(37))], [3])
+
+
+def test_bn_param_grad_multi():
+    """All BatchNorm layers' gamma / beta gradients in one launch == the per-layer kernel."""
+    items_e, items_c = [], []
+    emu = EmuOps(torch.float64)
+    ops = _ops("bf16")
+    for i, (G, C) in enumerate([(3, 128), (1, 24), (3, 512), (2, 640), (1, 80)]):
+        sums = rnd(G, C, 2, seed=i).double()
+        dg, db = rnd(C, seed=10 + i), rnd(C, seed=20 + i)
+        items_e.append((sums.clone(), dg.double().clone(), db.double().clone()))
+        items_c.append((sums.cuda(), dg.float().cuda(), db.float().cuda()))
+    emu.bn_param_grad_multi(items_e)
+    ops.bn_param_grad_multi(items_c)
+    torch.cuda.synchronize()
+    for (_, eg, eb), (_, cg, cb) in zip(items_e, items_c):
+        assert torch.allclose(cg.double().cpu(), eg, rtol=1e-5, atol=1e-6) and torch.allclose(cb.double().cpu(), eb, rtol=1e-5, atol=1e-6)
