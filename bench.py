@@ -428,17 +428,39 @@ def run_sampling(ops, world, rank, dev, reps=20, B=64):
     b.record()
     torch.cuda.synchronize()
     ms_e2e = a.elapsed_time(b) / reps
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    # the same end to end with uint8 pictures (out_dtype="uint8": a quarter of the read-back)
+    launches = smp.launches
+    del smp
+    torch.manual_seed(42)
+    smp8 = StackGANSampler(ConditioningAugmentation(512, 256, 128), StageIGenerator(128, 100),
+                           ConditioningAugmentation(512, 256, 128), StageIIGenerator(), B, ops=ops, out_dtype="uint8")
+    host8 = [torch.empty(B, 3, 256, 256, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for i in range(3):
+        smp8.sample_to_host(tem, z, e1, e2, host8[i & 1])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a.record()
+    for i in range(reps):
+        ev = smp8.sample_to_host(tem, z, e1, e2, host8[i & 1])
+    torch.cuda.current_stream().wait_event(ev)
+    b.record()
+    torch.cuda.synchronize()
+    ms_u8 = a.elapsed_time(b) / reps
+    t = torch.tensor([ms_dev, ms_e2e, ms_u8], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = t.tolist()
+    ms_dev, ms_e2e, ms_u8 = t.tolist()
     flops = (2 * F_CA + F_G1 + F_G2) * B
     return {"metric": "stackgan_sampling_images_per_sec", "value": round(B * world / (ms_dev * 1e-3), 1), "unit": "images/s",
             "batch_per_gpu": B, "ms_per_batch": round(ms_dev, 3), "tflops_per_gpu": round(flops / (ms_dev * 1e-3) / 1e12, 1),
             "e2e": {"value": round(B * world / (ms_e2e * 1e-3), 1), "ms_per_batch": round(ms_e2e, 3),
                     "h2d_bytes_per_step": B * (512 + 100 + 256) * 4, "d2h_bytes_per_step": B * 3 * 256 * 256 * 4,
                     "api": "StackGANSampler.sample_to_host (fp32 NCHW images into pinned host memory, read-back overlapped on a copy stream)"},
-            "gpu_launches_per_batch": smp.launches, "bn": "eval mode, folded into the packed conv weights"}
+            "e2e_uint8": {"value": round(B * world / (ms_u8 * 1e-3), 1), "ms_per_batch": round(ms_u8, 3),
+                          "h2d_bytes_per_step": B * (512 + 100 + 256) * 4, "d2h_bytes_per_step": B * 3 * 256 * 256,
+                          "api": "StackGANSampler(out_dtype='uint8').sample_to_host (NCHW uint8 pictures, round((x + 1) * 127.5))"},
+            "gpu_launches_per_batch": launches, "bn": "eval mode, folded into the packed conv weights"}
 
 
 def time_hbm_kernel(ops, peaks, reps=10):

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+namespace sg { extern int g_bstats_min_k; }
+
 extern "C" {
 int sg_conv_fprop_ffma(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int,
                        int, void*);
@@ -101,7 +103,8 @@ int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats,
 int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
                          const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                          int k, int s, int p, int dtype, void* stream) {
-    if (dtype == SG_BF16 && Co <= 256 * 8 && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+    if (dtype == SG_BF16 && Co <= 256 * 8 && Ci * k * k >= sg::g_bstats_min_k &&
+        sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
         return sg_conv_fprop_tc_bstats(x, pf, y, ybn, mr, gamma, beta, sums, groups, act, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
     int e = sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;
@@ -110,7 +113,8 @@ int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn
 int sg_conv_dgrad_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
                          const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                          int k, int s, int p, int dtype, void* stream) {
-    if (dtype == SG_BF16 && sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
+    if (dtype == SG_BF16 && Co * k * k / (s * s) >= sg::g_bstats_min_k &&
+        sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
         return sg_conv_dgrad_tc_bstats(dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, N, H, W, Ci, Ho, Wo, Co, k, s, p, stream);
     int e = sg_conv_dgrad(dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);
     if (e) return e;

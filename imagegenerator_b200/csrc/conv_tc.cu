@@ -391,7 +391,9 @@ __device__ __forceinline__ bool next_work(const TcpParams& P, int cluster_id, in
     return true;
 }
 
-template <int CG>
+// BS: instantiation with the BatchNorm-backward statistics in the epilogue (TcpParams::bs_*).  A template parameter, not a
+// run-time flag: carrying that code cost the plain launches 30 registers and ~4 % (critic ds3: 27.7 -> 29.2 us).
+template <int CG, bool BS>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcpParams P) {
@@ -400,7 +402,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint32_t tmem_slot;
     __shared__ float sstat[2][256][2];          // statistics staging, double-buffered by tile parity
     __shared__ uint4 sstage[TCP_EPI_WARPS][32 * 4];   // per epilogue warp: 32 rows x 64 B, for the coalesced store
-    __shared__ float4 sconst[256];              // backward statistics: (mean, rstd*gamma, beta, rstd) of the tile's columns
+    __shared__ float4 sconst[BS ? 256 : 1];     // backward statistics: (mean, rstd*gamma, beta, rstd) of the tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -616,7 +618,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             bf16* orow = P.out + (int64_t)((n_img * P.outH + oh) * P.outW + ow) * P.n_total + nt0;
             const int ncols = min(w.width, P.n_total - nt0);          // valid columns of this work item
             const uint32_t sb2 = ti & 1;           // statistics staging buffer
-            const bool bwd = P.bs_y != nullptr;
+            constexpr bool bwd = BS;
             if (bwd) {
                 // per-column constants of this tile's image group; the bar.sync that closed the previous tile guarantees that
                 // no warp still reads the previous tile's table
@@ -729,8 +731,9 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const float4 cst = sconst[min(c0 + j, 255)];
                             const float t = yv - cst.x;
                             const float dz = (t * cst.y + cst.z > 0.f) ? f[j] : slope * f[j];
-                            f[j] = (c0 + j < ncols) ? dz : 0.f;
-                            sq[j] = f[j] * (t * cst.w);
+                            const bool live = c0 + j < ncols;          // columns past the layer's channels: table entries unset
+                            f[j] = live ? dz : 0.f;
+                            sq[j] = live ? dz * (t * cst.w) : 0.f;
                         }
                     } else
 #pragma unroll
@@ -1307,13 +1310,21 @@ static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
 // 148 SMs).
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
 int g_use_slab = 1;      // option "slab": 0 = one activation box per tap (no sharing), for A/B measurements
+// option "bstats_min_k" / env SG_BSTATS_MIN_K: the BatchNorm-backward statistics ride in a conv's epilogue only when its
+// reduction is at least this deep (see conv_dispatch.cu); 0 = always, 1 << 30 = never.  Measured on B200 (bench.py, Stage-II
+// B=64, ms per outer step): always 36.55, >= 1500: 35.63, >= 2500: 35.41, >= 4000: 35.32, never: 35.40 (Stage-I: 5.76-5.81
+// whatever the setting).  The fused epilogue costs what the separate HBM-bound reduce pass (6 TB/s) saves: with two epilogue
+// warp groups per SM the y tile loads, the per-column constants and two more butterflies per 16 columns put the drain on the
+// critical path of every tile whose mainloop is shorter than ~4000 reduction elements.  Default: the deep layers only.
+int g_bstats_min_k = getenv("SG_BSTATS_MIN_K") ? atoi(getenv("SG_BSTATS_MIN_K")) : 4000;
 int g_use_nsplit = 1;    // option "nsplit": 0 = no column slices in the last round
 unsigned long long* g_trace = nullptr;   // sg_debug_conv_trace
 int g_rotate = 0;        // option "rotate": measured neutral on B200 (gpurun_out/bench_conv_r2i.txt), off
 // alternate-tile epilogue for narrow tiles (option "epi_alt" / env SG_EPI_ALT)
 int g_epi_alt = getenv("SG_EPI_ALT") ? atoi(getenv("SG_EPI_ALT")) : 1;
 static bool g_pattr_set = false;
-constexpr int TCP_SMEM_BYTES = 201 * 1024;      // + ~24 KB static (statistics staging, store transposes, BN constants) <= 227 KB
+constexpr int TCP_SMEM_BYTES = 205 * 1024;      // + ~20 KB static (statistics staging, store transposes) <= 227 KB
+constexpr int TCP_SMEM_BYTES_BS = 201 * 1024;   // the instantiation with the 4 KB BatchNorm constant table
 
 // column slices for the leftover tiles of the last round: returns S (1 = none) and the slice width
 static int nsplit_plan(long tiles, int units, int bn, int cg, int* bn2) {
@@ -1486,7 +1497,7 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     while (P.tmem_cols < P.nbuf * bn) P.tmem_cols *= 2;
     P.b_bytes = (bn / cg) * 128;
     P.stage_bytes = P.slab_pad + nv_max * P.b_bytes;
-    P.stages = (TCP_SMEM_BYTES - 1024) / P.stage_bytes;
+    P.stages = ((bs != nullptr ? TCP_SMEM_BYTES_BS : TCP_SMEM_BYTES) - 1024) / P.stage_bytes;
     if (P.stages > 8) P.stages = 8;
     if (g_force_stages && g_force_stages < P.stages) P.stages = g_force_stages;
     if (P.stages < 2) { set_error("conv_tcp: a %d-byte stage does not fit twice", P.stage_bytes); return SG_ERR_UNSUPPORTED; }
@@ -1510,8 +1521,10 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, P.BN2 / cg, &tmB2))) return e;
     size_t smem = (size_t)P.stages * P.stage_bytes + 1024;
     if (!g_pattr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES_BS);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES_BS);
         if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(tcp): %s", cudaGetErrorString(ce)); return (int)ce; }
         g_pattr_set = true;
     }
@@ -1528,8 +1541,13 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 2;
-    cudaError_t ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2>, tmA, tmB, tmB2, P)
-                             : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1>, tmA, tmB, tmB2, P);
+    cudaError_t ce;
+    if (bs != nullptr)
+        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, true>, tmA, tmB, tmB2, P)
+                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, true>, tmA, tmB, tmB2, P);
+    else
+        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, false>, tmA, tmB, tmB2, P)
+                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, false>, tmA, tmB, tmB2, P);
     if (ce != cudaSuccess) { set_error("conv_tcp launch: %s", cudaGetErrorString(ce)); return (int)ce; }
     g_launches.fetch_add(1);
     return check_launch("conv_tcp");
@@ -1725,6 +1743,7 @@ int sg_debug_conv_trace(void* buf) {
 int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "slab")) { g_use_slab = value; return 0; }
     if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
+    if (name && !strcmp(name, "bstats_min_k")) { g_bstats_min_k = value; return 0; }
     if (name && !strcmp(name, "rotate")) { g_rotate = value; return 0; }
     if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }
     if (name && !strcmp(name, "wgrad_mc_max")) { g_wgrad_mc_max = value; return 0; }

@@ -456,6 +456,22 @@ __global__ void nhwc_to_nchw_kernel(const T* src, float* dst, int N, int C, int6
         for (int c = 0; c < C; ++c) d[(int64_t)c * HW] = ldf(s + c);
     }
 }
+// NHWC tanh output in [-1, 1] -> NCHW uint8 image: round((x + 1) * 127.5), clamped (the usual de-normalisation of the
+// transforms.Normalize((0.5,)*3, (0.5,)*3) the reference trains with, train.py:104-110) -- a quarter of the fp32 read-back
+template <typename T>
+__global__ void nhwc_to_nchw_u8_kernel(const T* src, unsigned char* dst, int N, int C, int64_t HW) {
+    int64_t total = (int64_t)N * HW;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t n = i / HW, hw = i - n * HW;
+        const T* s = src + i * C;
+        unsigned char* d = dst + n * C * HW + hw;
+        for (int c = 0; c < C; ++c) {
+            const float v = fminf(fmaxf((ldf(s + c) + 1.f) * 127.5f, 0.f), 255.f);
+            d[(int64_t)c * HW] = (unsigned char)__float2int_rn(v);
+        }
+    }
+}
 // w[co][ci][t] (fp32 master) -> wt[(t, ci)][Kp] in the storage type, columns co >= Co zero: the forward operand of a
 // ConvTranspose2d on a 1x1 input run as a GEMM (engine.Up0Gemm).  Block = one ci; a thread owns one co, reads its kk <= 16
 // contiguous taps and stores them kk rows apart -- consecutive threads write consecutive columns.
@@ -909,6 +925,13 @@ int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
     SG_DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<grid_for((int64_t)N * HW, 256), 256, 0, SG_STREAM(stream)>>>(
                              (const T*)src, dst, N, C, HW)));
     SG_LAUNCHED("nhwc_to_nchw");
+    return 0;
+}
+int sg_nhwc_to_nchw_u8(const void* src, unsigned char* dst, int N, int C, int H, int W, int dtype, void* stream) {
+    int64_t HW = (int64_t)H * W;
+    SG_DISPATCH_T(dtype, (nhwc_to_nchw_u8_kernel<T><<<grid_for((int64_t)N * HW, 256), 256, 0, SG_STREAM(stream)>>>(
+                             (const T*)src, dst, N, C, HW)));
+    SG_LAUNCHED("nhwc_to_nchw_u8");
     return 0;
 }
 int sg_concat_rep(const void* x, const float* c, void* out, int N, int HW, int Cx, int Cc, int dtype, void* stream) {

@@ -282,10 +282,12 @@ class GenRT:
         _side_run(side, pgrad_last)
         ops.conv_fprop(self.dpre, last.pf, None, self.da[-1], last.k, last.s, last.p)
         bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
+        reduced = False           # sums[i] already came out of the epilogue of the conv that produced da[i]
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
-            ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,
-                              gamma=bn.weight.data, beta=bn.bias.data)
+            if not reduced:
+                ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,
+                                  gamma=bn.weight.data, beta=bn.bias.data)
             ops.bn_bwd_apply(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i],
                              self.dy[i], 1, ACT_RELU, beta=bn.bias.data)
             x_in = self.a[i - 1] if i > 0 else self.cg
@@ -301,7 +303,11 @@ class GenRT:
             if i == 0:
                 self.up0.input_grad(self.dy[0], self.dcg)
             else:
-                ops.conv_fprop(self.dy[i], L.pf, None, self.da[i - 1], L.k, L.s, L.p)
+                # d/d a of the layer below + that layer's BatchNorm-backward statistics in the same kernel
+                bnb = self.layers[i - 1].bn
+                ops.conv_fprop_bstats(self.dy[i], L.pf, self.da[i - 1], self.y[i - 1], self.mr[i - 1], bnb.weight.data,
+                                      bnb.bias.data, self.sums[i - 1], 1, ACT_RELU, L.k, L.s, L.p)
+                reduced = True
         _side_run(side, lambda: ops.bn_param_grad_multi(bn_items))
         return self.dcg
 
@@ -386,16 +392,36 @@ class CriticRT:
         B = self.B
         return t[g0 * B:(g0 + ng) * B]
 
-    def refresh_weights(self, with_text=False):
+    def refresh_weights(self, with_text=False, events=False):
         """bf16 operand packs + the collapsed head from the fp32 masters.  ``with_text``: also the compressed text of the
-        current batch (it depends on the compress weights only), so that the next forward finds it ready."""
+        current batch (it depends on the compress weights only), so that the next forward finds it ready.  ``events``
+        (when this runs on a side stream): record one CUDA event per layer and one for the head, so that the next forward
+        waits for layer l's operands right before conv l instead of for the whole re-pack before its first conv (the main
+        stream used to stall ~60 us per critic iteration behind head_prepare and the text compression)."""
         ops, m = self.ops, self.m
+        evs = [] if (events and not getattr(ops, "is_emulator", False)) else None
+        cur = torch.cuda.current_stream(ops.device) if evs is not None else None
+
+        def mark():
+            if evs is not None:
+                e = torch.cuda.Event()
+                e.record(cur)
+                evs.append(e)
         for L in self.layers:
             L.pack(ops)
+            mark()
         ops.head_prepare(m.channel_resize.weight.data, m.channel_resize.bias.data, m.critic_score.weight.data,
                          m.critic_score.bias.data, self.A, self.Bv, self.c0)
         if with_text:
             ops.linear_fwd(self.tem_all, m.compress.weight.data, m.compress.bias.data, self.ce)
+        mark()
+        self._pack_events = evs
+
+    def _wait_pack(self, i):
+        """Make the current stream wait for the i-th event of the last side-stream re-pack (layer i's operands; -1: the head)."""
+        evs = getattr(self, "_pack_events", None)
+        if evs:
+            torch.cuda.current_stream(self.ops.device).wait_event(evs[i])
 
     def set_text(self, tem, tem_mis):
         self.tem_all[:self.B].copy_(tem)
@@ -420,11 +446,14 @@ class CriticRT:
             _side_run(patches_on or None, lambda: ops.patchify(gv(self.a[0]), gv(self.P), L0.k, L0.s, L0.p))
         if training:
             ops.zero(self.stats_flat)
-        if before_weights is not None:
+        per_layer = bool(getattr(self, "_pack_events", None))
+        if before_weights is not None and not per_layer:
             before_weights()
+        self._wait_pack(0)
         ops.conv_fprop(gv(self.a[0]), L0.pf, L0.conv.bias.data, gv(self.a[1]), L0.k, L0.s, L0.p, act=ACT_LRELU)
         for l in range(1, self.nl):
             L, bn = self.layers[l], self.layers[l].bn
+            self._wait_pack(l)
             y = gv(self.y[l])
             mr = self.mr[l][g0:g0 + ng]
             if training:
@@ -439,6 +468,11 @@ class CriticRT:
                     ops.bn_eval_mr(bn.running_mean, bn.running_var, mr[g:g + 1])
                 ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)
         # head: compressed text, then the collapsed affine score
+        self._wait_pack(-1)
+        if per_layer:
+            if before_weights is not None:
+                before_weights()                 # the side stream's last event has been waited for: this join is free
+            self._pack_events = None             # consumed: later forwards of the same weights need no waits
         nt = 2 * B if with_mismatched else B
         if not ce_ready:
             ops.linear_fwd(self.tem_all[:nt], m.compress.weight.data, m.compress.bias.data, self.ce[:nt])
@@ -466,17 +500,26 @@ class CriticRT:
         if param_grads and head_reduce:
             ops.head_bwd_reduce(coef, a4, self.dA)
         bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
+        reduced = False           # sums[l] already came out of the epilogue of the conv that produced da[l + 1]
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
             da, a_out, y, dy = gv(self.da[l + 1]), gv(self.a[l + 1]), gv(self.y[l]), gv(self.dy[l])
-            ops.bn_bwd_reduce(da, a_out, y, mr, sums, ng, ACT_LRELU, gamma=bn.weight.data, beta=bn.bias.data)
+            if not reduced:
+                ops.bn_bwd_reduce(da, a_out, y, mr, sums, ng, ACT_LRELU, gamma=bn.weight.data, beta=bn.bias.data)
             ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
                              inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data)
             if param_grads:
                 bn_items.append((sums, bn.weight.grad, bn.bias.grad))
                 _side_run(side, lambda l=l, L=L, dy=dy: ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p))
-            ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
+            if l >= 2:
+                # d/d a of layer l-1 + that layer's BatchNorm-backward statistics in the same kernel
+                bnb = self.layers[l - 1].bn
+                ops.conv_dgrad_bstats(dy, L.pd, gv(self.da[l]), gv(self.y[l - 1]), self.mr[l - 1][g0:g0 + ng], bnb.weight.data,
+                                      bnb.bias.data, self.sums[l - 1][g0:g0 + ng], ng, ACT_LRELU, L.k, L.s, L.p)
+                reduced = True
+            else:
+                ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
         L0 = self.layers[0]
         dy0 = gv(self.dy[0])
         ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU)
@@ -514,14 +557,22 @@ class CriticRT:
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
         ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
+        reduced = False
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr = self.mr[l][2:3]
-            ops.bn_bwd_reduce(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.gsums[l], 1, ACT_LRELU,
-                              gamma=bn.weight.data, beta=bn.bias.data)
+            if not reduced:
+                ops.bn_bwd_reduce(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.gsums[l], 1, ACT_LRELU,
+                                  gamma=bn.weight.data, beta=bn.bias.data)
             ops.bn_bwd_apply(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
                              self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data)
-            ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
+            if l >= 2:
+                bnb = self.layers[l - 1].bn
+                ops.conv_dgrad_bstats(self.gdy[l], L.pd, self.gda[l], i2(self.y[l - 1]), self.mr[l - 1][2:3], bnb.weight.data,
+                                      bnb.bias.data, self.gsums[l - 1], 1, ACT_LRELU, L.k, L.s, L.p)
+                reduced = True
+            else:
+                ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
         L0 = self.layers[0]
         ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
         self.input_grad(self.gdy[0], self.g)
@@ -737,7 +788,8 @@ class Stage1Engine:
         ops.zero(d.fp.grad)                                      # :146
         ops.zero(d.head_grads)                                   # dA, dBv
         d.gp_first_order()                                       # utils.py:15-24
-        ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])   # :140-144
+        # :140-144; only the host reads the loss values: off the main stream
+        self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
         # head/text gradients first (dA is complete once the plain backward has added its head term)
         ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA)
@@ -750,7 +802,7 @@ class Stage1Engine:
                    head_reduce=False, side=self.side)
         self.optimizer_step(d.fp)                                # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
-        self.pack_side.run(lambda: d.refresh_weights(with_text=True))
+        self.pack_side.run(lambda: d.refresh_weights(with_text=True, events=True))
         self._ce_ready = True                                    # until the text changes (load_batch / next outer step)
 
     def generator_step(self):

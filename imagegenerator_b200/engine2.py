@@ -53,19 +53,28 @@ def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=Non
         ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
 
-def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=None):
+def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=None, reduced=False):
     """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads.  ``from_y``: the activation follows
     the BN directly, so the kernels take its sign from y and do not stream a_out (False for the layer that closes a
     residual block, whose ReLU sees bn(y) + identity).  ``bn_items``: list collecting (sums, gamma.grad, beta.grad) instead of
     launching the per-layer parameter-gradient kernel."""
     gb = dict(gamma=bn.weight.data, beta=bn.bias.data) if from_y else {}
-    ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act, **gb)
+    if not reduced:              # else: buf.sums came out of the epilogue of the conv that produced da (_conv_bstats)
+        ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act, **gb)
     ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act, **({"beta": bn.bias.data} if from_y else {}))
     if bn_items is not None:
         bn_items.append((buf.sums, bn.weight.grad, bn.bias.grad))       # the caller ends its pass with ONE launch for all layers
     else:
         _side_run(side, lambda: ops.bn_param_grad(buf.sums, bn.weight.grad, bn.bias.grad))
     return buf.dy
+
+
+def _conv_bstats(ops, direction, dy, L, da_out, below_bn, below_buf, act):
+    """Data-gradient conv of layer L whose result ``da_out`` is d loss / d a of the BatchNorm'ed layer below: the launch also
+    reduces that layer's BatchNorm-backward statistics (below_buf.sums) in its epilogue."""
+    fn = ops.conv_fprop_bstats if direction == "f" else ops.conv_dgrad_bstats
+    fn(dy, L.pf if direction == "f" else L.pd, da_out, below_buf.y, below_buf.mr, below_bn.weight.data, below_bn.bias.data,
+       below_buf.sums, 1, act, L.k, L.s, L.p)
 
 
 class Gen2RT:
@@ -170,23 +179,28 @@ class Gen2RT:
             ops.conv_wgrad(self.Pd, self.ub[2].a, L.conv.weight.grad.view(L.co, self.K0, 1, 1), 1, 1, 0)
         sr(pgrad_up3)
         ops.conv_fprop(self.dpre, L.pf, None, self.ub[2].da, L.k, L.s, L.p)
+        reduced = False           # the next layer's BN-backward statistics already came out of a conv epilogue
         for i in range(2, -1, -1):
             L, b = self.ups[i], self.ub[i]
-            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side, bn_items=bn_items)
+            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side, bn_items=bn_items, reduced=reduced)
             x_in = self.ub[i - 1].a if i > 0 else self.X[4]
             sr(lambda L=L, dy=dy, x_in=x_in: ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p))
-            ops.conv_fprop(dy, L.pf, None, self.ub[i - 1].da if i > 0 else self.dX[4], L.k, L.s, L.p)
+            if i > 0:
+                _conv_bstats(ops, "f", dy, L, self.ub[i - 1].da, self.ups[i - 1].bn, self.ub[i - 1], ACT_RELU)
+                reduced = True
+            else:
+                ops.conv_fprop(dy, L.pf, None, self.dX[4], L.k, L.s, L.p)
         for r in range(3, -1, -1):
             l1, l2, l3 = self.res[r]
             b1, b2, b3 = self.rb[r]
             dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False, bn_items=bn_items)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
             sr(lambda l3=l3, b2=b2, dy3=dy3: self._wgrad(l3, b2.a, dy3))
-            ops.conv_dgrad(dy3, l3.pd, None, b2.da, 3, 1, 1)
-            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items)
+            _conv_bstats(ops, "d", dy3, l3, b2.da, l2.bn, b2, ACT_RELU)
+            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items, reduced=True)
             sr(lambda l2=l2, b1=b1, dy2=dy2: self._wgrad(l2, b1.a, dy2))
-            ops.conv_dgrad(dy2, l2.pd, None, b1.da, 3, 1, 1)
-            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items)
+            _conv_bstats(ops, "d", dy2, l2, b1.da, l1.bn, b1, ACT_RELU)
+            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items, reduced=True)
             sr(lambda l1=l1, r=r, dy1=dy1: self._wgrad(l1, self.X[r], dy1))
             ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
             ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)
@@ -326,7 +340,8 @@ class Stage2Engine:
         ops.zero(d.fp.grad)                                         # :153
         ops.zero(d.head_grads)                                      # dA, dBv
         d.gp_first_order()
-        ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2])     # :148-152
+        # :148-152; only the host reads the loss values: off the main stream
+        self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=True,      # :154
                    input_grad_from=1, side=self.side)               # d/d real images is never used
@@ -337,7 +352,7 @@ class Stage2Engine:
         ops.scale_rows_add(d.group_view(d.dx, 2, 1), self.one_minus_eps, dfake, True)
         self._generator_backward(dfake, 0.0)                        # accumulates into G2 / CA2 (:154, no zero_grad)
         self.optimizer_step(d.fp)                                   # :155
-        self.pack_side.run(lambda: d.refresh_weights(with_text=True))   # joined before the next critic forward reads the packs
+        self.pack_side.run(lambda: d.refresh_weights(with_text=True, events=True))   # the next critic forward waits layer by layer
         self._ce_ready = True                                       # until the text changes (load_batch / next outer step)
 
     def generator_step(self):

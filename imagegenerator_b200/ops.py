@@ -80,6 +80,11 @@ _SIGS = {
     "sg_ca_reparam": [_P] * 6 + [_I, _I, _I, _I, _I, _P],
     "sg_ca_bwd_seed": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
     "sg_bn_param_grad_multi": [_P, _P, _P, _P, _P, _I, _P],
+    "sg_nhwc_to_nchw_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "sg_conv_fprop_bstats": [_P] * 8 + [_I] * 13 + [_P],
+    "sg_conv_dgrad_bstats": [_P] * 8 + [_I] * 13 + [_P],
+    "sg_conv_fprop_tc_bstats": [_P] * 8 + [_I] * 12 + [_P],
+    "sg_conv_dgrad_tc_bstats": [_P] * 8 + [_I] * 12 + [_P],
     "sg_ca_forward": [_P] * 14 + [_I] * 7 + [_P],
     "sg_ca_backward": [_P] * 4 + [_F] + [_P] * 15 + [_I] * 7 + [_P],
     "sg_interp": [_P, _P, _P, _P, _I, _L, _I, _P],
@@ -221,6 +226,13 @@ class CudaOps:
         assert dst.dtype == torch.float32 and dst.numel() == src.numel()
         self._ck(self.lib.sg_nhwc_to_nchw(_ptr(src), _ptr(dst), N, C, H, W, self._dt_of(src), self._st()))
 
+    def nhwc_to_nchw_u8(self, src, dst):
+        """tanh output in [-1, 1] -> NCHW uint8 image, round((x + 1) * 127.5)."""
+        self._c(src, dst)
+        N, C, H, W = dst.shape
+        assert dst.dtype == torch.uint8 and dst.numel() == src.numel()
+        self._ck(self.lib.sg_nhwc_to_nchw_u8(_ptr(src), _ptr(dst), N, C, H, W, self._dt_of(src), self._st()))
+
     def pack_weight(self, w, pf, pd):
         self._c(w, pf, pd)
         Co, Ci, k, _ = w.shape
@@ -326,6 +338,22 @@ class CudaOps:
         assert stats.dtype == torch.float64 and tuple(stats.shape) == (groups, d[3], 2)
         self._ck(self.lib.sg_conv_dgrad_stats(_ptr(dy), _ptr(pd), _ptr(dx), _ptr(stats), groups, *d, k, s, p,
                                               self._dt_of(dy), self._st()))
+
+    def conv_fprop_bstats(self, x, pf, y, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
+        """y = conv(x) is d loss / d a of the layer below (a = act(bn(ybn))); sums[groups][Co][2] = that layer's BN-backward
+        statistics, reduced in the conv epilogue (what bn_bwd_reduce(y, ., ybn, mr, sums, gamma=, beta=) would compute)."""
+        self._c(x, pf, y, ybn, mr, gamma, beta, sums)
+        d = self._conv_dims(x, y)
+        assert sums.dtype == torch.float64 and tuple(sums.shape) == (groups, d[6], 2) and ybn.shape == y.shape
+        self._ck(self.lib.sg_conv_fprop_bstats(_ptr(x), _ptr(pf), _ptr(y), _ptr(ybn), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
+                                               groups, act, *d, k, s, p, self._dt_of(x), self._st()))
+
+    def conv_dgrad_bstats(self, dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
+        self._c(dy, pd, dx, ybn, mr, gamma, beta, sums)
+        d = self._conv_dims(dx, dy)
+        assert sums.dtype == torch.float64 and tuple(sums.shape) == (groups, d[3], 2) and ybn.shape == dx.shape
+        self._ck(self.lib.sg_conv_dgrad_bstats(_ptr(dy), _ptr(pd), _ptr(dx), _ptr(ybn), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
+                                               groups, act, *d, k, s, p, self._dt_of(dy), self._st()))
 
     def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         self._c(x, dy, dw)

@@ -67,6 +67,9 @@ int sg_affine_f32(const float* x, float a, float b, float* out, int64_t n, void*
 /* ---- layout: the reference API is NCHW fp32 (e.g. generator_1.py:38-40 output) -------------- */
 int sg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dtype, void* stream);
 int sg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int dtype, void* stream);
+/* tanh output in [-1, 1] (NHWC, T) -> NCHW uint8 image round((x + 1) * 127.5): the de-normalised picture, a quarter of the
+   fp32 read-back (sampling / serving path; the reference normalises with mean = std = 0.5, train.py:104-110) */
+int sg_nhwc_to_nchw_u8(const void* src, unsigned char* dst, int N, int C, int H, int W, int dtype, void* stream);
 /* w [Co][Ci][k*k] fp32 -> pf [Co][k*k][Ci] and pd [Ci][k*k][Co] in T (either may be NULL) */
 int sg_pack_weight(const float* w, void* pf, void* pd, int Co, int Ci, int kk, int dtype, void* stream);
 /* wt[(t, ci)][Kp] (T) = w[co][ci][t], columns co >= Co zero: forward operand of ConvTranspose2d(Co -> Ci, k, s1, p0) on a 1x1
@@ -163,6 +166,24 @@ int sg_conv_fprop_stats(const void* x, const void* pf, void* y, double* stats, i
                         int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
 int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats, int groups,
                         int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
+
+/* conv whose RESULT is d loss / d a of the BatchNorm'ed layer below (a = act(bn(ybn)), generator_1.py:26-34, discrminator_1.py:29-37,
+ * generator_2.py:30-38): besides y / dx (T) the launch reduces that layer's BatchNorm-BACKWARD statistics
+ * sums[groups][C][2] = (sum dz, sum dz * xhat), dz = result * act'(gamma * xhat + beta), xhat = (ybn - mean) * rstd -- in the tcgen05
+ * epilogue when the shape allows (bf16), otherwise conv + sg_bn_bwd_reduce_y.  Replaces one pass over (da, y) per layer of every
+ * backward chain.  ybn has the result's layout; mr [groups][C][2]; act in {none, relu, lrelu}; C % 8 == 0. */
+int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
+                         const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, int dtype, void* stream);
+int sg_conv_dgrad_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
+                         const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
+                         int k, int s, int p, int dtype, void* stream);
+int sg_conv_fprop_tc_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
+                            const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo,
+                            int Co, int k, int s, int p, void* stream);
+int sg_conv_dgrad_tc_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
+                            const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo,
+                            int Co, int k, int s, int p, void* stream);
 int sg_conv_fprop_tc_stats(const void* x, const void* pf, void* y, double* stats, int groups, int N, int H, int W, int Ci,
                            int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream);
 int sg_conv_dgrad_tc_stats(const void* dy, const void* pd, void* dx, double* stats, int groups, int N, int H, int W, int Ci,

@@ -74,6 +74,9 @@ class EmuOps:
     def nhwc_to_nchw(self, src, dst):
         dst.copy_(nchw(src).to(dst.dtype))
 
+    def nhwc_to_nchw_u8(self, src, dst):
+        dst.copy_(torch.clamp(torch.round((nchw(src).to(torch.float32) + 1.0) * 127.5), 0, 255).to(torch.uint8))
+
     def pack_weight(self, w, pf, pd):
         """w [Co,Ci,kh,kw] fp32 -> pf [Co,kh,kw,Ci], pd [Ci,kh,kw,Co] in T."""
         if pf is not None:
@@ -146,6 +149,15 @@ class EmuOps:
     def conv_dgrad_stats(self, dy, pd, dx, stats, groups, k, s, p):
         self.conv_dgrad(dy, pd, None, dx, k, s, p)
         self.col_stats(dx, stats, groups)
+
+    def conv_fprop_bstats(self, x, pf, y, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
+        """conv, then the BatchNorm-backward statistics of the layer below from the STORED result."""
+        self.conv_fprop(x, pf, None, y, k, s, p)
+        self.bn_bwd_reduce(y, None, ybn, mr, sums, groups, act, gamma=gamma, beta=beta)
+
+    def conv_dgrad_bstats(self, dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
+        self.conv_dgrad(dy, pd, None, dx, k, s, p)
+        self.bn_bwd_reduce(dx, None, ybn, mr, sums, groups, act, gamma=gamma, beta=beta)
 
     def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         """dw[Co,Ci,kh,kw] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]."""

@@ -489,6 +489,74 @@ def test_conv_dgrad_stats(mode, case):
     _check_stats(ca[2], ca[3], st0, G)
 
 
+def _bstats_inputs(G, C, shape, act, seed):
+    """mean / rstd / gamma / beta and a pre-BN tensor whose activation argument gamma*xhat+beta stays 0.25 away from 0, so that
+    fp32 vs fp64 evaluation of the mask cannot disagree (a flipped mask moves a sum by a whole element)."""
+    g = torch.Generator().manual_seed(seed)
+    mr = torch.stack([torch.randn(G, C, generator=g) * 0.3, torch.rand(G, C, generator=g) + 0.5], dim=-1)
+    gamma = (torch.rand(C, generator=g) + 0.5) * torch.where(torch.rand(C, generator=g) < 0.3, -1.0, 1.0)
+    beta = torch.randn(C, generator=g) * 0.2
+    u = torch.randn(*shape, generator=g)
+    u = torch.sign(u) * (0.25 + u.abs())
+    N = shape[0]
+    mean = mr[:, :, 0].repeat_interleave(N // G, dim=0)[:, None, None, :]
+    rstd = mr[:, :, 1].repeat_interleave(N // G, dim=0)[:, None, None, :]
+    ybn = mean + (u - beta) / (rstd * gamma)
+    return mr, gamma, beta, ybn
+
+
+def _check_bstats(da_dev, ybn_dev, mr, gamma, beta, sums_dev, G, act):
+    """The statistics must be those of the STORED gradient (what bn_bwd_apply will read), recomputed in fp64."""
+    emu = EmuOps(torch.float64)
+    want = torch.zeros(sums_dev.shape, dtype=torch.float64)
+    da, ybn = da_dev.double().cpu(), ybn_dev.double().cpu()
+    emu.bn_bwd_reduce(da, None, ybn, mr.double(), want, G, act, gamma=gamma.double(), beta=beta.double())
+    C = da.shape[-1]
+    scale = da.abs().reshape(G, -1, C).sum(1)[:, :, None]
+    xmax = 12.0                                                       # |xhat| of the constructed data stays well below this
+    got = sums_dev.cpu()
+    assert ((got - want).abs() <= 2e-4 * scale * xmax + 1e-6).all(), ((got - want).abs() / (scale + 1e-9)).max().item()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", STATS_CASES)
+@pytest.mark.parametrize("act", [ACT_RELU, ACT_LRELU])
+def test_conv_fprop_bstats(mode, case, act):
+    """conv + the BatchNorm-backward statistics of the layer below in its epilogue == conv, then bn_bwd_reduce."""
+    N, H, Ci, Co, k, s, p, G = case
+    if Co % 8:
+        pytest.skip("the *_y BatchNorm kernels need C % 8 == 0")
+    Ho = (H + 2 * p - k) // s + 1
+    x, w = rnd(N, H, H, Ci), rnd(Co, Ci, k, k, scale=(Ci * k * k) ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    mr, gamma, beta, ybn = _bstats_inputs(G, Co, (N, Ho, Ho, Co), act, 5)
+    sums = torch.full((G, Co, 2), 7.0, dtype=torch.float64)           # must be overwritten, not accumulated
+    _ops(mode).set_option("bstats_min_k", 0)                          # the fused epilogue whatever the reduction depth
+    ea, ca = run_pair(mode, "conv_fprop_bstats", [T(x), T(pf), T(torch.zeros(N, Ho, Ho, Co)), T(ybn), F(mr), F(gamma), F(beta),
+                                                  D(sums), G, act, k, s, p], [2])
+    _ops(mode).set_option("bstats_min_k", 4000)
+    _check_bstats(ca[2], ca[3], mr, gamma, beta, ca[7], G, act)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", STATS_CASES)
+@pytest.mark.parametrize("act", [ACT_RELU, ACT_LRELU])
+def test_conv_dgrad_bstats(mode, case, act):
+    N, H, Ci, Co, k, s, p, G = case
+    if Ci % 8:
+        pytest.skip("the *_y BatchNorm kernels need C % 8 == 0")
+    Ho = (H + 2 * p - k) // s + 1
+    dy, w = rnd(N, Ho, Ho, Co), rnd(Co, Ci, k, k, scale=(Co * k * k / (s * s)) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    mr, gamma, beta, ybn = _bstats_inputs(G, Ci, (N, H, H, Ci), act, 6)
+    sums = torch.full((G, Ci, 2), 7.0, dtype=torch.float64)
+    _ops(mode).set_option("bstats_min_k", 0)
+    ea, ca = run_pair(mode, "conv_dgrad_bstats", [T(dy), T(pd), T(torch.zeros(N, H, H, Ci)), T(ybn), F(mr), F(gamma), F(beta),
+                                                  D(sums), G, act, k, s, p], [2])
+    _ops(mode).set_option("bstats_min_k", 4000)
+    _check_bstats(ca[2], ca[3], mr, gamma, beta, ca[7], G, act)
+
+
 def _wtc_ok(case):
     from imagegenerator_b200.ops import CudaOps
     N, H, Ci, Co, k, s, p = case

@@ -69,3 +69,34 @@ def test_sampler_matches_oracle(mode, batch_stats, B):
             assert frac_bad <= (1e-3 if mode == "bf16" else 0.0), (what, mode, use_graph, err.max().item(), frac_bad)
             rel = (got - ref).norm().item() / ref.norm().item()
             assert rel < (3e-2 if mode == "bf16" else 1e-4) + 3.0 * noise[what], (what, rel)
+
+
+def test_sample_to_host_and_uint8_pictures():
+    """``sample_to_host`` (read-back on a copy stream, two staging buffers) returns what ``sample`` computes, batch after
+    batch; ``out_dtype="uint8"`` is round((x + 1) * 127.5) of the same images."""
+    from imagegenerator_b200.ops import CudaOps
+    from imagegenerator_b200.sampler import StackGANSampler
+    B = 4
+    ms = build_all()
+    ops = CudaOps("bf16")
+    smp = StackGANSampler(ms["ca1"], ms["g1"], ms["ca2"], ms["g2"], B, ops=ops)
+    smp8 = StackGANSampler(ms["ca1"], ms["g1"], ms["ca2"], ms["g2"], B, ops=ops, out_dtype="uint8")
+    g = torch.Generator().manual_seed(1)
+    host = [torch.empty(B, 3, 256, 256).pin_memory() for _ in range(3)]
+    host64 = [torch.empty(B, 3, 64, 64).pin_memory() for _ in range(3)]
+    host8 = [torch.empty(B, 3, 256, 256, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    want, evs = [], []
+    for i in range(3):                                   # three batches in flight over two staging buffers
+        tem = torch.randn(B, 512, generator=g)
+        z, e1, e2 = (torch.randn(B, n, generator=g) for n in (100, 128, 128))
+        f64, f256 = smp.sample(tem, z, e1, e2)
+        want.append((f64.clone(), f256.clone()))
+        evs.append(smp.sample_to_host(tem, z, e1, e2, host[i], host64[i]))
+        evs.append(smp8.sample_to_host(tem, z, e1, e2, host8[i]))
+    for e in evs:
+        e.synchronize()
+    for i in range(3):
+        assert torch.equal(host[i], want[i][1].cpu()) and torch.equal(host64[i], want[i][0].cpu())
+        pic = torch.clamp(torch.round((want[i][1].cpu() + 1.0) * 127.5), 0, 255).to(torch.uint8)
+        assert (host8[i].int() - pic.int()).abs().max().item() <= 1          # round-half cases of (x + 1) * 127.5 in fp32
+        assert (host8[i] == pic).float().mean().item() > 0.999
