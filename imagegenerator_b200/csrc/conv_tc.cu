@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <map>
 #include <string.h>
 #include <stdlib.h>
@@ -290,6 +291,8 @@ struct TcpParams {
     float* out32;         // fp32 result instead of bf16 `out` (col2im input of the thin layers) or NULL
     const bf16* residual; // added before the activation (same layout as out) or NULL
     unsigned long long* trace;   // profiling hook (sg_debug_conv_trace): 16 globaltimer stamps per CTA, or NULL
+    unsigned int* sched;         // dynamic work distribution: {next item, clusters done} of this launch, or NULL = static lists
+    int sched_chunk;             // items per draw (consecutive numbers): > 1 for launches of many short items
     // BatchNorm-BACKWARD statistics fused into the epilogue (sg_conv_*_bstats): this launch's result is da = d loss / d a of
     // the layer below, a = act(bn(y)); with bs_y != NULL `stats` receives (S1, S2) = (sum dz, sum dz * xhat) per (group, channel),
     // dz = da * act'(gamma * xhat + beta), xhat = (y - mean) * rstd -- what sg_bn_bwd_reduce_y computes in a pass of its own
@@ -370,9 +373,7 @@ struct Work {
     int tile, nt0, width, sliced;     // tile index; first output column; columns this item computes; 1 = a column slice
 };
 
-__device__ __forceinline__ bool next_work(const TcpParams& P, int cluster_id, int num_clusters, int i, Work* w) {
-    const int t = cluster_id + i * num_clusters;
-    if (t >= P.total_work) return false;
+__device__ __forceinline__ void decode_work(const TcpParams& P, int t, Work* w) {
     int tile = t, sl = 0;
     w->sliced = 0;
     if (t >= P.full_tiles) {
@@ -388,12 +389,44 @@ __device__ __forceinline__ bool next_work(const TcpParams& P, int cluster_id, in
     const int nt = P.n_tiles != 1 ? r / P.m_tiles : 0;
     w->nt0 = nt * P.BN + sl * P.BN2;
     w->width = w->sliced ? min(P.BN2, P.BN - sl * P.BN2) : P.BN;
-    return true;
+}
+
+// ---- dynamic work distribution (TcpParams::sched != NULL).  The static schedule gives cluster c the items c, c+C, c+2C, ...:
+// fine on an empty machine, but the captured step runs these kernels NEXT TO the weight-gradient kernels of the side stream,
+// whose CTAs hold an SM for 20-60 us each -- a conv CTA that lands late still owns its whole list and the launch ends when it
+// does.  Here the leader CTA's producer warp draws item numbers from a global counter and hands them to every other role
+// through a 4-entry shared-memory queue (and to the peer CTA of a pair with st.async + complete_tx): a CTA that lands late
+// simply finds less -- or nothing -- left.  The last cluster to finish re-arms the counter for the next launch / graph replay.
+constexpr int WQ = 8;
+// wait on a queue barrier; bounded (~seconds), so that a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
 }
 
 // BS: instantiation with the BatchNorm-backward statistics in the epilogue (TcpParams::bs_*).  A template parameter, not a
 // run-time flag: carrying that code cost the plain launches 30 registers and ~4 % (critic ds3: 27.7 -> 29.2 us).
-template <int CG, bool BS>
+// DYN: instantiation with the dynamic work distribution (TcpParams::sched) -- also a template parameter: as a run-time flag the
+// queue code cost the static launches ~2 % (sampling 56.0 -> 52.7 k images/s).
+template <int CG, bool BS, bool DYN>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcpParams P) {
@@ -403,6 +436,8 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ float sstat[2][256][2];          // statistics staging, double-buffered by tile parity
     __shared__ uint4 sstage[TCP_EPI_WARPS][32 * 4];   // per epilogue warp: 32 rows x 64 B, for the coalesced store
     __shared__ float4 sconst[BS ? 256 : 1];     // backward statistics: (mean, rstd*gamma, beta, rstd) of the tile's columns
+    __shared__ int wq_id[DYN ? WQ : 1];         // dynamic schedule: queue of work-item numbers (deep enough for the producer's lead)
+    __shared__ uint64_t wq_full[DYN ? WQ : 1], wq_empty[DYN ? WQ : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -419,6 +454,10 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < P.nbuf; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (P.epi_alt ? TCP_EPI_WARPS / 2 : TCP_EPI_WARPS) * CG); }
+        // queue: full = the leader producer's publication (peer CTA: its remote expect_tx + the st.async bytes); empty (leader's
+        // copy only) = every consumer of the pair: MMA warp + 8 epilogue warps of the leader, producer + 8 epilogue warps of the peer
+        if (DYN)
+            for (int i = 0; i < WQ; ++i) { mbar_init(&wq_full[i], 1); mbar_init(&wq_empty[i], (1 + TCP_EPI_WARPS) * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (P.stats != nullptr)
@@ -441,6 +480,20 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) trace_stamp(P, 1);
     SG_PDL_SYNC();        // barriers, TMEM and the stats staging are set up: from here on global memory is touched
     if (threadIdx.x == 0) trace_stamp(P, 2);
+    constexpr bool dyn = DYN;
+    // consumer side of the work queue (every role but the leader CTA's producer): item number of this role's next round
+    int q_tail = 0;
+    uint32_t q_par = 0;
+    auto pop_work = [&]() -> int {
+        mbar_wait_bounded(&wq_full[q_tail], q_par);
+        const int t = *reinterpret_cast<volatile int*>(&wq_id[q_tail]);
+        __syncwarp();
+        if (lane == 0) {                      // the number is in registers: hand the slot back (to the leader's barrier)
+            if (CG == 2) mbar_arrive_leader(&wq_empty[q_tail]); else mbar_arrive_local(&wq_empty[q_tail]);
+        }
+        if (++q_tail == WQ) { q_tail = 0; q_par ^= 1; }
+        return t;
+    };
 
     if (warp == 0) {
         {
@@ -454,7 +507,42 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t par = 1;                         // parity to wait for on empty[st]: first round passes
             const uint32_t ring = smem_u32(smem);
             Work w;
-            for (int wi = 0; next_work(P, cluster_id, num_clusters, wi, &w); ++wi) {
+            // leader producer under the dynamic schedule: draws the item numbers (one ahead, so that the atomic's round
+            // trip hides behind the current item's loads) and publishes them
+            const bool fetcher = dyn && rank == 0;
+            // the first chunk of a cluster is static (items c*chunk ..: no round trip before the first load); every further
+            // chunk is  (C + draw) * chunk ..  with draw = atomicAdd(counter, 1), fetched one chunk ahead
+            const int chunk = P.sched_chunk;
+            int q_head = 0, t_base = cluster_id * chunk, t_in = 0, t_next = 0;
+            uint32_t q_epar = 1;
+            if (fetcher && lane == 0) t_next = (num_clusters + (int)atomicAdd(P.sched, 1u)) * chunk;
+            for (int wi = 0;; ++wi) {
+                int t;
+                if (!dyn) t = cluster_id + wi * num_clusters;
+                else if (!fetcher) t = pop_work();
+                else {
+                    if (t_in == chunk) {                 // chunk used up: switch to the prefetched one, draw the one after
+                        t_base = __shfl_sync(0xffffffffu, t_next, 0);
+                        t_in = 0;
+                        if (t_base < P.total_work && lane == 0) t_next = (num_clusters + (int)atomicAdd(P.sched, 1u)) * chunk;
+                    }
+                    t = t_base + t_in;
+                    ++t_in;
+                    mbar_wait_bounded(&wq_empty[q_head], q_epar);
+                    if (elect_one()) {
+                        wq_id[q_head] = t;
+                        if (CG == 2) {
+                            const uint32_t pf = mapa_u32(smem_u32(&wq_full[q_head]), 1u), pi = mapa_u32(smem_u32(&wq_id[q_head]), 1u);
+                            asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(pf), "r"(4u) : "memory");
+                            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(pi), "r"(t), "r"(pf) : "memory");
+                        }
+                        mbar_arrive_local(&wq_full[q_head]);
+                    }
+                    __syncwarp();
+                    if (++q_head == WQ) { q_head = 0; q_epar ^= 1; }
+                }
+                if (t >= P.total_work) break;
+                decode_work(P, t, &w);
                 int phase = 0, r = w.tile;
                 if (P.tiles_per_phase != P.total_tiles) { phase = w.tile / P.tiles_per_phase; r = w.tile - phase * P.tiles_per_phase; }
                 const int mt = P.n_tiles != 1 ? r % P.m_tiles : r;
@@ -517,7 +605,10 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int st = 0;
             uint32_t par = 0, ab = 0, abpar = 1;       // accumulator buffer ring: P.nbuf buffers of acc_stride TMEM columns
             Work w;
-            for (int wi = 0; next_work(P, cluster_id, num_clusters, wi, &w); ++wi) {
+            for (int wi = 0;; ++wi) {
+                const int t = dyn ? pop_work() : cluster_id + wi * num_clusters;
+                if (t >= P.total_work) break;
+                decode_work(P, t, &w);
                 const int phase = P.tiles_per_phase != P.total_tiles ? w.tile / P.tiles_per_phase : 0;
                 // the MMA's N: the slice width rounded up to what the staged weight rows cover (a trailing slice narrower
                 // than BN2 still multiplies BN2 staged rows -- rows past the layer's channels are TMA zero fill -- and the
@@ -592,8 +683,10 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         uint32_t ti = 0, ab = 0, abpar = 0;
         Work w;
-        for (int wi = 0; next_work(P, cluster_id, num_clusters, wi, &w);
-             ++wi, ++ti, ab = (ab + 1 == (uint32_t)P.nbuf ? 0 : ab + 1), abpar ^= (ab == 0 ? 1u : 0u)) {
+        for (int wi = 0;; ++wi, ++ti, ab = (ab + 1 == (uint32_t)P.nbuf ? 0 : ab + 1), abpar ^= (ab == 0 ? 1u : 0u)) {
+            const int t = dyn ? pop_work() : cluster_id + wi * num_clusters;
+            if (t >= P.total_work) break;
+            decode_work(P, t, &w);
             // epi_alt (narrow tiles without statistics): warps 2-5 drain the even work items, warps 6-9 the odd
             // ones, each warp all columns of its 32 rows -- the per-tile fixed cost (decode, row pointers, barrier round
             // trip: ~350 of the ~450 instructions a warp spends on a 128x64 tile) is paid by four warps instead of eight
@@ -879,6 +972,14 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (threadIdx.x == 0) trace_stamp(P, 10);
+    if (dyn && threadIdx.x == 0 && rank == 0) {
+        // every cluster draws (at least) its terminating number before it gets here: the last one to arrive re-arms both words
+        __threadfence();
+        if (atomicAdd(P.sched + 1, 1u) == (unsigned)(num_clusters - 1)) {
+            P.sched[0] = 0u; P.sched[1] = 0u;
+            __threadfence();
+        }
+    }
     if (warp == 1) {
         if (CG == 2)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
@@ -1310,6 +1411,15 @@ static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
 // 148 SMs).
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
 int g_use_slab = 1;      // option "slab": 0 = one activation box per tap (no sharing), for A/B measurements
+// option "dyn_sched" / env SG_DYN_SCHED: dynamic work distribution in the persistent conv kernel (see decode_work); needs the
+// counter pool of sg_init_workspace().  OFF by default: measured on B200 (round 2, bench.py) Stage-I 5.42 -> 5.60 ms and
+// Stage-II 35.2 -> 36.1 ms per step with it, critic ds3 fprop alone 27.7 -> 29.7 us, many-tile layers up to +28 % (D1 ds2
+// dgrad 42.1 -> 53.9 us): the queue hand-off sits in front of every item of every role, and with the main chain on a
+// high-priority stream the late-landing CTAs it was meant to cure are rare.  Kept for machines shared with other work.
+int g_dyn_sched = getenv("SG_DYN_SCHED") ? atoi(getenv("SG_DYN_SCHED")) : 0;
+constexpr unsigned SCHED_SLOTS = 4096;
+unsigned int* g_sched_pool = nullptr;        // SCHED_SLOTS x {next item, clusters done}, zero between launches
+std::atomic<unsigned> g_sched_seq{0};
 // option "bstats_min_k" / env SG_BSTATS_MIN_K: the BatchNorm-backward statistics ride in a conv's epilogue only when its
 // reduction is at least this deep (see conv_dispatch.cu); 0 = always, 1 << 30 = never.  Measured on B200 (bench.py, Stage-II
 // B=64, ms per outer step): always 36.55, >= 1500: 35.63, >= 2500: 35.41, >= 4000: 35.32, never: 35.40 (Stage-I: 5.76-5.81
@@ -1419,6 +1529,8 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     P.residual = (const bf16*)residual;
     if (bs != nullptr) { P.bs_y = (const bf16*)bs->y; P.bs_mr = bs->mr; P.bs_gamma = bs->gamma; P.bs_beta = bs->beta; P.bs_slope = bs->slope; }
     P.trace = g_trace;
+    P.sched = (g_dyn_sched && g_sched_pool != nullptr && bs == nullptr) ? g_sched_pool + 2 * (g_sched_seq.fetch_add(1) % SCHED_SLOTS) : nullptr;
+    P.sched_chunk = 1;
     if (out32) P.out = nullptr;
     P.imgs_per_group = groups > 0 ? N / groups : N;
     const int phases = mode == 0 ? 1 : s * s;
@@ -1515,16 +1627,22 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     }
     P.total_work = P.full_tiles + (P.total_tiles - P.full_tiles) * P.nslices;
     const int clusters = P.total_work < units ? P.total_work : units;
+    if (P.sched != nullptr) {                  // ~8 draws per cluster at least; never more than 8 items per draw
+        int c = P.total_work / (clusters * 8);
+        P.sched_chunk = c < 1 ? 1 : (c > 8 ? 8 : c);
+    }
     CUtensorMap tmA, tmB, tmB2;
     if ((e = get_slab_map(act, N, aH, aW, P.Ck, P.bw, slab_rows, P.bn, P.es, &tmA))) return e;
     if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, bn / cg, &tmB))) return e;
     if ((e = get_w_map(wpack, P.n_total, k * k * P.Ck, P.BN2 / cg, &tmB2))) return e;
     size_t smem = (size_t)P.stages * P.stage_bytes + 1024;
     if (!g_pattr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES_BS);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES_BS);
+        cudaError_t ce = cudaFuncSetAttribute(conv_tcp_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES_BS);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tcp_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES_BS);
         if (ce != cudaSuccess) { set_error("cudaFuncSetAttribute(tcp): %s", cudaGetErrorString(ce)); return (int)ce; }
         g_pattr_set = true;
     }
@@ -1543,11 +1661,14 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     cfg.attrs = attr; cfg.numAttrs = 2;
     cudaError_t ce;
     if (bs != nullptr)
-        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, true>, tmA, tmB, tmB2, P)
-                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, true>, tmA, tmB, tmB2, P);
+        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, true, false>, tmA, tmB, tmB2, P)
+                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, true, false>, tmA, tmB, tmB2, P);
+    else if (P.sched != nullptr)
+        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, false, true>, tmA, tmB, tmB2, P)
+                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, false, true>, tmA, tmB, tmB2, P);
     else
-        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, false>, tmA, tmB, tmB2, P)
-                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, false>, tmA, tmB, tmB2, P);
+        ce = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_tcp_kernel<2, false, false>, tmA, tmB, tmB2, P)
+                     : cudaLaunchKernelEx(&cfg, conv_tcp_kernel<1, false, false>, tmA, tmB, tmB2, P);
     if (ce != cudaSuccess) { set_error("conv_tcp launch: %s", cudaGetErrorString(ce)); return (int)ce; }
     g_launches.fetch_add(1);
     return check_launch("conv_tcp");
@@ -1740,9 +1861,22 @@ int sg_debug_conv_trace(void* buf) {
     return 0;
 }
 
+// One-time device allocations of the library (the launch entry points themselves never allocate): the counter pool of the
+// dynamic conv schedule.  Call once per process and device before the first launch, outside stream capture.
+int sg_init_workspace(void) {
+    if (g_sched_pool != nullptr) return 0;
+    unsigned int* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, SCHED_SLOTS * 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, SCHED_SLOTS * 2 * sizeof(unsigned int));
+    if (e != cudaSuccess) { set_error("sg_init_workspace: %s", cudaGetErrorString(e)); return (int)e; }
+    g_sched_pool = p;
+    return 0;
+}
+
 int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "slab")) { g_use_slab = value; return 0; }
     if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
+    if (name && !strcmp(name, "dyn_sched")) { g_dyn_sched = value; return 0; }
     if (name && !strcmp(name, "bstats_min_k")) { g_bstats_min_k = value; return 0; }
     if (name && !strcmp(name, "rotate")) { g_rotate = value; return 0; }
     if (name && !strcmp(name, "wgrad_mc")) { g_use_wgrad_mc = value; return 0; }

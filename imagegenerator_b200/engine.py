@@ -61,8 +61,12 @@ class SideStream:
         self.ops = ops
         self.enabled = (not getattr(ops, "is_emulator", False)) and os.environ.get("SG_NO_SIDE_STREAM") != "1"
         self.stream, self.pending, self.priority = None, False, priority
+        # timing experiment only (results are WRONG): drop this stream's work to see what the main chain costs alone
+        self.skip = os.environ.get("SG_EXPERIMENT_SKIP_SIDE") == "1"
 
     def run(self, fn):
+        if self.skip:
+            return
         if not self.enabled:
             fn()
             return

@@ -99,7 +99,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
-                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace", "sg_conv_thin_supported",
+                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace", "sg_conv_thin_supported", "sg_init_workspace",
                                  "sg_dp_max_world", "sg_dp_flag_ints", "sg_dp_sync_ints", "sg_dp_adam_step"])
 
 
@@ -132,6 +132,7 @@ def load_library(path=LIB_PATH):
     lib.sg_version.restype = _I
     lib.sg_last_error.restype = _c.c_char_p
     lib.sg_check_device.restype = _I
+    lib.sg_init_workspace.restype = _I
     lib.sg_launch_count.restype = _L
     return lib
 
@@ -152,6 +153,8 @@ class CudaOps:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         with torch.cuda.device(self.device):
             if self.lib.sg_check_device() != 0:
+                raise RuntimeError(self.lib.sg_last_error().decode())
+            if self.lib.sg_init_workspace() != 0:         # one-time allocations (never inside a launch / stream capture)
                 raise RuntimeError(self.lib.sg_last_error().decode())
         if dtype in ("bf16", torch.bfloat16):
             self.act_dtype, self.dt = torch.bfloat16, SG_BF16

@@ -57,6 +57,13 @@ int64_t sg_launch_count(void);
  * launches that follow; "wgrad_mc" = 1/0 TMA multicast in the weight-gradient kernel; "force_stages" caps the conv
  * pipeline depth; "epi_alt" = 1/0 alternate-tile epilogue for conv tiles <= 64 columns wide (default 0, env SG_EPI_ALT) */
 int sg_set_option(const char* name, int value);
+/* one-time device allocations of the library (the launch entry points never allocate): the counter pool of the dynamic conv
+   schedule.  Once per process, before the first launch, outside stream capture. */
+int sg_init_workspace(void);
+/* further options: "dyn_sched" = 1/0 dynamic work distribution in the persistent conv kernel (item numbers drawn from a global
+   counter instead of static per-cluster lists; env SG_DYN_SCHED); "bstats_min_k" = least reduction depth for which the
+   BatchNorm-backward statistics ride in a conv epilogue (env SG_BSTATS_MIN_K) */
+
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
 int sg_zero(void* ptr, int64_t bytes, void* stream);

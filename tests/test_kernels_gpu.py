@@ -662,3 +662,26 @@ def test_bn_param_grad_multi():
     torch.cuda.synchronize()
     for (_, eg, eb), (_, cg, cb) in zip(items_e, items_c):
         assert torch.allclose(cg.double().cpu(), eg, rtol=1e-5, atol=1e-6) and torch.allclose(cb.double().cpu(), eb, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [(48, 16, 128, 256, 4, 2, 1, 3), (6, 32, 64, 128, 4, 2, 1, 3), (4, 16, 640, 320, 3, 1, 1, 1),
+                                  (24, 32, 48, 64, 1, 1, 0, 1)])
+def test_conv_dynamic_schedule(case):
+    """The persistent conv kernel with work items drawn from a global counter (option dyn_sched; off by default) computes what
+    the static schedule does: many-tile and few-tile launches, CTA pairs, fused statistics, and the counter re-arms itself."""
+    N, H, Ci, Co, k, s, p, G = case
+    Ho = (H + 2 * p - k) // s + 1
+    ops = _ops("bf16")
+    ops.set_option("dyn_sched", 1)
+    try:
+        for rep in range(3):                                              # the same counter slot pool, launch after launch
+            x, w = rnd(N, H, H, Ci, seed=rep), rnd(Co, Ci, k, k, scale=(Ci * k * k) ** -0.5, seed=rep)
+            pf, pd = w.permute(0, 2, 3, 1).contiguous(), w.permute(1, 2, 3, 0).contiguous()
+            run_pair("bf16", "conv_fprop", [T(x), T(pf), F(rnd(Co)), T(torch.zeros(N, Ho, Ho, Co)), k, s, p], [3], dict(act=ACT_LRELU))
+            dy = rnd(N, Ho, Ho, Co, seed=rep + 7)
+            run_pair("bf16", "conv_dgrad", [T(dy), T(pd), None, T(torch.zeros(N, H, H, Ci)), k, s, p], [3])
+            st0 = torch.zeros(G, Co, 2, dtype=torch.float64)
+            ea, ca = run_pair("bf16", "conv_fprop_stats", [T(x), T(pf), T(torch.zeros(N, Ho, Ho, Co)), D(st0), G, k, s, p], [2])
+            _check_stats(ca[2], ca[3], st0, G)
+    finally:
+        ops.set_option("dyn_sched", 0)

@@ -90,3 +90,71 @@ def test_batchnorm_invariants_at_full_size(rows, C, G):
     scale = d.abs().sum(1)                                          # per (group, channel)
     assert (d.sum(1).abs() / scale).max().item() < 2e-3             # bf16 rounding of ~1e6 terms with random signs
     assert ((d * xh).sum(1).abs() / scale).max().item() < 2e-3
+
+
+THIN_FULL = [
+    # name, N, H (image side), Co
+    ("stage2 critic ds0, batch 64 x 3 groups (256x256x3 <-> 128x128x16)", 192, 256, 16),
+    ("stage2 G2 up3, batch 64 (128x128x80 <-> 256x256x3)", 64, 256, 80),
+    ("stage1 critic ds0, batch 128 x 3 groups (64x64x3 <-> 32x32x64)", 384, 64, 64),
+]
+
+
+@pytest.mark.parametrize("case", THIN_FULL, ids=[c[0] for c in THIN_FULL])
+def test_thin_kernels_adjoint_and_linear_at_full_size(case):
+    """The direct 3-channel kernels (thin_conv.cu) at BASELINE.json's full sizes: Conv2d(3->C) and ConvTranspose2d(C->3) of the
+    same weights are mutually adjoint, both agree with the weight gradient taken through the patch matrix, and both are linear."""
+    from imagegenerator_b200.ops import CudaOps
+    _, N, H, Co = case
+    ops = CudaOps("bf16")
+    assert ops.lib.sg_conv_thin_supported(0, N, H, H, 3, H // 2, H // 2, Co, 4, 2, 1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(N, H, H, 3, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(N, H // 2, H // 2, Co, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Co, 3, 4, 4, device="cuda", generator=g) * 48 ** -0.5).to(torch.bfloat16).float()
+    pf, pd = ops.empty((Co, 4, 4, 3)), ops.empty((3, 4, 4, Co))
+    ops.pack_weight(w, pf, pd)
+    y, dx = ops.empty((N, H // 2, H // 2, Co)), ops.empty((N, H, H, 3))
+    ops.conv_fprop(x, pf, None, y, 4, 2, 1)
+    ops.conv_dgrad(dy, pd, None, dx, 4, 2, 1)
+    P = ops.empty((N, H // 2, H // 2, 48))
+    ops.patchify(x, P, 4, 2, 1)
+    dw = torch.zeros(Co, 48, 1, 1, device="cuda")
+    ops.conv_wgrad(P, dy, dw, 1, 1, 0)                                  # PyTorch weight order (ci, kh, kw)
+    torch.cuda.synchronize()
+    a, b, c = _dot(dy, y), _dot(dx, x), _dot(dw, w.reshape(Co, 48, 1, 1))
+    scale = (dy.double().norm() * y.double().norm()).item()
+    assert abs(a - c) <= 2e-4 * scale and abs(b - c) <= 2e-4 * scale, (a, b, c, scale)
+    y2, dx2 = ops.empty(y.shape), ops.empty(dx.shape)
+    ops.conv_fprop((x.float() * 2).to(torch.bfloat16), pf, None, y2, 4, 2, 1)
+    ops.conv_dgrad((dy.float() * 2).to(torch.bfloat16), pd, None, dx2, 4, 2, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(y2.float(), y.float() * 2) and torch.equal(dx2.float(), dx.float() * 2)
+
+
+def test_fused_bn_backward_statistics_at_full_size():
+    """sg_conv_dgrad_bstats on the deepest Stage-II residual conv (640 -> 320, batch 64): the statistics that leave the conv
+    epilogue equal what sg_bn_bwd_reduce computes from the stored gradient, and the gradient equals the plain dgrad's."""
+    from imagegenerator_b200.ops import CudaOps, ACT_RELU
+    ops = CudaOps("bf16")
+    N, H, Ci, Co = 64, 16, 320, 640                                     # dgrad: dy [N,16,16,640] -> dx [N,16,16,320]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dy = torch.randn(N, H, H, Co, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * (Co * 9) ** -0.5
+    pd = ops.empty((Ci, 3, 3, Co))
+    ops.pack_weight(w, None, pd)
+    ybn = (torch.randn(N, H, H, Ci, device="cuda", generator=g) * 1.3).to(torch.bfloat16)
+    mr = torch.stack([torch.randn(1, Ci, device="cuda", generator=g) * 0.2, torch.rand(1, Ci, device="cuda", generator=g) + 0.5], -1)
+    gamma, beta = torch.rand(Ci, device="cuda", generator=g) + 0.5, torch.randn(Ci, device="cuda", generator=g) * 0.3
+    dx, dx_ref = ops.empty((N, H, H, Ci)), ops.empty((N, H, H, Ci))
+    sums = torch.full((1, Ci, 2), 3.0, dtype=torch.float64, device="cuda")
+    want = torch.zeros_like(sums)
+    ops.set_option("bstats_min_k", 0)
+    ops.conv_dgrad_bstats(dy, pd, dx, ybn, mr, gamma, beta, sums, 1, ACT_RELU, 3, 1, 1)
+    ops.set_option("bstats_min_k", 4000)
+    ops.conv_dgrad(dy, pd, None, dx_ref, 3, 1, 1)
+    ops.bn_bwd_reduce(dx, None, ybn, mr, want, 1, ACT_RELU, gamma=gamma, beta=beta)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx_ref)
+    scale = dx.double().abs().sum(dim=(0, 1, 2))[None, :, None] * 8.0
+    assert ((sums - want).abs() <= 2e-4 * scale + 1e-6).all(), ((sums - want).abs() / scale).max().item()
