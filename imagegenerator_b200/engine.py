@@ -353,16 +353,24 @@ class CriticRT:
         # memset per forward instead of one per layer
         self.stats_flat = ops.zeros((2 * G * sum(L.co for L in self.layers[1:]),), f64)
         soff = 0
+        # The weight gradient of layer l has two terms with the same weights: wgrad(a[l], dy[l]) over the three image groups of
+        # the plain backward and wgrad(w[l], gdy[l]) of the gradient penalty's second-order pass (one group, a third of the
+        # rows: a launch at half the efficiency).  w[l] and gdy[l] therefore live as a FOURTH group right behind a[l] and
+        # dy[l] (a_full / dy_full), so that one launch over 4B images does both (backward(merge_gp=True)).
+        self.a_full, self.dy_full = [None], []
         for l, L in enumerate(self.layers):
             h = _conv_out(h, L.k, L.s, L.p)
             shp, shp1 = (G * B, h, h, L.co), (B, h, h, L.co)
-            self.a.append(ops.empty(shp))
+            af, dyf = ops.empty(((G + 1) * B, h, h, L.co)), ops.empty(((G + 1) * B, h, h, L.co))
+            self.a_full.append(af)
+            self.dy_full.append(dyf)
+            self.a.append(af[:G * B])
             self.da.append(ops.empty(shp))
-            self.dy.append(ops.empty(shp))
+            self.dy.append(dyf[:G * B])
             self.gda.append(ops.empty(shp1))
-            self.gdy.append(ops.empty(shp1))
+            self.gdy.append(dyf[G * B:])
             self.v.append(ops.empty(shp1))
-            self.w.append(ops.empty(shp1))
+            self.w.append(af[G * B:])
             if l > 0:
                 self.y.append(ops.empty(shp))
                 self.mr.append(ops.empty((G, L.co, 2), f32))
@@ -379,8 +387,8 @@ class CriticRT:
         L0 = self.layers[0]
         h1 = _conv_out(module.in_hw, L0.k, L0.s, L0.p)
         self.K0 = L0.ci * L0.k * L0.k
-        self.P = ops.empty((G * B, h1, h1, self.K0))
-        self.Pv = ops.empty((B, h1, h1, self.K0))
+        self.P_full = ops.empty(((G + 1) * B, h1, h1, self.K0))        # patches of the images, then (4th group) of v0
+        self.P, self.Pv = self.P_full[:G * B], self.P_full[G * B:]
         cl, Nd = self.layers[-1].co, module.Nd
         self.head_grads = ops.zeros((16 * cl + Nd,), f32)            # dA and dBv: zeroed together every iteration
         self.A, self.dA = ops.empty((16, cl), f32), self.head_grads[:16 * cl].view(16, cl)
@@ -508,11 +516,15 @@ class CriticRT:
         ops, L0 = self.ops, self.layers[0]
         ops.conv_dgrad(dy0, L0.pd, None, dx, L0.k, L0.s, L0.p)
 
-    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, head_reduce=True, input_grad_from=None, side=None):
+    def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, head_reduce=True, input_grad_from=None, side=None,
+                 merge_gp=False):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
         d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).  ``coef`` holds the ng*B
         coefficients of these groups.  Groups are independent (own BN statistics, disjoint buffer slices; parameter gradients
-        accumulate with atomic adds), so two calls on disjoint groups may run on different streams."""
+        accumulate with atomic adds), so two calls on disjoint groups may run on different streams.  ``merge_gp`` (with all
+        three groups): every conv weight gradient also covers the gradient penalty's second-order term -- the fourth group of
+        a_full / dy_full, filled by gp_first_order / gp_second_order(defer_wgrad=True) -- in the same launch."""
+        merge_gp = merge_gp and param_grads and g0 == 0 and ng == self.NG
         ops, nl = self.ops, self.nl
         gv = lambda t: self.group_view(t, g0, ng)
         a4 = gv(self.a[nl])
@@ -531,7 +543,10 @@ class CriticRT:
                              inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data)
             if param_grads:
                 bn_items.append((sums, bn.weight.grad, bn.bias.grad))
-                _side_run(side, lambda l=l, L=L, dy=dy: ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p))
+                if merge_gp:
+                    _side_run(side, lambda l=l, L=L: ops.conv_wgrad(self.a_full[l], self.dy_full[l], L.conv.weight.grad, L.k, L.s, L.p))
+                else:
+                    _side_run(side, lambda l=l, L=L, dy=dy: ops.conv_wgrad(gv(self.a[l]), dy, L.conv.weight.grad, L.k, L.s, L.p))
             if l >= 2:
                 # d/d a of layer l-1 + that layer's BatchNorm-backward statistics in the same kernel
                 bnb = self.layers[l - 1].bn
@@ -546,7 +561,10 @@ class CriticRT:
         if param_grads:
             def pgrad0():
                 ops.bn_param_grad_multi(bn_items)
-                ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
+                if merge_gp:
+                    ops.conv_wgrad(self.P_full, self.dy_full[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
+                else:
+                    ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
                 ops.colsum(dy0, L0.conv.bias.grad)
             _side_run(side, pgrad0)
         if need_input_grad:
@@ -598,9 +616,11 @@ class CriticRT:
         self.input_grad(self.gdy[0], self.g)
         ops.sample_sqnorm(self.g, self.sq)
 
-    def gp_second_order(self, coef, side=None):
+    def gp_second_order(self, coef, side=None, defer_wgrad=False):
         """Backward of coef/2 * sum_b (||g_b||-1)^2 through the first-order graph: parameter grads
-        via wgrad / gamma / head, and gy[l] = d/d y_l for the plain backward to pick up."""
+        via wgrad / gamma / head, and gy[l] = d/d y_l for the plain backward to pick up.  ``defer_wgrad``: leave the conv
+        weight-gradient terms to the plain backward that follows (backward(merge_gp=True) covers w[l] / gdy[l] as a fourth
+        group of its own launches); only the patch matrix of v0 is built here."""
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
         ops.gp_seed(self.g, self.sq, coef, self.v0)
@@ -609,13 +629,15 @@ class CriticRT:
 
         def pgrad_v0():
             ops.patchify(self.v0, self.Pv, L0.k, L0.s, L0.p)
-            ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
+            if not defer_wgrad:
+                ops.conv_wgrad(self.Pv, self.gdy[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
         _side_run(side, pgrad_v0)
         ops.act_bwd(self.v[0], i2(self.a[1]), self.w[1], ACT_LRELU)
         for l in range(1, nl):
             L, bn = self.layers[l], self.layers[l].bn
             ops.conv_fprop(self.w[l], L.pf, None, self.v[l], L.k, L.s, L.p)
-            _side_run(side, lambda l=l, L=L: ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p))
+            if not defer_wgrad:
+                _side_run(side, lambda l=l, L=L: ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p))
             mr = self.mr[l][2:3]
             ops.gp_bn_reduce(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.tsums[l], ACT_LRELU)
             ops.gp_bn_apply(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
@@ -811,7 +833,7 @@ class Stage1Engine:
         d.gp_first_order()                                       # utils.py:15-24
         # :140-144; only the host reads the loss values: off the main stream
         self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
-        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
+        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side, defer_wgrad=True)
         # head/text gradients first (dA is complete once the plain backward has added its head term)
         ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA)
         self.side.run(lambda: d.text_backward(d.coef_text, 2 * B, 0.0, True, None))
@@ -820,7 +842,7 @@ class Stage1Engine:
         # Stage-I 5.56 -> 5.98 ms, Stage-II 34.6 -> 36.1 ms, 508 -> 603 launches): the persistent conv kernels take every SM
         # they can get, so the two chains do not really overlap, and every split launch pays its fixed ~10 us again.
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
-                   head_reduce=False, side=self.side)
+                   head_reduce=False, side=self.side, merge_gp=True)
         self.optimizer_step(d.fp)                                # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
         self.pack_side.run(lambda: d.refresh_weights(with_text=True, events=True))

@@ -342,9 +342,9 @@ class Stage2Engine:
         d.gp_first_order()
         # :148-152; only the host reads the loss values: off the main stream
         self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
-        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side)
+        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side, defer_wgrad=True)
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=True,      # :154
-                   input_grad_from=1, side=self.side)               # d/d real images is never used
+                   input_grad_from=1, side=self.side, merge_gp=True)   # d/d real images is never used
         self.side.run(lambda: d.text_backward(d.coef_text, 2 * B, 0.0, True, None))
         # d loss_critic / d fake_256 = d/d(fake group) + (1 - eps) * d/d(interpolated group)  (utils.py:11, not detached)
         ops.affine_f32(eps_gp, -1.0, 1.0, self.one_minus_eps)
