@@ -37,6 +37,10 @@ int sg_conv_fprop_tc_bstats(const void*, const void*, void*, const void*, const 
 int sg_conv_dgrad_tc_bstats(const void*, const void*, void*, const void*, const float*, const float*, const float*, double*, int, int,
                             int, int, int, int, int, int, int, int, int, int, void*);
 int sg_bn_bwd_reduce_y(const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, int, void*);
+int sg_conv_narrow_supported(int, int, int, int, int, int, int, int, int, int, int);
+int sg_conv_narrow_routed(int, int, int, int, int, int, int, int, int, int, int);
+int sg_conv_narrow_fprop(const void*, const void*, const float*, void*, double*, int, int, int, int, int, int, int, void*);
+int sg_conv_narrow_dgrad(const void*, const void*, const float*, void*, int, int, int, int, int, int, void*);
 int sg_conv_thin_supported(int, int, int, int, int, int, int, int, int, int, int);
 int sg_conv_thin_fprop(const void*, const void*, const float*, void*, int, int, int, int, int, void*);
 int sg_conv_thin_dgrad(const void*, const void*, const float*, void*, int, int, int, int, int, void*);
@@ -54,6 +58,9 @@ int sg_conv_fprop(const void* x, const void* pf, const float* bias, void* y, int
     if (dtype == SG_BF16) {
         // the 3-channel image side: direct kernel (thin_conv.cu), the 128-row tcgen05 tiles have nothing to contract there
         if (sg_conv_thin_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return sg_conv_thin_fprop(x, pf, bias, y, N, H, W, Co, act, stream);
+        // 16 / 32 input channels on large maps: HBM-bound, direct kernel (narrow_conv.cu) where it is the faster one
+        if (sg_conv_narrow_routed(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+            return sg_conv_narrow_fprop(x, pf, bias, y, nullptr, 1, N, H, W, Ci, Co, act, stream);
         if (!sg_conv_tc_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_fprop", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_fprop_tc(x, pf, bias, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
     }
@@ -63,6 +70,8 @@ int sg_conv_dgrad(const void* dy, const void* pd, const float* bias, void* dx, i
                   int Co, int k, int s, int p, int act, int dtype, void* stream) {
     if (dtype == SG_BF16) {
         if (sg_conv_thin_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return sg_conv_thin_dgrad(dy, pd, bias, dx, N, Ho, Wo, Co, act, stream);
+        if (sg_conv_narrow_routed(1, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+            return sg_conv_narrow_dgrad(dy, pd, bias, dx, N, Ho, Wo, Ci, Co, act, stream);
         if (!sg_conv_tc_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p)) return unsupported("conv_dgrad", N, H, W, Ci, Ho, Wo, Co, k, s, p);
         return sg_conv_dgrad_tc(dy, pd, bias, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, act, dtype, stream);
     }
@@ -82,6 +91,8 @@ int sg_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,
 // tensor-core epilogue when the shape allows, otherwise conv + sg_col_stats.
 int sg_conv_fprop_stats(const void* x, const void* pf, void* y, double* stats, int groups, int N, int H, int W, int Ci,
                         int Ho, int Wo, int Co, int k, int s, int p, int dtype, void* stream) {
+    if (dtype == SG_BF16 && groups >= 1 && N % groups == 0 && sg_conv_narrow_routed(0, N, H, W, Ci, Ho, Wo, Co, k, s, p))
+        return sg_conv_narrow_fprop(x, pf, nullptr, y, stats, groups, N, H, W, Ci, Co, SG_ACT_NONE, stream);
     if (dtype == SG_BF16 && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups))
         return sg_conv_fprop_tc_stats(x, pf, y, stats, groups, N, H, W, Ci, Ho, Wo, Co, k, s, p, dtype, stream);
     int e = sg_conv_fprop(x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, dtype, stream);

@@ -1410,6 +1410,7 @@ static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
 // (the tap's share of the activation slab + BN/CG rows of B) at ~44 B/cycle/SM (the ~12 TB/s L2->SM ceiling shared by
 // 148 SMs).
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
+extern int g_use_narrow, g_narrow_cfg; // narrow_conv.cu
 int g_use_slab = 1;      // option "slab": 0 = one activation box per tap (no sharing), for A/B measurements
 // option "dyn_sched" / env SG_DYN_SCHED: dynamic work distribution in the persistent conv kernel (see decode_work); needs the
 // counter pool of sg_init_workspace().  OFF by default: measured on B200 (round 2, bench.py) Stage-I 5.42 -> 5.60 ms and
@@ -1876,6 +1877,8 @@ int sg_init_workspace(void) {
 int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "slab")) { g_use_slab = value; return 0; }
     if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
+    if (name && !strcmp(name, "narrow")) { g_use_narrow = value; return 0; }
+    if (name && !strcmp(name, "narrow_cfg")) { g_narrow_cfg = value; return 0; }
     if (name && !strcmp(name, "dyn_sched")) { g_dyn_sched = value; return 0; }
     if (name && !strcmp(name, "bstats_min_k")) { g_bstats_min_k = value; return 0; }
     if (name && !strcmp(name, "rotate")) { g_rotate = value; return 0; }

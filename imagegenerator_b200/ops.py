@@ -94,12 +94,14 @@ _SIGS = {
     "sg_gen_loss": [_P, _P, _P, _P, _I, _I, _P],
     "sg_scale_rows_add": [_P, _P, _P, _I, _I, _L, _I, _P],
     "sg_adam_step": [_P, _P, _P, _P, _P, _L, _P],
+    "sg_conv_narrow_fprop": [_P, _P, _P, _P, _P] + [_I] * 7 + [_P],
+    "sg_conv_narrow_dgrad": [_P, _P, _P, _P] + [_I] * 6 + [_P],
     "sg_conv_thin_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "sg_conv_thin_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
 }
 
 EXPORTS = sorted(list(_SIGS) + ["sg_version", "sg_last_error", "sg_check_device", "sg_launch_count", "sg_conv_tc_supported", "sg_conv_wgrad_tc_supported", "sg_set_option",
-                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace", "sg_conv_thin_supported", "sg_init_workspace",
+                                 "sg_conv_tc_stats_supported", "sg_conv_wgrad_cl_supported", "sg_debug_conv_trace", "sg_conv_thin_supported", "sg_conv_narrow_supported", "sg_conv_narrow_routed", "sg_init_workspace",
                                  "sg_dp_max_world", "sg_dp_flag_ints", "sg_dp_sync_ints", "sg_dp_adam_step"])
 
 
@@ -326,6 +328,17 @@ class CudaOps:
         d = self._conv_dims(dx, dy)
         fn = getattr(self.lib, "sg_conv_dgrad" + impl)
         self._ck(fn(_ptr(dy), _ptr(pd), _ptr(bias), _ptr(dx), *d, k, s, p, act, self._dt_of(dy), self._st()))
+
+    def conv_narrow_fprop(self, x, pf, bias, y, act=ACT_NONE, stats=None, groups=1):
+        """The direct k4 s2 p1 kernel of narrow_conv.cu by name (conv_fprop / conv_fprop_stats route to it where it is faster)."""
+        self._c(x, pf, bias, y, stats)
+        N, H, W, Ci, Ho, Wo, Co = self._conv_dims(x, y)
+        self._ck(self.lib.sg_conv_narrow_fprop(_ptr(x), _ptr(pf), _ptr(bias), _ptr(y), _ptr(stats), groups, N, H, W, Ci, Co, act, self._st()))
+
+    def conv_narrow_dgrad(self, dy, pd, bias, dx, act=ACT_NONE):
+        self._c(dy, pd, bias, dx)
+        N, H, W, Ci, Ho, Wo, Co = self._conv_dims(dx, dy)
+        self._ck(self.lib.sg_conv_narrow_dgrad(_ptr(dy), _ptr(pd), _ptr(bias), _ptr(dx), N, Ho, Wo, Ci, Co, act, self._st()))
 
     def conv_fprop_stats(self, x, pf, y, stats, groups, k, s, p):
         """y = conv(x); stats[groups][Co][2] += (sum, sum^2) of y per image group (BN batch statistics)."""

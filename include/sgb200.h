@@ -117,6 +117,20 @@ int sg_conv_thin_fprop(const void* x, const void* pf, const float* bias, void* y
 int sg_conv_thin_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Ho, int Wo, int Co, int act,
                        void* stream);
 
+/* ---- narrow-channel k4 s2 p1 convs as direct kernels (narrow_conv.cu; bf16 only) -----------------------------------------
+ * (Ci, Co) in {(16, 32), (32, 64)} on large maps -- the Stage-II critic's second and third layer (discriminator_2.py:13-18) and
+ * their data gradients: HBM-bound shapes (150 MB for 13 GFLOP) whose 128 x 32 tcgen05 tiles cost more in the epilogue than in
+ * the mainloop.  Persistent CTAs, weights staged once, input tiles through a cp.async ring, mma.sync.  Output grid rows % 8 == 0,
+ * columns % 32 == 0.  sg_conv_fprop / sg_conv_fprop_stats / sg_conv_dgrad route a supported shape here when option "narrow"
+ * selects it -- a bit mask: 1 forward 16->32, 2 data gradient 16<-32, 4 forward 32->64, 8 data gradient 32<-64; the default is the
+ * set measured faster than the tcgen05 kernel on B200 (sg_conv_narrow_routed reports the decision). */
+int sg_conv_narrow_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
+int sg_conv_narrow_routed(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
+int sg_conv_narrow_fprop(const void* x, const void* pf, const float* bias, void* y, double* stats, int groups, int N, int H, int W,
+                         int Ci, int Co, int act, void* stream);
+int sg_conv_narrow_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Ho, int Wo, int Ci, int Co, int act,
+                         void* stream);
+
 /* out[n,hw,:Cx] = x, out[n,hw,Cx:] = c[n]  (generator_2.py:61-63 reshape/repeat/cat);  backward:
  * dx = dout[..., :Cx], dc[n] (fp32) = sum_hw dout[n,hw,Cx:] */
 int sg_concat_rep(const void* x, const float* c, void* out, int N, int HW, int Cx, int Cc, int dtype, void* stream);

@@ -141,6 +141,14 @@ class EmuOps:
         assert out.shape[2] == dx.shape[1], (out.shape, dx.shape)
         dx.copy_(nhwc(_act(out, act)).to(dx.dtype))
 
+    def conv_narrow_fprop(self, x, pf, bias, y, act=ACT_NONE, stats=None, groups=1):
+        self.conv_fprop(x, pf, bias, y, 4, 2, 1, act=act)
+        if stats is not None:
+            self.col_stats(y, stats, groups)
+
+    def conv_narrow_dgrad(self, dy, pd, bias, dx, act=ACT_NONE):
+        self.conv_dgrad(dy, pd, bias, dx, 4, 2, 1, act=act)
+
     def conv_fprop_stats(self, x, pf, y, stats, groups, k, s, p):
         """conv + (sum, sum^2) of the STORED result per image group (the statistics of the BN that follows)."""
         self.conv_fprop(x, pf, None, y, k, s, p)

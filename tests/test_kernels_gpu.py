@@ -137,6 +137,80 @@ def test_thin_conv_dgrad_direct(case, act, use_bias):
     run_pair("bf16", "conv_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, 3)), 4, 2, 1], [3], dict(act=act))
 
 
+# 16 / 32 input channels on large maps: the direct kernels of narrow_conv.cu, by name (persistent CTAs: a CTA walks several tiles
+# as soon as there are more tiles than SMs) and through the dispatcher's routing mask
+NARROW_CASES = [
+    # N, H (input side), Ci, Co, groups
+    (3, 64, 16, 32, 3),       # one 8 x 32 tile column, four tile rows: 12 tiles, one per CTA
+    (2, 128, 16, 32, 1),      # Stage-II critic ds1 at half size (2 x 8 tiles per image)
+    (1, 256, 16, 32, 1),      # ... at full size
+    (24, 128, 16, 32, 3),     # 384 tiles on 148 CTAs: 2-3 tiles per CTA, ranges crossing image and group boundaries
+    (6, 64, 32, 64, 3),       # Stage-II critic ds2 (64 x 64 -> 32 x 32)
+    (2, 128, 32, 64, 2),
+    (45, 64, 32, 64, 3),      # 180 tiles: one or two per CTA
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", NARROW_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True)])
+def test_narrow_conv_fprop_direct(case, act, use_bias):
+    N, H, Ci, Co, G = case
+    x, w = rnd(N, H, H, Ci), rnd(Co, Ci, 4, 4, scale=(16 * Ci) ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    bias = F(rnd(Co)) if use_bias else None
+    run_pair("bf16", "conv_narrow_fprop", [T(x), T(pf), bias, T(torch.zeros(N, H // 2, H // 2, Co))], [3], dict(act=act))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", NARROW_CASES)
+def test_narrow_conv_fprop_stats(case):
+    N, H, Ci, Co, G = case
+    x, w = rnd(N, H, H, Ci), rnd(Co, Ci, 4, 4, scale=(16 * Ci) ** -0.5)
+    pf = w.permute(0, 2, 3, 1).contiguous()
+    st0 = torch.ones(G, Co, 2, dtype=torch.float64) * 0.25
+    ea, ca = run_pair("bf16", "conv_narrow_fprop", [T(x), T(pf), None, T(torch.zeros(N, H // 2, H // 2, Co)), ACT_NONE, D(st0), G], [3])
+    _check_stats(ca[3], ca[5], st0, G)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", NARROW_CASES)
+@pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True)])
+def test_narrow_conv_dgrad_direct(case, act, use_bias):
+    N, H, Ci, Co, G = case
+    dy, w = rnd(N, H // 2, H // 2, Co), rnd(Co, Ci, 4, 4, scale=(Co * 4) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    bias = F(rnd(Ci)) if use_bias else None
+    run_pair("bf16", "conv_narrow_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci))], [3], dict(act=act))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mask", [0, 15])
+def test_narrow_routing_mask(mask):
+    """Option "narrow" (bit mask) decides which supported shapes the dispatcher sends to narrow_conv.cu; both backends agree."""
+    ops = _ops("bf16")
+    N, H, Ci, Co = 2, 128, 16, 32
+    dims = (N, H, H, Ci, H // 2, H // 2, Co, 4, 2, 1)
+    x = (rnd(N, H, H, Ci)).to(torch.bfloat16).cuda()
+    pf = rnd(Co, 4, 4, Ci, scale=(16 * Ci) ** -0.5).to(torch.bfloat16).cuda()
+    ya, yb = ops.empty((N, H // 2, H // 2, Co)), ops.empty((N, H // 2, H // 2, Co))
+    ops.conv_narrow_fprop(x, pf, None, ya)
+    default = [m for m in range(16) if all(bool(ops.lib.sg_conv_narrow_routed(md, N, H, H, ci, H // 2, H // 2, 2 * ci, 4, 2, 1)) == bool(m & ((2 if md else 1) << (2 if ci == 32 else 0)))
+                                           for md in (0, 1) for ci in (16, 32))][0]
+    ops.set_option("narrow", mask)
+    try:
+        assert ops.lib.sg_conv_narrow_supported(0, *dims) == 1
+        assert ops.lib.sg_conv_narrow_routed(0, *dims) == (1 if mask else 0)
+        assert ops.lib.sg_conv_narrow_routed(1, *dims) == (1 if mask else 0)
+        n0 = ops.launch_count()
+        ops.conv_fprop(x, pf, None, yb, 4, 2, 1)
+        assert ops.launch_count() == n0 + 1
+    finally:
+        ops.set_option("narrow", default)
+    torch.cuda.synchronize()
+    assert torch.allclose(ya.float(), yb.float(), rtol=2e-2, atol=2e-2)
+
+
 def test_bf16_dispatch_refuses_unsupported_shapes():
     from imagegenerator_b200.ops import CudaOps
     ops = CudaOps("bf16")

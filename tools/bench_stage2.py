@@ -18,6 +18,8 @@ torch.manual_seed(42)
 ca1, g1 = ConditioningAugmentation(512, 256, 128), StageIGenerator(128, 100)
 ca2, d2, g2 = ConditioningAugmentation(512, 256, 128), StageIIDiscriminator(512, 128), StageIIGenerator()
 ops = CudaOps(mode)
+for kv in filter(None, os.environ.get("SG_OPTS", "").split(",")):      # e.g. SG_OPTS=narrow=0
+    ops.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 eng = Stage2Engine(ca1, g1, ca2, d2, g2, B, ops=ops)
 g = torch.Generator().manual_seed(0)
 dev = "cuda"
