@@ -11,6 +11,16 @@
 #include <cstdlib>
 #include "common.cuh"
 
+// Register budget of the HBM-bound BatchNorm kernels.  Default: two CTAs of 256 threads per SM at up to 128 registers (the whole
+// register file).  -DSG_BN_MAXREG=88 caps them so that two CTAs (45 k registers) leave room for one conv_wgrad2 CTA (192 threads x
+// 92 registers) on the same SM: the side stream's tensor-bound weight-gradient kernels can then run UNDER the main chain's
+// bandwidth-bound passes instead of alternating with them.
+#ifdef SG_BN_MAXREG
+#define SG_BN_BOUNDS __maxnreg__(SG_BN_MAXREG)
+#else
+#define SG_BN_BOUNDS __launch_bounds__(256, 2)
+#endif
+
 namespace sg {
 
 struct V8 {
@@ -129,7 +139,7 @@ __device__ __forceinline__ void bn_mean_var(const double* stats, int64_t gc, dou
     if (var < 0) var = 0;
 }
 template <typename T, bool FIN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void SG_BN_BOUNDS
 bn_act8_kernel(const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out, Chunking k, int act,
                BnFinalize f) {
@@ -239,7 +249,7 @@ bn_act8_kernel(const T* __restrict__ y, const float* __restrict__ mr, const floa
 // ---- sums[g][c] += (sum dz, sum dz*xhat), dz = da * act'(a_out).  HAS_A = false: the activation output is not read;
 // its sign is recomputed from y (a = act(gamma*xhat + beta) has the sign of its argument), one tensor less to stream
 template <typename T, bool HAS_A>
-__global__ void __launch_bounds__(256, 2)
+__global__ void SG_BN_BOUNDS
 bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                       const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
                       double* __restrict__ sums, Chunking k, float slope) {
@@ -341,7 +351,7 @@ bn_bwd_reduce8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, con
 
 // ---- dy = gamma*rstd/n * (n dz - S1 - xhat S2) [+ inject on one group]
 template <typename T, bool HAS_A>
-__global__ void __launch_bounds__(256, 2)
+__global__ void SG_BN_BOUNDS
 bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                      const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const double* __restrict__ sums, const T* __restrict__ inject, int inject_group, T* __restrict__ dy,
@@ -435,7 +445,7 @@ act_bwd8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __rest
 // ---- gradient-penalty double backward through a train-mode BN (one image group), 8-wide.
 // reduce: tsums[c] += (sum v, sum v*xhat, sum v*dz)
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void SG_BN_BOUNDS
 gp_bn_reduce8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                      const float* __restrict__ mr, double* __restrict__ tsums, Chunking k, float slope) {
     SG_PDL_SYNC();
@@ -474,7 +484,7 @@ gp_bn_reduce8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T*
 // apply: w = u*act', gy = d/dy of the penalty term; the 8 per-channel constants live in shared memory
 //   u = A v - B1 - xhat B2,  G = -(E v + B2 dz),  gy = r (G - K1 - xhat K2)
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void SG_BN_BOUNDS
 gp_bn_apply8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                     const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
                     const double* __restrict__ tsums, T* __restrict__ w_out, T* __restrict__ gy_out, Chunking k, float slope,

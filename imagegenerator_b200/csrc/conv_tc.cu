@@ -1707,6 +1707,9 @@ static int get_rows_map_n(const void* ptr, int64_t rows, int C, int npix, CUtens
 }
 
 int g_use_wgrad_mc = 1;
+// option "wgrad_smem_kb": shared memory the wgrad pipeline may take (stages = that / stage bytes).  200 = the whole SM; ~150
+// leaves room for the BatchNorm kernels' CTAs next to a wgrad CTA (co-residency experiment, bn_fast.cu SG_BN_MAXREG)
+int g_wgrad_smem_kb = 200;
 // option "wgrad_mc_max": largest co-tile cluster the launcher may pick.  The kernel takes 2..8; the default stays at PAIRS:
 // measured on B200 (profiles/bench_wgrad_r2c.txt, bench_wgrad_r2d.txt) clusters of 3-5 co tiles never beat unicast even when
 // the whole grid is co-resident (res1: 75.9 us as triples, 64.4 us unicast; res3 / up0 as quintuples 65.5 / 107.6 vs
@@ -1721,8 +1724,9 @@ static int launch_wgrad2_pix(const void* x, const void* dy, TcW2Params P, int N,
     if (!choose_box_n(PIX, Ho, Wo, &bw, &bh, &bn)) { set_error("wgrad2: grid not tileable"); return SG_ERR_UNSUPPORTED; }
     P.total_kb = (P.Mpix + PIX - 1) / PIX;
     const int stage_bytes = PIX * 128 * (2 + P.nun_max);
-    P.stages = (200 * 1024) / stage_bytes;
+    P.stages = (g_wgrad_smem_kb * 1024) / stage_bytes;
     if (P.stages > 8) P.stages = 8;
+    if (P.stages < 1) { P.stages = (200 * 1024) / stage_bytes; }      // a stage that does not fit the reduced budget keeps the full one
     CUtensorMap tmDy, tmX;
     if ((e = get_rows_map_n(dy, P.Mpix, Co, PIX, &tmDy))) return e;
     if ((e = get_act_map(x, N, H, W, Ci, bw, bh, bn, s, &tmX))) return e;
@@ -1879,6 +1883,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
     if (name && !strcmp(name, "narrow")) { g_use_narrow = value; return 0; }
     if (name && !strcmp(name, "narrow_cfg")) { g_narrow_cfg = value; return 0; }
+    if (name && !strcmp(name, "wgrad_smem_kb")) { g_wgrad_smem_kb = value < 48 ? 48 : (value > 200 ? 200 : value); return 0; }
     if (name && !strcmp(name, "dyn_sched")) { g_dyn_sched = value; return 0; }
     if (name && !strcmp(name, "bstats_min_k")) { g_bstats_min_k = value; return 0; }
     if (name && !strcmp(name, "rotate")) { g_rotate = value; return 0; }

@@ -354,7 +354,9 @@ static int g_nf_grid[4] = {0, 0, 0, 0}, g_nd_grid[4] = {0, 0, 0, 0};     // CTAs
 // bit mask -- 1: forward 16 -> 32, 2: data gradient 16 <- 32, 4: forward 32 -> 64, 8: data gradient 32 <- 64 (15 = all, 0 = none).
 // Default = the ones measured faster on B200 (tools/bench_conv.py, profiles/bench_conv_r2k_narrow.txt).
 int g_use_narrow = 3;
-int g_narrow_cfg = 0;          // option "narrow_cfg" (A/B): 1 = forward 16->32 as one CTA per SM with a two-deep ring, 2 = data gradient 16<-32 at one CTA per SM
+// option "narrow_cfg" (A/B), bits: 4 = the mma.sync kernels of this file instead of the tcgen05 ones of direct_tc.cu wherever both take
+// the shape; for the mma.sync kernels: 1 = forward 16->32 as one CTA per SM with a two-deep ring, 2 = data gradient 16<-32 at one CTA per SM
+int g_narrow_cfg = 0;
 
 template <typename K>
 static int persistent_grid(K kernel, size_t smem, int* cache) {
@@ -388,6 +390,20 @@ static cudaError_t launch_nd(const void* dy, const void* pd, const float* bias, 
                       (const bf16*)pd, bias, (bf16*)dx, Ho, Wo, act, tiles_w, tiles_h, total);
 }
 
+// direct_tc.cu: the same operators on tcgen05 (staged spatial tile as the UMMA operand)
+bool direct_tc_supported(int mode, int Ci, int Co, int Hs, int Ws);
+cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, void* y, double* stats, int groups, int N, int H, int W, int Ci,
+                            int Co, int act, cudaStream_t st);
+cudaError_t direct_tc_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Hi, int Wi, int Ci, int Co, int act,
+                            cudaStream_t st);
+
+static bool mma_sync_supported(int Ho, int Wo) { return Ho % NC_TH == 0 && Wo % NC_TW == 0; }
+// which implementation a supported shape runs on: tcgen05 (direct_tc.cu) unless option "narrow_cfg" bit 4 asks for mma.sync
+static bool use_direct_tc(int mode, int Ci, int Co, int Hs, int Ws, int Ho, int Wo) {
+    if (!direct_tc_supported(mode, Ci, Co, Hs, Ws)) return false;
+    return !(g_narrow_cfg & 4) || !mma_sync_supported(Ho, Wo);
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -400,7 +416,7 @@ int sg_conv_narrow_supported(int mode, int N, int H, int W, int Ci, int Ho, int 
     (void)mode;
     if (k != 4 || s != 2 || p != 1 || Ho * 2 != H || Wo * 2 != W || N < 1) return 0;
     if (!((Ci == 16 && Co == 32) || (Ci == 32 && Co == 64))) return 0;
-    return (Ho % NC_TH == 0 && Wo % NC_TW == 0) ? 1 : 0;
+    return (mma_sync_supported(Ho, Wo) || direct_tc_supported(mode, Ci, Co, mode ? Ho : H, mode ? Wo : W)) ? 1 : 0;
 }
 
 // Routing policy of sg_conv_fprop / sg_conv_fprop_stats / sg_conv_dgrad: supported AND selected by option "narrow" (above).
@@ -415,7 +431,8 @@ int sg_conv_narrow_fprop(const void* x, const void* pf, const float* bias, void*
                          int Ci, int Co, int act, void* stream) {
     SG_REQUIRE(sg_conv_narrow_supported(0, N, H, W, Ci, H / 2, W / 2, Co, 4, 2, 1), "conv_narrow_fprop: unsupported shape N=%d %dx%d %d->%d", N, H, W, Ci, Co);
     SG_REQUIRE(stats == nullptr || (groups >= 1 && N % groups == 0), "conv_narrow_fprop: N %% groups != 0");
-    cudaError_t ce = Ci == 32 ? launch_nf<32, 8, 1, 1>(x, pf, bias, y, stats, N, H, W, act, groups, SG_STREAM(stream))
+    cudaError_t ce = use_direct_tc(0, Ci, Co, H, W, H / 2, W / 2) ? direct_tc_fprop(x, pf, bias, y, stats, groups, N, H, W, Ci, Co, act, SG_STREAM(stream))
+                     : Ci == 32 ? launch_nf<32, 8, 1, 1>(x, pf, bias, y, stats, N, H, W, act, groups, SG_STREAM(stream))
                      : (g_narrow_cfg & 1) ? launch_nf<16, 4, 2, 1>(x, pf, bias, y, stats, N, H, W, act, groups, SG_STREAM(stream))
                                           : launch_nf<16, 4, 1, 2>(x, pf, bias, y, stats, N, H, W, act, groups, SG_STREAM(stream));
     if (ce != cudaSuccess) { set_error("conv_narrow_fprop launch: %s", cudaGetErrorString(ce)); return (int)ce; }
@@ -427,7 +444,8 @@ int sg_conv_narrow_fprop(const void* x, const void* pf, const float* bias, void*
 int sg_conv_narrow_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Ho, int Wo, int Ci, int Co, int act,
                          void* stream) {
     SG_REQUIRE(sg_conv_narrow_supported(1, N, 2 * Ho, 2 * Wo, Ci, Ho, Wo, Co, 4, 2, 1), "conv_narrow_dgrad: unsupported shape N=%d %dx%d %d<-%d", N, Ho, Wo, Ci, Co);
-    cudaError_t ce = Co == 64 ? launch_nd<64, 4, 1>(dy, pd, bias, dx, N, Ho, Wo, act, SG_STREAM(stream))
+    cudaError_t ce = use_direct_tc(1, Ci, Co, Ho, Wo, Ho, Wo) ? direct_tc_dgrad(dy, pd, bias, dx, N, Ho, Wo, Ci, Co, act, SG_STREAM(stream))
+                     : Co == 64 ? launch_nd<64, 4, 1>(dy, pd, bias, dx, N, Ho, Wo, act, SG_STREAM(stream))
                      : (g_narrow_cfg & 2) ? launch_nd<32, 2, 1>(dy, pd, bias, dx, N, Ho, Wo, act, SG_STREAM(stream))
                                           : launch_nd<32, 2, 2>(dy, pd, bias, dx, N, Ho, Wo, act, SG_STREAM(stream));
     if (ce != cudaSuccess) { set_error("conv_narrow_dgrad launch: %s", cudaGetErrorString(ce)); return (int)ce; }

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgb200.so")
+LIB_PATH = os.environ.get("SG_LIB") or os.path.join(_HERE, "libsgb200.so")      # SG_LIB: A/B builds of the same library (tools/)
 
 SG_F32, SG_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
@@ -165,6 +165,9 @@ class CudaOps:
         else:
             raise ValueError(dtype)
         self.f32, self.f64 = torch.float32, torch.float64
+        # A/B measurements without code edits: SG_OPTS="name=value,..." sets library options (include/sgb200.h, sg_set_option)
+        for kv in filter(None, os.environ.get("SG_OPTS", "").split(",")):
+            self.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     # ---- plumbing
     def _st(self):

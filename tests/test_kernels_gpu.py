@@ -151,37 +151,59 @@ NARROW_CASES = [
 ]
 
 
+class _narrow_impl:
+    """option "narrow_cfg" bit 4: the mma.sync kernels of narrow_conv.cu instead of the tcgen05 ones of direct_tc.cu"""
+
+    def __init__(self, impl):
+        self.v = 4 if impl == "mma_sync" else 0
+
+    def __enter__(self):
+        _ops("bf16").set_option("narrow_cfg", self.v)
+
+    def __exit__(self, *a):
+        _ops("bf16").set_option("narrow_cfg", 0)
+
+
+NARROW_IMPLS = ["tcgen05", "mma_sync"]
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("impl", NARROW_IMPLS)
 @pytest.mark.parametrize("case", NARROW_CASES)
 @pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True)])
-def test_narrow_conv_fprop_direct(case, act, use_bias):
+def test_narrow_conv_fprop_direct(case, act, use_bias, impl):
     N, H, Ci, Co, G = case
     x, w = rnd(N, H, H, Ci), rnd(Co, Ci, 4, 4, scale=(16 * Ci) ** -0.5)
     pf = w.permute(0, 2, 3, 1).contiguous()
     bias = F(rnd(Co)) if use_bias else None
-    run_pair("bf16", "conv_narrow_fprop", [T(x), T(pf), bias, T(torch.zeros(N, H // 2, H // 2, Co))], [3], dict(act=act))
+    with _narrow_impl(impl):
+        run_pair("bf16", "conv_narrow_fprop", [T(x), T(pf), bias, T(torch.zeros(N, H // 2, H // 2, Co))], [3], dict(act=act))
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("impl", NARROW_IMPLS)
 @pytest.mark.parametrize("case", NARROW_CASES)
-def test_narrow_conv_fprop_stats(case):
+def test_narrow_conv_fprop_stats(case, impl):
     N, H, Ci, Co, G = case
     x, w = rnd(N, H, H, Ci), rnd(Co, Ci, 4, 4, scale=(16 * Ci) ** -0.5)
     pf = w.permute(0, 2, 3, 1).contiguous()
     st0 = torch.ones(G, Co, 2, dtype=torch.float64) * 0.25
-    ea, ca = run_pair("bf16", "conv_narrow_fprop", [T(x), T(pf), None, T(torch.zeros(N, H // 2, H // 2, Co)), ACT_NONE, D(st0), G], [3])
+    with _narrow_impl(impl):
+        ea, ca = run_pair("bf16", "conv_narrow_fprop", [T(x), T(pf), None, T(torch.zeros(N, H // 2, H // 2, Co)), ACT_NONE, D(st0), G], [3])
     _check_stats(ca[3], ca[5], st0, G)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("impl", NARROW_IMPLS)
 @pytest.mark.parametrize("case", NARROW_CASES)
 @pytest.mark.parametrize("act,use_bias", [(ACT_NONE, False), (ACT_LRELU, True)])
-def test_narrow_conv_dgrad_direct(case, act, use_bias):
+def test_narrow_conv_dgrad_direct(case, act, use_bias, impl):
     N, H, Ci, Co, G = case
     dy, w = rnd(N, H // 2, H // 2, Co), rnd(Co, Ci, 4, 4, scale=(Co * 4) ** -0.5)
     pd = w.permute(1, 2, 3, 0).contiguous()
     bias = F(rnd(Ci)) if use_bias else None
-    run_pair("bf16", "conv_narrow_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci))], [3], dict(act=act))
+    with _narrow_impl(impl):
+        run_pair("bf16", "conv_narrow_dgrad", [T(dy), T(pd), bias, T(torch.zeros(N, H, H, Ci))], [3], dict(act=act))
 
 
 @pytest.mark.gpu
