@@ -1367,6 +1367,31 @@ static int get_slab_map(const void* ptr, int N, int H, int W, int C, int bw, int
     return 0;
 }
 
+// direct_tc.cu: NHWC bf16 tensor [N][H][W][C] (C = 16 / 32 / 64 channels = one swizzle span), box {C, bw*es, bh, 1} with element
+// stride es along W only: bw pixels es apart x bh consecutive rows -> shared memory [row][pixel][C], swizzled at C*2 bytes
+int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, CUtensorMap* out) {
+    if (int e = ensure_encode()) return e;
+    MapKey key(ptr, N, H, W, C, bw, bh, 1, es, 7);
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(bw * es), (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)es, 1, 1};
+    const CUtensorMapSwizzle sw = C == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap m;
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(direct N=%d H=%d W=%d C=%d box=%d,%d es=%d) failed: %d", N, H, W, C, bw, bh, es, (int)r);
+        return SG_ERR_UNSUPPORTED;
+    }
+    g_maps[key] = m;
+    *out = m;
+    return 0;
+}
+
 // packed weights [rows][Ktot] bf16 (K contiguous), box {64, BN}
 static int get_w_map(const void* ptr, int rows, int Ktot, int BN, CUtensorMap* out) {
     MapKey key(ptr, rows, Ktot, BN, 0, 0, 0, 0, 0, 2);
@@ -1411,6 +1436,7 @@ static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
 // 148 SMs).
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
 extern int g_use_narrow, g_narrow_cfg; // narrow_conv.cu
+extern int g_dtc_diag;                 // direct_tc.cu
 int g_use_slab = 1;      // option "slab": 0 = one activation box per tap (no sharing), for A/B measurements
 // option "dyn_sched" / env SG_DYN_SCHED: dynamic work distribution in the persistent conv kernel (see decode_work); needs the
 // counter pool of sg_init_workspace().  OFF by default: measured on B200 (round 2, bench.py) Stage-I 5.42 -> 5.60 ms and
@@ -1883,6 +1909,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "nsplit")) { g_use_nsplit = value; return 0; }
     if (name && !strcmp(name, "narrow")) { g_use_narrow = value; return 0; }
     if (name && !strcmp(name, "narrow_cfg")) { g_narrow_cfg = value; return 0; }
+    if (name && !strcmp(name, "dtc_diag")) { g_dtc_diag = value; return 0; }
     if (name && !strcmp(name, "wgrad_smem_kb")) { g_wgrad_smem_kb = value < 48 ? 48 : (value > 200 ? 200 : value); return 0; }
     if (name && !strcmp(name, "dyn_sched")) { g_dyn_sched = value; return 0; }
     if (name && !strcmp(name, "bstats_min_k")) { g_bstats_min_k = value; return 0; }

@@ -1,25 +1,31 @@
-// direct_tc.cu -- the narrow k4 s2 p1 convolutions on tcgen05, fed from a spatial tile staged ONCE in shared memory.
+// direct_tc.cu -- the narrow k4 s2 p1 convolutions on tcgen05, fed from spatial tiles staged by TMA.
 //
 // Why a third conv kernel.  The Stage-II critic's 16 -> 32 (and 32 -> 64) channel layers on 128x128 / 64x64 maps
-// (discriminator_2.py:13-18) are HBM-bound: 151 MB for 12.9 GFLOP.  The implicit-GEMM kernel (conv_tc.cu) fetches every tap's
-// operand rows with TMA -- 16 channels = 32-byte rows, thousands of them per 128-row tile -- and lands at 1.2 TB/s; the warp-level
-// mma.sync kernels (narrow_conv.cu) stop at ~175 TFLOP/s whatever their shape, the legacy tensor path's own rate on this part
-// (profiles/bench_conv_r2k_narrow.txt).  Here the input tile is brought in once (cp.async, 16-byte chunks, zero-filled padding)
-// in a layout that IS the canonical K-major no-swizzle UMMA operand layout for every tap at once, so one tcgen05.mma per
-// (tap, 16 channels) reads its 128 x 16 operand straight out of the staged tile through a shared-memory descriptor:
+// (discriminator_2.py:13-18) are HBM-bound: 151 MB for 12.9 GFLOP.  The implicit-GEMM kernel (conv_tc.cu) brings every tap's
+// operand in 64-channel k-blocks -- with 16 channels a k-block is four taps = four TMA boxes of 32-byte rows per 128-row tile --
+// and lands at 1.2 TB/s; the warp-level mma.sync kernels (narrow_conv.cu) plateau at 2 TB/s (profiles/bench_conv_r2k_narrow.txt).
+// Here a CTA stages a SPATIAL tile of the input and every tap's operand is a window of it, read by tcgen05.mma through a
+// shared-memory descriptor -- no im2col anywhere, each input byte crosses L2 -> SM once per column phase:
 //
-//   forward   M = 16 output rows x 8 output columns.  Row m = (r, c) of tap (kh, kw) is input pixel (2r + kh, 2c + kw) of the
-//             tile.  The tile is stored [input row][column parity][8-channel chunk][column / 2][8 channels]: the 8 pixels of a
-//             core matrix (fixed r, c = 0..7) are 8 consecutive 16-byte entries (column parity kw & 1, starting at kw >> 1),
-//             the next 8-channel chunk is one plane further (LBO), the next output row two input rows further (SBO).
-//   data      M = 16 x 8 INPUT (dy) pixels q; the four output parities are the N dimension: N = (ph, pw, ci), K runs over the
-//   gradient  nine neighbours (dr, dc) of q times the dy channels, the weight matrix holds tap (ph + 1 - 2dr, pw + 1 - 2dc) or
-//             zero.  One accumulator row is then two output rows x two output pixels x ci -- 2 x 64 contiguous bytes.
+//   forward   M tile = 16 output rows x 8 output columns.  Row m = (r, c) of tap (kh, kw) is input pixel (2r + kh, 2c + kw - 1).
+//             One TMA box per kw with element stride 2 along W brings [34 input rows][16 pixels two apart][C channels]; a
+//             pixel's C channels are one swizzle span (32 / 64 bytes), eight neighbouring output columns one swizzle atom,
+//             the next output row two staged rows further (SBO).  Tap (kh, kw) = copy kw, start row kh.  K = C per tap.
+//   data      M tile = 16 x 8 INPUT (dy) pixels q; the four output parities are the N dimension: N = (ph, pw, ci), K runs over
+//   gradient  the nine neighbours (dr, dc) of q times the dy channels; the weight matrix holds tap (ph + 1 - 2dr, pw + 1 - 2dc)
+//             or zero.  One box per dc (shifted by a pixel, so every window starts on an atom).  An accumulator row is two
+//             output rows x two output pixels x ci: 2 x 64 contiguous bytes.
 //
-// Persistent CTAs (one per SM, a contiguous range of tiles each): warp 0 issues the MMAs, warps 1-4 drain the accumulators
-// (double-buffered in TMEM: tcgen05.ld -> bias / activation -> bf16 -> 16-byte stores, BatchNorm statistics by a transposing
-// butterfly into per-lane running sums), warps 5-8 stage the tiles (two-deep ring).  Weights are staged once per CTA.
+// The conv's zero padding is TMA's out-of-bounds fill.  Persistent CTAs (one per SM, a contiguous range of tiles each): warp 0
+// issues the MMAs (one elected lane, descriptors advanced by integer adds), warps 1-4 drain the accumulators (double-buffered in
+// TMEM: tcgen05.ld -> bias / activation -> bf16 -> 16-byte stores, BatchNorm statistics by a transposing butterfly into per-lane
+// running sums), one lane of warp 5 issues the TMA boxes of a two-deep tile ring.  Weights are staged once per CTA.
+//
+// History (profiles/bench_conv_r2l_direct_tc.txt): the first versions staged the tile with cp.async (16 bytes per thread and
+// instruction) -- correct, and stuck at 2.0-2.4 TB/s like the mma.sync kernels whatever the MMA layout: the per-thread copies, not
+// the contraction, were the common ceiling.
 #include "common.cuh"
+#include <cuda.h>
 #include <type_traits>
 
 namespace sg {
@@ -50,6 +56,14 @@ __device__ __forceinline__ void dbar_wait(uint64_t* bar, uint32_t parity) {
         if (spins > (1u << 24)) __trap();
         if (spins > 64) __nanosleep(64);
     }
+}
+__device__ __forceinline__ void dbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsaddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dtma_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(dsaddr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ bool dtc_elect() {
     uint32_t pred;
@@ -131,38 +145,29 @@ __device__ __forceinline__ float dtc_colsum(float (&a)[32], int lane) {
     return a[0];
 }
 
-constexpr int DT_THREADS = 288;      // warp 0: MMA, warps 1-4: epilogue, warps 5-8: tile producers
+constexpr int DT_THREADS = 192;      // warp 0: MMA, warps 1-4: epilogue, warp 5: TMA producer
 constexpr int DT_ROWS = 16;          // M = 16 rows x 8 columns per MMA
 
-// MODE 0 = forward (x [n,H,W,CI] -> y [n,H/2,W/2,CO]), 1 = data gradient (dy [n,Hi,Wi,CK] -> dx [n,2Hi,2Wi,CN]).
-// CK = channels contracted (the staged tensor's), CN = channels produced, NMT = M tiles side by side (tile = 16 x 8*NMT).
+// MODE 0 = forward (x [n,H,W,CK] -> y [n,H/2,W/2,CN]), 1 = data gradient (dy [n,Hi,Wi,CK] -> dx [n,2Hi,2Wi,CN]).
+// CK = channels contracted (the staged tensor's: 16 or 32), CN = channels produced, NMT = M tiles side by side (tile = 16 x 8*NMT).
 template <int MODE, int CK, int CN, int NMT, bool STATS>
 __global__ void __launch_bounds__(DT_THREADS, 1)
-direct_tc_kernel(const bf16* __restrict__ src, const bf16* __restrict__ wgt, const float* __restrict__ bias, bf16* __restrict__ dst,
-                 double* __restrict__ stats, int Hs, int Ws, int act, int imgs_per_group, int tiles_w, int tiles_h, int total) {
-    // SW (forward, 16 channels): 128-byte-swizzled operand rows instead of the 16-byte core-matrix rows of the no-swizzle layout.
-    // The tensor core fetches operand ROWS, about one row slice per cycle whatever its width -- measured with the no-swizzle
-    // layout: 64 MMAs of 128 x 32 x 16 took 17 k cycles per tile = 128 x 2 + 32 x 2 fetches each (profiles/bench_conv_r2l_direct_tc.txt).
-    // A 128-byte row here = the four kw taps of one output pixel = four consecutive input pixels x 16 channels, contiguous in NHWC
-    // memory.  Rows of neighbouring output columns overlap by two pixels, so the tile is staged twice: copy 0 holds the quads of
-    // the EVEN output columns (input columns 4e .. 4e+3), copy 1 those of the odd ones (4e+2 .. 4e+5); an M tile = 16 output rows x
-    // the 8 even (odd) columns of a 16-column tile, one swizzle atom per output row.  K = 64 per filter row kh: four MMAs.
-    constexpr bool SW = MODE == 0 && CK == 16;
-    static_assert(!SW || NMT == 2, "swizzled forward layout: M tiles = the even and the odd columns");
-    constexpr int NCH = CK / 8, TCOLS = 8 * NMT;
+direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict__ wgt, const float* __restrict__ bias, bf16* __restrict__ dst,
+                 double* __restrict__ stats, int Hs, int Ws, int act, int imgs_per_group, int tiles_w, int tiles_h, int total, int diag) {
+    constexpr int NCH = CK / 8, TCOLS = 8 * NMT, PIXB = CK * 2;             // bytes of a staged pixel = the swizzle span
     constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2;            // staged rows
-    constexpr int IC = MODE == 0 ? 2 * TCOLS + 2 : TCOLS + 2;                // staged columns
-    constexpr int CP = (MODE == 0 ? TCOLS + 1 : TCOLS + 2) * 16;             // bytes of one (row, [parity,] chunk) plane
-    constexpr int RB = SW ? 2048 : (MODE == 0 ? 2 : 1) * NCH * CP;           // bytes of one staged row
-    constexpr int TILE = IR * RB;
+    constexpr int NCOPY = MODE == 0 ? 4 : 3;                                 // one box per kw / per dc
+    constexpr int ROWB = TCOLS * PIXB, COPYB = (IR * ROWB + 1023) / 1024 * 1024, TILE = NCOPY * COPYB;
     constexpr int NN = MODE == 0 ? CN : 4 * CN;                              // MMA N
     constexpr int KPOS = MODE == 0 ? 16 : 9;                                 // taps / neighbours
     constexpr int KT = KPOS * CK;                                            // weight matrix K
     constexpr int ACC = NMT * NN;                                            // TMEM columns per accumulator buffer
-    static_assert(2 * ACC <= 512 && NN % 32 == 0 && NN <= 256, "accumulators do not fit");
+    constexpr int TM_COLS = 2 * ACC < 32 ? 32 : 2 * ACC;
+    static_assert(PIXB == 32 || PIXB == 64, "a pixel must be one 32- or 64-byte swizzle span");
+    static_assert(2 * ACC <= 512 && (TM_COLS & (TM_COLS - 1)) == 0 && NN % 32 == 0 && NN <= 256, "accumulators do not fit");
     extern __shared__ __align__(128) uint8_t dsm_raw[];
-    uint8_t* dsm = dsm_raw + ((1024u - (dsaddr(dsm_raw) & 1023u)) & 1023u);   // swizzle atoms are 1024-byte aligned
-    uint8_t* wsm = dsm + 2 * TILE;                                            // [NN / 8][KT / 8][8 rows][16 bytes]; SW: [kh][NN / 8][8 rows][128 B]
+    uint8_t* dsm = dsm_raw + ((1024u - (dsaddr(dsm_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned bases
+    uint8_t* wsm = dsm + 2 * TILE;                                            // [NN / 8][KT / 8][8 rows][16 bytes] (no swizzle)
     __shared__ uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float sbias[CN];
@@ -172,26 +177,20 @@ direct_tc_kernel(const bf16* __restrict__ src, const bf16* __restrict__ wgt, con
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            dbar_init(&full_bar[i], 128); dbar_init(&empty_bar[i], 1);
+            dbar_init(&full_bar[i], 1); dbar_init(&empty_bar[i], 1);
             dbar_init(&tfull_bar[i], 1); dbar_init(&tempty_bar[i], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dsaddr(&tmem_slot)), "r"((uint32_t)(2 * ACC))
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dsaddr(&tmem_slot)), "r"((uint32_t)TM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     SG_PDL_SYNC();
-    // ---- weights, once per CTA, into the K-major core-matrix layout
-    if (SW) {
-        // wgt = pf [CN][kh][kw][16]: per kh a K-major block of CN rows x 128 bytes (kw, ci), 128-byte swizzled
-        for (int i = tid; i < NN * 4 * 8; i += DT_THREADS) {
-            const int ch = i & 7, kh = (i >> 3) & 3, n = i >> 5;
-            *reinterpret_cast<uint4*>(wsm + kh * (NN * 128) + (n >> 3) * 1024 + (n & 7) * 128 + ((ch ^ (n & 7)) << 4)) =
-                __ldg(reinterpret_cast<const uint4*>(wgt + (size_t)n * KT + kh * 64 + ch * 8));
-        }
-    } else if (MODE == 0) {
+    // ---- weights, once per CTA, into the K-major core-matrix layout (8 rows x 16 bytes, K chunks 128 bytes apart)
+    if (MODE == 0) {
         // wgt = pf [CN][16 taps][CK]: row n, K index tap * CK + ck
         for (int i = tid; i < NN * (KT / 8); i += DT_THREADS) {
             const int n = i / (KT / 8), k8 = i - n * (KT / 8);
@@ -224,11 +223,10 @@ direct_tc_kernel(const bf16* __restrict__ src, const bf16* __restrict__ wgt, con
         // address of their low word: everything per MMA is an integer add (conv_tc.cu measured ~157 cycles per tcgen05.mma when
         // each descriptor was rebuilt with shifts and masks under a divergent `lane == 0`).
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t A_SBO = SW ? 2 * RB : (MODE == 0 ? 2 * RB : RB), B_SBO = SW ? 1024 : (KT / 8) * 128;
-        constexpr uint32_t A_HI = (A_SBO >> 4) | (1u << 14) | (SW ? (2u << 29) : 0u);
-        constexpr uint32_t B_HI = (B_SBO >> 4) | (1u << 14) | (SW ? (2u << 29) : 0u);
-        constexpr uint32_t A_LBO = SW ? 1u : (uint32_t)(CP >> 4), B_LBO = SW ? 1u : (uint32_t)(128 >> 4);
-        const uint32_t blo = ((dsaddr(wsm) >> 4) & 0x3FFFu) | (B_LBO << 16);
+        constexpr uint32_t A_SBO = (MODE == 0 ? 2 : 1) * ROWB;                 // the next output (dy) row: two (one) staged rows further
+        constexpr uint32_t A_HI = (A_SBO >> 4) | (1u << 14) | ((PIXB == 32 ? 6u : 4u) << 29);      // SWIZZLE_32B / SWIZZLE_64B
+        constexpr uint32_t B_HI = ((uint32_t)((KT / 8) * 128) >> 4) | (1u << 14);                  // no swizzle
+        const uint32_t blo = ((dsaddr(wsm) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
         auto mma = [&](uint32_t tacc, uint32_t alo, uint32_t bl, uint32_t acc) {
             dtc_mma(tacc, ((uint64_t)A_HI << 32) | alo, ((uint64_t)B_HI << 32) | bl, idesc, acc);
         };
@@ -237,33 +235,20 @@ direct_tc_kernel(const bf16* __restrict__ src, const bf16* __restrict__ wgt, con
             if (k >= 1) dbar_wait(&tempty_bar[s], (k - 1) & 1);
             dbar_wait(&full_bar[s], k & 1);
             dtc_after();
-            const uint32_t alo = ((dsaddr(dsm + s * TILE) >> 4) & 0x3FFFu) | (A_LBO << 16);
+            const uint32_t alo = ((dsaddr(dsm + s * TILE) >> 4) & 0x3FFFu) | (1u << 16);
             if (dtc_elect()) {
+                if (!(diag & 4))
 #pragma unroll
                 for (int mt = 0; mt < NMT; ++mt) {
                     const uint32_t tacc = tmem_base + (uint32_t)(s * ACC + mt * NN);
-                    if (SW) {
 #pragma unroll
-                        for (int kh = 0; kh < 4; ++kh)
+                    for (int pos = 0; pos < KPOS; ++pos) {
+                        // forward: tap (kh, kw) = copy kw from staged row kh;  gradient: neighbour (dr, dc) = copy dc from staged row dr
+                        const int cp = MODE == 0 ? (pos & 3) : pos % 3, row = MODE == 0 ? (pos >> 2) : pos / 3;
+                        const uint32_t aoff = cp * COPYB + row * ROWB + mt * 8 * PIXB;
 #pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4)
-                                mma(tacc, alo + (uint32_t)((kh * RB + mt * 1024 + k4 * 32) >> 4), blo + (uint32_t)((kh * (NN * 128) + k4 * 32) >> 4),
-                                    (kh | k4) != 0 ? 1u : 0u);
-                    } else {
-#pragma unroll
-                        for (int pos = 0; pos < KPOS; ++pos) {
-                            uint32_t aoff;
-                            if (MODE == 0) {
-                                const int kh = pos >> 2, kw = pos & 3;
-                                aoff = kh * RB + (kw & 1) * NCH * CP + (8 * mt + (kw >> 1)) * 16;
-                            } else {
-                                const int dr = pos / 3, dc = pos % 3;             // 0..2 = offset + 1
-                                aoff = dr * RB + (8 * mt + dc) * 16;
-                            }
-#pragma unroll
-                            for (int kc = 0; kc < CK / 16; ++kc)
-                                mma(tacc, alo + ((aoff + 2 * kc * CP) >> 4), blo + (uint32_t)(((pos * NCH + 2 * kc) * 128) >> 4), (pos | kc) != 0 ? 1u : 0u);
-                        }
+                        for (int kc = 0; kc < CK / 16; ++kc)
+                            mma(tacc, alo + ((aoff + kc * 32) >> 4), blo + (uint32_t)(((pos * NCH + 2 * kc) * 128) >> 4), (pos | kc) != 0 ? 1u : 0u);
                     }
                 }
                 dtc_commit(&empty_bar[s]);
@@ -321,14 +306,13 @@ direct_tc_kernel(const bf16* __restrict__ src, const bf16* __restrict__ wgt, con
                     else if (act == SG_ACT_RELU) finish(std::integral_constant<int, SG_ACT_RELU>{});
                     else finish(std::integral_constant<int, SG_ACT_TANH>{});
                     bf16* o;
-                    if (SW) {               // M tile mt = the even (odd) columns of the tile
-                        o = dst + ((size_t)(n * Hd + th * DT_ROWS + r) * Wd + tw * TCOLS + 2 * c + mt) * CN + cc * 32;
-                    } else if (MODE == 0) {
+                    if (MODE == 0) {
                         o = dst + ((size_t)(n * Hd + th * DT_ROWS + r) * Wd + tw * TCOLS + 8 * mt + c) * CN + cc * 32;
                     } else {
                         const int ph = (cc * 32) / (2 * CN), off = (cc * 32) % (2 * CN);
                         o = dst + ((size_t)(n * Hd + 2 * (th * DT_ROWS + r) + ph) * Wd + 2 * (tw * TCOLS + 8 * mt + c)) * CN + off;
                     }
+                    if (!(diag & 2))
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         reinterpret_cast<uint4*>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -351,97 +335,67 @@ direct_tc_kernel(const bf16* __restrict__ src, const bf16* __restrict__ wgt, con
         }
         if (STATS && cur_grp >= 0) flush(cur_grp);
     } else {
-        // ------------------------------------------------------------------------------------------ tile producers
-        const int ptid = tid - 160;
+        // ------------------------------------------------------------------------------------------ TMA producer
         for (int it = 0; it < ntiles; ++it) {
             const int t = t_begin + it, s = it & 1, k = it >> 1;
             const int tw = t % tiles_w, r2 = t / tiles_w, th = r2 % tiles_h, n = r2 / tiles_h;
-            const int ih0 = MODE == 0 ? 2 * th * DT_ROWS - 1 : th * DT_ROWS - 1;
-            const int iw0 = MODE == 0 ? 2 * tw * TCOLS - 1 : tw * TCOLS - 1;
-            const bf16* sin = src + (size_t)n * Hs * Ws * CK;
             if (k >= 1) dbar_wait(&empty_bar[s], (k - 1) & 1);
-            const uint32_t d0 = dsaddr(dsm + s * TILE);
-            // a thread owns the same 16-byte column chunk(s) in every staged row: column, bounds and destination once per tile,
-            // then one cp.async and a handful of adds per row (the first version recomputed everything per chunk: 45 instructions
-            // per cp.async, 6 k of the kernel's 8 k warp instructions per tile -- ncu: issue-bound at 1.2 IPC)
-            constexpr int PER_ROW = SW ? 128 : IC * NCH, NCC = (PER_ROW + 127) / 128;
-            int goff[NCC];
-            uint32_t doff[NCC];
-            bool okc[NCC], have[NCC];
+            if (dtc_elect()) {
+                const uint32_t d0 = dsaddr(dsm + s * TILE);
+                dbar_expect_tx(&full_bar[s], (uint32_t)(NCOPY * IR * ROWB));
 #pragma unroll
-            for (int q = 0; q < NCC; ++q) {
-                const int cc = ptid + 128 * q;
-                have[q] = cc < PER_ROW;
-                int iw;
-                if (SW) {       // chunk ch of quad e of copy cp: input column 2 cp + 4 e + ch / 2 (1 KB contiguous per (row, copy))
-                    const int ch = cc & 7, e = (cc >> 3) & 7, cp = cc >> 6;
-                    iw = iw0 + 2 * cp + 4 * e + (ch >> 1);
-                    goff[q] = iw * CK + (ch & 1) * 8;
-                    doff[q] = cp * 1024 + e * 128 + ((ch ^ e) << 4);
-                } else {
-                    const int cx = cc / NCH, j = cc - cx * NCH;
-                    iw = iw0 + cx;
-                    goff[q] = iw * CK + j * 8;
-                    doff[q] = MODE == 0 ? ((cx & 1) * NCH + j) * CP + (cx >> 1) * 16 : j * CP + cx * 16;
-                }
-                okc[q] = have[q] && iw >= 0 && iw < Ws;
-            }
-#pragma unroll 2
-            for (int R = 0; R < IR; ++R) {
-                const int ih = ih0 + R;
-                const bool okr = ih >= 0 && ih < Hs;
-                const bf16* rowp = sin + (size_t)(okr ? ih : 0) * Ws * CK;
-#pragma unroll
-                for (int q = 0; q < NCC; ++q) {
-                    const bool ok = okr && okc[q];
-                    if (have[q]) dcp16(d0 + R * RB + doff[q], ok ? rowp + goff[q] : src, ok ? 16 : 0);
+                for (int cp = 0; cp < NCOPY; ++cp) {
+                    // forward: pixels 2 (ow0 + c) - 1 + kw, rows 2 oh0 - 1 ..;  gradient: pixels qw0 + c + dc - 1, rows qh0 - 1 ..
+                    const int c1 = MODE == 0 ? 2 * tw * TCOLS - 1 + cp : tw * TCOLS - 1 + cp;
+                    const int c2 = MODE == 0 ? 2 * th * DT_ROWS - 1 : th * DT_ROWS - 1;
+                    dtma_4d(&tm, &full_bar[s], d0 + cp * COPYB, 0, c1, c2, n);
                 }
             }
-            dcp_commit();
-            if (it > 0) {                  // the previous tile has landed: publish it while this one is in flight
-                dcp_wait<1>();
-                dfence_async();
-                dbar_arrive(&full_bar[s ^ 1]);
-            }
-        }
-        if (ntiles > 0) {
-            dcp_wait<0>();
-            dfence_async();
-            dbar_arrive(&full_bar[(ntiles - 1) & 1]);
+            __syncwarp();
         }
     }
     dtc_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * ACC)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TM_COLS) : "memory");
     }
 }
 
 template <int MODE, int CK, int CN, int NMT>
 constexpr size_t direct_tc_smem() {
-    constexpr int NCH = CK / 8, TCOLS = 8 * NMT;
-    constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2;
-    constexpr int CP = (MODE == 0 ? TCOLS + 1 : TCOLS + 2) * 16;
-    constexpr int RB = (MODE == 0 && CK == 16) ? 2048 : (MODE == 0 ? 2 : 1) * NCH * CP;
+    constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, NCOPY = MODE == 0 ? 4 : 3;
+    constexpr int ROWB = 8 * NMT * CK * 2, COPYB = (IR * ROWB + 1023) / 1024 * 1024;
     constexpr int NN = MODE == 0 ? CN : 4 * CN, KT = (MODE == 0 ? 16 : 9) * CK;
-    return (size_t)2 * IR * RB + (size_t)NN * KT * 2 + 1024;
+    return (size_t)2 * NCOPY * COPYB + (size_t)NN * KT * 2 + 1024;
 }
+
+}  // namespace
+
+int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, CUtensorMap* out);      // conv_tc.cu
+// option "dtc_diag" (timing experiments only, results are WRONG with any bit set): 1 = contiguous TMA boxes instead of every second
+// pixel, 2 = the epilogue does not store, 4 = no MMAs are issued
+int g_dtc_diag = 0;
+
+namespace {
 
 template <int MODE, int CK, int CN, int NMT, bool STATS>
 cudaError_t launch_direct_tc(const void* src, const void* wgt, const float* bias, void* dst, double* stats, int groups, int N, int Hs, int Ws,
                              int act, cudaStream_t st) {
     constexpr size_t smem = direct_tc_smem<MODE, CK, CN, NMT>();
+    static_assert(smem <= 227 * 1024, "tile ring + weights exceed the SM's shared memory");
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = true;
     }
+    CUtensorMap tm;
+    if (get_direct_map(src, N, Hs, Ws, CK, 8 * NMT, MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, (MODE == 0 && !(g_dtc_diag & 1)) ? 2 : 1, &tm))
+        return cudaErrorInvalidValue;
     const int Hm = MODE == 0 ? Hs / 2 : Hs, Wm = MODE == 0 ? Ws / 2 : Ws;        // the grid the M tiles cover
     const int tiles_w = Wm / (8 * NMT), tiles_h = Hm / DT_ROWS, total = N * tiles_w * tiles_h;
     return launch_pdl(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, dim3((unsigned)(total < SG_NUM_SMS ? total : SG_NUM_SMS)), dim3(DT_THREADS),
-                      smem, st, (const bf16*)src, (const bf16*)wgt, bias, (bf16*)dst, stats, Hs, Ws, act, groups > 0 ? N / groups : N, tiles_w,
-                      tiles_h, total);
+                      smem, st, tm, (const bf16*)wgt, bias, (bf16*)dst, stats, Hs, Ws, act, groups > 0 ? N / groups : N, tiles_w, tiles_h, total, g_dtc_diag);
 }
 
 }  // namespace
@@ -452,8 +406,8 @@ bool direct_tc_supported(int mode, int Ci, int Co, int Hs, int Ws) {
     const int Hm = mode == 0 ? Hs / 2 : Hs, Wm = mode == 0 ? Ws / 2 : Ws;
     if (Hm % DT_ROWS != 0) return false;
     if (mode == 0 && Ci == 16 && Co == 32) return Wm % 16 == 0;
-    if (mode == 0 && Ci == 32 && Co == 64) return Wm % 16 == 0;
-    if (mode == 1 && Ci == 16 && Co == 32) return Wm % 32 == 0;
+    if (mode == 0 && Ci == 32 && Co == 64) return Wm % 8 == 0;
+    if (mode == 1 && Ci == 16 && Co == 32) return Wm % 16 == 0;
     return false;
 }
 cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, void* y, double* stats, int groups, int N, int H, int W, int Ci,
@@ -462,13 +416,13 @@ cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, vo
         return stats ? launch_direct_tc<0, 16, 32, 2, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 16, 32, 2, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     if (Ci == 32 && Co == 64)
-        return stats ? launch_direct_tc<0, 32, 64, 2, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
-                     : launch_direct_tc<0, 32, 64, 2, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+        return stats ? launch_direct_tc<0, 32, 64, 1, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 32, 64, 1, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     return cudaErrorInvalidValue;
 }
 cudaError_t direct_tc_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Hi, int Wi, int Ci, int Co, int act,
                             cudaStream_t st) {
-    if (Ci == 16 && Co == 32) return launch_direct_tc<1, 32, 16, 4, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
+    if (Ci == 16 && Co == 32) return launch_direct_tc<1, 32, 16, 2, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
     return cudaErrorInvalidValue;
 }
 

@@ -352,8 +352,9 @@ narrow_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pd, co
 static int g_nf_grid[4] = {0, 0, 0, 0}, g_nd_grid[4] = {0, 0, 0, 0};     // CTAs per launch (SMs x resident CTAs), per instantiation
 // option "narrow": which supported shapes sg_conv_fprop(_stats) / sg_conv_dgrad send here instead of to the tcgen05 kernel, as a
 // bit mask -- 1: forward 16 -> 32, 2: data gradient 16 <- 32, 4: forward 32 -> 64, 8: data gradient 32 <- 64 (15 = all, 0 = none).
-// Default = the ones measured faster on B200 (tools/bench_conv.py, profiles/bench_conv_r2k_narrow.txt).
-int g_use_narrow = 3;
+// Default = the ones measured faster on B200 (tools/bench_conv.py, profiles/bench_conv_r2k_narrow.txt, bench_conv_r2l_direct_tc.txt):
+// both directions of 16 <-> 32 and the forward 32 -> 64, all three on the tcgen05 kernels of direct_tc.cu.
+int g_use_narrow = 7;
 // option "narrow_cfg" (A/B), bits: 4 = the mma.sync kernels of this file instead of the tcgen05 ones of direct_tc.cu wherever both take
 // the shape; for the mma.sync kernels: 1 = forward 16->32 as one CTA per SM with a two-deep ring, 2 = data gradient 16<-32 at one CTA per SM
 int g_narrow_cfg = 0;
