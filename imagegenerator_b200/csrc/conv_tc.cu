@@ -1436,7 +1436,7 @@ static bool choose_box(int Hq, int Wq, int* bw, int* bh, int* bn) {
 // 148 SMs).
 int g_force_cg = 0, g_force_bn = 0, g_force_stages = 0, g_dbg = 0;
 extern int g_use_narrow, g_narrow_cfg; // narrow_conv.cu
-extern int g_dtc_diag;                 // direct_tc.cu
+extern int g_dtc_diag, g_dtc_wide;     // direct_tc.cu
 int g_use_slab = 1;      // option "slab": 0 = one activation box per tap (no sharing), for A/B measurements
 // option "dyn_sched" / env SG_DYN_SCHED: dynamic work distribution in the persistent conv kernel (see decode_work); needs the
 // counter pool of sg_init_workspace().  OFF by default: measured on B200 (round 2, bench.py) Stage-I 5.42 -> 5.60 ms and
@@ -1910,6 +1910,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "narrow")) { g_use_narrow = value; return 0; }
     if (name && !strcmp(name, "narrow_cfg")) { g_narrow_cfg = value; return 0; }
     if (name && !strcmp(name, "dtc_diag")) { g_dtc_diag = value; return 0; }
+    if (name && !strcmp(name, "dtc_wide")) { g_dtc_wide = value; return 0; }
     if (name && !strcmp(name, "wgrad_smem_kb")) { g_wgrad_smem_kb = value < 48 ? 48 : (value > 200 ? 200 : value); return 0; }
     if (name && !strcmp(name, "dyn_sched")) { g_dyn_sched = value; return 0; }
     if (name && !strcmp(name, "bstats_min_k")) { g_bstats_min_k = value; return 0; }

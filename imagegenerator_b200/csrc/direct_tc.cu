@@ -375,6 +375,10 @@ int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, 
 // option "dtc_diag" (timing experiments only, results are WRONG with any bit set): 1 = contiguous TMA boxes instead of every second
 // pixel, 2 = the epilogue does not store, 4 = no MMAs are issued
 int g_dtc_diag = 0;
+// option "dtc_wide": 1 (default) = tiles of two M tiles (16 x 16 pixels, one CTA per SM) for the 16 <-> 32 layers wherever the column
+// count allows, 0 = always one M tile (16 x 8 pixels, two CTAs per SM: the same staged bytes per pixel and twice the independent
+// pipelines per SM -- measured SLOWER, ds2 forward 63.9 vs 58.0 us, data gradient 59.4 vs 50.9: TMA boxes of 256-byte rows)
+int g_dtc_wide = 1;
 
 namespace {
 
@@ -383,18 +387,20 @@ cudaError_t launch_direct_tc(const void* src, const void* wgt, const float* bias
                              int act, cudaStream_t st) {
     constexpr size_t smem = direct_tc_smem<MODE, CK, CN, NMT>();
     static_assert(smem <= 227 * 1024, "tile ring + weights exceed the SM's shared memory");
-    static bool attr = false;
-    if (!attr) {
+    static int per_sm = 0;               // resident CTAs per SM (shared memory decides: 2 with one M tile per tile, else 1)
+    if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = true;
+        int n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, direct_tc_kernel<MODE, CK, CN, NMT, STATS>, DT_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+        per_sm = n > 2 ? 2 : n;
     }
     CUtensorMap tm;
     if (get_direct_map(src, N, Hs, Ws, CK, 8 * NMT, MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, (MODE == 0 && !(g_dtc_diag & 1)) ? 2 : 1, &tm))
         return cudaErrorInvalidValue;
     const int Hm = MODE == 0 ? Hs / 2 : Hs, Wm = MODE == 0 ? Ws / 2 : Ws;        // the grid the M tiles cover
     const int tiles_w = Wm / (8 * NMT), tiles_h = Hm / DT_ROWS, total = N * tiles_w * tiles_h;
-    return launch_pdl(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, dim3((unsigned)(total < SG_NUM_SMS ? total : SG_NUM_SMS)), dim3(DT_THREADS),
+    return launch_pdl(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, dim3((unsigned)(total < SG_NUM_SMS * per_sm ? total : SG_NUM_SMS * per_sm)), dim3(DT_THREADS),
                       smem, st, tm, (const bf16*)wgt, bias, (bf16*)dst, stats, Hs, Ws, act, groups > 0 ? N / groups : N, tiles_w, tiles_h, total, g_dtc_diag);
 }
 
@@ -405,16 +411,19 @@ cudaError_t launch_direct_tc(const void* src, const void* wgt, const float* bias
 bool direct_tc_supported(int mode, int Ci, int Co, int Hs, int Ws) {
     const int Hm = mode == 0 ? Hs / 2 : Hs, Wm = mode == 0 ? Ws / 2 : Ws;
     if (Hm % DT_ROWS != 0) return false;
-    if (mode == 0 && Ci == 16 && Co == 32) return Wm % 16 == 0;
+    if (mode == 0 && Ci == 16 && Co == 32) return Wm % 8 == 0;
     if (mode == 0 && Ci == 32 && Co == 64) return Wm % 8 == 0;
-    if (mode == 1 && Ci == 16 && Co == 32) return Wm % 16 == 0;
+    if (mode == 1 && Ci == 16 && Co == 32) return Wm % 8 == 0;
     return false;
 }
 cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, void* y, double* stats, int groups, int N, int H, int W, int Ci,
                             int Co, int act, cudaStream_t st) {
-    if (Ci == 16 && Co == 32)
+    if (Ci == 16 && Co == 32 && g_dtc_wide && (W / 2) % 16 == 0)
         return stats ? launch_direct_tc<0, 16, 32, 2, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 16, 32, 2, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+    if (Ci == 16 && Co == 32)
+        return stats ? launch_direct_tc<0, 16, 32, 1, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 16, 32, 1, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     if (Ci == 32 && Co == 64)
         return stats ? launch_direct_tc<0, 32, 64, 1, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 32, 64, 1, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
@@ -422,7 +431,8 @@ cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, vo
 }
 cudaError_t direct_tc_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Hi, int Wi, int Ci, int Co, int act,
                             cudaStream_t st) {
-    if (Ci == 16 && Co == 32) return launch_direct_tc<1, 32, 16, 2, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
+    if (Ci == 16 && Co == 32 && g_dtc_wide && Wi % 16 == 0) return launch_direct_tc<1, 32, 16, 2, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
+    if (Ci == 16 && Co == 32) return launch_direct_tc<1, 32, 16, 1, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
     return cudaErrorInvalidValue;
 }
 

@@ -50,12 +50,22 @@ const char* sg_last_error(void);
 int sg_check_device(void);
 /* number of kernels launched through this library since load (all threads) */
 int64_t sg_launch_count(void);
-/* tuning switches: "persist" = 1/0 persistent double-buffered conv kernel (default 1); "force_cg" / "force_bn" pin its
- * CTA-group size / tile width (0 = cost model); "tc2" = 1/0 CTA-pair tiles in the non-persistent kernels;
- * "wgrad2" = 1/0 unit-list weight-gradient kernel (default 1); "split" = 1/0 cut a partly filled last tile wave of the
- * persistent conv kernel along K over the idle SMs (default 1); "pdl" = 1/0 programmatic dependent launch for the
- * launches that follow; "wgrad_mc" = 1/0 TMA multicast in the weight-gradient kernel; "force_stages" caps the conv
- * pipeline depth; "epi_alt" = 1/0 alternate-tile epilogue for conv tiles <= 64 columns wide (default 0, env SG_EPI_ALT) */
+/* tuning switches (A/B measurements; defaults are the measured-best settings; SG_OPTS="name=value,..." sets them from the
+ * environment through the Python binding):
+ *  conv_tcp (conv_tc.cu):  "force_cg" / "force_bn" pin the CTA-group size / tile width (0 = cost model); "force_stages" caps the
+ *    pipeline depth; "slab" = 1/0 shared activation slabs; "nsplit" = 1/0 column slices for a partly filled last round; "rotate" =
+ *    rotate the slab order per cluster; "dyn_sched" = 1/0 dynamic tile schedule (default 0, measured slower); "epi_alt" = 1/0
+ *    alternate-tile epilogue for tiles <= 64 columns (default 0); "bstats_min_k" = shallowest reduction that gets the fused
+ *    BatchNorm-backward statistics (default 4000); "pdl" = 1/0 programmatic dependent launch for the launches that follow.
+ *  wgrad (conv_tc.cu):  "wgrad_mc" = 1/0 TMA multicast between co tiles, "wgrad_mc_max" largest co-tile cluster (default 2),
+ *    "wgrad_mc_odd" = 0 pairs only; "wgrad_smem_kb" shared memory the pipeline may take (default 200; ~150 leaves room for other
+ *    kernels' CTAs on the SM -- co-residency experiment, measured slower).
+ *  narrow layers (narrow_conv.cu / direct_tc.cu):  "narrow" = bit mask of the shapes routed to the direct kernels (1 forward
+ *    16->32, 2 data gradient 16<-32, 4 forward 32->64, 8 data gradient 32<-64; default 7); "narrow_cfg" bit 4 = the mma.sync
+ *    kernels instead of the tcgen05 ones, bits 1 / 2 = one CTA per SM for the mma.sync forward / data-gradient kernel;
+ *    "dtc_wide" = 1/0 two / one M tiles per tile in direct_tc.cu (default 1); "dtc_diag" = timing experiments that produce WRONG
+ *    results (1 contiguous boxes, 2 no stores, 4 no MMAs; default 0 -- never set it outside tools/).
+ *  "dbg" = verbose launch decisions on stderr. */
 int sg_set_option(const char* name, int value);
 /* one-time device allocations of the library (the launch entry points never allocate): the counter pool of the dynamic conv
    schedule.  Once per process, before the first launch, outside stream capture. */
@@ -117,13 +127,15 @@ int sg_conv_thin_fprop(const void* x, const void* pf, const float* bias, void* y
 int sg_conv_thin_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Ho, int Wo, int Co, int act,
                        void* stream);
 
-/* ---- narrow-channel k4 s2 p1 convs as direct kernels (narrow_conv.cu; bf16 only) -----------------------------------------
+/* ---- narrow-channel k4 s2 p1 convs as direct kernels (direct_tc.cu, narrow_conv.cu; bf16 only) -------------------------------
  * (Ci, Co) in {(16, 32), (32, 64)} on large maps -- the Stage-II critic's second and third layer (discriminator_2.py:13-18) and
- * their data gradients: HBM-bound shapes (150 MB for 13 GFLOP) whose 128 x 32 tcgen05 tiles cost more in the epilogue than in
- * the mainloop.  Persistent CTAs, weights staged once, input tiles through a cp.async ring, mma.sync.  Output grid rows % 8 == 0,
- * columns % 32 == 0.  sg_conv_fprop / sg_conv_fprop_stats / sg_conv_dgrad route a supported shape here when option "narrow"
- * selects it -- a bit mask: 1 forward 16->32, 2 data gradient 16<-32, 4 forward 32->64, 8 data gradient 32<-64; the default is the
- * set measured faster than the tcgen05 kernel on B200 (sg_conv_narrow_routed reports the decision). */
+ * their data gradients: HBM-bound shapes (150 MB for 13 GFLOP) whose 32-byte operand rows the implicit-GEMM kernel cannot feed.
+ * direct_tc.cu: persistent CTAs stage a spatial tile with TMA (one strided box per filter column, zero padding = out-of-bounds
+ * fill) and tcgen05.mma reads every tap's operand as a window of it; forward (both shapes, optional BatchNorm statistics) and the
+ * 16 <- 32 data gradient; output grid rows % 16 == 0, columns % 8 == 0.  narrow_conv.cu: the same operators with warp-level
+ * mma.sync (rows % 8, columns % 32), kept as the second implementation behind option "narrow_cfg" and for 32 <- 64.
+ * sg_conv_fprop / sg_conv_fprop_stats / sg_conv_dgrad route a supported shape here when option "narrow" selects it (bit mask,
+ * see sg_set_option; sg_conv_narrow_routed reports the decision). */
 int sg_conv_narrow_supported(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
 int sg_conv_narrow_routed(int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p);
 int sg_conv_narrow_fprop(const void* x, const void* pf, const float* bias, void* y, double* stats, int groups, int N, int H, int W,

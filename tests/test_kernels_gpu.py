@@ -207,6 +207,30 @@ def test_narrow_conv_dgrad_direct(case, act, use_bias, impl):
 
 
 @pytest.mark.gpu
+def test_narrow_one_m_tile_variant():
+    """Option "dtc_wide" = 0: the tcgen05 kernels with one M tile per tile (16 x 8 pixels, two CTAs per SM) give the same results."""
+    ops = _ops("bf16")
+    N, H, Ci, Co = 5, 128, 16, 32
+    x = rnd(N, H, H, Ci).to(torch.bfloat16).cuda()
+    pf = rnd(Co, 4, 4, Ci, scale=(16 * Ci) ** -0.5).to(torch.bfloat16).cuda()
+    dy = rnd(N, H // 2, H // 2, Co).to(torch.bfloat16).cuda()
+    pd = rnd(Ci, 4, 4, Co, scale=(4 * Co) ** -0.5).to(torch.bfloat16).cuda()
+    st = [torch.zeros(1, Co, 2, dtype=torch.float64, device="cuda") for _ in range(2)]
+    y = [ops.empty((N, H // 2, H // 2, Co)) for _ in range(2)]
+    dx = [ops.empty((N, H, H, Ci)) for _ in range(2)]
+    for i, wide in enumerate((1, 0)):
+        ops.set_option("dtc_wide", wide)
+        try:
+            ops.conv_narrow_fprop(x, pf, None, y[i], ACT_LRELU, st[i], 1)
+            ops.conv_narrow_dgrad(dy, pd, None, dx[i], ACT_NONE)
+        finally:
+            ops.set_option("dtc_wide", 1)
+    torch.cuda.synchronize()
+    assert torch.equal(y[0], y[1]) and torch.equal(dx[0], dx[1])
+    assert torch.allclose(st[0], st[1], rtol=1e-5)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mask", [0, 15])
 def test_narrow_routing_mask(mask):
     """Option "narrow" (bit mask) decides which supported shapes the dispatcher sends to narrow_conv.cu; both backends agree."""
