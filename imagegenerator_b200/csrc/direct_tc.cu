@@ -150,14 +150,19 @@ constexpr int DT_ROWS = 16;          // M = 16 rows x 8 columns per MMA
 
 // MODE 0 = forward (x [n,H,W,CK] -> y [n,H/2,W/2,CN]), 1 = data gradient (dy [n,Hi,Wi,CK] -> dx [n,2Hi,2Wi,CN]).
 // CK = channels contracted (the staged tensor's: 16 or 32), CN = channels produced, NMT = M tiles side by side (tile = 16 x 8*NMT).
-template <int MODE, int CK, int CN, int NMT, bool STATS>
+// ONE = 1: windows that start INSIDE a swizzle atom -- the forward kernel stages two copies (pixel parities, one column more) instead
+// of four, the gradient kernel one (two columns more) instead of three; tap kw / neighbour dc then shifts the window by a pixel.
+// Legal because the swizzle XOR is taken from absolute address bits by TMA and tensor core alike (bit-identical results, measured).
+// Forward 16 -> 32: 61.8 -> 47.2 us (half the staged bytes); gradient: 51.3 -> 57.4 us, so it keeps its three copies.
+template <int MODE, int CK, int CN, int NMT, bool STATS, int ONE>
 __global__ void __launch_bounds__(DT_THREADS, 1)
 direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict__ wgt, const float* __restrict__ bias, bf16* __restrict__ dst,
                  double* __restrict__ stats, int Hs, int Ws, int act, int imgs_per_group, int tiles_w, int tiles_h, int total, int diag) {
     constexpr int NCH = CK / 8, TCOLS = 8 * NMT, PIXB = CK * 2;             // bytes of a staged pixel = the swizzle span
     constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2;            // staged rows
-    constexpr int NCOPY = MODE == 0 ? 4 : 3;                                 // one box per kw / per dc
-    constexpr int ROWB = TCOLS * PIXB, COPYB = (IR * ROWB + 1023) / 1024 * 1024, TILE = NCOPY * COPYB;
+    constexpr int NCOPY = ONE ? (MODE == 0 ? 2 : 1) : (MODE == 0 ? 4 : 3);   // one box per kw / per dc (ONE: per pixel parity / a single one)
+    constexpr int BOXW = ONE ? (MODE == 0 ? TCOLS + 1 : TCOLS + 2) : TCOLS;  // staged pixels per row
+    constexpr int ROWB = BOXW * PIXB, COPYB = (IR * ROWB + 1023) / 1024 * 1024, TILE = NCOPY * COPYB;
     constexpr int NN = MODE == 0 ? CN : 4 * CN;                              // MMA N
     constexpr int KPOS = MODE == 0 ? 16 : 9;                                 // taps / neighbours
     constexpr int KT = KPOS * CK;                                            // weight matrix K
@@ -228,7 +233,9 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
         constexpr uint32_t B_HI = ((uint32_t)((KT / 8) * 128) >> 4) | (1u << 14);                  // no swizzle
         const uint32_t blo = ((dsaddr(wsm) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
         auto mma = [&](uint32_t tacc, uint32_t alo, uint32_t bl, uint32_t acc) {
-            dtc_mma(tacc, ((uint64_t)A_HI << 32) | alo, ((uint64_t)B_HI << 32) | bl, idesc, acc);
+            // descriptor base offset (bits 49-51): the phase of the swizzle pattern at a start address that is not atom-aligned
+            const uint32_t bo = (ONE && (diag & 16)) ? ((alo >> 3) & 7u) << 17 : 0u;
+            dtc_mma(tacc, ((uint64_t)(A_HI | bo) << 32) | alo, ((uint64_t)B_HI << 32) | bl, idesc, acc);
         };
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1, k = it >> 1;
@@ -244,8 +251,9 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
 #pragma unroll
                     for (int pos = 0; pos < KPOS; ++pos) {
                         // forward: tap (kh, kw) = copy kw from staged row kh;  gradient: neighbour (dr, dc) = copy dc from staged row dr
-                        const int cp = MODE == 0 ? (pos & 3) : pos % 3, row = MODE == 0 ? (pos >> 2) : pos / 3;
-                        const uint32_t aoff = cp * COPYB + row * ROWB + mt * 8 * PIXB;
+                        const int col = MODE == 0 ? (pos & 3) : pos % 3, row = MODE == 0 ? (pos >> 2) : pos / 3;
+                        const int cp = ONE ? (MODE == 0 ? (col & 1) : 0) : col, shift = ONE ? (MODE == 0 ? (col >> 1) : col) : 0;
+                        const uint32_t aoff = cp * COPYB + row * ROWB + (mt * 8 + shift) * PIXB;
 #pragma unroll
                         for (int kc = 0; kc < CK / 16; ++kc)
                             mma(tacc, alo + ((aoff + kc * 32) >> 4), blo + (uint32_t)(((pos * NCH + 2 * kc) * 128) >> 4), (pos | kc) != 0 ? 1u : 0u);
@@ -361,10 +369,11 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
     }
 }
 
-template <int MODE, int CK, int CN, int NMT>
+template <int MODE, int CK, int CN, int NMT, int ONE>
 constexpr size_t direct_tc_smem() {
-    constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, NCOPY = MODE == 0 ? 4 : 3;
-    constexpr int ROWB = 8 * NMT * CK * 2, COPYB = (IR * ROWB + 1023) / 1024 * 1024;
+    constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, NCOPY = ONE ? (MODE == 0 ? 2 : 1) : (MODE == 0 ? 4 : 3);
+    constexpr int BOXW = ONE ? (MODE == 0 ? 8 * NMT + 1 : 8 * NMT + 2) : 8 * NMT;
+    constexpr int ROWB = BOXW * CK * 2, COPYB = (IR * ROWB + 1023) / 1024 * 1024;
     constexpr int NN = MODE == 0 ? CN : 4 * CN, KT = (MODE == 0 ? 16 : 9) * CK;
     return (size_t)2 * NCOPY * COPYB + (size_t)NN * KT * 2 + 1024;
 }
@@ -372,8 +381,11 @@ constexpr size_t direct_tc_smem() {
 }  // namespace
 
 int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, CUtensorMap* out);      // conv_tc.cu
-// option "dtc_diag" (timing experiments only, results are WRONG with any bit set): 1 = contiguous TMA boxes instead of every second
-// pixel, 2 = the epilogue does not store, 4 = no MMAs are issued
+// option "dtc_diag": timing experiments.  Bits 1, 2, 4, 16 give WRONG results: 1 = contiguous TMA boxes instead of every second pixel,
+// 2 = the epilogue does not store, 4 = no MMAs are issued, 16 = descriptor base offset on windows that start inside a swizzle atom
+// (measured wrong: the tensor core's swizzle is a function of the absolute shared-memory address, like TMA's, so such windows
+// need NO base offset -- tools/exp_dtc_onecopy.py).  Bit 8 (correct results) swaps the copy scheme: forward one copy per kw instead
+// of one per pixel parity, gradient a single copy instead of one per dc.
 int g_dtc_diag = 0;
 // option "dtc_wide": 1 (default) = tiles of two M tiles (16 x 16 pixels, one CTA per SM) for the 16 <-> 32 layers wherever the column
 // count allows, 0 = always one M tile (16 x 8 pixels, two CTAs per SM: the same staged bytes per pixel and twice the independent
@@ -382,25 +394,25 @@ int g_dtc_wide = 1;
 
 namespace {
 
-template <int MODE, int CK, int CN, int NMT, bool STATS>
+template <int MODE, int CK, int CN, int NMT, bool STATS, int ONE = 0>
 cudaError_t launch_direct_tc(const void* src, const void* wgt, const float* bias, void* dst, double* stats, int groups, int N, int Hs, int Ws,
                              int act, cudaStream_t st) {
-    constexpr size_t smem = direct_tc_smem<MODE, CK, CN, NMT>();
+    constexpr size_t smem = direct_tc_smem<MODE, CK, CN, NMT, ONE>();
     static_assert(smem <= 227 * 1024, "tile ring + weights exceed the SM's shared memory");
     static int per_sm = 0;               // resident CTAs per SM (shared memory decides: 2 with one M tile per tile, else 1)
     if (per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(direct_tc_kernel<MODE, CK, CN, NMT, STATS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int n = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, direct_tc_kernel<MODE, CK, CN, NMT, STATS>, DT_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, direct_tc_kernel<MODE, CK, CN, NMT, STATS, ONE>, DT_THREADS, smem) != cudaSuccess || n < 1) n = 1;
         per_sm = n > 2 ? 2 : n;
     }
     CUtensorMap tm;
-    if (get_direct_map(src, N, Hs, Ws, CK, 8 * NMT, MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, (MODE == 0 && !(g_dtc_diag & 1)) ? 2 : 1, &tm))
+    if (get_direct_map(src, N, Hs, Ws, CK, ONE ? (MODE == 0 ? 8 * NMT + 1 : 8 * NMT + 2) : 8 * NMT, MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, (MODE == 0 && !(g_dtc_diag & 1)) ? 2 : 1, &tm))
         return cudaErrorInvalidValue;
     const int Hm = MODE == 0 ? Hs / 2 : Hs, Wm = MODE == 0 ? Ws / 2 : Ws;        // the grid the M tiles cover
     const int tiles_w = Wm / (8 * NMT), tiles_h = Hm / DT_ROWS, total = N * tiles_w * tiles_h;
-    return launch_pdl(direct_tc_kernel<MODE, CK, CN, NMT, STATS>, dim3((unsigned)(total < SG_NUM_SMS * per_sm ? total : SG_NUM_SMS * per_sm)), dim3(DT_THREADS),
+    return launch_pdl(direct_tc_kernel<MODE, CK, CN, NMT, STATS, ONE>, dim3((unsigned)(total < SG_NUM_SMS * per_sm ? total : SG_NUM_SMS * per_sm)), dim3(DT_THREADS),
                       smem, st, tm, (const bf16*)wgt, bias, (bf16*)dst, stats, Hs, Ws, act, groups > 0 ? N / groups : N, tiles_w, tiles_h, total, g_dtc_diag);
 }
 
@@ -418,21 +430,31 @@ bool direct_tc_supported(int mode, int Ci, int Co, int Hs, int Ws) {
 }
 cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, void* y, double* stats, int groups, int N, int H, int W, int Ci,
                             int Co, int act, cudaStream_t st) {
-    if (Ci == 16 && Co == 32 && g_dtc_wide && (W / 2) % 16 == 0)
-        return stats ? launch_direct_tc<0, 16, 32, 2, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
-                     : launch_direct_tc<0, 16, 32, 2, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+    const bool wide = g_dtc_wide && (W / 2) % 16 == 0;
+    if (Ci == 16 && Co == 32 && wide && (g_dtc_diag & 8))        // A/B: one copy per kw (four) instead of one per pixel parity (two)
+        return stats ? launch_direct_tc<0, 16, 32, 2, true, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 16, 32, 2, false, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+    if (Ci == 16 && Co == 32 && wide)
+        return stats ? launch_direct_tc<0, 16, 32, 2, true, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 16, 32, 2, false, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     if (Ci == 16 && Co == 32)
-        return stats ? launch_direct_tc<0, 16, 32, 1, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
-                     : launch_direct_tc<0, 16, 32, 1, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+        return stats ? launch_direct_tc<0, 16, 32, 1, true, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 16, 32, 1, false, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+    if (Ci == 32 && Co == 64 && wide && !(g_dtc_diag & 8))
+        return stats ? launch_direct_tc<0, 32, 64, 2, true, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 32, 64, 2, false, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     if (Ci == 32 && Co == 64)
-        return stats ? launch_direct_tc<0, 32, 64, 1, true>(x, pf, bias, y, stats, groups, N, H, W, act, st)
-                     : launch_direct_tc<0, 32, 64, 1, false>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+        return stats ? launch_direct_tc<0, 32, 64, 1, true, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 32, 64, 1, false, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     return cudaErrorInvalidValue;
 }
 cudaError_t direct_tc_dgrad(const void* dy, const void* pd, const float* bias, void* dx, int N, int Hi, int Wi, int Ci, int Co, int act,
                             cudaStream_t st) {
-    if (Ci == 16 && Co == 32 && g_dtc_wide && Wi % 16 == 0) return launch_direct_tc<1, 32, 16, 2, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
-    if (Ci == 16 && Co == 32) return launch_direct_tc<1, 32, 16, 1, false>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
+    const bool wide = g_dtc_wide && Wi % 16 == 0;
+    // the single-copy variant is SLOWER here (57.4 vs 51.3 us): A/B only
+    if (Ci == 16 && Co == 32 && wide && (g_dtc_diag & 8)) return launch_direct_tc<1, 32, 16, 2, false, 1>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
+    if (Ci == 16 && Co == 32 && wide) return launch_direct_tc<1, 32, 16, 2, false, 0>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
+    if (Ci == 16 && Co == 32) return launch_direct_tc<1, 32, 16, 1, false, 0>(dy, pd, bias, dx, nullptr, 1, N, Hi, Wi, act, st);
     return cudaErrorInvalidValue;
 }
 
