@@ -1367,11 +1367,11 @@ static int get_slab_map(const void* ptr, int N, int H, int W, int C, int bw, int
     return 0;
 }
 
-// direct_tc.cu: NHWC bf16 tensor [N][H][W][C] (C = 16 / 32 / 64 channels = one swizzle span), box {C, bw*es, bh, 1} with element
-// stride es along W only: bw pixels es apart x bh consecutive rows -> shared memory [row][pixel][C], swizzled at C*2 bytes
-int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, CUtensorMap* out) {
+// direct_tc.cu: NHWC bf16 tensor [N][H][W][C] (C = 16 / 32 / 64 channels), box {C, bw*es, bh, 1} with element stride es along W
+// only: bw pixels es apart x bh consecutive rows -> shared memory [row][pixel][C], swizzled with a span of swz bytes (>= C*2)
+int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, int swz, CUtensorMap* out) {
     if (int e = ensure_encode()) return e;
-    MapKey key(ptr, N, H, W, C, bw, bh, 1, es, 7);
+    MapKey key(ptr, N, H, W, C, bw, bh, swz, es, 7);
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
@@ -1379,7 +1379,7 @@ int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, 
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(bw * es), (cuuint32_t)bh, 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)es, 1, 1};
-    const CUtensorMapSwizzle sw = C == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    const CUtensorMapSwizzle sw = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     CUtensorMap m;
     CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

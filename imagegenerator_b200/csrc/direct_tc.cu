@@ -145,6 +145,26 @@ __device__ __forceinline__ float dtc_colsum(float (&a)[32], int lane) {
     return a[0];
 }
 
+template <int MODE, int CK, int CN, int NMT, int ONE>
+constexpr size_t direct_tc_tile_bytes() {
+    constexpr int IR = MODE == 0 ? 2 * 16 + 2 : 16 + 2, NCOPY = ONE == 2 ? 1 : ONE ? (MODE == 0 ? 2 : 1) : (MODE == 0 ? 4 : 3);
+    constexpr int BOXW = ONE == 2 ? 16 * NMT + 4 : ONE ? (MODE == 0 ? 8 * NMT + 1 : 8 * NMT + 2) : 8 * NMT;
+    constexpr int ROWB = BOXW * CK * 2, COPYB = (IR * ROWB + 1023) / 1024 * 1024;
+    return (size_t)NCOPY * COPYB;
+}
+template <int MODE, int CK, int CN, int NMT, int ONE>
+constexpr size_t direct_tc_weight_bytes() { return (size_t)(MODE == 0 ? CN : 4 * CN) * (MODE == 0 ? 16 : 9) * CK * 2; }
+template <int MODE, int CK, int CN, int NMT, int ONE>
+constexpr int direct_tc_slots() {
+    constexpr size_t room = 226 * 1024 - 1024 - direct_tc_weight_bytes<MODE, CK, CN, NMT, ONE>();
+    constexpr size_t n = room / direct_tc_tile_bytes<MODE, CK, CN, NMT, ONE>();
+    return n > 4 ? 4 : (int)n;
+}
+template <int MODE, int CK, int CN, int NMT, int ONE>
+constexpr size_t direct_tc_smem() {
+    return direct_tc_slots<MODE, CK, CN, NMT, ONE>() * direct_tc_tile_bytes<MODE, CK, CN, NMT, ONE>() + direct_tc_weight_bytes<MODE, CK, CN, NMT, ONE>() + 1024;
+}
+
 constexpr int DT_THREADS = 192;      // warp 0: MMA, warps 1-4: epilogue, warp 5: TMA producer
 constexpr int DT_ROWS = 16;          // M = 16 rows x 8 columns per MMA
 
@@ -160,20 +180,30 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
                  double* __restrict__ stats, int Hs, int Ws, int act, int imgs_per_group, int tiles_w, int tiles_h, int total, int diag) {
     constexpr int NCH = CK / 8, TCOLS = 8 * NMT, PIXB = CK * 2;             // bytes of a staged pixel = the swizzle span
     constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2;            // staged rows
-    constexpr int NCOPY = ONE ? (MODE == 0 ? 2 : 1) : (MODE == 0 ? 4 : 3);   // one box per kw / per dc (ONE: per pixel parity / a single one)
-    constexpr int BOXW = ONE ? (MODE == 0 ? TCOLS + 1 : TCOLS + 2) : TCOLS;  // staged pixels per row
+    // ONE = 2 (forward): ONE contiguous box per tile over the tensor seen as PIXEL PAIRS [n][H][W/2][2C]: [34 rows][TCOLS + 2 pairs],
+    // starting one pair left of the tile (pixel 2 ow0 - 2; the pair grid is the memory's, so out-of-bounds fill stays exact).  An
+    // operand row is a pair (= the swizzle span), tap kw starts kw + 1 pixels into the staged row and its K slice is that pixel's
+    // half of the pair -- no strided gather in the TMA unit.  (A 16-channel inner box under a 64-byte swizzle does NOT land densely:
+    // garbage and an illegal address, measured.)
+    static_assert(ONE != 2 || MODE == 0, "pixel-pair rows are the forward kernel's");
+    constexpr int NCOPY = ONE == 2 ? 1 : ONE ? (MODE == 0 ? 2 : 1) : (MODE == 0 ? 4 : 3);   // boxes per tile
+    constexpr int BOXW = ONE == 2 ? 2 * TCOLS + 4 : ONE ? (MODE == 0 ? TCOLS + 1 : TCOLS + 2) : TCOLS;  // staged pixels per row
+    constexpr int SPAN = ONE == 2 ? 2 * PIXB : PIXB;                          // swizzle span = pitch of the operand rows
     constexpr int ROWB = BOXW * PIXB, COPYB = (IR * ROWB + 1023) / 1024 * 1024, TILE = NCOPY * COPYB;
     constexpr int NN = MODE == 0 ? CN : 4 * CN;                              // MMA N
     constexpr int KPOS = MODE == 0 ? 16 : 9;                                 // taps / neighbours
     constexpr int KT = KPOS * CK;                                            // weight matrix K
     constexpr int ACC = NMT * NN;                                            // TMEM columns per accumulator buffer
     constexpr int TM_COLS = 2 * ACC < 32 ? 32 : 2 * ACC;
-    static_assert(PIXB == 32 || PIXB == 64, "a pixel must be one 32- or 64-byte swizzle span");
+    // depth of the tile ring: as many slots as fit next to the weights (up to 4).  With two, the kernels were bound by the LATENCY of
+    // the strided TMA boxes -- 37 us with neither MMAs nor stores (option dtc_diag = 6), 2 tiles in flight per SM
+    constexpr int NST = direct_tc_slots<MODE, CK, CN, NMT, ONE>();
+    static_assert(SPAN == 32 || SPAN == 64 || SPAN == 128, "operand rows must be one swizzle span");
     static_assert(2 * ACC <= 512 && (TM_COLS & (TM_COLS - 1)) == 0 && NN % 32 == 0 && NN <= 256, "accumulators do not fit");
     extern __shared__ __align__(128) uint8_t dsm_raw[];
     uint8_t* dsm = dsm_raw + ((1024u - (dsaddr(dsm_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned bases
-    uint8_t* wsm = dsm + 2 * TILE;                                            // [NN / 8][KT / 8][8 rows][16 bytes] (no swizzle)
-    __shared__ uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
+    uint8_t* wsm = dsm + NST * TILE;                                          // [NN / 8][KT / 8][8 rows][16 bytes] (no swizzle)
+    __shared__ uint64_t full_bar[NST], empty_bar[NST], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float sbias[CN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -181,10 +211,8 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
     const int ntiles = t_end - t_begin;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            dbar_init(&full_bar[i], 1); dbar_init(&empty_bar[i], 1);
-            dbar_init(&tfull_bar[i], 1); dbar_init(&tempty_bar[i], 128);
-        }
+        for (int i = 0; i < NST; ++i) { dbar_init(&full_bar[i], 1); dbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { dbar_init(&tfull_bar[i], 1); dbar_init(&tempty_bar[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
     }
@@ -229,7 +257,7 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
         // each descriptor was rebuilt with shifts and masks under a divergent `lane == 0`).
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t A_SBO = (MODE == 0 ? 2 : 1) * ROWB;                 // the next output (dy) row: two (one) staged rows further
-        constexpr uint32_t A_HI = (A_SBO >> 4) | (1u << 14) | ((PIXB == 32 ? 6u : 4u) << 29);      // SWIZZLE_32B / SWIZZLE_64B
+        constexpr uint32_t A_HI = (A_SBO >> 4) | (1u << 14) | ((SPAN == 32 ? 6u : SPAN == 64 ? 4u : 2u) << 29);      // SWIZZLE_32B / 64B / 128B
         constexpr uint32_t B_HI = ((uint32_t)((KT / 8) * 128) >> 4) | (1u << 14);                  // no swizzle
         const uint32_t blo = ((dsaddr(wsm) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
         auto mma = [&](uint32_t tacc, uint32_t alo, uint32_t bl, uint32_t acc) {
@@ -238,8 +266,8 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
             dtc_mma(tacc, ((uint64_t)(A_HI | bo) << 32) | alo, ((uint64_t)B_HI << 32) | bl, idesc, acc);
         };
         for (int it = 0; it < ntiles; ++it) {
-            const int s = it & 1, k = it >> 1;
-            if (k >= 1) dbar_wait(&tempty_bar[s], (k - 1) & 1);
+            const int s = it % NST, k = it / NST, b = it & 1, kb = it >> 1;        // ring slot, its use count; TMEM buffer, its use count
+            if (kb >= 1) dbar_wait(&tempty_bar[b], (kb - 1) & 1);
             dbar_wait(&full_bar[s], k & 1);
             dtc_after();
             const uint32_t alo = ((dsaddr(dsm + s * TILE) >> 4) & 0x3FFFu) | (1u << 16);
@@ -247,20 +275,20 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
                 if (!(diag & 4))
 #pragma unroll
                 for (int mt = 0; mt < NMT; ++mt) {
-                    const uint32_t tacc = tmem_base + (uint32_t)(s * ACC + mt * NN);
+                    const uint32_t tacc = tmem_base + (uint32_t)(b * ACC + mt * NN);
 #pragma unroll
                     for (int pos = 0; pos < KPOS; ++pos) {
                         // forward: tap (kh, kw) = copy kw from staged row kh;  gradient: neighbour (dr, dc) = copy dc from staged row dr
                         const int col = MODE == 0 ? (pos & 3) : pos % 3, row = MODE == 0 ? (pos >> 2) : pos / 3;
-                        const int cp = ONE ? (MODE == 0 ? (col & 1) : 0) : col, shift = ONE ? (MODE == 0 ? (col >> 1) : col) : 0;
-                        const uint32_t aoff = cp * COPYB + row * ROWB + (mt * 8 + shift) * PIXB;
+                        const int cp = ONE == 2 ? 0 : ONE ? (MODE == 0 ? (col & 1) : 0) : col, shift = ONE == 2 ? col + 1 : ONE ? (MODE == 0 ? (col >> 1) : col) : 0;
+                        const uint32_t aoff = cp * COPYB + row * ROWB + mt * 8 * SPAN + shift * PIXB;
 #pragma unroll
                         for (int kc = 0; kc < CK / 16; ++kc)
                             mma(tacc, alo + ((aoff + kc * 32) >> 4), blo + (uint32_t)(((pos * NCH + 2 * kc) * 128) >> 4), (pos | kc) != 0 ? 1u : 0u);
                     }
                 }
                 dtc_commit(&empty_bar[s]);
-                dtc_commit(&tfull_bar[s]);
+                dtc_commit(&tfull_bar[b]);
             }
             __syncwarp();
         }
@@ -345,7 +373,7 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
     } else {
         // ------------------------------------------------------------------------------------------ TMA producer
         for (int it = 0; it < ntiles; ++it) {
-            const int t = t_begin + it, s = it & 1, k = it >> 1;
+            const int t = t_begin + it, s = it % NST, k = it / NST;
             const int tw = t % tiles_w, r2 = t / tiles_w, th = r2 % tiles_h, n = r2 / tiles_h;
             if (k >= 1) dbar_wait(&empty_bar[s], (k - 1) & 1);
             if (dtc_elect()) {
@@ -354,7 +382,7 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
 #pragma unroll
                 for (int cp = 0; cp < NCOPY; ++cp) {
                     // forward: pixels 2 (ow0 + c) - 1 + kw, rows 2 oh0 - 1 ..;  gradient: pixels qw0 + c + dc - 1, rows qh0 - 1 ..
-                    const int c1 = MODE == 0 ? 2 * tw * TCOLS - 1 + cp : tw * TCOLS - 1 + cp;
+                    const int c1 = ONE == 2 ? tw * TCOLS - 1 : MODE == 0 ? 2 * tw * TCOLS - 1 + cp : tw * TCOLS - 1 + cp;      // ONE == 2: pair index
                     const int c2 = MODE == 0 ? 2 * th * DT_ROWS - 1 : th * DT_ROWS - 1;
                     dtma_4d(&tm, &full_bar[s], d0 + cp * COPYB, 0, c1, c2, n);
                 }
@@ -369,18 +397,9 @@ direct_tc_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict_
     }
 }
 
-template <int MODE, int CK, int CN, int NMT, int ONE>
-constexpr size_t direct_tc_smem() {
-    constexpr int IR = MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, NCOPY = ONE ? (MODE == 0 ? 2 : 1) : (MODE == 0 ? 4 : 3);
-    constexpr int BOXW = ONE ? (MODE == 0 ? 8 * NMT + 1 : 8 * NMT + 2) : 8 * NMT;
-    constexpr int ROWB = BOXW * CK * 2, COPYB = (IR * ROWB + 1023) / 1024 * 1024;
-    constexpr int NN = MODE == 0 ? CN : 4 * CN, KT = (MODE == 0 ? 16 : 9) * CK;
-    return (size_t)2 * NCOPY * COPYB + (size_t)NN * KT * 2 + 1024;
-}
-
 }  // namespace
 
-int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, CUtensorMap* out);      // conv_tc.cu
+int get_direct_map(const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, int swz, CUtensorMap* out);      // conv_tc.cu
 // option "dtc_diag": timing experiments.  Bits 1, 2, 4, 16 give WRONG results: 1 = contiguous TMA boxes instead of every second pixel,
 // 2 = the epilogue does not store, 4 = no MMAs are issued, 16 = descriptor base offset on windows that start inside a swizzle atom
 // (measured wrong: the tensor core's swizzle is a function of the absolute shared-memory address, like TMA's, so such windows
@@ -398,7 +417,7 @@ template <int MODE, int CK, int CN, int NMT, bool STATS, int ONE = 0>
 cudaError_t launch_direct_tc(const void* src, const void* wgt, const float* bias, void* dst, double* stats, int groups, int N, int Hs, int Ws,
                              int act, cudaStream_t st) {
     constexpr size_t smem = direct_tc_smem<MODE, CK, CN, NMT, ONE>();
-    static_assert(smem <= 227 * 1024, "tile ring + weights exceed the SM's shared memory");
+    static_assert(smem <= 227 * 1024 && direct_tc_slots<MODE, CK, CN, NMT, ONE>() >= 2, "tile ring + weights exceed the SM's shared memory");
     static int per_sm = 0;               // resident CTAs per SM (shared memory decides: 2 with one M tile per tile, else 1)
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(direct_tc_kernel<MODE, CK, CN, NMT, STATS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -408,7 +427,9 @@ cudaError_t launch_direct_tc(const void* src, const void* wgt, const float* bias
         per_sm = n > 2 ? 2 : n;
     }
     CUtensorMap tm;
-    if (get_direct_map(src, N, Hs, Ws, CK, ONE ? (MODE == 0 ? 8 * NMT + 1 : 8 * NMT + 2) : 8 * NMT, MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2, (MODE == 0 && !(g_dtc_diag & 1)) ? 2 : 1, &tm))
+    if (ONE == 2 ? get_direct_map(src, N, Hs, Ws / 2, 2 * CK, 8 * NMT + 2, 2 * DT_ROWS + 2, 1, CK * 4, &tm)         // pixel pairs
+                 : get_direct_map(src, N, Hs, Ws, CK, ONE ? (MODE == 0 ? 8 * NMT + 1 : 8 * NMT + 2) : 8 * NMT, MODE == 0 ? 2 * DT_ROWS + 2 : DT_ROWS + 2,
+                                  (MODE == 0 && !(g_dtc_diag & 1)) ? 2 : 1, CK * 2, &tm))
         return cudaErrorInvalidValue;
     const int Hm = MODE == 0 ? Hs / 2 : Hs, Wm = MODE == 0 ? Ws / 2 : Ws;        // the grid the M tiles cover
     const int tiles_w = Wm / (8 * NMT), tiles_h = Hm / DT_ROWS, total = N * tiles_w * tiles_h;
@@ -434,15 +455,21 @@ cudaError_t direct_tc_fprop(const void* x, const void* pf, const float* bias, vo
     if (Ci == 16 && Co == 32 && wide && (g_dtc_diag & 8))        // A/B: one copy per kw (four) instead of one per pixel parity (two)
         return stats ? launch_direct_tc<0, 16, 32, 2, true, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 16, 32, 2, false, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st);
-    if (Ci == 16 && Co == 32 && wide)
+    if (Ci == 16 && Co == 32 && wide && (g_dtc_diag & 32))       // A/B: two copies (pixel parities, strided boxes)
         return stats ? launch_direct_tc<0, 16, 32, 2, true, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 16, 32, 2, false, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+    if (Ci == 16 && Co == 32 && wide)
+        return stats ? launch_direct_tc<0, 16, 32, 2, true, 2>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 16, 32, 2, false, 2>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     if (Ci == 16 && Co == 32)
         return stats ? launch_direct_tc<0, 16, 32, 1, true, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 16, 32, 1, false, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st);
-    if (Ci == 32 && Co == 64 && wide && !(g_dtc_diag & 8))
+    if (Ci == 32 && Co == 64 && wide && (g_dtc_diag & 32))
         return stats ? launch_direct_tc<0, 32, 64, 2, true, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 32, 64, 2, false, 1>(x, pf, bias, y, stats, groups, N, H, W, act, st);
+    if (Ci == 32 && Co == 64 && wide && !(g_dtc_diag & 8))
+        return stats ? launch_direct_tc<0, 32, 64, 2, true, 2>(x, pf, bias, y, stats, groups, N, H, W, act, st)
+                     : launch_direct_tc<0, 32, 64, 2, false, 2>(x, pf, bias, y, stats, groups, N, H, W, act, st);
     if (Ci == 32 && Co == 64)
         return stats ? launch_direct_tc<0, 32, 64, 1, true, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st)
                      : launch_direct_tc<0, 32, 64, 1, false, 0>(x, pf, bias, y, stats, groups, N, H, W, act, st);
