@@ -423,6 +423,408 @@ bn_bwd_apply8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
     }
 }
 
+// ---- BatchNorm backward in ONE launch for tensors whose (da, y[, a]) fit the SMs' shared memory (every BN layer of Stage-I at
+// batch 128; the <= 40 MB layers of Stage-II).  CTA b owns the contiguous RANGE b of the vector stream:
+//   * one thread brings the range into shared memory with bulk async copies (cp.async.bulk + mbarrier transaction counts, one
+//     barrier per piece of U*active vectors) BEFORE anything else happens -- the whole range is in flight at once (up to
+//     ~190 KB per SM; the register-staged kernels above keep ~40 KB per SM in flight and are latency-bound on 6-25 MB
+//     tensors), and the per-channel constants are fetched under it;
+//   * phase 1 = bn_bwd_reduce8 out of shared memory, per-channel sums into global fp64 atomics;
+//   * a grid-wide rendezvous on the sums;
+//   * phase 2 = bn_bwd_apply8 out of shared memory: (da, y) cross the L2 -> SM path once instead of twice, and one launch +
+//     one dependency edge per layer disappear.  What does not fit (`keep` < range) takes the register path in both phases.
+//
+// The rendezvous does NOT assume co-residency (the captured steps run up to three streams): it counts finished
+// RANGES, not CTAs.  A CTA claims its own range with an atomic exchange; one that has waited `steal_ns` at the rendezvous
+// starts claiming ranges nobody has started (CTAs that are not resident yet) and reduces them through the register path, so
+// whatever subset of the grid is resident finishes by itself; CTAs that start late find their range taken and leave.
+// `work` = {-, ranges done, CTAs exited, error, claim[nranges]}: zero before the first launch, re-armed by the last CTA to
+// leave; owned by the caller (one per call site), so concurrent launches never share it.
+constexpr int FNT = 512;           // threads per CTA (one CTA per SM: the parked range is the SM's shared memory)
+constexpr int FMAXR = 160;         // ranges per launch (<= one per SM)
+constexpr int FPIECES = 16;        // bulk-copy pieces (mbarriers) per range
+struct FusedPlan {
+    int64_t gvec;                  // vectors per image group
+    int range, keep;               // vectors per range (multiple of active), parked per range (multiple of active)
+    int CV, active, rpg, nranges, dbg;     // rpg: ranges per image group -- a range never crosses a group boundary
+    int steal_ns;                          // patience at the rendezvous before taking over ranges nobody has started
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t fsaddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fbar_wait(uint64_t* bar, uint32_t parity) {     // bounded: a protocol bug traps, never hangs
+    const uint32_t addr = fsaddr(bar);
+    uint32_t done;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void fbulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(fsaddr(dst)), "l"(src), "r"(bytes), "r"(fsaddr(bar)) : "memory");
+}
+// thread 0 at the rendezvous: -1 = every range is reduced; r >= 0 = range r was not started by anybody, reduce it as well
+__device__ int fused_wait_or_steal(unsigned* work, int nranges, int steal_ns) {
+    unsigned* claim = work + 4;
+    long long t0 = globaltimer_ns();
+    const long long t_begin = t0;
+    for (;;) {
+        if (ld_acquire_u32(&work[1]) >= (unsigned)nranges) { __threadfence(); return -1; }
+        __nanosleep(40);
+        const long long now = globaltimer_ns();
+        if (now - t0 > steal_ns) {
+            for (int r = 0; r < nranges; ++r)
+                if (ld_acquire_u32(&claim[r]) == 0u && atomicExch(&claim[r], 1u) == 0u) return r;
+            t0 = now;
+            if (now - t_begin > 2000000000ll) { work[3] = 0xdeadu; __trap(); }      // 2 s: never hang the device
+        }
+    }
+}
+
+template <typename T, bool HAS_A>
+__global__ void __launch_bounds__(FNT, 1)
+bn_bwd_fused8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
+                     const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     double* __restrict__ sums, const T* __restrict__ inject, int inject_group, T* __restrict__ dy,
+                     FusedPlan k, float slope, float n, unsigned* __restrict__ work) {
+    SG_PDL_SYNC();
+    extern __shared__ __align__(128) unsigned char fsm[];
+    typedef Raw8<T> R8;
+    R8* p_da = reinterpret_cast<R8*>(fsm);
+    R8* p_y = p_da + k.keep;
+    R8* p_a = p_y + k.keep;
+    const int C = k.CV * 8, tid = (int)threadIdx.x;
+    float* cst = reinterpret_cast<float*>(p_a + (HAS_A ? k.keep : 0));        // [4][C]: mean, rstd, gamma, beta of the range's group
+    float* sacc = cst + 4 * C;                                                // [C][2]: the CTA's sums, later the grid's
+    __shared__ float part[16][FNT + 1];
+    __shared__ uint64_t bars[FPIECES];
+    __shared__ int s_cmd;
+    __shared__ int mine[FMAXR];
+    const int c0 = (tid % k.CV) * 8;
+    const bool worker = tid < k.active;
+    constexpr int U = Unroll<T>::U;
+    const int piece = k.active * U;
+    int nmine = 0;
+    // option bn_fused_dbg: globaltimer stamps of the first and the last CTA at work + 800 bytes (tools/bench_bn_fused.py)
+    long long* stamps = reinterpret_cast<long long*>(work + 200) + (blockIdx.x == 0 ? 0 : 8);
+    const bool stamp_on = k.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+#define FSTAMP(slot) do { if (stamp_on) stamps[slot] = globaltimer_ns(); } while (0)
+    FSTAMP(0);
+    auto range_of = [&](int r, int& g, int64_t& begin, int& len) {
+        g = r / k.rpg;
+        const int64_t off = (int64_t)(r % k.rpg) * k.range;
+        begin = (int64_t)g * k.gvec + off;
+        const int64_t left = k.gvec - off;
+        len = (int)(left < k.range ? left : k.range);
+    };
+
+    if (tid == 0) {
+        for (int p = 0; p < FPIECES; ++p)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fsaddr(&bars[p])), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int b = (int)blockIdx.x;
+        const bool own = atomicExch(&work[4 + b], 1u) == 0u;
+        s_cmd = own ? b : -1;
+        if (own) {                                   // the whole parked part of the range goes in flight right now
+            int g, len;
+            int64_t begin;
+            range_of(b, g, begin, len);
+            const int left = len < k.keep ? len : k.keep;
+            for (int p = 0, v0 = 0; v0 < left; ++p, v0 += piece) {
+                const int cnt = left - v0 < piece ? left - v0 : piece;
+                const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(R8);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"(fsaddr(&bars[p])), "r"(bytes * (HAS_A ? 3u : 2u)) : "memory");
+                fbulk_g2s(p_da + v0, da + (begin + v0) * 8, bytes, &bars[p]);
+                fbulk_g2s(p_y + v0, y + (begin + v0) * 8, bytes, &bars[p]);
+                if (HAS_A) fbulk_g2s(p_a + v0, a_out + (begin + v0) * 8, bytes, &bars[p]);
+            }
+        }
+    }
+    __syncthreads();
+    int cmd = s_cmd;
+    FSTAMP(1);
+
+    // ---------------- phase 1: per-channel sums of this CTA's range (and of ranges nobody else started)
+    while (cmd >= 0) {
+        const int r = cmd;
+        const int keep = nmine == 0 ? k.keep : 0;
+        if (tid == 0) mine[nmine] = r;
+        ++nmine;
+        int g, len;
+        int64_t begin;
+        range_of(r, g, begin, len);
+        // the group's per-channel constants: one coalesced pass into shared memory (under the copies in flight)
+        for (int c = tid; c < C; c += FNT) {
+            const float2 q = *reinterpret_cast<const float2*>(mr + ((int64_t)g * C + c) * 2);
+            cst[c] = q.x; cst[C + c] = q.y; cst[2 * C + c] = gamma[c]; cst[3 * C + c] = HAS_A ? 0.f : beta[c];
+            sacc[2 * c] = 0.f; sacc[2 * c + 1] = 0.f;
+        }
+        __syncthreads();
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        int v = tid;
+        if (worker && v < len) {
+            int waited = 0;                          // pieces of the parked range known to have landed
+            float m[8], rs[8], rg[HAS_A ? 1 : 8], bt[HAS_A ? 1 : 8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                m[j] = cst[c0 + j]; rs[j] = cst[C + c0 + j];
+                if (!HAS_A) { rg[j] = rs[j] * cst[2 * C + c0 + j]; bt[j] = cst[3 * C + c0 + j]; }
+            }
+            auto one = [&](const V8& d, const V8& a, const V8& yy) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float sgn = HAS_A ? a.v[j] : (yy.v[j] - m[j]) * rg[HAS_A ? 0 : j] + bt[HAS_A ? 0 : j];
+                    const float dz = sgn > 0.f ? d.v[j] : slope * d.v[j];
+                    s1[j] += dz;
+                    s2[j] += dz * ((yy.v[j] - m[j]) * rs[j]);
+                }
+            };
+            auto landed = [&](int vv) {              // vector vv of the parked range is in shared memory
+                const int need = vv / piece;
+                while (waited <= need) { fbar_wait(&bars[waited], 0); ++waited; }
+            };
+            while (v < len) {
+                if (v + (U - 1) * k.active < len) {
+                    R8 rd[U], ra[HAS_A ? U : 1], ry[U];
+                    if (v + (U - 1) * k.active < keep) {
+                        landed(v + (U - 1) * k.active);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            rd[u] = p_da[v + u * k.active]; ry[u] = p_y[v + u * k.active];
+                            if (HAS_A) ra[HAS_A ? u : 0] = p_a[v + u * k.active];
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int vv = v + u * k.active;
+                            const int64_t at = (begin + vv) * 8;
+                            if (vv < keep) {
+                                landed(vv);
+                                rd[u] = p_da[vv]; ry[u] = p_y[vv];
+                                if (HAS_A) ra[HAS_A ? u : 0] = p_a[vv];
+                            } else {
+                                rd[u] = ldraw(da + at); ry[u] = ldraw(y + at);
+                                if (HAS_A) ra[HAS_A ? u : 0] = ldraw(a_out + at);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const V8 yy = unpack(ry[u]);
+                        one(unpack(rd[u]), HAS_A ? unpack(ra[HAS_A ? u : 0]) : yy, yy);
+                    }
+                    v += U * k.active;
+                } else {
+                    R8 rd, ry, ra;
+                    const int64_t at = (begin + v) * 8;
+                    if (v < keep) { landed(v); rd = p_da[v]; ry = p_y[v]; if (HAS_A) ra = p_a[v]; }
+                    else { rd = ldraw(da + at); ry = ldraw(y + at); if (HAS_A) ra = ldraw(a_out + at); }
+                    const V8 yy = unpack(ry);
+                    one(unpack(rd), HAS_A ? unpack(ra) : yy, yy);
+                    v += k.active;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { part[2 * j][tid] = s1[j]; part[2 * j + 1][tid] = s2[j]; }
+        __syncthreads();
+        FSTAMP(2);
+        {   // one owner per (channel, sum, segment): the column entries of its channel vector, `nseg` threads share a column
+            const int nout = C * 2, nseg = FNT / nout > 0 ? FNT / nout : 1;
+            for (int w = tid; w < nout * nseg; w += FNT) {
+                const int o = w % nout, seg = w / nout;
+                const int c = o >> 1, row = 2 * (c & 7) + (o & 1);
+                float acc = 0.f;
+                for (int t = (c >> 3) + seg * k.CV; t < k.active; t += k.CV * nseg) acc += part[row][t];
+                if (nseg == 1) atomicAdd(sums + (int64_t)g * C * 2 + o, (double)acc);
+                else atomicAdd(sacc + o, acc);
+            }
+            if (nseg > 1) {
+                __syncthreads();
+                for (int o = tid; o < nout; o += FNT) atomicAdd(sums + (int64_t)g * C * 2 + o, (double)sacc[o]);
+            }
+        }
+        __syncthreads();
+        FSTAMP(3);
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&work[1], 1u);
+            FSTAMP(4);
+            s_cmd = fused_wait_or_steal(work, k.nranges, k.steal_ns);        // ---------------- the rendezvous
+        }
+        __syncthreads();
+        cmd = s_cmd;
+        FSTAMP(5);
+    }
+
+    // ---------------- phase 2: dy = gamma*rstd/n * (n dz - S1 - xhat S2) [+ inject]
+    for (int q = 0; q < nmine; ++q) {
+        const int r = mine[q];
+        const int keep = q == 0 ? k.keep : 0;
+        int g, len;
+        int64_t begin;
+        range_of(r, g, begin, len);
+        // the grid's sums of this group: ONE coalesced L2 read per CTA (every thread fetching its 16 values itself makes
+        // all SMs hammer the same few L2 lines: 15-20 us)
+        if (nmine > 1) {
+            __syncthreads();
+            for (int c = tid; c < C; c += FNT) {
+                const float2 t = *reinterpret_cast<const float2*>(mr + ((int64_t)g * C + c) * 2);
+                cst[c] = t.x; cst[C + c] = t.y; cst[2 * C + c] = gamma[c]; cst[3 * C + c] = HAS_A ? 0.f : beta[c];
+            }
+        }
+        for (int o = tid; o < C * 2; o += FNT) sacc[o] = (float)__ldcg(sums + (int64_t)g * C * 2 + o);
+        __syncthreads();
+        int v = tid;
+        if (!worker || v >= len) continue;
+        float m[8], rs[8], gr[8], c1[8], c2[8], rg[HAS_A ? 1 : 8], bt[HAS_A ? 1 : 8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            m[j] = cst[c0 + j]; rs[j] = cst[C + c0 + j];
+            const float gm = cst[2 * C + c0 + j];
+            const float coef = gm * rs[j] / n;
+            gr[j] = coef * n; c1[j] = coef * sacc[(c0 + j) * 2]; c2[j] = coef * sacc[(c0 + j) * 2 + 1];
+            if (!HAS_A) { rg[j] = rs[j] * gm; bt[j] = cst[3 * C + c0 + j]; }
+        }
+        const bool inj = inject != nullptr && g == inject_group;
+        auto one = [&](const V8& d, const V8& a, const V8& yy, int vv) {
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sgn = HAS_A ? a.v[j] : (yy.v[j] - m[j]) * rg[HAS_A ? 0 : j] + bt[HAS_A ? 0 : j];
+                const float dz = sgn > 0.f ? d.v[j] : slope * d.v[j];
+                const float xh = (yy.v[j] - m[j]) * rs[j];
+                o.v[j] = gr[j] * dz - c1[j] - xh * c2[j];
+            }
+            const int64_t at = begin + vv;
+            if (inj) {
+                V8 w = unpack(ldraw(inject + (at - (int64_t)inject_group * k.gvec) * 8));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] += w.v[j];
+            }
+            st8(dy + at * 8, o);
+        };
+        while (v < len) {
+            if (v + (U - 1) * k.active < len) {
+                R8 rd[U], ra[HAS_A ? U : 1], ry[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int vv = v + u * k.active;
+                    const int64_t at = (begin + vv) * 8;
+                    if (vv < keep) {
+                        rd[u] = p_da[vv]; ry[u] = p_y[vv];
+                        if (HAS_A) ra[HAS_A ? u : 0] = p_a[vv];
+                    } else {
+                        rd[u] = ldraw(da + at); ry[u] = ldraw(y + at);
+                        if (HAS_A) ra[HAS_A ? u : 0] = ldraw(a_out + at);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const V8 yy = unpack(ry[u]);
+                    one(unpack(rd[u]), HAS_A ? unpack(ra[HAS_A ? u : 0]) : yy, yy, v + u * k.active);
+                }
+                v += U * k.active;
+            } else {
+                R8 rd, ry, ra;
+                const int64_t at = (begin + v) * 8;
+                if (v < keep) { rd = p_da[v]; ry = p_y[v]; if (HAS_A) ra = p_a[v]; }
+                else { rd = ldraw(da + at); ry = ldraw(y + at); if (HAS_A) ra = ldraw(a_out + at); }
+                const V8 yy = unpack(ry);
+                one(unpack(rd), HAS_A ? unpack(ra) : yy, yy, v);
+                v += k.active;
+            }
+        }
+    }
+    // ---------------- the last CTA to leave re-arms the work words for the next launch of this call site
+    __syncthreads();
+    FSTAMP(6);
+#undef FSTAMP
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&work[2], 1u) == gridDim.x - 1) {
+            for (int r = 0; r < k.nranges; ++r) work[4 + r] = 0u;
+            work[1] = 0u; work[2] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+int g_bn_fused = 0;                // option "bn_fused": 1 = one launch where the tensor fits; default 0 (two kernels): inside the
+                                   // captured steps the one-launch kernel cannot share an SM with the side stream's wgrad CTAs
+                                   // (190 KB of shared memory each) and measured 1-2 % slower per step, see DESIGN.md section 5
+int g_bn_fused_keep_pct = 50;      // fuse when at least this share of a range can be parked in shared memory
+int g_bn_fused_steal_ns = 30000;   // option "bn_fused_steal_ns": taking over is a safety net, not a schedule (4 us: Stage-I 5.25 -> 5.64 ms)
+int g_bn_fused_dbg = 0;            // option "bn_fused_dbg": the first / last CTA leave globaltimer stamps in the work words
+
+// plan + launch; returns -1 (nothing launched) when the tensor is too large to profit -- the caller then runs reduce + apply
+template <typename T>
+int bn_bwd_fused8(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta,
+                  double* sums, const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups,
+                  int act, unsigned* work, cudaStream_t st) {
+    if (!g_bn_fused || work == nullptr) return -1;
+    constexpr int U = Unroll<T>::U;
+    FusedPlan k;
+    k.CV = C / 8;
+    if (k.CV > FNT || groups > SG_NUM_SMS) return -1;
+    k.gvec = rows_per_group * k.CV;
+    k.active = FNT / k.CV * k.CV;
+    const int slots = SG_NUM_SMS / groups;          // ranges per image group: one CTA per SM in total
+    const int64_t per = (k.gvec + slots - 1) / slots;
+    const int64_t range = (per + k.active - 1) / k.active * k.active;
+    if (range > (1 << 24)) return -1;
+    k.range = (int)range;
+    k.rpg = (int)((k.gvec + range - 1) / range);
+    k.nranges = k.rpg * groups;
+    if (k.nranges > FMAXR) return -1;
+    const size_t acc_bytes = (size_t)C * 6 * sizeof(float);       // per-channel constants [4][C] + sums [C][2]
+    const size_t vb = sizeof(Raw8<T>) * (a_out != nullptr ? 3 : 2);
+    const size_t budget = 188 * 1024;               // next to the 34 KB of static reduction scratch
+    if (acc_bytes + vb * k.active > budget) return -1;
+    int64_t keep = (int64_t)((budget - acc_bytes) / vb) / k.active * k.active;
+    if (keep > range) keep = range;
+    if (keep * 100 < range * g_bn_fused_keep_pct) return -1;
+    if ((keep + (int64_t)k.active * U - 1) / ((int64_t)k.active * U) > FPIECES) return -1;
+    k.keep = (int)keep;
+    k.dbg = g_bn_fused_dbg;
+    k.steal_ns = g_bn_fused_steal_ns;
+    const size_t smem = acc_bytes + vb * (size_t)keep;
+    if (a_out != nullptr) {
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(bn_bwd_fused8_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget); set = true; }
+        launch_pdl(bn_bwd_fused8_kernel<T, true>, dim3(k.nranges), dim3(FNT), smem, st, (const T*)da, (const T*)a_out, (const T*)y, mr,
+                   gamma, beta, sums, (const T*)inject, inject_group, (T*)dy, k, act_slope(act), (float)rows_per_group, work);
+    } else {
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(bn_bwd_fused8_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget); set = true; }
+        launch_pdl(bn_bwd_fused8_kernel<T, false>, dim3(k.nranges), dim3(FNT), smem, st, (const T*)da, (const T*)nullptr, (const T*)y, mr,
+                   gamma, beta, sums, (const T*)inject, inject_group, (T*)dy, k, act_slope(act), (float)rows_per_group, work);
+    }
+    g_launches.fetch_add(1);
+    return check_launch("bn_bwd_fused8");
+}
+template int bn_bwd_fused8<float>(const void*, const void*, const void*, const float*, const float*, const float*, double*, const void*, int, void*, int64_t, int, int, int, unsigned*, cudaStream_t);
+template int bn_bwd_fused8<bf16>(const void*, const void*, const void*, const float*, const float*, const float*, double*, const void*, int, void*, int64_t, int, int, int, unsigned*, cudaStream_t);
+
 // ---- out = da * act'(a_out), 8-wide (ReLU / LeakyReLU / Tanh / none)
 template <typename T>
 __global__ void __launch_bounds__(256, 4)

@@ -111,6 +111,15 @@ int sg_conv_dgrad_stats(const void* dy, const void* pd, void* dx, double* stats,
 // y = conv(x, W) is d loss / d a of the BatchNorm'ed layer below (a = act(bn(ybn))): also reduce that layer's backward
 // statistics sums[groups][Co][2] = (sum dz, sum dz * xhat) -- in the tensor-core epilogue when the shape allows (bf16), otherwise
 // conv + sg_bn_bwd_reduce_y.  act in {none, relu, lrelu}; Co % 8 == 0.
+// 1 when sg_conv_{fprop,dgrad}_bstats reduces the statistics in the tcgen05 epilogue for this shape, 0 when it would run the
+// conv followed by sg_bn_bwd_reduce_y -- a caller that follows up with sg_bn_bwd anyway (reduce + apply in one launch) then
+// prefers the plain conv.
+int sg_conv_bstats_in_epilogue(int dgrad, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups,
+                               int dtype) {
+    if (dtype != SG_BF16) return 0;
+    if (dgrad) return Co * k * k / (s * s) >= sg::g_bstats_min_k && sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups);
+    return Co <= 256 * 8 && Ci * k * k >= sg::g_bstats_min_k && sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups);
+}
 int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
                          const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                          int k, int s, int p, int dtype, void* stream) {

@@ -1924,6 +1924,10 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "force_bn")) { g_force_bn = value; return 0; }
     if (name && !strcmp(name, "force_stages")) { g_force_stages = value; return 0; }
     if (name && !strcmp(name, "dbg")) { g_dbg = value; return 0; }
+    if (name && !strcmp(name, "bn_fused")) { g_bn_fused = value; return 0; }
+    if (name && !strcmp(name, "bn_fused_keep_pct")) { g_bn_fused_keep_pct = value; return 0; }
+    if (name && !strcmp(name, "bn_fused_dbg")) { g_bn_fused_dbg = value; return 0; }
+    if (name && !strcmp(name, "bn_fused_steal_ns")) { g_bn_fused_steal_ns = value; return 0; }
     set_error("unknown option");
     return SG_ERR_BAD_ARG;
 }

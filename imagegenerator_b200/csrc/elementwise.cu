@@ -851,6 +851,7 @@ template <typename T> int bn_act8(const void*, const float*, const float*, const
 template <typename T> int bn_finalize_act8(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, const void*, void*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int bn_bwd_reduce8(const void*, const void*, const void*, const float*, const float*, const float*, double*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, const float*, const float*, const float*, const double*, const void*, int, void*, int64_t, int, int, int, cudaStream_t);
+template <typename T> int bn_bwd_fused8(const void*, const void*, const void*, const float*, const float*, const float*, double*, const void*, int, void*, int64_t, int, int, int, unsigned*, cudaStream_t);
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
 template <typename T> int gp_bn_reduce8(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
 template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
@@ -1149,6 +1150,32 @@ int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const floa
     SG_DISPATCH_T(dtype, e = bn_bwd_apply8<T>(da, nullptr, y, mr, gamma, beta, sums, inject, inject_group, dy, rows_per_group, C,
                                               groups, act, SG_STREAM(stream)));
     return e;
+}
+
+// BatchNorm backward as ONE call: reduce + apply.  Tensors that fit the SMs' shared memory run as a single launch
+// (bn_bwd_fused8_kernel: sums, grid-wide rendezvous, apply out of shared memory); larger ones as the two kernels above.
+// a_out == NULL: the activation's sign is recomputed from y (needs beta).  work: 1 KB of zeroed words owned by the call site.
+int sg_bn_bwd(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta, double* sums,
+              const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups, int act, int dtype,
+              void* work, void* stream) {
+    SG_REQUIRE(a_out != nullptr || beta != nullptr, "bn_bwd: a_out or beta (sign from y) is needed");
+    if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
+        cudaStream_t st = SG_STREAM(stream);
+        cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
+        int e = -1;
+        SG_DISPATCH_T(dtype, e = bn_bwd_fused8<T>(da, a_out, y, mr, gamma, beta, sums, inject, inject_group, dy, rows_per_group, C,
+                                                  groups, act, (unsigned*)work, st));
+        if (e >= 0) return e;
+        SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, a_out, y, mr, gamma, beta, sums, rows_per_group, C, groups, act, st));
+        if (e) return e;
+        SG_DISPATCH_T(dtype, e = bn_bwd_apply8<T>(da, a_out, y, mr, gamma, beta, sums, inject, inject_group, dy, rows_per_group, C,
+                                                  groups, act, st));
+        return e;
+    }
+    SG_REQUIRE(a_out != nullptr, "bn_bwd: this shape needs the activation tensor");
+    int e = sg_bn_bwd_reduce(da, a_out, y, mr, sums, rows_per_group, C, groups, act, dtype, stream);
+    if (e) return e;
+    return sg_bn_bwd_apply(da, a_out, y, mr, gamma, sums, inject, inject_group, dy, rows_per_group, C, groups, act, dtype, stream);
 }
 
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream) {

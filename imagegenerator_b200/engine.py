@@ -305,11 +305,8 @@ class GenRT:
         reduced = False           # sums[i] already came out of the epilogue of the conv that produced da[i]
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
-            if not reduced:
-                ops.bn_bwd_reduce(self.da[i], self.a[i], self.y[i], self.mr[i], self.sums[i], 1, ACT_RELU,
-                                  gamma=bn.weight.data, beta=bn.bias.data)
-            ops.bn_bwd_apply(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i],
-                             self.dy[i], 1, ACT_RELU, beta=bn.bias.data)
+            (ops.bn_bwd_apply if reduced else ops.bn_bwd)(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data,
+                                                          self.sums[i], self.dy[i], 1, ACT_RELU, beta=bn.bias.data)
             x_in = self.a[i - 1] if i > 0 else self.cg
 
             bn_items.append((self.sums[i], bn.weight.grad, bn.bias.grad))
@@ -325,9 +322,8 @@ class GenRT:
             else:
                 # d/d a of the layer below + that layer's BatchNorm-backward statistics in the same kernel
                 bnb = self.layers[i - 1].bn
-                ops.conv_fprop_bstats(self.dy[i], L.pf, self.da[i - 1], self.y[i - 1], self.mr[i - 1], bnb.weight.data,
-                                      bnb.bias.data, self.sums[i - 1], 1, ACT_RELU, L.k, L.s, L.p)
-                reduced = True
+                reduced = ops.conv_bstats_opt("f", self.dy[i], L.pf, self.da[i - 1], self.y[i - 1], self.mr[i - 1], bnb.weight.data,
+                                              bnb.bias.data, self.sums[i - 1], 1, ACT_RELU, L.k, L.s, L.p)
         _side_run(side, lambda: ops.bn_param_grad_multi(bn_items))
         return self.dcg
 
@@ -537,10 +533,9 @@ class CriticRT:
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
             da, a_out, y, dy = gv(self.da[l + 1]), gv(self.a[l + 1]), gv(self.y[l]), gv(self.dy[l])
-            if not reduced:
-                ops.bn_bwd_reduce(da, a_out, y, mr, sums, ng, ACT_LRELU, gamma=bn.weight.data, beta=bn.bias.data)
-            ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
-                             inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data)
+            (ops.bn_bwd_apply if reduced else ops.bn_bwd)(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
+                                                          inject=self.gy[l] if inject else None, inject_group=2 - g0,
+                                                          beta=bn.bias.data)
             if param_grads:
                 bn_items.append((sums, bn.weight.grad, bn.bias.grad))
                 if merge_gp:
@@ -550,9 +545,9 @@ class CriticRT:
             if l >= 2:
                 # d/d a of layer l-1 + that layer's BatchNorm-backward statistics in the same kernel
                 bnb = self.layers[l - 1].bn
-                ops.conv_dgrad_bstats(dy, L.pd, gv(self.da[l]), gv(self.y[l - 1]), self.mr[l - 1][g0:g0 + ng], bnb.weight.data,
-                                      bnb.bias.data, self.sums[l - 1][g0:g0 + ng], ng, ACT_LRELU, L.k, L.s, L.p)
-                reduced = True
+                reduced = ops.conv_bstats_opt("d", dy, L.pd, gv(self.da[l]), gv(self.y[l - 1]), self.mr[l - 1][g0:g0 + ng],
+                                              bnb.weight.data, bnb.bias.data, self.sums[l - 1][g0:g0 + ng], ng, ACT_LRELU,
+                                              L.k, L.s, L.p)
             else:
                 ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
         L0 = self.layers[0]
@@ -599,16 +594,12 @@ class CriticRT:
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr = self.mr[l][2:3]
-            if not reduced:
-                ops.bn_bwd_reduce(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.gsums[l], 1, ACT_LRELU,
-                                  gamma=bn.weight.data, beta=bn.bias.data)
-            ops.bn_bwd_apply(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
-                             self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data)
+            (ops.bn_bwd_apply if reduced else ops.bn_bwd)(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
+                                                          self.gsums[l], self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data)
             if l >= 2:
                 bnb = self.layers[l - 1].bn
-                ops.conv_dgrad_bstats(self.gdy[l], L.pd, self.gda[l], i2(self.y[l - 1]), self.mr[l - 1][2:3], bnb.weight.data,
-                                      bnb.bias.data, self.gsums[l - 1], 1, ACT_LRELU, L.k, L.s, L.p)
-                reduced = True
+                reduced = ops.conv_bstats_opt("d", self.gdy[l], L.pd, self.gda[l], i2(self.y[l - 1]), self.mr[l - 1][2:3],
+                                              bnb.weight.data, bnb.bias.data, self.gsums[l - 1], 1, ACT_LRELU, L.k, L.s, L.p)
             else:
                 ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
         L0 = self.layers[0]

@@ -58,10 +58,10 @@ def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=
     the BN directly, so the kernels take its sign from y and do not stream a_out (False for the layer that closes a
     residual block, whose ReLU sees bn(y) + identity).  ``bn_items``: list collecting (sums, gamma.grad, beta.grad) instead of
     launching the per-layer parameter-gradient kernel."""
-    gb = dict(gamma=bn.weight.data, beta=bn.bias.data) if from_y else {}
-    if not reduced:              # else: buf.sums came out of the epilogue of the conv that produced da (_conv_bstats)
-        ops.bn_bwd_reduce(da, a_out, buf.y, buf.mr, buf.sums, 1, act, **gb)
-    ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act, **({"beta": bn.bias.data} if from_y else {}))
+    # reduced: buf.sums came out of the epilogue of the conv that produced da (_conv_bstats); else reduce + apply (one launch
+    # for the layers that fit the SMs' shared memory)
+    (ops.bn_bwd_apply if reduced else ops.bn_bwd)(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act,
+                                                  **({"beta": bn.bias.data} if from_y else {}))
     if bn_items is not None:
         bn_items.append((buf.sums, bn.weight.grad, bn.bias.grad))       # the caller ends its pass with ONE launch for all layers
     else:
@@ -71,10 +71,10 @@ def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=
 
 def _conv_bstats(ops, direction, dy, L, da_out, below_bn, below_buf, act):
     """Data-gradient conv of layer L whose result ``da_out`` is d loss / d a of the BatchNorm'ed layer below: the launch also
-    reduces that layer's BatchNorm-backward statistics (below_buf.sums) in its epilogue."""
-    fn = ops.conv_fprop_bstats if direction == "f" else ops.conv_dgrad_bstats
-    fn(dy, L.pf if direction == "f" else L.pd, da_out, below_buf.y, below_buf.mr, below_bn.weight.data, below_bn.bias.data,
-       below_buf.sums, 1, act, L.k, L.s, L.p)
+    reduces that layer's BatchNorm-backward statistics (below_buf.sums) in its epilogue.  Returns whether it did (False: only
+    the conv ran; the BatchNorm backward of the layer below reduces + applies in one call)."""
+    return ops.conv_bstats_opt(direction, dy, L.pf if direction == "f" else L.pd, da_out, below_buf.y, below_buf.mr,
+                               below_bn.weight.data, below_bn.bias.data, below_buf.sums, 1, act, L.k, L.s, L.p)
 
 
 class Gen2RT:
@@ -186,8 +186,7 @@ class Gen2RT:
             x_in = self.ub[i - 1].a if i > 0 else self.X[4]
             sr(lambda L=L, dy=dy, x_in=x_in: ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p))
             if i > 0:
-                _conv_bstats(ops, "f", dy, L, self.ub[i - 1].da, self.ups[i - 1].bn, self.ub[i - 1], ACT_RELU)
-                reduced = True
+                reduced = _conv_bstats(ops, "f", dy, L, self.ub[i - 1].da, self.ups[i - 1].bn, self.ub[i - 1], ACT_RELU)
             else:
                 ops.conv_fprop(dy, L.pf, None, self.dX[4], L.k, L.s, L.p)
         for r in range(3, -1, -1):
@@ -196,11 +195,11 @@ class Gen2RT:
             dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False, bn_items=bn_items)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
             sr(lambda l3=l3, b2=b2, dy3=dy3: self._wgrad(l3, b2.a, dy3))
-            _conv_bstats(ops, "d", dy3, l3, b2.da, l2.bn, b2, ACT_RELU)
-            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items, reduced=True)
+            red = _conv_bstats(ops, "d", dy3, l3, b2.da, l2.bn, b2, ACT_RELU)
+            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items, reduced=red)
             sr(lambda l2=l2, b1=b1, dy2=dy2: self._wgrad(l2, b1.a, dy2))
-            _conv_bstats(ops, "d", dy2, l2, b1.da, l1.bn, b1, ACT_RELU)
-            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items, reduced=True)
+            red = _conv_bstats(ops, "d", dy2, l2, b1.da, l1.bn, b1, ACT_RELU)
+            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items, reduced=red)
             sr(lambda l1=l1, r=r, dy1=dy1: self._wgrad(l1, self.X[r], dy1))
             ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
             ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)

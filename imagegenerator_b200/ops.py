@@ -63,6 +63,7 @@ _SIGS = {
     "sg_bn_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
+    "sg_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P, _P],
     "sg_bn_bwd_reduce_y": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_apply_y": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_param_grad": [_P, _P, _P, _I, _I, _P],
@@ -83,6 +84,7 @@ _SIGS = {
     "sg_nhwc_to_nchw_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sg_conv_fprop_bstats": [_P] * 8 + [_I] * 13 + [_P],
     "sg_conv_dgrad_bstats": [_P] * 8 + [_I] * 13 + [_P],
+    "sg_conv_bstats_in_epilogue": [_I] * 13,
     "sg_conv_fprop_tc_bstats": [_P] * 8 + [_I] * 12 + [_P],
     "sg_conv_dgrad_tc_bstats": [_P] * 8 + [_I] * 12 + [_P],
     "sg_ca_forward": [_P] * 14 + [_I] * 7 + [_P],
@@ -165,6 +167,9 @@ class CudaOps:
         else:
             raise ValueError(dtype)
         self.f32, self.f64 = torch.float32, torch.float64
+        # work words of the one-launch BatchNorm backward (sg_bn_bwd): 1 KB per call site, allocated up front
+        self._bn_work = torch.zeros(256 * 1024, dtype=torch.int32, device=self.device)
+        self._bn_slot = {}
         # A/B measurements without code edits: SG_OPTS="name=value,..." sets library options (include/sgb200.h, sg_set_option)
         for kv in filter(None, os.environ.get("SG_OPTS", "").split(",")):
             self.set_option(kv.split("=")[0], int(kv.split("=")[1]))
@@ -366,6 +371,7 @@ class CudaOps:
         assert sums.dtype == torch.float64 and tuple(sums.shape) == (groups, d[6], 2) and ybn.shape == y.shape
         self._ck(self.lib.sg_conv_fprop_bstats(_ptr(x), _ptr(pf), _ptr(y), _ptr(ybn), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
                                                groups, act, *d, k, s, p, self._dt_of(x), self._st()))
+        return True
 
     def conv_dgrad_bstats(self, dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
         self._c(dy, pd, dx, ybn, mr, gamma, beta, sums)
@@ -373,6 +379,19 @@ class CudaOps:
         assert sums.dtype == torch.float64 and tuple(sums.shape) == (groups, d[3], 2) and ybn.shape == dx.shape
         self._ck(self.lib.sg_conv_dgrad_bstats(_ptr(dy), _ptr(pd), _ptr(dx), _ptr(ybn), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
                                                groups, act, *d, k, s, p, self._dt_of(dy), self._st()))
+        return True
+
+    def conv_bstats_opt(self, direction, src, pw, dst, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
+        """The engines' entry: ``direction`` 'f' / 'd'.  Shapes whose statistics come out of the tcgen05 epilogue run
+        conv_{fprop,dgrad}_bstats and return True (``sums`` written); for the others only the conv runs and the return is
+        False -- the caller's ``bn_bwd`` then reduces + applies in one launch instead of conv, reduce, apply."""
+        d = self._conv_dims(src, dst) if direction == "f" else self._conv_dims(dst, src)
+        if self.lib.sg_conv_bstats_in_epilogue(0 if direction == "f" else 1, *d, k, s, p, groups, self._dt_of(src)):
+            (self.conv_fprop_bstats if direction == "f" else self.conv_dgrad_bstats)(src, pw, dst, ybn, mr, gamma, beta, sums,
+                                                                                    groups, act, k, s, p)
+            return True
+        (self.conv_fprop if direction == "f" else self.conv_dgrad)(src, pw, None, dst, k, s, p)
+        return False
 
     def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         self._c(x, dy, dw)
@@ -461,6 +480,23 @@ class CudaOps:
         self._ck(self.lib.sg_bn_bwd_apply(_ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(sums),
                                           _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C, groups,
                                           act, self._dt_of(y), self._st()))
+
+    def bn_bwd(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None):
+        """bn_bwd_reduce + bn_bwd_apply as one call (``beta`` given: the activation's sign is recomputed from y).  Tensors that
+        fit the SMs' shared memory run as ONE launch (sg_bn_bwd); each call site -- identified by its ``sums`` buffer -- owns
+        1 KB of work words in a pool allocated up front (nothing is allocated under graph capture)."""
+        C = y.shape[-1]
+        if C % 8 != 0 or act == ACT_TANH:
+            self.bn_bwd_reduce(da, a_out, y, mr, sums, groups, act, gamma=gamma if beta is not None else None, beta=beta)
+            self.bn_bwd_apply(da, a_out, y, mr, gamma, sums, dy, groups, act, inject=inject, inject_group=inject_group, beta=beta)
+            return
+        self._c(da, a_out, y, mr, gamma, sums, dy, inject, beta)
+        slot = self._bn_slot.setdefault(sums.data_ptr(), len(self._bn_slot))
+        assert slot < 1024, "bn_bwd: out of work slots"
+        work = self._bn_work.data_ptr() + 1024 * slot
+        self._ck(self.lib.sg_bn_bwd(_ptr(da), None if beta is not None else _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma),
+                                    _ptr(beta), _ptr(sums), _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C,
+                                    groups, act, self._dt_of(y), work, self._st()))
 
     def bn_param_grad(self, sums, dgamma, dbeta):
         self._c(sums, dgamma, dbeta)

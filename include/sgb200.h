@@ -65,6 +65,11 @@ int64_t sg_launch_count(void);
  *    kernels instead of the tcgen05 ones, bits 1 / 2 = one CTA per SM for the mma.sync forward / data-gradient kernel;
  *    "dtc_wide" = 1/0 two / one M tiles per tile in direct_tc.cu (default 1); "dtc_diag" = timing experiments that produce WRONG
  *    results (1 contiguous boxes, 2 no stores, 4 no MMAs; default 0 -- never set it outside tools/).
+ *  BatchNorm backward (bn_fast.cu):  "bn_fused" = 1/0 sg_bn_bwd as ONE launch where (da, y) fit the SMs' shared memory (default 0:
+ *    faster alone -- 19 vs 26 us on the 12.6 MB critic layer -- but its 190 KB CTAs cannot share an SM with the side stream's
+ *    wgrad CTAs and the captured steps measured 1-2 % slower); "bn_fused_keep_pct" = least share of a range that must fit
+ *    (default 50); "bn_fused_steal_ns" = patience at the rendezvous before resident CTAs take over ranges of CTAs that have not
+ *    started (default 30000); "bn_fused_dbg" = globaltimer stamps of the first / last CTA in the work words.
  *  "dbg" = verbose launch decisions on stderr. */
 int sg_set_option(const char* name, int value);
 /* one-time device allocations of the library (the launch entry points never allocate): the counter pool of the dynamic conv
@@ -211,6 +216,10 @@ int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn
 int sg_conv_dgrad_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
                          const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                          int k, int s, int p, int dtype, void* stream);
+/* 1: the two calls above reduce the statistics in the tcgen05 epilogue for this shape; 0: they run the conv followed by
+ * sg_bn_bwd_reduce_y (a caller that follows up with sg_bn_bwd -- reduce + apply in one launch -- then prefers the plain conv) */
+int sg_conv_bstats_in_epilogue(int dgrad, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups,
+                               int dtype);
 int sg_conv_fprop_tc_bstats(const void* x, const void* pf, void* y, const void* ybn, const float* mr, const float* gamma,
                             const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo,
                             int Co, int k, int s, int p, void* stream);
@@ -275,6 +284,14 @@ int sg_bn_bwd_reduce_y(const void* da, const void* y, const float* mr, const flo
 int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const float* gamma, const float* beta,
                       const double* sums, const void* inject, int inject_group, void* dy,
                       int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream);
+/* BatchNorm backward in one call (sg_bn_bwd_reduce[_y] + sg_bn_bwd_apply[_y]; torch's native_batch_norm_backward behind
+ * generator_1.py:26-34 / discrminator_1.py:29-37 / generator_2.py:30-38).  Tensors whose (da, y[, a_out]) fit the SMs' shared
+ * memory run as ONE launch: per-channel sums, a grid-wide rendezvous that counts finished ranges (no co-residency assumed),
+ * apply out of shared memory; larger tensors run the two kernels.  a_out == NULL: act' from the sign of gamma*xhat+beta (needs beta).
+ * work: 1 KB of zero-initialised words owned by the call site (re-armed by the kernel), NULL = never fuse. */
+int sg_bn_bwd(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta,
+              double* sums, const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups,
+              int act, int dtype, void* work, void* stream);
 /* dgamma += sum_g S2, dbeta += sum_g S1 */
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream);
 /* the same for n_layers BatchNorm layers in one launch (host arrays of device pointers / sizes, <= 24 layers): a network's

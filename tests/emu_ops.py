@@ -167,6 +167,12 @@ class EmuOps:
         self.conv_dgrad(dy, pd, None, dx, k, s, p)
         self.bn_bwd_reduce(dx, None, ybn, mr, sums, groups, act, gamma=gamma, beta=beta)
 
+    def conv_bstats_opt(self, direction, src, pw, dst, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
+        """CudaOps.conv_bstats_opt: True = the statistics were reduced with the conv (always, here)."""
+        (self.conv_fprop_bstats if direction == "f" else self.conv_dgrad_bstats)(src, pw, dst, ybn, mr, gamma, beta, sums,
+                                                                                groups, act, k, s, p)
+        return True
+
     def conv_wgrad(self, x, dy, dw, k, s, p, impl=""):
         """dw[Co,Ci,kh,kw] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]."""
         g = torch.nn.grad.conv2d_weight(nchw(x).double(), dw.shape, nchw(dy).double(), stride=s, padding=p)
@@ -267,6 +273,11 @@ class EmuOps:
         if inject is not None:
             out[inject_group] += inject.reshape(-1, C).to(ft)
         dy.copy_(out.reshape(dy.shape).to(dy.dtype))
+
+    def bn_bwd(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None):
+        """reduce + apply in one call (CudaOps.bn_bwd: one launch when the tensor fits the SMs' shared memory)."""
+        self.bn_bwd_reduce(da, a_out, y, mr, sums, groups, act, gamma=gamma if beta is not None else None, beta=beta)
+        self.bn_bwd_apply(da, a_out, y, mr, gamma, sums, dy, groups, act, inject=inject, inject_group=inject_group, beta=beta)
 
     def bn_param_grad(self, sums, dgamma, dbeta):
         dgamma.add_(sums[:, :, 1].sum(0).to(dgamma.dtype))

@@ -397,6 +397,101 @@ def test_bn_backward_without_activation_tensor(mode, C, rows, G, act):
              dict(inject=T(inj), inject_group=G - 1, beta=F(beta)))
 
 
+BN_BWD_CASES = [
+    # C, rows per group, groups, act, stored activation tensor?, launches expected (1 = parked in shared memory, 2 = two kernels)
+    (24, 1024, 1, ACT_RELU, False, 1), (128, 512, 3, ACT_LRELU, False, 1), (640, 256, 1, ACT_RELU, False, 1),
+    (80, 4096, 1, ACT_NONE, False, 1), (64, 2048, 3, ACT_LRELU, True, 1), (512, 37, 3, ACT_LRELU, False, 1),
+    (128, 100000, 1, ACT_LRELU, False, 1),        # 25.6 MB in bf16: only part of every range is parked
+    (128, 33000, 3, ACT_LRELU, False, 1),         # the Stage-I critic's largest BatchNorm layer, ragged group size
+    (80, 400000, 1, ACT_RELU, False, 2),          # 64 MB: too large to profit, reduce + apply
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("C,rows,G,act,with_a,launches", BN_BWD_CASES)
+def test_bn_backward_one_call(mode, C, rows, G, act, with_a, launches):
+    """sg_bn_bwd (sums + rendezvous + apply in one launch when the tensor fits the SMs' shared memory) == reduce, then apply;
+    the work words re-arm themselves: the same call site repeated gives the same answer."""
+    y = rnd(G * rows, C)
+    mr = torch.stack([rnd(G, C, scale=0.1), torch.rand(G, C) + 0.5], dim=-1)
+    gamma, beta = torch.rand(C) + 0.5, rnd(C, scale=0.3)
+    da = rnd(G * rows, C, seed=3)
+    inj = rnd(rows, C, seed=5)
+    emu, ops = EmuOps(torch.float64), _ops(mode)
+    sd = ops.act_dtype
+    q = lambda t: t.to(sd)
+    a_out = None
+    if with_a:
+        a_out = torch.zeros(G * rows, C, dtype=torch.float64)
+        emu.bn_act(q(y).double(), mr.double(), gamma.double(), beta.double(), a_out, G, act)
+        a_out = q(a_out.float())
+    kw = dict(inject_group=G - 1) if with_a else dict(inject_group=G - 1)
+    want_sums, want = torch.zeros(G, C, 2, dtype=torch.float64), torch.zeros(G * rows, C, dtype=torch.float64)
+    emu.bn_bwd(q(da).double(), None if a_out is None else a_out.double(), q(y).double(), mr.double(), gamma.double(), want_sums,
+               want, G, act, inject=q(inj).double(), beta=None if with_a else beta.double(), **kw)
+    c = lambda t: t.cuda().contiguous()
+    cda, cy, cmr, cg, cb, cinj = c(q(da)), c(q(y)), c(mr.float()), c(gamma), c(beta), c(q(inj))
+    ca = None if a_out is None else c(a_out)
+    sums = torch.full((G, C, 2), 7.0, dtype=torch.float64, device="cuda")       # the call zeroes them itself
+    dy = torch.zeros(G * rows, C, dtype=sd, device="cuda")
+    first = None
+    try:
+        ops.set_option("bn_fused", 1)                  # the one-launch kernel (an option: off by default, DESIGN.md section 5)
+        for rep in range(4):
+            if rep == 3:
+                ops.set_option("bn_fused", 0)          # the default: memset + reduce + apply behind the same call
+            n0 = ops.launch_count()
+            ops.bn_bwd(cda, ca, cy, cmr, cg, sums, dy, G, act, inject=cinj, beta=None if with_a else cb, **kw)
+            torch.cuda.synchronize()
+            if rep == 3:
+                assert ops.launch_count() - n0 == 2
+            seen = ops.launch_count() - n0
+            if rep < 3:
+                assert seen == launches if mode == "bf16" else seen in (1, 2)  # fp32 storage: twice the bytes, the big cases do not fit
+            t = TOL[mode]
+            got_s, got = sums.cpu(), dy.double().cpu()
+            assert torch.allclose(got_s, want_sums, rtol=1e-3, atol=1e-4 * want_sums.abs().max().item())
+            assert torch.allclose(got, want, rtol=t["rtol"], atol=t["atol"] * want.abs().max().item()), (got - want).abs().max().item()
+            if first is None:
+                first = dy.clone()
+            else:
+                assert (dy.float() - first.float()).abs().max().item() <= t["atol"] * want.abs().max().item()
+    finally:
+        ops.set_option("bn_fused", 0)
+
+
+def test_bn_backward_one_call_under_contention():
+    """The rendezvous counts finished ranges, not CTAs: with a side stream hogging the SMs (some CTAs of the launch start
+    late and find their range taken over) the result is unchanged and nothing hangs."""
+    ops = _ops("bf16")
+    C, rows, G = 256, 128 * 64, 3
+    y, da = rnd(G * rows, C).cuda().bfloat16(), rnd(G * rows, C, seed=3).cuda().bfloat16()
+    mr = torch.stack([rnd(G, C, scale=0.1), torch.rand(G, C) + 0.5], dim=-1).cuda()
+    gamma, beta = (torch.rand(C) + 0.5).cuda(), rnd(C, scale=0.3).cuda()
+    sums = torch.zeros(G, C, 2, dtype=torch.float64, device="cuda")
+    dy = torch.zeros_like(y)
+    try:
+        ops.set_option("bn_fused", 1)
+        n0 = ops.launch_count()
+        ops.bn_bwd(da, None, y, mr, gamma, sums, dy, G, ACT_LRELU, beta=beta)
+        torch.cuda.synchronize()
+        assert ops.launch_count() - n0 == 1
+        want, want_s = dy.clone(), sums.clone()
+        side = torch.cuda.Stream()
+        big = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+        for rep in range(30):
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    big @ big
+            dy.zero_()
+            ops.bn_bwd(da, None, y, mr, gamma, sums, dy, G, ACT_LRELU, beta=beta)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("bn_fused", 0)
+    assert (dy.float() - want.float()).abs().max().item() <= 1e-2 * want.float().abs().max().item()
+    assert torch.allclose(sums, want_s, rtol=1e-6, atol=1e-6 * want_s.abs().max().item())
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_bn_eval_mr(mode):
     C = 96
