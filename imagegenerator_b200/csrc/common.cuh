@@ -127,6 +127,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     } while (0)
 
 extern int g_use_pdl;
+extern int g_dbg_skip_memset;
 extern int g_bn_fused, g_bn_fused_keep_pct, g_bn_fused_dbg, g_bn_fused_steal_ns;      // bn_fast.cu: BatchNorm backward as one launch
 
 template <typename... KArgs, typename... Args>

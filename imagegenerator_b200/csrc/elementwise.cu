@@ -10,6 +10,7 @@ namespace sg {
 
 std::atomic<long long> g_launches{0};
 int g_use_pdl = 1;
+int g_dbg_skip_memset = 0;     // option "dbg_skip_memset": timing experiment, WRONG results (what do the memset nodes cost?)
 static thread_local char g_err[512] = "";
 
 
@@ -856,6 +857,21 @@ template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int
 template <typename T> int gp_bn_reduce8(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
 template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
 
+// Several small buffers zeroed by ONE kernel node (the per-channel sums of every BatchNorm layer of a backward pass): a
+// cudaMemsetAsync in front of every reduction is a graph node of its own between two dependent kernels -- ~3 us each on the
+// latency-bound main chain, and it cuts the programmatic (PDL) edge between its neighbours (Stage-I: 60 per step,
+// 5.30 -> 5.10 ms without them).
+struct ZeroMultiArgs {
+    uint32_t* p[32];
+    int words[32];
+};
+__global__ void __launch_bounds__(256) zero_multi_kernel(ZeroMultiArgs A) {
+    SG_PDL_SYNC();
+    uint32_t* p = A.p[blockIdx.x];
+    const int n = A.words[blockIdx.x];
+    for (int i = threadIdx.x; i < n; i += 256) p[i] = 0u;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -879,6 +895,20 @@ int sg_check_device(void) {
         return SG_ERR_NO_DEVICE;
     }
     if (const char* e = getenv("SG_PDL")) sg::g_use_pdl = atoi(e);      // 0 disables programmatic dependent launch
+    return 0;
+}
+
+int sg_zero_multi(void* const* ptrs, const int64_t* bytes, int n, void* stream) {
+    SG_REQUIRE(n >= 1 && n <= 32, "zero_multi: 1..32 buffers per launch");
+    ZeroMultiArgs A;
+    for (int i = 0; i < n; ++i) {
+        SG_REQUIRE(bytes[i] % 4 == 0 && bytes[i] >= 0 && bytes[i] < (1ll << 31) && ((uintptr_t)ptrs[i] & 3) == 0,
+                   "zero_multi: 4-byte aligned buffers below 2 GB");
+        A.p[i] = (uint32_t*)ptrs[i];
+        A.words[i] = (int)(bytes[i] / 4);
+    }
+    launch_pdl(zero_multi_kernel, dim3(n), dim3(256), 0, SG_STREAM(stream), A);
+    SG_LAUNCHED("zero_multi");
     return 0;
 }
 
@@ -1099,7 +1129,7 @@ int sg_bn_finalize_act(const double* stats, int64_t count, float* mr, float* run
 int sg_bn_bwd_reduce(const void* da, const void* a_out, const void* y, const float* mr, double* sums,
                      int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream) {
     cudaStream_t st = SG_STREAM(stream);
-    cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
+    if (!sg::g_dbg_skip_memset) cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
     int e = 0;
     if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
         SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, a_out, y, mr, nullptr, nullptr, sums, rows_per_group, C, groups, act, st));
@@ -1137,7 +1167,7 @@ int sg_bn_bwd_reduce_y(const void* da, const void* y, const float* mr, const flo
                        int64_t rows_per_group, int C, int groups, int act, int dtype, void* stream) {
     SG_REQUIRE(C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH, "bn_bwd_reduce_y: C %% 8 == 0, act in {none, relu, lrelu}");
     cudaStream_t st = SG_STREAM(stream);
-    cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
+    if (!sg::g_dbg_skip_memset) cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
     int e = 0;
     SG_DISPATCH_T(dtype, e = bn_bwd_reduce8<T>(da, nullptr, y, mr, gamma, beta, sums, rows_per_group, C, groups, act, st));
     return e;
@@ -1157,11 +1187,11 @@ int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const floa
 // a_out == NULL: the activation's sign is recomputed from y (needs beta).  work: 1 KB of zeroed words owned by the call site.
 int sg_bn_bwd(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta, double* sums,
               const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups, int act, int dtype,
-              void* work, void* stream) {
+              int sums_zeroed, void* work, void* stream) {
     SG_REQUIRE(a_out != nullptr || beta != nullptr, "bn_bwd: a_out or beta (sign from y) is needed");
     if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
         cudaStream_t st = SG_STREAM(stream);
-        cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
+        if (!sums_zeroed && !sg::g_dbg_skip_memset) cudaMemsetAsync(sums, 0, (size_t)groups * C * 2 * sizeof(double), st);
         int e = -1;
         SG_DISPATCH_T(dtype, e = bn_bwd_fused8<T>(da, a_out, y, mr, gamma, beta, sums, inject, inject_group, dy, rows_per_group, C,
                                                   groups, act, (unsigned*)work, st));
@@ -1211,10 +1241,10 @@ int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act,
     return e;
 }
 
-int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums,
-                    int64_t rows, int C, int act, int dtype, void* stream) {
+static int gp_bn_reduce_impl(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums,
+                             int64_t rows, int C, int act, int dtype, void* stream, bool zero) {
     cudaStream_t st = SG_STREAM(stream);
-    cudaMemsetAsync(tsums, 0, (size_t)C * 3 * sizeof(double), st);
+    if (zero && !sg::g_dbg_skip_memset) cudaMemsetAsync(tsums, 0, (size_t)C * 3 * sizeof(double), st);
     int e = 0;
     if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
         SG_DISPATCH_T(dtype, e = gp_bn_reduce8<T>(v, da, a_out, y, mr, tsums, rows, C, act, st));
@@ -1225,6 +1255,16 @@ int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void
         e = launch_rowreduce<3>(f, tsums, rows, C, 1, st, "gp_bn_reduce");
     });
     return e;
+}
+
+int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums,
+                    int64_t rows, int C, int act, int dtype, void* stream) {
+    return gp_bn_reduce_impl(v, da, a_out, y, mr, tsums, rows, C, act, dtype, stream, true);
+}
+// the same, ADDING to tsums: the caller zeroed them (sg_zero_multi at the start of the pass) -- no memset node in the chain
+int sg_gp_bn_reduce_acc(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums,
+                        int64_t rows, int C, int act, int dtype, void* stream) {
+    return gp_bn_reduce_impl(v, da, a_out, y, mr, tsums, rows, C, act, dtype, stream, false);
 }
 
 int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
@@ -1289,10 +1329,18 @@ int sg_interp(const void* real, const void* fake, const float* eps, void* out, i
     return e;
 }
 
+static int sample_sqnorm_impl(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream, bool zero);
 int sg_sample_sqnorm(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream) {
+    return sample_sqnorm_impl(g, out, N, per_sample, dtype, stream, true);
+}
+// the same, ADDING to out: the caller zeroed it (sg_zero_multi)
+int sg_sample_sqnorm_acc(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream) {
+    return sample_sqnorm_impl(g, out, N, per_sample, dtype, stream, false);
+}
+static int sample_sqnorm_impl(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream, bool zero) {
     SG_REQUIRE(per_sample % 4 == 0, "sample_sqnorm: per_sample %% 4 != 0");
     cudaStream_t st = SG_STREAM(stream);
-    cudaMemsetAsync(out, 0, N * sizeof(float), st);
+    if (zero && !sg::g_dbg_skip_memset) cudaMemsetAsync(out, 0, N * sizeof(float), st);
     int64_t per_block = 256 * 4 * 4;
     int bx = (int)((per_sample + per_block - 1) / per_block);
     dim3 grid(bx, N);

@@ -293,6 +293,7 @@ class GenRT:
         SideStream for the parameter-gradient kernels (join before the optimizer step)."""
         ops = self.ops
         last = self.layers[-1]
+        ops.zero_multi(self.sums)          # every layer's BatchNorm-backward sums in one kernel node (no memset per layer)
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
 
         def pgrad_last():
@@ -305,8 +306,12 @@ class GenRT:
         reduced = False           # sums[i] already came out of the epilogue of the conv that produced da[i]
         for i in range(len(self.layers) - 2, -1, -1):
             L, bn = self.layers[i], self.layers[i].bn
-            (ops.bn_bwd_apply if reduced else ops.bn_bwd)(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data,
-                                                          self.sums[i], self.dy[i], 1, ACT_RELU, beta=bn.bias.data)
+            if reduced:
+                ops.bn_bwd_apply(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i], self.dy[i], 1,
+                                 ACT_RELU, beta=bn.bias.data)
+            else:
+                ops.bn_bwd(self.da[i], self.a[i], self.y[i], self.mr[i], bn.weight.data, self.sums[i], self.dy[i], 1,
+                           ACT_RELU, beta=bn.bias.data, zeroed=True)
             x_in = self.a[i - 1] if i > 0 else self.cg
 
             bn_items.append((self.sums[i], bn.weight.grad, bn.bias.grad))
@@ -524,6 +529,7 @@ class CriticRT:
         ops, nl = self.ops, self.nl
         gv = lambda t: self.group_view(t, g0, ng)
         a4 = gv(self.a[nl])
+        ops.zero_multi([self.sums[l][g0:g0 + ng] for l in range(1, nl)])      # this pass's BatchNorm-backward sums, one node
         ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
         if param_grads and head_reduce:
             ops.head_bwd_reduce(coef, a4, self.dA)
@@ -533,9 +539,12 @@ class CriticRT:
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
             da, a_out, y, dy = gv(self.da[l + 1]), gv(self.a[l + 1]), gv(self.y[l]), gv(self.dy[l])
-            (ops.bn_bwd_apply if reduced else ops.bn_bwd)(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
-                                                          inject=self.gy[l] if inject else None, inject_group=2 - g0,
-                                                          beta=bn.bias.data)
+            if reduced:
+                ops.bn_bwd_apply(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
+                                 inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data)
+            else:
+                ops.bn_bwd(da, a_out, y, mr, bn.weight.data, sums, dy, ng, ACT_LRELU,
+                           inject=self.gy[l] if inject else None, inject_group=2 - g0, beta=bn.bias.data, zeroed=True)
             if param_grads:
                 bn_items.append((sums, bn.weight.grad, bn.bias.grad))
                 if merge_gp:
@@ -589,13 +598,18 @@ class CriticRT:
         """g = d sum_b score_interp[b] / d interp through train-mode BN (utils.py:15-21)."""
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
+        ops.zero_multi([self.gsums[l] for l in range(1, nl)] + [self.sq])
         ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
         reduced = False
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr = self.mr[l][2:3]
-            (ops.bn_bwd_apply if reduced else ops.bn_bwd)(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
-                                                          self.gsums[l], self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data)
+            if reduced:
+                ops.bn_bwd_apply(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
+                                 self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data)
+            else:
+                ops.bn_bwd(self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
+                           self.gdy[l], 1, ACT_LRELU, beta=bn.bias.data, zeroed=True)
             if l >= 2:
                 bnb = self.layers[l - 1].bn
                 reduced = ops.conv_bstats_opt("d", self.gdy[l], L.pd, self.gda[l], i2(self.y[l - 1]), self.mr[l - 1][2:3],
@@ -605,7 +619,7 @@ class CriticRT:
         L0 = self.layers[0]
         ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
         self.input_grad(self.gdy[0], self.g)
-        ops.sample_sqnorm(self.g, self.sq)
+        ops.sample_sqnorm(self.g, self.sq, zeroed=True)
 
     def gp_second_order(self, coef, side=None, defer_wgrad=False):
         """Backward of coef/2 * sum_b (||g_b||-1)^2 through the first-order graph: parameter grads
@@ -614,6 +628,7 @@ class CriticRT:
         group of its own launches); only the patch matrix of v0 is built here."""
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
+        ops.zero_multi([self.tsums[l] for l in range(1, nl)])
         ops.gp_seed(self.g, self.sq, coef, self.v0)
         L0 = self.layers[0]
         ops.conv_fprop(self.v0, L0.pf, None, self.v[0], L0.k, L0.s, L0.p)
@@ -630,7 +645,8 @@ class CriticRT:
             if not defer_wgrad:
                 _side_run(side, lambda l=l, L=L: ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p))
             mr = self.mr[l][2:3]
-            ops.gp_bn_reduce(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.tsums[l], ACT_LRELU)
+            ops.gp_bn_reduce(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.tsums[l], ACT_LRELU,
+                             zeroed=True)
             ops.gp_bn_apply(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
                             self.gsums[l], self.tsums[l], self.w[l + 1], self.gy[l], bn.weight.grad, ACT_LRELU)
         ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA)

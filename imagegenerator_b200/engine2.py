@@ -53,15 +53,19 @@ def _conv_bn_forward(ops, direction, x, L, buf, out, act, training, residual=Non
         ops.bn_act(buf.y, buf.mr, bn.weight.data, bn.bias.data, out, 1, act, residual=residual)
 
 
-def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=None, reduced=False):
+def _bn_backward(ops, bn, buf, da, a_out, act, side=None, from_y=True, bn_items=None, reduced=False, zeroed=False):
     """dy = BN-backward of (da masked by act'(a_out)); accumulates gamma/beta grads.  ``from_y``: the activation follows
     the BN directly, so the kernels take its sign from y and do not stream a_out (False for the layer that closes a
     residual block, whose ReLU sees bn(y) + identity).  ``bn_items``: list collecting (sums, gamma.grad, beta.grad) instead of
     launching the per-layer parameter-gradient kernel."""
     # reduced: buf.sums came out of the epilogue of the conv that produced da (_conv_bstats); else reduce + apply (one launch
     # for the layers that fit the SMs' shared memory)
-    (ops.bn_bwd_apply if reduced else ops.bn_bwd)(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act,
-                                                  **({"beta": bn.bias.data} if from_y else {}))
+    # zeroed: the caller zeroed buf.sums (ops.zero_multi at the start of its pass)
+    kw = {"beta": bn.bias.data} if from_y else {}
+    if reduced:
+        ops.bn_bwd_apply(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act, **kw)
+    else:
+        ops.bn_bwd(da, a_out, buf.y, buf.mr, bn.weight.data, buf.sums, buf.dy, 1, act, zeroed=zeroed, **kw)
     if bn_items is not None:
         bn_items.append((buf.sums, bn.weight.grad, bn.bias.grad))       # the caller ends its pass with ONE launch for all layers
     else:
@@ -169,6 +173,8 @@ class Gen2RT:
         the parameter-gradient kernels (the caller joins before the optimizer step)."""
         ops = self.ops
         sr = lambda fn: _side_run(side, fn)
+        # every BatchNorm layer's backward sums zeroed by one kernel node (a memset per layer is a graph node in the chain each)
+        ops.zero_multi([b.sums for b in self.ub] + [b.sums for rb in self.rb for b in rb] + [self.b2.sums])
         L = self.up3
         bn_items = []             # (sums, gamma.grad, beta.grad) of the 16 BatchNorm layers: one launch at the end of the pass
         ops.act_bwd(dout, self.out, self.dpre, ACT_TANH)
@@ -182,7 +188,7 @@ class Gen2RT:
         reduced = False           # the next layer's BN-backward statistics already came out of a conv epilogue
         for i in range(2, -1, -1):
             L, b = self.ups[i], self.ub[i]
-            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side, bn_items=bn_items, reduced=reduced)
+            dy = _bn_backward(ops, L.bn, b, b.da, b.a, ACT_RELU, side, bn_items=bn_items, zeroed=True, reduced=reduced)
             x_in = self.ub[i - 1].a if i > 0 else self.X[4]
             sr(lambda L=L, dy=dy, x_in=x_in: ops.conv_wgrad(dy, x_in, L.conv.weight.grad, L.k, L.s, L.p))
             if i > 0:
@@ -192,20 +198,20 @@ class Gen2RT:
         for r in range(3, -1, -1):
             l1, l2, l3 = self.res[r]
             b1, b2, b3 = self.rb[r]
-            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False, bn_items=bn_items)
+            dy3 = _bn_backward(ops, l3.bn, b3, self.dX[r + 1], self.X[r + 1], ACT_RELU, side, from_y=False, bn_items=bn_items, zeroed=True)
             ops.act_bwd(self.dX[r + 1], self.X[r + 1], self.dz, ACT_RELU)            # identity branch
             sr(lambda l3=l3, b2=b2, dy3=dy3: self._wgrad(l3, b2.a, dy3))
             red = _conv_bstats(ops, "d", dy3, l3, b2.da, l2.bn, b2, ACT_RELU)
-            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items, reduced=red)
+            dy2 = _bn_backward(ops, l2.bn, b2, b2.da, b2.a, ACT_RELU, side, bn_items=bn_items, zeroed=True, reduced=red)
             sr(lambda l2=l2, b1=b1, dy2=dy2: self._wgrad(l2, b1.a, dy2))
             red = _conv_bstats(ops, "d", dy2, l2, b1.da, l1.bn, b1, ACT_RELU)
-            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items, reduced=red)
+            dy1 = _bn_backward(ops, l1.bn, b1, b1.da, b1.a, ACT_RELU, side, bn_items=bn_items, zeroed=True, reduced=red)
             sr(lambda l1=l1, r=r, dy1=dy1: self._wgrad(l1, self.X[r], dy1))
             ops.conv_dgrad(dy1, l1.pd, None, self.dX[r], 3, 1, 1)
             ops.scale_rows_add(self.dz, self.ones, self.dX[r], True)
         ops.split_rep_bwd(self.dX[0], self.b2.da, self.dc_hat)
         L = self.ds2
-        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU, side, bn_items=bn_items)
+        dy2 = _bn_backward(ops, L.bn, self.b2, self.b2.da, self.b2.a, ACT_LRELU, side, bn_items=bn_items, zeroed=True)
         sr(lambda L=L, dy2=dy2: ops.conv_wgrad(self.a1, dy2, L.conv.weight.grad, L.k, L.s, L.p))
         ops.conv_dgrad(dy2, L.pd, None, self.da1, L.k, L.s, L.p)
         L = self.ds0

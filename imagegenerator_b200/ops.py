@@ -63,12 +63,14 @@ _SIGS = {
     "sg_bn_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
-    "sg_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P, _P],
+    "sg_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P],
+    "sg_zero_multi": [_P, _P, _I, _P],
     "sg_bn_bwd_reduce_y": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_bwd_apply_y": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_param_grad": [_P, _P, _P, _I, _I, _P],
     "sg_act_bwd": [_P, _P, _P, _L, _I, _I, _P],
     "sg_gp_bn_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "sg_gp_bn_reduce_acc": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "sg_gp_bn_apply": [_P] * 11 + [_L, _I, _I, _I, _P],
     "sg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "sg_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -91,6 +93,7 @@ _SIGS = {
     "sg_ca_backward": [_P] * 4 + [_F] + [_P] * 15 + [_I] * 7 + [_P],
     "sg_interp": [_P, _P, _P, _P, _I, _L, _I, _P],
     "sg_sample_sqnorm": [_P, _P, _I, _L, _I, _P],
+    "sg_sample_sqnorm_acc": [_P, _P, _I, _L, _I, _P],
     "sg_gp_seed": [_P, _P, _F, _P, _I, _L, _I, _P],
     "sg_critic_loss": [_P, _P, _P, _P, _F, _P, _I, _P],
     "sg_gen_loss": [_P, _P, _P, _P, _I, _I, _P],
@@ -212,6 +215,18 @@ class CudaOps:
                 assert t.is_cuda and t.is_contiguous(), "libsgb200 needs contiguous CUDA tensors"
 
     # ---- memory
+    def zero_multi(self, ts):
+        """Up to 32 small buffers (per-channel sums of a backward pass) zeroed by ONE kernel node instead of a memset node in
+        front of every reduction (each a graph node between two dependent kernels: ~3 us on the latency-bound main chain)."""
+        ts = [t for t in ts if t is not None]
+        for i in range(0, len(ts), 32):
+            part = ts[i:i + 32]
+            self._c(*part)
+            n = len(part)
+            ptrs = (_c.c_void_p * n)(*[t.data_ptr() for t in part])
+            nbytes = (_c.c_int64 * n)(*[t.numel() * t.element_size() for t in part])
+            self._ck(self.lib.sg_zero_multi(ptrs, nbytes, n, self._st()))
+
     def zero(self, t):
         self._c(t)
         self._ck(self.lib.sg_zero(_ptr(t), t.numel() * t.element_size(), self._st()))
@@ -481,12 +496,13 @@ class CudaOps:
                                           _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C, groups,
                                           act, self._dt_of(y), self._st()))
 
-    def bn_bwd(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None):
+    def bn_bwd(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None, zeroed=False):
         """bn_bwd_reduce + bn_bwd_apply as one call (``beta`` given: the activation's sign is recomputed from y).  Tensors that
         fit the SMs' shared memory run as ONE launch (sg_bn_bwd); each call site -- identified by its ``sums`` buffer -- owns
-        1 KB of work words in a pool allocated up front (nothing is allocated under graph capture)."""
+        1 KB of work words in a pool allocated up front (nothing is allocated under graph capture).  ``zeroed``: the caller
+        zeroed ``sums`` with ``zero_multi`` at the start of its pass -- no memset node in front of the reduction."""
         C = y.shape[-1]
-        if C % 8 != 0 or act == ACT_TANH:
+        if C % 8 != 0 or act == ACT_TANH:        # (these zero ``sums`` themselves, whatever ``zeroed`` says)
             self.bn_bwd_reduce(da, a_out, y, mr, sums, groups, act, gamma=gamma if beta is not None else None, beta=beta)
             self.bn_bwd_apply(da, a_out, y, mr, gamma, sums, dy, groups, act, inject=inject, inject_group=inject_group, beta=beta)
             return
@@ -496,7 +512,7 @@ class CudaOps:
         work = self._bn_work.data_ptr() + 1024 * slot
         self._ck(self.lib.sg_bn_bwd(_ptr(da), None if beta is not None else _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma),
                                     _ptr(beta), _ptr(sums), _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C,
-                                    groups, act, self._dt_of(y), work, self._st()))
+                                    groups, act, self._dt_of(y), 1 if zeroed else 0, work, self._st()))
 
     def bn_param_grad(self, sums, dgamma, dbeta):
         self._c(sums, dgamma, dbeta)
@@ -520,10 +536,11 @@ class CudaOps:
         self._c(da, a_out, out)
         self._ck(self.lib.sg_act_bwd(_ptr(da), _ptr(a_out), _ptr(out), da.numel(), act, self._dt_of(da), self._st()))
 
-    def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act):
+    def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act, zeroed=False):
         self._c(v, da, a_out, y, mr, tsums)
         C = y.shape[-1]
-        self._ck(self.lib.sg_gp_bn_reduce(_ptr(v), _ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(tsums),
+        fn = self.lib.sg_gp_bn_reduce_acc if zeroed else self.lib.sg_gp_bn_reduce
+        self._ck(fn(_ptr(v), _ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(tsums),
                                           y.numel() // C, C, act, self._dt_of(y), self._st()))
 
     def gp_bn_apply(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act):
@@ -637,10 +654,11 @@ class CudaOps:
         self._ck(self.lib.sg_interp(_ptr(real), _ptr(fake), _ptr(eps), _ptr(out), N, real.numel() // N,
                                     self._dt_of(real), self._st()))
 
-    def sample_sqnorm(self, g, out):
+    def sample_sqnorm(self, g, out, zeroed=False):
         self._c(g, out)
         N = g.shape[0]
-        self._ck(self.lib.sg_sample_sqnorm(_ptr(g), _ptr(out), N, g.numel() // N, self._dt_of(g), self._st()))
+        fn = self.lib.sg_sample_sqnorm_acc if zeroed else self.lib.sg_sample_sqnorm
+        self._ck(fn(_ptr(g), _ptr(out), N, g.numel() // N, self._dt_of(g), self._st()))
 
     def gp_seed(self, g, sq, coef, v):
         self._c(g, sq, v)

@@ -82,6 +82,10 @@ int sg_init_workspace(void);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
 int sg_zero(void* ptr, int64_t bytes, void* stream);
+/* n <= 32 small buffers (4-byte aligned, sizes multiples of 4) zeroed by ONE kernel node: the per-channel sums of every
+   BatchNorm layer of a backward pass (torch zero-fills them inside native_batch_norm_backward).  A memset in front of every
+   reduction is a graph node between two dependent kernels: 60 per Stage-I step, 0.2 ms of its 5.3.  ptrs / bytes: host arrays. */
+int sg_zero_multi(void* const* ptrs, const int64_t* bytes, int n, void* stream);
 int sg_fill_f32(float* ptr, float value, int64_t n, void* stream);
 /* out = a*x + b on fp32 vectors (e.g. 1 - eps of utils.py:11) */
 int sg_affine_f32(const float* x, float a, float b, float* out, int64_t n, void* stream);
@@ -288,10 +292,11 @@ int sg_bn_bwd_apply_y(const void* da, const void* y, const float* mr, const floa
  * generator_1.py:26-34 / discrminator_1.py:29-37 / generator_2.py:30-38).  Tensors whose (da, y[, a_out]) fit the SMs' shared
  * memory run as ONE launch: per-channel sums, a grid-wide rendezvous that counts finished ranges (no co-residency assumed),
  * apply out of shared memory; larger tensors run the two kernels.  a_out == NULL: act' from the sign of gamma*xhat+beta (needs beta).
+ * sums_zeroed != 0: the caller zeroed sums (sg_zero_multi at the start of its pass) -- no memset node in front of the reduction.
  * work: 1 KB of zero-initialised words owned by the call site (re-armed by the kernel), NULL = never fuse. */
 int sg_bn_bwd(const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const float* beta,
               double* sums, const void* inject, int inject_group, void* dy, int64_t rows_per_group, int C, int groups,
-              int act, int dtype, void* work, void* stream);
+              int act, int dtype, int sums_zeroed, void* work, void* stream);
 /* dgamma += sum_g S2, dbeta += sum_g S1 */
 int sg_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int groups, int C, void* stream);
 /* the same for n_layers BatchNorm layers in one launch (host arrays of device pointers / sizes, <= 24 layers): a network's
@@ -306,6 +311,9 @@ int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act,
 /* tsums[C][3] (fp64) = (sum v, sum v*xhat, sum v*dz) */
 int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
                     double* tsums, int64_t rows, int C, int act, int dtype, void* stream);
+/* the same, ADDING to tsums which the caller zeroed (sg_zero_multi at the start of the pass): no memset node in the chain */
+int sg_gp_bn_reduce_acc(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
+                        double* tsums, int64_t rows, int C, int act, int dtype, void* stream);
 int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
                    const float* gamma, const double* sums, const double* tsums, void* w_out, void* gy_out,
                    float* dgamma, int64_t rows, int C, int act, int dtype, void* stream);
@@ -363,6 +371,7 @@ int sg_ca_backward(const void* dcg, const float* eps, const float* mu, const flo
 /* ---- losses (utils.py:8-26; stage_1_train_fn.py:134-144,154-159) ------------------------------ */
 int sg_interp(const void* real, const void* fake, const float* eps, void* out, int N, int64_t per_sample, int dtype, void* stream);
 int sg_sample_sqnorm(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream);
+int sg_sample_sqnorm_acc(const void* g, float* out, int N, int64_t per_sample, int dtype, void* stream);   /* out zeroed by the caller */
 int sg_gp_seed(const void* g, const float* sq, float coef, void* v, int N, int64_t per_sample, int dtype, void* stream);
 int sg_critic_loss(const float* s_real, const float* s_mis, const float* s_fake, const float* sq, float lam,
                    float* out2, int N, void* stream);

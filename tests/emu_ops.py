@@ -274,9 +274,15 @@ class EmuOps:
             out[inject_group] += inject.reshape(-1, C).to(ft)
         dy.copy_(out.reshape(dy.shape).to(dy.dtype))
 
-    def bn_bwd(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None):
-        """reduce + apply in one call (CudaOps.bn_bwd: one launch when the tensor fits the SMs' shared memory)."""
-        self.bn_bwd_reduce(da, a_out, y, mr, sums, groups, act, gamma=gamma if beta is not None else None, beta=beta)
+    def bn_bwd(self, da, a_out, y, mr, gamma, sums, dy, groups, act, inject=None, inject_group=0, beta=None, zeroed=False):
+        """reduce + apply in one call (CudaOps.bn_bwd: one launch when the tensor fits the SMs' shared memory).  ``zeroed``:
+        the caller promises zeroed sums and the kernels ADD to them -- so does this statement (a missing zero_multi shows)."""
+        part = torch.zeros_like(sums)
+        self.bn_bwd_reduce(da, a_out, y, mr, part, groups, act, gamma=gamma if beta is not None else None, beta=beta)
+        if zeroed:
+            sums.add_(part)
+        else:
+            sums.copy_(part)
         self.bn_bwd_apply(da, a_out, y, mr, gamma, sums, dy, groups, act, inject=inject, inject_group=inject_group, beta=beta)
 
     def bn_param_grad(self, sums, dgamma, dbeta):
@@ -291,15 +297,17 @@ class EmuOps:
         out.copy_((da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).to(out.dtype))
 
     # ---- gradient-penalty second order through a train-mode BN (one group)
-    def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act):
+    def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act, zeroed=False):
         """tsums[C,3] (f64) = (sum v, sum v*xhat, sum v*dz)."""
         C = y.shape[-1]
         vv = v.reshape(-1, C).to(torch.float64)
         dz = (da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).reshape(-1, C)
         xh = self._xhat(y, mr, 1)[0].to(torch.float64)
-        tsums[:, 0] = vv.sum(0)
-        tsums[:, 1] = (vv * xh).sum(0)
-        tsums[:, 2] = (vv * dz).sum(0)
+        part = torch.stack([vv.sum(0), (vv * xh).sum(0), (vv * dz).sum(0)], dim=1).to(tsums.dtype)
+        if zeroed:                                   # the caller zeroed tsums (zero_multi); the kernel adds
+            tsums.add_(part)
+        else:
+            tsums.copy_(part)
 
     def gp_bn_apply(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act):
         """Backward of dy = BNbwd(dz; y, gamma) given v = dL/d dy  (SURVEY section 7):
@@ -441,8 +449,12 @@ class EmuOps:
         e = eps.to(torch.float64)[:, None, None, None]
         out.copy_((real.to(torch.float64) * e + fake.to(torch.float64) * (1 - e)).to(out.dtype))
 
-    def sample_sqnorm(self, g, out):
-        out.copy_((g.reshape(g.shape[0], -1).to(torch.float64) ** 2).sum(1).to(out.dtype))
+    def sample_sqnorm(self, g, out, zeroed=False):
+        sq = (g.reshape(g.shape[0], -1).to(torch.float64) ** 2).sum(1).to(out.dtype)
+        if zeroed:
+            out.add_(sq)
+        else:
+            out.copy_(sq)
 
     def gp_seed(self, g, sq, coef, v):
         """v = coef * (1 - 1/||g||) g  (= d[coef/2 * sum (||g||-1)^2] / dg)."""
@@ -497,6 +509,11 @@ class EmuOps:
 
     def zero(self, t):
         t.zero_()
+
+    def zero_multi(self, ts):
+        for t in ts:
+            if t is not None:
+                t.zero_()
 
     def scale_rows_add(self, x, scale, out, accumulate):
         """out (+)= scale[n] * x[n, ...]   (per-sample scale)."""

@@ -450,7 +450,8 @@ def test_bn_backward_one_call(mode, C, rows, G, act, with_a, launches):
                 assert seen == launches if mode == "bf16" else seen in (1, 2)  # fp32 storage: twice the bytes, the big cases do not fit
             t = TOL[mode]
             got_s, got = sums.cpu(), dy.double().cpu()
-            assert torch.allclose(got_s, want_sums, rtol=1e-3, atol=1e-4 * want_sums.abs().max().item())
+            # (per-thread fp32 partial sums: the 32 M-element case sits at ~1e-4 of the largest sum, run to run)
+            assert torch.allclose(got_s, want_sums, rtol=1e-3, atol=1e-3 * want_sums.abs().max().item())
             assert torch.allclose(got, want, rtol=t["rtol"], atol=t["atol"] * want.abs().max().item()), (got - want).abs().max().item()
             if first is None:
                 first = dy.clone()
@@ -490,6 +491,40 @@ def test_bn_backward_one_call_under_contention():
         ops.set_option("bn_fused", 0)
     assert (dy.float() - want.float()).abs().max().item() <= 1e-2 * want.float().abs().max().item()
     assert torch.allclose(sums, want_s, rtol=1e-6, atol=1e-6 * want_s.abs().max().item())
+
+
+def test_zero_multi_and_accumulating_reductions():
+    """sg_zero_multi zeroes up to 32 buffers in one launch (more: one launch per 32); the *_acc reductions / sg_bn_bwd with
+    sums_zeroed ADD to what the caller zeroed -- twice the call, twice the sums."""
+    ops = _ops("bf16")
+    bufs = [torch.full((n,), 3.0, dtype=dt, device="cuda") for n, dt in
+            [(1, torch.float32), (7, torch.float32), (512 * 3 * 2, torch.float64), (1000, torch.float64), (128, torch.float32)] * 8]
+    n0 = ops.launch_count()
+    ops.zero_multi(bufs + [None])
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 == 2 and all(float(b.abs().max()) == 0.0 for b in bufs)
+    C, rows = 64, 4096
+    y, da, v = (rnd(rows, C, seed=i).cuda().bfloat16() for i in (1, 2, 3))
+    a = torch.nn.functional.leaky_relu(y.float(), 0.1).bfloat16()
+    mr = torch.stack([rnd(1, C, scale=0.1), torch.rand(1, C) + 0.5], dim=-1).cuda()
+    gamma, beta = (torch.rand(C) + 0.5).cuda(), rnd(C, scale=0.3).cuda()
+    ts1, ts2 = torch.full((C, 3), 5.0, dtype=torch.float64, device="cuda"), torch.zeros(C, 3, dtype=torch.float64, device="cuda")
+    ops.gp_bn_reduce(v, da, a, y, mr, ts1, ACT_LRELU)
+    ops.gp_bn_reduce(v, da, a, y, mr, ts2, ACT_LRELU, zeroed=True)
+    ops.gp_bn_reduce(v, da, a, y, mr, ts2, ACT_LRELU, zeroed=True)
+    assert torch.allclose(ts2, 2 * ts1, rtol=1e-6, atol=1e-6 * float(ts1.abs().max()))
+    g = rnd(8, 1024, seed=4).cuda().bfloat16()
+    q1, q2 = torch.full((8,), 5.0, device="cuda"), torch.zeros(8, device="cuda")
+    ops.sample_sqnorm(g, q1)
+    ops.sample_sqnorm(g, q2, zeroed=True)
+    ops.sample_sqnorm(g, q2, zeroed=True)
+    assert torch.allclose(q2, 2 * q1, rtol=1e-5)
+    s1, s2 = torch.full((1, C, 2), 5.0, dtype=torch.float64, device="cuda"), torch.zeros(1, C, 2, dtype=torch.float64, device="cuda")
+    dy = torch.zeros_like(y)
+    ops.bn_bwd(da, None, y, mr, gamma, s1, dy, 1, ACT_LRELU, beta=beta)
+    ops.bn_bwd(da, None, y, mr, gamma, s2, dy, 1, ACT_LRELU, beta=beta, zeroed=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(s2, s1, rtol=1e-6, atol=1e-6 * float(s1.abs().max()))
 
 
 @pytest.mark.parametrize("mode", MODES)
