@@ -844,6 +844,71 @@ act_bwd8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __rest
     }
 }
 
+// ---- out = da * act'(a_out) AND colsum[c] += sum_rows out[., c] (ReLU / LeakyReLU / none): the activation backward of a
+// conv + bias + activation layer and that layer's bias gradient in one pass -- the separate column-sum pass (25 us on the
+// critic's 50 MB first activation) sat on the tail of every critic iteration between the last data gradient and the optimizer.
+__device__ __forceinline__ float as_stored(float x, const bf16*) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float as_stored(float x, const float*) { return x; }
+template <typename T>
+__global__ void SG_BN_BOUNDS
+act_bwd8_colsum_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __restrict__ out, float* __restrict__ colsum,
+                       Chunking k, float slope) {
+    SG_PDL_SYNC();
+    __shared__ float part[8][257];
+    const int C = k.CV * 8;
+    int64_t i = (int64_t)blockIdx.x * k.chunk + threadIdx.x;
+    int64_t end = (int64_t)(blockIdx.x + 1) * k.chunk;
+    if (end > k.nvec) end = k.nvec;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if ((int)threadIdx.x < k.active) {
+        constexpr int U = Unroll<T>::U;
+        auto one = [&](const V8& d, const V8& a, int64_t at) {
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+            st8(out + at * 8, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += as_stored(o.v[j], out);      // sums of the STORED (rounded) gradient, as the separate pass saw it
+        };
+        while (i < end) {
+            if (i + (int64_t)(U - 1) * k.active < end) {
+                Raw8<T> rd[U], ra[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t at = (i + (int64_t)u * k.active) * 8;
+                    rd[u] = ldraw(da + at); ra[u] = ldraw(a_out + at);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) one(unpack(rd[u]), unpack(ra[u]), i + (int64_t)u * k.active);
+                i += (int64_t)U * k.active;
+            } else {
+                one(unpack(ldraw(da + i * 8)), unpack(ldraw(a_out + i * 8)), i);
+                i += k.active;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[j][threadIdx.x] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float acc = 0.f;
+        for (int t = c >> 3; t < k.active; t += k.CV) acc += part[c & 7][t];
+        atomicAdd(colsum + c, acc);
+    }
+}
+template <typename T>
+int act_bwd8_colsum(const void* da, const void* a_out, void* out, float* colsum, int64_t rows, int C, int act, cudaStream_t st) {
+    Chunking k = make_chunking(rows, C, 1, 8);
+    launch_pdl(act_bwd8_colsum_kernel<T>, dim3(k.blocks), dim3(256), 0, st, (const T*)da, (const T*)a_out, (T*)out, colsum, k,
+               act_slope(act));
+    g_launches.fetch_add(1);
+    return check_launch("act_bwd8_colsum");
+}
+template int act_bwd8_colsum<float>(const void*, const void*, void*, float*, int64_t, int, int, cudaStream_t);
+template int act_bwd8_colsum<bf16>(const void*, const void*, void*, float*, int64_t, int, int, cudaStream_t);
+
 // ---- gradient-penalty double backward through a train-mode BN (one image group), 8-wide.
 // reduce: tsums[c] += (sum v, sum v*xhat, sum v*dz)
 template <typename T>
@@ -890,12 +955,16 @@ __global__ void SG_BN_BOUNDS
 gp_bn_apply8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
                     const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
                     const double* __restrict__ tsums, T* __restrict__ w_out, T* __restrict__ gy_out, Chunking k, float slope,
-                    float n) {
+                    float n, float* __restrict__ dgamma) {
     SG_PDL_SYNC();
     extern __shared__ float cst[];                  // [8][C]: mean, r, A, B1, B2, E, K1, K2
     const int C = k.CV * 8;
     for (int c = threadIdx.x; c < C; c += 256) {
         const float mean = mr[c * 2], r = mr[c * 2 + 1];
+        if (blockIdx.x == 0 && dgamma != nullptr) {  // the penalty's gamma gradient (was a launch of its own on the main chain)
+            const double S1d = sums[c * 2], S2d = sums[c * 2 + 1], nd = (double)n;
+            dgamma[c] += (float)((double)r / nd * (nd * tsums[c * 3 + 2] - S1d * tsums[c * 3] - S2d * tsums[c * 3 + 1]));
+        }
         const float S1 = (float)sums[c * 2], S2 = (float)sums[c * 2 + 1];
         const float T1 = (float)tsums[c * 3], T2 = (float)tsums[c * 3 + 1], T3 = (float)tsums[c * 3 + 2];
         const float al = gamma[c] * r / n;
@@ -943,18 +1012,18 @@ int gp_bn_reduce8(const void* v, const void* da, const void* a_out, const void* 
 template <typename T>
 int gp_bn_apply8(const void* v, const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
                  const double* sums, const double* tsums, void* w_out, void* gy_out, int64_t rows, int C, int act,
-                 cudaStream_t st) {
+                 float* dgamma, cudaStream_t st) {
     Chunking k = make_chunking(rows, C, 1, 8);
     launch_pdl(gp_bn_apply8_kernel<T>, dim3(k.blocks), dim3(256), (size_t)C * 8 * sizeof(float), st, 
         (const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, tsums, (T*)w_out, (T*)gy_out, k,
-        act_slope(act), (float)rows);
+        act_slope(act), (float)rows, dgamma);
     g_launches.fetch_add(1);
     return check_launch("gp_bn_apply8");
 }
 template int gp_bn_reduce8<float>(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
 template int gp_bn_reduce8<bf16>(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
-template int gp_bn_apply8<float>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
-template int gp_bn_apply8<bf16>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
+template int gp_bn_apply8<float>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
+template int gp_bn_apply8<bf16>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
 
 template <typename T>
 int bn_act8(const void* y, const float* mr, const float* gamma, const float* beta, const void* res, void* out,

@@ -855,7 +855,8 @@ template <typename T> int bn_bwd_apply8(const void*, const void*, const void*, c
 template <typename T> int bn_bwd_fused8(const void*, const void*, const void*, const float*, const float*, const float*, double*, const void*, int, void*, int64_t, int, int, int, unsigned*, cudaStream_t);
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
 template <typename T> int gp_bn_reduce8(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
-template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, cudaStream_t);
+template <typename T> int act_bwd8_colsum(const void*, const void*, void*, float*, int64_t, int, int, cudaStream_t);
+template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
 
 // Several small buffers zeroed by ONE kernel node (the per-channel sums of every BatchNorm layer of a backward pass): a
 // cudaMemsetAsync in front of every reduction is a graph node of its own between two dependent kernels -- ~3 us each on the
@@ -1241,6 +1242,20 @@ int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act,
     return e;
 }
 
+// out = da * act'(a_out) and colsum[c] += column sums of out ([rows][C] tensors; the bias gradient of a conv + bias + activation
+// layer, discrminator_1.py:17-18) in ONE pass.  C % 8 == 0, act in {none, relu, lrelu}; otherwise sg_act_bwd + sg_colsum.
+int sg_act_bwd_colsum(const void* da, const void* a_out, void* out, float* colsum, int64_t rows, int C, int act, int dtype,
+                      void* stream) {
+    if (C % 8 == 0 && C <= 2048 && act != SG_ACT_TANH) {
+        int e = 0;
+        SG_DISPATCH_T(dtype, e = act_bwd8_colsum<T>(da, a_out, out, colsum, rows, C, act, SG_STREAM(stream)));
+        return e;
+    }
+    int e = sg_act_bwd(da, a_out, out, rows * C, act, dtype, stream);
+    if (e) return e;
+    return sg_colsum(out, colsum, rows, C, dtype, stream);
+}
+
 static int gp_bn_reduce_impl(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums,
                              int64_t rows, int C, int act, int dtype, void* stream, bool zero) {
     cudaStream_t st = SG_STREAM(stream);
@@ -1272,12 +1287,10 @@ int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void*
                    float* dgamma, int64_t rows, int C, int act, int dtype, void* stream) {
     int e = 0;
     if (C % 8 == 0 && C <= 1024 && act != SG_ACT_TANH) {
-        SG_DISPATCH_T(dtype, e = gp_bn_apply8<T>(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, rows, C, act,
+        // (the gamma gradient of the penalty term rides in CTA 0's prologue: it needs the same per-channel sums)
+        SG_DISPATCH_T(dtype, e = gp_bn_apply8<T>(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, rows, C, act, dgamma,
                                                  SG_STREAM(stream)));
-        if (e) return e;
-        gp_bn_dgamma_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(mr, sums, tsums, dgamma, (double)rows, C);
-        SG_LAUNCHED("gp_bn_dgamma");
-        return 0;
+        return e;
     }
     SG_DISPATCH_T(dtype, {
         GpBnApplyF<T> f{(const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr, gamma, sums, tsums,

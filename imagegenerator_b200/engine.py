@@ -561,7 +561,9 @@ class CriticRT:
                 ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
         L0 = self.layers[0]
         dy0 = gv(self.dy[0])
-        ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU)
+        # the first conv's bias gradient (column sums of dy0) rides in the activation-backward pass: as a pass of its own it sat
+        # on the tail of every critic iteration, between the last data gradient and the optimizer step
+        ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU, colsum=L0.conv.bias.grad if param_grads else None)
         if param_grads:
             def pgrad0():
                 ops.bn_param_grad_multi(bn_items)
@@ -569,7 +571,6 @@ class CriticRT:
                     ops.conv_wgrad(self.P_full, self.dy_full[0], L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
                 else:
                     ops.conv_wgrad(gv(self.P), dy0, L0.conv.weight.grad.view(L0.co, self.K0, 1, 1), 1, 1, 0)
-                ops.colsum(dy0, L0.conv.bias.grad)
             _side_run(side, pgrad0)
         if need_input_grad:
             # only for the groups [input_grad_from, g0+ng): the real images need no gradient
@@ -816,11 +817,13 @@ class Stage1Engine:
         self.ca.forward(self.d.tem_all[:self.B], eps_ca, z, cg=self.g.cg)   # stage_1_train_fn.py:120-122
         self.g.forward(training=True)                            # :123 -> critic group 1
 
-    def critic_iteration(self, z, eps_ca, eps_gp, next_noise=None):
+    def critic_iteration(self, z, eps_ca, eps_gp, next_noise=None, grads_zeroed=False, zero_after=False):
         """One critic update (stage_1_train_fn.py:120-149).  ``next_noise = (z, eps_ca)`` of the FOLLOWING iteration,
         if given, lets its fake batch be generated on a second stream while this iteration's gradient penalty and
         backward run: the generator's weights do not change between critic updates, and once the critic forward has
-        consumed the image buffer nothing reads it until the next iteration."""
+        consumed the image buffer nothing reads it until the next iteration.  ``grads_zeroed``: the critic's gradient
+        buffers are already zero (the previous iteration ran with ``zero_after``: they were cleared behind its optimizer
+        step on the re-pack stream, off the main chain -- two memset nodes less between forward and backward)."""
         ops, d, B = self.ops, self.d, self.B
         if self._fake_ready:
             self.gen_side.join()
@@ -835,8 +838,9 @@ class Stage1Engine:
             self.side.join()                 # the patch matrix of this iteration's images is built: group 1 may be overwritten
             self.gen_side.run(lambda: self._generate(*next_noise))
             self._fake_ready = True
-        ops.zero(d.fp.grad)                                      # :146
-        ops.zero(d.head_grads)                                   # dA, dBv
+        if not grads_zeroed:
+            ops.zero(d.fp.grad)                                  # :146
+            ops.zero(d.head_grads)                               # dA, dBv
         d.gp_first_order()                                       # utils.py:15-24
         # :140-144; only the host reads the loss values: off the main stream
         self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
@@ -852,16 +856,22 @@ class Stage1Engine:
                    head_reduce=False, side=self.side, merge_gp=True)
         self.optimizer_step(d.fp)                                # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
-        self.pack_side.run(lambda: d.refresh_weights(with_text=True, events=True))
+        def after_step():
+            d.refresh_weights(with_text=True, events=True)
+            if zero_after:                                       # the gradients are dead once the optimizer has read them (:146 of
+                ops.zero(d.fp.grad)                              # the NEXT iteration, issued here: nothing writes them before its
+                ops.zero(d.head_grads)                           # gradient-penalty pass, which waits for this stream's weights)
+        self.pack_side.run(after_step)
         self._ce_ready = True                                    # until the text changes (load_batch / next outer step)
 
-    def generator_step(self):
+    def generator_step(self, grads_zeroed=False):
         ops, d, B = self.ops, self.d, self.B
         d.forward(1, 1, dup_first=1, training=True, before_weights=self.pack_side.join,   # :154 (updated critic, last fake)
                   ce_ready=self._ce_ready)
         st = self.ca.st
         ops.gen_loss(d.score[2], st.mu, st.sigma, self.losses[2:4])          # :155-159
-        ops.zero(self.g.fp.grad); ops.zero(self.ca.fp.grad)      # :161-164
+        if not grads_zeroed:
+            ops.zero(self.g.fp.grad); ops.zero(self.ca.fp.grad)  # :161-164
         d.backward(1, 1, d.coef_gen, inject=False, param_grads=False, need_input_grad=True)
         d.text_backward(d.coef_gen, B, -1.0, False, d.dtem)      # d lossG/d tem through the critic head
         self.g.backward(d.group_view(d.dx, 1, 1), side=self.side)
@@ -873,10 +883,15 @@ class Stage1Engine:
     def outer_step(self, z, eps_ca, eps_gp):
         """z [5,B,100], eps_ca [5,B,128], eps_gp [5,B] (fp32, device)."""
         self._ce_ready = False                                   # a new batch: its text has not been compressed yet
+        ops = self.ops
+        # :161-164 early and off the main chain: nothing touches the generator's / CA's gradients during the critic updates,
+        # and every optimizer_step joins this stream
+        self.side.run(lambda: (ops.zero(self.g.fp.grad), ops.zero(self.ca.fp.grad)))
         for it in range(N_CRITIC):
             nxt = (z[it + 1], eps_ca[it + 1]) if it + 1 < N_CRITIC else None
-            self.critic_iteration(z[it], eps_ca[it], eps_gp[it], next_noise=nxt)
-        self.generator_step()
+            self.critic_iteration(z[it], eps_ca[it], eps_gp[it], next_noise=nxt, grads_zeroed=it > 0,
+                                  zero_after=it + 1 < N_CRITIC)
+        self.generator_step(grads_zeroed=True)
 
     # -- whole step behind static buffers, replayed as one CUDA graph
     def _ensure_static(self):

@@ -69,6 +69,7 @@ _SIGS = {
     "sg_bn_bwd_apply_y": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _P],
     "sg_bn_param_grad": [_P, _P, _P, _I, _I, _P],
     "sg_act_bwd": [_P, _P, _P, _L, _I, _I, _P],
+    "sg_act_bwd_colsum": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "sg_gp_bn_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "sg_gp_bn_reduce_acc": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "sg_gp_bn_apply": [_P] * 11 + [_L, _I, _I, _I, _P],
@@ -532,8 +533,14 @@ class CudaOps:
                                                      P(*[_ptr(t[2]) for t in part]), I(*[t[0].shape[0] for t in part]),
                                                      I(*[t[0].shape[1] for t in part]), n, self._st()))
 
-    def act_bwd(self, da, a_out, out, act):
-        self._c(da, a_out, out)
+    def act_bwd(self, da, a_out, out, act, colsum=None):
+        """out = da * act'(a_out); ``colsum`` (fp32 [C]) += the column sums of out (the layer's bias gradient) in the same pass."""
+        self._c(da, a_out, out, colsum)
+        if colsum is not None:
+            C = da.shape[-1]
+            self._ck(self.lib.sg_act_bwd_colsum(_ptr(da), _ptr(a_out), _ptr(out), _ptr(colsum), da.numel() // C, C, act,
+                                                self._dt_of(da), self._st()))
+            return
         self._ck(self.lib.sg_act_bwd(_ptr(da), _ptr(a_out), _ptr(out), da.numel(), act, self._dt_of(da), self._st()))
 
     def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act, zeroed=False):

@@ -305,6 +305,10 @@ int sg_bn_param_grad_multi(const double* const* sums, float* const* dgamma, floa
                            int n_layers, void* stream);
 /* out = da * act'(a_out)   (LeakyReLU / ReLU / Tanh backward without BN) */
 int sg_act_bwd(const void* da, const void* a_out, void* out, int64_t n, int act, int dtype, void* stream);
+/* the same on a [rows][C] tensor AND colsum[c] += sum_rows out[., c]: the activation backward of a conv + bias + activation layer
+   together with that layer's bias gradient (discrminator_1.py:17-18) in one pass over the tensor */
+int sg_act_bwd_colsum(const void* da, const void* a_out, void* out, float* colsum, int64_t rows, int C, int act, int dtype,
+                      void* stream);
 
 /* ---- WGAN-GP second order through a train-mode BN (replaces autograd's double backward of
  *      utils.py:15-21 under stage_1_train_fn.py:147) ------------------------------------------ */

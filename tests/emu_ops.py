@@ -293,8 +293,10 @@ class EmuOps:
         for sums, dgamma, dbeta in items:
             self.bn_param_grad(sums, dgamma, dbeta)
 
-    def act_bwd(self, da, a_out, out, act):
+    def act_bwd(self, da, a_out, out, act, colsum=None):
         out.copy_((da.to(torch.float64) * _mask(a_out, act).to(torch.float64)).to(out.dtype))
+        if colsum is not None:
+            self.colsum(out, colsum)
 
     # ---- gradient-penalty second order through a train-mode BN (one group)
     def gp_bn_reduce(self, v, da, a_out, y, mr, tsums, act, zeroed=False):
