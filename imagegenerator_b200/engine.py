@@ -517,8 +517,16 @@ class CriticRT:
         ops, L0 = self.ops, self.layers[0]
         ops.conv_dgrad(dy0, L0.pd, None, dx, L0.k, L0.s, L0.p)
 
+    def zero_pass_buffers(self):
+        """The per-channel sums of ALL three passes of a critic update (gp_first_order, gp_second_order, backward over the three
+        groups) + the per-sample squared norms, zeroed by one kernel node; the passes then run with ``prezeroed=True``.  The
+        engine issues it behind the previous optimizer step on the re-pack stream -- off the main chain."""
+        nl = self.nl
+        self.ops.zero_multi([self.sums[l] for l in range(1, nl)] + [self.gsums[l] for l in range(1, nl)] +
+                            [self.tsums[l] for l in range(1, nl)] + [self.sq])
+
     def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, head_reduce=True, input_grad_from=None, side=None,
-                 merge_gp=False):
+                 merge_gp=False, prezeroed=False):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
         d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).  ``coef`` holds the ng*B
         coefficients of these groups.  Groups are independent (own BN statistics, disjoint buffer slices; parameter gradients
@@ -529,10 +537,11 @@ class CriticRT:
         ops, nl = self.ops, self.nl
         gv = lambda t: self.group_view(t, g0, ng)
         a4 = gv(self.a[nl])
-        ops.zero_multi([self.sums[l][g0:g0 + ng] for l in range(1, nl)])      # this pass's BatchNorm-backward sums, one node
+        if not prezeroed:
+            ops.zero_multi([self.sums[l][g0:g0 + ng] for l in range(1, nl)])  # this pass's BatchNorm-backward sums, one node
         ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
-        if param_grads and head_reduce:
-            ops.head_bwd_reduce(coef, a4, self.dA)
+        if param_grads and head_reduce:                  # (same stream as gp_second_order's term: both ADD to dA)
+            _side_run(side, lambda: ops.head_bwd_reduce(coef, a4, self.dA))
         bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
         reduced = False           # sums[l] already came out of the epilogue of the conv that produced da[l + 1]
         for l in range(nl - 1, 0, -1):
@@ -595,11 +604,12 @@ class CriticRT:
             ops.linear_bwd(self.tem_all[:B], m.compress.weight.data, self.dce[:B], None, None, dtem, dx_acc=False)
 
     # ---------------------------------------------------------------- gradient penalty
-    def gp_first_order(self):
+    def gp_first_order(self, prezeroed=False):
         """g = d sum_b score_interp[b] / d interp through train-mode BN (utils.py:15-21)."""
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
-        ops.zero_multi([self.gsums[l] for l in range(1, nl)] + [self.sq])
+        if not prezeroed:
+            ops.zero_multi([self.gsums[l] for l in range(1, nl)] + [self.sq])
         ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
         reduced = False
         for l in range(nl - 1, 0, -1):
@@ -622,14 +632,15 @@ class CriticRT:
         self.input_grad(self.gdy[0], self.g)
         ops.sample_sqnorm(self.g, self.sq, zeroed=True)
 
-    def gp_second_order(self, coef, side=None, defer_wgrad=False):
+    def gp_second_order(self, coef, side=None, defer_wgrad=False, prezeroed=False):
         """Backward of coef/2 * sum_b (||g_b||-1)^2 through the first-order graph: parameter grads
         via wgrad / gamma / head, and gy[l] = d/d y_l for the plain backward to pick up.  ``defer_wgrad``: leave the conv
         weight-gradient terms to the plain backward that follows (backward(merge_gp=True) covers w[l] / gdy[l] as a fourth
         group of its own launches); only the patch matrix of v0 is built here."""
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
-        ops.zero_multi([self.tsums[l] for l in range(1, nl)])
+        if not prezeroed:
+            ops.zero_multi([self.tsums[l] for l in range(1, nl)])
         ops.gp_seed(self.g, self.sq, coef, self.v0)
         L0 = self.layers[0]
         ops.conv_fprop(self.v0, L0.pf, None, self.v[0], L0.k, L0.s, L0.p)
@@ -650,7 +661,8 @@ class CriticRT:
                              zeroed=True)
             ops.gp_bn_apply(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
                             self.gsums[l], self.tsums[l], self.w[l + 1], self.gy[l], bn.weight.grad, ACT_LRELU)
-        ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA)
+        # dA is read by the head / text parameter gradients only (side stream): keep the reduction off the data-gradient chain
+        _side_run(side, lambda: ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA))
 
 
 def export_optimizer_state(opt, fp):
@@ -841,19 +853,20 @@ class Stage1Engine:
         if not grads_zeroed:
             ops.zero(d.fp.grad)                                  # :146
             ops.zero(d.head_grads)                               # dA, dBv
-        d.gp_first_order()                                       # utils.py:15-24
+            d.zero_pass_buffers()
+        d.gp_first_order(prezeroed=True)                         # utils.py:15-24
         # :140-144; only the host reads the loss values: off the main stream
         self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
-        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side, defer_wgrad=True)
-        # head/text gradients first (dA is complete once the plain backward has added its head term)
-        ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA)
-        self.side.run(lambda: d.text_backward(d.coef_text, 2 * B, 0.0, True, None))
+        d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side, defer_wgrad=True, prezeroed=True)
+        # head/text gradients on the side stream, in order: dA is complete once the plain backward's head term is added
+        self.side.run(lambda: (ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA),
+                               d.text_backward(d.coef_text, 2 * B, 0.0, True, None)))
         # One batched backward over all three groups.  Running the gradient-penalty chain (one group) and the interpolated
         # group's backward on a second stream next to a two-group backward was measured and REJECTED (B200, round 2:
         # Stage-I 5.56 -> 5.98 ms, Stage-II 34.6 -> 36.1 ms, 508 -> 603 launches): the persistent conv kernels take every SM
         # they can get, so the two chains do not really overlap, and every split launch pays its fixed ~10 us again.
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
-                   head_reduce=False, side=self.side, merge_gp=True)
+                   head_reduce=False, side=self.side, merge_gp=True, prezeroed=True)
         self.optimizer_step(d.fp)                                # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
         def after_step():
@@ -861,6 +874,7 @@ class Stage1Engine:
             if zero_after:                                       # the gradients are dead once the optimizer has read them (:146 of
                 ops.zero(d.fp.grad)                              # the NEXT iteration, issued here: nothing writes them before its
                 ops.zero(d.head_grads)                           # gradient-penalty pass, which waits for this stream's weights)
+                d.zero_pass_buffers()                            # and the per-channel sums of its three passes
         self.pack_side.run(after_step)
         self._ce_ready = True                                    # until the text changes (load_batch / next outer step)
 
