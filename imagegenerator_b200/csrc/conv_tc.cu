@@ -301,6 +301,7 @@ struct TcpParams {
     const float* bs_gamma;
     const float* bs_beta;
     float bs_slope;              // activation slope for negative pre-activations (0 ReLU, 0.1 LeakyReLU, 1 none)
+    int bs_mask_out;             // store dz (the masked gradient) instead of da: conv + activation backward in one kernel
     SlabEnt slab[4][16];
 };
 
@@ -795,6 +796,15 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     return;
                 }
+                if (bwd && P.bs_mask_out) {                            // the stored result is dz = da * act'(gamma * xhat + beta)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float yv = 0.f;
+                        if (row_ok && c0 + j < ncols) yv = __bfloat162float(yrow[c0 + j]);
+                        const float4 cst = sconst[min(c0 + j, 255)];
+                        f[j] = ((yv - cst.x) * cst.y + cst.z > 0.f) ? f[j] : slope * f[j];
+                    }
+                }
                 uint32_t pk[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -823,7 +833,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             if (row_ok && c0 + j < ncols) yv = __bfloat162float(yrow[c0 + j]);
                             const float4 cst = sconst[min(c0 + j, 255)];
                             const float t = yv - cst.x;
-                            const float dz = (t * cst.y + cst.z > 0.f) ? f[j] : slope * f[j];
+                            const float dz = (P.bs_mask_out || t * cst.y + cst.z > 0.f) ? f[j] : slope * f[j];   // (masked already)
                             const bool live = c0 + j < ncols;          // columns past the layer's channels: table entries unset
                             f[j] = live ? dz : 0.f;
                             sq[j] = live ? dz * (t * cst.w) : 0.f;
@@ -881,6 +891,26 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = tanh_approx(f[j]);
                     }
+                    uint32_t yk[16];
+                    if (bwd) {
+                        // the row's 32 pre-BN values (64 contiguous bytes per lane)
+                        uint4 y0 = make_uint4(0u, 0u, 0u, 0u), y1 = y0, y2 = y0, y3 = y0;
+                        if (n_img < P.n_img) {
+                            const uint4* yp = reinterpret_cast<const uint4*>(yrow + c0);
+                            y0 = __ldg(yp); y1 = __ldg(yp + 1); y2 = __ldg(yp + 2); y3 = __ldg(yp + 3);
+                        }
+                        yk[0] = y0.x; yk[1] = y0.y; yk[2] = y0.z; yk[3] = y0.w; yk[4] = y1.x; yk[5] = y1.y; yk[6] = y1.z; yk[7] = y1.w;
+                        yk[8] = y2.x; yk[9] = y2.y; yk[10] = y2.z; yk[11] = y2.w; yk[12] = y3.x; yk[13] = y3.y; yk[14] = y3.z; yk[15] = y3.w;
+                        if (P.bs_mask_out) {                          // the stored result is dz = da * act'(gamma * xhat + beta)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const uint32_t w2 = yk[j >> 1];
+                                const float yv = __uint_as_float((j & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
+                                const float4 cst = sconst[c0 + j];
+                                f[j] = ((yv - cst.x) * cst.y + cst.z > 0.f) ? f[j] : slope * f[j];
+                            }
+                        }
+                    }
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -902,17 +932,6 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (has_stats) {
                         const bool ok = n_img < P.n_img;
-                        uint32_t yk[16];
-                        if (bwd) {
-                            // the row's 32 pre-BN values (64 contiguous bytes per lane)
-                            uint4 y0 = make_uint4(0u, 0u, 0u, 0u), y1 = y0, y2 = y0, y3 = y0;
-                            if (ok) {
-                                const uint4* yp = reinterpret_cast<const uint4*>(yrow + c0);
-                                y0 = __ldg(yp); y1 = __ldg(yp + 1); y2 = __ldg(yp + 2); y3 = __ldg(yp + 3);
-                            }
-                            yk[0] = y0.x; yk[1] = y0.y; yk[2] = y0.z; yk[3] = y0.w; yk[4] = y1.x; yk[5] = y1.y; yk[6] = y1.z; yk[7] = y1.w;
-                            yk[8] = y2.x; yk[9] = y2.y; yk[10] = y2.z; yk[11] = y2.w; yk[12] = y3.x; yk[13] = y3.y; yk[14] = y3.z; yk[15] = y3.w;
-                        }
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
                             float a[16], sq[16];
@@ -928,7 +947,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                     const float yv = __uint_as_float((j & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
                                     const float4 cst = sconst[c0 + h2 * 16 + j];
                                     const float t = yv - cst.x;
-                                    a[j] = (t * cst.y + cst.z > 0.f) ? a[j] : slope * a[j];
+                                    a[j] = (P.bs_mask_out || t * cst.y + cst.z > 0.f) ? a[j] : slope * a[j];   // (masked already)
                                     sq[j] = a[j] * (t * cst.w);
                                 }
                             } else
@@ -1524,7 +1543,7 @@ static void pick_tcp_config(int M, int n_total, int phases, int nkb, double a_sh
 // mode 0: fprop (act = x [N][H][W][Ck], out = y [N][Ho][Wo][n_total]);
 // mode 1: dgrad (act = dy [N][Ho][Wo][Ck], out = dx [N][H][W][n_total])
 struct BsArgs {            // BatchNorm-backward statistics in the epilogue (TcpParams::bs_*)
-    const void* y; const float* mr; const float* gamma; const float* beta; float slope;
+    const void* y; const float* mr; const float* gamma; const float* beta; float slope; int mask_out;
 };
 
 static int launch_conv_tcp(int mode, const void* act, const void* wpack, const float* bias, void* out, int N, int H, int W,
@@ -1554,7 +1573,7 @@ static int launch_conv_tcp(int mode, const void* act, const void* wpack, const f
     P.stats = stats;
     P.out32 = out32;
     P.residual = (const bf16*)residual;
-    if (bs != nullptr) { P.bs_y = (const bf16*)bs->y; P.bs_mr = bs->mr; P.bs_gamma = bs->gamma; P.bs_beta = bs->beta; P.bs_slope = bs->slope; }
+    if (bs != nullptr) { P.bs_y = (const bf16*)bs->y; P.bs_mr = bs->mr; P.bs_gamma = bs->gamma; P.bs_beta = bs->beta; P.bs_slope = bs->slope; P.bs_mask_out = bs->mask_out; }
     P.trace = g_trace;
     P.sched = (g_dyn_sched && g_sched_pool != nullptr && bs == nullptr) ? g_sched_pool + 2 * (g_sched_seq.fetch_add(1) % SCHED_SLOTS) : nullptr;
     P.sched_chunk = 1;
@@ -2028,7 +2047,7 @@ int sg_conv_fprop_tc_bstats(const void* x, const void* pf, void* y, const void* 
     SG_REQUIRE(sg_conv_tc_stats_supported(0, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups) && Co <= 2048, "conv_fprop_tc_bstats: unsupported shape");
     SG_REQUIRE(act == SG_ACT_NONE || act == SG_ACT_RELU || act == SG_ACT_LRELU, "conv_fprop_tc_bstats: act in {none, relu, lrelu}");
     cudaMemsetAsync(sums, 0, (size_t)groups * Co * 2 * sizeof(double), SG_STREAM(stream));
-    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act)};
+    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act), 0};
     return launch_conv_tcp(0, x, pf, nullptr, y, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, sums, groups, SG_STREAM(stream), nullptr,
                            nullptr, &bs);
 }
@@ -2039,9 +2058,29 @@ int sg_conv_dgrad_tc_bstats(const void* dy, const void* pd, void* dx, const void
     SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc_bstats: inconsistent sizes");
     SG_REQUIRE(act == SG_ACT_NONE || act == SG_ACT_RELU || act == SG_ACT_LRELU, "conv_dgrad_tc_bstats: act in {none, relu, lrelu}");
     cudaMemsetAsync(sums, 0, (size_t)groups * Ci * 2 * sizeof(double), SG_STREAM(stream));
-    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act)};
+    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act), 0};
     return launch_conv_tcp(1, dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, sums, groups, SG_STREAM(stream), nullptr,
                            nullptr, &bs);
+}
+
+// The same with the MASKED gradient stored: dx = dz = conv result * act'(gamma * xhat + beta) -- data-gradient conv + activation
+// (+ BatchNorm-statistics) backward in one kernel, sums[.][.][0] = the column sums of dz.  With the identity table (mean 0, rstd 1,
+// gamma 1, beta 0) and ybn = the stored activation of a conv + bias + activation layer (discrminator_1.py:17-18) this replaces the
+// separate activation-backward pass over the critics' largest activation, and sums[.][.][0] is that layer's bias gradient.
+int sg_conv_dgrad_tc_bstats_masked(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
+                                   const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho,
+                                   int Wo, int Co, int k, int s, int p, int sums_zeroed, void* stream) {
+    SG_REQUIRE(sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups) && Ci <= 256 && Ci % 32 == 0,
+               "conv_dgrad_tc_bstats_masked: unsupported shape");
+    SG_REQUIRE(H == (Ho - 1) * s - 2 * p + k && W == (Wo - 1) * s - 2 * p + k, "conv_dgrad_tc_bstats_masked: inconsistent sizes");
+    SG_REQUIRE(act == SG_ACT_NONE || act == SG_ACT_RELU || act == SG_ACT_LRELU, "conv_dgrad_tc_bstats_masked: act in {none, relu, lrelu}");
+    if (!sums_zeroed) cudaMemsetAsync(sums, 0, (size_t)groups * Ci * 2 * sizeof(double), SG_STREAM(stream));
+    BsArgs bs{ybn, mr, gamma, beta, bs_slope_of(act), 1};
+    return launch_conv_tcp(1, dy, pd, nullptr, dx, N, H, W, Ci, Ho, Wo, Co, k, s, p, SG_ACT_NONE, sums, groups, SG_STREAM(stream), nullptr,
+                           nullptr, &bs);
+}
+int sg_conv_dgrad_tc_bstats_masked_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups) {
+    return sg_conv_tc_stats_supported(1, N, H, W, Ci, Ho, Wo, Co, k, s, p, groups) && Ci <= 256 && Ci % 32 == 0;
 }
 
 }  // extern "C"

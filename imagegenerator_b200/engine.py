@@ -100,6 +100,13 @@ def _capture_stream(device, default_priority=0):
     return torch.cuda.Stream(device=device, priority=pr) if pr != 0 else None
 
 
+# A/B switch (default off, measured): the data-gradient conv of the critic's second layer stores dy0 = da1 * act'(a1) itself and
+# leaves the first conv's bias gradient in its epilogue sums (ops.conv_dgrad_masked) instead of conv + activation-backward pass.
+# Correct (tests/test_kernels_gpu.py::test_conv_dgrad_masked, step parity green) and SLOWER: Stage-I 4.86 -> 5.34 ms -- the
+# statistics epilogue of conv_tcp_kernel costs more on this 512-deep reduction than the 21 us pass it removes.
+MASKED_DGRAD = os.environ.get("SG_MASKED_DGRAD") == "1"
+
+
 def _side_run(side, fn):
     if side is None:
         fn()
@@ -383,6 +390,15 @@ class CriticRT:
                 self.gy.append(ops.empty(shp1))
         assert h == 4, h
         self.nl = len(self.layers)
+        # identity "BatchNorm" table for the first layer (conv + bias + LeakyReLU, no BN): with it the masked data-gradient conv
+        # (ops.conv_dgrad_masked) writes dy0 = da1 * act'(a1) directly and leaves the bias gradient in sums0[.][.][0]
+        C0 = self.layers[0].co
+        self.sums0, self.gsums0 = ops.zeros((G, C0, 2), f64), ops.zeros((1, C0, 2), f64)
+        self.id_mr = ops.zeros((G, C0, 2), f32)
+        self.id_mr[:, :, 1] = 1.0
+        self.id_gamma, self.id_beta = ops.zeros((C0,), f32), ops.zeros((C0,), f32)
+        self.id_gamma.fill_(1.0)
+        self.bias_scratch = ops.zeros((C0,), f32)                    # receives the meaningless "gamma gradient" of that table
         # first layer (3-channel image): forward and input gradient are direct kernels (thin_conv.cu); its WEIGHT gradient
         # is a 1x1 GEMM over the patch matrix P[pix][ci*16+tap] -- the PyTorch weight order, so the gradient lands in place
         L0 = self.layers[0]
@@ -517,16 +533,23 @@ class CriticRT:
         ops, L0 = self.ops, self.layers[0]
         ops.conv_dgrad(dy0, L0.pd, None, dx, L0.k, L0.s, L0.p)
 
+    def seed_heads(self, coef):
+        """d score / d (last activation) = coef (x) A for the plain backward over all three groups and 1 (x) A for the
+        penalty's first-order pass: both depend on the head weights only, so the engine issues them behind the re-pack of
+        the weights (re-pack stream) and runs the passes with ``seeded=True`` -- two launches less on the main chain."""
+        self.ops.head_bwd_data(self.coef_one, self.A, self.gda[self.nl])
+        self.ops.head_bwd_data(coef, self.A, self.da[self.nl])
+
     def zero_pass_buffers(self):
         """The per-channel sums of ALL three passes of a critic update (gp_first_order, gp_second_order, backward over the three
         groups) + the per-sample squared norms, zeroed by one kernel node; the passes then run with ``prezeroed=True``.  The
         engine issues it behind the previous optimizer step on the re-pack stream -- off the main chain."""
         nl = self.nl
         self.ops.zero_multi([self.sums[l] for l in range(1, nl)] + [self.gsums[l] for l in range(1, nl)] +
-                            [self.tsums[l] for l in range(1, nl)] + [self.sq])
+                            [self.tsums[l] for l in range(1, nl)] + [self.sq, self.sums0, self.gsums0])
 
     def backward(self, g0, ng, coef, inject, param_grads, need_input_grad, head_reduce=True, input_grad_from=None, side=None,
-                 merge_gp=False, prezeroed=False):
+                 merge_gp=False, prezeroed=False, seeded=False):
         """Backward of sum_n coef[n]*score[n] over groups [g0,g0+ng) (+ ``inject``: extra
         d loss / d y_l on the interpolated group from the gradient-penalty second-order pass).  ``coef`` holds the ng*B
         coefficients of these groups.  Groups are independent (own BN statistics, disjoint buffer slices; parameter gradients
@@ -539,11 +562,13 @@ class CriticRT:
         a4 = gv(self.a[nl])
         if not prezeroed:
             ops.zero_multi([self.sums[l][g0:g0 + ng] for l in range(1, nl)])  # this pass's BatchNorm-backward sums, one node
-        ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
+        if not seeded:
+            ops.head_bwd_data(coef, self.A, gv(self.da[nl]))
         if param_grads and head_reduce:                  # (same stream as gp_second_order's term: both ADD to dA)
             _side_run(side, lambda: ops.head_bwd_reduce(coef, a4, self.dA))
         bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
         reduced = False           # sums[l] already came out of the epilogue of the conv that produced da[l + 1]
+        L0, dy0, masked0 = self.layers[0], gv(self.dy[0]), False
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
@@ -566,13 +591,20 @@ class CriticRT:
                 reduced = ops.conv_bstats_opt("d", dy, L.pd, gv(self.da[l]), gv(self.y[l - 1]), self.mr[l - 1][g0:g0 + ng],
                                               bnb.weight.data, bnb.bias.data, self.sums[l - 1][g0:g0 + ng], ng, ACT_LRELU,
                                               L.k, L.s, L.p)
+            elif MASKED_DGRAD and ops.conv_dgrad_masked_supported(dy, dy0, L.k, L.s, L.p, ng):
+                # l == 1: the data-gradient conv stores dy0 = da1 * act'(a1) itself (no activation-backward pass over the
+                # critic's largest tensor) and its epilogue leaves the first conv's bias gradient in sums0[.][.][0]
+                s0 = self.sums0[g0:g0 + ng]
+                ops.conv_dgrad_masked(dy, L.pd, dy0, gv(self.a[1]), self.id_mr[g0:g0 + ng], self.id_gamma, self.id_beta, s0, ng,
+                                      ACT_LRELU, L.k, L.s, L.p, zeroed=prezeroed)
+                if param_grads:
+                    bn_items.append((s0, self.bias_scratch, L0.conv.bias.grad))
+                masked0 = True
             else:
                 ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
-        L0 = self.layers[0]
-        dy0 = gv(self.dy[0])
-        # the first conv's bias gradient (column sums of dy0) rides in the activation-backward pass: as a pass of its own it sat
-        # on the tail of every critic iteration, between the last data gradient and the optimizer step
-        ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU, colsum=L0.conv.bias.grad if param_grads else None)
+        if not masked0:
+            # the first conv's bias gradient (column sums of dy0) rides in the activation-backward pass
+            ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU, colsum=L0.conv.bias.grad if param_grads else None)
         if param_grads:
             def pgrad0():
                 ops.bn_param_grad_multi(bn_items)
@@ -604,14 +636,15 @@ class CriticRT:
             ops.linear_bwd(self.tem_all[:B], m.compress.weight.data, self.dce[:B], None, None, dtem, dx_acc=False)
 
     # ---------------------------------------------------------------- gradient penalty
-    def gp_first_order(self, prezeroed=False):
+    def gp_first_order(self, prezeroed=False, seeded=False):
         """g = d sum_b score_interp[b] / d interp through train-mode BN (utils.py:15-21)."""
         ops, nl = self.ops, self.nl
         i2 = lambda t: self.group_view(t, 2, 1)
         if not prezeroed:
             ops.zero_multi([self.gsums[l] for l in range(1, nl)] + [self.sq])
-        ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
-        reduced = False
+        if not seeded:
+            ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
+        reduced, masked0 = False, False
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr = self.mr[l][2:3]
@@ -625,10 +658,14 @@ class CriticRT:
                 bnb = self.layers[l - 1].bn
                 reduced = ops.conv_bstats_opt("d", self.gdy[l], L.pd, self.gda[l], i2(self.y[l - 1]), self.mr[l - 1][2:3],
                                               bnb.weight.data, bnb.bias.data, self.gsums[l - 1], 1, ACT_LRELU, L.k, L.s, L.p)
+            elif MASKED_DGRAD and ops.conv_dgrad_masked_supported(self.gdy[l], self.gdy[0], L.k, L.s, L.p, 1):
+                ops.conv_dgrad_masked(self.gdy[l], L.pd, self.gdy[0], i2(self.a[1]), self.id_mr[2:3], self.id_gamma, self.id_beta,
+                                      self.gsums0, 1, ACT_LRELU, L.k, L.s, L.p, zeroed=prezeroed)
+                masked0 = True
             else:
                 ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
-        L0 = self.layers[0]
-        ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
+        if not masked0:
+            ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
         self.input_grad(self.gdy[0], self.g)
         ops.sample_sqnorm(self.g, self.sq, zeroed=True)
 
@@ -764,6 +801,7 @@ class Stage1Engine:
         self.pack_side = SideStream(ops, priority=_prio("SG_PACK_PRIO", 0))
         self._ce_ready = False                        # compressed text valid for the current weights + batch
         self._fake_ready = False
+        self._interp_ready = False       # the next iteration's interpolated images were produced ahead as well
         self.allreduce = allreduce                   # callable(flat_grad) or None (legacy, unbucketed)
         self.comm = comm                             # comm.PeerComm / comm.DistComm or None
         self.world = world_size
@@ -835,26 +873,36 @@ class Stage1Engine:
         backward run: the generator's weights do not change between critic updates, and once the critic forward has
         consumed the image buffer nothing reads it until the next iteration.  ``grads_zeroed``: the critic's gradient
         buffers are already zero (the previous iteration ran with ``zero_after``: they were cleared behind its optimizer
-        step on the re-pack stream, off the main chain -- two memset nodes less between forward and backward)."""
+        step on the re-pack stream, off the main chain, together with the per-channel sums of this iteration's three passes and
+        the head seeds of its two backward passes -- seven graph nodes less between forward and optimizer step).  A third
+        element of ``next_noise`` (the next eps_gp) moves the next interpolation onto the generator's side stream too."""
         ops, d, B = self.ops, self.d, self.B
+        X = d.a[0]
+        interp = lambda e: ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), e, d.group_view(X, 2, 1))   # utils.py:10-11
         if self._fake_ready:
             self.gen_side.join()
             self._fake_ready = False
+            if not self._interp_ready:
+                interp(eps_gp)
         else:
             self._generate(z, eps_ca)
-        X = d.a[0]
-        ops.interp(d.group_view(X, 0, 1), d.group_view(X, 1, 1), eps_gp, d.group_view(X, 2, 1))   # utils.py:10-11
+            interp(eps_gp)
+        self._interp_ready = False
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,    # :125-132 + utils.py:13
                   before_weights=self.pack_side.join, ce_ready=self._ce_ready, patches_on=self.side)
         if next_noise is not None and self.gen_side.enabled:
             self.side.join()                 # the patch matrix of this iteration's images is built: group 1 may be overwritten
-            self.gen_side.run(lambda: self._generate(*next_noise))
+            if len(next_noise) > 2:          # + the next interpolation (its eps given): one launch less at the head of the chain
+                self.gen_side.run(lambda: (self._generate(*next_noise[:2]), interp(next_noise[2])))
+                self._interp_ready = True
+            else:
+                self.gen_side.run(lambda: self._generate(*next_noise))
             self._fake_ready = True
         if not grads_zeroed:
             ops.zero(d.fp.grad)                                  # :146
             ops.zero(d.head_grads)                               # dA, dBv
             d.zero_pass_buffers()
-        d.gp_first_order(prezeroed=True)                         # utils.py:15-24
+        d.gp_first_order(prezeroed=True, seeded=grads_zeroed)    # utils.py:15-24
         # :140-144; only the host reads the loss values: off the main stream
         self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side, defer_wgrad=True, prezeroed=True)
@@ -866,7 +914,7 @@ class Stage1Engine:
         # Stage-I 5.56 -> 5.98 ms, Stage-II 34.6 -> 36.1 ms, 508 -> 603 launches): the persistent conv kernels take every SM
         # they can get, so the two chains do not really overlap, and every split launch pays its fixed ~10 us again.
         d.backward(0, 3, d.coef_critic, inject=True, param_grads=True, need_input_grad=False,   # :147
-                   head_reduce=False, side=self.side, merge_gp=True, prezeroed=True)
+                   head_reduce=False, side=self.side, merge_gp=True, prezeroed=True, seeded=grads_zeroed)
         self.optimizer_step(d.fp)                                # :149
         # re-pack the bf16 operands on a side stream: the next forward's interpolation / patch matrix need no weights
         def after_step():
@@ -875,6 +923,7 @@ class Stage1Engine:
                 ops.zero(d.fp.grad)                              # the NEXT iteration, issued here: nothing writes them before its
                 ops.zero(d.head_grads)                           # gradient-penalty pass, which waits for this stream's weights)
                 d.zero_pass_buffers()                            # and the per-channel sums of its three passes
+                d.seed_heads(d.coef_critic)                      # its backward seeds: functions of the new head weights only
         self.pack_side.run(after_step)
         self._ce_ready = True                                    # until the text changes (load_batch / next outer step)
 
@@ -902,7 +951,7 @@ class Stage1Engine:
         # and every optimizer_step joins this stream
         self.side.run(lambda: (ops.zero(self.g.fp.grad), ops.zero(self.ca.fp.grad)))
         for it in range(N_CRITIC):
-            nxt = (z[it + 1], eps_ca[it + 1]) if it + 1 < N_CRITIC else None
+            nxt = (z[it + 1], eps_ca[it + 1], eps_gp[it + 1]) if it + 1 < N_CRITIC else None
             self.critic_iteration(z[it], eps_ca[it], eps_gp[it], next_noise=nxt, grads_zeroed=it > 0,
                                   zero_after=it + 1 < N_CRITIC)
         self.generator_step(grads_zeroed=True)

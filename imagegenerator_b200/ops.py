@@ -88,6 +88,8 @@ _SIGS = {
     "sg_conv_fprop_bstats": [_P] * 8 + [_I] * 13 + [_P],
     "sg_conv_dgrad_bstats": [_P] * 8 + [_I] * 13 + [_P],
     "sg_conv_bstats_in_epilogue": [_I] * 13,
+    "sg_conv_dgrad_tc_bstats_masked": [_P] * 8 + [_I] * 13 + [_P],
+    "sg_conv_dgrad_tc_bstats_masked_supported": [_I] * 11,
     "sg_conv_fprop_tc_bstats": [_P] * 8 + [_I] * 12 + [_P],
     "sg_conv_dgrad_tc_bstats": [_P] * 8 + [_I] * 12 + [_P],
     "sg_ca_forward": [_P] * 14 + [_I] * 7 + [_P],
@@ -396,6 +398,20 @@ class CudaOps:
         self._ck(self.lib.sg_conv_dgrad_bstats(_ptr(dy), _ptr(pd), _ptr(dx), _ptr(ybn), _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
                                                groups, act, *d, k, s, p, self._dt_of(dy), self._st()))
         return True
+
+    def conv_dgrad_masked_supported(self, dy, dx, k, s, p, groups):
+        d = self._conv_dims(dx, dy)
+        return dy.dtype == torch.bfloat16 and bool(self.lib.sg_conv_dgrad_tc_bstats_masked_supported(*d, k, s, p, groups))
+
+    def conv_dgrad_masked(self, dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, k, s, p, zeroed=False):
+        """dx = conv_dgrad(dy) * act'(gamma * xhat(ybn) + beta) -- the data-gradient conv and the activation backward of the layer
+        below in one kernel; sums[groups][C][0] = column sums of dx (with the identity table and ybn = that layer's stored
+        activation: its bias gradient)."""
+        self._c(dy, pd, dx, ybn, mr, gamma, beta, sums)
+        d = self._conv_dims(dx, dy)
+        assert sums.dtype == torch.float64 and tuple(sums.shape) == (groups, d[3], 2) and ybn.shape == dx.shape
+        self._ck(self.lib.sg_conv_dgrad_tc_bstats_masked(_ptr(dy), _ptr(pd), _ptr(dx), _ptr(ybn), _ptr(mr), _ptr(gamma), _ptr(beta),
+                                                         _ptr(sums), groups, act, *d, k, s, p, 1 if zeroed else 0, self._st()))
 
     def conv_bstats_opt(self, direction, src, pw, dst, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
         """The engines' entry: ``direction`` 'f' / 'd'.  Shapes whose statistics come out of the tcgen05 epilogue run

@@ -220,6 +220,15 @@ int sg_conv_fprop_bstats(const void* x, const void* pf, void* y, const void* ybn
 int sg_conv_dgrad_bstats(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
                          const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho, int Wo, int Co,
                          int k, int s, int p, int dtype, void* stream);
+/* sg_conv_dgrad_bstats with the MASKED gradient stored: dx = dz = conv result * act'(gamma * xhat + beta), sums[.][.][0] = the
+ * column sums of dz -- data-gradient conv + activation backward in one kernel (tcgen05 epilogue; bf16, Ci % 32 == 0, Ci <= 256).
+ * With the identity table (mean 0, rstd 1, gamma 1, beta 0) and ybn = the stored activation of a conv + bias + activation layer
+ * (discrminator_1.py:17-18) it replaces the activation-backward pass over the critics' largest activation, and sums[.][.][0] is
+ * that layer's bias gradient.  sums_zeroed: the caller zeroed sums (sg_zero_multi). */
+int sg_conv_dgrad_tc_bstats_masked(const void* dy, const void* pd, void* dx, const void* ybn, const float* mr, const float* gamma,
+                                   const float* beta, double* sums, int groups, int act, int N, int H, int W, int Ci, int Ho,
+                                   int Wo, int Co, int k, int s, int p, int sums_zeroed, void* stream);
+int sg_conv_dgrad_tc_bstats_masked_supported(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups);
 /* 1: the two calls above reduce the statistics in the tcgen05 epilogue for this shape; 0: they run the conv followed by
  * sg_bn_bwd_reduce_y (a caller that follows up with sg_bn_bwd -- reduce + apply in one launch -- then prefers the plain conv) */
 int sg_conv_bstats_in_epilogue(int dgrad, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int k, int s, int p, int groups,

@@ -167,6 +167,24 @@ class EmuOps:
         self.conv_dgrad(dy, pd, None, dx, k, s, p)
         self.bn_bwd_reduce(dx, None, ybn, mr, sums, groups, act, gamma=gamma, beta=beta)
 
+    def conv_dgrad_masked_supported(self, dy, dx, k, s, p, groups):
+        return True
+
+    def conv_dgrad_masked(self, dy, pd, dx, ybn, mr, gamma, beta, sums, groups, act, k, s, p, zeroed=False):
+        """dx = conv_dgrad(dy) * act'(gamma * xhat(ybn) + beta); sums (+)= (sum dx, sum dx * xhat) per (group, channel) of the stored dx."""
+        da = torch.zeros_like(dx)
+        self.conv_dgrad(dy, pd, None, da, k, s, p)
+        C = dx.shape[-1]
+        sign = self._act_sign_from_y(ybn, mr, gamma, beta, groups)
+        dx.copy_((da.to(torch.float64) * _mask(sign, act).to(torch.float64)).to(dx.dtype))
+        dz = dx.to(torch.float64).reshape(groups, -1, C)
+        xh = self._xhat(ybn, mr, groups).to(torch.float64)
+        part = torch.stack([dz.sum(1), (dz * xh).sum(1)], dim=-1)
+        if zeroed:
+            sums.add_(part)
+        else:
+            sums.copy_(part)
+
     def conv_bstats_opt(self, direction, src, pw, dst, ybn, mr, gamma, beta, sums, groups, act, k, s, p):
         """CudaOps.conv_bstats_opt: True = the statistics were reduced with the conv (always, here)."""
         (self.conv_fprop_bstats if direction == "f" else self.conv_dgrad_bstats)(src, pw, dst, ybn, mr, gamma, beta, sums,

@@ -830,6 +830,37 @@ def test_conv_dgrad_bstats(mode, case, act):
     _check_bstats(ca[2], ca[3], mr, gamma, beta, ca[7], G, act)
 
 
+MASKED_CASES = [(24, 8, 256, 512, 4, 2, 1, 3), (48, 16, 128, 256, 4, 2, 1, 3), (6, 32, 64, 128, 4, 2, 1, 3), (6, 32, 64, 128, 4, 2, 1, 1),
+                (4, 16, 96, 192, 4, 2, 1, 1)]
+
+
+@pytest.mark.parametrize("case", MASKED_CASES)
+@pytest.mark.parametrize("act", [ACT_RELU, ACT_LRELU])
+@pytest.mark.parametrize("identity", [False, True])
+def test_conv_dgrad_masked(case, act, identity):
+    """sg_conv_dgrad_tc_bstats_masked: the data-gradient conv stores dz = conv * act'(gamma * xhat + beta) itself (conv + activation
+    backward in one kernel) == conv_dgrad, then the mask; sums = (sum dz, sum dz * xhat) of the stored dz.  ``identity``: the table
+    the engines use for the first critic layer (mean 0, rstd 1, gamma 1, beta 0, ybn = the stored activation)."""
+    N, H, Ci, Co, k, s, p, G = case
+    Ho = (H + 2 * p - k) // s + 1
+    dy, w = rnd(N, Ho, Ho, Co), rnd(Co, Ci, k, k, scale=(Co * k * k / (s * s)) ** -0.5)
+    pd = w.permute(1, 2, 3, 0).contiguous()
+    mr, gamma, beta, ybn = _bstats_inputs(G, Ci, (N, H, H, Ci), act, 6)
+    if identity:
+        mr = torch.stack([torch.zeros(G, Ci), torch.ones(G, Ci)], dim=-1)
+        gamma, beta = torch.ones(Ci), torch.zeros(Ci)
+        u = rnd(N, H, H, Ci, seed=8)
+        ybn = torch.sign(u) * (0.25 + u.abs())
+    ops = _ops("bf16")
+    assert ops.conv_dgrad_masked_supported(torch.empty(N, Ho, Ho, Co, dtype=torch.bfloat16), torch.empty(N, H, H, Ci), k, s, p, G)
+    for zeroed in (False, True):
+        sums = torch.zeros(G, Ci, 2, dtype=torch.float64) if zeroed else torch.full((G, Ci, 2), 7.0, dtype=torch.float64)
+        ea, ca = run_pair("bf16", "conv_dgrad_masked", [T(dy), T(pd), T(torch.zeros(N, H, H, Ci)), T(ybn), F(mr), F(gamma), F(beta),
+                                                        D(sums), G, act, k, s, p], [2], dict(zeroed=zeroed))
+        # the statistics are those of the STORED masked gradient: re-mask it with slope 1 (none) to re-use the checker
+        _check_bstats(ca[2], ca[3], mr, gamma, beta, ca[7], G, ACT_NONE)
+
+
 def _wtc_ok(case):
     from imagegenerator_b200.ops import CudaOps
     N, H, Ci, Co, k, s, p = case
