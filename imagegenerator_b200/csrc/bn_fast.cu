@@ -771,9 +771,11 @@ bn_bwd_fused8_kernel(const T* __restrict__ da, const T* __restrict__ a_out, cons
 
 int g_bn_fused = 0;                // option "bn_fused": 1 = one launch where the tensor fits; default 0 (two kernels): inside the
                                    // captured steps the one-launch kernel cannot share an SM with the side stream's wgrad CTAs
-                                   // (190 KB of shared memory each) and measured 1-2 % slower per step, see DESIGN.md section 5
+                                   // (190 KB of shared memory each) and measured 1-2 % slower per step, see DESIGN.md section 5;
+                                   // the engines switch it on around the gradient penalty's first-order pass (side streams idle)
 int g_bn_fused_keep_pct = 50;      // fuse when at least this share of a range can be parked in shared memory
 int g_bn_fused_steal_ns = 30000;   // option "bn_fused_steal_ns": taking over is a safety net, not a schedule (4 us: Stage-I 5.25 -> 5.64 ms)
+int g_gp_bn_fused = 1;             // option "gp_bn_fused": the penalty's second-order BatchNorm pair as one launch
 int g_bn_fused_dbg = 0;            // option "bn_fused_dbg": the first / last CTA leave globaltimer stamps in the work words
 
 // plan + launch; returns -1 (nothing launched) when the tensor is too large to profit -- the caller then runs reduce + apply
@@ -999,6 +1001,242 @@ gp_bn_apply8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* 
         st8(gy_out + i * 8, gy);
     }
 }
+
+// ---- gradient-penalty double backward through a train-mode BN as ONE launch (gp_bn_reduce8 + rendezvous + gp_bn_apply8): the
+// same scheme as bn_bwd_fused8_kernel -- range b of the vector stream is parked in CTA b's shared memory by bulk async copies
+// (FOUR tensors: v, da, a, y), phase 1 reduces (sum v, sum v*xhat, sum v*dz), a rendezvous that counts finished ranges, phase 2
+// writes w and gy out of the parked copy; CTA 0 adds the penalty's gamma gradient.  This pass runs while the side streams are
+// idle (the second-order chain of a critic update), where the one-launch scheme pays.  tsums must be ZERO on entry.
+template <typename T>
+__global__ void __launch_bounds__(FNT, 1)
+gp_bn_fused8_kernel(const T* __restrict__ v, const T* __restrict__ da, const T* __restrict__ a_out, const T* __restrict__ y,
+                    const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ sums,
+                    double* __restrict__ tsums, T* __restrict__ w_out, T* __restrict__ gy_out, float* __restrict__ dgamma,
+                    FusedPlan k, float slope, float n, unsigned* __restrict__ work) {
+    SG_PDL_SYNC();
+    extern __shared__ __align__(128) unsigned char fsm[];
+    typedef Raw8<T> R8;
+    R8* p_v = reinterpret_cast<R8*>(fsm);
+    R8* p_da = p_v + k.keep;
+    R8* p_a = p_da + k.keep;
+    R8* p_y = p_a + k.keep;
+    const int C = k.CV * 8, tid = (int)threadIdx.x;
+    float* cst = reinterpret_cast<float*>(p_y + k.keep);                      // [8][C]: mean, r, A, B1, B2, E, K1, K2 (phase 1: rows 0-1)
+    float* sacc = cst + 8 * C;                                                // [C][3] segment sums
+    __shared__ float part[16][FNT + 1];
+    __shared__ uint64_t bars[FPIECES];
+    __shared__ int s_cmd;
+    __shared__ int mine[FMAXR];
+    const int c0 = (tid % k.CV) * 8;
+    const bool worker = tid < k.active;
+    constexpr int U = Unroll<T>::U > 2 ? 2 : Unroll<T>::U;                    // four tensors per vector: two vectors in flight
+    const int piece = k.active * U;
+    int nmine = 0;
+    bool has0 = false;                               // this CTA reduced range 0: it adds the gamma gradient (exactly one CTA does)
+    auto range_of = [&](int r, int64_t& begin, int& len) {
+        begin = (int64_t)r * k.range;
+        const int64_t left = k.gvec - begin;
+        len = (int)(left < k.range ? left : k.range);
+    };
+    if (tid == 0) {
+        for (int p = 0; p < FPIECES; ++p)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fsaddr(&bars[p])), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int b = (int)blockIdx.x;
+        const bool own = atomicExch(&work[4 + b], 1u) == 0u;
+        s_cmd = own ? b : -1;
+        if (own) {
+            int len;
+            int64_t begin;
+            range_of(b, begin, len);
+            const int left = len < k.keep ? len : k.keep;
+            for (int p = 0, v0 = 0; v0 < left; ++p, v0 += piece) {
+                const int cnt = left - v0 < piece ? left - v0 : piece;
+                const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(R8);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fsaddr(&bars[p])), "r"(bytes * 4u) : "memory");
+                fbulk_g2s(p_v + v0, v + (begin + v0) * 8, bytes, &bars[p]);
+                fbulk_g2s(p_da + v0, da + (begin + v0) * 8, bytes, &bars[p]);
+                fbulk_g2s(p_a + v0, a_out + (begin + v0) * 8, bytes, &bars[p]);
+                fbulk_g2s(p_y + v0, y + (begin + v0) * 8, bytes, &bars[p]);
+            }
+        }
+    }
+    for (int c = tid; c < C; c += FNT) {             // (mean, rstd): one coalesced pass under the copies in flight
+        const float2 q = *reinterpret_cast<const float2*>(mr + (int64_t)c * 2);
+        cst[c] = q.x; cst[C + c] = q.y;
+    }
+    __syncthreads();
+    int cmd = s_cmd;
+
+    // ---------------- phase 1: (sum v, sum v*xhat, sum v*dz) of this CTA's range (and of ranges nobody else started)
+    while (cmd >= 0) {
+        const int r = cmd;
+        const int keep = nmine == 0 ? k.keep : 0;
+        if (tid == 0) mine[nmine] = r;
+        ++nmine;
+        if (r == 0) has0 = true;
+        int len;
+        int64_t begin;
+        range_of(r, begin, len);
+        for (int t = tid; t < C * 3; t += FNT) sacc[t] = 0.f;
+        float t1[8], t2[8], t3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { t1[j] = 0.f; t2[j] = 0.f; t3[j] = 0.f; }
+        int vi = tid;
+        if (worker && vi < len) {
+            int waited = 0;
+            float m[8], rs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { m[j] = cst[c0 + j]; rs[j] = cst[C + c0 + j]; }
+            auto landed = [&](int vv) {
+                const int need = vv / piece;
+                while (waited <= need) { fbar_wait(&bars[waited], 0); ++waited; }
+            };
+            for (; vi < len; vi += k.active) {
+                R8 rv, rd, ra, ry;
+                const int64_t at = (begin + vi) * 8;
+                if (vi < keep) { landed(vi); rv = p_v[vi]; rd = p_da[vi]; ra = p_a[vi]; ry = p_y[vi]; }
+                else { rv = ldraw(v + at); rd = ldraw(da + at); ra = ldraw(a_out + at); ry = ldraw(y + at); }
+                const V8 vv = unpack(rv), d = unpack(rd), a = unpack(ra), yy = unpack(ry);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dz = a.v[j] > 0.f ? d.v[j] : slope * d.v[j];
+                    t1[j] += vv.v[j];
+                    t2[j] += vv.v[j] * ((yy.v[j] - m[j]) * rs[j]);
+                    t3[j] += vv.v[j] * dz;
+                }
+            }
+        }
+        // cross-thread sums in two rounds through the 16-row scratch: (t1, t2), then t3
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { part[2 * j][tid] = t1[j]; part[2 * j + 1][tid] = t2[j]; }
+        __syncthreads();
+        for (int o = tid; o < C * 2; o += FNT) {
+            const int c = o >> 1, row = 2 * (c & 7) + (o & 1);
+            float acc = 0.f;
+            for (int t = c >> 3; t < k.active; t += k.CV) acc += part[row][t];
+            sacc[c * 3 + (o & 1)] = acc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[j][tid] = t3[j];
+        __syncthreads();
+        for (int c = tid; c < C; c += FNT) {
+            float acc = 0.f;
+            for (int t = c >> 3; t < k.active; t += k.CV) acc += part[c & 7][t];
+            sacc[c * 3 + 2] = acc;
+        }
+        __syncthreads();
+        for (int t = tid; t < C * 3; t += FNT) atomicAdd(tsums + t, (double)sacc[t]);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&work[1], 1u);
+            s_cmd = fused_wait_or_steal(work, k.nranges, k.steal_ns);        // ---------------- the rendezvous
+        }
+        __syncthreads();
+        cmd = s_cmd;
+    }
+
+    // ---------------- phase 2: w = u*act', gy = d/dy of the penalty term (gp_bn_apply8)
+    if (nmine > 0) {
+        for (int c = tid; c < C; c += FNT) {
+            const float mean = cst[c], r = cst[C + c];
+            const double S1d = __ldcg(sums + c * 2), S2d = __ldcg(sums + c * 2 + 1);
+            const double T1d = __ldcg(tsums + c * 3), T2d = __ldcg(tsums + c * 3 + 1), T3d = __ldcg(tsums + c * 3 + 2);
+            if (has0 && dgamma != nullptr)
+                dgamma[c] += (float)((double)r / (double)n * ((double)n * T3d - S1d * T1d - S2d * T2d));
+            const float S1 = (float)S1d, S2 = (float)S2d, T1 = (float)T1d, T2 = (float)T2d, T3 = (float)T3d;
+            const float al = gamma[c] * r / n;
+            const float P = al * (n * T3 - S1 * T1 - S2 * T2);
+            const float sG = -al * (S2 * T1 + S1 * T2), sGx = -2.f * al * S2 * T2;
+            (void)mean;
+            cst[2 * C + c] = al * n; cst[3 * C + c] = al * T1; cst[4 * C + c] = al * T2;
+            cst[5 * C + c] = al * S2; cst[6 * C + c] = sG / n; cst[7 * C + c] = sGx / n + P / n;
+        }
+        __syncthreads();
+        for (int q = 0; q < nmine; ++q) {
+            const int r = mine[q];
+            const int keep = q == 0 ? k.keep : 0;
+            int len;
+            int64_t begin;
+            range_of(r, begin, len);
+            if (!worker) continue;
+            for (int vi = tid; vi < len; vi += k.active) {
+                R8 rv, rd, ra, ry;
+                const int64_t at = (begin + vi) * 8;
+                if (vi < keep) { rv = p_v[vi]; rd = p_da[vi]; ra = p_a[vi]; ry = p_y[vi]; }
+                else { rv = ldraw(v + at); rd = ldraw(da + at); ra = ldraw(a_out + at); ry = ldraw(y + at); }
+                const V8 vv = unpack(rv), d = unpack(rd), a = unpack(ra), yy = unpack(ry);
+                V8 w, gy;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    const float mk = a.v[j] > 0.f ? 1.f : slope;
+                    const float dz = d.v[j] * mk;
+                    const float rr = cst[C + c];
+                    const float xh = (yy.v[j] - cst[c]) * rr;
+                    const float u = cst[2 * C + c] * vv.v[j] - cst[3 * C + c] - xh * cst[4 * C + c];
+                    w.v[j] = u * mk;
+                    const float G = -(cst[5 * C + c] * vv.v[j] + cst[4 * C + c] * dz);
+                    gy.v[j] = rr * (G - cst[6 * C + c] - xh * cst[7 * C + c]);
+                }
+                st8(w_out + at, w);
+                st8(gy_out + at, gy);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&work[2], 1u) == gridDim.x - 1) {
+            for (int r = 0; r < k.nranges; ++r) work[4 + r] = 0u;
+            work[1] = 0u; work[2] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// plan + launch; -1 = nothing launched (too large to profit / option off): the caller runs gp_bn_reduce8 + gp_bn_apply8
+template <typename T>
+int gp_bn_fused8(const void* v, const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
+                 const double* sums, double* tsums, void* w_out, void* gy_out, float* dgamma, int64_t rows, int C, int act,
+                 unsigned* work, cudaStream_t st) {
+    if (!g_gp_bn_fused || work == nullptr) return -1;
+    FusedPlan k;
+    k.CV = C / 8;
+    if (k.CV > FNT || C > 1024) return -1;
+    k.gvec = rows * k.CV;
+    k.active = FNT / k.CV * k.CV;
+    const int64_t per = (k.gvec + SG_NUM_SMS - 1) / SG_NUM_SMS;
+    const int64_t range = (per + k.active - 1) / k.active * k.active;
+    if (range > (1 << 24)) return -1;
+    k.range = (int)range;
+    k.rpg = (int)((k.gvec + range - 1) / range);
+    k.nranges = k.rpg;
+    if (k.nranges > FMAXR) return -1;
+    const size_t acc_bytes = (size_t)C * 11 * sizeof(float);      // constants [8][C] + segment sums [C][3]
+    const size_t vb = sizeof(Raw8<T>) * 4;
+    const size_t budget = 188 * 1024;
+    if (acc_bytes + vb * k.active > budget) return -1;
+    int64_t keep = (int64_t)((budget - acc_bytes) / vb) / k.active * k.active;
+    if (keep > range) keep = range;
+    if (keep * 100 < range * g_bn_fused_keep_pct) return -1;
+    constexpr int U = Unroll<T>::U > 2 ? 2 : Unroll<T>::U;
+    if ((keep + (int64_t)k.active * U - 1) / ((int64_t)k.active * U) > FPIECES) return -1;
+    k.keep = (int)keep;
+    k.dbg = 0;
+    k.steal_ns = g_bn_fused_steal_ns;
+    const size_t smem = acc_bytes + vb * (size_t)keep;
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(gp_bn_fused8_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget); set = true; }
+    launch_pdl(gp_bn_fused8_kernel<T>, dim3(k.nranges), dim3(FNT), smem, st, (const T*)v, (const T*)da, (const T*)a_out, (const T*)y, mr,
+               gamma, sums, tsums, (T*)w_out, (T*)gy_out, dgamma, k, act_slope(act), (float)rows, work);
+    g_launches.fetch_add(1);
+    return check_launch("gp_bn_fused8");
+}
+template int gp_bn_fused8<float>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, double*, void*, void*, float*, int64_t, int, int, unsigned*, cudaStream_t);
+template int gp_bn_fused8<bf16>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, double*, void*, void*, float*, int64_t, int, int, unsigned*, cudaStream_t);
 
 template <typename T>
 int gp_bn_reduce8(const void* v, const void* da, const void* a_out, const void* y, const float* mr, double* tsums, int64_t rows,

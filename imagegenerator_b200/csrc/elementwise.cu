@@ -856,6 +856,7 @@ template <typename T> int bn_bwd_fused8(const void*, const void*, const void*, c
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
 template <typename T> int gp_bn_reduce8(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
 template <typename T> int act_bwd8_colsum(const void*, const void*, void*, float*, int64_t, int, int, cudaStream_t);
+template <typename T> int gp_bn_fused8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, double*, void*, void*, float*, int64_t, int, int, unsigned*, cudaStream_t);
 template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
 
 // Several small buffers zeroed by ONE kernel node (the per-channel sums of every BatchNorm layer of a backward pass): a
@@ -1301,6 +1302,25 @@ int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void*
     gp_bn_dgamma_kernel<<<(C + 127) / 128, 128, 0, SG_STREAM(stream)>>>(mr, sums, tsums, dgamma, (double)rows, C);
     SG_LAUNCHED("gp_bn_dgamma");
     return 0;
+}
+
+// sg_gp_bn_reduce + sg_gp_bn_apply behind ONE call; one launch (gp_bn_fused8_kernel) where the four tensors fit the SMs' shared
+// memory.  tsums_zeroed: the caller zeroed tsums (sg_zero_multi).  work: 1 KB of zeroed words owned by the call site, NULL = two kernels.
+int sg_gp_bn(const void* v, const void* da, const void* a_out, const void* y, const float* mr, const float* gamma, const double* sums,
+             double* tsums, void* w_out, void* gy_out, float* dgamma, int64_t rows, int C, int act, int dtype, int tsums_zeroed,
+             void* work, void* stream) {
+    if (C % 8 == 0 && C <= 1024 && act != SG_ACT_TANH && work != nullptr) {
+        cudaStream_t st = SG_STREAM(stream);
+        if (!tsums_zeroed && !sg::g_dbg_skip_memset) cudaMemsetAsync(tsums, 0, (size_t)C * 3 * sizeof(double), st);
+        int e = -1;
+        SG_DISPATCH_T(dtype, e = gp_bn_fused8<T>(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, rows, C, act,
+                                                 (unsigned*)work, st));
+        if (e >= 0) return e;
+        tsums_zeroed = 1;                               // (zeroed just above)
+    }
+    int e = gp_bn_reduce_impl(v, da, a_out, y, mr, tsums, rows, C, act, dtype, stream, !tsums_zeroed);
+    if (e) return e;
+    return sg_gp_bn_apply(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, rows, C, act, dtype, stream);
 }
 
 int sg_outer(const float* coef, const float* vec, void* out, int N, int M, int out_dtype, void* stream) {

@@ -105,6 +105,9 @@ def _capture_stream(device, default_priority=0):
 # Correct (tests/test_kernels_gpu.py::test_conv_dgrad_masked, step parity green) and SLOWER: Stage-I 4.86 -> 5.34 ms -- the
 # statistics epilogue of conv_tcp_kernel costs more on this 512-deep reduction than the 21 us pass it removes.
 MASKED_DGRAD = os.environ.get("SG_MASKED_DGRAD") == "1"
+# The one-launch BatchNorm backward (option bn_fused) for the gradient penalty's first-order pass only (one image group: 2-8 MB
+# tensors, and the side streams are nearly idle there): Stage-I 4.89 -> 4.85 ms.  SG_BN_FUSED_GP1=0 switches it off.
+BN_FUSED_GP1 = os.environ.get("SG_BN_FUSED_GP1", "1") == "1"
 
 
 def _side_run(side, fn):
@@ -645,6 +648,9 @@ class CriticRT:
         if not seeded:
             ops.head_bwd_data(self.coef_one, self.A, self.gda[nl])
         reduced, masked0 = False, False
+        fuse = BN_FUSED_GP1 and hasattr(ops, "set_option")
+        if fuse:
+            ops.set_option("bn_fused", 1)      # (launch-time switch: baked into the captured graph)
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr = self.mr[l][2:3]
@@ -664,6 +670,8 @@ class CriticRT:
                 masked0 = True
             else:
                 ops.conv_dgrad(self.gdy[l], L.pd, None, self.gda[l], L.k, L.s, L.p)
+        if fuse:
+            ops.set_option("bn_fused", 0)
         if not masked0:
             ops.act_bwd(self.gda[1], i2(self.a[1]), self.gdy[0], ACT_LRELU)
         self.input_grad(self.gdy[0], self.g)
@@ -694,10 +702,8 @@ class CriticRT:
             if not defer_wgrad:
                 _side_run(side, lambda l=l, L=L: ops.conv_wgrad(self.w[l], self.gdy[l], L.conv.weight.grad, L.k, L.s, L.p))
             mr = self.mr[l][2:3]
-            ops.gp_bn_reduce(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, self.tsums[l], ACT_LRELU,
-                             zeroed=True)
-            ops.gp_bn_apply(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data,
-                            self.gsums[l], self.tsums[l], self.w[l + 1], self.gy[l], bn.weight.grad, ACT_LRELU)
+            ops.gp_bn(self.v[l], self.gda[l + 1], i2(self.a[l + 1]), i2(self.y[l]), mr, bn.weight.data, self.gsums[l],
+                      self.tsums[l], self.w[l + 1], self.gy[l], bn.weight.grad, ACT_LRELU, zeroed=True)
         # dA is read by the head / text parameter gradients only (side stream): keep the reduction off the data-gradient chain
         _side_run(side, lambda: ops.head_bwd_reduce(self.coef_one, self.w[nl], self.dA))
 

@@ -73,6 +73,7 @@ _SIGS = {
     "sg_gp_bn_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "sg_gp_bn_reduce_acc": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "sg_gp_bn_apply": [_P] * 11 + [_L, _I, _I, _I, _P],
+    "sg_gp_bn": [_P] * 11 + [_L, _I, _I, _I, _I, _P, _P],
     "sg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "sg_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "sg_head_prepare": [_P] * 7 + [_I, _I, _I, _P],
@@ -524,9 +525,7 @@ class CudaOps:
             self.bn_bwd_apply(da, a_out, y, mr, gamma, sums, dy, groups, act, inject=inject, inject_group=inject_group, beta=beta)
             return
         self._c(da, a_out, y, mr, gamma, sums, dy, inject, beta)
-        slot = self._bn_slot.setdefault(sums.data_ptr(), len(self._bn_slot))
-        assert slot < 1024, "bn_bwd: out of work slots"
-        work = self._bn_work.data_ptr() + 1024 * slot
+        work = self._work_slot(sums.data_ptr())
         self._ck(self.lib.sg_bn_bwd(_ptr(da), None if beta is not None else _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma),
                                     _ptr(beta), _ptr(sums), _ptr(inject), inject_group, _ptr(dy), y.numel() // (C * groups), C,
                                     groups, act, self._dt_of(y), 1 if zeroed else 0, work, self._st()))
@@ -565,6 +564,19 @@ class CudaOps:
         fn = self.lib.sg_gp_bn_reduce_acc if zeroed else self.lib.sg_gp_bn_reduce
         self._ck(fn(_ptr(v), _ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(tsums),
                                           y.numel() // C, C, act, self._dt_of(y), self._st()))
+
+    def _work_slot(self, key):
+        slot = self._bn_slot.setdefault(key, len(self._bn_slot))
+        assert slot < 1024, "out of one-launch work slots"
+        return self._bn_work.data_ptr() + 1024 * slot
+
+    def gp_bn(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act, zeroed=False):
+        """gp_bn_reduce + gp_bn_apply as one call (one launch where the four tensors fit the SMs' shared memory)."""
+        self._c(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma)
+        C = y.shape[-1]
+        self._ck(self.lib.sg_gp_bn(_ptr(v), _ptr(da), _ptr(a_out), _ptr(y), _ptr(mr), _ptr(gamma), _ptr(sums), _ptr(tsums),
+                                   _ptr(w_out), _ptr(gy_out), _ptr(dgamma), y.numel() // C, C, act, self._dt_of(y),
+                                   1 if zeroed else 0, self._work_slot(tsums.data_ptr()), self._st()))
 
     def gp_bn_apply(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act):
         self._c(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma)

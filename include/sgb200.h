@@ -67,7 +67,9 @@ int64_t sg_launch_count(void);
  *    results (1 contiguous boxes, 2 no stores, 4 no MMAs; default 0 -- never set it outside tools/).
  *  BatchNorm backward (bn_fast.cu):  "bn_fused" = 1/0 sg_bn_bwd as ONE launch where (da, y) fit the SMs' shared memory (default 0:
  *    faster alone -- 19 vs 26 us on the 12.6 MB critic layer -- but its 190 KB CTAs cannot share an SM with the side stream's
- *    wgrad CTAs and the captured steps measured 1-2 % slower); "bn_fused_keep_pct" = least share of a range that must fit
+ *    wgrad CTAs and the captured steps measured 1-2 % slower; the engines switch it on for the gradient penalty's first-order
+ *    pass, where the side streams are nearly idle); "gp_bn_fused" = 1/0 the same scheme for sg_gp_bn (default 1: the penalty's
+ *    second-order pass runs alone on the GPU, Stage-I 4.82 -> 4.76 ms); "bn_fused_keep_pct" = least share of a range that must fit
  *    (default 50); "bn_fused_steal_ns" = patience at the rendezvous before resident CTAs take over ranges of CTAs that have not
  *    started (default 30000); "bn_fused_dbg" = globaltimer stamps of the first / last CTA in the work words.
  *  "dbg" = verbose launch decisions on stderr. */
@@ -327,6 +329,12 @@ int sg_gp_bn_reduce(const void* v, const void* da, const void* a_out, const void
 /* the same, ADDING to tsums which the caller zeroed (sg_zero_multi at the start of the pass): no memset node in the chain */
 int sg_gp_bn_reduce_acc(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
                         double* tsums, int64_t rows, int C, int act, int dtype, void* stream);
+/* sg_gp_bn_reduce + sg_gp_bn_apply behind ONE call: one launch where (v, da, a_out, y) fit the SMs' shared memory (the scheme of
+ * sg_bn_bwd's one-launch kernel; this pass runs while the side streams are idle, where it pays), else the two kernels.
+ * tsums_zeroed: the caller zeroed tsums; work: 1 KB of zeroed words owned by the call site (NULL = two kernels); option "gp_bn_fused". */
+int sg_gp_bn(const void* v, const void* da, const void* a_out, const void* y, const float* mr, const float* gamma,
+             const double* sums, double* tsums, void* w_out, void* gy_out, float* dgamma, int64_t rows, int C, int act,
+             int dtype, int tsums_zeroed, void* work, void* stream);
 int sg_gp_bn_apply(const void* v, const void* da, const void* a_out, const void* y, const float* mr,
                    const float* gamma, const double* sums, const double* tsums, void* w_out, void* gy_out,
                    float* dgamma, int64_t rows, int C, int act, int dtype, void* stream);

@@ -329,6 +329,10 @@ class EmuOps:
         else:
             tsums.copy_(part)
 
+    def gp_bn(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act, zeroed=False):
+        self.gp_bn_reduce(v, da, a_out, y, mr, tsums, act, zeroed=zeroed)
+        self.gp_bn_apply(v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act)
+
     def gp_bn_apply(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act):
         """Backward of dy = BNbwd(dz; y, gamma) given v = dL/d dy  (SURVEY section 7):
              w_out  = mask * a (N v - T1 - xhat T2)                      (dL/d da: feeds the next conv_fprop)

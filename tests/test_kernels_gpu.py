@@ -516,6 +516,49 @@ def test_act_bwd_with_column_sums(mode, C, rows, act):
     assert torch.allclose(cs.double().cpu(), want_cs, rtol=1e-3, atol=1e-3 * want_cs.abs().max().item())
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("C,rows,launches", [(128, 128 * 256, 1), (256, 128 * 64, 1), (512, 2048, 1), (64, 50000, 1), (24, 3000, 1),
+                                             (128, 400000, 2)])
+def test_gp_bn_one_call(mode, C, rows, launches):
+    """sg_gp_bn: the penalty's second-order pass through a train-mode BN as one call (ONE launch where the four tensors fit the
+    SMs' shared memory: sums, rendezvous, apply) == gp_bn_reduce, then gp_bn_apply; repeated on the same call site."""
+    ops, emu = _ops(mode), EmuOps(torch.float64)
+    sd = ops.act_dtype
+    q = lambda t: t.to(sd)
+    y, da, v = rnd(rows, C, seed=1), rnd(rows, C, seed=2), rnd(rows, C, seed=3)
+    mr = torch.stack([rnd(1, C, scale=0.1), torch.rand(1, C) + 0.5], dim=-1)
+    gamma, beta = torch.rand(C) + 0.5, rnd(C, scale=0.3)
+    a = torch.zeros(rows, C, dtype=torch.float64)
+    emu.bn_act(q(y).double(), mr.double(), gamma.double(), beta.double(), a, 1, ACT_LRELU)
+    a = q(a.float())
+    sums = torch.zeros(1, C, 2, dtype=torch.float64)
+    emu.bn_bwd_reduce(q(da).double(), a.double(), q(y).double(), mr.double(), sums, 1, ACT_LRELU)
+    dg0 = rnd(C, seed=4)
+    want_t, want_w, want_gy, want_dg = (torch.zeros(C, 3, dtype=torch.float64), torch.zeros(rows, C, dtype=torch.float64),
+                                        torch.zeros(rows, C, dtype=torch.float64), dg0.double().clone())
+    emu.gp_bn(q(v).double(), q(da).double(), a.double(), q(y).double(), mr.double(), gamma.double(), sums, want_t, want_w, want_gy,
+              want_dg, ACT_LRELU)
+    c = lambda t: t.cuda().contiguous()
+    cv, cda, ca, cy, cmr, cg, cs = c(q(v)), c(q(da)), c(a), c(q(y)), c(mr.float()), c(gamma), c(sums)
+    ts = torch.full((C, 3), 7.0, dtype=torch.float64, device="cuda")
+    w, gy = torch.zeros(rows, C, dtype=sd, device="cuda"), torch.zeros(rows, C, dtype=sd, device="cuda")
+    tol = dict(rtol=3e-2, atol=2e-3) if mode == "bf16" else dict(rtol=1e-3, atol=1e-4)
+    for rep in range(3):
+        dg = dg0.cuda()
+        if rep == 2:
+            ts.zero_()
+        n0 = ops.launch_count()
+        ops.gp_bn(cv, cda, ca, cy, cmr, cg, cs, ts, w, gy, dg, ACT_LRELU, zeroed=rep == 2)
+        torch.cuda.synchronize()
+        seen = ops.launch_count() - n0
+        assert seen == launches if mode == "bf16" else seen in (1, 2, 3), seen     # (two kernels + dgamma's fallback = 2 or 3)
+        assert torch.allclose(ts.cpu(), want_t, rtol=1e-3, atol=1e-3 * want_t.abs().max().item())
+        for got, want in ((w, want_w), (gy, want_gy)):
+            assert torch.allclose(got.double().cpu(), want, rtol=tol["rtol"], atol=tol["atol"] * want.abs().max().item()), \
+                (got.double().cpu() - want).abs().max().item()
+        assert torch.allclose(dg.double().cpu(), want_dg, rtol=1e-3, atol=1e-3 * want_dg.abs().max().item())
+
+
 def test_zero_multi_and_accumulating_reductions():
     """sg_zero_multi zeroes up to 32 buffers in one launch (more: one launch per 32); the *_acc reductions / sg_bn_bwd with
     sums_zeroed ADD to what the caller zeroed -- twice the call, twice the sums."""
