@@ -1263,6 +1263,130 @@ template int gp_bn_reduce8<bf16>(const void*, const void*, const void*, const vo
 template int gp_bn_apply8<float>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
 template int gp_bn_apply8<bf16>(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
 
+// ---- bn_act8_kernel<T, true> (finalize + apply) with the CTA's range brought in by bulk async copies: the whole range (<= 188 KB
+// per SM) is in flight at once while the CTA turns the raw sums of its image group into (mean, rstd*gamma, beta) -- the
+// register-staged kernel keeps ~40 KB per SM in flight and is latency-bound on the 6-25 MB tensors of the Stage-I critic forward
+// (16 / 12 / 12 us for 50 / 25 / 13 MB of traffic).  One CTA per SM (it does not share an SM with other kernels' CTAs, so the
+// engines use it only where the side streams are idle: option "bn_act_bulk").  Ranges never cross an image group.
+template <typename T>
+__global__ void __launch_bounds__(FNT, 1)
+bn_act8_bulk_kernel(const T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out,
+                    FusedPlan k, int act, BnFinalize f) {
+    SG_PDL_SYNC();
+    extern __shared__ __align__(128) unsigned char fsm[];
+    typedef Raw8<T> R8;
+    R8* p_y = reinterpret_cast<R8*>(fsm);
+    const int C = k.CV * 8, tid = (int)threadIdx.x;
+    float* fin = reinterpret_cast<float*>(p_y + k.keep);                      // [C][3]: mean, rstd*gamma, beta of this CTA's group
+    __shared__ uint64_t bars[FPIECES];
+    constexpr int U = Unroll<T>::U;
+    const int piece = k.active * U;
+    const int r = (int)blockIdx.x;
+    const int g = r / k.rpg;
+    const int64_t off = (int64_t)(r % k.rpg) * k.range;
+    const int64_t begin = (int64_t)g * k.gvec + off;
+    const int len = (int)(k.gvec - off < k.range ? k.gvec - off : k.range);
+    if (tid == 0) {
+        for (int p = 0; p < FPIECES; ++p)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fsaddr(&bars[p])), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int p = 0, v0 = 0; v0 < len; ++p, v0 += piece) {
+            const int cnt = len - v0 < piece ? len - v0 : piece;
+            const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(R8);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fsaddr(&bars[p])), "r"(bytes) : "memory");
+            fbulk_g2s(p_y + v0, y + (begin + v0) * 8, bytes, &bars[p]);
+        }
+    }
+    for (int c = tid; c < C; c += FNT) {
+        const int64_t gc = (int64_t)g * C + c;
+        double mean, var;
+        bn_mean_var(f.stats, gc, f.count, mean, var);
+        const float mf = (float)mean, rf = (float)(1.0 / sqrt(var + (double)f.eps));
+        fin[c * 3] = mf; fin[c * 3 + 1] = rf * gamma[c]; fin[c * 3 + 2] = beta[c];
+    }
+    if (blockIdx.x == 0) {                           // what the separate sg_bn_finalize launch did
+        for (int idx = tid; idx < f.G * C; idx += FNT) {
+            double mean, var;
+            bn_mean_var(f.stats, idx, f.count, mean, var);
+            f.mr[(int64_t)idx * 2] = (float)mean; f.mr[(int64_t)idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)f.eps));
+        }
+        if (f.update_running) {
+            if (tid == 0 && f.nbt) *f.nbt += f.dup_first + f.G - 1;
+            for (int c = tid; c < C; c += FNT) {
+                float m_run = f.rm[c], v_run = f.rv[c];
+                for (int gg = 0; gg < f.G; ++gg) {
+                    double mean, var;
+                    bn_mean_var(f.stats, (int64_t)gg * C + c, f.count, mean, var);
+                    const float unb = (float)(var * f.count / (f.count > 1 ? f.count - 1 : 1));
+                    const int reps = gg == 0 ? f.dup_first : 1;
+                    for (int q = 0; q < reps; ++q) {
+                        m_run = (1.f - f.momentum) * m_run + f.momentum * (float)mean;
+                        v_run = (1.f - f.momentum) * v_run + f.momentum * unb;
+                    }
+                }
+                f.rm[c] = m_run; f.rv[c] = v_run;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid >= k.active) return;
+    const int c0 = (tid % k.CV) * 8;
+    float m[8], rg[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = fin[(c0 + j) * 3]; rg[j] = fin[(c0 + j) * 3 + 1]; b[j] = fin[(c0 + j) * 3 + 2]; }
+    const float slope = act == SG_ACT_RELU ? 0.f : (act == SG_ACT_LRELU ? 0.1f : 1.f);
+    int waited = 0;
+    for (int v = tid; v < len; v += k.active) {
+        const int need = v / piece;
+        while (waited <= need) { fbar_wait(&bars[waited], 0); ++waited; }
+        const V8 yy = unpack(p_y[v]);
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = (yy.v[j] - m[j]) * rg[j] + b[j];
+            o.v[j] = t > 0.f ? t : slope * t;
+        }
+        st8(out + (begin + v) * 8, o);
+    }
+}
+int g_bn_act_bulk = 0;             // option "bn_act_bulk": set by the engines around passes that run alone on the GPU
+
+// -1 = nothing launched (option off, residual / tanh, or the tensor does not fit the SMs' shared memory)
+template <typename T>
+int bn_finalize_act8_bulk(const double* stats, double count, float* mr, float* rm, float* rv, long long* nbt, int dup_first,
+                          int update_running, float momentum, float eps, const void* y, const float* gamma, const float* beta,
+                          void* out, int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {
+    if (!g_bn_act_bulk || act == SG_ACT_TANH) return -1;
+    constexpr int U = Unroll<T>::U;
+    FusedPlan k;
+    k.CV = C / 8;
+    if (k.CV > FNT || groups > SG_NUM_SMS) return -1;
+    k.gvec = rows_per_group * k.CV;
+    k.active = FNT / k.CV * k.CV;
+    const int slots = SG_NUM_SMS / groups;
+    const int64_t per = (k.gvec + slots - 1) / slots;
+    const int64_t range = (per + k.active - 1) / k.active * k.active;
+    k.range = (int)range;
+    k.rpg = (int)((k.gvec + range - 1) / range);
+    k.nranges = k.rpg * groups;
+    const size_t fin_bytes = (size_t)C * 3 * sizeof(float);
+    const size_t budget = 200 * 1024;
+    if (range > (1 << 24) || fin_bytes + sizeof(Raw8<T>) * (size_t)range > budget) return -1;
+    if ((range + (int64_t)k.active * U - 1) / ((int64_t)k.active * U) > FPIECES) return -1;
+    if (k.gvec * groups * (int64_t)sizeof(Raw8<T>) < (2 << 20)) return -1;          // tiny tensors: the plain kernel is as fast
+    k.keep = (int)range;
+    k.dbg = 0; k.steal_ns = 0;
+    BnFinalize f{stats, count, mr, rm, rv, nbt, dup_first, update_running, groups, momentum, eps};
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(bn_act8_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget); set = true; }
+    launch_pdl(bn_act8_bulk_kernel<T>, dim3(k.nranges), dim3(FNT), fin_bytes + sizeof(Raw8<T>) * (size_t)range, st, (const T*)y, gamma,
+               beta, (T*)out, k, act, f);
+    g_launches.fetch_add(1);
+    return check_launch("bn_finalize_act8_bulk");
+}
+template int bn_finalize_act8_bulk<float>(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, void*, int64_t, int, int, int, cudaStream_t);
+template int bn_finalize_act8_bulk<bf16>(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, void*, int64_t, int, int, int, cudaStream_t);
+
 template <typename T>
 int bn_act8(const void* y, const float* mr, const float* gamma, const float* beta, const void* res, void* out,
             int64_t rows_per_group, int C, int groups, int act, cudaStream_t st) {

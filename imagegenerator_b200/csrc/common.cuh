@@ -128,6 +128,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 extern int g_use_pdl;
 extern int g_dbg_skip_memset;
+extern int g_bn_act_bulk;
 extern int g_bn_fused, g_bn_fused_keep_pct, g_bn_fused_dbg, g_bn_fused_steal_ns, g_gp_bn_fused;      // bn_fast.cu: BatchNorm backward as one launch
 
 template <typename... KArgs, typename... Args>

@@ -1946,6 +1946,7 @@ int sg_set_option(const char* name, int value) {
     if (name && !strcmp(name, "bn_fused")) { g_bn_fused = value; return 0; }
     if (name && !strcmp(name, "bn_fused_keep_pct")) { g_bn_fused_keep_pct = value; return 0; }
     if (name && !strcmp(name, "dbg_skip_memset")) { g_dbg_skip_memset = value; return 0; }
+    if (name && !strcmp(name, "bn_act_bulk")) { g_bn_act_bulk = value; return 0; }
     if (name && !strcmp(name, "gp_bn_fused")) { g_gp_bn_fused = value; return 0; }
     if (name && !strcmp(name, "bn_fused_dbg")) { g_bn_fused_dbg = value; return 0; }
     if (name && !strcmp(name, "bn_fused_steal_ns")) { g_bn_fused_steal_ns = value; return 0; }

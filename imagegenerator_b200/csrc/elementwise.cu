@@ -856,6 +856,7 @@ template <typename T> int bn_bwd_fused8(const void*, const void*, const void*, c
 template <typename T> int act_bwd8(const void*, const void*, void*, int64_t, int, cudaStream_t);
 template <typename T> int gp_bn_reduce8(const void*, const void*, const void*, const void*, const float*, double*, int64_t, int, int, cudaStream_t);
 template <typename T> int act_bwd8_colsum(const void*, const void*, void*, float*, int64_t, int, int, cudaStream_t);
+template <typename T> int bn_finalize_act8_bulk(const double*, double, float*, float*, float*, long long*, int, int, float, float, const void*, const float*, const float*, void*, int64_t, int, int, int, cudaStream_t);
 template <typename T> int gp_bn_fused8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, double*, void*, void*, float*, int64_t, int, int, unsigned*, cudaStream_t);
 template <typename T> int gp_bn_apply8(const void*, const void*, const void*, const void*, const float*, const float*, const double*, const double*, void*, void*, int64_t, int, int, float*, cudaStream_t);
 
@@ -1116,7 +1117,12 @@ int sg_bn_finalize_act(const double* stats, int64_t count, float* mr, float* run
                        const float* beta, const void* residual, void* out, int64_t rows_per_group, int C, int groups, int act,
                        int dtype, void* stream) {
     if (C % 8 == 0 && C <= 2048) {
-        int e = 0;
+        int e = -1;
+        if (residual == nullptr)                                      // option "bn_act_bulk": the range-parked variant
+            SG_DISPATCH_T(dtype, e = bn_finalize_act8_bulk<T>(stats, (double)count, mr, running_mean, running_var, (long long*)nbt,
+                                                              dup_first, update_running, momentum, eps, y, gamma, beta, out,
+                                                              rows_per_group, C, groups, act, SG_STREAM(stream)));
+        if (e >= 0) return e;
         SG_DISPATCH_T(dtype, e = bn_finalize_act8<T>(stats, (double)count, mr, running_mean, running_var, (long long*)nbt,
                                                      dup_first, update_running, momentum, eps, y, gamma, beta, residual, out,
                                                      rows_per_group, C, groups, act, SG_STREAM(stream)));

@@ -108,6 +108,10 @@ MASKED_DGRAD = os.environ.get("SG_MASKED_DGRAD") == "1"
 # The one-launch BatchNorm backward (option bn_fused) for the gradient penalty's first-order pass only (one image group: 2-8 MB
 # tensors, and the side streams are nearly idle there): Stage-I 4.89 -> 4.85 ms.  SG_BN_FUSED_GP1=0 switches it off.
 BN_FUSED_GP1 = os.environ.get("SG_BN_FUSED_GP1", "1") == "1"
+# A/B switch (default off, measured neutral: Stage-I 4.757 -> 4.753 ms): the critic forward's BatchNorm finalize + apply with
+# bulk-copy staged ranges (option bn_act_bulk, one CTA per SM) -- y was just written by the conv and is L2-resident, so the deeper
+# prefetch buys nothing there.
+BN_ACT_BULK = os.environ.get("SG_BN_ACT_BULK", "0") == "1"
 
 
 def _side_run(side, fn):
@@ -499,6 +503,9 @@ class CriticRT:
             before_weights()
         self._wait_pack(0)
         ops.conv_fprop(gv(self.a[0]), L0.pf, L0.conv.bias.data, gv(self.a[1]), L0.k, L0.s, L0.p, act=ACT_LRELU)
+        bulk = BN_ACT_BULK and training and hasattr(ops, "set_option")
+        if bulk:
+            ops.set_option("bn_act_bulk", 1)     # launch-time switch: the critic forward runs (nearly) alone on the GPU
         for l in range(1, self.nl):
             L, bn = self.layers[l], self.layers[l].bn
             self._wait_pack(l)
@@ -515,6 +522,8 @@ class CriticRT:
                 for g in range(ng):
                     ops.bn_eval_mr(bn.running_mean, bn.running_var, mr[g:g + 1])
                 ops.bn_act(y, mr, bn.weight.data, bn.bias.data, gv(self.a[l + 1]), ng, ACT_LRELU)
+        if bulk:
+            ops.set_option("bn_act_bulk", 0)
         # head: compressed text, then the collapsed affine score
         self._wait_pack(-1)
         if per_layer:
@@ -572,6 +581,9 @@ class CriticRT:
         bn_items = []             # (sums, gamma.grad, beta.grad) of every BatchNorm layer: ONE launch at the end
         reduced = False           # sums[l] already came out of the epilogue of the conv that produced da[l + 1]
         L0, dy0, masked0 = self.layers[0], gv(self.dy[0]), False
+        fuse = BN_FUSED_GP1 and not param_grads and hasattr(ops, "set_option")     # no wgrad stream next to this pass
+        if fuse:
+            ops.set_option("bn_fused", 1)
         for l in range(nl - 1, 0, -1):
             L, bn = self.layers[l], self.layers[l].bn
             mr, sums = self.mr[l][g0:g0 + ng], self.sums[l][g0:g0 + ng]
@@ -605,6 +617,8 @@ class CriticRT:
                 masked0 = True
             else:
                 ops.conv_dgrad(dy, L.pd, None, gv(self.da[l]), L.k, L.s, L.p)
+        if fuse:
+            ops.set_option("bn_fused", 0)
         if not masked0:
             # the first conv's bias gradient (column sums of dy0) rides in the activation-backward pass
             ops.act_bwd(gv(self.da[1]), gv(self.a[1]), dy0, ACT_LRELU, colsum=L0.conv.bias.grad if param_grads else None)

@@ -69,7 +69,8 @@ int64_t sg_launch_count(void);
  *    faster alone -- 19 vs 26 us on the 12.6 MB critic layer -- but its 190 KB CTAs cannot share an SM with the side stream's
  *    wgrad CTAs and the captured steps measured 1-2 % slower; the engines switch it on for the gradient penalty's first-order
  *    pass, where the side streams are nearly idle); "gp_bn_fused" = 1/0 the same scheme for sg_gp_bn (default 1: the penalty's
- *    second-order pass runs alone on the GPU, Stage-I 4.82 -> 4.76 ms); "bn_fused_keep_pct" = least share of a range that must fit
+ *    second-order pass runs alone on the GPU, Stage-I 4.82 -> 4.76 ms); "bn_act_bulk" = 1/0 sg_bn_finalize_act with bulk-copy
+ *    staged ranges, one CTA per SM (default 0: measured neutral in the step, its input is L2-resident); "bn_fused_keep_pct" = least share of a range that must fit
  *    (default 50); "bn_fused_steal_ns" = patience at the rendezvous before resident CTAs take over ranges of CTAs that have not
  *    started (default 30000); "bn_fused_dbg" = globaltimer stamps of the first / last CTA in the work words.
  *  "dbg" = verbose launch decisions on stderr. */

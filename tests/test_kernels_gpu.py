@@ -559,6 +559,34 @@ def test_gp_bn_one_call(mode, C, rows, launches):
         assert torch.allclose(dg.double().cpu(), want_dg, rtol=1e-3, atol=1e-3 * want_dg.abs().max().item())
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("C,rows,G,act", [(128, 32768, 3, ACT_LRELU), (256, 8192, 3, ACT_LRELU), (512, 2048, 3, ACT_LRELU),
+                                          (64, 100000, 1, ACT_RELU), (24, 131072, 1, ACT_NONE)])
+def test_bn_finalize_act_bulk(mode, C, rows, G, act):
+    """Option bn_act_bulk: finalize + apply with every CTA's range brought in by bulk async copies (one CTA per SM) == the
+    register-staged kernel's contract (mr, running statistics, batch counter, output)."""
+    g = torch.Generator().manual_seed(C + rows)
+    y = torch.randn(G * rows, C, generator=g) * 2 + 0.5
+    emu = EmuOps(torch.float64)
+    sd = torch.bfloat16 if mode == "bf16" else torch.float32
+    stats = torch.zeros(G, C, 2, dtype=torch.float64)
+    emu.col_stats(y.to(sd).double().reshape(G, rows, 1, C), stats, G)
+    rm, rv, nbt = rnd(C) * 0.1, torch.rand(C) + 0.5, torch.tensor(3)
+    gamma, beta = rnd(C) * 0.5 + 1, rnd(C) * 0.2
+    y4 = y.reshape(G * rows, 1, 1, C)
+    ops = _ops(mode)
+    try:
+        ops.set_option("bn_act_bulk", 1)
+        n0 = ops.launch_count()
+        ea, ca = run_pair(mode, "bn_finalize_act", [D(stats), rows, F(torch.zeros(G, C, 2)), F(rm), F(rv), I64(nbt), 2, T(y4),
+                                                    F(gamma), F(beta), T(torch.zeros_like(y4)), act], [2, 3, 4, 10],
+                          tol=dict(rtol=1e-4, atol=1e-5) if mode == "fp32" else None)
+        assert int(ca[5]) == 3 + G + 1
+        assert ops.launch_count() - n0 == 1
+    finally:
+        ops.set_option("bn_act_bulk", 0)
+
+
 def test_zero_multi_and_accumulating_reductions():
     """sg_zero_multi zeroes up to 32 buffers in one launch (more: one launch per 32); the *_acc reductions / sg_bn_bwd with
     sums_zeroed ADD to what the caller zeroed -- twice the call, twice the sums."""
