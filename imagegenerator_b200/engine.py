@@ -108,6 +108,11 @@ MASKED_DGRAD = os.environ.get("SG_MASKED_DGRAD") == "1"
 # The one-launch BatchNorm backward (option bn_fused) for the gradient penalty's first-order pass only (one image group: 2-8 MB
 # tensors, and the side streams are nearly idle there): Stage-I 4.89 -> 4.85 ms.  SG_BN_FUSED_GP1=0 switches it off.
 BN_FUSED_GP1 = os.environ.get("SG_BN_FUSED_GP1", "1") == "1"
+# Where the next critic iteration's fake batch is produced on the generator's side stream: 0 = right after the critic forward
+# (next to the penalty's first-order pass), 1 = after that pass (next to the second-order pass), 2 = next to the plain backward.
+# Measured (Stage-I ms per step, two runs each): 4.766 / 4.783 / 4.741 -- the two penalty passes run one-launch BatchNorm kernels
+# that want every SM, the plain backward's kernels share SMs with other streams anyway.
+GEN_AHEAD_AT = int(os.environ.get("SG_GEN_AHEAD_AT", "2"))
 # A/B switch (default off, measured neutral: Stage-I 4.757 -> 4.753 ms): the critic forward's BatchNorm finalize + apply with
 # bulk-copy staged ranges (option bn_act_bulk, one CTA per SM) -- y was just written by the conv and is L2-resident, so the deeper
 # prefetch buys nothing there.
@@ -910,22 +915,29 @@ class Stage1Engine:
         self._interp_ready = False
         d.forward(0, 3, dup_first=2, training=True, with_mismatched=True,    # :125-132 + utils.py:13
                   before_weights=self.pack_side.join, ce_ready=self._ce_ready, patches_on=self.side)
-        if next_noise is not None and self.gen_side.enabled:
-            self.side.join()                 # the patch matrix of this iteration's images is built: group 1 may be overwritten
-            if len(next_noise) > 2:          # + the next interpolation (its eps given): one launch less at the head of the chain
-                self.gen_side.run(lambda: (self._generate(*next_noise[:2]), interp(next_noise[2])))
-                self._interp_ready = True
-            else:
-                self.gen_side.run(lambda: self._generate(*next_noise))
-            self._fake_ready = True
+        def generate_ahead():
+            if next_noise is not None and self.gen_side.enabled:
+                self.side.join()             # the patch matrix of this iteration's images is built: group 1 may be overwritten
+                if len(next_noise) > 2:      # + the next interpolation (its eps given): one launch less at the head of the chain
+                    self.gen_side.run(lambda: (self._generate(*next_noise[:2]), interp(next_noise[2])))
+                    self._interp_ready = True
+                else:
+                    self.gen_side.run(lambda: self._generate(*next_noise))
+                self._fake_ready = True
+        if GEN_AHEAD_AT == 0:
+            generate_ahead()
         if not grads_zeroed:
             ops.zero(d.fp.grad)                                  # :146
             ops.zero(d.head_grads)                               # dA, dBv
             d.zero_pass_buffers()
         d.gp_first_order(prezeroed=True, seeded=grads_zeroed)    # utils.py:15-24
+        if GEN_AHEAD_AT == 1:
+            generate_ahead()
         # :140-144; only the host reads the loss values: off the main stream
         self.side.run(lambda: ops.critic_loss(d.score[0], d.score[1], d.score[2], d.sq, LAMBDA_GP, self.losses[0:2]))
         d.gp_second_order(2.0 * LAMBDA_GP / B, side=self.side, defer_wgrad=True, prezeroed=True)
+        if GEN_AHEAD_AT == 2:
+            generate_ahead()
         # head/text gradients on the side stream, in order: dA is complete once the plain backward's head term is added
         self.side.run(lambda: (ops.head_bwd_reduce(d.coef_critic, d.a[d.nl], d.dA),
                                d.text_backward(d.coef_text, 2 * B, 0.0, True, None)))
