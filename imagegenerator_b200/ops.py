@@ -566,8 +566,13 @@ class CudaOps:
                                           y.numel() // C, C, act, self._dt_of(y), self._st()))
 
     def _work_slot(self, key):
-        slot = self._bn_slot.setdefault(key, len(self._bn_slot))
-        assert slot < 1024, "out of one-launch work slots"
+        """1 KB of work words for the call site ``key`` (the address of its sums buffer); None once the pool is used up --
+        the library then runs the two-kernel path for that site."""
+        slot = self._bn_slot.get(key)
+        if slot is None:
+            if len(self._bn_slot) >= 1024:
+                return None
+            slot = self._bn_slot[key] = len(self._bn_slot)
         return self._bn_work.data_ptr() + 1024 * slot
 
     def gp_bn(self, v, da, a_out, y, mr, gamma, sums, tsums, w_out, gy_out, dgamma, act, zeroed=False):
