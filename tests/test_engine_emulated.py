@@ -88,6 +88,35 @@ def test_stage1_outer_step_fp64_matches_oracle(B):
                 assert int(sd[k]) == int(v), (key, k, int(sd[k]), int(v))
 
 
+def test_outer_step_off_chain_bookkeeping_equals_the_plain_iterations():
+    """outer_step runs the critic updates with the main-chain shortcuts -- gradient buffers, the per-channel sums of all three
+    passes and the head seeds prepared behind the PREVIOUS optimizer step (grads_zeroed / zero_after / prezeroed / seeded), the
+    generator's gradients cleared at the start of the step -- and the reductions ADD to what was zeroed.  Two outer steps must
+    leave exactly the parameters that plain critic_iteration / generator_step calls (each zeroing for itself) leave."""
+    B, dt = 4, torch.float64
+    params = []
+    for shortcut in (False, True):
+        ca, d1, g1 = build_modules()
+        eng = Stage1Engine(ca, d1, g1, B, ops=EmuOps(dt))
+        for step in range(2):
+            b = O.synthetic_batch(B, 1, step, dtype=dt)
+            eng.load_batch(b["real"], b["tem"], b["tem"][b["perm"]])
+            if shortcut:
+                eng.outer_step(b["z"], b["eps_ca"], b["eps_gp"])
+            else:
+                eng._ce_ready = False
+                for it in range(5):
+                    eng.critic_iteration(b["z"][it], b["eps_ca"][it], b["eps_gp"][it])
+                eng.generator_step()
+        params.append({f"{n}.{k}": v.detach().clone() for n, m in (("ca", ca), ("d1", d1), ("g1", g1))
+                       for k, v in m.state_dict().items()})
+    for k, v in params[0].items():
+        if v.is_floating_point():
+            assert torch.allclose(params[1][k].double(), v.double(), rtol=1e-7, atol=1e-9), k   # fp32 masters: a few ulps from the order of += terms
+        else:
+            assert int(params[1][k]) == int(v), k
+
+
 def test_compressed_text_is_recomputed_for_every_new_batch():
     """The critic's compressed text is computed on the weight re-pack stream after each critic update and reused by the
     following forwards -- but never across batches: the first critic forward of every outer step (and of every
