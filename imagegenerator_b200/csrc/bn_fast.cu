@@ -8,6 +8,14 @@
 // registers and the inner loop is loads -> a few FMAs per element -> store, no integer division.  A CTA's
 // range touches at most two image groups, so per-channel reductions are combined in shared memory and
 // leave the CTA as one fp64 atomic per (group, channel, quantity).
+//
+// Second family (round 2, final session): RANGE-PARKING kernels -- bn_bwd_fused8_kernel (BatchNorm backward in one launch),
+// gp_bn_fused8_kernel (the gradient penalty's second-order pair in one launch), bn_act8_bulk_kernel (forward apply).  One CTA per
+// SM owns a range that never crosses an image group, brings ALL of it into shared memory with cp.async.bulk + mbarrier
+// transaction counts (the whole range in flight at once), and -- for the two backward kernels -- meets the other CTAs at a
+// rendezvous that counts finished ranges, so that nothing depends on the grid being co-resident.  They take every SM they run
+// on: the engines use them in the passes that have the GPU to themselves and keep the register-staged kernels (which share SMs
+// with the weight-gradient stream) everywhere else.
 #include <cstdlib>
 #include "common.cuh"
 
